@@ -1,0 +1,125 @@
+/* zkgpu.h — C ABI of the B200-native STARK proving path for zk_evm's evm_arithmetization.
+ *
+ * The reference (Rust) has no FFI layer; its seams are generic call sites into plonky2/starky.  Each entry point
+ * below names the reference interface it replaces (paths relative to /root/reference):
+ *
+ *   S1  PolynomialBatch::from_values / from_coeffs      evm_arithmetization/src/prover.rs:100-107, verifier.rs:69-76
+ *   S2  starky get_ctl_data                             evm_arithmetization/src/prover.rs:134-144
+ *   S3  starky prove_with_commitment (prove_single_table)  evm_arithmetization/src/prover.rs:301-341
+ *   top prove_with_traces / prove_with_commitments      evm_arithmetization/src/prover.rs:72-194, 211-293
+ *
+ * Conventions: every function returns ZKGPU_OK (0) or a negative zkgpu_status; nothing throws or aborts across
+ * the boundary; zkgpu_last_error() gives the message of the last failure on the calling thread.  Field elements
+ * are canonical Goldilocks u64 (< 2^64 - 2^32 + 1), little-endian in memory.  Columns are column-major: one
+ * contiguous array of n u64 per column, exactly `PolynomialValues<F>::values`.  Input pointers are borrowed for
+ * the duration of the call and may be pageable or pinned host memory (or device memory when the
+ * ZKGPU_MEM_DEVICE flag is given); outputs are written to caller-owned buffers or returned as opaque handles
+ * released with the matching *_free.  One zkgpu_ctx per (host thread, device); calls on a ctx are serialised
+ * on its stream.  The library fails loudly (ZKGPU_ERR_CUDA) when no CUDA device is usable: there is no CPU path.
+ */
+#ifndef ZKGPU_H
+#define ZKGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    ZKGPU_OK = 0,
+    ZKGPU_ERR_INVALID = -1,   /* bad argument (non power-of-two length, null pointer, cap too high ...) */
+    ZKGPU_ERR_CUDA = -2,      /* CUDA runtime failure or no device */
+    ZKGPU_ERR_ABORTED = -3,   /* abort flag observed (prover.rs:346-354 check_abort_signal) */
+    ZKGPU_ERR_PROOF = -4,     /* proving failed (e.g. zeta in the trace subgroup, PoW search exhausted) */
+    ZKGPU_ERR_NOMEM = -5
+} zkgpu_status;
+
+enum { ZKGPU_MEM_HOST = 0, ZKGPU_MEM_DEVICE = 1 };
+
+/* Table ids == `Table` enum, evm_arithmetization/src/all_stark.rs:74-86 */
+enum {
+    ZKGPU_TABLE_ARITHMETIC = 0, ZKGPU_TABLE_BYTE_PACKING = 1, ZKGPU_TABLE_CPU = 2, ZKGPU_TABLE_KECCAK = 3,
+    ZKGPU_TABLE_KECCAK_SPONGE = 4, ZKGPU_TABLE_LOGIC = 5, ZKGPU_TABLE_MEMORY = 6, ZKGPU_TABLE_MEM_BEFORE = 7,
+    ZKGPU_TABLE_MEM_AFTER = 8, ZKGPU_NUM_TABLES = 9
+};
+
+typedef struct zkgpu_ctx zkgpu_ctx;
+typedef struct zkgpu_batch zkgpu_batch;     /* device-resident PolynomialBatch */
+typedef struct zkgpu_ctl zkgpu_ctl;         /* device-resident CtlData of one table */
+typedef struct zkgpu_proof zkgpu_proof;     /* host-resident StarkProofWithMetadata */
+
+/* StarkConfig (starky config.rs) + FriConfig; standard_fast_config = {100, 2, 1, 4, 16, 4, 5, 84},
+ * TEST_STARK_CONFIG (evm_arithmetization/src/testing_utils.rs:41-52) = {1, 1, 1, 4, 1, 4, 5, 1}. */
+typedef struct {
+    uint32_t security_bits;
+    uint32_t num_challenges;
+    uint32_t rate_bits;
+    uint32_t cap_height;
+    uint32_t proof_of_work_bits;
+    uint32_t fri_arity_bits;        /* FriReductionStrategy::ConstantArityBits(arity_bits, final_poly_bits) */
+    uint32_t fri_final_poly_bits;
+    uint32_t num_query_rounds;
+} zkgpu_stark_config;
+
+/* Constants of the assembled EVM kernel that appear in CpuStark constraints (KERNEL.global_labels[...]:
+ * cpu/control_flow.rs:38-44, cpu/syscalls_exceptions.rs:68-73).  They come from assembling the 160 asm files,
+ * which the Rust host does; the device evaluator takes them as parameters. */
+typedef struct {
+    uint64_t halt_final;
+    uint64_t init;              /* label "init" (segment start), NOT "main" */
+    uint64_t syscall_jumptable;
+    uint64_t exception_jumptable;
+} zkgpu_kernel_labels;
+
+const char* zkgpu_last_error(void);
+const char* zkgpu_version(void);
+
+int zkgpu_ctx_create(int device, zkgpu_ctx** out);
+void zkgpu_ctx_destroy(zkgpu_ctx* ctx);
+int zkgpu_ctx_sync(zkgpu_ctx* ctx);
+/* device-memory high-water mark and kernel-launch counter (bench.py's gpu_launches) */
+int zkgpu_ctx_stats(zkgpu_ctx* ctx, uint64_t* kernel_launches, uint64_t* bytes_in_use, uint64_t* bytes_peak);
+
+/* ---- S1: commitments ------------------------------------------------------------------------------------- */
+/* PolynomialBatch::from_values(values, rate_bits, blinding=false, cap_height): per column ifft -> zero-pad ->
+ * coset FFT (shift = MULTIPLICATIVE_GROUP_GENERATOR) -> bit-reversed rows -> Poseidon Merkle tree.
+ * `cols` = ncols pointers to n elements each (mem_kind says where they live).  keep_values != 0 keeps the raw
+ * trace values on the device (needed later by zkgpu_ctl_data / lookup columns). */
+int zkgpu_commit_values(zkgpu_ctx* ctx, const uint64_t* const* cols, size_t ncols, size_t n, uint32_t rate_bits,
+                        uint32_t cap_height, int mem_kind, int keep_values, zkgpu_batch** out);
+/* same, but the columns are one contiguous column-major block: col c at base + c*n */
+int zkgpu_commit_values_contig(zkgpu_ctx* ctx, const uint64_t* base, size_t ncols, size_t n, uint32_t rate_bits,
+                               uint32_t cap_height, int mem_kind, int keep_values, zkgpu_batch** out);
+/* PolynomialBatch::from_coeffs */
+int zkgpu_commit_coeffs(zkgpu_ctx* ctx, const uint64_t* const* coeff_cols, size_t ncols, size_t n,
+                        uint32_t rate_bits, uint32_t cap_height, int mem_kind, zkgpu_batch** out);
+void zkgpu_batch_free(zkgpu_batch* b);
+int zkgpu_batch_dims(const zkgpu_batch* b, size_t* ncols, size_t* n, uint32_t* rate_bits, uint32_t* cap_height);
+/* merkle_tree.cap: (1 << cap_height) * 4 u64 */
+int zkgpu_batch_cap(const zkgpu_batch* b, uint64_t* out_cap);
+/* Fill the fields of a host PolynomialBatch (all buffers caller-owned, any may be NULL to skip):
+ *   coeffs  ncols*n               polynomials[c].coeffs, column-major
+ *   leaves  (n<<rate_bits)*ncols  merkle_tree.leaves, row-major, row j = LDE row bitrev(j)
+ *   digests 2*((n<<rate_bits) - (1<<cap_height))*4   merkle_tree.digests in plonky2's recursive layout */
+int zkgpu_batch_export(const zkgpu_batch* b, uint64_t* coeffs, uint64_t* leaves, uint64_t* digests);
+
+/* ---- fine-grained entry points (per-kernel parity tests, ncu) --------------------------------------------- */
+/* In-place batched NTT over `ncols` host columns of length n (column-major contiguous).
+ * inverse=0: out[i] = sum_j in[j] w^(ij) (plonky2 fft, natural order in and out); inverse=1: ifft.
+ * coset_shift != 0 and != 1: coset_fft(c, s) / coset_ifft(v, s). */
+int zkgpu_ntt(zkgpu_ctx* ctx, uint64_t* data, size_t ncols, size_t n, int inverse, uint64_t coset_shift);
+/* Poseidon permutation on `count` 12-element states (host memory) */
+int zkgpu_poseidon_permute(zkgpu_ctx* ctx, uint64_t* states, size_t count);
+/* hash_or_noop over `nrows` rows of `width` elements given column-major (col c at data + c*nrows): out nrows*4 */
+int zkgpu_poseidon_hash_rows(zkgpu_ctx* ctx, const uint64_t* data_colmajor, size_t nrows, size_t width, uint64_t* out);
+/* device-resident micro-benchmarks used by bench.py for the roofline numbers: run the kernel `iters` times on
+ * synthetic device data and return the average milliseconds per launch measured with CUDA events on the ctx stream */
+int zkgpu_bench_ntt(zkgpu_ctx* ctx, size_t ncols, size_t n, int iters, float* ms_per_iter, uint64_t* launches);
+int zkgpu_bench_leaf_hash(zkgpu_ctx* ctx, size_t ncols, size_t nrows, int iters, float* ms_per_iter);
+int zkgpu_bench_merkle_levels(zkgpu_ctx* ctx, size_t nleaves, int iters, float* ms_per_iter);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKGPU_H */

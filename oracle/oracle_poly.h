@@ -1,0 +1,67 @@
+// ORACLE (test infrastructure, NOT product code) — PolynomialBatch restatement.
+// Follows plonky2 1.0.0 fri/oracle.rs `PolynomialBatch::{from_values, from_coeffs, get_lde_values}` as called from
+// /root/reference/evm_arithmetization/src/prover.rs:100-107 and verifier.rs:69-76.
+// Parity unpinned (no golden vectors in the reference); validated by the restated verifier.
+#pragma once
+#include "oracle_core.h"
+
+namespace orc {
+
+struct PolyBatch {
+    size_t ncols = 0, n = 0;
+    unsigned log_n = 0, rate_bits = 0;
+    std::vector<uint64_t> coeffs;   // column-major: coeffs[c*n + j]
+    MerkleTree tree;                // leaves[j] = LDE row bitrev(j), row-major
+
+    size_t lde_size() const { return n << rate_bits; }
+    const uint64_t* col(size_t c) const { return &coeffs[c * n]; }
+    // get_lde_values(i, step): row of the LDE at natural index i*step
+    const uint64_t* lde_row(size_t i, size_t step = 1) const { return tree.leaf(bitrev(i * step, log_n + rate_bits)); }
+
+    // from_coeffs: lde_values[c][i] = poly_c(g * w_{k+r}^i); leaves = transpose, bit-reversed rows; MerkleTree::new
+    void from_coeffs(std::vector<uint64_t>&& cf, size_t ncols_, size_t n_, unsigned rate_bits_, unsigned cap_height) {
+        coeffs = std::move(cf); ncols = ncols_; n = n_; rate_bits = rate_bits_;
+        log_n = 0; while (((size_t)1 << log_n) < n) log_n++;
+        if (((size_t)1 << log_n) != n) throw std::runtime_error("n must be a power of two");
+        size_t N = lde_size(); unsigned log_N = log_n + rate_bits;
+        std::vector<uint64_t> rows(N * ncols);
+        #pragma omp parallel
+        {
+            std::vector<uint64_t> tmp(N);
+            #pragma omp for schedule(dynamic, 1)
+            for (size_t c = 0; c < ncols; c++) {
+                memcpy(tmp.data(), &coeffs[c * n], n * 8);
+                memset(tmp.data() + n, 0, (N - n) * 8);
+                coset_fft_inplace(tmp.data(), log_N, GL_GENERATOR);
+                for (size_t j = 0; j < N; j++) rows[j * ncols + c] = tmp[bitrev(j, log_N)];
+            }
+        }
+        tree.build(std::move(rows), N, ncols, cap_height);
+    }
+    // from_values: per-column ifft first
+    void from_values(const uint64_t* const* cols, size_t ncols_, size_t n_, unsigned rate_bits_, unsigned cap_height) {
+        std::vector<uint64_t> cf(ncols_ * n_);
+        unsigned lg = 0; while (((size_t)1 << lg) < n_) lg++;
+        #pragma omp parallel for schedule(dynamic, 1)
+        for (size_t c = 0; c < ncols_; c++) {
+            memcpy(&cf[c * n_], cols[c], n_ * 8);
+            ifft_inplace(&cf[c * n_], lg);
+        }
+        from_coeffs(std::move(cf), ncols_, n_, rate_bits_, cap_height);
+    }
+    // evaluate column c at an extension point (PolynomialCoeffs::to_extension().eval)
+    Ext eval_ext(size_t c, Ext z) const {
+        Ext acc;
+        const uint64_t* p = col(c);
+        for (size_t j = n; j-- > 0;) acc = acc * z + Ext(p[j], 0);
+        return acc;
+    }
+    uint64_t eval_base(size_t c, uint64_t z) const {
+        uint64_t acc = 0;
+        const uint64_t* p = col(c);
+        for (size_t j = n; j-- > 0;) acc = gl_add(gl_mul(acc, z), p[j]);
+        return acc;
+    }
+};
+
+}  // namespace orc

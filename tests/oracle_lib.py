@@ -1,0 +1,117 @@
+"""ctypes access to oracle/liboracle.so — the CPU restatement used as the parity checker.
+
+Test infrastructure only: nothing under zk_evm_b200/ imports this.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+u64p = C.POINTER(C.c_uint64)
+P = 0xFFFFFFFF00000001
+GENERATOR = 14293326489335486720
+
+
+def _ptr(a):
+    return a.ctypes.data_as(u64p)
+
+
+class Oracle:
+    def __init__(self, lib):
+        self.lib = lib
+        for f in ("orc_gl_add", "orc_gl_sub", "orc_gl_mul", "orc_gl_inv", "orc_gl_pow", "orc_root_of_unity"):
+            getattr(lib, f).restype = C.c_uint64
+        lib.orc_gl_add.argtypes = lib.orc_gl_sub.argtypes = lib.orc_gl_mul.argtypes = lib.orc_gl_pow.argtypes = [C.c_uint64, C.c_uint64]
+        lib.orc_gl_inv.argtypes = [C.c_uint64]
+        lib.orc_challenger_run.restype = C.c_size_t
+
+    def poseidon(self, states):
+        s = np.ascontiguousarray(states, dtype=np.uint64).reshape(-1, 12).copy()
+        self.lib.orc_poseidon(_ptr(s), C.c_size_t(s.shape[0]))
+        return s
+
+    def hash_no_pad(self, xs):
+        a = np.ascontiguousarray(xs, dtype=np.uint64)
+        out = np.empty(4, dtype=np.uint64)
+        self.lib.orc_hash_no_pad(_ptr(a), C.c_size_t(a.size), _ptr(out))
+        return out
+
+    def hash_or_noop(self, xs):
+        a = np.ascontiguousarray(xs, dtype=np.uint64)
+        out = np.empty(4, dtype=np.uint64)
+        self.lib.orc_hash_or_noop(_ptr(a), C.c_size_t(a.size), _ptr(out))
+        return out
+
+    def two_to_one(self, l, r):
+        l = np.ascontiguousarray(l, dtype=np.uint64); r = np.ascontiguousarray(r, dtype=np.uint64)
+        out = np.empty(4, dtype=np.uint64)
+        self.lib.orc_two_to_one(_ptr(l), _ptr(r), _ptr(out))
+        return out
+
+    def hash_rows_colmajor(self, data):
+        a = np.ascontiguousarray(data, dtype=np.uint64)
+        out = np.empty((a.shape[1], 4), dtype=np.uint64)
+        self.lib.orc_hash_rows_colmajor(_ptr(a), C.c_size_t(a.shape[1]), C.c_size_t(a.shape[0]), _ptr(out))
+        return out
+
+    def ntt(self, data, kind=0, shift=0):
+        a = np.ascontiguousarray(data, dtype=np.uint64).copy()
+        if a.ndim == 1:
+            a = a.reshape(1, -1)
+        self.lib.orc_ntt(_ptr(a), C.c_size_t(a.shape[0]), C.c_size_t(a.shape[1]), int(kind), C.c_uint64(shift))
+        return a
+
+    def naive_dft(self, x):
+        a = np.ascontiguousarray(x, dtype=np.uint64)
+        out = np.empty_like(a)
+        self.lib.orc_naive_dft(_ptr(a), _ptr(out), C.c_size_t(a.size))
+        return out
+
+    def commit(self, cols, rate_bits=1, cap_height=4, from_coeffs=False):
+        a = np.ascontiguousarray(cols, dtype=np.uint64)
+        ncols, n = a.shape
+        N = n << rate_bits
+        coeffs = np.empty((ncols, n), dtype=np.uint64)
+        leaves = np.empty((N, ncols), dtype=np.uint64)
+        digests = np.empty((2 * (N - (1 << cap_height)), 4), dtype=np.uint64)
+        cap = np.empty((1 << cap_height, 4), dtype=np.uint64)
+        rc = self.lib.orc_commit(_ptr(a), C.c_size_t(ncols), C.c_size_t(n), C.c_uint(rate_bits), C.c_uint(cap_height),
+                                 int(from_coeffs), _ptr(coeffs), _ptr(leaves), _ptr(digests), _ptr(cap))
+        if rc != 0:
+            raise RuntimeError("oracle commit failed")
+        return coeffs, leaves, digests, cap
+
+    def challenger_run(self, ops):
+        """ops: list of ('o', v) | ('c',) | ('k',) -> (challenges, final state)"""
+        enc = []
+        for op in ops:
+            if op[0] == 'o':
+                enc += [0, op[1]]
+            elif op[0] == 'c':
+                enc += [1, 0]
+            else:
+                enc += [2, 0]
+        a = np.array(enc, dtype=np.uint64)
+        out = np.zeros(len(ops) + 1, dtype=np.uint64)
+        st = np.zeros(12, dtype=np.uint64)
+        k = self.lib.orc_challenger_run(_ptr(a), C.c_size_t(len(ops)), _ptr(out), _ptr(st))
+        return out[:k].copy(), st
+
+
+def build():
+    subprocess.check_call(["make", "-C", ORACLE_DIR, "-s"])
+
+
+def load():
+    if not os.path.exists(LIB):
+        build()
+    return Oracle(C.CDLL(LIB))
+
+
+def rand_field(rng, shape):
+    """uniform canonical Goldilocks elements"""
+    x = rng.integers(0, P, size=shape, dtype=np.uint64, endpoint=False)
+    return x

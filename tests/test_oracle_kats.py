@@ -1,0 +1,145 @@
+"""Pins the oracle against every known answer the reference holds for this path.  CPU only."""
+import numpy as np
+from tests.oracle_lib import P, GENERATOR, rand_field
+
+
+def test_poseidon_hash_zeros(oracle):
+    # smt_trie/src/keys.rs:10-15  HASH_ZEROS = poseidon([0;12])[0..4]
+    out = oracle.poseidon(np.zeros(12, dtype=np.uint64))[0]
+    assert list(out[:4]) == [4330397376401421145, 14124799381142128323, 8742572140681234676, 14345658006221440202]
+
+
+def test_empty_consolidated_blockhash(oracle):
+    # evm_arithmetization/src/proof.rs:505-510: hash_no_pad of 2048 zeros (consolidate_hashes, proof.rs:385-393)
+    out = oracle.hash_no_pad(np.zeros(2048, dtype=np.uint64))
+    assert list(out) == [5498946765822202150, 10724662260254836878, 9161393967331872654, 5704373722058976135]
+
+
+def _hash_contract_bytecode(oracle, code: bytes):
+    # restates smt_trie/src/code.rs:10-47: pad with 0x01, zeros to a multiple of 56, last byte |= 0x80; 7-byte LE limbs;
+    # capacity carried between blocks: state = [8 limbs | capacity(4)], capacity starts 0, output = perm[0..4]
+    code = bytearray(code) + b"\x01"
+    while len(code) % 56 != 0:
+        code.append(0)
+    code[-1] |= 0x80
+    capacity = [0, 0, 0, 0]
+    for i in range(0, len(code), 56):
+        block = code[i:i + 56]
+        limbs = [int.from_bytes(block[7 * j:7 * j + 7], "little") for j in range(8)]
+        st = oracle.poseidon(np.array(limbs + capacity, dtype=np.uint64))[0]
+        capacity = [int(x) for x in st[:4]]
+    return capacity
+
+
+def test_hash_contract_bytecode_empty(oracle):
+    # smt_trie/src/code.rs:57-67
+    assert _hash_contract_bytecode(oracle, b"") == [10052403398432742521, 15195891732843337299,
+                                                    2019258788108304834, 4300613462594703212]
+
+
+def test_field_inverse_65536(oracle):
+    # arithmetic/addcy.rs:67 GOLDILOCKS_INVERSE_65536
+    assert oracle.lib.orc_gl_inv(65536) == 18446462594437939201
+    assert oracle.lib.orc_gl_mul(65536, 18446462594437939201) == 1
+
+
+def test_field_against_python_ints(oracle):
+    rng = np.random.default_rng(7)
+    xs = [0, 1, P - 1, P - 2, 2**32, 2**32 - 1, 2**63] + [int(v) for v in rand_field(rng, 200)]
+    for a in xs[:40]:
+        for b in xs[:40]:
+            assert oracle.lib.orc_gl_mul(a, b) == a * b % P
+            assert oracle.lib.orc_gl_add(a, b) == (a + b) % P
+            assert oracle.lib.orc_gl_sub(a, b) == (a - b) % P
+    for a in xs:
+        if a:
+            assert oracle.lib.orc_gl_inv(a) == pow(a, P - 2, P)
+
+
+def test_generators(oracle):
+    # g^((p-1)/2^32) is the 2^32 generator; root(k)^(2^k) == 1 and root(k)^(2^(k-1)) == -1
+    assert pow(GENERATOR, (P - 1) >> 32, P) == 7277203076849721926
+    for k in (1, 5, 16, 32):
+        w = oracle.lib.orc_root_of_unity(k)
+        assert pow(w, 1 << k, P) == 1 and pow(w, 1 << (k - 1), P) == P - 1
+
+
+def test_fft_matches_naive_dft(oracle):
+    rng = np.random.default_rng(1)
+    for lg in (0, 1, 2, 5, 8):
+        x = rand_field(rng, 1 << lg)
+        assert np.array_equal(oracle.ntt(x, 0)[0], oracle.naive_dft(x))
+
+
+def test_ntt_roundtrip_2_16(oracle):
+    # BASELINE config #1: 2^16-point NTT round trip, 1 and 128 columns, plus edge vectors
+    rng = np.random.default_rng(1)
+    n = 1 << 16
+    x = rand_field(rng, (128, n))
+    x[0] = 0
+    x[1] = P - 1
+    x[2] = 0; x[2, 0] = 1
+    x[3] = 0; x[3, n - 1] = 1
+    y = oracle.ntt(x, 0)
+    assert np.array_equal(oracle.ntt(y, 1), x)
+    assert np.all(y[0] == 0)
+    assert np.all(y[2] == 1)                       # DFT of the unit impulse
+    yc = oracle.ntt(x, 2, GENERATOR)
+    assert np.array_equal(oracle.ntt(yc, 3, GENERATOR), x)
+    # coset_fft(c, s) evaluates the polynomial at s*w^i: check a few points by Horner on a short column
+    c = rand_field(rng, 64)
+    ev = oracle.ntt(c, 2, GENERATOR)[0]
+    w = oracle.lib.orc_root_of_unity(6)
+    for i in (0, 1, 17, 63):
+        pt = GENERATOR * pow(w, i, P) % P
+        acc = 0
+        for cj in reversed([int(v) for v in c]):
+            acc = (acc * pt + cj) % P
+        assert int(ev[i]) == acc
+
+
+def test_challenger_semantics(oracle):
+    # plonky2 iop/challenger.rs: outputs are popped from the back of state[0..8] after a duplex
+    ch, st = oracle.challenger_run([('o', 1), ('o', 2), ('c',), ('c',)])
+    perm = oracle.poseidon(np.array([1, 2] + [0] * 10, dtype=np.uint64))[0]
+    assert list(ch) == [int(perm[7]), int(perm[6])]
+    # observing after a challenge clears the output buffer; 8 observations trigger a duplex immediately
+    ch2, st2 = oracle.challenger_run([('o', i) for i in range(8)] + [('c',)])
+    perm2 = oracle.poseidon(np.array(list(range(8)) + [0] * 4, dtype=np.uint64))[0]
+    assert list(ch2) == [int(perm2[7])] and list(st2) == list(perm2)
+    # compact absorbs pending input
+    _, st3 = oracle.challenger_run([('o', 5), ('k',)])
+    assert list(st3) == list(oracle.poseidon(np.array([5] + [0] * 11, dtype=np.uint64))[0])
+
+
+def test_merkle_layout_and_proofs(oracle):
+    rng = np.random.default_rng(3)
+    ncols, n = 7, 64
+    cols = rand_field(rng, (ncols, n))
+    coeffs, leaves, digests, cap = oracle.commit(cols, rate_bits=1, cap_height=2)
+    N = 2 * n
+    # leaf j = LDE row bitrev(j): check via direct evaluation of column 0 at g*w^bitrev(j)
+    w = oracle.lib.orc_root_of_unity(7)
+    c0 = [int(v) for v in coeffs[0]]
+    for j in (0, 1, 5, 127):
+        i = int('{:07b}'.format(j)[::-1], 2)
+        pt = GENERATOR * pow(w, i, P) % P
+        acc = 0
+        for cj in reversed(c0):
+            acc = (acc * pt + cj) % P
+        assert int(leaves[j, 0]) == acc
+    # interpolation: coeffs evaluate back to the trace on the subgroup
+    assert np.array_equal(oracle.ntt(coeffs, 0), cols)
+    # digests layout: recompute cap[0] from the first subtree buffer (2*32-2 entries)
+    per = N // 4
+    sub = digests[: 2 * per - 2]
+
+    def root(buf, lo, m):
+        if m == 1:
+            return oracle.hash_or_noop(leaves[lo])
+        half = m - 2
+        l = root(buf[:half], lo, m // 2)
+        r = root(buf[half + 2:], lo + m // 2, m // 2)
+        assert np.array_equal(buf[half], l) and np.array_equal(buf[half + 1], r)
+        return oracle.two_to_one(l, r)
+    assert np.array_equal(root(sub, 0, per), cap[0])

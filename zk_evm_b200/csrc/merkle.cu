@@ -1,0 +1,132 @@
+// Poseidon Merkle tree over the rows of a column-major, bit-reversed LDE.
+//
+// Replaces plonky2 1.0.0 hash/merkle_tree.rs `MerkleTree::new(leaves, cap_height)` + `PoseidonHash::hash_or_noop`
+// / `two_to_one`, reached through PolynomialBatch::from_values at
+// /root/reference/evm_arithmetization/src/prover.rs:100-107.
+//
+// Leaf kernel: one thread per leaf (LDE row).  Row j is lde[c*N + j] over columns c, so a warp's 32 lanes read 32
+// consecutive 8-byte elements of every column: fully coalesced 256-byte requests, each column read exactly once.
+// The 12-word sponge state lives in registers; the sponge overwrites state[0..8] with 8 columns per permutation.
+// Inner levels: one thread per node, children are adjacent 32-byte digests.
+#include "internal.h"
+#include "poseidon.cuh"
+#include "merkle.h"
+
+namespace zk {
+
+__global__ void __launch_bounds__(128) leaf_hash_kernel(const uint64_t* __restrict__ data, size_t stride, size_t ncols,
+                                                        size_t nrows, uint64_t* __restrict__ digests) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nrows) return;
+    uint64_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = 0;
+    const uint64_t* p = data + j;
+    if (ncols <= 4) {   // hash_or_noop: short rows are copied, zero padded
+        for (size_t c = 0; c < ncols; c++) s[c] = p[c * stride];
+    } else {
+        size_t c = 0;
+        for (; c + 8 <= ncols; c += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) s[k] = p[(c + k) * stride];
+            poseidon_permute(s);
+        }
+        if (c < ncols) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (c + k < ncols) s[k] = p[(c + k) * stride];
+            poseidon_permute(s);
+        }
+    }
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(digests + 4 * j);
+    o[0] = make_ulonglong2(s[0], s[1]);
+    o[1] = make_ulonglong2(s[2], s[3]);
+}
+
+__global__ void __launch_bounds__(128) merkle_level_kernel(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+                                                           size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const ulonglong2* c = reinterpret_cast<const ulonglong2*>(in + 8 * i);
+    ulonglong2 a = c[0], b = c[1], d = c[2], e = c[3];
+    uint64_t s[12] = {a.x, a.y, b.x, b.y, d.x, d.y, e.x, e.y, 0, 0, 0, 0};
+    poseidon_permute(s);
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(out + 4 * i);
+    o[0] = make_ulonglong2(s[0], s[1]);
+    o[1] = make_ulonglong2(s[2], s[3]);
+}
+
+__global__ void poseidon_states_kernel(uint64_t* states, size_t count) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint64_t s[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) s[k] = states[12 * i + k];
+    poseidon_permute(s);
+#pragma unroll
+    for (int k = 0; k < 12; k++) states[12 * i + k] = s[k];
+}
+
+void poseidon_states(Ctx& c, uint64_t* dev_states, size_t count) {
+    if (!count) return;
+    poseidon_states_kernel<<<(unsigned)((count + 127) / 128), 128, 0, c.stream>>>(dev_states, count);
+    c.count_launch();
+    c.check_launch("poseidon_states_kernel");
+}
+
+void leaf_hash(Ctx& c, const uint64_t* data, size_t stride, size_t ncols, size_t nrows, uint64_t* digests) {
+    leaf_hash_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, c.stream>>>(data, stride, ncols, nrows, digests);
+    c.count_launch();
+    c.check_launch("leaf_hash_kernel");
+}
+
+void merkle_layout(size_t nleaves, unsigned cap_height, std::vector<size_t>& off, std::vector<size_t>& cnt) {
+    off.clear(); cnt.clear();
+    size_t o = 0, k = nleaves;
+    for (;;) {
+        off.push_back(o); cnt.push_back(k);
+        o += 4 * k;
+        if (k <= ((size_t)1 << cap_height)) break;
+        k >>= 1;
+    }
+}
+
+// digests: level 0 already filled with leaf digests
+void merkle_inner_levels(Ctx& c, uint64_t* digests, const std::vector<size_t>& off, const std::vector<size_t>& cnt) {
+    for (size_t l = 1; l < off.size(); l++) {
+        merkle_level_kernel<<<(unsigned)((cnt[l] + 127) / 128), 128, 0, c.stream>>>(digests + off[l - 1],
+                                                                                     digests + off[l], cnt[l]);
+        c.count_launch();
+    }
+    c.check_launch("merkle_level_kernel");
+}
+
+void merkle_build(Ctx& c, const uint64_t* rows_colmajor, size_t stride, size_t ncols, size_t nleaves,
+                  unsigned cap_height, DevBuf& digests, std::vector<size_t>& off, std::vector<size_t>& cnt) {
+    ZK_REQUIRE(((size_t)1 << cap_height) <= nleaves, "cap_height too large for the number of leaves");
+    merkle_layout(nleaves, cap_height, off, cnt);
+    digests = DevBuf(&c, (off.back() + 4 * cnt.back()) * 8);
+    leaf_hash(c, rows_colmajor, stride, ncols, nleaves, digests.get());
+    merkle_inner_levels(c, digests.get(), off, cnt);
+}
+
+// plonky2 `digests` layout from level arrays (host): per cap subtree, recursively
+//   buf(left) | digest(left child) | digest(right child) | buf(right)
+static void fill_rec(uint64_t* buf, const std::vector<uint64_t>& lv, const std::vector<size_t>& off, size_t lvl, size_t idx) {
+    if (lvl == 0) return;
+    size_t m = (size_t)1 << lvl, half_buf = m - 2;
+    fill_rec(buf, lv, off, lvl - 1, 2 * idx);
+    memcpy(buf + 4 * half_buf, &lv[off[lvl - 1] + 4 * (2 * idx)], 32);
+    memcpy(buf + 4 * (half_buf + 1), &lv[off[lvl - 1] + 4 * (2 * idx + 1)], 32);
+    fill_rec(buf + 4 * (half_buf + 2), lv, off, lvl - 1, 2 * idx + 1);
+}
+void merkle_export_plonky2(const std::vector<uint64_t>& levels_host, const std::vector<size_t>& off,
+                           const std::vector<size_t>& cnt, uint64_t* out) {
+    size_t ncap = cnt.back(), nleaves = cnt[0];
+    size_t per = nleaves / ncap;
+    if (per < 2) return;
+    size_t sub = 2 * per - 2;
+    for (size_t cidx = 0; cidx < ncap; cidx++) fill_rec(out + 4 * cidx * sub, levels_host, off, off.size() - 1, cidx);
+}
+
+}  // namespace zk
