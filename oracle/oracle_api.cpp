@@ -97,3 +97,79 @@ size_t orc_challenger_run(const uint64_t* ops, size_t nops, uint64_t* out, uint6
 }
 
 }  // extern "C"
+
+// ---- per-table STARK prover / verifier (oracle_stark.h) ---------------------------------------------------------
+#include "oracle_stark.h"
+
+static Config cfg_from(const uint32_t c[8]) {
+    Config k;
+    k.security_bits = c[0]; k.num_challenges = c[1]; k.rate_bits = c[2]; k.cap_height = c[3]; k.pow_bits = c[4];
+    k.arity_bits = c[5]; k.final_poly_bits = c[6]; k.num_queries = c[7];
+    return k;
+}
+static TableParams params_from(const uint64_t l[4]) {
+    TableParams p; p.halt_final = l[0]; p.init = l[1]; p.syscall_jumptable = l[2]; p.exception_jumptable = l[3];
+    return p;
+}
+static thread_local std::string g_orc_err;
+
+extern "C" {
+
+const char* orc_last_error(void) { return g_orc_err.c_str(); }
+uint32_t orc_table_num_columns(uint32_t table) { return zkstark::table_num_columns(table); }
+int orc_table_supported(uint32_t table) { return zkstark::table_supported(table) ? 1 : 0; }
+size_t orc_table_num_aux(uint32_t table, uint32_t num_challenges) {
+    return aux_shape(table, zkstark::all_cross_table_lookups(), num_challenges, zkstark::CONSTRAINT_DEGREE).num_aux();
+}
+
+// prove_single_table (prover.rs:301-341) for one table given its trace and the CTL challenges.
+// trace: ncols*n column-major.  beta_gamma: [beta_0, gamma_0, beta_1, gamma_1 ...].  chal_state: compacted transcript
+// state in, state after this table's proof out.  Returns the number of proof words written (or needed when out is too
+// small / null), negative on failure.
+long orc_prove_table(uint32_t table, const uint32_t cfgw[8], const uint64_t* trace, size_t ncols, size_t n,
+                     const uint64_t* beta_gamma, uint64_t chal_state[12], const uint64_t labels[4], const uint64_t* forced_pow,
+                     uint64_t* out, size_t out_cap, uint64_t* aux_out, uint64_t* quot_out, uint64_t* fri_values_out) {
+    try {
+        Config cfg = cfg_from(cfgw);
+        if (ncols != zkstark::table_num_columns(table)) throw std::runtime_error("wrong number of trace columns");
+        std::vector<const uint64_t*> cols(ncols);
+        for (size_t c = 0; c < ncols; c++) cols[c] = trace + c * n;
+        PolyBatch tc;
+        tc.from_values(cols.data(), ncols, n, cfg.rate_bits, cfg.cap_height);
+        std::vector<uint64_t> betas, gammas;
+        for (unsigned i = 0; i < cfg.num_challenges; i++) { betas.push_back(beta_gamma[2 * i]); gammas.push_back(beta_gamma[2 * i + 1]); }
+        auto ctls = zkstark::all_cross_table_lookups();
+        CtlData ctl = ctl_data_for_table(table, cols.data(), n, ctls, betas, gammas, zkstark::CONSTRAINT_DEGREE);
+        Challenger ch; ch.set_state(chal_state);
+        ProveDebug dbg;
+        StarkProofData p = prove_table(table, cfg, cols.data(), n, tc, ctl, betas, gammas, ch, params_from(labels), forced_pow, ctls, &dbg);
+        ch.compact();
+        memcpy(chal_state, ch.state, 96);
+        if (aux_out) for (size_t c = 0; c < dbg.aux_values.size(); c++) memcpy(aux_out + c * n, dbg.aux_values[c].data(), n * 8);
+        if (quot_out) memcpy(quot_out, dbg.quotient_chunk_coeffs.data(), dbg.quotient_chunk_coeffs.size() * 8);
+        if (fri_values_out) for (size_t i = 0; i < dbg.fri_final_values.size(); i++) { fri_values_out[2 * i] = dbg.fri_final_values[i].a; fri_values_out[2 * i + 1] = dbg.fri_final_values[i].b; }
+        Words w = zkstark::serialize_proof(p);
+        if (out && out_cap >= w.size()) memcpy(out, w.data(), w.size() * 8);
+        return (long)w.size();
+    } catch (const std::exception& e) { g_orc_err = e.what(); return -1; }
+}
+
+// verify one table's proof; returns 1 if valid, 0 if rejected (reason in orc_last_error), -1 on malformed input
+int orc_verify_table(uint32_t table, const uint32_t cfgw[8], const uint64_t* proof, size_t len, const uint64_t* beta_gamma,
+                     uint64_t chal_state[12], const uint64_t labels[4]) {
+    try {
+        Config cfg = cfg_from(cfgw);
+        StarkProofData p = zkstark::deserialize_proof(proof, len);
+        std::vector<uint64_t> betas, gammas;
+        for (unsigned i = 0; i < cfg.num_challenges; i++) { betas.push_back(beta_gamma[2 * i]); gammas.push_back(beta_gamma[2 * i + 1]); }
+        Challenger ch; ch.set_state(chal_state);
+        std::string err;
+        bool ok = verify_table(table, cfg, p, betas, gammas, ch, params_from(labels), zkstark::all_cross_table_lookups(), err);
+        ch.compact();
+        memcpy(chal_state, ch.state, 96);
+        g_orc_err = err;
+        return ok ? 1 : 0;
+    } catch (const std::exception& e) { g_orc_err = e.what(); return -1; }
+}
+
+}  // extern "C"

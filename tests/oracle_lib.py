@@ -115,3 +115,57 @@ def rand_field(rng, shape):
     """uniform canonical Goldilocks elements"""
     x = rng.integers(0, P, size=shape, dtype=np.uint64, endpoint=False)
     return x
+
+
+# ---- per-table STARK prover / verifier --------------------------------------------------------------------------
+STANDARD_FAST = (100, 2, 1, 4, 16, 4, 5, 84)     # StarkConfig::standard_fast_config
+TEST_CONFIG = (1, 1, 1, 4, 1, 4, 5, 1)           # TEST_STARK_CONFIG, testing_utils.rs:41-52
+DEFAULT_LABELS = (0x1234, 0x77, 0x4000, 0x5000)   # halt_final, init, syscall_jumptable, exception_jumptable (arbitrary)
+
+
+def _cfg(cfg):
+    return (C.c_uint32 * 8)(*cfg)
+
+
+def orc_prove_table(orc, table, cfg, trace, beta_gamma, state, labels=DEFAULT_LABELS, forced_pow=None, debug=False):
+    """returns (proof words, new challenger state[, aux values, quotient chunk coeffs, fri values])"""
+    lib = orc.lib
+    lib.orc_prove_table.restype = C.c_long
+    lib.orc_last_error.restype = C.c_char_p
+    lib.orc_table_num_aux.restype = C.c_size_t
+    t = np.ascontiguousarray(trace, dtype=np.uint64)
+    ncols, n = t.shape
+    bg = np.ascontiguousarray(beta_gamma, dtype=np.uint64)
+    st = np.ascontiguousarray(state, dtype=np.uint64).copy()
+    lab = np.array(labels, dtype=np.uint64)
+    fp = np.array([forced_pow if forced_pow is not None else 0], dtype=np.uint64)
+    na = lib.orc_table_num_aux(C.c_uint32(table), C.c_uint32(cfg[1]))
+    aux = np.zeros((na, n), dtype=np.uint64) if debug else None
+    quot = np.zeros((2 * cfg[1], n), dtype=np.uint64) if debug else None
+    fri = np.zeros((n << cfg[2], 2), dtype=np.uint64) if debug else None
+    cap = 1 << 16
+    while True:
+        out = np.zeros(cap, dtype=np.uint64)
+        st2 = st.copy()
+        r = lib.orc_prove_table(C.c_uint32(table), _cfg(cfg), _ptr(t), C.c_size_t(ncols), C.c_size_t(n), _ptr(bg), _ptr(st2),
+                                _ptr(lab), _ptr(fp) if forced_pow is not None else None, _ptr(out), C.c_size_t(cap),
+                                _ptr(aux) if debug and na else None, _ptr(quot) if debug else None, _ptr(fri) if debug else None)
+        if r < 0:
+            raise RuntimeError("oracle prove_table failed: " + lib.orc_last_error().decode())
+        if r <= cap:
+            break
+        cap = int(r)
+    if debug:
+        return out[:r].copy(), st2, aux, quot, fri
+    return out[:r].copy(), st2
+
+
+def orc_verify_table(orc, table, cfg, proof, beta_gamma, state, labels=DEFAULT_LABELS):
+    lib = orc.lib
+    lib.orc_last_error.restype = C.c_char_p
+    p = np.ascontiguousarray(proof, dtype=np.uint64)
+    bg = np.ascontiguousarray(beta_gamma, dtype=np.uint64)
+    st = np.ascontiguousarray(state, dtype=np.uint64).copy()
+    lab = np.array(labels, dtype=np.uint64)
+    r = lib.orc_verify_table(C.c_uint32(table), _cfg(cfg), _ptr(p), C.c_size_t(p.size), _ptr(bg), _ptr(st), _ptr(lab))
+    return r == 1, lib.orc_last_error().decode(), st

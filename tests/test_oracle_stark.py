@@ -1,0 +1,57 @@
+"""CPU: the oracle's restated prover produces proofs the oracle's restated verifier accepts (valid traces), and rejects
+tampered ones.  This is the self-consistency pin for every [UPSTREAM-RECALL] convention."""
+import numpy as np
+import pytest
+from tests import traces
+from tests.oracle_lib import orc_prove_table, orc_verify_table, STANDARD_FAST, TEST_CONFIG, P
+
+BG2 = np.array([0x1111111111, 0x2222222222, 0x3333333333, 0x4444444444], dtype=np.uint64)
+STATE0 = np.arange(1, 13, dtype=np.uint64)
+
+
+def _trace(table, lg, seed):
+    if table in (traces.T_MEM_BEFORE, traces.T_MEM_AFTER):
+        return traces.memcont_trace(lg, seed)
+    if table == traces.T_LOGIC:
+        return traces.logic_trace(lg, seed)
+    if table == traces.T_MEMORY:
+        return traces.memory_trace_simple(lg)
+    raise ValueError(table)
+
+
+@pytest.mark.parametrize("table,lg,cfg", [
+    (traces.T_MEM_BEFORE, 7, TEST_CONFIG), (traces.T_MEM_AFTER, 5, TEST_CONFIG), (traces.T_MEM_BEFORE, 9, STANDARD_FAST),
+    (traces.T_LOGIC, 6, TEST_CONFIG), (traces.T_LOGIC, 8, STANDARD_FAST),
+    (traces.T_MEMORY, 6, TEST_CONFIG), (traces.T_MEMORY, 10, STANDARD_FAST), (traces.T_MEMORY, 4, TEST_CONFIG),
+])
+def test_prove_then_verify(oracle, table, lg, cfg):
+    tr = _trace(table, lg, 42 + lg)
+    bg = BG2[:2 * cfg[1]]
+    proof, st = orc_prove_table(oracle, table, cfg, tr, bg, STATE0)
+    ok, err, st2 = orc_verify_table(oracle, table, cfg, proof, bg, STATE0)
+    assert ok, err
+    assert np.array_equal(st, st2)       # prover and verifier leave the shared transcript in the same state
+    # tamper with the aux cap, a trace opening and the final polynomial
+    for pos in (82, 212, len(proof) - 3):
+        bad = proof.copy()
+        bad[pos] = (int(bad[pos]) + 1) % P
+        ok, err, _ = orc_verify_table(oracle, table, cfg, bad, bg, STATE0)
+        assert not ok
+
+
+def test_invalid_trace_is_rejected(oracle):
+    tr = traces.logic_trace(6, 1)
+    tr[515, 3] = (int(tr[515, 3]) + 1) % P        # wrong result limb
+    proof, _ = orc_prove_table(oracle, traces.T_LOGIC, TEST_CONFIG, tr, BG2[:2], STATE0)
+    ok, err, _ = orc_verify_table(oracle, traces.T_LOGIC, TEST_CONFIG, proof, BG2[:2], STATE0)
+    assert not ok and "quotient" in err
+
+
+def test_forced_pow_witness(oracle):
+    tr = traces.memcont_trace(6, 3)
+    proof, st = orc_prove_table(oracle, traces.T_MEM_AFTER, STANDARD_FAST, tr, BG2, STATE0)
+    w = int(proof[-1])
+    proof2, st2 = orc_prove_table(oracle, traces.T_MEM_AFTER, STANDARD_FAST, tr, BG2, STATE0, forced_pow=w)
+    assert np.array_equal(proof, proof2) and np.array_equal(st, st2)
+    with pytest.raises(RuntimeError):
+        orc_prove_table(oracle, traces.T_MEM_AFTER, STANDARD_FAST, tr, BG2, STATE0, forced_pow=w + 1 if w + 1 != 0 else 2)

@@ -1,0 +1,94 @@
+// Lookup (logUp) and cross-table-lookup constraint checks, interpreted from a FlatView.
+// Restates starky 1.0.0 lookup.rs `eval_packed_lookups_generic` / `eval_helper_columns` and cross_table_lookup.rs
+// `eval_cross_table_lookup_checks` (called from eval_vanishing_poly after the table's own constraints; in-tree
+// spec: /root/reference/book/src/framework/range_check.md:55-120 and ctls.md:17-25).
+#pragma once
+#include "hd.h"
+#include "lookup.h"
+
+namespace zkstark {
+
+template <class P, class V>
+ZKS_HD P flat_eval_col(const FlatView& f, uint32_t id, const V& lv, const V& nv) {
+    const ColRec r = f.cols[id];
+    P acc = P::from_u64(r.constant);
+    for (uint32_t t = r.lin_begin; t < r.lin_end; t++) acc = acc + lv[f.term_col[t]] * P::from_u64(f.term_coef[t]);
+    for (uint32_t t = r.next_begin; t < r.next_end; t++) acc = acc + nv[f.term_col[t]] * P::from_u64(f.term_coef[t]);
+    return acc;
+}
+template <class P, class V>
+ZKS_HD P flat_eval_filter(const FlatView& f, uint32_t id, const V& lv, const V& nv) {
+    const FilterRec r = f.filters[id];
+    P acc = P::zero();
+    for (uint32_t k = r.prod_begin; k < r.prod_end; k += 2)
+        acc = acc + flat_eval_col<P>(f, f.prod_ids[k], lv, nv) * flat_eval_col<P>(f, f.prod_ids[k + 1], lv, nv);
+    for (uint32_t k = r.const_begin; k < r.const_end; k++) acc = acc + flat_eval_col<P>(f, f.const_ids[k], lv, nv);
+    return acc;
+}
+// GrandProductChallenge::combine: sum_i v_i beta^i + gamma
+template <class P, class V>
+ZKS_HD P flat_combine(const FlatView& f, const EntryRec& e, P beta, P gamma, const V& lv, const V& nv) {
+    P acc = P::zero();
+    for (uint32_t k = e.col_end; k-- > e.col_begin;) acc = acc * beta + flat_eval_col<P>(f, f.col_ids[k], lv, nv);
+    return acc + gamma;
+}
+
+// eval_helper_columns: chunks of two entries per helper column
+template <class P, class V, class A, class CC>
+ZKS_HD void flat_eval_helpers(const FlatView& f, uint32_t entry_begin, uint32_t entry_end, uint32_t num_helpers,
+                              uint32_t helper_begin, P beta, P gamma, const V& lv, const V& nv, const A& aux_lv, CC& yc) {
+    for (uint32_t t = 0; t < num_helpers; t++) {
+        uint32_t e0 = entry_begin + 2 * t;
+        P h = aux_lv[helper_begin + t];
+        P c0 = flat_combine<P>(f, f.entries[e0], beta, gamma, lv, nv);
+        P f0 = flat_eval_filter<P>(f, f.entries[e0].filter, lv, nv);
+        if (e0 + 1 < entry_end) {
+            P c1 = flat_combine<P>(f, f.entries[e0 + 1], beta, gamma, lv, nv);
+            P f1 = flat_eval_filter<P>(f, f.entries[e0 + 1].filter, lv, nv);
+            yc.constraint(c1 * c0 * h - f0 * c1 - f1 * c0);
+        } else {
+            yc.constraint(c0 * h - f0);
+        }
+    }
+}
+
+// betas / gammas: the CTL challenges (lookups use beta_k as their challenge with combine(beta=1, gamma=beta_k))
+template <class P, class V, class A, class CC>
+ZKS_HD void flat_eval_lookups(const FlatView& f, const P* betas, const V& lv, const V& nv, const A& aux_lv, const A& aux_nv, CC& yc) {
+    for (uint32_t li = 0; li < f.n_lookups; li++) {
+        const LookupRec l = f.lookups[li];
+        P ch = betas[l.challenge];
+        flat_eval_helpers<P>(f, l.entry_begin, l.entry_end, l.num_helpers, l.helper_begin, P::one(), ch, lv, nv, aux_lv, yc);
+        P z = aux_lv[l.z_col], next_z = aux_nv[l.z_col];
+        P table_with_challenge = flat_eval_col<P>(f, l.table_col, lv, nv) + ch;   // table column has no next-row terms
+        P hsum = P::zero();
+        for (uint32_t t = 0; t < l.num_helpers; t++) hsum = hsum + aux_lv[l.helper_begin + t];
+        P y = hsum * table_with_challenge - flat_eval_col<P>(f, l.freq_col, lv, nv);
+        yc.constraint_first_row(z);
+        yc.constraint((next_z - z) * table_with_challenge - y);
+    }
+}
+
+template <class P, class V, class A, class CC>
+ZKS_HD void flat_eval_ctls(const FlatView& f, const P* betas, const P* gammas, const V& lv, const V& nv, const A& aux_lv,
+                           const A& aux_nv, CC& yc) {
+    for (uint32_t zi = 0; zi < f.n_ctl_zs; zi++) {
+        const CtlZRec c = f.ctl_zs[zi];
+        P beta = betas[c.challenge], gamma = gammas[c.challenge];
+        P local_z = aux_lv[c.z_col], next_z = aux_nv[c.z_col];
+        if (c.num_helpers) {
+            flat_eval_helpers<P>(f, c.entry_begin, c.entry_end, c.num_helpers, c.helper_begin, beta, gamma, lv, nv, aux_lv, yc);
+            P hsum = P::zero();
+            for (uint32_t t = 0; t < c.num_helpers; t++) hsum = hsum + aux_lv[c.helper_begin + t];
+            yc.constraint_last_row(local_z - hsum);
+            yc.constraint_transition(local_z - next_z - hsum);
+        } else {
+            P c0 = flat_combine<P>(f, f.entries[c.entry_begin], beta, gamma, lv, nv);
+            P f0 = flat_eval_filter<P>(f, f.entries[c.entry_begin].filter, lv, nv);
+            yc.constraint_last_row(c0 * local_z - f0);
+            yc.constraint_transition(c0 * (local_z - next_z) - f0);
+        }
+    }
+}
+
+}  // namespace zkstark

@@ -104,17 +104,62 @@ struct Lookup {
 };
 
 // ---------------------------------------------------------------------------------------------------------------
-// Flat (POD) form
+// Per-table view of the cross-table lookups: the list of CtlZData a table carries, in the order starky's
+// cross_table_lookup_data pushes them (for each CTL, for each challenge: one item per run of consecutive looking
+// entries on this table, then the looked item if this table is the looked one).
+// ---------------------------------------------------------------------------------------------------------------
+struct CtlZItem {
+    std::vector<std::pair<std::vector<Column>, Filter>> entries;
+    uint32_t challenge = 0;
+    uint32_t ctl_index = 0;
+    bool looked = false;
+    // partial_sums keeps the helper columns only when there is more than one (columns, filter) pair
+    uint32_t num_helpers(unsigned constraint_degree) const {
+        uint32_t d = constraint_degree - 1;
+        return entries.size() > 1 ? (uint32_t)((entries.size() + d - 1) / d) : 0;
+    }
+};
+inline std::vector<CtlZItem> table_ctl_items(uint32_t table, const std::vector<CrossTableLookup>& ctls, unsigned num_challenges) {
+    std::vector<CtlZItem> items;
+    for (size_t ci = 0; ci < ctls.size(); ci++) {
+        const CrossTableLookup& ctl = ctls[ci];
+        for (unsigned ch = 0; ch < num_challenges; ch++) {
+            size_t i = 0;
+            while (i < ctl.looking_tables.size()) {
+                size_t j = i;
+                while (j < ctl.looking_tables.size() && ctl.looking_tables[j].table == ctl.looking_tables[i].table) j++;
+                if (ctl.looking_tables[i].table == table) {
+                    CtlZItem it; it.challenge = ch; it.ctl_index = (uint32_t)ci;
+                    for (size_t k = i; k < j; k++) it.entries.push_back({ctl.looking_tables[k].columns, ctl.looking_tables[k].filter});
+                    items.push_back(it);
+                }
+                i = j;
+            }
+            if (ctl.looked_table.table == table) {
+                CtlZItem it; it.challenge = ch; it.ctl_index = (uint32_t)ci; it.looked = true;
+                it.entries.push_back({ctl.looked_table.columns, ctl.looked_table.filter});
+                items.push_back(it);
+            }
+        }
+    }
+    return items;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Flat (POD) form: what the CUDA kernels interpret.  All index ranges are half-open.
 // ---------------------------------------------------------------------------------------------------------------
 struct ColRec { uint32_t lin_begin, lin_end, next_begin, next_end; uint64_t constant; };
-struct FilterRec { uint32_t prod_begin, prod_end;     // pairs: prod[2k], prod[2k+1] are ColRec ids
-                   uint32_t const_begin, const_end; };   // consts[k] are ColRec ids
-// one (columns, filter) pair of a lookup: `ncols` ColRec ids starting at col_begin in `col_ids`
-struct EntryRec { uint32_t col_begin, col_end; uint32_t filter; };
-// one CtlZData of a table: entries [entry_begin, entry_end), helper columns count, which challenge pair
-struct CtlZRec { uint32_t entry_begin, entry_end; uint32_t num_helpers; uint32_t challenge; };
-// one in-table Lookup: entries (single-column) [entry_begin, entry_end), table/frequency ColRec ids
-struct LookupRec { uint32_t entry_begin, entry_end; uint32_t table_col, freq_col; uint32_t num_helpers; /* without Z */ };
+struct FilterRec { uint32_t prod_begin, prod_end;     // prod_ids[2k], prod_ids[2k+1] are ColRec ids
+                   uint32_t const_begin, const_end; };   // const_ids[k] are ColRec ids
+// one (columns, filter) pair: ColRec ids col_ids[col_begin .. col_end)
+struct EntryRec { uint32_t col_begin, col_end; uint32_t filter; uint32_t pad; };
+// one CtlZData of a table: entries [entry_begin, entry_end); helper columns live at aux index helper_begin..+num_helpers,
+// the running sum Z at aux index z_col
+struct CtlZRec { uint32_t entry_begin, entry_end; uint32_t num_helpers; uint32_t challenge; uint32_t helper_begin; uint32_t z_col; };
+// one in-table Lookup for one challenge: single-column entries [entry_begin, entry_end); helpers at aux index
+// helper_begin..+num_helpers, Z at z_col
+struct LookupRec { uint32_t entry_begin, entry_end; uint32_t table_col, freq_col; uint32_t num_helpers; uint32_t challenge;
+                   uint32_t helper_begin; uint32_t z_col; };
 
 struct Flat {
     std::vector<uint32_t> term_col;
@@ -127,6 +172,8 @@ struct Flat {
     std::vector<EntryRec> entries;
     std::vector<CtlZRec> ctl_zs;
     std::vector<LookupRec> lookups;
+    uint32_t num_lookup_cols = 0, num_ctl_helpers = 0, num_ctl_zs = 0;
+    uint32_t num_aux() const { return num_lookup_cols + num_ctl_helpers + num_ctl_zs; }
 
     uint32_t add_column(const Column& c) {
         ColRec r;
@@ -141,11 +188,14 @@ struct Flat {
     }
     uint32_t add_filter(const Filter& f) {
         FilterRec r;
+        std::vector<uint32_t> pp, cc;
+        for (auto& pr : f.products) { pp.push_back(add_column(pr.first)); pp.push_back(add_column(pr.second)); }
+        for (auto& c : f.constants) cc.push_back(add_column(c));
         r.prod_begin = (uint32_t)prod_ids.size();
-        for (auto& pr : f.products) { uint32_t a = add_column(pr.first), b = add_column(pr.second); prod_ids.push_back(a); prod_ids.push_back(b); }
+        prod_ids.insert(prod_ids.end(), pp.begin(), pp.end());
         r.prod_end = (uint32_t)prod_ids.size();
         r.const_begin = (uint32_t)const_ids.size();
-        for (auto& c : f.constants) const_ids.push_back(add_column(c));
+        const_ids.insert(const_ids.end(), cc.begin(), cc.end());
         r.const_end = (uint32_t)const_ids.size();
         filters.push_back(r);
         return (uint32_t)filters.size() - 1;
@@ -158,9 +208,58 @@ struct Flat {
         for (uint32_t id : ids) col_ids.push_back(id);
         e.col_end = (uint32_t)col_ids.size();
         e.filter = add_filter(f);
+        e.pad = 0;
         entries.push_back(e);
         return (uint32_t)entries.size() - 1;
     }
+};
+
+// Auxiliary-column layout of one table (starky prove_with_commitment): lookup columns (per lookup, per challenge:
+// helpers..., Z) ++ CTL helper columns of every item ++ CTL Z of every item.
+inline Flat build_table_flat(const std::vector<Lookup>& lookups, const std::vector<CtlZItem>& items, unsigned num_challenges,
+                             unsigned constraint_degree) {
+    Flat f;
+    uint32_t aux = 0;
+    for (const Lookup& l : lookups) {
+        uint32_t first_entry = (uint32_t)f.entries.size();
+        for (size_t i = 0; i < l.columns.size(); i++) f.add_entry({l.columns[i]}, l.filter_columns[i]);
+        uint32_t last_entry = (uint32_t)f.entries.size();
+        uint32_t tcol = f.add_column(l.table_column), fcol = f.add_column(l.frequencies_column);
+        uint32_t nh = (uint32_t)l.num_helper_columns(constraint_degree) - 1;
+        for (unsigned ch = 0; ch < num_challenges; ch++) {
+            LookupRec r;
+            r.entry_begin = first_entry; r.entry_end = last_entry; r.table_col = tcol; r.freq_col = fcol;
+            r.num_helpers = nh; r.challenge = ch; r.helper_begin = aux; r.z_col = aux + nh;
+            aux += nh + 1;
+            f.lookups.push_back(r);
+        }
+    }
+    f.num_lookup_cols = aux;
+    uint32_t helpers = 0;
+    for (const CtlZItem& it : items) helpers += it.num_helpers(constraint_degree);
+    f.num_ctl_helpers = helpers;
+    f.num_ctl_zs = (uint32_t)items.size();
+    uint32_t hpos = aux, zpos = aux + helpers;
+    for (const CtlZItem& it : items) {
+        CtlZRec r;
+        r.entry_begin = (uint32_t)f.entries.size();
+        for (auto& e : it.entries) f.add_entry(e.first, e.second);
+        r.entry_end = (uint32_t)f.entries.size();
+        r.num_helpers = it.num_helpers(constraint_degree);
+        r.challenge = it.challenge;
+        r.helper_begin = hpos; hpos += r.num_helpers;
+        r.z_col = zpos++;
+        f.ctl_zs.push_back(r);
+    }
+    return f;
+}
+
+// raw-pointer view of a Flat (host vectors or device copies)
+struct FlatView {
+    const uint32_t* term_col; const uint64_t* term_coef; const ColRec* cols; const uint32_t* col_ids;
+    const uint32_t* prod_ids; const uint32_t* const_ids; const FilterRec* filters; const EntryRec* entries;
+    const CtlZRec* ctl_zs; const LookupRec* lookups;
+    uint32_t n_ctl_zs, n_lookups, num_lookup_cols, num_ctl_helpers, num_ctl_zs;
 };
 
 }  // namespace zkstark
