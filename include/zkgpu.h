@@ -78,6 +78,9 @@ const char* zkgpu_version(void);
 int zkgpu_ctx_create(int device, zkgpu_ctx** out);
 void zkgpu_ctx_destroy(zkgpu_ctx* ctx);
 int zkgpu_ctx_sync(zkgpu_ctx* ctx);
+/* CUDA-event stopwatch on the context's stream: device milliseconds between start and stop */
+int zkgpu_ctx_timer_start(zkgpu_ctx* ctx);
+int zkgpu_ctx_timer_stop(zkgpu_ctx* ctx, float* ms);
 /* device-memory high-water mark and kernel-launch counter (bench.py's gpu_launches) */
 int zkgpu_ctx_stats(zkgpu_ctx* ctx, uint64_t* kernel_launches, uint64_t* bytes_in_use, uint64_t* bytes_peak);
 
@@ -103,6 +106,44 @@ int zkgpu_batch_cap(const zkgpu_batch* b, uint64_t* out_cap);
  *   leaves  (n<<rate_bits)*ncols  merkle_tree.leaves, row-major, row j = LDE row bitrev(j)
  *   digests 2*((n<<rate_bits) - (1<<cap_height))*4   merkle_tree.digests in plonky2's recursive layout */
 int zkgpu_batch_export(const zkgpu_batch* b, uint64_t* coeffs, uint64_t* leaves, uint64_t* digests);
+
+/* ---- S2: cross-table-lookup data of one table -------------------------------------------------------------- */
+/* Shape of a table under the AllStark registry (all_stark.rs:153-172): trace width and the auxiliary-column layout
+ * lookup columns ++ CTL helper columns ++ CTL Z columns for `num_challenges` challenges. */
+int zkgpu_table_info(uint32_t table_id, uint32_t num_challenges, uint32_t* num_columns, uint32_t* num_lookup_columns,
+                     uint32_t* num_ctl_helper_columns, uint32_t* num_ctl_zs);
+/* The per-table slice of starky get_ctl_data (prover.rs:137-143): for every cross-table lookup this table takes part in
+ * and every challenge, the helper columns h = sum filter/combine(columns) and the running sum Z (ctls.md:17-25).
+ * `trace` must have been committed with keep_values.  beta_gamma = [beta_0, gamma_0, beta_1, gamma_1]: the
+ * GrandProductChallengeSet drawn by the caller's transcript after observing all trace caps and the public values. */
+int zkgpu_ctl_data(zkgpu_ctx* ctx, uint32_t table_id, const zkgpu_batch* trace, const uint64_t* beta_gamma,
+                   uint32_t num_challenges, zkgpu_ctl** out);
+void zkgpu_ctl_free(zkgpu_ctl* ctl);
+/* (num_ctl_helper_columns + num_ctl_zs) * n values, column-major: CtlData.zs_columns[*].helper_columns then [*].z */
+int zkgpu_ctl_export(const zkgpu_ctl* ctl, uint64_t* out_cols);
+
+/* ---- S3: prove_single_table (prover.rs:301-341) == starky prove_with_commitment ------------------------------- */
+/* challenger_state: the 12-word sponge state of the shared transcript, in: as left by the previous table (or by
+ * get_ctl_data for the first one), out: after this table's query challenges; buffers are compacted on both sides
+ * exactly like `challenger.compact()` at prover.rs:320.  forced_pow_witness: NULL = search the smallest valid
+ * witness; otherwise use the given one (plonky2 picks an arbitrary valid witness with rayon find_any, so a reference
+ * proof can only be reproduced bit for bit when its witness is forced).  abort_flag: polled between stages
+ * (prover.rs:317,346-354) -> ZKGPU_ERR_ABORTED.  labels may be NULL for every table but Cpu. */
+int zkgpu_prove_table(zkgpu_ctx* ctx, uint32_t table_id, const zkgpu_kernel_labels* labels, const zkgpu_stark_config* config,
+                      const zkgpu_batch* trace, const zkgpu_ctl* ctl, uint64_t challenger_state[12],
+                      const uint64_t* forced_pow_witness, volatile const int* abort_flag, zkgpu_proof** out);
+void zkgpu_proof_free(zkgpu_proof* proof);
+/* StarkProofWithMetadata as little-endian u64 words (layout: zk_evm_b200/csrc/stark/proof.h).  *len_words in: capacity
+ * of buf, out: words needed; buf may be NULL to query the size. */
+int zkgpu_proof_serialize(const zkgpu_proof* proof, uint64_t* buf, size_t* len_words);
+
+/* ---- stage-by-stage parity hooks (tests) ---------------------------------------------------------------------- */
+/* when on, proofs retain their auxiliary / quotient PolynomialBatch and the FRI input values */
+int zkgpu_ctx_set_debug(zkgpu_ctx* ctx, int on);
+/* which: 0 = auxiliary polynomials, 1 = quotient chunks; the handle is borrowed from the proof */
+int zkgpu_proof_debug_batch(const zkgpu_proof* proof, int which, const zkgpu_batch** out);
+/* values of the FRI input polynomial on the LDE coset, bit-reversed order, (c0, c1) pairs */
+int zkgpu_proof_debug_fri_values(const zkgpu_proof* proof, uint64_t* out, size_t* len_words);
 
 /* ---- fine-grained entry points (per-kernel parity tests, ncu) --------------------------------------------- */
 /* In-place batched NTT over `ncols` host columns of length n (column-major contiguous).

@@ -1,3 +1,4 @@
 """zk_evm_b200 — B200-native STARK proving path for zk_evm's evm_arithmetization (host-side mirror over libzkgpu)."""
 from ._lib import ZkGpuError, StarkConfig, KernelLabels, lib, declared_symbols  # noqa: F401
-from .prover import Context, PolynomialBatch  # noqa: F401
+from .prover import (Context, PolynomialBatch, CtlData, StarkProof, table_info, get_ctl_data, prove_single_table,  # noqa: F401
+                     set_debug)

@@ -53,7 +53,7 @@ static void finish_commit(Ctx& c, Batch& b) {
     c.d2h(b.cap_host.data(), b.cap_dev(), b.cap_host.size() * 8);
 }
 
-static void init_batch(Ctx& c, Batch& b, size_t ncols, size_t n, uint32_t rate_bits, uint32_t cap_height) {
+void init_batch(Ctx& c, Batch& b, size_t ncols, size_t n, uint32_t rate_bits, uint32_t cap_height) {
     ZK_REQUIRE(ncols > 0 && n > 0, "empty batch");
     b.ctx = &c;
     b.ncols = ncols;
@@ -130,9 +130,11 @@ void zkgpu_ctx_destroy(zkgpu_ctx* h) {
     cudaSetDevice(h->c.device);
     cudaStreamSynchronize(h->c.stream);
     h->c.table_cache.clear();
+    h->c.stark_tables.clear();
     h->c.ntt.roots_fwd.release();
     h->c.ntt.roots_inv.release();
     cudaStreamSynchronize(h->c.stream);
+    if (h->c.ev0) { cudaEventDestroy(h->c.ev0); cudaEventDestroy(h->c.ev1); }
     cudaStreamDestroy(h->c.stream);
     cudaStreamDestroy(h->c.copy_stream);
     delete h;
@@ -142,6 +144,27 @@ int zkgpu_ctx_sync(zkgpu_ctx* h) {
     ZK_API_BEGIN
     ZK_REQUIRE(h, "ctx is null");
     h->c.sync();
+    ZK_API_END
+}
+
+// CUDA-event timer on the context's stream (bench.py: device time of a step, events on the launching stream)
+int zkgpu_ctx_timer_start(zkgpu_ctx* h) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(h, "ctx is null");
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    if (!c.ev0) { ZK_CUDA(cudaEventCreate(&c.ev0)); ZK_CUDA(cudaEventCreate(&c.ev1)); }
+    ZK_CUDA(cudaEventRecord(c.ev0, c.stream));
+    ZK_API_END
+}
+int zkgpu_ctx_timer_stop(zkgpu_ctx* h, float* ms) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(h && ms && h->c.ev0, "timer not started");
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    ZK_CUDA(cudaEventRecord(c.ev1, c.stream));
+    ZK_CUDA(cudaEventSynchronize(c.ev1));
+    ZK_CUDA(cudaEventElapsedTime(ms, c.ev0, c.ev1));
     ZK_API_END
 }
 

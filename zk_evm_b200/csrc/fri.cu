@@ -1,0 +1,233 @@
+// Openings and the FRI commit phase on the device.
+//
+// Replaces starky 1.0.0 proof.rs `StarkOpeningSet::new` and plonky2 1.0.0 fri/oracle.rs `PolynomialBatch::prove_openings`
+// + fri/prover.rs `fri_committed_trees` / `fri_proof_of_work` / `fri_prover_query_rounds`, reached from
+// /root/reference/evm_arithmetization/src/prover.rs:322-334 through prove_with_commitment.
+//
+// Differences in HOW (results are identical, the arithmetic is exact):
+//  * openings: every coefficient column is read once; zeta, g*zeta and 1 are evaluated in the same pass
+//    (thread t takes coefficients t, t+T, ... of a segment: Horner in zeta^T, then a block reduction).
+//  * batch reduction: the reference combines coefficient vectors (sum_j alpha^j f_j), runs synthetic division by
+//    (X - z) per batch and then a size-2n coset FFT.  Here the same polynomial's VALUES on the coset are produced
+//    directly from the LDE columns that are already resident: v(x) = sum_b alpha^(..) (sum_j alpha^j f_j(x) - sum_j alpha^j
+//    f_j(z_b)) / (x - z_b), one streaming pass, no scan; its coefficients come from one small inverse NTT.
+//  * proof of work: grid search with atomicMin -> the smallest valid witness (the reference's rayon find_any
+//    returns an arbitrary one; zkgpu_prove_table accepts a forced witness to reproduce a given proof).
+#include "stark_dev.h"
+#include "poseidon.cuh"
+
+namespace zk {
+
+// ---- openings ---------------------------------------------------------------------------------------------------
+static constexpr int EVAL_THREADS = 256;
+static constexpr size_t EVAL_SEG = (size_t)1 << 14;
+
+__device__ __forceinline__ Fp2 fp2_mul_base(Fp2 x, uint64_t s) { return Fp2(gl_mul(x.a, s), gl_mul(x.b, s)); }
+
+__global__ void __launch_bounds__(EVAL_THREADS) eval_columns_kernel(const uint64_t* __restrict__ coeffs, size_t n, size_t seg_len, Fp2 zeta,
+                                                                    Fp2 zeta_next, uint64_t* __restrict__ partial, size_t nseg) {
+    __shared__ uint64_t sm[5][EVAL_THREADS];
+    const size_t col = blockIdx.y, seg = blockIdx.x;
+    const uint64_t* p = coeffs + col * n + seg * seg_len;
+    const unsigned t = threadIdx.x;
+    // thread t: sum_k c[t + kT] (z^T)^k, then * z^(seg*seg_len + t)
+    Fp2 acc0(0, 0), acc1(0, 0);
+    uint64_t acc2 = 0;
+    if (t < seg_len) {
+        const Fp2 zT = fp2_pow(zeta, EVAL_THREADS), znT = fp2_pow(zeta_next, EVAL_THREADS);
+        size_t kmax = (seg_len - t + EVAL_THREADS - 1) / EVAL_THREADS;
+        for (size_t k = kmax; k-- > 0;) {
+            uint64_t cval = p[t + k * EVAL_THREADS];
+            acc0 = acc0 * zT; acc0.a = gl_add(acc0.a, cval);
+            acc1 = acc1 * znT; acc1.a = gl_add(acc1.a, cval);
+            acc2 = gl_add(acc2, cval);
+        }
+        uint64_t e = seg * seg_len + t;
+        acc0 = acc0 * fp2_pow(zeta, e);
+        acc1 = acc1 * fp2_pow(zeta_next, e);
+    }
+    sm[0][t] = acc0.a; sm[1][t] = acc0.b; sm[2][t] = acc1.a; sm[3][t] = acc1.b; sm[4][t] = acc2;
+    __syncthreads();
+    for (int off = EVAL_THREADS / 2; off > 0; off >>= 1) {
+        if (t < off)
+#pragma unroll
+            for (int q = 0; q < 5; q++) sm[q][t] = gl_add(sm[q][t], sm[q][t + off]);
+        __syncthreads();
+    }
+    if (t < 5) partial[(col * nseg + seg) * 5 + t] = sm[t][0];
+}
+
+void eval_columns(Ctx& c, const uint64_t* coeffs, size_t ncols, size_t n, Fp2 zeta, Fp2 zeta_next, std::vector<uint64_t>& out5) {
+    out5.assign(ncols * 5, 0);
+    if (!ncols) return;
+    size_t seg_len = n < EVAL_SEG ? n : EVAL_SEG;
+    size_t nseg = n / seg_len;
+    DevBuf partial(&c, ncols * nseg * 5 * 8);
+    for (size_t c0 = 0; c0 < ncols; c0 += 65535) {
+        unsigned cnt = (unsigned)std::min<size_t>(65535, ncols - c0);
+        dim3 grid((unsigned)nseg, cnt);
+        eval_columns_kernel<<<grid, EVAL_THREADS, 0, c.stream>>>(coeffs + c0 * n, n, seg_len, zeta, zeta_next,
+                                                                 partial.get() + c0 * nseg * 5, nseg);
+        c.count_launch();
+    }
+    c.check_launch("eval_columns_kernel");
+    std::vector<uint64_t> h(ncols * nseg * 5);
+    c.d2h(h.data(), partial.get(), h.size() * 8);
+    for (size_t col = 0; col < ncols; col++)
+        for (size_t s = 0; s < nseg; s++)
+            for (int q = 0; q < 5; q++) out5[col * 5 + q] = gl_add(out5[col * 5 + q], h[(col * nseg + s) * 5 + q]);
+}
+
+// ---- batch reduction straight to coset values --------------------------------------------------------------------
+struct CombineKernelArgs {
+    const uint64_t* lde[3];
+    uint32_t ncols[3];
+    uint32_t zs_begin;
+    uint32_t log_N;
+    const uint64_t* apow;     // alpha^j as (a, b) pairs, j < ncols[0]+ncols[1]+ncols[2]
+    Fp2 zeta, zeta_next, v0, v1, v2;
+    Fp2 shift1, shift2;       // alpha^(#polys of batch 1), alpha^(#polys of batch 2)
+    uint64_t w_N;
+    int has_b2;
+    uint64_t* out_re; uint64_t* out_im;
+};
+
+__global__ void __launch_bounds__(256) fri_combine_kernel(CombineKernelArgs a) {
+    const size_t N = (size_t)1 << a.log_N;
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const uint32_t i = bitrev32((uint32_t)j, a.log_N);
+    const uint64_t x = gl_mul(GL_GENERATOR, gl_pow(a.w_N, i));
+    Fp2 s_ta(0, 0), s_q(0, 0), s_z(0, 0);
+    uint32_t k = 0;
+    for (uint32_t c = 0; c < a.ncols[0]; c++, k++) {
+        uint64_t v = __ldg(a.lde[0] + (size_t)c * N + j);
+        s_ta = s_ta + fp2_mul_base(Fp2(a.apow[2 * k], a.apow[2 * k + 1]), v);
+    }
+    for (uint32_t c = 0; c < a.ncols[1]; c++, k++) {
+        uint64_t v = __ldg(a.lde[1] + (size_t)c * N + j);
+        s_ta = s_ta + fp2_mul_base(Fp2(a.apow[2 * k], a.apow[2 * k + 1]), v);
+        if (c >= a.zs_begin) { uint32_t kz = c - a.zs_begin; s_z = s_z + fp2_mul_base(Fp2(a.apow[2 * kz], a.apow[2 * kz + 1]), v); }
+    }
+    for (uint32_t c = 0; c < a.ncols[2]; c++, k++) {
+        uint64_t v = __ldg(a.lde[2] + (size_t)c * N + j);
+        s_q = s_q + fp2_mul_base(Fp2(a.apow[2 * k], a.apow[2 * k + 1]), v);
+    }
+    const Fp2 xe(x, 0);
+    Fp2 q0 = (s_ta + s_q - a.v0) * fp2_inv(xe - a.zeta);
+    Fp2 q1 = (s_ta - a.v1) * fp2_inv(xe - a.zeta_next);
+    Fp2 fin = q0 * a.shift1 + q1;
+    if (a.has_b2) {
+        Fp2 q2 = fp2_mul_base(s_z - a.v2, gl_inv(gl_sub(x, 1)));
+        fin = fin * a.shift2 + q2;
+    }
+    a.out_re[j] = fin.a;
+    a.out_im[j] = fin.b;
+}
+
+void fri_combine(Ctx& c, const CombineArgs& a) {
+    size_t total = a.ncols[0] + a.ncols[1] + a.ncols[2];
+    std::vector<uint64_t> apow(2 * total);
+    Fp2 p(1, 0);
+    for (size_t k = 0; k < total; k++) { apow[2 * k] = p.a; apow[2 * k + 1] = p.b; p = p * a.alpha; }
+    DevBuf dap(&c, apow.size() * 8 + 16);
+    c.h2d(dap.get(), apow.data(), apow.size() * 8);
+    CombineKernelArgs k;
+    for (int o = 0; o < 3; o++) { k.lde[o] = a.lde[o]; k.ncols[o] = (uint32_t)a.ncols[o]; }
+    k.zs_begin = (uint32_t)a.zs_begin; k.log_N = a.log_N; k.apow = dap.get();
+    k.zeta = a.zeta; k.zeta_next = a.zeta_next; k.v0 = a.v0; k.v1 = a.v1; k.v2 = a.v2;
+    k.shift1 = fp2_pow(a.alpha, a.ncols[0] + a.ncols[1]);
+    k.shift2 = fp2_pow(a.alpha, a.ncols[1] - a.zs_begin);
+    k.w_N = gl_root_of_unity(a.log_N);
+    k.has_b2 = a.has_b2 ? 1 : 0;
+    k.out_re = a.out_re; k.out_im = a.out_im;
+    size_t N = (size_t)1 << a.log_N;
+    fri_combine_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(k);
+    c.count_launch();
+    c.check_launch("fri_combine_kernel");
+    c.sync();
+}
+
+// ---- commit-phase layers -----------------------------------------------------------------------------------------
+__global__ void fri_leaves_kernel(const uint64_t* __restrict__ re, const uint64_t* __restrict__ im, size_t rows, unsigned arity_bits,
+                                  uint64_t* __restrict__ out) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t width = (size_t)2 << arity_bits;
+    if (idx >= rows * width) return;
+    size_t k = idx / rows, r = idx % rows;
+    const uint64_t* src = (k & 1) ? im : re;
+    out[idx] = src[(r << arity_bits) + (k >> 1)];
+}
+void fri_leaves(Ctx& c, const uint64_t* re, const uint64_t* im, size_t M, unsigned arity_bits, uint64_t* out) {
+    size_t rows = M >> arity_bits, total = rows * ((size_t)2 << arity_bits);
+    fri_leaves_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>(re, im, rows, arity_bits, out);
+    c.count_launch();
+    c.check_launch("fri_leaves_kernel");
+}
+
+__global__ void fri_fold_kernel(const uint64_t* __restrict__ re, const uint64_t* __restrict__ im, size_t out_len, unsigned arity_bits,
+                                Fp2 beta, uint64_t* __restrict__ out_re, uint64_t* __restrict__ out_im) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= out_len) return;
+    size_t arity = (size_t)1 << arity_bits;
+    Fp2 acc(0, 0);
+    for (size_t t = arity; t-- > 0;) acc = acc * beta + Fp2(re[i * arity + t], im[i * arity + t]);
+    out_re[i] = acc.a;
+    out_im[i] = acc.b;
+}
+void fri_fold(Ctx& c, const uint64_t* re, const uint64_t* im, size_t M, unsigned arity_bits, Fp2 beta, uint64_t* out_re,
+              uint64_t* out_im) {
+    size_t out_len = M >> arity_bits;
+    fri_fold_kernel<<<(unsigned)((out_len + 127) / 128), 128, 0, c.stream>>>(re, im, out_len, arity_bits, beta, out_re, out_im);
+    c.count_launch();
+    c.check_launch("fri_fold_kernel");
+}
+
+// ---- proof of work -------------------------------------------------------------------------------------------------
+struct PowState { uint64_t s[12]; };
+__global__ void __launch_bounds__(128) pow_kernel(PowState st, unsigned pos, unsigned bits, uint64_t base, unsigned long long* best) {
+    uint64_t cand = base + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cand >= GL_P) return;
+    uint64_t s[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = st.s[i];
+#pragma unroll
+    for (int i = 0; i < 12; i++) if (i == (int)pos) s[i] = cand;
+    poseidon_permute(s);
+    if (bits == 0 || (s[7] >> (64 - bits)) == 0) atomicMin(best, (unsigned long long)cand);
+}
+uint64_t pow_grind(Ctx& c, const uint64_t state[12], unsigned pos, unsigned bits) {
+    ZK_REQUIRE(pos < 8 && bits < 40, "pow_grind: bad arguments");
+    PowState st;
+    memcpy(st.s, state, 96);
+    DevBuf best(&c, 8);
+    unsigned long long init = ~0ULL;
+    c.h2d(best.get(), &init, 8);
+    const uint64_t batch = (uint64_t)1 << 20;
+    for (uint64_t base = 0;; base += batch) {
+        pow_kernel<<<(unsigned)(batch / 128), 128, 0, c.stream>>>(st, pos, bits, base, (unsigned long long*)best.get());
+        c.count_launch();
+        c.check_launch("pow_kernel");
+        unsigned long long r;
+        c.d2h(&r, best.get(), 8);
+        if (r != ~0ULL) return r;
+        if (base > ((uint64_t)1 << 44)) throw ZkError(ZKGPU_ERR_PROOF, "proof of work search exhausted");
+    }
+}
+
+// ---- gather ------------------------------------------------------------------------------------------------------
+__global__ void gather_kernel(const uint64_t* __restrict__ src, const uint64_t* __restrict__ offs, size_t cnt, uint64_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) out[i] = src[offs[i]];
+}
+void gather_words(Ctx& c, const uint64_t* src, const std::vector<uint64_t>& offsets, uint64_t* out_host) {
+    if (offsets.empty()) return;
+    DevBuf o(&c, offsets.size() * 8), d(&c, offsets.size() * 8);
+    c.h2d(o.get(), offsets.data(), offsets.size() * 8);
+    gather_kernel<<<(unsigned)((offsets.size() + 255) / 256), 256, 0, c.stream>>>(src, o.get(), offsets.size(), d.get());
+    c.count_launch();
+    c.check_launch("gather_kernel");
+    c.d2h(out_host, d.get(), offsets.size() * 8);
+}
+
+}  // namespace zk

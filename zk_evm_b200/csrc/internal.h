@@ -7,6 +7,7 @@
 #include <vector>
 #include <map>
 #include <stdexcept>
+#include <memory>
 #include "../../include/zkgpu.h"
 #include "gl.cuh"
 
@@ -57,6 +58,7 @@ static inline unsigned log2_exact(size_t n) {
 }
 
 struct Ctx;
+struct TableDev;
 
 // stream-ordered device buffer
 struct DevBuf {
@@ -87,6 +89,7 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaMemPool_t pool = nullptr;
     int num_sms = 148;
     uint64_t launches = 0;
@@ -94,6 +97,9 @@ struct Ctx {
     NttTables ntt;
     // cache: key -> device table (inter-pass twiddles, coset power tables, lagrange selectors ...)
     std::map<std::string, DevBuf> table_cache;
+    // per (table, num_challenges): lookup / CTL descriptors uploaded to the device (stark_dev.h)
+    std::map<uint32_t, std::shared_ptr<TableDev>> stark_tables;
+    bool debug = false;   // proofs keep their aux / quotient batches and FRI input values for stage-by-stage parity tests
     // pinned staging buffer for H2D / D2H of pageable memory
     void* staging = nullptr;
     size_t staging_bytes = 0;

@@ -6,6 +6,7 @@ numpy arrays stand in for Vec<PolynomialValues<F>>: shape (ncols, n), dtype uint
 columns of n canonical Goldilocks elements.
 """
 import ctypes as C
+import weakref
 import numpy as np
 from . import _lib
 from ._lib import u64p, check, lib
@@ -29,9 +30,12 @@ class Context:
         self._h = C.c_void_p()
         check(lib().zkgpu_ctx_create(int(device), C.byref(self._h)))
         self.device = device
+        self._children = weakref.WeakSet()   # device objects must be released before the context (its stream frees them)
 
     def close(self):
         if self._h:
+            for ch in list(self._children):
+                ch.free()
             lib().zkgpu_ctx_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -43,6 +47,14 @@ class Context:
 
     def sync(self):
         check(lib().zkgpu_ctx_sync(self._h))
+
+    def timer_start(self):
+        check(lib().zkgpu_ctx_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(lib().zkgpu_ctx_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     def stats(self):
         k, u, p = C.c_uint64(), C.c_uint64(), C.c_uint64()
@@ -88,9 +100,12 @@ class Context:
 class PolynomialBatch:
     """Device-resident PolynomialBatch (polynomials + Merkle tree of the blown-up evaluations)."""
 
-    def __init__(self, ctx, handle):
+    def __init__(self, ctx, handle, borrowed=False):
         self.ctx = ctx
         self._h = handle
+        self._borrowed = borrowed
+        if not borrowed:
+            ctx._children.add(self)
         nc, n, rb, ch = C.c_size_t(), C.c_size_t(), C.c_uint32(), C.c_uint32()
         check(lib().zkgpu_batch_dims(self._h, C.byref(nc), C.byref(n), C.byref(rb), C.byref(ch)))
         self.ncols, self.n, self.rate_bits, self.cap_height = nc.value, n.value, rb.value, ch.value
@@ -105,6 +120,15 @@ class PolynomialBatch:
         return cls(ctx, h)
 
     @classmethod
+    def from_device_values(cls, ctx, device_ptr, ncols, n, rate_bits=1, cap_height=4, keep_values=False):
+        """Same as from_values for a trace already resident in HBM: `device_ptr` is the address of ncols*n contiguous
+        column-major u64 (e.g. a torch.int64 CUDA tensor's data_ptr()); the data is copied device-to-device."""
+        h = C.c_void_p()
+        check(lib().zkgpu_commit_values_contig(ctx._h, C.cast(C.c_void_p(int(device_ptr)), u64p), C.c_size_t(ncols), C.c_size_t(n),
+                                               C.c_uint32(rate_bits), C.c_uint32(cap_height), 1, int(keep_values), C.byref(h)))
+        return cls(ctx, h)
+
+    @classmethod
     def from_coeffs(cls, ctx, coeffs, rate_bits=1, cap_height=4):
         a = _as_cols(coeffs)
         ptrs = (u64p * a.shape[0])(*[a[i].ctypes.data_as(u64p) for i in range(a.shape[0])])
@@ -115,7 +139,8 @@ class PolynomialBatch:
 
     def free(self):
         if self._h:
-            lib().zkgpu_batch_free(self._h)
+            if not self._borrowed:
+                lib().zkgpu_batch_free(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -140,3 +165,94 @@ class PolynomialBatch:
         check(lib().zkgpu_batch_export(self._h, _ptr(co) if coeffs else None, _ptr(le) if leaves else None,
                                        _ptr(di) if digests else None))
         return co, le, di
+
+
+class CtlData:
+    """Device-resident CtlData of one table (the per-table slice of starky get_ctl_data, prover.rs:137-143)."""
+
+    def __init__(self, ctx, handle, table, n, num_challenges):
+        self.ctx, self._h, self.table, self.n, self.num_challenges = ctx, handle, table, n, num_challenges
+        ctx._children.add(self)
+
+    def export(self):
+        info = table_info(self.table, self.num_challenges)
+        k = info["num_ctl_helper_columns"] + info["num_ctl_zs"]
+        out = np.empty((k, self.n), dtype=np.uint64)
+        if k:
+            check(lib().zkgpu_ctl_export(self._h, _ptr(out)))
+        return out
+
+    def free(self):
+        if self._h:
+            lib().zkgpu_ctl_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class StarkProof:
+    """StarkProofWithMetadata of one table; `words` is the canonical serialisation (csrc/stark/proof.h)."""
+
+    def __init__(self, ctx, handle):
+        self._h = handle
+        ctx._children.add(self)
+        n = C.c_size_t(0)
+        check(lib().zkgpu_proof_serialize(self._h, None, C.byref(n)))
+        self.words = np.empty(n.value, dtype=np.uint64)
+        check(lib().zkgpu_proof_serialize(self._h, _ptr(self.words), C.byref(n)))
+
+    def debug_batch(self, ctx, which):
+        h = C.c_void_p()
+        check(lib().zkgpu_proof_debug_batch(self._h, int(which), C.byref(h)))
+        return PolynomialBatch(ctx, h, borrowed=True)
+
+    def debug_fri_values(self):
+        n = C.c_size_t(0)
+        check(lib().zkgpu_proof_debug_fri_values(self._h, None, C.byref(n)))
+        out = np.empty(n.value, dtype=np.uint64)
+        check(lib().zkgpu_proof_debug_fri_values(self._h, _ptr(out), C.byref(n)))
+        return out.reshape(-1, 2)
+
+    def free(self):
+        if self._h:
+            lib().zkgpu_proof_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def table_info(table, num_challenges):
+    a, b, c_, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    check(lib().zkgpu_table_info(C.c_uint32(table), C.c_uint32(num_challenges), C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
+    return {"num_columns": a.value, "num_lookup_columns": b.value, "num_ctl_helper_columns": c_.value, "num_ctl_zs": d.value}
+
+
+def get_ctl_data(ctx, table, trace_batch, beta_gamma, num_challenges):
+    bg = np.ascontiguousarray(beta_gamma, dtype=np.uint64)
+    h = C.c_void_p()
+    check(lib().zkgpu_ctl_data(ctx._h, C.c_uint32(table), trace_batch._h, _ptr(bg), C.c_uint32(num_challenges), C.byref(h)))
+    return CtlData(ctx, h, table, trace_batch.n, num_challenges)
+
+
+def prove_single_table(ctx, table, config, trace_batch, ctl_data, challenger_state, labels=None, forced_pow_witness=None,
+                       abort_flag=None):
+    """prover.rs:301-341.  Returns (StarkProof, challenger state after the proof)."""
+    st = np.ascontiguousarray(challenger_state, dtype=np.uint64).copy()
+    h = C.c_void_p()
+    fp = C.c_uint64(forced_pow_witness) if forced_pow_witness is not None else None
+    check(lib().zkgpu_prove_table(ctx._h, C.c_uint32(table), C.byref(labels) if labels is not None else None, C.byref(config),
+                                  trace_batch._h, ctl_data._h, _ptr(st), C.byref(fp) if fp is not None else None,
+                                  C.byref(abort_flag) if abort_flag is not None else None, C.byref(h)))
+    return StarkProof(ctx, h), st
+
+
+def set_debug(ctx, on=True):
+    check(lib().zkgpu_ctx_set_debug(ctx._h, int(bool(on))))
