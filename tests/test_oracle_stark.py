@@ -55,3 +55,54 @@ def test_forced_pow_witness(oracle):
     assert np.array_equal(proof, proof2) and np.array_equal(st, st2)
     with pytest.raises(RuntimeError):
         orc_prove_table(oracle, traces.T_MEM_AFTER, STANDARD_FAST, tr, BG2, STATE0, forced_pow=w + 1 if w + 1 != 0 else 2)
+
+
+# ---- the remaining tables: valid traces from restated generators must satisfy the transcribed constraints --------------------
+def test_keccak_generator_is_keccak_f():
+    """the trace generator's permutation output equals Keccak-f[1600] (checked through hashlib's SHA3-256 of b'')"""
+    import hashlib
+    block = bytearray(200)
+    block[0] = 0x06
+    block[135] |= 0x80
+    lanes = np.frombuffer(bytes(block), dtype="<u8").reshape(1, 25)
+    _, out = traces.keccak_trace(5, lanes)
+    assert out[0, :4].astype("<u8").tobytes() == hashlib.sha3_256(b"").digest()
+
+
+@pytest.mark.parametrize("table,lg,cfg", [
+    (traces.T_CPU, 6, TEST_CONFIG), (traces.T_CPU, 9, STANDARD_FAST),
+    (traces.T_KECCAK, 5, TEST_CONFIG), (traces.T_KECCAK, 7, STANDARD_FAST),
+    (traces.T_BYTE_PACKING, 8, TEST_CONFIG), (traces.T_BYTE_PACKING, 9, STANDARD_FAST),
+    (traces.T_ARITHMETIC, 16, TEST_CONFIG),
+])
+def test_prove_then_verify_more_tables(oracle, table, lg, cfg):
+    rng = np.random.default_rng(lg)
+    if table == traces.T_CPU:
+        tr = traces.cpu_padding_trace(lg)
+    elif table == traces.T_KECCAK:
+        nperm = (1 << lg) // 24 - (1 if lg == 7 else 0)      # leave padding rows in one case
+        tr, _ = traces.keccak_trace(lg, rng.integers(0, 2 ** 63, size=(max(nperm, 1), 25), dtype=np.uint64))
+    elif table == traces.T_BYTE_PACKING:
+        tr = traces.byte_packing_trace(lg, 5)
+    else:
+        tr = traces.arithmetic_addcy_trace(lg, 6)
+    bg = BG2[:2 * cfg[1]]
+    proof, st = orc_prove_table(oracle, table, cfg, tr, bg, STATE0)
+    ok, err, st2 = orc_verify_table(oracle, table, cfg, proof, bg, STATE0)
+    assert ok, err
+    assert np.array_equal(st, st2)
+
+
+@pytest.mark.parametrize("table", [traces.T_KECCAK, traces.T_BYTE_PACKING])
+def test_corrupted_valid_trace_is_rejected(oracle, table):
+    rng = np.random.default_rng(1)
+    if table == traces.T_KECCAK:
+        tr, _ = traces.keccak_trace(5, rng.integers(0, 2 ** 63, size=(1, 25), dtype=np.uint64))
+        tr[traces.K_START_A_PP + 3, 5] ^= np.uint64(4)
+    else:
+        tr = traces.byte_packing_trace(8, 2)
+        tr[37 + 31, 0] = 9 if tr[1 + 31, 0] == 0 else tr[37 + 31, 0]     # a byte past the sequence length
+        tr[1, 3] = 2                                                      # non-boolean index flag
+    proof, _ = orc_prove_table(oracle, table, TEST_CONFIG, tr, BG2[:2], STATE0)
+    ok, err, _ = orc_verify_table(oracle, table, TEST_CONFIG, proof, BG2[:2], STATE0)
+    assert not ok

@@ -58,3 +58,148 @@ def memory_trace_simple(log_n):
     t[28] = np.arange(n, dtype=np.uint64)      # counter
     t[29, 0] = n                               # frequencies: range_check == 0 on every row
     return t
+
+
+# ---- CpuStark: all-padding trace (generation/mod.rs:646-663; halt.rs:16-52) ----------------------------------------------
+def cpu_padding_trace(log_n, halt_final=0x1234):
+    n = 1 << log_n
+    t = np.zeros((85, n), dtype=np.uint64)
+    t[2] = halt_final                                  # program_counter
+    t[3] = 7                                           # stack_len (constant)
+    t[4] = 1                                           # is_kernel_mode
+    t[5] = 1000                                        # gas (constant)
+    t[40] = np.arange(1, n + 1, dtype=np.uint64)       # clock starts at 1
+    return t
+
+
+# ---- KeccakStark (keccak_stark.rs:70-250) ---------------------------------------------------------------------------------
+KECCAK_RC = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B,
+             0x0000000080000001, 0x8000000080008081, 0x8000000000008009, 0x000000000000008A, 0x0000000000000088,
+             0x0000000080008009, 0x000000008000000A, 0x000000008000808B, 0x800000000000008B, 0x8000000000008089,
+             0x8000000000008003, 0x8000000000008002, 0x8000000000000080, 0x000000000000800A, 0x800000008000000A,
+             0x8000000080008081, 0x8000000000008080, 0x0000000080000001, 0x8000000080008008]
+KECCAK_R = [[0, 36, 3, 41, 18], [1, 44, 10, 45, 2], [62, 6, 43, 15, 61], [28, 55, 25, 21, 56], [27, 20, 39, 8, 14]]
+K_TIMESTAMP, K_START_A = 24, 25
+K_START_C = K_START_A + 50
+K_START_C_PRIME = K_START_C + 320
+K_START_A_PRIME = K_START_C_PRIME + 320
+K_START_A_PP = K_START_A_PRIME + 1600
+K_START_A_PP_BITS = K_START_A_PP + 50
+K_A_PPP_00_LO = K_START_A_PP_BITS + 64
+
+
+def _rotl(x, r):
+    r %= 64
+    if r == 0:
+        return x
+    return ((x << np.uint64(r)) | (x >> np.uint64(64 - r)))
+
+
+def _bits(x):
+    """(64, nperm) array of the bits of a uint64 vector"""
+    return ((x[None, :] >> np.arange(64, dtype=np.uint64)[:, None]) & np.uint64(1)).astype(np.uint64)
+
+
+def keccak_trace(log_n, inputs, timestamps=None):
+    """inputs: (nperm, 25) uint64, lane i = y*5 + x.  Returns (trace (2431, n), outputs (nperm, 25))."""
+    inputs = np.ascontiguousarray(inputs, dtype=np.uint64)
+    nperm = inputs.shape[0]
+    n = 1 << log_n
+    assert nperm * 24 <= n
+    t = np.zeros((2431, n), dtype=np.uint64)
+    if timestamps is None:
+        timestamps = np.arange(1, nperm + 1, dtype=np.uint64) * np.uint64(7)
+    A = [[inputs[:, y * 5 + x].copy() for y in range(5)] for x in range(5)]
+    M32 = np.uint64(0xFFFFFFFF)
+    S32 = np.uint64(32)
+    for rnd in range(24):
+        rows = np.arange(nperm) * 24 + rnd
+        t[rnd, rows] = 1
+        t[K_TIMESTAMP, rows] = timestamps
+        for x in range(5):
+            for y in range(5):
+                t[K_START_A + (x * 5 + y) * 2, rows] = A[x][y] & M32
+                t[K_START_A + (x * 5 + y) * 2 + 1, rows] = A[x][y] >> S32
+        C = [A[x][0] ^ A[x][1] ^ A[x][2] ^ A[x][3] ^ A[x][4] for x in range(5)]
+        Cp = [C[x] ^ C[(x + 4) % 5] ^ _rotl(C[(x + 1) % 5], 1) for x in range(5)]
+        for x in range(5):
+            t[K_START_C + 64 * x:K_START_C + 64 * x + 64, rows] = _bits(C[x])
+            t[K_START_C_PRIME + 64 * x:K_START_C_PRIME + 64 * x + 64, rows] = _bits(Cp[x])
+        Ap = [[A[x][y] ^ C[x] ^ Cp[x] for y in range(5)] for x in range(5)]
+        for x in range(5):
+            for y in range(5):
+                o = K_START_A_PRIME + x * 320 + y * 64
+                t[o:o + 64, rows] = _bits(Ap[x][y])
+        B = [[_rotl(Ap[(x + 3 * y) % 5][x], KECCAK_R[(x + 3 * y) % 5][x]) for y in range(5)] for x in range(5)]
+        App = [[B[x][y] ^ (~B[(x + 1) % 5][y] & B[(x + 2) % 5][y]) for y in range(5)] for x in range(5)]
+        for x in range(5):
+            for y in range(5):
+                t[K_START_A_PP + x * 10 + y * 2, rows] = App[x][y] & M32
+                t[K_START_A_PP + x * 10 + y * 2 + 1, rows] = App[x][y] >> S32
+        t[K_START_A_PP_BITS:K_START_A_PP_BITS + 64, rows] = _bits(App[0][0])
+        a000 = App[0][0] ^ np.uint64(KECCAK_RC[rnd])
+        t[K_A_PPP_00_LO, rows] = a000 & M32
+        t[K_A_PPP_00_LO + 1, rows] = a000 >> S32
+        App[0][0] = a000
+        A = App
+    out = np.stack([A[i % 5][i // 5] for i in range(25)], axis=1)
+    return t, out
+
+
+# ---- BytePackingStark (byte_packing_stark.rs:193-280) ------------------------------------------------------------------------
+def byte_packing_trace(log_n, seed, fill=0.6):
+    rng = np.random.default_rng(seed)
+    n = 1 << log_n
+    assert n >= 256
+    t = np.zeros((71, n), dtype=np.uint64)
+    nops = max(1, int(n * fill))
+    lens = rng.integers(1, 33, size=nops)
+    t[0, :nops] = rng.integers(0, 2, size=nops)                 # is_read
+    t[1 + (lens - 1), np.arange(nops)] = 1                      # index_len[len-1]
+    t[33, :nops] = rng.integers(0, 100, size=nops)              # addr_context
+    t[34, :nops] = rng.integers(0, 30, size=nops)               # addr_segment
+    t[35, :nops] = rng.integers(0, 1 << 20, size=nops)          # addr_virtual
+    t[36, :nops] = rng.integers(1, 1 << 20, size=nops)          # timestamp
+    byts = rng.integers(0, 256, size=(32, nops), dtype=np.uint64)
+    byts[np.arange(32)[:, None] >= lens[None, :]] = 0           # bytes past the length are zero
+    t[37:69, :nops] = byts
+    t[69] = np.minimum(np.arange(n), 255).astype(np.uint64)     # range_counter
+    t[70, :256] = np.bincount(t[37:69].astype(np.int64).ravel(), minlength=256).astype(np.uint64)
+    return t
+
+
+# ---- ArithmeticStark: ADD / SUB / LT / GT rows (addcy.rs:24-60) + range-check columns (arithmetic_stark.rs:130-156) -------------
+def _limbs16(vals):
+    """list of python ints (< 2^256) -> (16, len) uint64 of 16-bit limbs"""
+    return np.array([[(v >> (16 * i)) & 0xFFFF for v in vals] for i in range(16)], dtype=np.uint64)
+
+
+def arithmetic_addcy_trace(log_n, seed, nops=1000):
+    rng = np.random.default_rng(seed)
+    n = 1 << log_n
+    assert n >= 1 << 16
+    t = np.zeros((116, n), dtype=np.uint64)
+    ops = rng.integers(0, 4, size=nops)           # 0 add, 1 sub, 2 lt, 3 gt
+    a = [int.from_bytes(rng.bytes(32), "little") for _ in range(nops)]
+    b = [int.from_bytes(rng.bytes(32), "little") for _ in range(nops)]
+    M = 1 << 256
+    out, aux = [], []
+    for k in range(nops):
+        if ops[k] == 0:
+            s = a[k] + b[k]; out.append(s % M); aux.append(s >> 256)                 # in0 + in1 = out + cy 2^256
+        elif ops[k] == 1:
+            d = a[k] - b[k]; out.append(d % M); aux.append(1 if d < 0 else 0)        # in1 + out = in0 + cy 2^256
+        elif ops[k] == 2:
+            d = a[k] - b[k]; aux.append(d % M); out.append(1 if d < 0 else 0)        # in1 + aux = in0 + out 2^256
+        else:
+            d = b[k] - a[k]; aux.append(d % M); out.append(1 if d < 0 else 0)        # in0 + aux = in1 + out 2^256
+    flag_col = {0: 0, 1: 2, 2: 11, 3: 12}
+    for k in range(nops):
+        t[flag_col[int(ops[k])], k] = 1
+    t[18:34, :nops] = _limbs16(a)
+    t[34:50, :nops] = _limbs16(b)
+    t[66:82, :nops] = _limbs16(out)
+    t[82:98, :nops] = _limbs16(aux)
+    t[114] = np.minimum(np.arange(n), 65535).astype(np.uint64)
+    t[115, :65536] = np.bincount(t[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
+    return t
