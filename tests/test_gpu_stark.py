@@ -34,6 +34,16 @@ def _valid_trace(table, lg, seed):
         return traces.logic_trace(lg, seed)
     if table == traces.T_MEMORY:
         return traces.memory_trace_simple(lg)
+    if table == traces.T_CPU:
+        return traces.cpu_padding_trace(lg, halt_final=DEFAULT_LABELS[0])
+    if table == traces.T_KECCAK:
+        rng = np.random.default_rng(seed)
+        nperm = max(1, (1 << lg) // 24 - 1)
+        return traces.keccak_trace(lg, rng.integers(0, 2 ** 63, size=(nperm, 25), dtype=np.uint64))[0]
+    if table == traces.T_BYTE_PACKING:
+        return traces.byte_packing_trace(lg, seed)
+    if table == traces.T_ARITHMETIC:
+        return traces.arithmetic_addcy_trace(lg, seed)
     raise ValueError(table)
 
 
@@ -42,6 +52,12 @@ CASES = [
     (traces.T_MEM_BEFORE, 10, STANDARD_FAST, "random"),
     (traces.T_LOGIC, 6, TEST_CONFIG, "valid"), (traces.T_LOGIC, 9, STANDARD_FAST, "random"),
     (traces.T_MEMORY, 4, TEST_CONFIG, "valid"), (traces.T_MEMORY, 8, STANDARD_FAST, "valid"), (traces.T_MEMORY, 12, STANDARD_FAST, "random"),
+    (traces.T_CPU, 6, TEST_CONFIG, "valid"), (traces.T_CPU, 10, STANDARD_FAST, "valid"), (traces.T_CPU, 9, STANDARD_FAST, "random"),
+    (traces.T_KECCAK, 5, TEST_CONFIG, "valid"), (traces.T_KECCAK, 7, STANDARD_FAST, "valid"), (traces.T_KECCAK, 6, STANDARD_FAST, "random"),
+    (traces.T_BYTE_PACKING, 8, TEST_CONFIG, "valid"), (traces.T_BYTE_PACKING, 9, STANDARD_FAST, "valid"),
+    (traces.T_BYTE_PACKING, 8, STANDARD_FAST, "random"),
+    (traces.T_ARITHMETIC, 16, TEST_CONFIG, "valid"), (traces.T_ARITHMETIC, 8, STANDARD_FAST, "random"),
+    (traces.T_KECCAK_SPONGE, 8, STANDARD_FAST, "random"), (traces.T_KECCAK_SPONGE, 5, TEST_CONFIG, "random"),
 ]
 
 
