@@ -173,7 +173,7 @@ def run_ours(args):
                 "note": "Poseidon is integer-ALU bound (~2e4 int ops per 64 B); HBM fraction reported because the metric asks for it",
                 "ntt": {"kernel": "ntt_dif_pass_kernel size-n batch of %d cols" % ncols, "achieved": 16.0 * ncols * n / ntt_ms / 1e6,
                         "frac": 16.0 * ncols * n / ntt_ms / 1e6 / peak, "unit": "GB/s"}}
-        cpu = cpu_baseline(table, args, full_log_n=log_n)
+        cpu = None if args.no_cpu_baseline else cpu_baseline(table, args, full_log_n=log_n)
         line = {"metric": METRIC, "value": world * args.steps / (ms / 1e3), "unit": "proofs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks, exact)", "data": "synthetic",
@@ -261,6 +261,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=20, help="log2 of the trace length (BASELINE config #2: 20)")
     ap.add_argument("--table", type=int, default=None, help="table id (default: CpuStark)")
     ap.add_argument("--cpu-sample-log-n", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiler runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -137,6 +137,52 @@ void zkgpu_proof_free(zkgpu_proof* proof);
  * of buf, out: words needed; buf may be NULL to query the size. */
 int zkgpu_proof_serialize(const zkgpu_proof* proof, uint64_t* buf, size_t* len_words);
 
+/* ---- the shared Fiat-Shamir transcript: plonky2 Challenger<F, PoseidonHash> (prover.rs:118-144, 320) --------------------------- */
+/* Host-side and tiny (a Poseidon permutation every 8 elements); exposed so a host without plonky2 (the Python mirror, a C++
+ * harness) can replay prove_with_traces' transcript.  A Rust host keeps using plonky2's own Challenger and only passes the
+ * 12-word state across the boundary. */
+typedef struct zkgpu_challenger zkgpu_challenger;
+int zkgpu_challenger_new(zkgpu_challenger** out);
+void zkgpu_challenger_free(zkgpu_challenger* ch);
+int zkgpu_challenger_observe(zkgpu_challenger* ch, const uint64_t* elements, size_t n);        /* observe_elements */
+int zkgpu_challenger_get_challenges(zkgpu_challenger* ch, uint64_t* out, size_t n);            /* get_n_challenges */
+int zkgpu_challenger_compact(zkgpu_challenger* ch, uint64_t state_out[12]);                    /* compact() */
+int zkgpu_challenger_set_state(zkgpu_challenger* ch, const uint64_t state[12]);
+/* prover.rs:118-144 in one call: observe the 9 trace caps in Table order (trace_caps = 9 x (4 << cap_height) words; an optional
+ * table with table_in_use[t] == 0 contributes a zero cap, prover.rs:120-123), observe the flattened public values
+ * (get_challenges.rs:202-227), draw (beta, gamma) x num_challenges into beta_gamma, return the compacted state the first
+ * prove_single_table starts from. */
+int zkgpu_segment_challenges(const uint64_t* trace_caps, const uint8_t* table_in_use, uint32_t cap_height, const uint64_t* public_values,
+                             size_t n_public_values, uint32_t num_challenges, uint64_t* beta_gamma, uint64_t challenger_state[12]);
+
+/* ---- prove_single_table split where the shared transcript is first needed (table-sharded multi-GPU runs) -------------------- */
+/* begin: auxiliary polynomials (logUp columns ++ CTL helpers ++ CTL Zs) and their commitment — depends only on the trace and the
+ * CTL challenges; finish: everything that consumes the transcript (alphas, quotient, zeta, openings, FRI, PoW, queries).
+ * zkgpu_prove_table == begin + finish.  trace and ctl must outlive the job. */
+typedef struct zkgpu_table_job zkgpu_table_job;
+int zkgpu_table_job_begin(zkgpu_ctx* ctx, uint32_t table_id, const zkgpu_kernel_labels* labels, const zkgpu_stark_config* config,
+                          const zkgpu_batch* trace, const zkgpu_ctl* ctl, volatile const int* abort_flag, zkgpu_table_job** out);
+int zkgpu_table_job_aux_cap(const zkgpu_table_job* job, uint64_t* out_cap, size_t* len_words);
+int zkgpu_table_job_finish(zkgpu_table_job* job, uint64_t challenger_state[12], const uint64_t* forced_pow_witness,
+                           volatile const int* abort_flag, zkgpu_proof** out);
+void zkgpu_table_job_free(zkgpu_table_job* job);
+
+/* ---- top: prove_with_traces (prover.rs:72-194) on one device ------------------------------------------------------------------ */
+/* traces[t]: the trace of table t as one contiguous column-major block (column c at cols + c*n), or cols == NULL for an optional
+ * table that is not in use (table_in_use[t] == false: zero cap observed, proof None -> proofs_out[t] == NULL).
+ * public_values: the elements observe_public_values feeds the challenger, in order (the host flattens PublicValues).
+ * forced_pow_witnesses: NULL, or 9 witnesses (entries of unused tables ignored).  ctl_challenges_out (nullable):
+ * [beta_0, gamma_0, beta_1, gamma_1].  trace_caps_out (nullable): 9 x (4 << cap_height) words (MemBefore / MemAfter caps
+ * become PublicValues.mem_before / mem_after, prover.rs:261-271). */
+typedef struct {
+    const uint64_t* cols;
+    size_t n;
+} zkgpu_table_trace;
+int zkgpu_prove_segment(zkgpu_ctx* ctx, const zkgpu_table_trace* traces /*[ZKGPU_NUM_TABLES]*/, int mem_kind, const uint64_t* public_values,
+                        size_t n_public_values, const zkgpu_kernel_labels* labels, const zkgpu_stark_config* config,
+                        const uint64_t* forced_pow_witnesses, volatile const int* abort_flag, zkgpu_proof** proofs_out /*[ZKGPU_NUM_TABLES]*/,
+                        uint64_t* ctl_challenges_out, uint64_t* trace_caps_out);
+
 /* ---- stage-by-stage parity hooks (tests) ---------------------------------------------------------------------- */
 /* when on, proofs retain their auxiliary / quotient PolynomialBatch and the FRI input values */
 int zkgpu_ctx_set_debug(zkgpu_ctx* ctx, int on);

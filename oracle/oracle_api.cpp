@@ -173,3 +173,119 @@ int orc_verify_table(uint32_t table, const uint32_t cfgw[8], const uint64_t* pro
 }
 
 }  // extern "C"
+
+// ---- whole-segment prover / verifier: prove_with_traces (prover.rs:72-194) and verify_proof (verifier.rs:172-313) ------------
+static void segment_transcript(Challenger& ch, const std::vector<Words>& caps, const uint8_t in_use[9], size_t cap_words,
+                               const uint64_t* pv, size_t npv, unsigned nch, std::vector<uint64_t>& betas, std::vector<uint64_t>& gammas) {
+    for (uint32_t t = 0; t < zkstark::NUM_TABLES; t++) {
+        if (!in_use[t]) {
+            if (!zkstark::table_is_optional(t)) throw std::runtime_error("only optional tables may be left out");
+            for (size_t i = 0; i < cap_words; i++) ch.observe(0);      // zero cap, prover.rs:120-123
+        } else ch.observe_n(caps[t].data(), cap_words);
+    }
+    ch.observe_n(pv, npv);                                             // observe_public_values, flattened by the caller
+    for (unsigned i = 0; i < nch; i++) { betas.push_back(ch.challenge()); gammas.push_back(ch.challenge()); }
+}
+
+extern "C" {
+
+// traces[t]: ncols(t)*n[t] column-major, or null (table not in use).  Proof words of table t are written at
+// out[offsets[t] .. offsets[t+1]) (empty for unused tables).  Returns total words (needed if > out_cap), negative on failure.
+long orc_prove_segment(const uint32_t cfgw[8], const uint64_t* const* traces, const size_t* ns, const uint64_t* public_values, size_t npv,
+                       const uint64_t labels[4], const uint64_t* forced_pows, uint64_t* out, size_t out_cap, size_t offsets[10],
+                       uint64_t* beta_gamma_out, uint64_t* caps_out) {
+    try {
+        Config cfg = cfg_from(cfgw);
+        const size_t capw = (size_t)4 << cfg.cap_height;
+        auto ctls = zkstark::all_cross_table_lookups();
+        uint8_t in_use[9];
+        std::vector<std::vector<const uint64_t*>> cols(9);
+        std::vector<PolyBatch> commits(9);
+        std::vector<Words> caps(9);
+        for (uint32_t t = 0; t < 9; t++) {
+            in_use[t] = traces[t] != nullptr;
+            if (!in_use[t]) { caps[t].assign(capw, 0); continue; }
+            size_t nc = zkstark::table_num_columns(t);
+            cols[t].resize(nc);
+            for (size_t c = 0; c < nc; c++) cols[t][c] = traces[t] + c * ns[t];
+            commits[t].from_values(cols[t].data(), nc, ns[t], cfg.rate_bits, cfg.cap_height);
+            caps[t] = cap_words(commits[t].tree);
+        }
+        if (caps_out) for (uint32_t t = 0; t < 9; t++) memcpy(caps_out + t * capw, caps[t].data(), capw * 8);
+        Challenger ch;
+        std::vector<uint64_t> betas, gammas;
+        segment_transcript(ch, caps, in_use, capw, public_values, npv, cfg.num_challenges, betas, gammas);
+        if (beta_gamma_out) for (unsigned i = 0; i < cfg.num_challenges; i++) { beta_gamma_out[2 * i] = betas[i]; beta_gamma_out[2 * i + 1] = gammas[i]; }
+        std::vector<Words> proofs(9);
+        for (uint32_t t = 0; t < 9; t++) {
+            if (!in_use[t]) continue;
+            CtlData ctl = ctl_data_for_table(t, cols[t].data(), ns[t], ctls, betas, gammas, zkstark::CONSTRAINT_DEGREE);
+            StarkProofData p = prove_table(t, cfg, cols[t].data(), ns[t], commits[t], ctl, betas, gammas, ch, params_from(labels),
+                                           forced_pows ? &forced_pows[t] : nullptr, ctls, nullptr);
+            proofs[t] = zkstark::serialize_proof(p);
+            commits[t] = PolyBatch();
+        }
+        size_t total = 0;
+        for (uint32_t t = 0; t < 9; t++) { offsets[t] = total; total += proofs[t].size(); }
+        offsets[9] = total;
+        if (out && out_cap >= total) for (uint32_t t = 0; t < 9; t++) if (!proofs[t].empty()) memcpy(out + offsets[t], proofs[t].data(), proofs[t].size() * 8);
+        return (long)total;
+    } catch (const std::exception& e) { g_orc_err = e.what(); return -1; }
+}
+
+// verify_proof: re-derive every challenge from the proofs (get_challenges.rs:273-314), verify each table's proof, then check the
+// cross-table-lookup sums (starky verify_cross_table_lookups) with the caller's extra looking sums (verifier.rs:240-262:
+// extra[ctl_index * num_challenges + c], only the memory CTL is non-zero in the reference).  1 valid, 0 rejected, -1 malformed.
+int orc_verify_segment(const uint32_t cfgw[8], const uint64_t* proofs, const size_t offsets[10], const uint64_t* public_values, size_t npv,
+                       const uint64_t labels[4], const uint64_t* extra_looking_sums) {
+    try {
+        Config cfg = cfg_from(cfgw);
+        const size_t capw = (size_t)4 << cfg.cap_height;
+        auto ctls = zkstark::all_cross_table_lookups();
+        uint8_t in_use[9];
+        std::vector<StarkProofData> ps(9);
+        std::vector<Words> caps(9);
+        for (uint32_t t = 0; t < 9; t++) {
+            in_use[t] = offsets[t + 1] > offsets[t];
+            if (!in_use[t]) continue;
+            ps[t] = zkstark::deserialize_proof(proofs + offsets[t], offsets[t + 1] - offsets[t]);
+            if (ps[t].trace_cap.size() != capw) throw std::runtime_error("trace cap has the wrong size");
+            caps[t] = ps[t].trace_cap;
+        }
+        Challenger ch;
+        std::vector<uint64_t> betas, gammas;
+        segment_transcript(ch, caps, in_use, capw, public_values, npv, cfg.num_challenges, betas, gammas);
+        for (uint32_t t = 0; t < 9; t++) {
+            if (!in_use[t]) continue;
+            std::string err;
+            if (!verify_table(t, cfg, ps[t], betas, gammas, ch, params_from(labels), ctls, err)) {
+                g_orc_err = std::string(zkstark::table_name(t)) + ": " + err;
+                return 0;
+            }
+        }
+        // verify_cross_table_lookups
+        std::vector<size_t> pos(9, 0);
+        std::vector<Words> zs(9);
+        for (uint32_t t = 0; t < 9; t++) {
+            if (in_use[t]) zs[t] = ps[t].ctl_zs_first;
+            else zs[t].assign(aux_shape(t, ctls, cfg.num_challenges, zkstark::CONSTRAINT_DEGREE).ctl_entries.size(), 0);   // verifier.rs:283-293
+        }
+        for (size_t ci = 0; ci < ctls.size(); ci++) {
+            std::vector<uint32_t> lookers;
+            for (auto& l : ctls[ci].looking_tables) { bool seen = false; for (uint32_t x : lookers) seen |= x == l.table; if (!seen) lookers.push_back(l.table); }
+            for (unsigned c = 0; c < cfg.num_challenges; c++) {
+                uint64_t sum = extra_looking_sums ? extra_looking_sums[ci * cfg.num_challenges + c] : 0;
+                for (uint32_t t : lookers) { if (pos[t] >= zs[t].size()) throw std::runtime_error("ctl_zs_first too short"); sum = gl_add(sum, zs[t][pos[t]++]); }
+                uint32_t lt = ctls[ci].looked_table.table;
+                if (pos[lt] >= zs[lt].size()) throw std::runtime_error("ctl_zs_first too short");
+                uint64_t looked = zs[lt][pos[lt]++];
+                if (sum != looked) { g_orc_err = "Cross-table lookup " + std::to_string(ci) + " verification failed (challenge " + std::to_string(c) + ")"; return 0; }
+            }
+        }
+        for (uint32_t t = 0; t < 9; t++) if (pos[t] != zs[t].size()) throw std::runtime_error("unused ctl_zs_first entries");
+        g_orc_err.clear();
+        return 1;
+    } catch (const std::exception& e) { g_orc_err = e.what(); return -1; }
+}
+
+}  // extern "C"

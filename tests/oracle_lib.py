@@ -169,3 +169,49 @@ def orc_verify_table(orc, table, cfg, proof, beta_gamma, state, labels=DEFAULT_L
     lab = np.array(labels, dtype=np.uint64)
     r = lib.orc_verify_table(C.c_uint32(table), _cfg(cfg), _ptr(p), C.c_size_t(p.size), _ptr(bg), _ptr(st), _ptr(lab))
     return r == 1, lib.orc_last_error().decode(), st
+
+
+# ---- whole segment ---------------------------------------------------------------------------------------------------------
+def orc_prove_segment(orc, cfg, traces, public_values, labels=DEFAULT_LABELS, forced_pows=None):
+    """traces: list of 9 (ncols, n) arrays or None.  Returns (list of 9 proof-word arrays or None, beta_gamma, caps (9,16,4))."""
+    lib = orc.lib
+    lib.orc_prove_segment.restype = C.c_long
+    lib.orc_last_error.restype = C.c_char_p
+    arrs = [None if t is None else np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
+    ptrs = (u64p * 9)(*[None if a is None else _ptr(a) for a in arrs])
+    ns = (C.c_size_t * 9)(*[0 if a is None else a.shape[1] for a in arrs])
+    pv = np.ascontiguousarray(public_values, dtype=np.uint64)
+    lab = np.array(labels, dtype=np.uint64)
+    fp = None if forced_pows is None else np.ascontiguousarray(forced_pows, dtype=np.uint64)
+    offs = (C.c_size_t * 10)()
+    bg = np.zeros(2 * cfg[1], dtype=np.uint64)
+    caps = np.zeros((9, 1 << cfg[3], 4), dtype=np.uint64)
+    cap = 1 << 18
+    while True:
+        out = np.zeros(cap, dtype=np.uint64)
+        r = lib.orc_prove_segment(_cfg(cfg), ptrs, ns, _ptr(pv), C.c_size_t(pv.size), _ptr(lab), _ptr(fp) if fp is not None else None,
+                                  _ptr(out), C.c_size_t(cap), offs, _ptr(bg), _ptr(caps))
+        if r < 0:
+            raise RuntimeError("oracle prove_segment failed: " + lib.orc_last_error().decode())
+        if r <= cap:
+            break
+        cap = int(r)
+    proofs = [out[offs[t]:offs[t + 1]].copy() if offs[t + 1] > offs[t] else None for t in range(9)]
+    return proofs, bg, caps
+
+
+def orc_verify_segment(orc, cfg, proofs, public_values, labels=DEFAULT_LABELS, extra_looking_sums=None):
+    lib = orc.lib
+    lib.orc_last_error.restype = C.c_char_p
+    offs = (C.c_size_t * 10)()
+    tot = 0
+    for t in range(9):
+        offs[t] = tot
+        tot += 0 if proofs[t] is None else len(proofs[t])
+    offs[9] = tot
+    buf = np.concatenate([np.asarray(p, dtype=np.uint64) for p in proofs if p is not None]) if tot else np.zeros(1, dtype=np.uint64)
+    pv = np.ascontiguousarray(public_values, dtype=np.uint64)
+    lab = np.array(labels, dtype=np.uint64)
+    ex = None if extra_looking_sums is None else np.ascontiguousarray(extra_looking_sums, dtype=np.uint64)
+    r = lib.orc_verify_segment(_cfg(cfg), _ptr(buf), offs, _ptr(pv), C.c_size_t(pv.size), _ptr(lab), _ptr(ex) if ex is not None else None)
+    return r == 1, lib.orc_last_error().decode()

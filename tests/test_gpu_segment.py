@@ -1,0 +1,69 @@
+"""GPU parity at the top of the path: prove_with_traces (all tables of a segment, shared transcript) through the C ABI
+vs the oracle's prove_segment, bit for bit, and the oracle's verify_proof (incl. cross-table-lookup sums) on the result."""
+import numpy as np
+import pytest
+from tests import traces
+from tests.oracle_lib import orc_prove_segment, orc_verify_segment, STANDARD_FAST, TEST_CONFIG, DEFAULT_LABELS
+import zk_evm_b200 as zk
+
+pytestmark = pytest.mark.gpu
+PUBLIC_VALUES = np.arange(1000, 1000 + 37, dtype=np.uint64)
+
+
+def _same(ap, want, bg, caps):
+    assert np.array_equal(ap.ctl_challenges, bg)
+    assert np.array_equal(ap.trace_caps, caps)
+    for t in range(9):
+        assert (ap.stark_proofs[t] is None) == (want[t] is None), "table %d presence" % t
+        if want[t] is not None:
+            assert np.array_equal(ap.stark_proofs[t], want[t]), "table %s proof differs" % zk.TABLE_NAMES[t]
+
+
+@pytest.mark.parametrize("cfg", [TEST_CONFIG, STANDARD_FAST])
+def test_valid_segment_matches_oracle_and_verifies(ctx, oracle, cfg):
+    tr = traces.valid_segment(seed=11)
+    ap = zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, zk.StarkConfig(*cfg), zk.KernelLabels(*DEFAULT_LABELS))
+    want, bg, caps = orc_prove_segment(oracle, cfg, tr, PUBLIC_VALUES)
+    _same(ap, want, bg, caps)
+    ok, err = orc_verify_segment(oracle, cfg, ap.stark_proofs, PUBLIC_VALUES)
+    assert ok, err
+    assert np.array_equal(ap.mem_before_cap, caps[7]) and np.array_equal(ap.mem_after_cap, caps[8])
+
+
+def test_random_nine_table_segment_matches_oracle(ctx, oracle):
+    log_ns = [9, 8, 10, 6, 7, 8, 11, 9, 7]
+    tr = traces.random_segment(log_ns, seed=5)
+    ap = zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, zk.StarkConfig(*STANDARD_FAST), zk.KernelLabels(*DEFAULT_LABELS))
+    want, bg, caps = orc_prove_segment(oracle, STANDARD_FAST, tr, PUBLIC_VALUES)
+    _same(ap, want, bg, caps)
+    # forcing the witnesses reproduces the same proofs; a wrong one is refused
+    pows = np.array([int(p[-1]) if p is not None else 0 for p in want], dtype=np.uint64)
+    ap2 = zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, zk.StarkConfig(*STANDARD_FAST), zk.KernelLabels(*DEFAULT_LABELS),
+                               forced_pow_witnesses=pows)
+    _same(ap2, want, bg, caps)
+
+
+def test_sharded_path_on_one_gpu_and_device_resident_traces(ctx, oracle):
+    import torch
+    tr = traces.valid_segment(seed=12, k=23)
+    in_use = [t is not None for t in tr]
+    cfg = zk.StarkConfig(*TEST_CONFIG)
+    backend = zk.ZkGpuBackend(ctx, cfg, zk.KernelLabels(*DEFAULT_LABELS))
+    ap = zk.prove_with_traces_sharded(backend, zk.LocalComm(), tr, in_use, PUBLIC_VALUES)
+    want, bg, caps = orc_prove_segment(oracle, TEST_CONFIG, tr, PUBLIC_VALUES)
+    _same(ap, want, bg, caps)
+    # traces already in HBM (torch tensors): same proofs through both entry points
+    dev = [None if t is None else torch.from_numpy(t.view(np.int64)).cuda() for t in tr]
+    ptrs = [None if d is None else (d.data_ptr(), d.shape[1]) for d in dev]
+    torch.cuda.synchronize()
+    ap2 = zk.prove_with_traces(ctx, None, PUBLIC_VALUES, cfg, zk.KernelLabels(*DEFAULT_LABELS), device_ptrs=ptrs)
+    _same(ap2, want, bg, caps)
+    ap3 = zk.prove_with_traces_sharded(backend, zk.LocalComm(), ptrs, in_use, PUBLIC_VALUES)
+    _same(ap3, want, bg, caps)
+
+
+def test_missing_mandatory_table_is_an_error(ctx):
+    tr = traces.valid_segment(seed=1)
+    tr[traces.T_CPU] = None
+    with pytest.raises(zk.ZkGpuError):
+        zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, zk.StarkConfig(*TEST_CONFIG), zk.KernelLabels(*DEFAULT_LABELS))

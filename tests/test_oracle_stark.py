@@ -106,3 +106,25 @@ def test_corrupted_valid_trace_is_rejected(oracle, table):
     proof, _ = orc_prove_table(oracle, table, TEST_CONFIG, tr, BG2[:2], STATE0)
     ok, err, _ = orc_verify_table(oracle, table, TEST_CONFIG, proof, BG2[:2], STATE0)
     assert not ok
+
+
+# ---- whole segment: prove_with_traces + verify_proof incl. the cross-table-lookup sums ----------------------------------------
+PUBLIC_VALUES = np.arange(1000, 1000 + 37, dtype=np.uint64)     # stand-in for the flattened PublicValues
+
+
+def test_segment_prove_verify_with_ctl_sums(oracle):
+    from tests.oracle_lib import orc_prove_segment, orc_verify_segment
+    tr = traces.valid_segment(seed=3)
+    proofs, bg, caps = orc_prove_segment(oracle, TEST_CONFIG, tr, PUBLIC_VALUES)
+    assert [p is not None for p in proofs] == [True, False, True, False, False, False, True, True, True]
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PUBLIC_VALUES)
+    assert ok, err
+    # the memory <-> mem_before / mem_after lookups really carry something: dropping one MemAfter row breaks the sum check only
+    bad = [None if t is None else t.copy() for t in tr]
+    bad[traces.T_MEM_AFTER][0, 5] = 0                       # filter off: the row is no longer looked
+    proofs2, _, _ = orc_prove_segment(oracle, TEST_CONFIG, bad, PUBLIC_VALUES)
+    ok2, err2 = orc_verify_segment(oracle, TEST_CONFIG, proofs2, PUBLIC_VALUES)
+    assert not ok2 and "Cross-table lookup 8" in err2, err2
+    # other public values -> other challenges -> the old proofs no longer verify
+    ok3, _ = orc_verify_segment(oracle, TEST_CONFIG, proofs, PUBLIC_VALUES + np.uint64(1))
+    assert not ok3

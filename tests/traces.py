@@ -203,3 +203,65 @@ def arithmetic_addcy_trace(log_n, seed, nops=1000):
     t[114] = np.minimum(np.arange(n), 65535).astype(np.uint64)
     t[115, :65536] = np.bincount(t[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
     return t
+
+
+# ---- a VALID multi-table segment: CPU padding + empty Arithmetic + Memory initialised from MemBefore, final state in MemAfter ----
+def memory_trace_from_mem_before(log_n, addrs, values):
+    """MemoryStark trace whose only real operations are the timestamp-0 initialisation writes of `mem_before`
+    (memory_stark.rs:408-423): one row per (context, segment, virt) address, sorted, then dummy-read padding rows
+    (pad_memory_ops, memory_stark.rs:358-385).  All addresses share context 0 and one non-preinitialised segment, with
+    consecutive virtual addresses, so every range-checked difference is 0.  values: (K, 8) 32-bit limbs."""
+    n = 1 << log_n
+    K = len(addrs)
+    assert 0 < K < n
+    ctx, seg, v0 = addrs[0]
+    assert all(a == (ctx, seg, v0 + i) for i, a in enumerate(addrs)) and seg not in (0, 12, 34, 35)
+    t = np.zeros((30, n), dtype=np.uint64)
+    p = lambda x: np.uint64(x % P)
+    t[0, :K] = 1                                        # filter
+    t[1, K:] = 1; t[2, K:] = 1                          # padding rows: timestamp 1, timestamp_inv 1
+    t[3, K:] = 1                                        # is_read (initialisation rows are writes)
+    t[4] = ctx; t[5] = seg
+    t[6, :K] = v0 + np.arange(K); t[6, K:] = v0 + K
+    t[7:15, :K] = np.asarray(values, dtype=np.uint64).T
+    t[17, :K] = 1                                       # virtual_first_change: the next row has another address
+    aux = (seg - 34) * (seg - 35)
+    pre = seg * (seg - 12) * aux
+    t[20] = p(aux); t[19] = p(pre)
+    t[18, K - 1] = p(pre)                               # initialize_aux: the row after the last write is a first read
+    t[25, :K] = 1; t[26, :K] = 1                        # maybe_in_mem_after, mem_after_filter
+    t[28] = np.arange(n, dtype=np.uint64)               # counter
+    t[29, 0] = n                                        # every range_check value is 0
+    return t
+
+
+def memcont_trace_from(log_n, addrs, values):
+    n = 1 << log_n
+    K = len(addrs)
+    assert K <= n
+    t = np.zeros((12, n), dtype=np.uint64)
+    t[0, :K] = 1
+    a = np.asarray(addrs, dtype=np.uint64)
+    t[1, :K], t[2, :K], t[3, :K] = a[:, 0], a[:, 1], a[:, 2]
+    t[4:12, :K] = np.asarray(values, dtype=np.uint64).T
+    return t
+
+
+def valid_segment(seed=0, log_cpu=6, log_mem=6, log_memcont=7, k=40, halt_final=0x1234):
+    """traces[table] or None: Arithmetic (no operations), Cpu (padding), Memory, MemBefore, MemAfter in use; the optional
+    BytePacking / Keccak / KeccakSponge / Logic tables left out (table_in_use = false)."""
+    rng = np.random.default_rng(seed)
+    addrs = [(0, 1, 100 + i) for i in range(k)]
+    values = rng.integers(0, 1 << 32, size=(k, 8), dtype=np.uint64)
+    tr = [None] * 9
+    tr[T_ARITHMETIC] = arithmetic_addcy_trace(16, seed, nops=0)
+    tr[T_CPU] = cpu_padding_trace(log_cpu, halt_final)
+    tr[T_MEMORY] = memory_trace_from_mem_before(log_mem, addrs, values)
+    tr[T_MEM_BEFORE] = memcont_trace_from(log_memcont, addrs, values)
+    tr[T_MEM_AFTER] = memcont_trace_from(log_memcont, addrs, values)
+    return tr
+
+
+def random_segment(log_ns, seed):
+    """uniformly random traces of the given heights (log_ns[table] or None) — throughput / parity inputs, not valid witnesses"""
+    return [None if lg is None else random_trace(t, lg, seed * 16 + t) for t, lg in enumerate(log_ns)]

@@ -14,7 +14,7 @@
 //  * proof of work: grid search with atomicMin -> the smallest valid witness (the reference's rayon find_any
 //    returns an arbitrary one; zkgpu_prove_table accepts a forced witness to reproduce a given proof).
 #include "stark_dev.h"
-#include "poseidon.cuh"
+#include "poseidon_fast.cuh"
 
 namespace zk {
 
@@ -193,8 +193,8 @@ __global__ void __launch_bounds__(128) pow_kernel(PowState st, unsigned pos, uns
     for (int i = 0; i < 12; i++) s[i] = st.s[i];
 #pragma unroll
     for (int i = 0; i < 12; i++) if (i == (int)pos) s[i] = cand;
-    poseidon_permute(s);
-    if (bits == 0 || (s[7] >> (64 - bits)) == 0) atomicMin(best, (unsigned long long)cand);
+    pf_permute(s);
+    if (bits == 0 || (pf_canon(s[7]) >> (64 - bits)) == 0) atomicMin(best, (unsigned long long)cand);
 }
 uint64_t pow_grind(Ctx& c, const uint64_t state[12], unsigned pos, unsigned bits) {
     ZK_REQUIRE(pos < 8 && bits < 40, "pow_grind: bad arguments");

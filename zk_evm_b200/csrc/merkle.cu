@@ -9,7 +9,7 @@
 // The 12-word sponge state lives in registers; the sponge overwrites state[0..8] with 8 columns per permutation.
 // Inner levels: one thread per node, children are adjacent 32-byte digests.
 #include "internal.h"
-#include "poseidon.cuh"
+#include "poseidon_fast.cuh"
 #include "merkle.h"
 
 namespace zk {
@@ -23,20 +23,20 @@ __global__ void __launch_bounds__(128) leaf_hash_kernel(const uint64_t* __restri
     for (int i = 0; i < 12; i++) s[i] = 0;
     const uint64_t* p = data + j;
     if (ncols <= 4) {   // hash_or_noop: short rows are copied, zero padded
-        for (size_t c = 0; c < ncols; c++) s[c] = p[c * stride];
-    } else {
-        size_t c = 0;
-        for (; c + 8 <= ncols; c += 8) {
 #pragma unroll
-            for (int k = 0; k < 8; k++) s[k] = p[(c + k) * stride];
-            poseidon_permute(s);
-        }
-        if (c < ncols) {
+        for (int k = 0; k < 4; k++)
+            if ((size_t)k < ncols) s[k] = p[k * stride];
+    } else {
+        // one permutation call site (the permutation body must stay resident in the instruction cache)
+#pragma unroll 1
+        for (size_t c = 0; c < ncols; c += 8) {
 #pragma unroll
             for (int k = 0; k < 8; k++)
                 if (c + k < ncols) s[k] = p[(c + k) * stride];
-            poseidon_permute(s);
+            pf_permute(s);
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++) s[k] = pf_canon(s[k]);   // the sponge state is non-canonical between permutations
     }
     ulonglong2* o = reinterpret_cast<ulonglong2*>(digests + 4 * j);
     o[0] = make_ulonglong2(s[0], s[1]);
@@ -50,7 +50,9 @@ __global__ void __launch_bounds__(128) merkle_level_kernel(const uint64_t* __res
     const ulonglong2* c = reinterpret_cast<const ulonglong2*>(in + 8 * i);
     ulonglong2 a = c[0], b = c[1], d = c[2], e = c[3];
     uint64_t s[12] = {a.x, a.y, b.x, b.y, d.x, d.y, e.x, e.y, 0, 0, 0, 0};
-    poseidon_permute(s);
+    pf_permute(s);
+#pragma unroll
+    for (int k = 0; k < 4; k++) s[k] = pf_canon(s[k]);
     ulonglong2* o = reinterpret_cast<ulonglong2*>(out + 4 * i);
     o[0] = make_ulonglong2(s[0], s[1]);
     o[1] = make_ulonglong2(s[2], s[3]);
@@ -62,9 +64,9 @@ __global__ void poseidon_states_kernel(uint64_t* states, size_t count) {
     uint64_t s[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) s[k] = states[12 * i + k];
-    poseidon_permute(s);
+    pf_permute(s);
 #pragma unroll
-    for (int k = 0; k < 12; k++) states[12 * i + k] = s[k];
+    for (int k = 0; k < 12; k++) states[12 * i + k] = pf_canon(s[k]);
 }
 
 void poseidon_states(Ctx& c, uint64_t* dev_states, size_t count) {

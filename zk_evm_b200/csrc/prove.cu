@@ -12,12 +12,21 @@ namespace zk {
 
 using zkstark::StarkProofData; using zkstark::Words; using zkstark::Config;
 
-static Config config_from(const zkgpu_stark_config* k) {
+Config config_from(const zkgpu_stark_config* k) {
     Config c;
     c.security_bits = k->security_bits; c.num_challenges = k->num_challenges; c.rate_bits = k->rate_bits;
     c.cap_height = k->cap_height; c.pow_bits = k->proof_of_work_bits; c.arity_bits = k->fri_arity_bits;
     c.final_poly_bits = k->fri_final_poly_bits; c.num_queries = k->num_query_rounds;
     return c;
+}
+
+zkstark::TableParams params_from(const zkgpu_kernel_labels* labels) {
+    zkstark::TableParams prm = {0, 0, 0, 0};
+    if (labels) {
+        prm.halt_final = labels->halt_final; prm.init = labels->init;
+        prm.syscall_jumptable = labels->syscall_jumptable; prm.exception_jumptable = labels->exception_jumptable;
+    }
+    return prm;
 }
 
 static void check_abort(volatile const int* flag) {
@@ -55,8 +64,11 @@ struct FriLayer {
     size_t rows = 0, width = 0;
 };
 
-void prove_table(Ctx& c, uint32_t table, const zkstark::TableParams& prm, const Config& cfg, const Batch& trace, const Ctl& ctl,
-                 uint64_t challenger_state[12], const uint64_t* forced_pow, volatile const int* abort_flag, Proof& out) {
+// Challenger-independent half of prove_single_table: the auxiliary polynomials (lookup columns ++ CTL helpers ++ CTL Zs)
+// and their commitment depend only on the trace and the CTL challenges, so a table-sharded run computes them for all
+// tables in parallel before the serial transcript relay reaches the table (DESIGN.md "multi-GPU").
+void prove_table_begin(Ctx& c, uint32_t table, const zkstark::TableParams& prm, const Config& cfg, const Batch& trace, const Ctl& ctl,
+                       volatile const int* abort_flag, TableJob& job) {
     ZK_REQUIRE(zkstark::table_supported(table), "table id not supported");
     ZK_REQUIRE(cfg.rate_bits == 1, "only rate_bits = 1 (quotient degree factor 2) is implemented");
     ZK_REQUIRE(cfg.num_challenges >= 1 && cfg.num_challenges <= 2, "num_challenges must be 1 or 2");
@@ -64,6 +76,34 @@ void prove_table(Ctx& c, uint32_t table, const zkstark::TableParams& prm, const 
     ZK_REQUIRE(trace.rate_bits == cfg.rate_bits && trace.cap_height == cfg.cap_height, "trace commitment made with another config");
     ZK_REQUIRE(trace.values.get() != nullptr, "trace batch must be committed with keep_values (needed for the lookup columns)");
     ZK_REQUIRE(ctl.table == table && ctl.n == trace.n && ctl.num_challenges == cfg.num_challenges, "ctl data does not match the table");
+    check_abort(abort_flag);
+    job.ctx = &c; job.table = table; job.prm = prm; job.cfg = cfg; job.trace = &trace; job.ctl = &ctl;
+    const size_t n = trace.n;
+    const TableDev& td = get_table_dev(c, table, cfg.num_challenges);
+    const zkstark::Flat& fl = td.flat;
+    const size_t na = fl.num_aux();
+    job.aux.reset(new zkgpu_batch());
+    Batch& aux = job.aux->b;
+    if (na) {
+        init_batch(c, aux, na, n, cfg.rate_bits, cfg.cap_height);
+        aux.values = DevBuf(&c, na * n * 8);
+        if (fl.num_lookup_cols) lookup_columns(c, td, trace.values.get(), n, ctl.betas, aux.values.get());
+        size_t nctl = fl.num_ctl_helpers + fl.num_ctl_zs;
+        if (nctl) ZK_CUDA(cudaMemcpyAsync(aux.values.get() + (size_t)fl.num_lookup_cols * n, ctl.cols.get(), nctl * n * 8,
+                                          cudaMemcpyDeviceToDevice, c.stream));
+        commit_from_device_values(c, aux, c.debug);
+    }
+    job.begun = true;
+}
+
+void prove_table_finish(Ctx& c, TableJob& job, uint64_t challenger_state[12], const uint64_t* forced_pow,
+                        volatile const int* abort_flag, Proof& out) {
+    ZK_REQUIRE(job.begun && job.ctx == &c, "table job was not begun on this context");
+    const uint32_t table = job.table;
+    const zkstark::TableParams& prm = job.prm;
+    const Config& cfg = job.cfg;
+    const Batch& trace = *job.trace;
+    const Ctl& ctl = *job.ctl;
     check_abort(abort_flag);
     const unsigned k = trace.log_n, logN = k + 1;
     const size_t n = trace.n, N = trace.N, ncols = trace.ncols;
@@ -84,17 +124,11 @@ void prove_table(Ctx& c, uint32_t table, const zkstark::TableParams& prm, const 
     memcpy(p.init_challenger_state, ch.state, 96);
     p.trace_cap = cap_words(trace);
 
-    // 1. auxiliary polynomials = lookup columns ++ CTL helpers ++ CTL Zs
-    std::unique_ptr<zkgpu_batch> auxh(new zkgpu_batch());
+    // 1. auxiliary polynomials: committed by prove_table_begin
+    std::unique_ptr<zkgpu_batch> auxh = std::move(job.aux);
+    job.begun = false;
     Batch& aux = auxh->b;
     if (na) {
-        init_batch(c, aux, na, n, cfg.rate_bits, cfg.cap_height);
-        aux.values = DevBuf(&c, na * n * 8);
-        if (fl.num_lookup_cols) lookup_columns(c, td, trace.values.get(), n, ctl.betas, aux.values.get());
-        size_t nctl = fl.num_ctl_helpers + fl.num_ctl_zs;
-        if (nctl) ZK_CUDA(cudaMemcpyAsync(aux.values.get() + (size_t)fl.num_lookup_cols * n, ctl.cols.get(), nctl * n * 8,
-                                          cudaMemcpyDeviceToDevice, c.stream));
-        commit_from_device_values(c, aux, c.debug);
         p.aux_cap = cap_words(aux);
         ch.observe_vec(p.aux_cap);
     }
@@ -269,6 +303,25 @@ void prove_table(Ctx& c, uint32_t table, const zkstark::TableParams& prm, const 
     c.sync();
 }
 
+void make_ctl_data(Ctx& c, uint32_t table_id, const Batch& b, const uint64_t* beta_gamma, uint32_t num_challenges, Ctl& k) {
+    ZK_REQUIRE(num_challenges >= 1 && num_challenges <= 2, "num_challenges must be 1 or 2");
+    ZK_REQUIRE(b.values.get() != nullptr, "trace batch must be committed with keep_values");
+    ZK_REQUIRE(zkstark::table_supported(table_id) && b.ncols == zkstark::table_num_columns(table_id), "trace width does not match the table");
+    const TableDev& td = get_table_dev(c, table_id, num_challenges);
+    k.ctx = &c; k.table = table_id; k.n = b.n; k.num_challenges = num_challenges;
+    for (uint32_t i = 0; i < num_challenges; i++) { k.betas[i] = gl_canon(beta_gamma[2 * i]); k.gammas[i] = gl_canon(beta_gamma[2 * i + 1]); }
+    size_t nctl = td.flat.num_ctl_helpers + td.flat.num_ctl_zs;
+    k.cols = DevBuf(&c, nctl * b.n * 8);
+    if (nctl) ctl_columns(c, td, b.values.get(), b.n, k.betas, k.gammas, k.cols.get());
+}
+
+void prove_table(Ctx& c, uint32_t table, const zkstark::TableParams& prm, const Config& cfg, const Batch& trace, const Ctl& ctl,
+                 uint64_t challenger_state[12], const uint64_t* forced_pow, volatile const int* abort_flag, Proof& out) {
+    TableJob job;
+    prove_table_begin(c, table, prm, cfg, trace, ctl, abort_flag, job);
+    prove_table_finish(c, job, challenger_state, forced_pow, abort_flag, out);
+}
+
 }  // namespace zk
 
 using namespace zk;
@@ -299,20 +352,10 @@ int zkgpu_ctl_data(zkgpu_ctx* h, uint32_t table_id, const zkgpu_batch* trace, co
                    zkgpu_ctl** out) {
     ZK_API_BEGIN
     ZK_REQUIRE(h && trace && beta_gamma && out, "null argument");
-    ZK_REQUIRE(num_challenges >= 1 && num_challenges <= 2, "num_challenges must be 1 or 2");
     Ctx& c = h->c;
     ZK_CUDA(cudaSetDevice(c.device));
-    const Batch& b = trace->b;
-    ZK_REQUIRE(b.values.get() != nullptr, "trace batch must be committed with keep_values");
-    ZK_REQUIRE(zkstark::table_supported(table_id) && b.ncols == zkstark::table_num_columns(table_id), "trace width does not match the table");
-    const TableDev& td = get_table_dev(c, table_id, num_challenges);
     std::unique_ptr<zkgpu_ctl> hc(new zkgpu_ctl());
-    Ctl& k = hc->c;
-    k.ctx = &c; k.table = table_id; k.n = b.n; k.num_challenges = num_challenges;
-    for (uint32_t i = 0; i < num_challenges; i++) { k.betas[i] = gl_canon(beta_gamma[2 * i]); k.gammas[i] = gl_canon(beta_gamma[2 * i + 1]); }
-    size_t nctl = td.flat.num_ctl_helpers + td.flat.num_ctl_zs;
-    k.cols = DevBuf(&c, nctl * b.n * 8);
-    if (nctl) ctl_columns(c, td, b.values.get(), b.n, k.betas, k.gammas, k.cols.get());
+    make_ctl_data(c, table_id, trace->b, beta_gamma, num_challenges, hc->c);
     c.sync();
     *out = hc.release();
     ZK_API_END
@@ -342,9 +385,7 @@ int zkgpu_prove_table(zkgpu_ctx* h, uint32_t table_id, const zkgpu_kernel_labels
     ZK_REQUIRE(h && config && trace && ctl && challenger_state && out, "null argument");
     Ctx& c = h->c;
     ZK_CUDA(cudaSetDevice(c.device));
-    zkstark::TableParams prm = {0, 0, 0, 0};
-    if (labels) { prm.halt_final = labels->halt_final; prm.init = labels->init; prm.syscall_jumptable = labels->syscall_jumptable;
-                  prm.exception_jumptable = labels->exception_jumptable; }
+    zkstark::TableParams prm = params_from(labels);
     std::unique_ptr<zkgpu_proof> hp(new zkgpu_proof());
     uint64_t st[12];
     memcpy(st, challenger_state, 96);

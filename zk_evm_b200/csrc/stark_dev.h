@@ -34,6 +34,28 @@ struct Proof {
     std::vector<uint64_t> fri_values;   // N x (re, im), bit-reversed order
 };
 
+// prove_single_table split at the point where the shared transcript is first needed (prove.cu)
+struct TableJob {
+    Ctx* ctx = nullptr;
+    uint32_t table = 0;
+    zkstark::TableParams prm = {0, 0, 0, 0};
+    zkstark::Config cfg;
+    const Batch* trace = nullptr;
+    const Ctl* ctl = nullptr;
+    std::unique_ptr<zkgpu_batch> aux;   // committed auxiliary polynomials
+    bool begun = false;
+};
+void prove_table_begin(Ctx& c, uint32_t table, const zkstark::TableParams& prm, const zkstark::Config& cfg, const Batch& trace,
+                       const Ctl& ctl, volatile const int* abort_flag, TableJob& job);
+void prove_table_finish(Ctx& c, TableJob& job, uint64_t challenger_state[12], const uint64_t* forced_pow,
+                        volatile const int* abort_flag, Proof& out);
+void prove_table(Ctx& c, uint32_t table, const zkstark::TableParams& prm, const zkstark::Config& cfg, const Batch& trace, const Ctl& ctl,
+                 uint64_t challenger_state[12], const uint64_t* forced_pow, volatile const int* abort_flag, Proof& out);
+zkstark::Config config_from(const zkgpu_stark_config* k);
+zkstark::TableParams params_from(const zkgpu_kernel_labels* labels);
+// get_ctl_data for one table (prove.cu)
+void make_ctl_data(Ctx& c, uint32_t table, const Batch& trace, const uint64_t* beta_gamma, uint32_t num_challenges, Ctl& out);
+
 // ---- aux.cu ---------------------------------------------------------------------------------------------------
 // CTL helper + Z columns of a table (starky cross_table_lookup_data / partial_sums) into out[(helpers+zs) x n]
 void ctl_columns(Ctx& c, const TableDev& t, const uint64_t* values, size_t n, const uint64_t* betas, const uint64_t* gammas,
@@ -86,3 +108,4 @@ void init_batch(Ctx& c, Batch& b, size_t ncols, size_t n, uint32_t rate_bits, ui
 
 struct zkgpu_ctl { zk::Ctl c; };
 struct zkgpu_proof { zk::Proof p; };
+struct zkgpu_table_job { zk::TableJob j; };

@@ -1,0 +1,277 @@
+"""Segment-level host mirror: `prove_with_traces` / `prove_with_commitments` of evm_arithmetization/src/prover.rs:72-293.
+
+Two ways to prove the tables of one segment:
+  * `prove_with_traces`         one device, one call into the C ABI (zkgpu_prove_segment);
+  * `prove_with_traces_sharded` the tables of the segment spread over the ranks of a process group (one process per GPU):
+        phase 1 (parallel)  every rank commits the traces of its tables;
+        exchange 1          all-gather of the 9 trace caps (512 B each) -> every rank replays the transcript
+                            (caps, public values) and draws the same CTL challenges (prover.rs:118-144);
+        phase 2 (parallel)  CTL / lookup auxiliary columns and their commitment for the local tables (table_job_begin);
+        phase 3 (relay)     in Table order the owner of table t finishes its proof from the shared transcript state and
+                            broadcasts the 12-word state it ends with (prover.rs:251-259 proves the tables one after the
+                            other with the same challenger, so this chain is part of the protocol, not of the implementation).
+The compute steps go through a small backend object so the sharding logic can be exercised on CPU (gloo) with the test
+oracle as the backend; the product backend is `ZkGpuBackend` (CUDA only, no fallback).
+"""
+import ctypes as C
+import numpy as np
+from ._lib import u64p, check, lib
+from . import prover as _p
+
+NUM_TABLES = 9
+TABLE_NAMES = ("arithmetic", "byte_packing", "cpu", "keccak", "keccak_sponge", "logic", "memory", "mem_before", "mem_after")
+OPTIONAL_TABLES = (1, 3, 4, 5, 8)          # OPTIONAL_TABLE_INDICES, all_stark.rs:110-117
+
+
+def _ptr(a):
+    return a.ctypes.data_as(u64p)
+
+
+class Challenger:
+    """plonky2 Challenger<F, PoseidonHash> (host side)."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        check(lib().zkgpu_challenger_new(C.byref(self._h)))
+
+    def observe_elements(self, xs):
+        a = np.ascontiguousarray(xs, dtype=np.uint64).ravel()
+        check(lib().zkgpu_challenger_observe(self._h, _ptr(a), C.c_size_t(a.size)))
+
+    def get_n_challenges(self, n):
+        out = np.empty(n, dtype=np.uint64)
+        check(lib().zkgpu_challenger_get_challenges(self._h, _ptr(out), C.c_size_t(n)))
+        return out
+
+    def compact(self):
+        st = np.empty(12, dtype=np.uint64)
+        check(lib().zkgpu_challenger_compact(self._h, _ptr(st)))
+        return st
+
+    def set_state(self, st):
+        a = np.ascontiguousarray(st, dtype=np.uint64)
+        check(lib().zkgpu_challenger_set_state(self._h, _ptr(a)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().zkgpu_challenger_free(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+
+def segment_challenges(trace_caps, table_in_use, cap_height, public_values, num_challenges):
+    """prover.rs:118-144: (beta_gamma, compacted challenger state before the first table)."""
+    caps = np.ascontiguousarray(trace_caps, dtype=np.uint64).reshape(NUM_TABLES, -1)
+    assert caps.shape[1] == 4 << cap_height
+    use = np.ascontiguousarray(table_in_use, dtype=np.uint8)
+    pv = np.ascontiguousarray(public_values, dtype=np.uint64).ravel()
+    bg = np.empty(2 * num_challenges, dtype=np.uint64)
+    st = np.empty(12, dtype=np.uint64)
+    check(lib().zkgpu_segment_challenges(_ptr(caps), use.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_uint32(cap_height), _ptr(pv),
+                                         C.c_size_t(pv.size), C.c_uint32(num_challenges), _ptr(bg), _ptr(st)))
+    return bg, st
+
+
+class AllProof:
+    """AllProof / MultiProof (proof.rs:29-54): per-table StarkProofWithMetadata words (None = table not in use), the CTL
+    challenges and the trace caps (MemBefore / MemAfter caps feed PublicValues.mem_before / mem_after, prover.rs:261-271)."""
+
+    def __init__(self, stark_proofs, ctl_challenges, trace_caps, table_in_use):
+        self.stark_proofs, self.ctl_challenges, self.trace_caps, self.table_in_use = stark_proofs, ctl_challenges, trace_caps, table_in_use
+
+    @property
+    def mem_before_cap(self):
+        return self.trace_caps[7]
+
+    @property
+    def mem_after_cap(self):
+        return self.trace_caps[8] if self.table_in_use[8] else np.zeros_like(self.trace_caps[8])
+
+
+class _Trace(C.Structure):
+    _fields_ = [("cols", u64p), ("n", C.c_size_t)]
+
+
+def prove_with_traces(ctx, traces, public_values, config, labels=None, forced_pow_witnesses=None, abort_flag=None, device_ptrs=None):
+    """prove_with_traces on one device.  traces: list of 9 (ncols, n) uint64 arrays, None for an optional table not in use.
+    device_ptrs: instead of host arrays, list of 9 (device address, n) or None (traces already resident in HBM)."""
+    arr = (_Trace * NUM_TABLES)()
+    keep = []
+    in_use = [False] * NUM_TABLES
+    for t in range(NUM_TABLES):
+        if device_ptrs is not None:
+            if device_ptrs[t] is not None:
+                arr[t].cols = C.cast(C.c_void_p(int(device_ptrs[t][0])), u64p)
+                arr[t].n = int(device_ptrs[t][1])
+                in_use[t] = True
+        elif traces[t] is not None:
+            a = np.ascontiguousarray(traces[t], dtype=np.uint64)
+            info = _p.table_info(t, config.num_challenges)
+            if a.ndim != 2 or a.shape[0] != info["num_columns"]:
+                raise ValueError("table %s: expected a (%d, n) trace" % (TABLE_NAMES[t], info["num_columns"]))
+            keep.append(a)
+            arr[t].cols = _ptr(a)
+            arr[t].n = a.shape[1]
+            in_use[t] = True
+    pv = np.ascontiguousarray(public_values, dtype=np.uint64).ravel()
+    fp = None if forced_pow_witnesses is None else np.ascontiguousarray(forced_pow_witnesses, dtype=np.uint64)
+    outs = (C.c_void_p * NUM_TABLES)()
+    bg = np.zeros(4, dtype=np.uint64)
+    caps = np.zeros((NUM_TABLES, 1 << config.cap_height, 4), dtype=np.uint64)
+    check(lib().zkgpu_prove_segment(ctx._h, arr, 1 if device_ptrs is not None else 0, _ptr(pv), C.c_size_t(pv.size),
+                                    C.byref(labels) if labels is not None else None, C.byref(config),
+                                    _ptr(fp) if fp is not None else None, C.byref(abort_flag) if abort_flag is not None else None,
+                                    outs, _ptr(bg), _ptr(caps)))
+    proofs = []
+    for t in range(NUM_TABLES):
+        if outs[t]:
+            sp = _p.StarkProof(ctx, C.c_void_p(outs[t]))
+            proofs.append(sp.words)
+            sp.free()
+        else:
+            proofs.append(None)
+    return AllProof(proofs, bg[:2 * config.num_challenges].copy(), caps, in_use)
+
+
+# ---- table-sharded proving ------------------------------------------------------------------------------------------------
+class ZkGpuBackend:
+    """The compute steps of one rank on its GPU (through the C ABI)."""
+
+    def __init__(self, ctx, config, labels=None):
+        self.ctx, self.config, self.labels = ctx, config, labels
+
+    def commit(self, table, trace):
+        if isinstance(trace, tuple):      # (device address, n)
+            info = _p.table_info(table, self.config.num_challenges)
+            return _p.PolynomialBatch.from_device_values(self.ctx, trace[0], info["num_columns"], trace[1], self.config.rate_bits,
+                                                         self.config.cap_height, keep_values=True)
+        return _p.PolynomialBatch.from_values(self.ctx, trace, self.config.rate_bits, self.config.cap_height, keep_values=True)
+
+    def cap(self, handle):
+        return handle.cap
+
+    def segment_challenges(self, caps, in_use, public_values):
+        return segment_challenges(caps, in_use, self.config.cap_height, public_values, self.config.num_challenges)
+
+    def begin(self, table, handle, beta_gamma):
+        ctl = _p.get_ctl_data(self.ctx, table, handle, beta_gamma, self.config.num_challenges)
+        job = C.c_void_p()
+        check(lib().zkgpu_table_job_begin(self.ctx._h, C.c_uint32(table), C.byref(self.labels) if self.labels is not None else None,
+                                          C.byref(self.config), handle._h, ctl._h, None, C.byref(job)))
+        return (job, ctl, handle)
+
+    def finish(self, job, state, forced_pow=None):
+        jh, ctl, handle = job
+        st = np.ascontiguousarray(state, dtype=np.uint64).copy()
+        fp = C.c_uint64(forced_pow) if forced_pow is not None else None
+        h = C.c_void_p()
+        try:
+            check(lib().zkgpu_table_job_finish(jh, _ptr(st), C.byref(fp) if fp is not None else None, None, C.byref(h)))
+        finally:
+            lib().zkgpu_table_job_free(jh)
+        sp = _p.StarkProof(self.ctx, h)
+        words = sp.words
+        sp.free(); ctl.free(); handle.free()
+        return words, st
+
+
+class TorchComm:
+    """torch.distributed plumbing of the two exchanges (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group, self.device = torch, dist, group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def _t(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a).view(np.int64).copy()).to(self.device) if self.device is not None \
+            else self.torch.from_numpy(np.ascontiguousarray(a).view(np.int64).copy())
+
+    def all_gather(self, a):
+        """(world, *a.shape) uint64"""
+        t = self._t(a)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t, group=self.group)
+        return np.stack([o.cpu().numpy().view(np.uint64) for o in out])
+
+    def broadcast(self, a, src):
+        t = self._t(a)
+        self.dist.broadcast(t, src=src, group=self.group)
+        return t.cpu().numpy().view(np.uint64)
+
+    def gather_proofs(self, proofs, owner):
+        """every rank ends up with all proofs (object all-gather: proofs are a few hundred kB)"""
+        mine = {t: p for t, p in enumerate(proofs) if p is not None and owner[t] == self.rank}
+        out = [None] * self.world
+        self.dist.all_gather_object(out, mine, group=self.group)
+        res = [None] * NUM_TABLES
+        for d in out:
+            for t, p in d.items():
+                res[t] = p
+        return res
+
+
+class LocalComm:
+    """world of one (same code path as the sharded run, no process group)"""
+    rank, world = 0, 1
+
+    def all_gather(self, a):
+        return np.asarray(a)[None]
+
+    def broadcast(self, a, src):
+        return np.asarray(a)
+
+    def gather_proofs(self, proofs, owner):
+        return proofs
+
+
+def default_owner(world, weights=None):
+    """table -> rank.  Longest-processing-time bin packing on per-table weights (default: a static cost model
+    rows-independent ~ columns * ceil(columns / 8), dominated by Keccak, KeccakSponge, Logic, Arithmetic, Cpu)."""
+    if weights is None:
+        weights = [116 * 15, 71 * 9, 85 * 11, 2431 * 304, 438 * 55, 523 * 66, 30 * 4, 12 * 2, 12 * 2]
+    load = [0.0] * world
+    owner = [0] * NUM_TABLES
+    for t in sorted(range(NUM_TABLES), key=lambda t: -weights[t]):
+        r = min(range(world), key=lambda r: load[r])
+        owner[t] = r
+        load[r] += weights[t]
+    return owner
+
+
+def prove_with_traces_sharded(backend, comm, traces, table_in_use, public_values, owner=None, forced_pow_witnesses=None,
+                              gather=True, cap_height=4):
+    """traces[t] is needed on owner[t] only (host array or (device address, n)); table_in_use must agree on every rank."""
+    owner = owner if owner is not None else default_owner(comm.world)
+    cap_words = 4 << cap_height
+    # phase 1: commitments of the local tables
+    handles = {}
+    caps = np.zeros((NUM_TABLES, cap_words), dtype=np.uint64)
+    for t in range(NUM_TABLES):
+        if table_in_use[t] and owner[t] == comm.rank:
+            if traces[t] is None:
+                raise ValueError("rank %d owns table %s but has no trace for it" % (comm.rank, TABLE_NAMES[t]))
+            handles[t] = backend.commit(t, traces[t])
+            caps[t] = np.asarray(backend.cap(handles[t]), dtype=np.uint64).ravel()
+    # exchange 1: all-gather of the caps; row t of the result comes from the owner of table t
+    allcaps = comm.all_gather(caps)
+    caps = np.stack([allcaps[owner[t], t] for t in range(NUM_TABLES)])
+    # transcript replay (identical on every rank)
+    beta_gamma, state = backend.segment_challenges(caps, table_in_use, public_values)
+    # phase 2: auxiliary polynomials of the local tables
+    jobs = {t: backend.begin(t, h, beta_gamma) for t, h in handles.items()}
+    # phase 3: relay of the transcript state in Table order
+    proofs = [None] * NUM_TABLES
+    for t in range(NUM_TABLES):
+        if not table_in_use[t]:
+            continue
+        if owner[t] == comm.rank:
+            fp = None if forced_pow_witnesses is None else int(forced_pow_witnesses[t])
+            proofs[t], state = backend.finish(jobs.pop(t), state, fp)
+        state = comm.broadcast(state, src=owner[t])
+    if gather:
+        proofs = comm.gather_proofs(proofs, owner)
+    return AllProof(proofs, np.asarray(beta_gamma), caps.reshape(NUM_TABLES, -1, 4), list(table_in_use))
