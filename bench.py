@@ -1,18 +1,21 @@
 #!/usr/bin/env python3
-"""bench.py — headline benchmark of the B200 STARK proving path (contract: see the task statement / DESIGN.md §measurement).
+"""bench.py — headline benchmark of the B200 STARK proving path (contract: task statement / DESIGN.md "Measurement").
 
   python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the zkgpu C ABI)
   python bench.py --impl reference --gpus N ...            # reference arm: the CPU restatement (oracle) on all host cores
 
-A step = one complete proof of the workload through the reference-shaped API (PolynomialBatch.from_values ->
-get_ctl_data -> prove_single_table): trace commitment, CTL/lookup auxiliary columns + commitment, quotient evaluation +
-commitment, openings, FRI commit phase, proof of work, query answers.
-  value : proofs/s with the trace already resident in HBM (device-to-device ingest), device time from CUDA events on
-          the library's stream, max over ranks
-  e2e   : the same through the host API with the trace in pinned host memory (H2D inside the timed region) and the
-          serialised proof read back (D2H)
-N > 1 : one process per GPU (torchrun), every rank proves its own instance of the workload ("weak" scaling: the path
-shards by table / by segment with no data-path collective).
+Metric (BASELINE.json): segment proofs/sec.  A step = ONE segment proof = prove_with_traces over all nine STARK tables of a
+synthetic segment with the table heights of the `witness_b19807080` CI ranges: per table the trace
+commitment, CTL / lookup auxiliary columns + commitment, fused quotient evaluation + commitment, openings, FRI commit phase,
+proof of work and query answers, all tables chained through one Fiat-Shamir transcript.
+  value : proofs/s with the traces already resident in HBM, device time (CUDA events on the library's stream), max over ranks
+  e2e   : the same call with the traces in pinned host memory (H2D inside the timed region) and the proofs read back (D2H)
+N > 1 (one process per GPU, torchrun):
+  --parallelism segments (default)  every rank proves its own segment — segments are independent proofs (own transcript), the
+                                    way the reference spreads them over workers; no data-path collective; "weak" scaling
+  --parallelism tables              the north-star layout: the nine tables of ONE segment spread over the ranks, one all-gather
+                                    of trace caps + the transcript relay (DESIGN.md "Multi-GPU"); "strong" scaling
+--workload cpu_table  times BASELINE config #2 (single CpuStark table, 2^20 rows) instead.
 """
 import argparse
 import ctypes as C
@@ -28,14 +31,18 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-T_CPU, T_MEMORY = 2, 6
-TABLE_NAMES = {0: "ArithmeticStark", 1: "BytePackingStark", 2: "CpuStark", 3: "KeccakStark", 4: "KeccakSpongeStark",
-               5: "LogicStark", 6: "MemoryStark", 7: "MemBeforeStark", 8: "MemAfterStark"}
+T_CPU = 2
+TABLE_NAMES = ("Arithmetic", "BytePacking", "Cpu", "Keccak", "KeccakSponge", "Logic", "Memory", "MemBefore", "MemAfter")
+NUM_COLUMNS = (116, 71, 85, 2431, 438, 523, 30, 12, 12)
+# top of the CI height ranges of artifacts/witness_b19807080.json (scripts/prove_stdio.rs:89-101)
+SEGMENT_LOG_NS = (17, 14, 19, 17, 13, 16, 21, 19, 19)
 STANDARD_FAST = (100, 2, 1, 4, 16, 4, 5, 84)
 LABELS = (0x1234, 0x77, 0x4000, 0x5000)
+PUBLIC_VALUES = np.arange(1, 2180, dtype=np.uint64)       # ~2.2k observed elements (get_challenges.rs:202-227), synthetic
 BG = np.array([0x1111111111, 0x2222222222, 0x3333333333, 0x4444444444], dtype=np.uint64)
 STATE0 = np.arange(1, 13, dtype=np.uint64)
 METRIC = "segment proofs/sec"
+FAMILIES = ("leaf_hash", "merkle_levels", "ntt", "quotient", "aux_columns", "openings", "fri", "pow")
 
 
 def measured_peak():
@@ -71,13 +78,23 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": reasons, "samples": len(sm)}
 
 
-def workload(args):
-    import zk_evm_b200 as zk
-    table = T_CPU if zk.lib().zkgpu_table_info(C.c_uint32(T_CPU), C.c_uint32(2), None, None, None, None) == 0 else T_MEMORY
-    if args.table is not None:
-        table = args.table
-    info = zk.table_info(table, 2)
-    return table, args.log_n, info
+def segment_shape(args):
+    if args.workload == "cpu_table":
+        return [args.log_n if t == T_CPU else None for t in range(9)]
+    return [max(4, lg - args.shrink) for lg in SEGMENT_LOG_NS]
+
+
+def describe(log_ns):
+    return ", ".join("%s 2^%d x %d" % (TABLE_NAMES[t], lg, NUM_COLUMNS[t]) for t, lg in enumerate(log_ns) if lg is not None)
+
+
+def kernel_stats(zk, ctx):
+    out = {}
+    for i, name in enumerate(FAMILIES):
+        l, ms, b = C.c_uint64(), C.c_double(), C.c_double()
+        zk._lib.check(zk.lib().zkgpu_ctx_kernel_stats(ctx._h, C.c_uint32(i), C.byref(l), C.byref(ms), C.byref(b)))
+        out[name] = {"launches": l.value, "ms": ms.value, "bytes": b.value}
+    return out
 
 
 def run_ours(args):
@@ -91,38 +108,48 @@ def run_ours(args):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    table, log_n, info = workload(args)
-    ncols, n = info["num_columns"], 1 << log_n
-    na = info["num_lookup_columns"] + info["num_ctl_helper_columns"] + info["num_ctl_zs"]
     dev = torch.device("cuda", local_rank)
     ctx = zk.Context(local_rank)
     cfg = zk.StarkConfig(*STANDARD_FAST)
     labels = zk.KernelLabels(*LABELS)
+    log_ns = segment_shape(args)
+    in_use = [lg is not None for lg in log_ns]
+    sharded = args.parallelism == "tables" and world > 1
+    owner = zk.default_owner(world, weights=[(0 if lg is None else (1 << lg) * NUM_COLUMNS[t] * ((NUM_COLUMNS[t] + 7) // 8 + 6))
+                                             for t, lg in enumerate(log_ns)]) if sharded else [rank] * 9
+    mine = [in_use[t] and owner[t] == rank for t in range(9)]
+
+    # synthetic traces: uniform random canonical field elements (seed 4 + rank; with rate_bits = 1 the prover does the
+    # same work on any trace), resident in HBM and mirrored in pinned host memory for the e2e leg
     g = torch.Generator(device=dev)
-    g.manual_seed(2 + rank)
-    trace_dev = torch.randint(0, 2 ** 63 - 1, (ncols, n), dtype=torch.int64, device=dev, generator=g)   # canonical: < p
-    trace_host = torch.empty((ncols, n), dtype=torch.int64, pin_memory=True)
-    trace_host.copy_(trace_dev)
-    trace_np = trace_host.numpy().view(np.uint64)
+    g.manual_seed(4 + (0 if sharded else rank))
+    dev_traces, host_traces = [None] * 9, [None] * 9
+    for t in range(9):
+        if not in_use[t]:
+            continue
+        x = torch.randint(0, 2 ** 63 - 1, (NUM_COLUMNS[t], 1 << log_ns[t]), dtype=torch.int64, device=dev, generator=g)
+        if mine[t]:
+            dev_traces[t] = x
+            h = torch.empty(x.shape, dtype=torch.int64, pin_memory=True)
+            h.copy_(x)
+            host_traces[t] = h.numpy().view(np.uint64)
+        del x
     torch.cuda.synchronize()
-    pow_w = [None]
+    ptrs = [None if d is None else (d.data_ptr(), d.shape[1]) for d in dev_traces]
+    h2d_bytes = sum(8 * NUM_COLUMNS[t] * (1 << log_ns[t]) for t in range(9) if mine[t])
+    comm = zk.TorchComm(device=dev) if sharded else None
+    backend = zk.ZkGpuBackend(ctx, cfg, labels)
+    d2h = [0]
 
-    def step_device():
-        tb = zk.PolynomialBatch.from_device_values(ctx, trace_dev.data_ptr(), ncols, n, keep_values=True)
-        ctl = zk.get_ctl_data(ctx, table, tb, BG, 2)
-        proof, _ = zk.prove_single_table(ctx, table, cfg, tb, ctl, STATE0, labels=labels)
-        nwords = len(proof.words)
-        pow_w[0] = int(proof.words[-1])
-        proof.free(); ctl.free(); tb.free()
-        return nwords
-
-    def step_host():
-        tb = zk.PolynomialBatch.from_values(ctx, trace_np, keep_values=True)
-        ctl = zk.get_ctl_data(ctx, table, tb, BG, 2)
-        proof, _ = zk.prove_single_table(ctx, table, cfg, tb, ctl, STATE0, labels=labels)
-        nwords = len(proof.words)
-        proof.free(); ctl.free(); tb.free()
-        return nwords
+    def step(host):
+        if sharded:
+            ap = zk.prove_with_traces_sharded(backend, comm, host_traces if host else ptrs, in_use, PUBLIC_VALUES, owner=owner, gather=False)
+        elif host:
+            ap = zk.prove_with_traces(ctx, host_traces, PUBLIC_VALUES, cfg, labels)
+        else:
+            ap = zk.prove_with_traces(ctx, None, PUBLIC_VALUES, cfg, labels, device_ptrs=ptrs)
+        d2h[0] = sum(8 * len(p) for p in ap.stark_proofs if p is not None)
+        return ap
 
     def barrier():
         torch.cuda.synchronize()
@@ -130,12 +157,12 @@ def run_ours(args):
         if dist is not None:
             dist.barrier()
 
-    def timed(fn, steps):
+    def timed(host, steps):
         barrier()
         ctx.timer_start()
         t0 = time.perf_counter()
         for _ in range(steps):
-            nw = fn()
+            step(host)
         ms = ctx.timer_stop()
         wall = (time.perf_counter() - t0) * 1e3
         barrier()
@@ -143,47 +170,59 @@ def run_ours(args):
             t = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms, wall = float(t[0]), float(t[1])
-        return ms, wall, nw
+        return ms, wall
 
     for _ in range(args.warmup):
-        step_device()
+        step(False)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    zk._lib.check(zk.lib().zkgpu_ctx_set_profiling(ctx._h, 0 if args.no_kernel_events else 1))
     l0 = ctx.stats()["kernel_launches"]
-    ms, wall, nwords = timed(step_device, args.steps)
+    ms, wall = timed(False, args.steps)
     launches = ctx.stats()["kernel_launches"] - l0
+    kst = kernel_stats(zk, ctx)
+    zk._lib.check(zk.lib().zkgpu_ctx_set_profiling(ctx._h, 0))
     for _ in range(min(args.warmup, 1)):
-        step_host()
-    e_ms, e_wall, _ = timed(step_host, args.steps)
+        step(True)
+    e_ms, e_wall = timed(True, args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
     line = None
     if rank == 0:
         peak, peak_src = measured_peak()
-        # dominant kernel: the Poseidon leaf hash over the 2n LDE rows of the trace (profiles/: launch-list share)
-        N = 2 * n
-        lh_ms = ctx.bench_leaf_hash(ncols, N, 3)
-        lh_bytes = (8.0 * ncols + 32.0) * N
-        ntt_ms, _ = ctx.bench_ntt(ncols, n, 3)
-        roof = {"bound": "hbm", "kernel": "leaf_hash_kernel (Poseidon sponge over %d LDE rows x %d cols)" % (N, ncols),
-                "achieved": lh_bytes / lh_ms / 1e6, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": lh_bytes / lh_ms / 1e6 / peak, "traffic": None,
-                "perms_per_s": ((ncols + 7) // 8) * N / lh_ms * 1e3,
-                "note": "Poseidon is integer-ALU bound (~2e4 int ops per 64 B); HBM fraction reported because the metric asks for it",
-                "ntt": {"kernel": "ntt_dif_pass_kernel size-n batch of %d cols" % ncols, "achieved": 16.0 * ncols * n / ntt_ms / 1e6,
-                        "frac": 16.0 * ncols * n / ntt_ms / 1e6 / peak, "unit": "GB/s"}}
-        cpu = None if args.no_cpu_baseline else cpu_baseline(table, args, full_log_n=log_n)
-        line = {"metric": METRIC, "value": world * args.steps / (ms / 1e3), "unit": "proofs/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks, exact)", "data": "synthetic",
-                "config": {"workload": "single %s table prove, trace 2^%d rows x %d cols (+%d aux cols), standard_fast_config; "
-                                       "uniform random trace (synthetic, seed 2+rank)" % (TABLE_NAMES[table], log_n, ncols, na),
-                           "l2": "inputs larger than L2 (trace %.0f MiB, LDE %.0f MiB)" % (8.0 * ncols * n / 2 ** 20, 16.0 * ncols * n / 2 ** 20),
-                           "timing": "CUDA events on the library stream, max over ranks", "pow_witness": pow_w[0]},
+        segs = args.steps * (1 if sharded else world)          # segment proofs completed by all ranks
+        tot_ms = sum(v["ms"] for v in kst.values()) or 1.0
+        top = max(kst, key=lambda k: kst[k]["ms"])
+
+        def fam(k):
+            v = kst[k]
+            per = v["ms"] / max(v["launches"], 1)
+            ach = v["bytes"] / v["ms"] / 1e6 if v["ms"] > 0 else 0.0
+            return {"launches_per_step": v["launches"] / args.steps, "ms_per_step": v["ms"] / args.steps, "share_of_kernel_time": v["ms"] / tot_ms,
+                    "avg_launch_ms": per, "algorithmic_GB_per_step": v["bytes"] / args.steps / 1e9, "achieved_GBps": ach, "frac_of_peak": ach / peak}
+        roof = {"bound": "hbm", "kernel": top, "achieved": fam(top)["achieved_GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": fam(top)["frac_of_peak"], "traffic": None,
+                "how": "CUDA events recorded by the library on its launching stream around every launch group inside the timed region; "
+                       "achieved = algorithmic bytes of the group (DESIGN.md) / event time, summed over the timed steps",
+                "families": {k: fam(k) for k in FAMILIES}}
+        if top == "leaf_hash":
+            perms = sum(2 * (1 << log_ns[t]) * ((NUM_COLUMNS[t] + 7) // 8) for t in range(9) if mine[t] and NUM_COLUMNS[t] > 4)
+            roof["note"] = "Poseidon is integer-issue bound (~2.6e4 instr per 64-byte absorb): HBM fraction reported because the metric asks " \
+                           "for it; trace-leaf permutations alone: %.0f Mperm/s" % (perms * args.steps / max(kst["leaf_hash"]["ms"], 1e-9) / 1e3)
+        cpu = None if args.no_cpu_baseline else cpu_baseline(args, log_ns)
+        line = {"metric": METRIC, "value": segs / (ms / 1e3), "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+                "dtype": "u64 (Goldilocks, exact)", "data": "synthetic",
+                "config": {"workload": ("segment proof (AllStark, 9 tables, heights of witness_b19807080's CI ranges): " if args.workload == "segment"
+                                        else "single-table prove (BASELINE config #2): ") + describe(log_ns) + "; standard_fast_config",
+                           "parallelism": ("tables of one segment sharded over %d GPUs (owner %s)" % (world, owner)) if sharded
+                           else ("%d independent segment(s), one per GPU" % world),
+                           "l2": "inputs larger than L2 (%.2f GB of trace per segment)" % (sum(8 * NUM_COLUMNS[t] * (1 << log_ns[t]) for t in range(9) if in_use[t]) / 1e9),
+                           "timing": "CUDA events on the library stream, max over ranks"},
                 "wall_ms_per_step": wall / args.steps,
-                "e2e": {"value": world * args.steps / (e_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": 8 * ncols * n,
-                        "d2h_bytes_per_step": 8 * nwords, "ms_per_step": e_ms / args.steps, "wall_ms_per_step": e_wall / args.steps},
+                "e2e": {"value": segs / (e_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h[0],
+                        "ms_per_step": e_ms / args.steps, "wall_ms_per_step": e_wall / args.steps},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
     ctx.close()
     if dist is not None:
@@ -193,49 +232,44 @@ def run_ours(args):
         print(json.dumps(line))
 
 
-def oracle_prove_time(table, log_n, threads=None):
+# ---- CPU side: the oracle (C++17 + OpenMP restatement of the plonky2 / starky prover) ----------------------------------------
+def oracle_segment_time(log_ns, threads=None):
     from tests import oracle_lib
     orc = oracle_lib.load()
     if threads:
         orc.lib.orc_set_num_threads(int(threads))
-    ncols = orc.lib.orc_table_num_columns(C.c_uint32(table))
-    rng = np.random.default_rng(2)
-    tr = rng.integers(0, 2 ** 63 - 1, size=(ncols, 1 << log_n), dtype=np.uint64)
+    rng = np.random.default_rng(4)
+    traces = [None if lg is None else rng.integers(0, 2 ** 63 - 1, size=(NUM_COLUMNS[t], 1 << lg), dtype=np.uint64) for t, lg in enumerate(log_ns)]
     t0 = time.perf_counter()
-    oracle_lib.orc_prove_table(orc, table, STANDARD_FAST, tr, BG, STATE0, labels=LABELS)
+    oracle_lib.orc_prove_segment(orc, STANDARD_FAST, traces, PUBLIC_VALUES, labels=LABELS)
     return time.perf_counter() - t0, orc.lib.orc_num_threads()
 
 
-def cpu_baseline(table, args, full_log_n):
-    """The CPU restatement (oracle, C++/OpenMP) on the host cores, on a bounded sample: the same table at 2^sample rows,
-    scaled linearly in rows to the workload size (n log n terms make this slightly favourable to the CPU)."""
-    sample = min(full_log_n, args.cpu_sample_log_n)
-    secs, threads = oracle_prove_time(table, sample)
-    scale = float(1 << (full_log_n - sample))
+def cpu_sample_shape(args, log_ns):
+    sh = args.cpu_shrink
+    return [None if lg is None else max(4, lg - sh) for lg in log_ns], float(1 << sh)
+
+
+def cpu_baseline(args, log_ns):
+    """bounded sample: the same segment with every table 2^cpu_shrink times shorter, time scaled back linearly in rows
+    (the n log n terms make this slightly favourable to the CPU)"""
+    sample, scale = cpu_sample_shape(args, log_ns)
+    secs, threads = oracle_segment_time(sample)
     return {"value": 1.0 / (secs * scale), "unit": "proofs/s", "cores": int(threads), "kind": "port",
-            "sample": "oracle prove_table of the same table at 2^%d rows took %.2f s on %d threads; scaled x%d in rows to 2^%d"
-                      % (sample, secs, threads, int(scale), full_log_n)}
+            "sample": "oracle prove_segment with every table 2^%d x shorter took %.2f s on %d threads; scaled x%d"
+                      % (args.cpu_shrink, secs, threads, int(scale))}
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    sys.path.insert(0, ROOT)
-    from tests import oracle_lib
-    orc = oracle_lib.load()
-    table = args.table
-    if table is None:
-        table = T_CPU if orc.lib.orc_table_supported(C.c_uint32(T_CPU)) else T_MEMORY
-    ncols = orc.lib.orc_table_num_columns(C.c_uint32(table))
-    sample = min(args.log_n, args.cpu_sample_log_n)
-    scale = float(1 << (args.log_n - sample))
+    log_ns = segment_shape(args)
+    sample, scale = cpu_sample_shape(args, log_ns)
     for _ in range(min(args.warmup, 1)):
-        oracle_prove_time(table, max(8, sample - 4))
-    t = 0.0
-    threads = 1
+        oracle_segment_time([None if lg is None else max(4, lg - 4) for lg in sample])
+    t, threads = 0.0, 1
     for _ in range(args.steps):
-        s, threads = oracle_prove_time(table, sample)
+        s, threads = oracle_segment_time(sample)
         t += s
     per_step = t / args.steps * scale
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -244,11 +278,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 (Goldilocks, exact)", "data": "synthetic",
-        "config": {"workload": "single %s table prove, trace 2^%d rows x %d cols, standard_fast_config; CPU restatement "
-                               "(oracle/, C++17 + OpenMP) of the plonky2/starky prover: the Rust reference cannot be built here "
-                               "(no cargo/rustc, crates not vendored)" % (TABLE_NAMES[table], args.log_n, ncols)},
+        "config": {"workload": ("segment proof (AllStark, 9 tables): " if args.workload == "segment" else "single-table prove: ") + describe(log_ns)
+                               + "; standard_fast_config; CPU restatement (oracle/, C++17 + OpenMP) of the plonky2/starky prover — the Rust "
+                                 "reference cannot be built here (no cargo/rustc, crates not vendored)"},
         "cpu_baseline": {"value": val, "unit": "proofs/s", "cores": int(threads), "kind": "port",
-                         "sample": "each step proves the table at 2^%d rows; time scaled x%d in rows to 2^%d" % (sample, int(scale), args.log_n)},
+                         "sample": "each step proves the segment with every table 2^%d x shorter; time scaled x%d" % (args.cpu_shrink, int(scale))},
         "e2e": {"value": val, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -258,10 +292,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--log-n", type=int, default=20, help="log2 of the trace length (BASELINE config #2: 20)")
-    ap.add_argument("--table", type=int, default=None, help="table id (default: CpuStark)")
-    ap.add_argument("--cpu-sample-log-n", type=int, default=16)
+    ap.add_argument("--workload", default="segment", choices=["segment", "cpu_table"])
+    ap.add_argument("--parallelism", default="segments", choices=["segments", "tables"])
+    ap.add_argument("--log-n", type=int, default=20, help="cpu_table workload: log2 of the trace length (BASELINE config #2: 20)")
+    ap.add_argument("--shrink", type=int, default=0, help="segment workload: make every table 2^shrink times shorter (smoke runs)")
+    ap.add_argument("--cpu-shrink", type=int, default=5, help="CPU legs prove tables 2^k times shorter and scale the time")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiler runs)")
+    ap.add_argument("--no-kernel-events", action="store_true", help="do not bracket kernel families with CUDA events")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

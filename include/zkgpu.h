@@ -84,6 +84,15 @@ int zkgpu_ctx_timer_stop(zkgpu_ctx* ctx, float* ms);
 /* device-memory high-water mark and kernel-launch counter (bench.py's gpu_launches) */
 int zkgpu_ctx_stats(zkgpu_ctx* ctx, uint64_t* kernel_launches, uint64_t* bytes_in_use, uint64_t* bytes_peak);
 
+/* In-library profiler for bench.py's roofline numbers: while on, every launch group of a kernel family is bracketed by CUDA
+ * events on the context's stream (the stream the kernels run on) and accounted with its ALGORITHMIC bytes.
+ * family: 0 leaf_hash (Poseidon sponge over LDE rows), 1 merkle inner levels, 2 NTT / LDE passes, 3 quotient evaluation,
+ * 4 CTL + lookup auxiliary columns, 5 openings, 6 FRI combine / fold / layer leaves, 7 proof-of-work grind. */
+enum { ZKGPU_KF_LEAF_HASH = 0, ZKGPU_KF_MERKLE_LEVELS, ZKGPU_KF_NTT, ZKGPU_KF_QUOTIENT, ZKGPU_KF_AUX, ZKGPU_KF_OPENINGS, ZKGPU_KF_FRI,
+       ZKGPU_KF_POW, ZKGPU_KF_COUNT };
+int zkgpu_ctx_set_profiling(zkgpu_ctx* ctx, int on);   /* on: also resets the counters */
+int zkgpu_ctx_kernel_stats(zkgpu_ctx* ctx, uint32_t family, uint64_t* launches, double* ms_total, double* algorithmic_bytes);
+
 /* ---- S1: commitments ------------------------------------------------------------------------------------- */
 /* PolynomialBatch::from_values(values, rate_bits, blinding=false, cap_height): per column ifft -> zero-pad ->
  * coset FFT (shift = MULTIPLICATIVE_GROUP_GENERATOR) -> bit-reversed rows -> Poseidon Merkle tree.

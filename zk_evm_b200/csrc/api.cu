@@ -39,6 +39,16 @@ void Ctx::d2h(void* dst, const void* src, size_t bytes) {
     ZK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
     ZK_CUDA(cudaStreamSynchronize(stream));
 }
+void Ctx::prof_collect() {
+    if (prof_pending.empty()) return;
+    ZK_CUDA(cudaStreamSynchronize(stream));
+    for (ProfRec& r : prof_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { prof_ms[r.fam] += ms; prof_bytes[r.fam] += r.bytes; prof_launches[r.fam] += r.launches; }
+        prof_free_events.push_back(r.e0); prof_free_events.push_back(r.e1);
+    }
+    prof_pending.clear();
+}
 void Ctx::check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) throw ZkError(ZKGPU_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -174,6 +184,28 @@ int zkgpu_ctx_stats(zkgpu_ctx* h, uint64_t* kernel_launches, uint64_t* bytes_in_
     if (kernel_launches) *kernel_launches = h->c.launches;
     if (bytes_in_use) *bytes_in_use = h->c.bytes_in_use;
     if (bytes_peak) *bytes_peak = h->c.bytes_peak;
+    ZK_API_END
+}
+
+int zkgpu_ctx_set_profiling(zkgpu_ctx* h, int on) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(h, "ctx is null");
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    c.prof_collect();
+    c.profiling = on != 0;
+    if (on) for (int i = 0; i < KF_COUNT; i++) { c.prof_ms[i] = 0; c.prof_bytes[i] = 0; c.prof_launches[i] = 0; }
+    ZK_API_END
+}
+int zkgpu_ctx_kernel_stats(zkgpu_ctx* h, uint32_t family, uint64_t* launches, double* ms_total, double* algorithmic_bytes) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(h && family < KF_COUNT, "bad argument");
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    c.prof_collect();
+    if (launches) *launches = c.prof_launches[family];
+    if (ms_total) *ms_total = c.prof_ms[family];
+    if (algorithmic_bytes) *algorithmic_bytes = c.prof_bytes[family];
     ZK_API_END
 }
 

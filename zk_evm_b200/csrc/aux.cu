@@ -206,6 +206,7 @@ static void run_zsums(Ctx& c, const TableDev& t, const std::vector<ZJob>& jobs, 
 
 void ctl_columns(Ctx& c, const TableDev& t, const uint64_t* values, size_t n, const uint64_t* betas, const uint64_t* gammas,
                  uint64_t* out) {
+    KernelScope ks(c, KF_AUX, 8.0 * n * (zkstark::table_num_columns(t.table) + t.flat.num_ctl_helpers + t.flat.num_ctl_zs));
     const zkstark::Flat& f = t.flat;
     const uint32_t base = f.num_lookup_cols;   // `out` starts at the first CTL helper column
     std::vector<HelperJob> hj;
@@ -238,6 +239,7 @@ void ctl_columns(Ctx& c, const TableDev& t, const uint64_t* values, size_t n, co
 }
 
 void lookup_columns(Ctx& c, const TableDev& t, const uint64_t* values, size_t n, const uint64_t* betas, uint64_t* out) {
+    KernelScope ks(c, KF_AUX, 8.0 * n * (zkstark::table_num_columns(t.table) + t.flat.num_lookup_cols));
     const zkstark::Flat& f = t.flat;
     std::vector<HelperJob> hj;
     std::vector<ZJob> zj;

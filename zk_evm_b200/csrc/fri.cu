@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_columns_kernel(const uint64
 }
 
 void eval_columns(Ctx& c, const uint64_t* coeffs, size_t ncols, size_t n, Fp2 zeta, Fp2 zeta_next, std::vector<uint64_t>& out5) {
+    KernelScope ks(c, KF_OPENINGS, 8.0 * n * ncols);
     out5.assign(ncols * 5, 0);
     if (!ncols) return;
     size_t seg_len = n < EVAL_SEG ? n : EVAL_SEG;
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(256) fri_combine_kernel(CombineKernelArgs a) {
 }
 
 void fri_combine(Ctx& c, const CombineArgs& a) {
+    KernelScope ks(c, KF_FRI, 8.0 * ((size_t)1 << a.log_N) * (a.ncols[0] + a.ncols[1] + a.ncols[2] + 2));
     size_t total = a.ncols[0] + a.ncols[1] + a.ncols[2];
     std::vector<uint64_t> apow(2 * total);
     Fp2 p(1, 0);
@@ -159,6 +161,7 @@ __global__ void fri_leaves_kernel(const uint64_t* __restrict__ re, const uint64_
     out[idx] = src[(r << arity_bits) + (k >> 1)];
 }
 void fri_leaves(Ctx& c, const uint64_t* re, const uint64_t* im, size_t M, unsigned arity_bits, uint64_t* out) {
+    KernelScope ks(c, KF_FRI, 32.0 * M);
     size_t rows = M >> arity_bits, total = rows * ((size_t)2 << arity_bits);
     fri_leaves_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>(re, im, rows, arity_bits, out);
     c.count_launch();
@@ -177,6 +180,7 @@ __global__ void fri_fold_kernel(const uint64_t* __restrict__ re, const uint64_t*
 }
 void fri_fold(Ctx& c, const uint64_t* re, const uint64_t* im, size_t M, unsigned arity_bits, Fp2 beta, uint64_t* out_re,
               uint64_t* out_im) {
+    KernelScope ks(c, KF_FRI, 16.0 * M + 16.0 * (M >> arity_bits));
     size_t out_len = M >> arity_bits;
     fri_fold_kernel<<<(unsigned)((out_len + 127) / 128), 128, 0, c.stream>>>(re, im, out_len, arity_bits, beta, out_re, out_im);
     c.count_launch();
@@ -198,6 +202,7 @@ __global__ void __launch_bounds__(128) pow_kernel(PowState st, unsigned pos, uns
 }
 uint64_t pow_grind(Ctx& c, const uint64_t state[12], unsigned pos, unsigned bits) {
     ZK_REQUIRE(pos < 8 && bits < 40, "pow_grind: bad arguments");
+    KernelScope ks(c, KF_POW, 0.0);
     PowState st;
     memcpy(st.s, state, 96);
     DevBuf best(&c, 8);

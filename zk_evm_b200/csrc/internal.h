@@ -85,6 +85,11 @@ struct NttTables {
     DevBuf roots_fwd, roots_inv;
 };
 
+// kernel families the in-library profiler accounts for (zkgpu_ctx_kernel_stats)
+enum KernelFamily { KF_LEAF_HASH = 0, KF_MERKLE_LEVELS, KF_NTT, KF_QUOTIENT, KF_AUX, KF_OPENINGS, KF_FRI, KF_POW, KF_COUNT };
+
+struct ProfRec { int fam; cudaEvent_t e0, e1; double bytes; uint64_t launches; };
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -99,6 +104,13 @@ struct Ctx {
     std::map<std::string, DevBuf> table_cache;
     // per (table, num_challenges): lookup / CTL descriptors uploaded to the device (stark_dev.h)
     std::map<uint32_t, std::shared_ptr<TableDev>> stark_tables;
+    // in-library profiler: CUDA events on `stream` around each launch group, with its algorithmic bytes
+    bool profiling = false;
+    std::vector<ProfRec> prof_pending;
+    std::vector<cudaEvent_t> prof_free_events;
+    double prof_ms[KF_COUNT] = {0}, prof_bytes[KF_COUNT] = {0};
+    uint64_t prof_launches[KF_COUNT] = {0};
+    void prof_collect();   // resolve finished event pairs (synchronises the stream)
     bool debug = false;   // proofs keep their aux / quotient batches and FRI input values for stage-by-stage parity tests
     // pinned staging buffer for H2D / D2H of pageable memory
     void* staging = nullptr;
@@ -109,6 +121,23 @@ struct Ctx {
     void h2d(void* dst, const void* src, size_t bytes);
     void d2h(void* dst, const void* src, size_t bytes);   // synchronous on return
     void check_launch(const char* what);
+};
+
+// RAII scope: times the launches issued inside it as one group of `fam` (no-op unless profiling is on)
+struct KernelScope {
+    Ctx& c; int fam; double bytes; uint64_t l0; cudaEvent_t e0 = nullptr;
+    KernelScope(Ctx& c_, int fam_, double algorithmic_bytes) : c(c_), fam(fam_), bytes(algorithmic_bytes), l0(c_.launches) {
+        if (!c.profiling) return;
+        auto get = [&]() { cudaEvent_t e; if (!c.prof_free_events.empty()) { e = c.prof_free_events.back(); c.prof_free_events.pop_back(); } else cudaEventCreate(&e); return e; };
+        e0 = get();
+        cudaEventRecord(e0, c.stream);
+    }
+    ~KernelScope() {
+        if (!e0) return;
+        cudaEvent_t e1; if (!c.prof_free_events.empty()) { e1 = c.prof_free_events.back(); c.prof_free_events.pop_back(); } else cudaEventCreate(&e1);
+        cudaEventRecord(e1, c.stream);
+        c.prof_pending.push_back({fam, e0, e1, bytes, c.launches - l0});
+    }
 };
 
 // ---- PolynomialBatch on the device ----------------------------------------------------------------------

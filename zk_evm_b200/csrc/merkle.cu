@@ -77,6 +77,7 @@ void poseidon_states(Ctx& c, uint64_t* dev_states, size_t count) {
 }
 
 void leaf_hash(Ctx& c, const uint64_t* data, size_t stride, size_t ncols, size_t nrows, uint64_t* digests) {
+    KernelScope ks(c, KF_LEAF_HASH, (8.0 * ncols + 32.0) * nrows);
     leaf_hash_kernel<<<(unsigned)((nrows + 127) / 128), 128, 0, c.stream>>>(data, stride, ncols, nrows, digests);
     c.count_launch();
     c.check_launch("leaf_hash_kernel");
@@ -95,6 +96,9 @@ void merkle_layout(size_t nleaves, unsigned cap_height, std::vector<size_t>& off
 
 // digests: level 0 already filled with leaf digests
 void merkle_inner_levels(Ctx& c, uint64_t* digests, const std::vector<size_t>& off, const std::vector<size_t>& cnt) {
+    double nodes = 0;
+    for (size_t l = 1; l < cnt.size(); l++) nodes += (double)cnt[l];
+    KernelScope ks(c, KF_MERKLE_LEVELS, 96.0 * nodes);
     for (size_t l = 1; l < off.size(); l++) {
         merkle_level_kernel<<<(unsigned)((cnt[l] + 127) / 128), 128, 0, c.stream>>>(digests + off[l - 1],
                                                                                      digests + off[l], cnt[l]);

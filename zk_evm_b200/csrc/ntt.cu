@@ -226,6 +226,7 @@ void ntt_dif(Ctx& c, const uint64_t* src, size_t src_stride, unsigned src_shift,
              size_t ntrans, unsigned L, bool inverse, const uint64_t* prescale0, const uint64_t* prescale1,
              unsigned prescale_mask) {
     if (ntrans == 0) return;
+    KernelScope ks(c, KF_NTT, 16.0 * (double)ntrans * (double)((size_t)1 << L));
     if (L == 0) {
         // size-1 transforms: copy (with prescale == 1 at j = 0)
         for (size_t t = 0; t < ntrans; t++)
@@ -290,6 +291,7 @@ void ntt_dif(Ctx& c, const uint64_t* src, size_t src_stride, unsigned src_shift,
 void bitrev_permute(Ctx& c, const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, size_t ncols,
                     unsigned L, uint64_t scale, const uint64_t* tab) {
     if (ncols == 0) return;
+    KernelScope ks(c, KF_NTT, 0.0);   // part of the inverse transform: its algorithmic bytes are counted by ntt_dif
     ZK_REQUIRE(in != out, "bitrev_permute must be out of place");
     unsigned a = L / 2 < 5 ? L / 2 : 5;
     size_t mids = (size_t)1 << (L - 2 * a);

@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotKernelArgs a) {
 
 void quotient_values(Ctx& c, const TableDev& t, const QuotientArgs& q) {
     ZK_REQUIRE(q.num_challenges >= 1 && q.num_challenges <= 2, "num_challenges must be 1 or 2");
+    // each LDE row of trace + aux read once, num_challenges values per point written (16n(c+a) + 16n*nc)
+    KernelScope ks(c, KF_QUOTIENT, 8.0 * ((size_t)2 << q.log_n) * (zkstark::table_num_columns(q.table) + t.flat.num_aux() + q.num_challenges));
     QuotKernelArgs a;
     const unsigned k = q.log_n;
     a.trace_lde = q.trace_lde; a.aux_lde = q.aux_lde; a.out = q.out;
