@@ -110,6 +110,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     ctx = zk.Context(local_rank)
+    # --streams S: S segments in flight per GPU, each on its own context (own CUDA stream) driven by its own host thread (ctypes
+    # releases the GIL): the latency-bound tails (small Merkle levels, transcript round trips) of one overlap the kernels of another
+    nstreams = 1 if (args.parallelism == "tables" and world > 1) else max(1, args.streams)
+    ctxs = [ctx] + [zk.Context(local_rank) for _ in range(nstreams - 1)]
     cfg = zk.StarkConfig(*STANDARD_FAST)
     labels = zk.KernelLabels(*LABELS)
     log_ns = segment_shape(args)
@@ -141,7 +145,23 @@ def run_ours(args):
     backend = zk.ZkGpuBackend(ctx, cfg, labels)
     d2h = [0]
 
+    def one_segment(cx, host):
+        if host:
+            return zk.prove_with_traces(cx, host_traces, PUBLIC_VALUES, cfg, labels)
+        return zk.prove_with_traces(cx, None, PUBLIC_VALUES, cfg, labels, device_ptrs=ptrs)
+
     def step(host):
+        if nstreams > 1:
+            res = [None] * nstreams
+            ths = [threading.Thread(target=lambda i=i: res.__setitem__(i, one_segment(ctxs[i], host))) for i in range(nstreams)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+            if any(r is None for r in res):
+                raise RuntimeError("a segment stream failed")
+            d2h[0] = sum(8 * len(p) for r in res for p in r.stark_proofs if p is not None)
+            return res[0]
         if sharded:
             ap = zk.prove_with_traces_sharded(backend, comm, host_traces if host else ptrs, in_use, PUBLIC_VALUES, owner=owner, gather=False)
         elif host:
@@ -153,17 +173,32 @@ def run_ours(args):
 
     def barrier():
         torch.cuda.synchronize()
-        ctx.sync()
+        for cx in ctxs:
+            cx.sync()
         if dist is not None:
             dist.barrier()
 
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
     def timed(host, steps):
         barrier()
-        ctx.timer_start()
+        if nstreams > 1:
+            # several library streams: bracket with events on torch's stream, made to wait for / be waited on by a full device sync
+            ev0.record()
+            torch.cuda.synchronize()
+        else:
+            ctx.timer_start()
         t0 = time.perf_counter()
         for _ in range(steps):
             step(host)
-        ms = ctx.timer_stop()
+        if nstreams > 1:
+            for cx in ctxs:
+                cx.sync()
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1)
+        else:
+            ms = ctx.timer_stop()
         wall = (time.perf_counter() - t0) * 1e3
         barrier()
         if dist is not None:
@@ -176,12 +211,18 @@ def run_ours(args):
         step(False)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    zk._lib.check(zk.lib().zkgpu_ctx_set_profiling(ctx._h, 0 if args.no_kernel_events else 1))
-    l0 = ctx.stats()["kernel_launches"]
+    for cx in ctxs:
+        zk._lib.check(zk.lib().zkgpu_ctx_set_profiling(cx._h, 0 if args.no_kernel_events else 1))
+    l0 = sum(cx.stats()["kernel_launches"] for cx in ctxs)
     ms, wall = timed(False, args.steps)
-    launches = ctx.stats()["kernel_launches"] - l0
-    kst = kernel_stats(zk, ctx)
-    zk._lib.check(zk.lib().zkgpu_ctx_set_profiling(ctx._h, 0))
+    launches = sum(cx.stats()["kernel_launches"] for cx in ctxs) - l0
+    kst = kernel_stats(zk, ctxs[0])
+    for cx in ctxs[1:]:
+        for k, v in kernel_stats(zk, cx).items():
+            for f in ("launches", "ms", "bytes"):
+                kst[k][f] += v[f]
+    for cx in ctxs:
+        zk._lib.check(zk.lib().zkgpu_ctx_set_profiling(cx._h, 0))
     for _ in range(min(args.warmup, 1)):
         step(True)
     e_ms, e_wall = timed(True, args.steps)
@@ -191,7 +232,7 @@ def run_ours(args):
     line = None
     if rank == 0:
         peak, peak_src = measured_peak()
-        segs = args.steps * (1 if sharded else world)          # segment proofs completed by all ranks
+        segs = args.steps * (1 if sharded else world) * nstreams          # segment proofs completed by all ranks
         tot_ms = sum(v["ms"] for v in kst.values()) or 1.0
         top = max(kst, key=lambda k: kst[k]["ms"])
 
@@ -217,14 +258,15 @@ def run_ours(args):
                 "config": {"workload": ("segment proof (AllStark, 9 tables, heights of witness_b19807080's CI ranges): " if args.workload == "segment"
                                         else "single-table prove (BASELINE config #2): ") + describe(log_ns) + "; standard_fast_config",
                            "parallelism": ("tables of one segment sharded over %d GPUs (owner %s)" % (world, owner)) if sharded
-                           else ("%d independent segment(s), one per GPU" % world),
+                           else ("%d independent segment(s) in flight, %d per GPU (one context + CUDA stream + host thread each)" % (world * nstreams, nstreams)),
                            "l2": "inputs larger than L2 (%.2f GB of trace per segment)" % (sum(8 * NUM_COLUMNS[t] * (1 << log_ns[t]) for t in range(9) if in_use[t]) / 1e9),
                            "timing": "CUDA events on the library stream, max over ranks"},
                 "wall_ms_per_step": wall / args.steps,
-                "e2e": {"value": segs / (e_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h[0],
+                "e2e": {"value": segs / (e_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": h2d_bytes * nstreams, "d2h_bytes_per_step": d2h[0],
                         "ms_per_step": e_ms / args.steps, "wall_ms_per_step": e_wall / args.steps},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
-    ctx.close()
+    for cx in ctxs:
+        cx.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -297,6 +339,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=20, help="cpu_table workload: log2 of the trace length (BASELINE config #2: 20)")
     ap.add_argument("--shrink", type=int, default=0, help="segment workload: make every table 2^shrink times shorter (smoke runs)")
     ap.add_argument("--cpu-shrink", type=int, default=5, help="CPU legs prove tables 2^k times shorter and scale the time")
+    ap.add_argument("--streams", type=int, default=1, help="segments in flight per GPU (parallelism=segments)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiler runs)")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not bracket kernel families with CUDA events")
     args = ap.parse_args()

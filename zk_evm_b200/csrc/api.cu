@@ -3,6 +3,9 @@
 #include "ntt.h"
 #include "merkle.h"
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 #include <functional>
 #include <memory>
 
@@ -38,6 +41,16 @@ void Ctx::h2d(void* dst, const void* src, size_t bytes) {
 void Ctx::d2h(void* dst, const void* src, size_t bytes) {
     ZK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
     ZK_CUDA(cudaStreamSynchronize(stream));
+}
+double StageLog::now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+StageLog::StageLog(Ctx& c_) : c(c_) { const char* e = getenv("ZKGPU_TRACE"); on = e && *e == '1'; t0 = on ? now() : 0; }
+void StageLog::mark(const char* what) {
+    if (!on) return;
+    double a = now();
+    cudaStreamSynchronize(c.stream);
+    double b = now();
+    fprintf(stderr, "[zkgpu] %-28s host %8.3f ms  +drain %8.3f ms\n", what, a - t0, b - a);
+    t0 = b;
 }
 void Ctx::prof_collect() {
     if (prof_pending.empty()) return;

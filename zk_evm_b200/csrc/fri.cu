@@ -14,6 +14,7 @@
 //  * proof of work: grid search with atomicMin -> the smallest valid witness (the reference's rayon find_any
 //    returns an arbitrary one; zkgpu_prove_table accepts a forced witness to reproduce a given proof).
 #include "stark_dev.h"
+#include <algorithm>
 #include "poseidon_fast.cuh"
 
 namespace zk {
@@ -208,7 +209,8 @@ uint64_t pow_grind(Ctx& c, const uint64_t state[12], unsigned pos, unsigned bits
     DevBuf best(&c, 8);
     unsigned long long init = ~0ULL;
     c.h2d(best.get(), &init, 8);
-    const uint64_t batch = (uint64_t)1 << 20;
+    // expected number of candidates is 2^bits: a first batch of 4 * 2^bits finds a witness with probability 1 - e^-4
+    const uint64_t batch = std::max<uint64_t>((uint64_t)1 << 14, std::min<uint64_t>((uint64_t)4 << bits, (uint64_t)1 << 22));
     for (uint64_t base = 0;; base += batch) {
         pow_kernel<<<(unsigned)(batch / 128), 128, 0, c.stream>>>(st, pos, bits, base, (unsigned long long*)best.get());
         c.count_launch();

@@ -30,6 +30,68 @@ ZK_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
 #endif
 }
 
+#if defined(__CUDA_ARCH__)
+// ---- device forms: carry-flag arithmetic instead of compare/select chains ------------------------------------------------
+// Measured on sm_100a (tools/pipebench.cu): IADD3/LOP3/LEA issue at 1 warp-instr/clk/SMSP, IMAD at 1/2, IMAD.WIDE and
+// IMAD.HI at 1/4 and not overlapped with the ALU pipe — so a product is four IMAD.WIDE and everything else is IADD3 carry chains.
+__device__ __forceinline__ void gl_unpack(uint64_t x, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x)); }
+__device__ __forceinline__ uint64_t gl_pack(uint32_t lo, uint32_t hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+
+// (a - b) mod p for any a and b <= p; canonical when a < p
+__device__ __forceinline__ uint64_t gl_sub(uint64_t a, uint64_t b) {
+    uint32_t a0, a1, b0, b1, m;
+    gl_unpack(a, a0, a1); gl_unpack(b, b0, b1);
+    asm("sub.cc.u32 %0, %0, %3;\n\t"
+        "subc.cc.u32 %1, %1, %4;\n\t"
+        "subc.u32 %2, 0, 0;\n\t" : "+r"(a0), "+r"(a1), "=r"(m) : "r"(b0), "r"(b1));     // m = 0xFFFFFFFF on borrow
+    asm("sub.cc.u32 %0, %0, %2;\n\t"
+        "subc.u32 %1, %1, 0;\n\t" : "+r"(a0), "+r"(a1) : "r"(m));                        // + p == - EPS (mod 2^64)
+    return gl_pack(a0, a1);
+}
+__device__ __forceinline__ uint64_t gl_neg(uint64_t a) { return gl_sub(0, a); }
+// a + b = a - (p - b); p - b is computed without reduction (b <= p), p - 0 = p is a valid second operand of gl_sub
+__device__ __forceinline__ uint64_t gl_add(uint64_t a, uint64_t b) { return gl_sub(a, GL_P - b); }
+__device__ __forceinline__ uint64_t gl_dbl(uint64_t a) { return gl_add(a, a); }
+
+// w0 + 2^32 w1 + 2^64 w2 + 2^96 w3 -> canonical
+__device__ __forceinline__ uint64_t gl_reduce_words(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    uint32_t t0, t1, m, u0, u1;
+    asm("sub.cc.u32 %0, %3, %5;\n\t"
+        "subc.cc.u32 %1, %4, 0;\n\t"
+        "subc.u32 %2, 0, 0;\n\t" : "=r"(t0), "=r"(t1), "=r"(m) : "r"(w0), "r"(w1), "r"(w3));   // (w1:w0) - w3, 2^96 == -1
+    asm("sub.cc.u32 %0, %0, %2;\n\t"
+        "subc.u32 %1, %1, 0;\n\t" : "+r"(t0), "+r"(t1) : "r"(m));
+    asm("sub.cc.u32 %0, 0, %2;\n\t"
+        "subc.u32 %1, %2, 0;\n\t" : "=r"(u0), "=r"(u1) : "r"(w2));                               // w2 * (2^32 - 1), 2^64 == 2^32 - 1
+    asm("add.cc.u32 %0, %0, %3;\n\t"
+        "addc.cc.u32 %1, %1, %4;\n\t"
+        "addc.u32 %2, 0, 0;\n\t" : "+r"(t0), "+r"(t1), "=r"(m) : "r"(u0), "r"(u1));
+    m = 0u - m;
+    asm("add.cc.u32 %0, %0, %2;\n\t"
+        "addc.u32 %1, %1, 0;\n\t" : "+r"(t0), "+r"(t1) : "r"(m));
+    uint64_t r = gl_pack(t0, t1);
+    return r >= GL_P ? r - GL_P : r;
+}
+__device__ __forceinline__ uint64_t gl_reduce128(uint64_t lo, uint64_t hi) {
+    uint32_t w0, w1, w2, w3;
+    gl_unpack(lo, w0, w1); gl_unpack(hi, w2, w3);
+    return gl_reduce_words(w0, w1, w2, w3);
+}
+__device__ __forceinline__ uint64_t gl_mul(uint64_t a, uint64_t b) {
+    uint32_t a0, a1, b0, b1;
+    gl_unpack(a, a0, a1); gl_unpack(b, b0, b1);
+    uint64_t p00, mid, mid2, hi;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p00) : "r"(a0), "r"(b0));
+    uint32_t w0, c0; gl_unpack(p00, w0, c0);
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(mid) : "r"(a0), "r"(b1), "l"((uint64_t)c0));
+    uint32_t m0, m1; gl_unpack(mid, m0, m1);
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(mid2) : "r"(a1), "r"(b0), "l"((uint64_t)m0));
+    uint32_t w1, m2; gl_unpack(mid2, w1, m2);
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(hi) : "r"(a1), "r"(b1), "l"((uint64_t)m1 + (uint64_t)m2));
+    uint32_t w2, w3; gl_unpack(hi, w2, w3);
+    return gl_reduce_words(w0, w1, w2, w3);
+}
+#else
 ZK_HD uint64_t gl_add(uint64_t a, uint64_t b) {
     uint64_t s = a + b;
     // a, b < p so the true sum is < 2p: one conditional subtraction
@@ -53,6 +115,7 @@ ZK_HD uint64_t gl_reduce128(uint64_t lo, uint64_t hi) {
     return t2 >= GL_P ? t2 - GL_P : t2;
 }
 ZK_HD uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_reduce128(a * b, mulhi64(a, b)); }
+#endif
 ZK_HD uint64_t gl_sqr(uint64_t a) { return gl_mul(a, a); }
 // reduce a 96-bit value lo + 2^64 * hi32 (hi32 < 2^32)
 ZK_HD uint64_t gl_reduce96(uint64_t lo, uint32_t hi32) {

@@ -123,6 +123,14 @@ struct Ctx {
     void check_launch(const char* what);
 };
 
+// ZKGPU_TRACE=1: wall-clock stage log on stderr (synchronises at every mark; diagnosis only)
+struct StageLog {
+    Ctx& c; bool on; double t0;
+    static double now();
+    explicit StageLog(Ctx& c_);
+    void mark(const char* what);
+};
+
 // RAII scope: times the launches issued inside it as one group of `fam` (no-op unless profiling is on)
 struct KernelScope {
     Ctx& c; int fam; double bytes; uint64_t l0; cudaEvent_t e0 = nullptr;

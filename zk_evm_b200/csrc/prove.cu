@@ -84,6 +84,7 @@ void prove_table_begin(Ctx& c, uint32_t table, const zkstark::TableParams& prm, 
     const size_t na = fl.num_aux();
     job.aux.reset(new zkgpu_batch());
     Batch& aux = job.aux->b;
+    StageLog lg(c);
     if (na) {
         init_batch(c, aux, na, n, cfg.rate_bits, cfg.cap_height);
         aux.values = DevBuf(&c, na * n * 8);
@@ -91,7 +92,9 @@ void prove_table_begin(Ctx& c, uint32_t table, const zkstark::TableParams& prm, 
         size_t nctl = fl.num_ctl_helpers + fl.num_ctl_zs;
         if (nctl) ZK_CUDA(cudaMemcpyAsync(aux.values.get() + (size_t)fl.num_lookup_cols * n, ctl.cols.get(), nctl * n * 8,
                                           cudaMemcpyDeviceToDevice, c.stream));
+        lg.mark("aux columns");
         commit_from_device_values(c, aux, c.debug);
+        lg.mark("aux commit");
     }
     job.begun = true;
 }
@@ -115,6 +118,7 @@ void prove_table_finish(Ctx& c, TableJob& job, uint64_t challenger_state[12], co
         unsigned tot = 0; for (unsigned a : arities) tot += a;
         ZK_REQUIRE(tot <= k + cfg.rate_bits - cfg.cap_height, "FRI total arity is too large");
     }
+    StageLog lg(c);
     StarkProofData& p = out.data;
     p = StarkProofData();
     p.table_id = table; p.degree_bits = k;
@@ -149,11 +153,14 @@ void prove_table_finish(Ctx& c, TableJob& job, uint64_t challenger_state[12], co
         for (int i = 0; i < 4; i++) { qa.alphas[i] = alphas[i]; qa.betas[i] = ctl.betas[i]; qa.gammas[i] = ctl.gammas[i]; }
         qa.prm = prm; qa.out = qv.get();
         quotient_values(c, td, qa);
+        lg.mark("quotient eval");
         init_batch(c, quot, nq, n, cfg.rate_bits, cfg.cap_height);
         quot.coeffs = DevBuf(&c, nq * n * 8);
         // coset_ifft of each challenge's 2n values; the 2n coefficients of challenge j are chunks 2j, 2j+1
         intt_natural(c, qv.get(), scratch.get(), quot.coeffs.get(), cfg.num_challenges, logN, GL_GENERATOR);
+        lg.mark("quotient intt");
         commit_from_device_coeffs(c, quot);
+        lg.mark("quotient commit");
     }
     p.quotient_cap = cap_words(quot);
     ch.observe_vec(p.quotient_cap);
@@ -168,6 +175,7 @@ void prove_table_finish(Ctx& c, TableJob& job, uint64_t challenger_state[12], co
     eval_columns(c, trace.coeffs.get(), ncols, n, zeta, zeta_next, ev_t);
     if (na) eval_columns(c, aux.coeffs.get(), na, n, zeta, zeta_next, ev_a);
     eval_columns(c, quot.coeffs.get(), nq, n, zeta, zeta_next, ev_q);
+    lg.mark("openings eval");
     for (size_t i = 0; i < ncols; i++) { push_ext(p.local_values, ev_t[5 * i], ev_t[5 * i + 1]); push_ext(p.next_values, ev_t[5 * i + 2], ev_t[5 * i + 3]); }
     for (size_t i = 0; i < na; i++) { push_ext(p.aux_polys, ev_a[5 * i], ev_a[5 * i + 1]); push_ext(p.aux_polys_next, ev_a[5 * i + 2], ev_a[5 * i + 3]); }
     for (size_t i = 0; i < nq; i++) push_ext(p.quotient_polys, ev_q[5 * i], ev_q[5 * i + 1]);
@@ -177,6 +185,7 @@ void prove_table_finish(Ctx& c, TableJob& job, uint64_t challenger_state[12], co
     ch.observe_vec(p.next_values); ch.observe_vec(p.aux_polys_next);
     for (uint64_t v : p.ctl_zs_first) { ch.observe(v); ch.observe(0); }
 
+    lg.mark("observe openings (host)");
     // 5./6. FRI: alpha, reduced openings, values of the combined quotient on the coset
     Fp2 alpha = ch.ext_challenge();
     auto reduce = [&](std::initializer_list<const Words*> parts) {
@@ -214,6 +223,7 @@ void prove_table_finish(Ctx& c, TableJob& job, uint64_t challenger_state[12], co
         intt_natural(c, nat.get(), scratch.get(), coeffs.get(), 2, logN, GL_GENERATOR);
     }
     check_abort(abort_flag);
+    lg.mark("fri combine + intt");
 
     // 7. commit phase
     std::vector<FriLayer> layers;
@@ -251,6 +261,7 @@ void prove_table_finish(Ctx& c, TableJob& job, uint64_t challenger_state[12], co
         for (size_t i = 0; i < keep; i++) push_ext(p.final_poly, h[i], h[M + i]);
     }
     ch.observe_vec(p.final_poly);
+    lg.mark("fri commit phase");
 
     // 8. proof of work
     {
@@ -269,6 +280,7 @@ void prove_table_finish(Ctx& c, TableJob& job, uint64_t challenger_state[12], co
     }
     check_abort(abort_flag);
 
+    lg.mark("pow");
     // 9. query rounds
     std::vector<size_t> xs(cfg.num_queries);
     for (auto& x : xs) x = (size_t)(ch.challenge() % N);
@@ -296,6 +308,7 @@ void prove_table_finish(Ctx& c, TableJob& job, uint64_t challenger_state[12], co
             }
         }
     }
+    lg.mark("queries");
     ch.compact();
     memcpy(challenger_state, ch.state, 96);
     out.words = zkstark::serialize_proof(p);

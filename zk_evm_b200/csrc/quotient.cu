@@ -11,73 +11,11 @@
 // request) for the local row, and — because i+2 only disturbs the high bits of j — another contiguous 32-element run
 // for the next row.  The two running accumulators per challenge live in registers; columns are streamed straight from
 // global memory / L2 (each is touched by a handful of constraints).
-#include "stark_dev.h"
+#include "quotient_kernel.cuh"
 
 namespace zk {
 
 using namespace zkstark;
-
-struct DevRow {
-    const uint64_t* p;
-    size_t stride;
-    __device__ __forceinline__ Fp operator[](uint32_t c) const { return Fp(__ldg(p + (size_t)c * stride)); }
-};
-
-struct QuotKernelArgs {
-    const uint64_t* trace_lde;
-    const uint64_t* aux_lde;
-    uint64_t* out;
-    size_t N;
-    unsigned log_N, nc;
-    uint64_t alphas[2], betas[2], gammas[2];
-    uint64_t w_N;            // generator of the LDE domain
-    uint64_t last;           // w_n^-1
-    uint64_t zh_inv[2];      // 1 / (g^n (-1)^i - 1)
-    uint64_t c_first[2];     // Z_H / n            -> L_first(x) = c_first / (x - 1)
-    uint64_t c_last[2];      // Z_H * last / n     -> L_last(x)  = c_last / (x - last)
-    FlatView flat;
-    TableParams prm;
-};
-
-template <uint32_t TABLE>
-__global__ void __launch_bounds__(128) quotient_kernel(QuotKernelArgs a) {
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= a.N) return;
-    const uint32_t i = bitrev32((uint32_t)j, a.log_N);
-    const uint32_t inext = (i + 2) & (uint32_t)(a.N - 1);
-    const size_t jn = bitrev32(inext, a.log_N);
-    const uint64_t x = gl_mul(GL_GENERATOR, gl_pow(a.w_N, i));
-
-    Consumer<Fp, 2> yc;
-    yc.nc = (int)a.nc;
-#pragma unroll
-    for (int k = 0; k < 2; k++) { yc.alpha[k] = Fp(a.alphas[k]); yc.acc[k] = Fp(0); }
-    const uint64_t xm1 = gl_sub(x, 1), xml = gl_sub(x, a.last);
-    const uint64_t d = gl_inv(gl_mul(xm1, xml));
-    yc.z_last = Fp(xml);
-    yc.lagrange_first = Fp(gl_mul(a.c_first[i & 1], gl_mul(d, xml)));
-    yc.lagrange_last = Fp(gl_mul(a.c_last[i & 1], gl_mul(d, xm1)));
-
-    DevRow lv{a.trace_lde + j, a.N}, nv{a.trace_lde + jn, a.N};
-    DevRow alv{a.aux_lde + j, a.N}, anv{a.aux_lde + jn, a.N};
-
-    if constexpr (TABLE == T_LOGIC) logic::eval<Fp>(lv, nv, yc);
-    else if constexpr (TABLE == T_MEMORY) memory::eval<Fp>(lv, nv, yc);
-    else if constexpr (TABLE == T_MEM_BEFORE || TABLE == T_MEM_AFTER) memcont::eval<Fp>(lv, nv, yc);
-#if ZKS_ALL_TABLES
-    else if constexpr (TABLE == T_ARITHMETIC) arithmetic::eval<Fp>(lv, nv, yc);
-    else if constexpr (TABLE == T_BYTE_PACKING) byte_packing::eval<Fp>(lv, nv, yc);
-    else if constexpr (TABLE == T_CPU) cpu::eval<Fp>(lv, nv, yc, a.prm);
-    else if constexpr (TABLE == T_KECCAK) keccak::eval<Fp>(lv, nv, yc);
-    else if constexpr (TABLE == T_KECCAK_SPONGE) keccak_sponge::eval<Fp>(lv, nv, yc);
-#endif
-
-    Fp betas[2] = {Fp(a.betas[0]), Fp(a.betas[1])}, gammas[2] = {Fp(a.gammas[0]), Fp(a.gammas[1])};
-    flat_eval_lookups<Fp>(a.flat, betas, lv, nv, alv, anv, yc);
-    flat_eval_ctls<Fp>(a.flat, betas, gammas, lv, nv, alv, anv, yc);
-
-    for (unsigned k = 0; k < a.nc; k++) a.out[(size_t)k * a.N + i] = gl_mul(yc.acc[k].v, a.zh_inv[i & 1]);
-}
 
 void quotient_values(Ctx& c, const TableDev& t, const QuotientArgs& q) {
     ZK_REQUIRE(q.num_challenges >= 1 && q.num_challenges <= 2, "num_challenges must be 1 or 2");
@@ -104,15 +42,15 @@ void quotient_values(Ctx& c, const TableDev& t, const QuotientArgs& q) {
     a.prm = q.prm;
     unsigned blocks = (unsigned)((a.N + 127) / 128);
     switch (q.table) {
-        case T_LOGIC: quotient_kernel<T_LOGIC><<<blocks, 128, 0, c.stream>>>(a); break;
-        case T_MEMORY: quotient_kernel<T_MEMORY><<<blocks, 128, 0, c.stream>>>(a); break;
-        case T_MEM_BEFORE: case T_MEM_AFTER: quotient_kernel<T_MEM_BEFORE><<<blocks, 128, 0, c.stream>>>(a); break;
+        case T_LOGIC: launch_quotient<T_LOGIC>(a, blocks, c.stream); break;
+        case T_MEMORY: launch_quotient<T_MEMORY>(a, blocks, c.stream); break;
+        case T_MEM_BEFORE: case T_MEM_AFTER: launch_quotient<T_MEM_BEFORE>(a, blocks, c.stream); break;
 #if ZKS_ALL_TABLES
-        case T_ARITHMETIC: quotient_kernel<T_ARITHMETIC><<<blocks, 128, 0, c.stream>>>(a); break;
-        case T_BYTE_PACKING: quotient_kernel<T_BYTE_PACKING><<<blocks, 128, 0, c.stream>>>(a); break;
-        case T_CPU: quotient_kernel<T_CPU><<<blocks, 128, 0, c.stream>>>(a); break;
-        case T_KECCAK: quotient_kernel<T_KECCAK><<<blocks, 128, 0, c.stream>>>(a); break;
-        case T_KECCAK_SPONGE: quotient_kernel<T_KECCAK_SPONGE><<<blocks, 128, 0, c.stream>>>(a); break;
+        case T_ARITHMETIC: launch_quotient<T_ARITHMETIC>(a, blocks, c.stream); break;
+        case T_BYTE_PACKING: launch_quotient<T_BYTE_PACKING>(a, blocks, c.stream); break;
+        case T_CPU: launch_quotient<T_CPU>(a, blocks, c.stream); break;
+        case T_KECCAK: launch_quotient<T_KECCAK>(a, blocks, c.stream); break;
+        case T_KECCAK_SPONGE: launch_quotient<T_KECCAK_SPONGE>(a, blocks, c.stream); break;
 #endif
         default: throw ZkError(ZKGPU_ERR_INVALID, "quotient: table id not supported");
     }

@@ -139,6 +139,7 @@ int zkgpu_prove_segment(zkgpu_ctx* h, const zkgpu_table_trace* traces, int mem_k
     for (uint32_t t = 0; t < ZKGPU_NUM_TABLES; t++) proofs_out[t] = nullptr;
 
     // 1. trace commitments (prover.rs:92-116)
+    StageLog lg(c);
     std::unique_ptr<zkgpu_batch> tb[ZKGPU_NUM_TABLES];
     std::vector<uint64_t> caps(ZKGPU_NUM_TABLES * cap_words, 0);
     uint8_t in_use[ZKGPU_NUM_TABLES];
@@ -152,7 +153,9 @@ int zkgpu_prove_segment(zkgpu_ctx* h, const zkgpu_table_trace* traces, int mem_k
         b.values = DevBuf(&c, b.ncols * b.n * 8);
         ZK_CUDA(cudaMemcpyAsync(b.values.get(), traces[t].cols, b.ncols * b.n * 8,
                                 mem_kind == ZKGPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
+        lg.mark("trace upload");
         commit_from_device_values(c, b, true);
+        lg.mark(zkstark::table_name(t));
         memcpy(&caps[t * cap_words], b.cap_host.data(), cap_words * 8);
     }
     if (trace_caps_out) memcpy(trace_caps_out, caps.data(), caps.size() * 8);
@@ -171,10 +174,13 @@ int zkgpu_prove_segment(zkgpu_ctx* h, const zkgpu_table_trace* traces, int mem_k
     for (uint32_t t = 0; t < ZKGPU_NUM_TABLES; t++) {
         if (!in_use[t]) continue;
         Ctl ctl;
+        lg.mark("--");
         make_ctl_data(c, t, tb[t]->b, bg, cfg.num_challenges, ctl);
+        lg.mark("ctl data");
         proofs[t].reset(new zkgpu_proof());
         prove_table(c, t, prm, cfg, tb[t]->b, ctl, st, forced_pow_witnesses ? &forced_pow_witnesses[t] : nullptr, abort_flag, proofs[t]->p);
         tb[t].reset();   // release the table's device memory before the next one
+        lg.mark(zkstark::table_name(t));
     }
     for (uint32_t t = 0; t < ZKGPU_NUM_TABLES; t++) proofs_out[t] = proofs[t].release();
     ZK_API_END
