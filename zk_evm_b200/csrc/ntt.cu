@@ -33,6 +33,45 @@ struct PassParams {
     unsigned prescale_mask;          // table = (t & mask) ? prescale1 : prescale0
 };
 
+// K consecutive DIF stages (halves 2^s ... 2^(s-K+1)) of the size-2^r transforms held in sm[jd * 2^t + u]: every work item
+// loads the 2^K elements jd = (hi << (s+1)) | (k << (s-K+1)) | lo, k < 2^K, runs the K stages in registers and writes them
+// back, so shared memory is touched once per K stages.  Items are numbered u fastest, then lo, then hi: for a fixed k a
+// warp reads 32 consecutive elements whenever 2^t * 2^(s-K+1) >= 32.
+template <int K, int THREADS>
+__device__ __forceinline__ void dif_round(uint64_t* sm, const uint64_t* __restrict__ roots, int s, unsigned r, unsigned t) {
+    constexpr int E = 1 << K;
+    const int low = s - K + 1;
+    const unsigned items = (1u << (r - K)) << t;
+    for (unsigned w = threadIdx.x; w < items; w += THREADS) {
+        const unsigned u = w & ((1u << t) - 1), g = w >> t;
+        const unsigned lo = g & ((1u << low) - 1), hi = g >> low;
+        const unsigned base = ((((hi << K) << low) | lo) << t) + u;     // element k lives at base + (k << (low + t))
+        uint64_t x[E];
+#pragma unroll
+        for (int k = 0; k < E; k++) x[k] = sm[base + ((unsigned)k << (low + t))];
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            const int lh = s - j;                  // this stage's log2(half), in units of jd
+            constexpr int dummy = 0; (void)dummy;
+            const int hk = 1 << (K - 1 - j);       // the partner's distance in k
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                if (k & hk) continue;
+                uint64_t a = x[k], b = x[k + hk];
+                x[k] = gl_add(a, b);
+                uint64_t d = gl_sub(a, b);
+                if (lh > 0) {
+                    const unsigned j_in = ((unsigned)(k & (hk - 1)) << low) | lo;
+                    d = gl_mul(d, __ldg(roots + ((size_t)j_in << (ROOT_LOG - 1 - lh))));
+                }
+                x[k + hk] = d;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < E; k++) sm[base + ((unsigned)k << (low + t))] = x[k];
+    }
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) ntt_dif_pass_kernel(PassParams p) {
     extern __shared__ uint64_t sm[];
@@ -72,22 +111,18 @@ __global__ void __launch_bounds__(THREADS) ntt_dif_pass_kernel(PassParams p) {
     }
     __syncthreads();
 
-    // ---- r radix-2 DIF stages over jd ----
-    const unsigned nb = tile_elems >> 1;
-    for (unsigned lh = r; lh-- > 0;) {   // log2(half): r-1 ... 0
-        const unsigned half = 1u << lh;
-        for (unsigned b = threadIdx.x; b < nb; b += THREADS) {
-            unsigned u = b & (T - 1), q = b >> t;
-            unsigned j_in = q & (half - 1);
-            unsigned jd0 = ((q >> lh) << (lh + 1)) | j_in;
-            unsigned i0 = (jd0 << t) + u, i1 = i0 + (half << t);
-            uint64_t a = sm[i0], c = sm[i1];
-            uint64_t s = gl_add(a, c), d = gl_sub(a, c);
-            if (lh) d = gl_mul(d, __ldg(p.roots + ((size_t)j_in << (ROOT_LOG - 1 - lh))));
-            sm[i0] = s;
-            sm[i1] = d;
-        }
+    // ---- r radix-2 DIF stages over jd, K (<= 3) stages per shared-memory round trip on a register tile of 2^K elements ----
+    {
+        int s = (int)r - 1;                       // log2(half) of the next stage
+        const int first = (r % 3) ? (int)(r % 3) : 3;
+        if (first == 1) dif_round<1, THREADS>(sm, p.roots, s, r, t);
+        else if (first == 2) dif_round<2, THREADS>(sm, p.roots, s, r, t);
+        else dif_round<3, THREADS>(sm, p.roots, s, r, t);
         __syncthreads();
+        for (s -= first; s >= 0; s -= 3) {
+            dif_round<3, THREADS>(sm, p.roots, s, r, t);
+            __syncthreads();
+        }
     }
 
     // ---- inter-pass twiddle + store (in place: digit position jd_pos holds kd = rev_r(jd_pos)) ----
