@@ -20,56 +20,125 @@
 namespace zk {
 
 // ---- openings ---------------------------------------------------------------------------------------------------
+// f(zeta), f(g zeta) and f(1) for every coefficient column.  The coefficients are base-field elements, so with a table of the
+// powers zeta^i and (g zeta)^i (built once per table proof, shared by all columns, L2-resident) each coefficient costs four
+// 64x64 products accumulated WITHOUT reduction: the partial products a0*b0, a0*b1 + a1*b0, a1*b1 of every term go to three
+// 96-bit accumulators per component (no carry counters: a 96-bit accumulator holds 2^32 64-bit terms), reduced once per
+// thread, then a block reduction.  The previous form (extension Horner in zeta^T per thread) cost ~10 field products per coefficient.
 static constexpr int EVAL_THREADS = 256;
-static constexpr size_t EVAL_SEG = (size_t)1 << 14;
+static constexpr int EVAL_K = 16;                 // coefficient indices per thread
+static constexpr int EVAL_G = 2;                  // columns per block
 
-__device__ __forceinline__ Fp2 fp2_mul_base(Fp2 x, uint64_t s) { return Fp2(gl_mul(x.a, s), gl_mul(x.b, s)); }
+struct Acc96 { uint32_t w0, w1, w2; };
+__device__ __forceinline__ void acc96_add(Acc96& a, uint64_t v) {
+    uint32_t lo, hi; gl_unpack(v, lo, hi);
+    asm("add.cc.u32 %0, %0, %3;\n\t"
+        "addc.cc.u32 %1, %1, %4;\n\t"
+        "addc.u32 %2, %2, 0;\n\t" : "+r"(a.w0), "+r"(a.w1), "+r"(a.w2) : "r"(lo), "r"(hi));
+}
+// sum_i c_i * b_i for 64-bit c, b: lo += c0*b0, mid += c0*b1 + c1*b0 (weight 2^32), hi += c1*b1 (weight 2^64)
+struct Dot { Acc96 lo, mid, hi; };
+__device__ __forceinline__ void dot_init(Dot& d) { d.lo = {0, 0, 0}; d.mid = {0, 0, 0}; d.hi = {0, 0, 0}; }
+__device__ __forceinline__ void dot_mac(Dot& d, uint32_t c0, uint32_t c1, uint64_t b) {
+    uint32_t b0, b1; gl_unpack(b, b0, b1);
+    uint64_t p;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(c0), "r"(b0)); acc96_add(d.lo, p);
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(c0), "r"(b1)); acc96_add(d.mid, p);
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(c1), "r"(b0)); acc96_add(d.mid, p);
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(p) : "r"(c1), "r"(b1)); acc96_add(d.hi, p);
+}
+// a 96-bit value mod p: w0 + 2^32 w1 + 2^64 w2
+__device__ __forceinline__ uint64_t acc96_reduce(const Acc96& a) { return gld_reduce_words(a.w0, a.w1, a.w2, 0); }
+__device__ __forceinline__ uint64_t dot_reduce(const Dot& d) {
+    // lo + 2^32 mid + 2^64 hi ;  2^32 and 2^64 == 2^32 - 1 are field constants
+    uint64_t r = acc96_reduce(d.lo);
+    r = gl_add(r, gl_mul(acc96_reduce(d.mid), (uint64_t)1 << 32));
+    r = gl_add(r, gl_mul(acc96_reduce(d.hi), GL_EPS));
+    return r;
+}
 
-__global__ void __launch_bounds__(EVAL_THREADS) eval_columns_kernel(const uint64_t* __restrict__ coeffs, size_t n, size_t seg_len, Fp2 zeta,
-                                                                    Fp2 zeta_next, uint64_t* __restrict__ partial, size_t nseg) {
-    __shared__ uint64_t sm[5][EVAL_THREADS];
-    const size_t col = blockIdx.y, seg = blockIdx.x;
-    const uint64_t* p = coeffs + col * n + seg * seg_len;
+// tab[i] = (zeta^i.a, zeta^i.b, (g zeta)^i.a, (g zeta)^i.b), i < n; each thread starts from a power and walks 16 steps
+__global__ void eval_powers_kernel(ulonglong4* __restrict__ tab, size_t n, Fp2 zeta, Fp2 zeta_next) {
+    size_t start = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (start >= n) return;
+    Fp2 a = fp2_pow(zeta, start), b = fp2_pow(zeta_next, start);
+    for (size_t i = start; i < start + 16 && i < n; i++) {
+        tab[i] = make_ulonglong4(a.a, a.b, b.a, b.b);
+        a = a * zeta; b = b * zeta_next;
+    }
+}
+
+__global__ void __launch_bounds__(EVAL_THREADS) eval_columns_kernel(const uint64_t* __restrict__ coeffs, size_t ncols, size_t n,
+                                                                    const ulonglong4* __restrict__ tab, uint64_t* __restrict__ partial,
+                                                                    size_t nseg) {
+    __shared__ uint64_t sm[EVAL_G * 5][EVAL_THREADS / 32];
+    const size_t seg = blockIdx.x, col0 = (size_t)blockIdx.y * EVAL_G;
     const unsigned t = threadIdx.x;
-    // thread t: sum_k c[t + kT] (z^T)^k, then * z^(seg*seg_len + t)
-    Fp2 acc0(0, 0), acc1(0, 0);
-    uint64_t acc2 = 0;
-    if (t < seg_len) {
-        const Fp2 zT = fp2_pow(zeta, EVAL_THREADS), znT = fp2_pow(zeta_next, EVAL_THREADS);
-        size_t kmax = (seg_len - t + EVAL_THREADS - 1) / EVAL_THREADS;
-        for (size_t k = kmax; k-- > 0;) {
-            uint64_t cval = p[t + k * EVAL_THREADS];
-            acc0 = acc0 * zT; acc0.a = gl_add(acc0.a, cval);
-            acc1 = acc1 * znT; acc1.a = gl_add(acc1.a, cval);
-            acc2 = gl_add(acc2, cval);
-        }
-        uint64_t e = seg * seg_len + t;
-        acc0 = acc0 * fp2_pow(zeta, e);
-        acc1 = acc1 * fp2_pow(zeta_next, e);
-    }
-    sm[0][t] = acc0.a; sm[1][t] = acc0.b; sm[2][t] = acc1.a; sm[3][t] = acc1.b; sm[4][t] = acc2;
-    __syncthreads();
-    for (int off = EVAL_THREADS / 2; off > 0; off >>= 1) {
-        if (t < off)
+    const size_t seg_len = (size_t)EVAL_THREADS * EVAL_K;
+    Dot d[EVAL_G][4];
+    Acc96 one[EVAL_G];
 #pragma unroll
-            for (int q = 0; q < 5; q++) sm[q][t] = gl_add(sm[q][t], sm[q][t + off]);
-        __syncthreads();
+    for (int g = 0; g < EVAL_G; g++) { one[g] = {0, 0, 0}; for (int q = 0; q < 4; q++) dot_init(d[g][q]); }
+#pragma unroll 1
+    for (int k = 0; k < EVAL_K; k++) {
+        size_t i = seg * seg_len + (size_t)k * EVAL_THREADS + t;
+        if (i >= n) break;
+        const ulonglong2 pw0 = __ldg(reinterpret_cast<const ulonglong2*>(tab + i)), pw1 = __ldg(reinterpret_cast<const ulonglong2*>(tab + i) + 1);
+#pragma unroll
+        for (int g = 0; g < EVAL_G; g++) {
+            if (col0 + g >= ncols) break;
+            const uint64_t cv = __ldg(coeffs + (col0 + g) * n + i);
+            uint32_t c0, c1; gl_unpack(cv, c0, c1);
+            dot_mac(d[g][0], c0, c1, pw0.x); dot_mac(d[g][1], c0, c1, pw0.y);
+            dot_mac(d[g][2], c0, c1, pw1.x); dot_mac(d[g][3], c0, c1, pw1.y);
+            acc96_add(one[g], cv);
+        }
     }
-    if (t < 5) partial[(col * nseg + seg) * 5 + t] = sm[t][0];
+    // per-thread reduction to field elements, warp shuffle tree, then one value per warp through shared memory
+#pragma unroll
+    for (int g = 0; g < EVAL_G; g++) {
+#pragma unroll
+        for (int q = 0; q < 5; q++) {
+            uint64_t v = q < 4 ? dot_reduce(d[g][q]) : acc96_reduce(one[g]);
+            for (int off = 16; off > 0; off >>= 1) v = gl_add(v, __shfl_down_sync(0xFFFFFFFFu, v, off));
+            if ((t & 31) == 0) sm[g * 5 + q][t >> 5] = v;
+        }
+    }
+    __syncthreads();
+    if (t < EVAL_G * 5) {
+        uint64_t v = 0;
+        for (int w = 0; w < EVAL_THREADS / 32; w++) v = gl_add(v, sm[t][w]);
+        size_t col = col0 + t / 5;
+        if (col < ncols) partial[(col * nseg + seg) * 5 + (t % 5)] = v;
+    }
 }
 
 void eval_columns(Ctx& c, const uint64_t* coeffs, size_t ncols, size_t n, Fp2 zeta, Fp2 zeta_next, std::vector<uint64_t>& out5) {
     KernelScope ks(c, KF_OPENINGS, 8.0 * n * ncols);
     out5.assign(ncols * 5, 0);
     if (!ncols) return;
-    size_t seg_len = n < EVAL_SEG ? n : EVAL_SEG;
-    size_t nseg = n / seg_len;
+    // power table: cached per (zeta, n) for the three calls (trace, aux, quotient) of one table proof
+    std::string key = "evalpow";
+    auto it = c.table_cache.find(key);
+    if (it == c.table_cache.end() || c.evalpow_n != n || !(c.evalpow_zeta[0] == zeta.a && c.evalpow_zeta[1] == zeta.b)) {
+        if (it != c.table_cache.end()) c.table_cache.erase(it);
+        DevBuf b(&c, n * 32);
+        eval_powers_kernel<<<(unsigned)(((n + 15) / 16 + 127) / 128), 128, 0, c.stream>>>((ulonglong4*)b.get(), n, zeta, zeta_next);
+        c.count_launch();
+        c.check_launch("eval_powers_kernel");
+        it = c.table_cache.emplace(key, std::move(b)).first;
+        c.evalpow_n = n; c.evalpow_zeta[0] = zeta.a; c.evalpow_zeta[1] = zeta.b;
+    }
+    const ulonglong4* tab = (const ulonglong4*)it->second.get();
+    const size_t seg_len = (size_t)EVAL_THREADS * EVAL_K;
+    size_t nseg = (n + seg_len - 1) / seg_len;
     DevBuf partial(&c, ncols * nseg * 5 * 8);
-    for (size_t c0 = 0; c0 < ncols; c0 += 65535) {
-        unsigned cnt = (unsigned)std::min<size_t>(65535, ncols - c0);
+    size_t groups = (ncols + EVAL_G - 1) / EVAL_G;
+    for (size_t g0 = 0; g0 < groups; g0 += 65535) {
+        unsigned cnt = (unsigned)std::min<size_t>(65535, groups - g0);
         dim3 grid((unsigned)nseg, cnt);
-        eval_columns_kernel<<<grid, EVAL_THREADS, 0, c.stream>>>(coeffs + c0 * n, n, seg_len, zeta, zeta_next,
-                                                                 partial.get() + c0 * nseg * 5, nseg);
+        eval_columns_kernel<<<grid, EVAL_THREADS, 0, c.stream>>>(coeffs + g0 * EVAL_G * n, ncols - g0 * EVAL_G, n, tab,
+                                                                 partial.get() + g0 * EVAL_G * nseg * 5, nseg);
         c.count_launch();
     }
     c.check_launch("eval_columns_kernel");
@@ -79,6 +148,8 @@ void eval_columns(Ctx& c, const uint64_t* coeffs, size_t ncols, size_t n, Fp2 ze
         for (size_t s = 0; s < nseg; s++)
             for (int q = 0; q < 5; q++) out5[col * 5 + q] = gl_add(out5[col * 5 + q], h[(col * nseg + s) * 5 + q]);
 }
+
+__device__ __forceinline__ Fp2 fp2_mul_base(Fp2 x, uint64_t s) { return Fp2(gl_mul(x.a, s), gl_mul(x.b, s)); }
 
 // ---- batch reduction straight to coset values --------------------------------------------------------------------
 struct CombineKernelArgs {

@@ -30,7 +30,7 @@ ZK_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
 #endif
 }
 
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 // ---- device forms: carry-flag arithmetic instead of compare/select chains ------------------------------------------------
 // Measured on sm_100a (tools/pipebench.cu): IADD3/LOP3/LEA issue at 1 warp-instr/clk/SMSP, IMAD at 1/2, IMAD.WIDE and
 // IMAD.HI at 1/4 and not overlapped with the ALU pipe — so a product is four IMAD.WIDE and everything else is IADD3 carry chains.
@@ -38,7 +38,7 @@ __device__ __forceinline__ void gl_unpack(uint64_t x, uint32_t& lo, uint32_t& hi
 __device__ __forceinline__ uint64_t gl_pack(uint32_t lo, uint32_t hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
 
 // (a - b) mod p for any a and b <= p; canonical when a < p
-__device__ __forceinline__ uint64_t gl_sub(uint64_t a, uint64_t b) {
+__device__ __forceinline__ uint64_t gld_sub(uint64_t a, uint64_t b) {
     uint32_t a0, a1, b0, b1, m;
     gl_unpack(a, a0, a1); gl_unpack(b, b0, b1);
     asm("sub.cc.u32 %0, %0, %3;\n\t"
@@ -48,13 +48,13 @@ __device__ __forceinline__ uint64_t gl_sub(uint64_t a, uint64_t b) {
         "subc.u32 %1, %1, 0;\n\t" : "+r"(a0), "+r"(a1) : "r"(m));                        // + p == - EPS (mod 2^64)
     return gl_pack(a0, a1);
 }
-__device__ __forceinline__ uint64_t gl_neg(uint64_t a) { return gl_sub(0, a); }
+__device__ __forceinline__ uint64_t gld_neg(uint64_t a) { return gld_sub(0, a); }
 // a + b = a - (p - b); p - b is computed without reduction (b <= p), p - 0 = p is a valid second operand of gl_sub
-__device__ __forceinline__ uint64_t gl_add(uint64_t a, uint64_t b) { return gl_sub(a, GL_P - b); }
-__device__ __forceinline__ uint64_t gl_dbl(uint64_t a) { return gl_add(a, a); }
+__device__ __forceinline__ uint64_t gld_add(uint64_t a, uint64_t b) { return gld_sub(a, GL_P - b); }
+__device__ __forceinline__ uint64_t gld_dbl(uint64_t a) { return gld_add(a, a); }
 
 // w0 + 2^32 w1 + 2^64 w2 + 2^96 w3 -> canonical
-__device__ __forceinline__ uint64_t gl_reduce_words(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+__device__ __forceinline__ uint64_t gld_reduce_words(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
     uint32_t t0, t1, m, u0, u1;
     asm("sub.cc.u32 %0, %3, %5;\n\t"
         "subc.cc.u32 %1, %4, 0;\n\t"
@@ -72,12 +72,12 @@ __device__ __forceinline__ uint64_t gl_reduce_words(uint32_t w0, uint32_t w1, ui
     uint64_t r = gl_pack(t0, t1);
     return r >= GL_P ? r - GL_P : r;
 }
-__device__ __forceinline__ uint64_t gl_reduce128(uint64_t lo, uint64_t hi) {
+__device__ __forceinline__ uint64_t gld_reduce128(uint64_t lo, uint64_t hi) {
     uint32_t w0, w1, w2, w3;
     gl_unpack(lo, w0, w1); gl_unpack(hi, w2, w3);
-    return gl_reduce_words(w0, w1, w2, w3);
+    return gld_reduce_words(w0, w1, w2, w3);
 }
-__device__ __forceinline__ uint64_t gl_mul(uint64_t a, uint64_t b) {
+__device__ __forceinline__ uint64_t gld_mul(uint64_t a, uint64_t b) {
     uint32_t a0, a1, b0, b1;
     gl_unpack(a, a0, a1); gl_unpack(b, b0, b1);
     uint64_t p00, mid, mid2, hi;
@@ -89,23 +89,38 @@ __device__ __forceinline__ uint64_t gl_mul(uint64_t a, uint64_t b) {
     uint32_t w1, m2; gl_unpack(mid2, w1, m2);
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(hi) : "r"(a1), "r"(b1), "l"((uint64_t)m1 + (uint64_t)m2));
     uint32_t w2, w3; gl_unpack(hi, w2, w3);
-    return gl_reduce_words(w0, w1, w2, w3);
+    return gld_reduce_words(w0, w1, w2, w3);
 }
-#else
+#endif  // __CUDACC__
+
 ZK_HD uint64_t gl_add(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return gld_add(a, b);
+#endif
     uint64_t s = a + b;
     // a, b < p so the true sum is < 2p: one conditional subtraction
     return (s < a || s >= GL_P) ? s - GL_P : s;
 }
 ZK_HD uint64_t gl_sub(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return gld_sub(a, b);
+#endif
     uint64_t d = a - b;
     return (a < b) ? d + GL_P : d;
 }
-ZK_HD uint64_t gl_neg(uint64_t a) { return a ? GL_P - a : 0; }
+ZK_HD uint64_t gl_neg(uint64_t a) {
+#if defined(__CUDA_ARCH__)
+    return gld_neg(a);
+#endif
+    return a ? GL_P - a : 0;
+}
 ZK_HD uint64_t gl_dbl(uint64_t a) { return gl_add(a, a); }
 
 // reduce lo + 2^64 * hi to a canonical element
 ZK_HD uint64_t gl_reduce128(uint64_t lo, uint64_t hi) {
+#if defined(__CUDA_ARCH__)
+    return gld_reduce128(lo, hi);
+#endif
     uint64_t hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
     uint64_t t0 = lo - hi_hi;
     if (lo < hi_hi) t0 -= GL_EPS;           // borrowed 2^64 == EPS (mod p)
@@ -114,8 +129,12 @@ ZK_HD uint64_t gl_reduce128(uint64_t lo, uint64_t hi) {
     if (t2 < t1) t2 += GL_EPS;              // carried 2^64 == EPS; cannot carry again
     return t2 >= GL_P ? t2 - GL_P : t2;
 }
-ZK_HD uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_reduce128(a * b, mulhi64(a, b)); }
+ZK_HD uint64_t gl_mul(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return gld_mul(a, b);
 #endif
+    return gl_reduce128(a * b, mulhi64(a, b));
+}
 ZK_HD uint64_t gl_sqr(uint64_t a) { return gl_mul(a, a); }
 // reduce a 96-bit value lo + 2^64 * hi32 (hi32 < 2^32)
 ZK_HD uint64_t gl_reduce96(uint64_t lo, uint32_t hi32) {

@@ -111,6 +111,7 @@ struct Ctx {
     double prof_ms[KF_COUNT] = {0}, prof_bytes[KF_COUNT] = {0};
     uint64_t prof_launches[KF_COUNT] = {0};
     void prof_collect();   // resolve finished event pairs (synchronises the stream)
+    size_t evalpow_n = 0; uint64_t evalpow_zeta[2] = {0, 0};   // key of the cached zeta-power table (fri.cu eval_columns)
     bool debug = false;   // proofs keep their aux / quotient batches and FRI input values for stage-by-stage parity tests
     // pinned staging buffer for H2D / D2H of pageable memory
     void* staging = nullptr;

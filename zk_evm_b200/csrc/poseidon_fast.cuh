@@ -157,45 +157,7 @@ constexpr PfRc3 pf_make_rc3() {
 }
 static __device__ __constant__ PfRc3 POSEIDON_RC3_DEV = pf_make_rc3();
 
-__device__ __forceinline__ void pf_mds_fft_limb(const uint32_t s[12], uint32_t o[12]) {
-    uint32_t F1[3], Fm[3], Fc[3], Fd[3];
-#pragma unroll
-    for (int b = 0; b < 3; b++) {
-        uint32_t x0 = s[b], x1 = s[b + 3], x2 = s[b + 6], x3 = s[b + 9];
-        uint32_t A = x0 + x2, B = x1 + x3;
-        Fc[b] = x0 - x2; Fd[b] = x1 - x3;
-        F1[b] = A + B; Fm[b] = A - B;
-    }
-    uint32_t T = F1[0] + F1[1] + F1[2];
-    uint32_t G1[3] = {(T + F1[2]) << 4, (T + F1[0]) << 4, (T + F1[1]) << 4};
-    uint32_t Gm[3] = {(Fm[2] << 3) - (Fm[1] << 1) - Fm[0], 0u - (Fm[0] << 3) - (Fm[2] << 1) - Fm[1], (Fm[0] << 1) - (Fm[1] << 3) - Fm[2]};
-    // complex products with k0 = 2+i, k1 = -4-i, k2 = 16-i :  (p+qi)(c+di) = (pc - qd) + (pd + qc) i
-    //   k0 F = (2c - d, 2d + c) ; k1 F = (-4c + d, -4d - c) ; k2 F = (16c + d, 16d - c)
-    // Gi_0 = k0 F0 + i (k1 F2 + k2 F1) ; Gi_1 = k0 F1 + k1 F0 + i k2 F2 ; Gi_2 = k0 F2 + k1 F1 + k2 F0
-    uint32_t u[3], v[3];
-    {
-        // k1 F2 + k2 F1 = (-4c2 + d2 + 16c1 + d1, -4d2 - c2 + 16d1 - c1); times i -> (-(im), re)
-        uint32_t re = (Fc[1] << 4) - (Fc[2] << 2) + Fd[2] + Fd[1];
-        uint32_t im = (Fd[1] << 4) - (Fd[2] << 2) - Fc[2] - Fc[1];
-        u[0] = (Fc[0] << 1) - Fd[0] - im;
-        v[0] = (Fd[0] << 1) + Fc[0] + re;
-    }
-    {
-        // k0 F1 + k1 F0 + i k2 F2, k2 F2 = (16c2 + d2, 16d2 - c2) -> i * = (-(16d2 - c2), 16c2 + d2)
-        u[1] = (Fc[1] << 1) - Fd[1] - (Fc[0] << 2) + Fd[0] - (Fd[2] << 4) + Fc[2];
-        v[1] = (Fd[1] << 1) + Fc[1] - (Fd[0] << 2) - Fc[0] + (Fc[2] << 4) + Fd[2];
-    }
-    {
-        u[2] = (Fc[2] << 1) - Fd[2] - (Fc[1] << 2) + Fd[1] + (Fc[0] << 4) + Fd[0];
-        v[2] = (Fd[2] << 1) + Fc[2] - (Fd[1] << 2) - Fc[1] + (Fd[0] << 4) - Fc[0];
-    }
-#pragma unroll
-    for (int b = 0; b < 3; b++) {
-        uint32_t P = G1[b] + Gm[b], Q = G1[b] - Gm[b];
-        o[b] = P + u[b]; o[b + 3] = Q + v[b]; o[b + 6] = P - u[b]; o[b + 9] = Q - v[b];
-    }
-    o[0] += s[0] << 3;
-}
+__device__ __forceinline__ void pf_mds_fft_limb(const uint32_t s[12], uint32_t o[12]) { poseidon_mds_freq<uint32_t>(s, o); }
 
 // rc3: the next round's constants pre-split into the same limbs ([12][3]), or nullptr
 template <bool ADD_RC>
