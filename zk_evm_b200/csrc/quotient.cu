@@ -17,6 +17,38 @@ namespace zk {
 
 using namespace zkstark;
 
+__global__ void quotient_domain_kernel(DomArgs a) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.N) return;
+    const uint32_t i = bitrev32((uint32_t)j, a.log_N);
+    const uint64_t x = gl_mul(GL_GENERATOR, gl_pow(a.w_N, i));
+    const uint64_t xm1 = gl_sub(x, 1), xml = gl_sub(x, a.last);
+    const uint64_t d = gl_inv(gl_mul(xm1, xml));
+    a.dom[j] = xml;
+    a.dom[a.N + j] = gl_mul(a.c_first[i & 1], gl_mul(d, xml));      // L_first(x) = (Z_H(x) / n) / (x - 1)
+    a.dom[2 * a.N + j] = gl_mul(a.c_last[i & 1], gl_mul(d, xm1));   // L_last(x) = (Z_H(x) w_n^-1 / n) / (x - w_n^-1)
+}
+
+static const uint64_t* get_domain(Ctx& c, unsigned k, const uint64_t zh[2]) {
+    std::string key = "qdom:" + std::to_string(k);
+    auto it = c.table_cache.find(key);
+    if (it != c.table_cache.end()) return it->second.get();
+    DomArgs a;
+    a.log_N = k + 1; a.N = (size_t)2 << k;
+    DevBuf b(&c, 3 * a.N * 8);
+    a.dom = b.get();
+    a.w_N = gl_root_of_unity(k + 1);
+    a.last = gl_inv(gl_root_of_unity(k));
+    uint64_t ninv = gl_inv(gl_canon((uint64_t)1 << k));
+    for (int h = 0; h < 2; h++) { a.c_first[h] = gl_mul(zh[h], ninv); a.c_last[h] = gl_mul(gl_mul(zh[h], a.last), ninv); }
+    quotient_domain_kernel<<<(unsigned)((a.N + 127) / 128), 128, 0, c.stream>>>(a);
+    c.count_launch();
+    c.check_launch("quotient_domain_kernel");
+    const uint64_t* p = b.get();
+    c.table_cache.emplace(key, std::move(b));
+    return p;
+}
+
 void quotient_values(Ctx& c, const TableDev& t, const QuotientArgs& q) {
     ZK_REQUIRE(q.num_challenges >= 1 && q.num_challenges <= 2, "num_challenges must be 1 or 2");
     // each LDE row of trace + aux read once, num_challenges values per point written (16n(c+a) + 16n*nc)
@@ -28,16 +60,10 @@ void quotient_values(Ctx& c, const TableDev& t, const QuotientArgs& q) {
     for (unsigned i = 0; i < 2; i++) {
         a.alphas[i] = i < a.nc ? q.alphas[i] : 0; a.betas[i] = i < a.nc ? q.betas[i] : 0; a.gammas[i] = i < a.nc ? q.gammas[i] : 0;
     }
-    a.w_N = gl_root_of_unity(k + 1);
-    a.last = gl_inv(gl_root_of_unity(k));
     uint64_t gn = gl_pow(GL_GENERATOR, (uint64_t)1 << k);
     uint64_t zh[2] = {gl_sub(gn, 1), gl_sub(gl_neg(gn), 1)};
-    uint64_t ninv = gl_inv(gl_canon((uint64_t)1 << k));
-    for (int b = 0; b < 2; b++) {
-        a.zh_inv[b] = gl_inv(zh[b]);
-        a.c_first[b] = gl_mul(zh[b], ninv);
-        a.c_last[b] = gl_mul(gl_mul(zh[b], a.last), ninv);
-    }
+    for (int b = 0; b < 2; b++) a.zh_inv[b] = gl_inv(zh[b]);
+    a.dom = get_domain(c, k, zh);
     a.flat = t.view;
     a.prm = q.prm;
     unsigned blocks = (unsigned)((a.N + 127) / 128);

@@ -33,33 +33,30 @@ struct QuotKernelArgs {
     size_t N;
     unsigned log_N, nc;
     uint64_t alphas[2], betas[2], gammas[2];
-    uint64_t w_N;            // generator of the LDE domain
-    uint64_t last;           // w_n^-1
+    // per-point domain values in storage order j (they depend on log_N only; built once per size and cached):
+    // dom[j] = x - w_n^-1 (vanishes on the last row), dom[N + j] = L_first(x), dom[2N + j] = L_last(x), x = g w_N^bitrev(j)
+    const uint64_t* dom;
     uint64_t zh_inv[2];      // 1 / (g^n (-1)^i - 1)
-    uint64_t c_first[2];     // Z_H / n            -> L_first(x) = c_first / (x - 1)
-    uint64_t c_last[2];      // Z_H * last / n     -> L_last(x)  = c_last / (x - last)
     FlatView flat;
     TableParams prm;
 };
 
 template <uint32_t TABLE>
 __global__ void __launch_bounds__(128) quotient_kernel(QuotKernelArgs a) {
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= a.N) return;
+    // the grid covers exactly N points (block = min(128, N) threads, N a power of two): no early exit, the constraint code
+    // contains block-wide barriers (ZKS_SYNC)
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t i = bitrev32((uint32_t)j, a.log_N);
     const uint32_t inext = (i + 2) & (uint32_t)(a.N - 1);
     const size_t jn = bitrev32(inext, a.log_N);
-    const uint64_t x = gl_mul(GL_GENERATOR, gl_pow(a.w_N, i));
 
     Consumer<Fp, 2> yc;
     yc.nc = (int)a.nc;
 #pragma unroll
     for (int k = 0; k < 2; k++) { yc.alpha[k] = Fp(a.alphas[k]); yc.acc[k] = Fp(0); }
-    const uint64_t xm1 = gl_sub(x, 1), xml = gl_sub(x, a.last);
-    const uint64_t d = gl_inv(gl_mul(xm1, xml));
-    yc.z_last = Fp(xml);
-    yc.lagrange_first = Fp(gl_mul(a.c_first[i & 1], gl_mul(d, xml)));
-    yc.lagrange_last = Fp(gl_mul(a.c_last[i & 1], gl_mul(d, xm1)));
+    yc.z_last = Fp(__ldg(a.dom + j));
+    yc.lagrange_first = Fp(__ldg(a.dom + a.N + j));
+    yc.lagrange_last = Fp(__ldg(a.dom + 2 * a.N + j));
 
     DevRow lv{a.trace_lde + j, a.N}, nv{a.trace_lde + jn, a.N};
     DevRow alv{a.aux_lde + j, a.N}, anv{a.aux_lde + jn, a.N};
@@ -82,11 +79,14 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotKernelArgs a) {
     for (unsigned k = 0; k < a.nc; k++) a.out[(size_t)k * a.N + i] = gl_mul(yc.acc[k].v, a.zh_inv[i & 1]);
 }
 
+// domain table of the quotient kernels (see QuotKernelArgs::dom)
+struct DomArgs { uint64_t* dom; size_t N; unsigned log_N; uint64_t w_N, last, c_first[2], c_last[2]; };
+
 // one launcher per table, defined in quotient_t<N>.cu
 template <uint32_t TABLE> void launch_quotient(const QuotKernelArgs& a, unsigned blocks, cudaStream_t stream);
 #define ZK_INSTANTIATE_QUOTIENT(TABLE)                                                                       \
     template <> void launch_quotient<TABLE>(const QuotKernelArgs& a, unsigned blocks, cudaStream_t stream) { \
-        quotient_kernel<TABLE><<<blocks, 128, 0, stream>>>(a);                                               \
+        quotient_kernel<TABLE><<<blocks, a.N < 128 ? (unsigned)a.N : 128u, 0, stream>>>(a);                  \
     }
 
 }  // namespace zk

@@ -8,16 +8,26 @@
 
 namespace zkstark {
 
+// The interpreter functions are NOT inlined on the device: they are called from many sites and the quotient kernels are
+// already far larger than the instruction cache.
 template <class P, class V>
 ZKS_HD P flat_eval_col(const FlatView& f, uint32_t id, const V& lv, const V& nv) {
     const ColRec r = f.cols[id];
     P acc = P::from_u64(r.constant);
-    for (uint32_t t = r.lin_begin; t < r.lin_end; t++) acc = acc + lv[f.term_col[t]] * P::from_u64(f.term_coef[t]);
-    for (uint32_t t = r.next_begin; t < r.next_end; t++) acc = acc + nv[f.term_col[t]] * P::from_u64(f.term_coef[t]);
+    for (uint32_t t = r.lin_begin; t < r.lin_end; t++) {
+        const uint64_t k = f.term_coef[t];
+        P v = lv[f.term_col[t]];
+        acc = acc + (k == 1 ? v : v * P::from_u64(k));       // most CTL columns are plain cells
+    }
+    for (uint32_t t = r.next_begin; t < r.next_end; t++) {
+        const uint64_t k = f.term_coef[t];
+        P v = nv[f.term_col[t]];
+        acc = acc + (k == 1 ? v : v * P::from_u64(k));
+    }
     return acc;
 }
 template <class P, class V>
-ZKS_HD P flat_eval_filter(const FlatView& f, uint32_t id, const V& lv, const V& nv) {
+ZKS_HD_NOINLINE P flat_eval_filter(const FlatView& f, uint32_t id, const V& lv, const V& nv) {
     const FilterRec r = f.filters[id];
     P acc = P::zero();
     for (uint32_t k = r.prod_begin; k < r.prod_end; k += 2)
@@ -27,7 +37,7 @@ ZKS_HD P flat_eval_filter(const FlatView& f, uint32_t id, const V& lv, const V& 
 }
 // GrandProductChallenge::combine: sum_i v_i beta^i + gamma
 template <class P, class V>
-ZKS_HD P flat_combine(const FlatView& f, const EntryRec& e, P beta, P gamma, const V& lv, const V& nv) {
+ZKS_HD_NOINLINE P flat_combine(const FlatView& f, const EntryRec& e, P beta, P gamma, const V& lv, const V& nv) {
     P acc = P::zero();
     for (uint32_t k = e.col_end; k-- > e.col_begin;) acc = acc * beta + flat_eval_col<P>(f, f.col_ids[k], lv, nv);
     return acc + gamma;

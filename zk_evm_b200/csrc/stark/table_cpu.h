@@ -606,22 +606,39 @@ ZKS_HD void eval_syscalls_exceptions(const V& lv, const V& nv, CC& yc, const Tab
 template <class P, class V, class CC>
 ZKS_HD void eval(const V& lv, const V& nv, CC& yc, const TableParams& prm) {
     eval_byte_unpacking<P>(lv, nv, yc);
+    ZKS_SYNC();
     eval_clock<P>(lv, nv, yc);
+    ZKS_SYNC();
     eval_contextops<P>(lv, nv, yc);
+    ZKS_SYNC();
     eval_control_flow<P>(lv, nv, yc, prm);
+    ZKS_SYNC();
     eval_decode<P>(lv, yc);
+    ZKS_SYNC();
     eval_dup_swap<P>(lv, nv, yc);
+    ZKS_SYNC();
     eval_gas<P>(lv, nv, yc);
+    ZKS_SYNC();
     eval_halt<P>(lv, nv, yc, prm);
+    ZKS_SYNC();
     eval_jumps<P>(lv, nv, yc);
+    ZKS_SYNC();
     eval_membus<P>(lv, yc);
+    ZKS_SYNC();
     eval_memio<P>(lv, nv, yc);
+    ZKS_SYNC();
     eval_modfp254<P>(lv, yc);
+    ZKS_SYNC();
     eval_pc<P>(lv, nv, yc);
+    ZKS_SYNC();
     eval_push0<P>(lv, nv, yc);
+    ZKS_SYNC();
     eval_shift<P>(lv, yc);
+    ZKS_SYNC();
     eval_simple_logic<P>(lv, nv, yc);
+    ZKS_SYNC();
     eval_stack<P>(lv, nv, yc);
+    ZKS_SYNC();
     eval_syscalls_exceptions<P>(lv, nv, yc, prm);
 }
 

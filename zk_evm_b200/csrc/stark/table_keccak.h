@@ -77,47 +77,63 @@ ZKS_HD void eval(const V& lv, const V& nv, CC& yc) {
     yc.constraint(sum_round_flags * not_final_step * (nv[TIMESTAMP] - lv[TIMESTAMP]));
 
     // C'[x, z] = xor(C[x, z], C[x - 1, z], C[x + 1, z - 1])
-    for (uint32_t x = 0; x < 5; x++)
-        for (uint32_t z = 0; z < 64; z++) {
-            P x3 = xor3_gen<P>(lv[reg_c(x, z)], lv[reg_c((x + 4) % 5, z)], lv[reg_c((x + 1) % 5, (z + 63) % 64)]);
-            yc.constraint(lv[reg_c_prime(x, z)] - x3);
+    ZKS_NOUNROLL for (uint32_t x = 0; x < 5; x++)
+        ZKS_NOUNROLL for (uint32_t z0 = 0; z0 < 64; z0 += 8) {
+            P c0[8], c1[8], c2[8], cp[8];
+            ZKS_UNROLL for (uint32_t k = 0; k < 8; k++) {
+                uint32_t z = z0 + k;
+                c0[k] = lv[reg_c(x, z)]; c1[k] = lv[reg_c((x + 4) % 5, z)]; c2[k] = lv[reg_c((x + 1) % 5, (z + 63) % 64)]; cp[k] = lv[reg_c_prime(x, z)];
+            }
+            ZKS_UNROLL for (uint32_t k = 0; k < 8; k++) yc.constraint(cp[k] - xor3_gen<P>(c0[k], c1[k], c2[k]));
         }
     // A[x, y, z] = xor(A'[x, y, z], C[x, z], C'[x, z])
-    for (uint32_t x = 0; x < 5; x++)
-        for (uint32_t y = 0; y < 5; y++) {
+    ZKS_NOUNROLL for (uint32_t x = 0; x < 5; x++)
+        ZKS_NOUNROLL for (uint32_t y = 0; y < 5; y++) {
             P a_lo = lv[reg_a(x, y)], a_hi = lv[reg_a(x, y) + 1];
             P computed_lo = P::zero(), computed_hi = P::zero();
-            for (uint32_t z = 32; z-- > 0;) {
-                P bit = xor3_gen<P>(lv[reg_a_prime(x, y, z)], lv[reg_c(x, z)], lv[reg_c_prime(x, z)]);
-                computed_lo = computed_lo + computed_lo + bit;
-            }
-            for (uint32_t z = 64; z-- > 32;) {
-                P bit = xor3_gen<P>(lv[reg_a_prime(x, y, z)], lv[reg_c(x, z)], lv[reg_c_prime(x, z)]);
-                computed_hi = computed_hi + computed_hi + bit;
+            // bits from the top down, eight at a time: the 24 column loads of a batch are issued before any of them is used
+            ZKS_NOUNROLL for (uint32_t z0 = 64; z0 > 0; z0 -= 8) {
+                P ap[8], cc[8], cp[8];
+                ZKS_UNROLL for (uint32_t k = 0; k < 8; k++) {
+                    uint32_t z = z0 - 1 - k;
+                    ap[k] = lv[reg_a_prime(x, y, z)]; cc[k] = lv[reg_c(x, z)]; cp[k] = lv[reg_c_prime(x, z)];
+                }
+                P acc = z0 > 32 ? computed_hi : computed_lo;
+                ZKS_UNROLL for (uint32_t k = 0; k < 8; k++) acc = acc + acc + xor3_gen<P>(ap[k], cc[k], cp[k]);
+                if (z0 > 32) computed_hi = acc; else computed_lo = acc;
             }
             yc.constraint(computed_lo - a_lo);
             yc.constraint(computed_hi - a_hi);
         }
     // xor_{i<5} A'[x, i, z] = C'[x, z]: diff (diff - 2) (diff - 4) = 0
-    for (uint32_t x = 0; x < 5; x++)
-        for (uint32_t z = 0; z < 64; z++) {
-            P sum = P::zero();
-            for (uint32_t i = 0; i < 5; i++) sum = sum + lv[reg_a_prime(x, i, z)];
-            P diff = sum - lv[reg_c_prime(x, z)];
-            yc.constraint(diff * (diff - P::from_u64(2)) * (diff - P::from_u64(4)));
+    ZKS_NOUNROLL for (uint32_t x = 0; x < 5; x++)
+        ZKS_NOUNROLL for (uint32_t z0 = 0; z0 < 64; z0 += 4) {
+            P ap[4][5], cp[4];
+            ZKS_UNROLL for (uint32_t k = 0; k < 4; k++) {
+                ZKS_UNROLL for (uint32_t i = 0; i < 5; i++) ap[k][i] = lv[reg_a_prime(x, i, z0 + k)];
+                cp[k] = lv[reg_c_prime(x, z0 + k)];
+            }
+            ZKS_UNROLL for (uint32_t k = 0; k < 4; k++) {
+                P sum = P::zero();
+                ZKS_UNROLL for (uint32_t i = 0; i < 5; i++) sum = sum + ap[k][i];
+                P diff = sum - cp[k];
+                yc.constraint(diff * (diff - P::from_u64(2)) * (diff - P::from_u64(4)));
+            }
         }
     // A''[x, y] = xor(B[x, y], andn(B[x + 1, y], B[x + 2, y]))
-    for (uint32_t x = 0; x < 5; x++)
-        for (uint32_t y = 0; y < 5; y++) {
+    ZKS_NOUNROLL for (uint32_t x = 0; x < 5; x++)
+        ZKS_NOUNROLL for (uint32_t y = 0; y < 5; y++) {
             P lo = lv[reg_a_prime_prime(x, y)], hi = lv[reg_a_prime_prime(x, y) + 1];
             P computed_lo = P::zero(), computed_hi = P::zero();
-            for (uint32_t z = 32; z-- > 0;) {
-                P bit = xor_gen<P>(lv[reg_b(x, y, z)], andn_gen<P>(lv[reg_b((x + 1) % 5, y, z)], lv[reg_b((x + 2) % 5, y, z)]));
-                computed_lo = computed_lo + computed_lo + bit;
-            }
-            for (uint32_t z = 64; z-- > 32;) {
-                P bit = xor_gen<P>(lv[reg_b(x, y, z)], andn_gen<P>(lv[reg_b((x + 1) % 5, y, z)], lv[reg_b((x + 2) % 5, y, z)]));
-                computed_hi = computed_hi + computed_hi + bit;
+            ZKS_NOUNROLL for (uint32_t z0 = 64; z0 > 0; z0 -= 8) {
+                P b0[8], b1[8], b2[8];
+                ZKS_UNROLL for (uint32_t k = 0; k < 8; k++) {
+                    uint32_t z = z0 - 1 - k;
+                    b0[k] = lv[reg_b(x, y, z)]; b1[k] = lv[reg_b((x + 1) % 5, y, z)]; b2[k] = lv[reg_b((x + 2) % 5, y, z)];
+                }
+                P acc = z0 > 32 ? computed_hi : computed_lo;
+                ZKS_UNROLL for (uint32_t k = 0; k < 8; k++) acc = acc + acc + xor_gen<P>(b0[k], andn_gen<P>(b1[k], b2[k]));
+                if (z0 > 32) computed_hi = acc; else computed_lo = acc;
             }
             yc.constraint(computed_lo - lo);
             yc.constraint(computed_hi - hi);
@@ -144,8 +160,8 @@ ZKS_HD void eval(const V& lv, const V& nv, CC& yc) {
         yc.constraint(x_hi - lv[reg_a_prime_prime_prime(0, 0) + 1]);
     }
     // this round's output equals the next round's input
-    for (uint32_t x = 0; x < 5; x++)
-        for (uint32_t y = 0; y < 5; y++) {
+    ZKS_NOUNROLL for (uint32_t x = 0; x < 5; x++)
+        ZKS_NOUNROLL for (uint32_t y = 0; y < 5; y++) {
             P output_lo = lv[reg_a_prime_prime_prime(x, y)], output_hi = lv[reg_a_prime_prime_prime(x, y) + 1];
             P input_lo = nv[reg_a(x, y)], input_hi = nv[reg_a(x, y) + 1];
             P not_last_round = one - lv[reg_step(NUM_ROUNDS - 1)];
