@@ -18,7 +18,9 @@ N > 1 (one process per GPU, torchrun):
 --workload cpu_table  times BASELINE config #2 (single CpuStark table, 2^20 rows) instead.
 """
 import argparse
+import contextlib
 import ctypes as C
+import io
 import json
 import os
 import subprocess
@@ -150,8 +152,8 @@ def run_ours(args):
             return zk.prove_with_traces(cx, host_traces, PUBLIC_VALUES, cfg, labels)
         return zk.prove_with_traces(cx, None, PUBLIC_VALUES, cfg, labels, device_ptrs=ptrs)
 
-    def step(host):
-        if nstreams > 1:
+    def step(host, single=False):
+        if nstreams > 1 and not single:
             res = [None] * nstreams
             ths = [threading.Thread(target=lambda i=i: res.__setitem__(i, one_segment(ctxs[i], host))) for i in range(nstreams)]
             for th in ths:
@@ -180,9 +182,10 @@ def run_ours(args):
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def timed(host, steps):
+    def timed(host, steps, single=False):
         barrier()
-        if nstreams > 1:
+        multi = nstreams > 1 and not single
+        if multi:
             # several library streams: bracket with events on torch's stream, made to wait for / be waited on by a full device sync
             ev0.record()
             torch.cuda.synchronize()
@@ -190,8 +193,8 @@ def run_ours(args):
             ctx.timer_start()
         t0 = time.perf_counter()
         for _ in range(steps):
-            step(host)
-        if nstreams > 1:
+            step(host, single)
+        if multi:
             for cx in ctxs:
                 cx.sync()
             ev1.record()
@@ -211,18 +214,15 @@ def run_ours(args):
         step(False)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for cx in ctxs:
-        zk._lib.check(zk.lib().zkgpu_ctx_set_profiling(cx._h, 0 if args.no_kernel_events else 1))
     l0 = sum(cx.stats()["kernel_launches"] for cx in ctxs)
     ms, wall = timed(False, args.steps)
     launches = sum(cx.stats()["kernel_launches"] for cx in ctxs) - l0
-    kst = kernel_stats(zk, ctxs[0])
-    for cx in ctxs[1:]:
-        for k, v in kernel_stats(zk, cx).items():
-            for f in ("launches", "ms", "bytes"):
-                kst[k][f] += v[f]
-    for cx in ctxs:
-        zk._lib.check(zk.lib().zkgpu_ctx_set_profiling(cx._h, 0))
+    # kernel-family breakdown: a second timed region of the same K steps on ONE stream with the library's CUDA-event brackets on
+    # (with several segments in flight the brackets of one stream would also count the other streams' kernels)
+    zk._lib.check(zk.lib().zkgpu_ctx_set_profiling(ctx._h, 0 if args.no_kernel_events else 1))
+    ms1, wall1 = (ms, wall) if False else timed(False, args.steps, single=True)
+    kst = kernel_stats(zk, ctx)
+    zk._lib.check(zk.lib().zkgpu_ctx_set_profiling(ctx._h, 0))
     for _ in range(min(args.warmup, 1)):
         step(True)
     e_ms, e_wall = timed(True, args.steps)
@@ -244,8 +244,9 @@ def run_ours(args):
                     "avg_launch_ms": per, "algorithmic_GB_per_step": v["bytes"] / args.steps / 1e9, "achieved_GBps": ach, "frac_of_peak": ach / peak}
         roof = {"bound": "hbm", "kernel": top, "achieved": fam(top)["achieved_GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": fam(top)["frac_of_peak"], "traffic": None,
-                "how": "CUDA events recorded by the library on its launching stream around every launch group inside the timed region; "
-                       "achieved = algorithmic bytes of the group (DESIGN.md) / event time, summed over the timed steps",
+                "how": "CUDA events recorded by the library on its launching stream around every launch group inside a timed region of the same "
+                       "K steps run with ONE segment in flight (%.1f ms/step, %.3f proofs/s); achieved = algorithmic bytes of the group "
+                       "(DESIGN.md) / event time, summed over the steps" % (ms1 / args.steps, (1 if sharded else world) * args.steps / (ms1 / 1e3)),
                 "families": {k: fam(k) for k in FAMILIES}}
         if top == "leaf_hash":
             perms = sum(2 * (1 << log_ns[t]) * ((NUM_COLUMNS[t] + 7) // 8) for t in range(9) if mine[t] and NUM_COLUMNS[t] > 4)
@@ -339,14 +340,28 @@ def main():
     ap.add_argument("--log-n", type=int, default=20, help="cpu_table workload: log2 of the trace length (BASELINE config #2: 20)")
     ap.add_argument("--shrink", type=int, default=0, help="segment workload: make every table 2^shrink times shorter (smoke runs)")
     ap.add_argument("--cpu-shrink", type=int, default=5, help="CPU legs prove tables 2^k times shorter and scale the time")
-    ap.add_argument("--streams", type=int, default=1, help="segments in flight per GPU (parallelism=segments)")
+    ap.add_argument("--streams", type=int, default=2, help="segments in flight per GPU (parallelism=segments)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiler runs)")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not bracket kernel families with CUDA events")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly ONE JSON line: anything a library prints meanwhile (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    out = buf.getvalue().strip()
+    if out:
+        print(out.splitlines()[-1], flush=True)
 
 
 if __name__ == "__main__":
