@@ -122,6 +122,24 @@ size_t orc_table_num_aux(uint32_t table, uint32_t num_challenges) {
     return aux_shape(table, zkstark::all_cross_table_lookups(), num_challenges, zkstark::CONSTRAINT_DEGREE).num_aux();
 }
 
+// The device's index-addressed (reordered) evaluators must give what the reference's emission order gives on ANY two rows, not
+// only on valid traces: evaluates both forms of a table's constraints on the given rows (base field, two alphas) and returns 1
+// when the accumulators agree.  Only Keccak has a reordered form so far.
+int orc_eval_forms_agree(uint32_t table, const uint64_t* lv, const uint64_t* nv, const uint64_t alphas[2], const uint64_t sel[3],
+                         uint64_t out_seq[2], uint64_t out_blk[2]) {
+    ConsumerT<OF> a, b;
+    for (ConsumerT<OF>* y : {&a, &b}) {
+        for (int j = 0; j < 2; j++) { y->alphas.push_back(OF(alphas[j])); y->acc.push_back(OF(0)); }
+        y->z_last = OF(sel[0]); y->lagrange_first = OF(sel[1]); y->lagrange_last = OF(sel[2]);
+    }
+    RowOF l{lv}, n{nv};
+    if (table != zkstark::T_KECCAK) return -1;
+    zkstark::keccak::eval<OF>(l, n, a);
+    zkstark::keccak::eval_blocked<OF>(l, n, b);
+    for (int j = 0; j < 2; j++) { out_seq[j] = a.acc[j].v; out_blk[j] = b.acc[j].v; }
+    return (a.acc[0].v == b.acc[0].v && a.acc[1].v == b.acc[1].v) ? 1 : 0;
+}
+
 // prove_single_table (prover.rs:301-341) for one table given its trace and the CTL challenges.
 // trace: ncols*n column-major.  beta_gamma: [beta_0, gamma_0, beta_1, gamma_1 ...].  chal_state: compacted transcript
 // state in, state after this table's proof out.  Returns the number of proof words written (or needed when out is too

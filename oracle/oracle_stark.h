@@ -197,6 +197,19 @@ template <class P> struct ConsumerT {
     std::vector<P> alphas, acc;
     P z_last, lagrange_first, lagrange_last;
     void constraint(P c) { for (size_t j = 0; j < acc.size(); j++) acc[j] = acc[j] * alphas[j] + c; }
+    // index-addressed block (see stark/consumer.h): only used to check the device's reordered evaluators against the sequential ones
+    std::vector<std::vector<P>> apow;
+    uint32_t blk_top = 0;
+    void block_begin(uint32_t M) {
+        apow.assign(acc.size(), std::vector<P>());
+        for (size_t j = 0; j < acc.size(); j++) {
+            P w = P::one();
+            for (uint32_t e = 0; e <= M; e++) { apow[j].push_back(w); w = w * alphas[j]; }
+            acc[j] = acc[j] * apow[j][M];
+        }
+        blk_top = M - 1;
+    }
+    void block_put(uint32_t idx, P c) { for (size_t j = 0; j < acc.size(); j++) acc[j] = acc[j] + c * apow[j][blk_top - idx]; }
     void constraint_transition(P c) { constraint(c * z_last); }
     void constraint_first_row(P c) { constraint(c * lagrange_first); }
     void constraint_last_row(P c) { constraint(c * lagrange_last); }

@@ -128,3 +128,25 @@ def test_segment_prove_verify_with_ctl_sums(oracle):
     # other public values -> other challenges -> the old proofs no longer verify
     ok3, _ = orc_verify_segment(oracle, TEST_CONFIG, proofs, PUBLIC_VALUES + np.uint64(1))
     assert not ok3
+
+
+def test_keccak_blocked_evaluator_equals_reference_order():
+    """the device's reordered Keccak evaluator (index-addressed alpha powers) == the reference emission order on arbitrary rows"""
+    import ctypes as C
+    from tests import oracle_lib
+    orc = oracle_lib.load()
+    rng = np.random.default_rng(11)
+    u64p = C.POINTER(C.c_uint64)
+    for trial in range(3):
+        lv = oracle_lib.rand_field(rng, (2431,))
+        nv = oracle_lib.rand_field(rng, (2431,))
+        if trial == 2:   # bit-valued rows as in a real trace
+            lv = (lv & np.uint64(1)).astype(np.uint64)
+            nv = (nv & np.uint64(1)).astype(np.uint64)
+        al = oracle_lib.rand_field(rng, (2,))
+        sel = oracle_lib.rand_field(rng, (3,))
+        a, b = np.zeros(2, np.uint64), np.zeros(2, np.uint64)
+        r = orc.lib.orc_eval_forms_agree(3, lv.ctypes.data_as(u64p), nv.ctypes.data_as(u64p), al.ctypes.data_as(u64p),
+                                         sel.ctypes.data_as(u64p), a.ctypes.data_as(u64p), b.ctypes.data_as(u64p))
+        assert r == 1, (a, b)
+        assert a[0] != 0 or trial == 2

@@ -208,6 +208,13 @@ static const uint64_t* get_roots(Ctx& c, bool inverse) {
     return b.get();
 }
 
+// out[j] = c0 * base^j, j < len (uncached)
+void fill_powers(Ctx& c, uint64_t* out, size_t len, uint64_t base, uint64_t c0) {
+    powers_kernel<<<(unsigned)(((len + 15) / 16 + 127) / 128), 128, 0, c.stream>>>(out, len, base, c0);
+    c.count_launch();
+    c.check_launch("powers_kernel");
+}
+
 const uint64_t* get_power_table(Ctx& c, uint64_t base, uint64_t c0, size_t len) {
     std::string key = "pow:" + std::to_string(base) + ":" + std::to_string(c0) + ":" + std::to_string(len);
     auto it = c.table_cache.find(key);

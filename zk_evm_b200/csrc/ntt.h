@@ -10,6 +10,8 @@ void ntt_dif(Ctx& c, const uint64_t* src, size_t src_stride, unsigned src_shift,
 // out[col][bitrev(p)] = in[col][p] * scale * (tab ? tab[bitrev(p)] : 1)   (out of place)
 void bitrev_permute(Ctx& c, const uint64_t* in, size_t in_stride, uint64_t* out, size_t out_stride, size_t ncols,
                     unsigned L, uint64_t scale, const uint64_t* tab);
+// out[j] = c0 * base^j, j < len (uncached, caller-owned buffer)
+void fill_powers(Ctx& c, uint64_t* out, size_t len, uint64_t base, uint64_t c0);
 // cached table: out[j] = c0 * base^j, j < len
 const uint64_t* get_power_table(Ctx& c, uint64_t base, uint64_t c0, size_t len);
 // values (natural) -> coefficients (natural): ifft, or coset_ifft when coset_shift > 1

@@ -12,6 +12,7 @@
 // for the next row.  The two running accumulators per challenge live in registers; columns are streamed straight from
 // global memory / L2 (each is touched by a handful of constraints).
 #include "quotient_kernel.cuh"
+#include "ntt.h"
 
 namespace zk {
 
@@ -66,6 +67,11 @@ void quotient_values(Ctx& c, const TableDev& t, const QuotientArgs& q) {
     a.dom = get_domain(c, k, zh);
     a.flat = t.view;
     a.prm = q.prm;
+    // powers of the alphas for the index-addressed constraint blocks (2 x 1024 elements, rebuilt per proof: alpha is fresh)
+    static_assert(zkstark::keccak::MIDDLE_CONSTRAINTS <= APOW_MAX, "alpha power table too short");
+    DevBuf apow(&c, 2 * (size_t)(APOW_MAX + 1) * 8);
+    for (unsigned i = 0; i < 2; i++) fill_powers(c, apow.get() + i * (size_t)(APOW_MAX + 1), APOW_MAX + 1, a.alphas[i], 1);
+    a.apow = apow.get();
     unsigned blocks = (unsigned)((a.N + 127) / 128);
     switch (q.table) {
         case T_LOGIC: launch_quotient<T_LOGIC>(a, blocks, c.stream); break;

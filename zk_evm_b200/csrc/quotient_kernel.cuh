@@ -26,6 +26,8 @@ struct DevRow {
     __device__ __forceinline__ Fp operator[](uint32_t c) const { return Fp(__ldg(p + (size_t)c * stride)); }
 };
 
+static constexpr unsigned APOW_MAX = 1023;
+
 struct QuotKernelArgs {
     const uint64_t* trace_lde;
     const uint64_t* aux_lde;
@@ -37,12 +39,16 @@ struct QuotKernelArgs {
     // dom[j] = x - w_n^-1 (vanishes on the last row), dom[N + j] = L_first(x), dom[2N + j] = L_last(x), x = g w_N^bitrev(j)
     const uint64_t* dom;
     uint64_t zh_inv[2];      // 1 / (g^n (-1)^i - 1)
+    // alpha_j^e, e <= APOW_MAX, for the index-addressed constraint blocks (Consumer::block_put): apow + j * (APOW_MAX + 1)
+    const uint64_t* apow;
     FlatView flat;
     TableParams prm;
 };
 
+// registers: the Keccak kernel is a load stream (2431 columns per point) and wants several 128-thread blocks per SM with ~40 loads
+// in flight per thread; the others are instruction-bound and take what they need
 template <uint32_t TABLE>
-__global__ void __launch_bounds__(128) quotient_kernel(QuotKernelArgs a) {
+__global__ void __launch_bounds__(128, TABLE == T_KECCAK ? 4 : 1) quotient_kernel(QuotKernelArgs a) {
     // the grid covers exactly N points (block = min(128, N) threads, N a power of two): no early exit, the constraint code
     // contains block-wide barriers (ZKS_SYNC)
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -53,7 +59,10 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotKernelArgs a) {
     Consumer<Fp, 2> yc;
     yc.nc = (int)a.nc;
 #pragma unroll
-    for (int k = 0; k < 2; k++) { yc.alpha[k] = Fp(a.alphas[k]); yc.acc[k] = Fp(0); }
+    for (int k = 0; k < 2; k++) {
+        yc.alpha[k] = Fp(a.alphas[k]); yc.acc[k] = Fp(0);
+        yc.apow[k] = reinterpret_cast<const Fp*>(a.apow) + k * (APOW_MAX + 1);
+    }
     yc.z_last = Fp(__ldg(a.dom + j));
     yc.lagrange_first = Fp(__ldg(a.dom + a.N + j));
     yc.lagrange_last = Fp(__ldg(a.dom + 2 * a.N + j));
@@ -68,7 +77,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(QuotKernelArgs a) {
     else if constexpr (TABLE == T_ARITHMETIC) arithmetic::eval<Fp>(lv, nv, yc);
     else if constexpr (TABLE == T_BYTE_PACKING) byte_packing::eval<Fp>(lv, nv, yc);
     else if constexpr (TABLE == T_CPU) cpu::eval<Fp>(lv, nv, yc, a.prm);
-    else if constexpr (TABLE == T_KECCAK) keccak::eval<Fp>(lv, nv, yc);
+    else if constexpr (TABLE == T_KECCAK) keccak::eval_blocked<Fp>(lv, nv, yc);
     else if constexpr (TABLE == T_KECCAK_SPONGE) keccak_sponge::eval<Fp>(lv, nv, yc);
 #endif
 

@@ -7,6 +7,7 @@
 #include "stark_dev.h"
 #include "challenger.h"
 #include <string.h>
+#include <algorithm>
 
 struct zkgpu_challenger { zk::Challenger ch; };
 
@@ -138,21 +139,51 @@ int zkgpu_prove_segment(zkgpu_ctx* h, const zkgpu_table_trace* traces, int mem_k
     const size_t cap_words = (size_t)4 << cfg.cap_height;
     for (uint32_t t = 0; t < ZKGPU_NUM_TABLES; t++) proofs_out[t] = nullptr;
 
-    // 1. trace commitments (prover.rs:92-116)
+    // 1. trace commitments (prover.rs:92-116).  The caps enter the transcript in Table order only after every table is
+    // committed, so the tables are uploaded and committed smallest first: all uploads are queued on the copy stream up front
+    // (one event per table) and the upload of table k+1 runs under the commitment of table k — hashing a trace takes longer than
+    // moving it over PCIe, so after the first (smallest) table the copies are hidden.
     StageLog lg(c);
     std::unique_ptr<zkgpu_batch> tb[ZKGPU_NUM_TABLES];
     std::vector<uint64_t> caps(ZKGPU_NUM_TABLES * cap_words, 0);
     uint8_t in_use[ZKGPU_NUM_TABLES];
+    std::vector<uint32_t> order;
     for (uint32_t t = 0; t < ZKGPU_NUM_TABLES; t++) {
         in_use[t] = traces[t].cols != nullptr;
         if (!in_use[t]) continue;
-        if (abort_flag && *abort_flag) throw ZkError(ZKGPU_ERR_ABORTED, "abort signal observed (prover.rs:346-354)");
         tb[t].reset(new zkgpu_batch());
         Batch& b = tb[t]->b;
         init_batch(c, b, zkstark::table_num_columns(t), traces[t].n, cfg.rate_bits, cfg.cap_height);
         b.values = DevBuf(&c, b.ncols * b.n * 8);
-        ZK_CUDA(cudaMemcpyAsync(b.values.get(), traces[t].cols, b.ncols * b.n * 8,
-                                mem_kind == ZKGPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
+        order.push_back(t);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return tb[x]->b.ncols * tb[x]->b.n < tb[y]->b.ncols * tb[y]->b.n; });
+    struct EventGuard {
+        std::vector<cudaEvent_t> ev;
+        ~EventGuard() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+        cudaEvent_t make() { cudaEvent_t e; ZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ev.push_back(e); return e; }
+    } events;
+    cudaEvent_t uploaded[ZKGPU_NUM_TABLES] = {nullptr};
+    {
+        // the buffers are stream-ordered allocations of c.stream: the copy stream may touch them only after that point
+        cudaEvent_t allocated = events.make();
+        ZK_CUDA(cudaEventRecord(allocated, c.stream));
+        ZK_CUDA(cudaStreamWaitEvent(c.copy_stream, allocated, 0));
+        for (uint32_t t : order) {
+            Batch& b = tb[t]->b;
+            ZK_CUDA(cudaMemcpyAsync(b.values.get(), traces[t].cols, b.ncols * b.n * 8,
+                                    mem_kind == ZKGPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.copy_stream));
+            uploaded[t] = events.make();
+            ZK_CUDA(cudaEventRecord(uploaded[t], c.copy_stream));
+        }
+    }
+    struct CopyDrain {   // on any exit (errors included) the copy stream is drained before the buffers it writes are freed
+        Ctx& c; ~CopyDrain() { cudaStreamSynchronize(c.copy_stream); }
+    } drain{c};
+    for (uint32_t t : order) {
+        if (abort_flag && *abort_flag) throw ZkError(ZKGPU_ERR_ABORTED, "abort signal observed (prover.rs:346-354)");
+        Batch& b = tb[t]->b;
+        ZK_CUDA(cudaStreamWaitEvent(c.stream, uploaded[t], 0));
         lg.mark("trace upload");
         commit_from_device_values(c, b, true);
         lg.mark(zkstark::table_name(t));

@@ -19,6 +19,23 @@ struct Consumer {
         for (int j = 0; j < MAXC; j++)
             if (j < nc) acc[j] = acc[j] * alpha[j] + c;
     }
+    // A block of M constraints that may be emitted in ANY order by their index inside the block (the position they have in the
+    // reference's emission order): with acc' = acc alpha^M + sum_i c_i alpha^(M-1-i) the result is the one Horner gives for
+    // the same M constraints emitted in order.  apow[j][e] = alpha_j^e for e <= M.  This is what lets a wide table (Keccak) walk
+    // its columns once instead of once per constraint family.
+    const P* apow[MAXC];
+    uint32_t blk_top;
+    ZKS_HD void block_begin(uint32_t M) {
+#pragma unroll
+        for (int j = 0; j < MAXC; j++)
+            if (j < nc) acc[j] = acc[j] * apow[j][M];
+        blk_top = M - 1;
+    }
+    ZKS_HD void block_put(uint32_t idx, P c) {
+#pragma unroll
+        for (int j = 0; j < MAXC; j++)
+            if (j < nc) acc[j] = acc[j] + c * apow[j][blk_top - idx];
+    }
     ZKS_HD void constraint_transition(P c) { constraint(c * z_last); }
     ZKS_HD void constraint_first_row(P c) { constraint(c * lagrange_first); }
     ZKS_HD void constraint_last_row(P c) { constraint(c * lagrange_last); }
