@@ -12,137 +12,14 @@
 // (shifts g and g*w_2n) read from the same coefficient column: lde_br[h*n + p] = DIF_n(c_j (g w_2n^h)^j)[p].
 #include "internal.h"
 #include "ntt.h"
+#include "ntt_tile.cuh"
 
 namespace zk {
 
-static constexpr unsigned ROOT_LOG = 13;      // roots tables hold w_{2^13}^k, k < 2^12
-static constexpr unsigned MAX_TILE_LOG = 12;  // 4096 elements = 32 KB shared memory per CTA
-static constexpr unsigned MAX_STRIDED_R = 8;
-static constexpr unsigned STRIDED_T = 4;      // 16 contiguous elements = 128 B per row of a strided tile
-
-struct PassParams {
-    const uint64_t* src;
-    uint64_t* dst;
-    size_t src_stride, dst_stride;   // elements between consecutive transforms
-    unsigned src_shift;              // transform t reads source column t >> src_shift
-    unsigned log_n, m, r, t;
-    const uint64_t* roots;           // w_{2^ROOT_LOG}^(+-k)
-    const uint64_t* interpass;       // [kd * M' + j'] or nullptr
-    const uint64_t* prescale0;       // per natural index j, or nullptr
-    const uint64_t* prescale1;
-    unsigned prescale_mask;          // table = (t & mask) ? prescale1 : prescale0
-};
-
-// K consecutive DIF stages (halves 2^s ... 2^(s-K+1)) of the size-2^r transforms held in sm[jd * 2^t + u]: every work item
-// loads the 2^K elements jd = (hi << (s+1)) | (k << (s-K+1)) | lo, k < 2^K, runs the K stages in registers and writes them
-// back, so shared memory is touched once per K stages.  Items are numbered u fastest, then lo, then hi: for a fixed k a
-// warp reads 32 consecutive elements whenever 2^t * 2^(s-K+1) >= 32.
-template <int K, int THREADS>
-__device__ __forceinline__ void dif_round(uint64_t* sm, const uint64_t* __restrict__ roots, int s, unsigned r, unsigned t) {
-    constexpr int E = 1 << K;
-    const int low = s - K + 1;
-    const unsigned items = (1u << (r - K)) << t;
-    for (unsigned w = threadIdx.x; w < items; w += THREADS) {
-        const unsigned u = w & ((1u << t) - 1), g = w >> t;
-        const unsigned lo = g & ((1u << low) - 1), hi = g >> low;
-        const unsigned base = ((((hi << K) << low) | lo) << t) + u;     // element k lives at base + (k << (low + t))
-        uint64_t x[E];
-#pragma unroll
-        for (int k = 0; k < E; k++) x[k] = sm[base + ((unsigned)k << (low + t))];
-#pragma unroll
-        for (int j = 0; j < K; j++) {
-            const int lh = s - j;                  // this stage's log2(half), in units of jd
-            constexpr int dummy = 0; (void)dummy;
-            const int hk = 1 << (K - 1 - j);       // the partner's distance in k
-#pragma unroll
-            for (int k = 0; k < E; k++) {
-                if (k & hk) continue;
-                uint64_t a = x[k], b = x[k + hk];
-                x[k] = gl_add(a, b);
-                uint64_t d = gl_sub(a, b);
-                if (lh > 0) {
-                    const unsigned j_in = ((unsigned)(k & (hk - 1)) << low) | lo;
-                    d = gl_mul(d, __ldg(roots + ((size_t)j_in << (ROOT_LOG - 1 - lh))));
-                }
-                x[k + hk] = d;
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < E; k++) sm[base + ((unsigned)k << (low + t))] = x[k];
-    }
-}
-
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) ntt_dif_pass_kernel(PassParams p) {
+template <int THREADS, bool INV>
+__global__ void __launch_bounds__(THREADS) ntt_pass_kernel(PassParams p) {
     extern __shared__ uint64_t sm[];
-    const unsigned r = p.r, t = p.t, m = p.m;
-    const unsigned R = 1u << r, T = 1u << t;
-    const unsigned tile_elems = R << t;
-    const size_t trans = blockIdx.y;
-    const uint64_t* src = p.src + (trans >> p.src_shift) * p.src_stride;
-    uint64_t* dst = p.dst + trans * p.dst_stride;
-    const uint64_t* prescale = p.prescale0 ? ((trans & p.prescale_mask) ? p.prescale1 : p.prescale0) : nullptr;
-    const size_t tile = blockIdx.x;
-    const unsigned mp = m - r;   // log M'
-    const bool strided = mp >= t;   // else: final pass (mp == 0), tile = 2^t consecutive blocks of R
-
-    // ---- load ----
-    size_t base;
-    if (strided) {
-        // tile id = hi * 2^(mp - t) + lo_hi
-        size_t hi = tile >> (mp - t), lo_hi = tile & (((size_t)1 << (mp - t)) - 1);
-        base = (hi << m) + (lo_hi << t);
-        for (unsigned e = threadIdx.x; e < tile_elems; e += THREADS) {
-            unsigned lo_t = e & (T - 1), jd = e >> t;
-            size_t g = base + ((size_t)jd << mp) + lo_t;
-            uint64_t v = src[g];
-            if (prescale) v = gl_mul(v, prescale[g]);
-            sm[e] = v;   // layout [jd][lo_t]
-        }
-    } else {
-        base = tile * (size_t)tile_elems;
-        for (unsigned e = threadIdx.x; e < tile_elems; e += THREADS) {
-            unsigned jd = e & (R - 1), u = e >> r;
-            size_t g = base + e;
-            uint64_t v = src[g];
-            if (prescale) v = gl_mul(v, prescale[g]);
-            sm[(jd << t) + u] = v;   // layout [jd][u]; (bank-conflicted store, r stages amortise it)
-        }
-    }
-    __syncthreads();
-
-    // ---- r radix-2 DIF stages over jd, K (<= 3) stages per shared-memory round trip on a register tile of 2^K elements ----
-    {
-        int s = (int)r - 1;                       // log2(half) of the next stage
-        const int first = (r % 3) ? (int)(r % 3) : 3;
-        if (first == 1) dif_round<1, THREADS>(sm, p.roots, s, r, t);
-        else if (first == 2) dif_round<2, THREADS>(sm, p.roots, s, r, t);
-        else dif_round<3, THREADS>(sm, p.roots, s, r, t);
-        __syncthreads();
-        for (s -= first; s >= 0; s -= 3) {
-            dif_round<3, THREADS>(sm, p.roots, s, r, t);
-            __syncthreads();
-        }
-    }
-
-    // ---- inter-pass twiddle + store (in place: digit position jd_pos holds kd = rev_r(jd_pos)) ----
-    if (strided) {
-        const size_t lo_base = (tile & (((size_t)1 << (mp - t)) - 1)) << t;
-        for (unsigned e = threadIdx.x; e < tile_elems; e += THREADS) {
-            unsigned lo_t = e & (T - 1), jd = e >> t;
-            uint64_t v = sm[e];
-            if (p.interpass) {
-                unsigned kd = __brev(jd) >> (32 - r);
-                v = gl_mul(v, __ldg(p.interpass + ((size_t)kd << mp) + lo_base + lo_t));
-            }
-            dst[base + ((size_t)jd << mp) + lo_t] = v;
-        }
-    } else {
-        for (unsigned e = threadIdx.x; e < tile_elems; e += THREADS) {
-            unsigned jd = e & (R - 1), u = e >> r;
-            dst[base + e] = sm[(jd << t) + u];
-        }
-    }
+    ntt_pass_tile<INV>(p, blockIdx.x, blockIdx.y, sm, threadIdx.x, THREADS);
 }
 
 // out[j] = c0 * base^j
@@ -197,9 +74,9 @@ __global__ void __launch_bounds__(256) bitrev_permute_kernel(const uint64_t* in,
 static const uint64_t* get_roots(Ctx& c, bool inverse) {
     DevBuf& b = inverse ? c.ntt.roots_inv : c.ntt.roots_fwd;
     if (!b.get()) {
-        size_t len = (size_t)1 << (ROOT_LOG - 1);
+        size_t len = (size_t)1 << NTT_ROOT_LOG;
         b = DevBuf(&c, len * 8);
-        uint64_t w = gl_root_of_unity(ROOT_LOG);
+        uint64_t w = gl_root_of_unity(NTT_ROOT_LOG);
         if (inverse) w = gl_inv(w);
         powers_kernel<<<(unsigned)((len / 16 + 127) / 128), 128, 0, c.stream>>>(b.get(), len, w, 1);
         c.count_launch();
@@ -244,26 +121,6 @@ static const uint64_t* get_interpass(Ctx& c, unsigned m, unsigned r, bool invers
     return p;
 }
 
-// digit plan, most significant digit first; the last entry is the final (contiguous) pass
-static void plan_passes(unsigned L, std::vector<unsigned>& digits) {
-    digits.clear();
-    if (L <= MAX_TILE_LOG) { digits.push_back(L); return; }
-    if (L <= MAX_TILE_LOG + MAX_STRIDED_R) {
-        // two passes: keep both tiles large (r1 + STRIDED_T and L - r1 close to MAX_TILE_LOG)
-        unsigned r1 = L - MAX_TILE_LOG;
-        unsigned half = L / 2 < MAX_STRIDED_R ? L / 2 : MAX_STRIDED_R;
-        if (r1 < half) r1 = half;
-        digits.push_back(r1);
-        digits.push_back(L - r1);
-        return;
-    }
-    unsigned rest = L - MAX_TILE_LOG;
-    unsigned ns = (rest + MAX_STRIDED_R - 1) / MAX_STRIDED_R;
-    unsigned per = rest / ns, extra = rest % ns;
-    for (unsigned i = 0; i < ns; i++) digits.push_back(per + (i < extra ? 1 : 0));
-    digits.push_back(MAX_TILE_LOG);
-}
-
 void ntt_dif(Ctx& c, const uint64_t* src, size_t src_stride, unsigned src_shift, uint64_t* dst, size_t dst_stride,
              size_t ntrans, unsigned L, bool inverse, const uint64_t* prescale0, const uint64_t* prescale1,
              unsigned prescale_mask) {
@@ -277,7 +134,7 @@ void ntt_dif(Ctx& c, const uint64_t* src, size_t src_stride, unsigned src_shift,
         return;
     }
     std::vector<unsigned> digits;
-    plan_passes(L, digits);
+    ntt_plan_passes(L, digits);
     const uint64_t* roots = get_roots(c, inverse);
     unsigned m = L;
     for (size_t pi = 0; pi < digits.size(); pi++) {
@@ -295,19 +152,12 @@ void ntt_dif(Ctx& c, const uint64_t* src, size_t src_stride, unsigned src_shift,
         p.prescale0 = first ? prescale0 : nullptr;
         p.prescale1 = first ? prescale1 : nullptr;
         p.prescale_mask = prescale_mask;
-        if (last) {
-            // final pass: m == r; fill the tile with 2^t consecutive blocks
-            unsigned t = MAX_TILE_LOG > p.r ? MAX_TILE_LOG - p.r : 0;
-            if (t > L - m) t = L - m;
-            p.t = t;
-            p.interpass = nullptr;
-        } else {
-            p.t = STRIDED_T;
-            p.interpass = get_interpass(c, m, p.r, inverse);
-        }
+        p.strided = last ? 0 : 1;
+        p.t = ntt_pass_t(L, m, p.r, last);
+        p.interpass = last ? nullptr : get_interpass(c, m, p.r, inverse);
         unsigned tile_log = p.r + p.t;
         size_t tiles = (size_t)1 << (L - tile_log);
-        size_t smem = ((size_t)8) << tile_log;
+        size_t smem = (size_t)8 * ntt_pad(1u << tile_log);
         for (size_t t0 = 0; t0 < ntrans; t0 += 65535) {
             size_t cnt = ntrans - t0 < 65535 ? ntrans - t0 : 65535;
             PassParams q = p;
@@ -319,13 +169,16 @@ void ntt_dif(Ctx& c, const uint64_t* src, size_t src_stride, unsigned src_shift,
                 q.dst += t0 * q.dst_stride;
             }
             dim3 grid((unsigned)tiles, (unsigned)cnt);
-            if (tile_log >= 10)
-                ntt_dif_pass_kernel<256><<<grid, 256, smem, c.stream>>>(q);
-            else
-                ntt_dif_pass_kernel<64><<<grid, 64, smem, c.stream>>>(q);
+            if (tile_log >= 10) {
+                if (inverse) ntt_pass_kernel<256, true><<<grid, 256, smem, c.stream>>>(q);
+                else ntt_pass_kernel<256, false><<<grid, 256, smem, c.stream>>>(q);
+            } else {
+                if (inverse) ntt_pass_kernel<64, true><<<grid, 64, smem, c.stream>>>(q);
+                else ntt_pass_kernel<64, false><<<grid, 64, smem, c.stream>>>(q);
+            }
             c.count_launch();
         }
-        c.check_launch("ntt_dif_pass_kernel");
+        c.check_launch("ntt_pass_kernel");
         m -= p.r;
     }
 }

@@ -1,0 +1,241 @@
+// One tile of one pass of the batched Goldilocks NTT (see ntt.cu), host+device so the index arithmetic and the butterfly
+// network can be executed on the CPU by tests/native/ntt_tile_host.cpp (tid = 0, nthreads = 1 walks every item of every phase in
+// program order) and compared with the oracle transform without a GPU.
+//
+// Replaces plonky2_field 1.0.0 fft.rs `fft_classic` (radix-2, one twiddle multiplication per butterfly).  Here a pass over an
+// r-bit index digit runs in ROUNDS of up to four radix-2 stages on 16 elements held in registers.  In Goldilocks 2 has order 192
+// (2^96 = -1) and plonky2's primitive roots satisfy w_64 = 2^3, w_16 = 2^12, w_8 = 2^24, w_4 = 2^48: every twiddle INSIDE a round
+// is a power of two, i.e. a compile-time shift followed by the 96-bit shift-add reduction — no multiplier.  One general
+// multiplication per element remains per round (the twiddle w^(kf * lo) between rounds), instead of one per two stages.
+#pragma once
+#include "gl.cuh"
+#include <utility>
+#include <vector>
+
+namespace zk {
+
+static constexpr unsigned NTT_ROOT_LOG = 12;       // roots[k] = w_4096^(+-k), k < 4096
+static constexpr unsigned NTT_MAX_TILE_LOG = 12;   // 4096 elements (+ padding) = 34 KB shared memory per CTA
+static constexpr unsigned NTT_STRIDED_T = 4;       // 16 contiguous elements = 128 B per row of a strided tile
+
+struct PassParams {
+    const uint64_t* src;
+    uint64_t* dst;
+    size_t src_stride, dst_stride;   // elements between consecutive transforms
+    unsigned src_shift;              // transform t reads source column t >> src_shift
+    unsigned log_n, m, r, t;         // transform size, size of the sub-transforms this pass starts from, digit bits, tile columns
+    unsigned strided;                // 1: tile = 2^r digit values x 2^t contiguous elements; 0: final pass, 2^t consecutive blocks of 2^r
+    const uint64_t* roots;           // w_4096^(+-k)
+    const uint64_t* interpass;       // [kd * M' + j'] or nullptr
+    const uint64_t* prescale0;       // per natural index j, or nullptr
+    const uint64_t* prescale1;
+    unsigned prescale_mask;          // table = (t & mask) ? prescale1 : prescale0
+};
+
+// digit plan of a size-2^L transform, most significant digit first; the last entry is the final (contiguous) pass
+static constexpr unsigned NTT_MAX_STRIDED_R = 8;
+inline void ntt_plan_passes(unsigned L, std::vector<unsigned>& digits) {
+    digits.clear();
+    if (L <= NTT_MAX_TILE_LOG) { digits.push_back(L); return; }
+    if (L <= NTT_MAX_TILE_LOG + NTT_MAX_STRIDED_R) {
+        // two passes: keep both tiles large (r1 + NTT_STRIDED_T and L - r1 close to NTT_MAX_TILE_LOG)
+        unsigned r1 = L - NTT_MAX_TILE_LOG;
+        unsigned half = L / 2 < NTT_MAX_STRIDED_R ? L / 2 : NTT_MAX_STRIDED_R;
+        if (r1 < half) r1 = half;
+        digits.push_back(r1);
+        digits.push_back(L - r1);
+        return;
+    }
+    unsigned rest = L - NTT_MAX_TILE_LOG;
+    unsigned ns = (rest + NTT_MAX_STRIDED_R - 1) / NTT_MAX_STRIDED_R;
+    unsigned per = rest / ns, extra = rest % ns;
+    for (unsigned i = 0; i < ns; i++) digits.push_back(per + (i < extra ? 1 : 0));
+    digits.push_back(NTT_MAX_TILE_LOG);
+}
+// tile columns of pass `pi` of the plan: strided passes stage 16 contiguous elements per digit value, the final pass as many
+// consecutive sub-transforms as fit
+inline unsigned ntt_pass_t(unsigned L, unsigned m, unsigned r, bool last) {
+    if (!last) return NTT_STRIDED_T;
+    unsigned t = NTT_MAX_TILE_LOG > r ? NTT_MAX_TILE_LOG - r : 0;
+    if (t > L - m) t = L - m;
+    return t;
+}
+
+ZK_HD uint64_t ntt_ld(const uint64_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// one padding element per 16: the 16 lanes of a half-warp that walk the tile with a stride of 16 (or 256, ...) elements then
+// fall into distinct 8-byte banks
+ZK_HD unsigned ntt_pad(unsigned idx) { return idx + (idx >> 4); }
+static constexpr unsigned NTT_TILE_WORDS = (1u << NTT_MAX_TILE_LOG) + (1u << (NTT_MAX_TILE_LOG - 4));
+
+// x * 2^S for canonical x, 0 <= S < 96; canonical result
+template <int S>
+ZK_HD uint64_t gl_mul_pow2(uint64_t x) {
+    static_assert(S >= 0 && S < 96, "shift out of range");
+    if constexpr (S == 0) return x;
+#if defined(__CUDA_ARCH__)
+    constexpr int q = S / 32, r = S % 32;
+    uint32_t lo, hi;
+    gl_unpack(x, lo, hi);
+    uint32_t v0, v1, v2;   // x << r as three words
+    if constexpr (r == 0) { v0 = lo; v1 = hi; v2 = 0; }
+    else { v0 = lo << r; v1 = __funnelshift_l(lo, hi, r); v2 = hi >> (32 - r); }
+    if constexpr (q == 0) {
+        // (v1:v0) + v2 * 2^64, 2^64 == 2^32 - 1
+        uint32_t u0, u1, m;
+        asm("sub.cc.u32 %0, 0, %2;\n\t"
+            "subc.u32 %1, %2, 0;\n\t" : "=r"(u0), "=r"(u1) : "r"(v2));
+        asm("add.cc.u32 %0, %0, %3;\n\t"
+            "addc.cc.u32 %1, %1, %4;\n\t"
+            "addc.u32 %2, 0, 0;\n\t" : "+r"(v0), "+r"(v1), "=r"(m) : "r"(u0), "r"(u1));
+        m = 0u - m;
+        asm("add.cc.u32 %0, %0, %2;\n\t"
+            "addc.u32 %1, %1, 0;\n\t" : "+r"(v0), "+r"(v1) : "r"(m));
+        return gl_canon(gl_pack(v0, v1));
+    } else if constexpr (q == 1) {
+        return gld_reduce_words(0, v0, v1, v2);
+    } else {
+        // v0 2^64 + v1 2^96 + v2 2^128 == v0 (2^32 - 1) - (v1 + 2^32 v2);  the subtrahend is < 2^63
+        uint32_t u0, u1;
+        asm("sub.cc.u32 %0, 0, %2;\n\t"
+            "subc.u32 %1, %2, 0;\n\t" : "=r"(u0), "=r"(u1) : "r"(v0));
+        return gld_sub(gl_pack(u0, u1), gl_pack(v1, v2));
+    }
+#else
+    const uint64_t c = S < 64 ? ((uint64_t)1 << (S & 63)) : gl_mul(GL_EPS, (uint64_t)1 << ((S - 64) & 63));
+    return gl_mul(x, c);
+#endif
+}
+
+// butterfly I of stage J of the radix-2^K DIF network on x[0 .. 2^K): pair (k, k + hk), twiddle w_{2^(K-J)}^pos = 2^(+-(192 >> (K-J)) pos)
+template <int K, bool INV, int J, int I>
+ZK_HD void ntt_bfly(uint64_t (&x)[1 << K]) {
+    constexpr int hk = 1 << (K - 1 - J);
+    constexpr int pos = I % hk, k = (I / hk) * 2 * hk + pos;
+    constexpr int E = (192 >> (K - J)) * pos;            // forward exponent of 2, < 96
+    constexpr int e = INV ? (192 - E) % 192 : E;         // 2^-E = 2^(192 - E)
+    const uint64_t a = x[k], b = x[k + hk];
+    x[k] = gl_add(a, b);
+    if constexpr (e == 0) x[k + hk] = gl_sub(a, b);
+    else if constexpr (e < 96) x[k + hk] = gl_mul_pow2<e>(gl_sub(a, b));
+    else x[k + hk] = gl_mul_pow2<e - 96>(gl_sub(b, a));   // 2^96 = -1
+}
+template <int K, bool INV, int J, int... I>
+ZK_HD void ntt_stage(uint64_t (&x)[1 << K], std::integer_sequence<int, I...>) { (ntt_bfly<K, INV, J, I>(x), ...); }
+template <int K, bool INV, int... J>
+ZK_HD void ntt_stages(uint64_t (&x)[1 << K], std::integer_sequence<int, J...>) {
+    (ntt_stage<K, INV, J>(x, std::make_integer_sequence<int, (1 << K) / 2>()), ...);
+}
+// size-2^K DFT with root w_{2^K}^(+-1): natural order in, bit-reversed order out
+template <int K, bool INV>
+ZK_HD void ntt_dft_regs(uint64_t (&x)[1 << K]) { ntt_stages<K, INV>(x, std::make_integer_sequence<int, K>()); }
+
+// One round: the K DIF stages over bits s .. s-K+1 of the digit index jd of every sub-transform in the tile, followed by the
+// twiddle w_{2^(s+1)}^(kf * lo) (kf = frequency index produced by this round, lo = the bits of jd below the round) when lo exists.
+// Tile element (jd, u) lives at ntt_pad((jd << t) + u).  Items are numbered u fastest, then lo, then the bits above the round.
+template <int K, bool INV>
+ZK_HD void ntt_round(uint64_t* sm, const uint64_t* __restrict__ roots, int s, unsigned tile_log, unsigned t, unsigned tid, unsigned nthreads) {
+    constexpr int E = 1 << K;
+    const int low = s - K + 1;
+    const unsigned items = 1u << (tile_log - K);
+    for (unsigned w = tid; w < items; w += nthreads) {
+        const unsigned u = w & ((1u << t) - 1), g = w >> t;
+        const unsigned lo = g & ((1u << low) - 1), hi = g >> low;
+        const unsigned base = ((((hi << K) << low) | lo) << t) + u;
+        uint64_t x[E];
+#pragma unroll
+        for (int k = 0; k < E; k++) x[k] = sm[ntt_pad(base + ((unsigned)k << (low + t)))];
+        ntt_dft_regs<K, INV>(x);
+        if (low > 0) {
+            const unsigned sh = NTT_ROOT_LOG - (unsigned)(low + K);
+#pragma unroll
+            for (int kp = 1; kp < E; kp++) {
+                const unsigned kf = bitrev32((uint32_t)kp, K);
+                x[kp] = gl_mul(x[kp], ntt_ld(roots + ((size_t)(kf * lo) << sh)));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < E; k++) sm[ntt_pad(base + ((unsigned)k << (low + t)))] = x[k];
+    }
+}
+
+#if defined(__CUDA_ARCH__)
+#define NTT_TILE_SYNC() __syncthreads()
+#else
+#define NTT_TILE_SYNC() ((void)0)
+#endif
+
+// the whole tile: load (+ coset prescale), the rounds of the r-bit digit, inter-pass twiddle + store (in place: digit position
+// jd holds frequency kd = rev_r(jd))
+template <bool INV>
+ZK_HD void ntt_pass_tile(const PassParams& p, size_t tile, size_t trans, uint64_t* sm, unsigned tid, unsigned nthreads) {
+    const unsigned r = p.r, t = p.t, m = p.m;
+    const unsigned tile_log = r + t, tile_elems = 1u << tile_log;
+    const uint64_t* src = p.src + (trans >> p.src_shift) * p.src_stride;
+    uint64_t* dst = p.dst + trans * p.dst_stride;
+    const uint64_t* prescale = p.prescale0 ? ((trans & p.prescale_mask) ? p.prescale1 : p.prescale0) : nullptr;
+    const unsigned mp = m - r;   // log M'
+    const unsigned T = 1u << t;
+    size_t base;
+    if (p.strided) {
+        // tile id = hi * 2^(mp - t) + lo_hi; element (jd, lo_t) is transform index hi 2^m + jd 2^mp + lo_hi 2^t + lo_t
+        const size_t hi = tile >> (mp - t), lo_hi = tile & (((size_t)1 << (mp - t)) - 1);
+        base = (hi << m) + (lo_hi << t);
+        for (unsigned e = tid; e < tile_elems; e += nthreads) {
+            const unsigned lo_t = e & (T - 1), jd = e >> t;
+            const size_t g = base + ((size_t)jd << mp) + lo_t;
+            uint64_t v = src[g];
+            if (prescale) v = gl_mul(v, ntt_ld(prescale + g));
+            sm[ntt_pad(e)] = v;
+        }
+    } else {
+        // final pass (mp == 0): 2^t consecutive sub-transforms of 2^r elements, tile index = u 2^r + jd
+        base = tile * (size_t)tile_elems;
+        for (unsigned e = tid; e < tile_elems; e += nthreads) {
+            const size_t g = base + e;
+            uint64_t v = src[g];
+            if (prescale) v = gl_mul(v, ntt_ld(prescale + g));
+            sm[ntt_pad(e)] = v;
+        }
+    }
+    NTT_TILE_SYNC();
+
+    // rounds of four stages, the first one takes the remainder
+    {
+        const unsigned tt = p.strided ? t : 0;
+        int s = (int)r - 1;
+        const int first = (r % 4) ? (int)(r % 4) : 4;
+        if (first == 1) ntt_round<1, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads);
+        else if (first == 2) ntt_round<2, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads);
+        else if (first == 3) ntt_round<3, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads);
+        else ntt_round<4, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads);
+        NTT_TILE_SYNC();
+        for (s -= first; s >= 0; s -= 4) {
+            ntt_round<4, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads);
+            NTT_TILE_SYNC();
+        }
+    }
+
+    if (p.strided) {
+        const size_t lo_base = (tile & (((size_t)1 << (mp - t)) - 1)) << t;
+        for (unsigned e = tid; e < tile_elems; e += nthreads) {
+            const unsigned lo_t = e & (T - 1), jd = e >> t;
+            uint64_t v = sm[ntt_pad(e)];
+            if (p.interpass) {
+                const unsigned kd = bitrev32(jd, r);
+                v = gl_mul(v, ntt_ld(p.interpass + ((size_t)kd << mp) + lo_base + lo_t));
+            }
+            dst[base + ((size_t)jd << mp) + lo_t] = v;
+        }
+    } else {
+        for (unsigned e = tid; e < tile_elems; e += nthreads) dst[base + e] = sm[ntt_pad(e)];
+    }
+}
+
+}  // namespace zk
