@@ -6,8 +6,10 @@
 // book/src/framework/ctls.md:17-25, range_check.md:55-120).
 //
 // Three small kernels over the raw trace values (column-major, natural row order):
-//   1. helper_kernel   one thread per (row, helper column): h = sum over <= 2 (columns, filter) pairs of filter/combined
-//                      (the CPU code batch-inverts a whole column; here each thread does one Fermat inversion for its pair)
+//   1. helper_kernel   per helper column, a thread takes AUX_ROWS rows (a block-stride apart, so every load stays coalesced):
+//                      h = sum over <= 2 (columns, filter) pairs of filter/combined; the AUX_ROWS denominators share ONE Fermat
+//                      inversion (Montgomery's trick: 3 products per row + 76 per thread instead of 76 per row), as the CPU code
+//                      batch-inverts a whole column
 //   2. zsum_kernel     per running-sum column the per-row increment (sum of helpers [- freq/(table+challenge)])
 //   3. scan            modular prefix / suffix sums (block scan + scan of block totals + offset add)
 #include "stark_dev.h"
@@ -42,22 +44,48 @@ __device__ __forceinline__ uint64_t combine_table(const FlatView& f, const Entry
 
 struct HelperJob { uint32_t entry_begin, entry_end, out_col, pad; uint64_t beta, gamma; };
 
+static constexpr int AUX_ROWS = 8;
+// inv[i] = 1 / d[i] for the rows < cnt (0 where d[i] == 0, as gl_inv(0) = 0): one inversion for the whole batch
+__device__ __forceinline__ void batch_inverse(const uint64_t (&d)[AUX_ROWS], uint64_t (&inv)[AUX_ROWS]) {
+    uint64_t pre[AUX_ROWS];
+    uint64_t run = 1;
+#pragma unroll
+    for (int i = 0; i < AUX_ROWS; i++) { pre[i] = run; run = gl_mul(run, d[i] ? d[i] : 1); }
+    uint64_t r = gl_inv(run);
+#pragma unroll
+    for (int i = AUX_ROWS - 1; i >= 0; i--) {
+        inv[i] = d[i] ? gl_mul(r, pre[i]) : 0;
+        r = gl_mul(r, d[i] ? d[i] : 1);
+    }
+}
+
 __global__ void __launch_bounds__(256) helper_kernel(FlatView f, const HelperJob* __restrict__ jobs, const uint64_t* __restrict__ values,
                                                      size_t n, uint64_t* __restrict__ out) {
-    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
     const HelperJob j = jobs[blockIdx.y];
-    uint64_t fs[2] = {0, 0}, cs[2] = {1, 1};
-    for (uint32_t e = j.entry_begin; e < j.entry_end; e++) {
-        const EntryRec er = f.entries[e];
-        uint64_t fv = filter_eval_table(f, er.filter, values, n, r);
-        fs[e - j.entry_begin] = fv;
-        if (fv) cs[e - j.entry_begin] = combine_table(f, er, j.beta, j.gamma, values, n, r);
+    const size_t r0 = (size_t)blockIdx.x * (256 * AUX_ROWS) + threadIdx.x;
+    uint64_t num[AUX_ROWS], den[AUX_ROWS], inv[AUX_ROWS];
+#pragma unroll
+    for (int i = 0; i < AUX_ROWS; i++) {
+        const size_t r = r0 + (size_t)i * 256;
+        num[i] = 0; den[i] = 1;
+        if (r >= n) continue;
+        uint64_t fs[2] = {0, 0}, cs[2] = {1, 1};
+        for (uint32_t e = j.entry_begin; e < j.entry_end; e++) {
+            const EntryRec er = f.entries[e];
+            uint64_t fv = filter_eval_table(f, er.filter, values, n, r);
+            fs[e - j.entry_begin] = fv;
+            if (fv) cs[e - j.entry_begin] = combine_table(f, er, j.beta, j.gamma, values, n, r);
+        }
+        // f0/c0 + f1/c1 = (f0 c1 + f1 c0) / (c0 c1)
+        den[i] = gl_mul(cs[0], cs[1]);
+        num[i] = gl_add(gl_mul(fs[0], cs[1]), gl_mul(fs[1], cs[0]));
     }
-    // f0/c0 + f1/c1 with one inversion
-    uint64_t inv = gl_inv(gl_mul(cs[0], cs[1]));
-    uint64_t num = gl_add(gl_mul(fs[0], cs[1]), gl_mul(fs[1], cs[0]));
-    out[(size_t)j.out_col * n + r] = gl_mul(num, inv);
+    batch_inverse(den, inv);
+#pragma unroll
+    for (int i = 0; i < AUX_ROWS; i++) {
+        const size_t r = r0 + (size_t)i * 256;
+        if (r < n) out[(size_t)j.out_col * n + r] = gl_mul(num[i], inv[i]);
+    }
 }
 
 struct ZJob { uint32_t kind;   // 0: CTL (sum of helper columns), 1: lookup (shifted increment)
@@ -65,20 +93,39 @@ struct ZJob { uint32_t kind;   // 0: CTL (sum of helper columns), 1: lookup (shi
 
 __global__ void __launch_bounds__(256) zsum_kernel(FlatView f, const ZJob* __restrict__ jobs, const uint64_t* __restrict__ values,
                                                    size_t n, uint64_t* __restrict__ out) {
-    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
     const ZJob j = jobs[blockIdx.y];
-    uint64_t acc = 0;
+    const size_t r0 = (size_t)blockIdx.x * (256 * AUX_ROWS) + threadIdx.x;
     if (j.kind == 0) {
-        for (uint32_t t = 0; t < j.num_helpers; t++) acc = gl_add(acc, out[(size_t)(j.helper_begin + t) * n + r]);
-    } else if (r > 0) {
-        // Z(r) = Z(r-1) + sum_t h_t(r-1) - freq(r-1) / (table(r-1) + challenge): store the increment at row r
-        size_t q = r - 1;
-        for (uint32_t t = 0; t < j.num_helpers; t++) acc = gl_add(acc, out[(size_t)(j.helper_begin + t) * n + q]);
-        uint64_t tinv = gl_inv(gl_add(col_eval_table(f, j.table_col, values, n, q), j.challenge));
-        acc = gl_sub(acc, gl_mul(col_eval_table(f, j.freq_col, values, n, q), tinv));
+#pragma unroll 1
+        for (int i = 0; i < AUX_ROWS; i++) {
+            const size_t r = r0 + (size_t)i * 256;
+            if (r >= n) break;
+            uint64_t acc = 0;
+            for (uint32_t t = 0; t < j.num_helpers; t++) acc = gl_add(acc, out[(size_t)(j.helper_begin + t) * n + r]);
+            out[(size_t)j.out_col * n + r] = acc;
+        }
+        return;
     }
-    out[(size_t)j.out_col * n + r] = acc;
+    // Z(r) = Z(r-1) + sum_t h_t(r-1) - freq(r-1) / (table(r-1) + challenge): store the increment at row r
+    uint64_t acc[AUX_ROWS], den[AUX_ROWS], inv[AUX_ROWS], fr[AUX_ROWS];
+#pragma unroll
+    for (int i = 0; i < AUX_ROWS; i++) {
+        const size_t r = r0 + (size_t)i * 256;
+        acc[i] = 0; den[i] = 1; fr[i] = 0;
+        if (r >= n || r == 0) continue;
+        const size_t q = r - 1;
+        uint64_t a = 0;
+        for (uint32_t t = 0; t < j.num_helpers; t++) a = gl_add(a, out[(size_t)(j.helper_begin + t) * n + q]);
+        acc[i] = a;
+        den[i] = gl_add(col_eval_table(f, j.table_col, values, n, q), j.challenge);
+        fr[i] = col_eval_table(f, j.freq_col, values, n, q);
+    }
+    batch_inverse(den, inv);
+#pragma unroll
+    for (int i = 0; i < AUX_ROWS; i++) {
+        const size_t r = r0 + (size_t)i * 256;
+        if (r < n) out[(size_t)j.out_col * n + r] = gl_sub(acc[i], gl_mul(fr[i], inv[i]));
+    }
 }
 
 // ---- modular scan ------------------------------------------------------------------------------------------------
@@ -187,7 +234,7 @@ static void run_helpers(Ctx& c, const TableDev& t, const std::vector<HelperJob>&
     DevBuf dj = upload_vec(c, jobs);
     for (size_t j0 = 0; j0 < jobs.size(); j0 += 65535) {
         unsigned cnt = (unsigned)std::min<size_t>(65535, jobs.size() - j0);
-        dim3 grid((unsigned)((n + 255) / 256), cnt);
+        dim3 grid((unsigned)((n + 256 * AUX_ROWS - 1) / (256 * AUX_ROWS)), cnt);
         helper_kernel<<<grid, 256, 0, c.stream>>>(t.view, (const HelperJob*)dj.get() + j0, values, n, out);
         c.count_launch();
     }
@@ -197,7 +244,7 @@ static void run_helpers(Ctx& c, const TableDev& t, const std::vector<HelperJob>&
 static void run_zsums(Ctx& c, const TableDev& t, const std::vector<ZJob>& jobs, const uint64_t* values, size_t n, uint64_t* out) {
     if (jobs.empty()) return;
     DevBuf dj = upload_vec(c, jobs);
-    dim3 grid((unsigned)((n + 255) / 256), (unsigned)jobs.size());
+    dim3 grid((unsigned)((n + 256 * AUX_ROWS - 1) / (256 * AUX_ROWS)), (unsigned)jobs.size());
     zsum_kernel<<<grid, 256, 0, c.stream>>>(t.view, (const ZJob*)dj.get(), values, n, out);
     c.count_launch();
     c.check_launch("zsum_kernel");

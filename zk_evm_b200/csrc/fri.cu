@@ -165,33 +165,56 @@ struct CombineKernelArgs {
     uint64_t* out_re; uint64_t* out_im;
 };
 
+// sum_j alpha^j f_j(x) per batch: extension x base products, accumulated WITHOUT reduction in three 96-bit accumulators per
+// component (Dot above: 4 IMAD.WIDE + 12 carry adds per product instead of a full multiply-reduce-add), reduced once per point.
+// The three denominators (x - zeta), (x - g zeta) [extension] and (x - 1) share ONE Fermat inversion: 1/(x - z) = conj / norm with
+// norm in the base field, and the three base-field values are inverted together (Montgomery's trick).
+struct DotExt { Dot re, im; };
+__device__ __forceinline__ void dotext_init(DotExt& d) { dot_init(d.re); dot_init(d.im); }
+__device__ __forceinline__ void dotext_mac(DotExt& d, uint64_t v, const uint64_t* __restrict__ ap) {
+    uint32_t v0, v1; gl_unpack(v, v0, v1);
+    const ulonglong2 w = __ldg(reinterpret_cast<const ulonglong2*>(ap));
+    dot_mac(d.re, v0, v1, w.x); dot_mac(d.im, v0, v1, w.y);
+}
+__device__ __forceinline__ Fp2 dotext_reduce(const DotExt& d) { return Fp2(dot_reduce(d.re), dot_reduce(d.im)); }
+
 __global__ void __launch_bounds__(256) fri_combine_kernel(CombineKernelArgs a) {
     const size_t N = (size_t)1 << a.log_N;
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
     const uint32_t i = bitrev32((uint32_t)j, a.log_N);
     const uint64_t x = gl_mul(GL_GENERATOR, gl_pow(a.w_N, i));
-    Fp2 s_ta(0, 0), s_q(0, 0), s_z(0, 0);
+    DotExt d_ta, d_q, d_z;
+    dotext_init(d_ta); dotext_init(d_q); dotext_init(d_z);
     uint32_t k = 0;
-    for (uint32_t c = 0; c < a.ncols[0]; c++, k++) {
-        uint64_t v = __ldg(a.lde[0] + (size_t)c * N + j);
-        s_ta = s_ta + fp2_mul_base(Fp2(a.apow[2 * k], a.apow[2 * k + 1]), v);
+#pragma unroll 4
+    for (uint32_t c = 0; c < a.ncols[0]; c++, k++) dotext_mac(d_ta, __ldg(a.lde[0] + (size_t)c * N + j), a.apow + 2 * k);
+    {
+        const uint32_t nz = a.zs_begin < a.ncols[1] ? a.zs_begin : a.ncols[1];
+#pragma unroll 4
+        for (uint32_t c = 0; c < nz; c++, k++) dotext_mac(d_ta, __ldg(a.lde[1] + (size_t)c * N + j), a.apow + 2 * k);
+        for (uint32_t c = nz; c < a.ncols[1]; c++, k++) {
+            const uint64_t v = __ldg(a.lde[1] + (size_t)c * N + j);
+            dotext_mac(d_ta, v, a.apow + 2 * k);
+            dotext_mac(d_z, v, a.apow + 2 * (c - a.zs_begin));
+        }
     }
-    for (uint32_t c = 0; c < a.ncols[1]; c++, k++) {
-        uint64_t v = __ldg(a.lde[1] + (size_t)c * N + j);
-        s_ta = s_ta + fp2_mul_base(Fp2(a.apow[2 * k], a.apow[2 * k + 1]), v);
-        if (c >= a.zs_begin) { uint32_t kz = c - a.zs_begin; s_z = s_z + fp2_mul_base(Fp2(a.apow[2 * kz], a.apow[2 * kz + 1]), v); }
-    }
-    for (uint32_t c = 0; c < a.ncols[2]; c++, k++) {
-        uint64_t v = __ldg(a.lde[2] + (size_t)c * N + j);
-        s_q = s_q + fp2_mul_base(Fp2(a.apow[2 * k], a.apow[2 * k + 1]), v);
-    }
-    const Fp2 xe(x, 0);
-    Fp2 q0 = (s_ta + s_q - a.v0) * fp2_inv(xe - a.zeta);
-    Fp2 q1 = (s_ta - a.v1) * fp2_inv(xe - a.zeta_next);
+    for (uint32_t c = 0; c < a.ncols[2]; c++, k++) dotext_mac(d_q, __ldg(a.lde[2] + (size_t)c * N + j), a.apow + 2 * k);
+    const Fp2 s_ta = dotext_reduce(d_ta), s_q = dotext_reduce(d_q), s_z = dotext_reduce(d_z);
+    // 1 / (x - z) for z = zeta, g zeta (extension) and 1 (base) from one inversion
+    const Fp2 e0 = Fp2(x, 0) - a.zeta, e1 = Fp2(x, 0) - a.zeta_next;
+    const uint64_t n0 = gl_sub(gl_sqr(e0.a), gl_mul7(gl_sqr(e0.b))), n1 = gl_sub(gl_sqr(e1.a), gl_mul7(gl_sqr(e1.b)));
+    const uint64_t n2 = a.has_b2 ? gl_sub(x, 1) : 1;
+    const uint64_t n01 = gl_mul(n0, n1);
+    const uint64_t inv_all = gl_inv(gl_mul(n01, n2));
+    const uint64_t i2 = gl_mul(inv_all, n01), i01 = gl_mul(inv_all, n2);
+    const uint64_t i0 = gl_mul(i01, n1), i1 = gl_mul(i01, n0);
+    const Fp2 inv0(gl_mul(e0.a, i0), gl_mul(gl_neg(e0.b), i0)), inv1(gl_mul(e1.a, i1), gl_mul(gl_neg(e1.b), i1));
+    Fp2 q0 = (s_ta + s_q - a.v0) * inv0;
+    Fp2 q1 = (s_ta - a.v1) * inv1;
     Fp2 fin = q0 * a.shift1 + q1;
     if (a.has_b2) {
-        Fp2 q2 = fp2_mul_base(s_z - a.v2, gl_inv(gl_sub(x, 1)));
+        Fp2 q2 = fp2_mul_base(s_z - a.v2, i2);
         fin = fin * a.shift2 + q2;
     }
     a.out_re[j] = fin.a;

@@ -17,7 +17,7 @@
 namespace zk {
 
 template <int THREADS, bool INV>
-__global__ void __launch_bounds__(THREADS) ntt_pass_kernel(PassParams p) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 8) ntt_pass_kernel(PassParams p) {
     extern __shared__ uint64_t sm[];
     ntt_pass_tile<INV>(p, blockIdx.x, blockIdx.y, sm, threadIdx.x, THREADS);
 }

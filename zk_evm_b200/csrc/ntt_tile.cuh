@@ -136,11 +136,29 @@ ZK_HD void ntt_stages(uint64_t (&x)[1 << K], std::integer_sequence<int, J...>) {
 template <int K, bool INV>
 ZK_HD void ntt_dft_regs(uint64_t (&x)[1 << K]) { ntt_stages<K, INV>(x, std::make_integer_sequence<int, K>()); }
 
+// where the tile's elements live in global memory (tile index idx = (jd << t) + u for a strided pass, the offset inside the tile for
+// the final pass)
+struct TileIO {
+    const uint64_t* src;
+    uint64_t* dst;
+    const uint64_t* prescale;    // per transform index, or nullptr
+    const uint64_t* interpass;   // already offset to this tile's low index bits, or nullptr
+    size_t base;
+    unsigned strided, t, mp, r;
+    ZK_HD size_t gaddr(unsigned idx) const {
+        return strided ? base + ((size_t)(idx >> t) << mp) + (idx & ((1u << t) - 1)) : base + idx;
+    }
+};
+
 // One round: the K DIF stages over bits s .. s-K+1 of the digit index jd of every sub-transform in the tile, followed by the
 // twiddle w_{2^(s+1)}^(kf * lo) (kf = frequency index produced by this round, lo = the bits of jd below the round) when lo exists.
 // Tile element (jd, u) lives at ntt_pad((jd << t) + u).  Items are numbered u fastest, then lo, then the bits above the round.
+// from_global: the round reads its 2^K elements straight from global memory (+ coset prescale) — the first round of a pass, 2^K
+// independent loads in flight per thread; to_global: it writes them straight back (+ inter-pass twiddle) — the last round of a
+// strided pass, where the 16 lanes of a half-warp still cover one 128-byte row.
 template <int K, bool INV>
-ZK_HD void ntt_round(uint64_t* sm, const uint64_t* __restrict__ roots, int s, unsigned tile_log, unsigned t, unsigned tid, unsigned nthreads) {
+ZK_HD void ntt_round(uint64_t* sm, const uint64_t* __restrict__ roots, int s, unsigned tile_log, unsigned t, unsigned tid, unsigned nthreads,
+                     const TileIO& io, bool from_global, bool to_global) {
     constexpr int E = 1 << K;
     const int low = s - K + 1;
     const unsigned items = 1u << (tile_log - K);
@@ -149,8 +167,17 @@ ZK_HD void ntt_round(uint64_t* sm, const uint64_t* __restrict__ roots, int s, un
         const unsigned lo = g & ((1u << low) - 1), hi = g >> low;
         const unsigned base = ((((hi << K) << low) | lo) << t) + u;
         uint64_t x[E];
+        if (from_global) {
 #pragma unroll
-        for (int k = 0; k < E; k++) x[k] = sm[ntt_pad(base + ((unsigned)k << (low + t)))];
+            for (int k = 0; k < E; k++) x[k] = io.src[io.gaddr(base + ((unsigned)k << (low + t)))];
+            if (io.prescale) {
+#pragma unroll
+                for (int k = 0; k < E; k++) x[k] = gl_mul(x[k], ntt_ld(io.prescale + io.gaddr(base + ((unsigned)k << (low + t)))));
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; k++) x[k] = sm[ntt_pad(base + ((unsigned)k << (low + t)))];
+        }
         ntt_dft_regs<K, INV>(x);
         if (low > 0) {
             const unsigned sh = NTT_ROOT_LOG - (unsigned)(low + K);
@@ -160,8 +187,22 @@ ZK_HD void ntt_round(uint64_t* sm, const uint64_t* __restrict__ roots, int s, un
                 x[kp] = gl_mul(x[kp], ntt_ld(roots + ((size_t)(kf * lo) << sh)));
             }
         }
+        if (to_global) {
+            // low == 0 here: element k is digit position jd = (hi << K) | k, holding frequency kd = rev_r(jd)
 #pragma unroll
-        for (int k = 0; k < E; k++) sm[ntt_pad(base + ((unsigned)k << (low + t)))] = x[k];
+            for (int k = 0; k < E; k++) {
+                const unsigned idx = base + ((unsigned)k << (low + t));
+                uint64_t v = x[k];
+                if (io.interpass) {
+                    const unsigned kd = bitrev32(idx >> t, io.r);
+                    v = gl_mul(v, ntt_ld(io.interpass + ((size_t)kd << io.mp) + (idx & ((1u << t) - 1))));
+                }
+                io.dst[io.gaddr(idx)] = v;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; k++) sm[ntt_pad(base + ((unsigned)k << (low + t)))] = x[k];
+        }
     }
 }
 
@@ -171,70 +212,44 @@ ZK_HD void ntt_round(uint64_t* sm, const uint64_t* __restrict__ roots, int s, un
 #define NTT_TILE_SYNC() ((void)0)
 #endif
 
-// the whole tile: load (+ coset prescale), the rounds of the r-bit digit, inter-pass twiddle + store (in place: digit position
-// jd holds frequency kd = rev_r(jd))
+// the whole tile: the rounds of the r-bit digit (first one loading from global memory, last one of a strided pass storing to it),
+// in place: digit position jd ends up holding frequency kd = rev_r(jd)
 template <bool INV>
 ZK_HD void ntt_pass_tile(const PassParams& p, size_t tile, size_t trans, uint64_t* sm, unsigned tid, unsigned nthreads) {
     const unsigned r = p.r, t = p.t, m = p.m;
     const unsigned tile_log = r + t, tile_elems = 1u << tile_log;
-    const uint64_t* src = p.src + (trans >> p.src_shift) * p.src_stride;
-    uint64_t* dst = p.dst + trans * p.dst_stride;
-    const uint64_t* prescale = p.prescale0 ? ((trans & p.prescale_mask) ? p.prescale1 : p.prescale0) : nullptr;
     const unsigned mp = m - r;   // log M'
-    const unsigned T = 1u << t;
-    size_t base;
+    TileIO io;
+    io.src = p.src + (trans >> p.src_shift) * p.src_stride;
+    io.dst = p.dst + trans * p.dst_stride;
+    io.prescale = p.prescale0 ? ((trans & p.prescale_mask) ? p.prescale1 : p.prescale0) : nullptr;
+    io.strided = p.strided; io.t = t; io.mp = mp; io.r = r;
     if (p.strided) {
         // tile id = hi * 2^(mp - t) + lo_hi; element (jd, lo_t) is transform index hi 2^m + jd 2^mp + lo_hi 2^t + lo_t
         const size_t hi = tile >> (mp - t), lo_hi = tile & (((size_t)1 << (mp - t)) - 1);
-        base = (hi << m) + (lo_hi << t);
-        for (unsigned e = tid; e < tile_elems; e += nthreads) {
-            const unsigned lo_t = e & (T - 1), jd = e >> t;
-            const size_t g = base + ((size_t)jd << mp) + lo_t;
-            uint64_t v = src[g];
-            if (prescale) v = gl_mul(v, ntt_ld(prescale + g));
-            sm[ntt_pad(e)] = v;
-        }
+        io.base = (hi << m) + (lo_hi << t);
+        io.interpass = p.interpass ? p.interpass + (lo_hi << t) : nullptr;
     } else {
         // final pass (mp == 0): 2^t consecutive sub-transforms of 2^r elements, tile index = u 2^r + jd
-        base = tile * (size_t)tile_elems;
-        for (unsigned e = tid; e < tile_elems; e += nthreads) {
-            const size_t g = base + e;
-            uint64_t v = src[g];
-            if (prescale) v = gl_mul(v, ntt_ld(prescale + g));
-            sm[ntt_pad(e)] = v;
-        }
+        io.base = tile * (size_t)tile_elems;
+        io.interpass = nullptr;
     }
-    NTT_TILE_SYNC();
-
-    // rounds of four stages, the first one takes the remainder
-    {
-        const unsigned tt = p.strided ? t : 0;
-        int s = (int)r - 1;
-        const int first = (r % 4) ? (int)(r % 4) : 4;
-        if (first == 1) ntt_round<1, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads);
-        else if (first == 2) ntt_round<2, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads);
-        else if (first == 3) ntt_round<3, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads);
-        else ntt_round<4, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads);
+    const unsigned tt = p.strided ? t : 0;
+    int s = (int)r - 1;
+    const int first = (r % 4) ? (int)(r % 4) : 4;
+    const bool single = first == (int)r;
+    const bool last_to_global = p.strided != 0;
+    if (first == 1) ntt_round<1, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, true, single && last_to_global);
+    else if (first == 2) ntt_round<2, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, true, single && last_to_global);
+    else if (first == 3) ntt_round<3, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, true, single && last_to_global);
+    else ntt_round<4, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, true, single && last_to_global);
+    for (s -= first; s >= 0; s -= 4) {
         NTT_TILE_SYNC();
-        for (s -= first; s >= 0; s -= 4) {
-            ntt_round<4, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads);
-            NTT_TILE_SYNC();
-        }
+        ntt_round<4, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, false, s < 4 && last_to_global);
     }
-
-    if (p.strided) {
-        const size_t lo_base = (tile & (((size_t)1 << (mp - t)) - 1)) << t;
-        for (unsigned e = tid; e < tile_elems; e += nthreads) {
-            const unsigned lo_t = e & (T - 1), jd = e >> t;
-            uint64_t v = sm[ntt_pad(e)];
-            if (p.interpass) {
-                const unsigned kd = bitrev32(jd, r);
-                v = gl_mul(v, ntt_ld(p.interpass + ((size_t)kd << mp) + lo_base + lo_t));
-            }
-            dst[base + ((size_t)jd << mp) + lo_t] = v;
-        }
-    } else {
-        for (unsigned e = tid; e < tile_elems; e += nthreads) dst[base + e] = sm[ntt_pad(e)];
+    if (!last_to_global) {
+        NTT_TILE_SYNC();
+        for (unsigned e = tid; e < tile_elems; e += nthreads) io.dst[io.base + e] = sm[ntt_pad(e)];
     }
 }
 

@@ -45,10 +45,15 @@ struct QuotKernelArgs {
     TableParams prm;
 };
 
-// registers: the Keccak kernel is a load stream (2431 columns per point) and wants several 128-thread blocks per SM with ~40 loads
-// in flight per thread; the others are instruction-bound and take what they need
+// 128-thread blocks per SM the kernel is compiled for (i.e. its register budget, 65536 / (128 * blocks)).  Measured (profiles/r1h,
+// r1k): the Keccak kernel is a load stream (2431 columns per point) and wants ~40 loads in flight per thread at 128 registers; the
+// Arithmetic and Cpu evaluators hold long-lived limb arrays (168 registers); the others are small and run best at high occupancy.
+// Letting ptxas take 255 registers (min blocks = 1) made Cpu 25 % and Arithmetic 34 % slower.
+constexpr int quotient_min_blocks(uint32_t table) {
+    return table == T_KECCAK ? 4 : (table == T_ARITHMETIC || table == T_CPU) ? 3 : table == T_MEMORY ? 7 : 8;
+}
 template <uint32_t TABLE>
-__global__ void __launch_bounds__(128, TABLE == T_KECCAK ? 4 : 1) quotient_kernel(QuotKernelArgs a) {
+__global__ void __launch_bounds__(128, quotient_min_blocks(TABLE)) quotient_kernel(QuotKernelArgs a) {
     // the grid covers exactly N points (block = min(128, N) threads, N a power of two): no early exit, the constraint code
     // contains block-wide barriers (ZKS_SYNC)
     const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
