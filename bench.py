@@ -44,6 +44,10 @@ PUBLIC_VALUES = np.arange(1, 2180, dtype=np.uint64)       # ~2.2k observed eleme
 BG = np.array([0x1111111111, 0x2222222222, 0x3333333333, 0x4444444444], dtype=np.uint64)
 STATE0 = np.arange(1, 13, dtype=np.uint64)
 METRIC = "segment proofs/sec"
+# DRAM bytes per algorithmic byte of the dominant kernel (leaf_hash), from the committed `ncu --set full` capture
+# profiles/r1j_ncu_leaf_hash.raw.csv: Keccak trace leaves, dram__bytes_read.sum + dram__bytes_write.sum = 5.1175 GB + 0.0162 GB for
+# (8 * 2431 + 32) * 2^18 = 5.1066 GB algorithmic (every LDE column read once, one digest written per row)
+LEAF_HASH_TRAFFIC_PER_ALGORITHMIC_BYTE = 5.13375 / 5.10657
 FAMILIES = ("leaf_hash", "merkle_levels", "ntt", "quotient", "aux_columns", "openings", "fri", "pow")
 
 
@@ -242,8 +246,14 @@ def run_ours(args):
             ach = v["bytes"] / v["ms"] / 1e6 if v["ms"] > 0 else 0.0
             return {"launches_per_step": v["launches"] / args.steps, "ms_per_step": v["ms"] / args.steps, "share_of_kernel_time": v["ms"] / tot_ms,
                     "avg_launch_ms": per, "algorithmic_GB_per_step": v["bytes"] / args.steps / 1e9, "achieved_GBps": ach, "frac_of_peak": ach / peak}
+        traffic = None
+        if top == "leaf_hash" and kst[top]["launches"]:
+            # per launch, like `achieved`: measured DRAM bytes per algorithmic byte (ncu capture above) x algorithmic bytes per launch
+            traffic = LEAF_HASH_TRAFFIC_PER_ALGORITHMIC_BYTE * kst[top]["bytes"] / kst[top]["launches"]
         roof = {"bound": "hbm", "kernel": top, "achieved": fam(top)["achieved_GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": fam(top)["frac_of_peak"], "traffic": None,
+                "frac": fam(top)["frac_of_peak"], "traffic": traffic,
+                "traffic_source": "profiles/r1j_ncu_leaf_hash.raw.csv (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                                  "scaled to the average launch of the timed region); bytes" if traffic is not None else None,
                 "how": "CUDA events recorded by the library on its launching stream around every launch group inside a timed region of the same "
                        "K steps run with ONE segment in flight (%.1f ms/step, %.3f proofs/s); achieved = algorithmic bytes of the group "
                        "(DESIGN.md) / event time, summed over the steps" % (ms1 / args.steps, (1 if sharded else world) * args.steps / (ms1 / 1e3)),

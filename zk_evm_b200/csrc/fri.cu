@@ -68,7 +68,7 @@ __global__ void eval_powers_kernel(ulonglong4* __restrict__ tab, size_t n, Fp2 z
     }
 }
 
-__global__ void __launch_bounds__(EVAL_THREADS) eval_columns_kernel(const uint64_t* __restrict__ coeffs, size_t ncols, size_t n,
+__global__ void __launch_bounds__(EVAL_THREADS, 2) eval_columns_kernel(const uint64_t* __restrict__ coeffs, size_t ncols, size_t n,
                                                                     const ulonglong4* __restrict__ tab, uint64_t* __restrict__ partial,
                                                                     size_t nseg) {
     __shared__ uint64_t sm[EVAL_G * 5][EVAL_THREADS / 32];
@@ -79,19 +79,38 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_columns_kernel(const uint64
     Acc96 one[EVAL_G];
 #pragma unroll
     for (int g = 0; g < EVAL_G; g++) { one[g] = {0, 0, 0}; for (int q = 0; q < 4; q++) dot_init(d[g][q]); }
+    // the operands of iteration k + 1 are requested before the products of iteration k are formed
+    const size_t i0 = seg * seg_len + t;
+    ulonglong2 pw0 = make_ulonglong2(0, 0), pw1 = make_ulonglong2(0, 0);
+    uint64_t cv[EVAL_G];
+#pragma unroll
+    for (int g = 0; g < EVAL_G; g++) cv[g] = 0;
+    if (i0 < n) {
+        pw0 = __ldg(reinterpret_cast<const ulonglong2*>(tab + i0)); pw1 = __ldg(reinterpret_cast<const ulonglong2*>(tab + i0) + 1);
+#pragma unroll
+        for (int g = 0; g < EVAL_G; g++) if (col0 + g < ncols) cv[g] = __ldg(coeffs + (col0 + g) * n + i0);
+    }
 #pragma unroll 1
     for (int k = 0; k < EVAL_K; k++) {
-        size_t i = seg * seg_len + (size_t)k * EVAL_THREADS + t;
+        const size_t i = i0 + (size_t)k * EVAL_THREADS;
         if (i >= n) break;
-        const ulonglong2 pw0 = __ldg(reinterpret_cast<const ulonglong2*>(tab + i)), pw1 = __ldg(reinterpret_cast<const ulonglong2*>(tab + i) + 1);
+        const ulonglong2 q0 = pw0, q1 = pw1;
+        uint64_t cc[EVAL_G];
+#pragma unroll
+        for (int g = 0; g < EVAL_G; g++) cc[g] = cv[g];
+        const size_t inx = i + EVAL_THREADS;
+        if (k + 1 < EVAL_K && inx < n) {
+            pw0 = __ldg(reinterpret_cast<const ulonglong2*>(tab + inx)); pw1 = __ldg(reinterpret_cast<const ulonglong2*>(tab + inx) + 1);
+#pragma unroll
+            for (int g = 0; g < EVAL_G; g++) if (col0 + g < ncols) cv[g] = __ldg(coeffs + (col0 + g) * n + inx);
+        }
 #pragma unroll
         for (int g = 0; g < EVAL_G; g++) {
             if (col0 + g >= ncols) break;
-            const uint64_t cv = __ldg(coeffs + (col0 + g) * n + i);
-            uint32_t c0, c1; gl_unpack(cv, c0, c1);
-            dot_mac(d[g][0], c0, c1, pw0.x); dot_mac(d[g][1], c0, c1, pw0.y);
-            dot_mac(d[g][2], c0, c1, pw1.x); dot_mac(d[g][3], c0, c1, pw1.y);
-            acc96_add(one[g], cv);
+            uint32_t c0, c1; gl_unpack(cc[g], c0, c1);
+            dot_mac(d[g][0], c0, c1, q0.x); dot_mac(d[g][1], c0, c1, q0.y);
+            dot_mac(d[g][2], c0, c1, q1.x); dot_mac(d[g][3], c0, c1, q1.y);
+            acc96_add(one[g], cc[g]);
         }
     }
     // per-thread reduction to field elements, warp shuffle tree, then one value per warp through shared memory
@@ -187,7 +206,7 @@ __global__ void __launch_bounds__(256) fri_combine_kernel(CombineKernelArgs a) {
     DotExt d_ta, d_q, d_z;
     dotext_init(d_ta); dotext_init(d_q); dotext_init(d_z);
     uint32_t k = 0;
-#pragma unroll 4
+#pragma unroll 8
     for (uint32_t c = 0; c < a.ncols[0]; c++, k++) dotext_mac(d_ta, __ldg(a.lde[0] + (size_t)c * N + j), a.apow + 2 * k);
     {
         const uint32_t nz = a.zs_begin < a.ncols[1] ? a.zs_begin : a.ncols[1];
@@ -303,8 +322,9 @@ uint64_t pow_grind(Ctx& c, const uint64_t state[12], unsigned pos, unsigned bits
     DevBuf best(&c, 8);
     unsigned long long init = ~0ULL;
     c.h2d(best.get(), &init, 8);
-    // expected number of candidates is 2^bits: a first batch of 4 * 2^bits finds a witness with probability 1 - e^-4
-    const uint64_t batch = std::max<uint64_t>((uint64_t)1 << 14, std::min<uint64_t>((uint64_t)4 << bits, (uint64_t)1 << 22));
+    // expected number of candidates is 2^bits: a batch of 2 * 2^bits (one wave of the GPU for 16 bits) finds a witness with
+    // probability 1 - e^-2; batches are scanned in order, so the result is still the smallest witness
+    const uint64_t batch = std::max<uint64_t>((uint64_t)1 << 14, std::min<uint64_t>((uint64_t)2 << bits, (uint64_t)1 << 22));
     for (uint64_t base = 0;; base += batch) {
         pow_kernel<<<(unsigned)(batch / 128), 128, 0, c.stream>>>(st, pos, bits, base, (unsigned long long*)best.get());
         c.count_launch();

@@ -16,10 +16,16 @@
 
 namespace zk {
 
+// 80 registers per thread: three 256-thread blocks (or the equivalent in smaller ones) per SM
 template <int THREADS, bool INV>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 3 : 8) ntt_pass_kernel(PassParams p) {
+__global__ void __launch_bounds__(THREADS, 768 / THREADS) ntt_pass_kernel(PassParams p) {
     extern __shared__ uint64_t sm[];
     ntt_pass_tile<INV>(p, blockIdx.x, blockIdx.y, sm, threadIdx.x, THREADS);
+}
+template <int THREADS>
+static void launch_pass(dim3 grid, size_t smem, cudaStream_t stream, const PassParams& q, bool inverse) {
+    if (inverse) ntt_pass_kernel<THREADS, true><<<grid, THREADS, smem, stream>>>(q);
+    else ntt_pass_kernel<THREADS, false><<<grid, THREADS, smem, stream>>>(q);
 }
 
 // out[j] = c0 * base^j
@@ -169,13 +175,11 @@ void ntt_dif(Ctx& c, const uint64_t* src, size_t src_stride, unsigned src_shift,
                 q.dst += t0 * q.dst_stride;
             }
             dim3 grid((unsigned)tiles, (unsigned)cnt);
-            if (tile_log >= 10) {
-                if (inverse) ntt_pass_kernel<256, true><<<grid, 256, smem, c.stream>>>(q);
-                else ntt_pass_kernel<256, false><<<grid, 256, smem, c.stream>>>(q);
-            } else {
-                if (inverse) ntt_pass_kernel<64, true><<<grid, 64, smem, c.stream>>>(q);
-                else ntt_pass_kernel<64, false><<<grid, 64, smem, c.stream>>>(q);
-            }
+            // one radix-16 item (16 elements) per thread and round
+            if (tile_log >= 12) launch_pass<256>(grid, smem, c.stream, q, inverse);
+            else if (tile_log >= 11) launch_pass<128>(grid, smem, c.stream, q, inverse);
+            else if (tile_log >= 10) launch_pass<64>(grid, smem, c.stream, q, inverse);
+            else launch_pass<32>(grid, smem, c.stream, q, inverse);
             c.count_launch();
         }
         c.check_launch("ntt_pass_kernel");

@@ -35,22 +35,12 @@ struct PassParams {
 // digit plan of a size-2^L transform, most significant digit first; the last entry is the final (contiguous) pass
 static constexpr unsigned NTT_MAX_STRIDED_R = 8;
 inline void ntt_plan_passes(unsigned L, std::vector<unsigned>& digits) {
+    // strided passes always take 8 bits (a full 2^8 x 16 tile: 256 threads, one radix-16 item each, two rounds); the final
+    // contiguous pass takes what is left (<= 12 bits, as many consecutive sub-transforms per tile as fit in 4096 elements)
     digits.clear();
-    if (L <= NTT_MAX_TILE_LOG) { digits.push_back(L); return; }
-    if (L <= NTT_MAX_TILE_LOG + NTT_MAX_STRIDED_R) {
-        // two passes: keep both tiles large (r1 + NTT_STRIDED_T and L - r1 close to NTT_MAX_TILE_LOG)
-        unsigned r1 = L - NTT_MAX_TILE_LOG;
-        unsigned half = L / 2 < NTT_MAX_STRIDED_R ? L / 2 : NTT_MAX_STRIDED_R;
-        if (r1 < half) r1 = half;
-        digits.push_back(r1);
-        digits.push_back(L - r1);
-        return;
-    }
-    unsigned rest = L - NTT_MAX_TILE_LOG;
-    unsigned ns = (rest + NTT_MAX_STRIDED_R - 1) / NTT_MAX_STRIDED_R;
-    unsigned per = rest / ns, extra = rest % ns;
-    for (unsigned i = 0; i < ns; i++) digits.push_back(per + (i < extra ? 1 : 0));
-    digits.push_back(NTT_MAX_TILE_LOG);
+    unsigned rem = L;
+    while (rem > NTT_MAX_TILE_LOG) { digits.push_back(NTT_MAX_STRIDED_R); rem -= NTT_MAX_STRIDED_R; }
+    digits.push_back(rem);
 }
 // tile columns of pass `pi` of the plan: strided passes stage 16 contiguous elements per digit value, the final pass as many
 // consecutive sub-transforms as fit

@@ -72,17 +72,16 @@ void quotient_values(Ctx& c, const TableDev& t, const QuotientArgs& q) {
     DevBuf apow(&c, 2 * (size_t)(APOW_MAX + 1) * 8);
     for (unsigned i = 0; i < 2; i++) fill_powers(c, apow.get() + i * (size_t)(APOW_MAX + 1), APOW_MAX + 1, a.alphas[i], 1);
     a.apow = apow.get();
-    unsigned blocks = (unsigned)((a.N + 127) / 128);
     switch (q.table) {
-        case T_LOGIC: launch_quotient<T_LOGIC>(a, blocks, c.stream); break;
-        case T_MEMORY: launch_quotient<T_MEMORY>(a, blocks, c.stream); break;
-        case T_MEM_BEFORE: case T_MEM_AFTER: launch_quotient<T_MEM_BEFORE>(a, blocks, c.stream); break;
+        case T_LOGIC: launch_quotient<T_LOGIC>(a, c.stream); break;
+        case T_MEMORY: launch_quotient<T_MEMORY>(a, c.stream); break;
+        case T_MEM_BEFORE: case T_MEM_AFTER: launch_quotient<T_MEM_BEFORE>(a, c.stream); break;
 #if ZKS_ALL_TABLES
-        case T_ARITHMETIC: launch_quotient<T_ARITHMETIC>(a, blocks, c.stream); break;
-        case T_BYTE_PACKING: launch_quotient<T_BYTE_PACKING>(a, blocks, c.stream); break;
-        case T_CPU: launch_quotient<T_CPU>(a, blocks, c.stream); break;
-        case T_KECCAK: launch_quotient<T_KECCAK>(a, blocks, c.stream); break;
-        case T_KECCAK_SPONGE: launch_quotient<T_KECCAK_SPONGE>(a, blocks, c.stream); break;
+        case T_ARITHMETIC: launch_quotient<T_ARITHMETIC>(a, c.stream); break;
+        case T_BYTE_PACKING: launch_quotient<T_BYTE_PACKING>(a, c.stream); break;
+        case T_CPU: launch_quotient<T_CPU>(a, c.stream); break;
+        case T_KECCAK: launch_quotient<T_KECCAK>(a, c.stream); break;
+        case T_KECCAK_SPONGE: launch_quotient<T_KECCAK_SPONGE>(a, c.stream); break;
 #endif
         default: throw ZkError(ZKGPU_ERR_INVALID, "quotient: table id not supported");
     }

@@ -50,13 +50,20 @@ struct QuotKernelArgs {
 // Arithmetic and Cpu evaluators hold long-lived limb arrays (168 registers); the others are small and run best at high occupancy.
 // Letting ptxas take 255 registers (min blocks = 1) made Cpu 25 % and Arithmetic 34 % slower.
 constexpr int quotient_min_blocks(uint32_t table) {
-    return table == T_KECCAK ? 4 : (table == T_ARITHMETIC || table == T_CPU) ? 3 : table == T_MEMORY ? 7 : 8;
+    return table == T_KECCAK ? 4 : (table == T_ARITHMETIC || table == T_CPU) ? 1 : table == T_MEMORY ? 7 : 8;
 }
+// The Arithmetic and Cpu evaluators are 60-80 k instructions of straight-line code (1 MB, the instruction cache holds 32 KB) and
+// ncu shows their warps waiting for instructions: ONE 384-thread block per SM (170 registers per thread) walks that code in
+// lock-step (ZKS_SYNC barriers between constraint groups), so a line fetched for one warp serves all twelve.
+constexpr unsigned quotient_block_threads(uint32_t table) { return (table == T_ARITHMETIC || table == T_CPU) ? 384 : 128; }
+
 template <uint32_t TABLE>
-__global__ void __launch_bounds__(128, quotient_min_blocks(TABLE)) quotient_kernel(QuotKernelArgs a) {
-    // the grid covers exactly N points (block = min(128, N) threads, N a power of two): no early exit, the constraint code
-    // contains block-wide barriers (ZKS_SYNC)
-    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(quotient_block_threads(TABLE), quotient_min_blocks(TABLE)) quotient_kernel(QuotKernelArgs a) {
+    // every thread runs the whole evaluator (the constraint code contains block-wide barriers, ZKS_SYNC): threads past the end of
+    // the domain recompute the last point and skip the store
+    const size_t j0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = j0 < a.N;
+    const size_t j = live ? j0 : a.N - 1;
     const uint32_t i = bitrev32((uint32_t)j, a.log_N);
     const uint32_t inext = (i + 2) & (uint32_t)(a.N - 1);
     const size_t jn = bitrev32(inext, a.log_N);
@@ -90,17 +97,19 @@ __global__ void __launch_bounds__(128, quotient_min_blocks(TABLE)) quotient_kern
     flat_eval_lookups<Fp>(a.flat, betas, lv, nv, alv, anv, yc);
     flat_eval_ctls<Fp>(a.flat, betas, gammas, lv, nv, alv, anv, yc);
 
-    for (unsigned k = 0; k < a.nc; k++) a.out[(size_t)k * a.N + i] = gl_mul(yc.acc[k].v, a.zh_inv[i & 1]);
+    if (live)
+        for (unsigned k = 0; k < a.nc; k++) a.out[(size_t)k * a.N + i] = gl_mul(yc.acc[k].v, a.zh_inv[i & 1]);
 }
 
 // domain table of the quotient kernels (see QuotKernelArgs::dom)
 struct DomArgs { uint64_t* dom; size_t N; unsigned log_N; uint64_t w_N, last, c_first[2], c_last[2]; };
 
 // one launcher per table, defined in quotient_t<N>.cu
-template <uint32_t TABLE> void launch_quotient(const QuotKernelArgs& a, unsigned blocks, cudaStream_t stream);
+template <uint32_t TABLE> void launch_quotient(const QuotKernelArgs& a, cudaStream_t stream);
 #define ZK_INSTANTIATE_QUOTIENT(TABLE)                                                                       \
-    template <> void launch_quotient<TABLE>(const QuotKernelArgs& a, unsigned blocks, cudaStream_t stream) { \
-        quotient_kernel<TABLE><<<blocks, a.N < 128 ? (unsigned)a.N : 128u, 0, stream>>>(a);                  \
+    template <> void launch_quotient<TABLE>(const QuotKernelArgs& a, cudaStream_t stream) {                  \
+        constexpr unsigned T = quotient_block_threads(TABLE);                                                \
+        quotient_kernel<TABLE><<<(unsigned)((a.N + T - 1) / T), T, 0, stream>>>(a);                          \
     }
 
 }  // namespace zk

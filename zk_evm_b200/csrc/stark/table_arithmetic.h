@@ -158,11 +158,13 @@ ZKS_HD void eval_modular(const V& lv, const V& nv, CC& yc) {
         for (uint32_t i = N_LIMBS; i < 2 * N_LIMBS; i++) yc.constraint(sub_filter * quot[i]);
         modular_constr_poly<P>(lv, nv, yc, sub_filter, output, modulus, quot, sub_cp);
     }
+    ZKS_SYNC();
     {
         for (uint32_t i = 0; i < N_LIMBS; i++) { output[i] = lv[MODULAR_OUTPUT + i]; modulus[i] = lv[MODULAR_MODULUS + i]; }
         for (uint32_t i = 0; i < 2 * N_LIMBS; i++) quot[i] = lv[MODULAR_QUO_INPUT + i];
         modular_constr_poly<P>(lv, nv, yc, addmul_filter, output, modulus, quot, mod_cp);
     }
+    ZKS_SYNC();
     // add: constr_poly - (a + b)
     for (uint32_t k = 0; k < 2 * N_LIMBS; k++) {
         P c = mod_cp[k];
@@ -259,8 +261,11 @@ ZKS_HD void eval(const V& lv, const V& nv, CC& yc) {
     yc.constraint_transition(incr * incr - incr);
     yc.constraint_last_row(rc1 - P::from_u64(RANGE_MAX - 1));
 
+    // ZKS_SYNC: the warps of the (one) block of an SM walk this megabyte of straight-line code together and share the fetched lines
+    ZKS_SYNC();
     // MUL
     eval_mul<P>(lv, lv[IS_MUL], INPUT_REGISTER_0, INPUT_REGISTER_1, yc);
+    ZKS_SYNC();
     // ADD, SUB, LT, GT (addcy.rs:135-153): x + y = z + cy * 2^256
     {
         Reg<P, V> in0{&lv, INPUT_REGISTER_0}, in1{&lv, INPUT_REGISTER_1}, out{&lv, OUTPUT_REGISTER}, aux{&lv, AUX_INPUT_REGISTER_0};
@@ -269,15 +274,21 @@ ZKS_HD void eval(const V& lv, const V& nv, CC& yc) {
         eval_addcy<P>(yc, lv[IS_LT], in1, aux, in0, out, false);
         eval_addcy<P>(yc, lv[IS_GT], in0, aux, in1, out, false);
     }
+    ZKS_SYNC();
     // DIV, MOD
     eval_divmod_helper<P>(lv, nv, yc, lv[IS_DIV], INPUT_REGISTER_0, INPUT_REGISTER_1, OUTPUT_REGISTER, AUX_INPUT_REGISTER_0);
+    ZKS_SYNC();
     eval_divmod_helper<P>(lv, nv, yc, lv[IS_MOD], INPUT_REGISTER_0, INPUT_REGISTER_1, AUX_INPUT_REGISTER_0, OUTPUT_REGISTER);
+    ZKS_SYNC();
     // ADDMOD, SUBMOD, MULMOD and the FP254 variants
     eval_modular<P>(lv, nv, yc);
+    ZKS_SYNC();
     // BYTE
     eval_byte<P>(lv, yc);
+    ZKS_SYNC();
     // SHL (== MUL on registers 1, 2), SHR (== DIV on registers 1, 2)
     eval_mul<P>(lv, lv[IS_SHL], INPUT_REGISTER_1, INPUT_REGISTER_2, yc);
+    ZKS_SYNC();
     eval_divmod_helper<P>(lv, nv, yc, lv[IS_SHR], INPUT_REGISTER_1, INPUT_REGISTER_2, OUTPUT_REGISTER, AUX_INPUT_REGISTER_0);
 }
 
