@@ -195,110 +195,13 @@ __device__ __forceinline__ void pf_mds_fft(uint64_t s[12], const uint32_t* __res
     }
 }
 
-// ---- limb form of the state, kept ACROSS the 22 partial rounds ---------------------------------------------------------------
-// In a partial round only lane 0 goes through the S-box; lanes 1..11 see nothing but the (linear) MDS layer and the round
-// constants.  Going back to 64-bit words after every MDS layer (pf_mds_fft) costs ~18 instructions per lane and round for the
-// split + the 3-limb -> 64-bit fold.  Instead lanes 1..11 stay in three limbs x0 + 2^22 x1 + 2^44 x2 and are only re-normalised:
-//   carries x0 -> x1 -> x2, then the overflow h = x2 >> 20 (weight 2^64 == 2^32 - 1) is folded back as the two limbs of the
-//   NON-NEGATIVE integer h (2^32 - 1) < 2^41, so every limb stays >= 0 and wrap-around (mod 2^32) arithmetic stays exact.
-// Invariant after pf_limb_norm: x0 < 2^23, x1 < 2^22 + 2^19, x2 < 2^20; one MDS layer (row sums <= 264) plus constants < 2^22
-// then gives limbs < 264 * 2^23 + 2^22 < 2^32: no overflow.  Lane 0 is folded to 64 bits every round (the S-box needs it).
-struct PfLimbs { uint32_t x0[12], x1[12], x2[12]; };
-
-__device__ __forceinline__ void pf_limb_split(uint64_t v, uint32_t& x0, uint32_t& x1, uint32_t& x2) {
-    uint32_t lo, hi; pf_unpack(v, lo, hi);
-    x0 = lo & 0x3FFFFFu;
-    x1 = __funnelshift_r(lo, hi, 22) & 0x3FFFFFu;
-    x2 = hi >> 12;
-}
-// x0 + 2^22 x1 + 2^44 x2 (x0 < 2^32, x1 + 2^10 (x2 >> 20) < 2^32) -> some u64 congruent mod p
-__device__ __forceinline__ uint64_t pf_limb_fold(uint32_t x0, uint32_t x1, uint32_t x2) {
-    // x2 = 2^20 h + l : 2^64 h == (2^32 - 1) h
-    uint32_t h = x2 >> 20, l = x2 & 0xFFFFFu;
-    x1 += h << 10;                                  // 2^32 h = 2^22 (2^10 h)
-    uint32_t t0, t1, m;
-    // t = x0 + 2^22 x1 - h   (>= 0 because x1 >= 2^10 h)
-    uint32_t s0 = x1 << 22, s1 = x1 >> 10;
-    asm("add.cc.u32 %0, %2, %3;\n\t"
-        "addc.u32 %1, %4, 0;\n\t" : "=r"(t0), "=r"(t1) : "r"(x0), "r"(s0), "r"(s1));
-    asm("sub.cc.u32 %0, %0, %2;\n\t"
-        "subc.u32 %1, %1, 0;\n\t" : "+r"(t0), "+r"(t1) : "r"(h));
-    // + 2^44 l : may carry out of 64 bits (2^64 == EPS)
-    asm("add.cc.u32 %0, %0, %2;\n\t"
-        "addc.u32 %1, 0, 0;\n\t" : "+r"(t1), "=r"(m) : "r"(l << 12));
-    m = 0u - m;
-    asm("add.cc.u32 %0, %0, %2;\n\t"
-        "addc.u32 %1, %1, 0;\n\t" : "+r"(t0), "+r"(t1) : "r"(m));
-    return pf_pack(t0, t1);
-}
-// limbs < 2^32 (x2 < 2^30) -> the invariant above, same value mod p
-__device__ __forceinline__ void pf_limb_norm(uint32_t& x0, uint32_t& x1, uint32_t& x2) {
-    x1 += x0 >> 22; x0 &= 0x3FFFFFu;
-    x2 += x1 >> 22; x1 &= 0x3FFFFFu;
-    const uint32_t h = x2 >> 20; x2 &= 0xFFFFFu;
-    // h (2^32 - 1) as a 64-bit integer, then its limbs of weight 1 and 2^22 (it is < 2^42: no third limb)
-    uint32_t e0, e1;
-    asm("sub.cc.u32 %0, 0, %2;\n\t"
-        "subc.u32 %1, %2, 0;\n\t" : "=r"(e0), "=r"(e1) : "r"(h));
-    x0 += e0 & 0x3FFFFFu;
-    x1 += __funnelshift_r(e0, e1, 22);
-}
-
-// the 22 partial rounds (rounds 4..25): constants of round r+1 are folded into the MDS layer of round r as everywhere else
-__device__ __forceinline__ void pf_partial_rounds(uint64_t s[12]) {
-    uint32_t a0[12], a1[12], a2[12];
-#pragma unroll
-    for (int i = 1; i < 12; i++) pf_limb_split(s[i], a0[i], a1[i], a2[i]);
-    uint64_t s0 = s[0];
-#pragma unroll 1
-    for (int r = 4; r < 26; r++) {
-        s0 = pf_sbox7(s0);
-        pf_limb_split(s0, a0[0], a1[0], a2[0]);
-        uint32_t o0[12], o1[12], o2[12];
-        pf_mds_fft_limb(a0, o0); pf_mds_fft_limb(a1, o1); pf_mds_fft_limb(a2, o2);
-        const uint32_t* __restrict__ rc3 = POSEIDON_RC3_DEV.v + 36 * (r + 1);
-        s0 = pf_limb_fold(o0[0] + rc3[0], o1[0] + rc3[1], o2[0] + rc3[2]);
-#pragma unroll
-        for (int i = 1; i < 12; i++) {
-            a0[i] = o0[i] + rc3[3 * i]; a1[i] = o1[i] + rc3[3 * i + 1]; a2[i] = o2[i] + rc3[3 * i + 2];
-            pf_limb_norm(a0[i], a1[i], a2[i]);
-        }
-    }
-    s[0] = s0;
-#pragma unroll
-    for (int i = 1; i < 12; i++) s[i] = pf_limb_fold(a0[i], a1[i], a2[i]);
-}
-
 // s: canonical or not on input; NON-canonical on output (apply pf_canon to the words that are stored).
 //
 // Code size matters more than instruction count here: the fully unrolled 30-round body is ~90 KB of SASS, far beyond the
 // 32 KB L1.5 instruction cache, and ncu showed warps stalled on instruction fetch ("no_instructions") for most cycles.
-// So there is ONE full-round body (the S-box layer is 3 iterations of "4 S-boxes + rotate the state by 4 lanes", static register
-// indices, 24 moves per iteration; the MDS layer with the next round's constants folded in appears once), executed 4 + 4 times
-// around ONE partial-round loop.
+// So there is ONE round loop: the full S-box layer is 3 iterations of "4 S-boxes + rotate the state by 4 lanes" (static
+// register indices, 24 moves per iteration), the MDS layer (with the next round's constants folded in) appears once.
 __device__ __forceinline__ void pf_permute(uint64_t s[12]) {
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = pf_add_canon(s[i], POSEIDON_RC_DEV[i]);
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-#pragma unroll 1
-        for (int q = 0; q < 4; q++) {
-            const int r = half * 26 + q;
-#pragma unroll 1
-            for (int k = 0; k < 3; k++) {
-                uint64_t t0 = pf_sbox7(s[0]), t1 = pf_sbox7(s[1]), t2 = pf_sbox7(s[2]), t3 = pf_sbox7(s[3]);
-#pragma unroll
-                for (int i = 0; i < 8; i++) s[i] = s[i + 4];
-                s[8] = t0; s[9] = t1; s[10] = t2; s[11] = t3;
-            }
-            pf_mds_fft<true>(s, POSEIDON_RC3_DEV.v + 36 * (r + 1));
-        }
-        if (half == 0) pf_partial_rounds(s);
-    }
-}
-
-// the previous form (every round folds back to 64-bit words), kept for the micro-benchmark
-__device__ __forceinline__ void pf_permute_v3(uint64_t s[12]) {
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = pf_add_canon(s[i], POSEIDON_RC_DEV[i]);
 #pragma unroll 1
