@@ -164,6 +164,7 @@ ZKS_HD void eval_middle_blocked(const V& lv, const V& nv, CC& yc) {
         ZKS_UNROLL for (uint32_t y = 0; y < 5; y++) acc[y] = P::zero();
         const uint32_t xm = (x + 4) % 5, xp = (x + 1) % 5;
         ZKS_NOUNROLL for (uint32_t z0 = 64; z0 > 0; z0 -= 4) {
+            ZKS_SYNC();   // the warps of a block walk the loop body together (instruction-cache sharing, see quotient_kernel.cuh)
             P c0[4], c1[4], c2[4], cp[4], ap[4][5];
             ZKS_UNROLL for (uint32_t k = 0; k < 4; k++) {
                 const uint32_t z = z0 - 1 - k;
@@ -198,6 +199,7 @@ ZKS_HD void eval_middle_blocked(const V& lv, const V& nv, CC& yc) {
         P acc[5];
         ZKS_UNROLL for (uint32_t x = 0; x < 5; x++) acc[x] = P::zero();
         ZKS_NOUNROLL for (uint32_t z0 = 64; z0 > 0; z0 -= 4) {
+            ZKS_SYNC();
             P b[4][5];
             ZKS_UNROLL for (uint32_t k = 0; k < 4; k++) {
                 const uint32_t z = z0 - 1 - k;
