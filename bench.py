@@ -260,8 +260,15 @@ def run_ours(args):
                 "families": {k: fam(k) for k in FAMILIES}}
         if top == "leaf_hash":
             perms = sum(2 * (1 << log_ns[t]) * ((NUM_COLUMNS[t] + 7) // 8) for t in range(9) if mine[t] and NUM_COLUMNS[t] > 4)
+            pps = perms * args.steps / max(kst["leaf_hash"]["ms"], 1e-9) * 1e3
             roof["note"] = "Poseidon is integer-issue bound (~2.6e4 instr per 64-byte absorb): HBM fraction reported because the metric asks " \
-                           "for it; trace-leaf permutations alone: %.0f Mperm/s" % (perms * args.steps / max(kst["leaf_hash"]["ms"], 1e-9) / 1e3)
+                           "for it; trace-leaf permutations alone: %.0f Mperm/s" % (pps / 1e6)
+            # the roofline that actually bounds this kernel: warp-instruction issue (1 per clock per SM sub-partition).  26.2 k
+            # instructions per permutation is the ncu count of the committed capture (smsp__inst_executed.sum / permutations).
+            sm_mhz = (sampler.summary().get("sm_mhz") or 1965)
+            peak_issue = 148 * 4 * 32 * sm_mhz * 1e6
+            roof["issue"] = {"bound": "integer issue slots", "achieved": pps * 26.2e3 / 1e12, "peak": peak_issue / 1e12, "unit": "T thread-instr/s",
+                             "frac": pps * 26.2e3 / peak_issue, "source": "profiles/r1j_ncu_leaf_hash.raw.csv: 26.2 k instr / permutation, ALU pipe 82 %, FMA-heavy pipe 75 % busy"}
         cpu = None if args.no_cpu_baseline else cpu_baseline(args, log_ns)
         line = {"metric": METRIC, "value": segs / (ms / 1e3), "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,

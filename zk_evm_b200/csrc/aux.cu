@@ -20,6 +20,7 @@ using zkstark::FlatView; using zkstark::ColRec; using zkstark::FilterRec; using 
 
 // Column::eval_table: next-row terms count as zero on the last row
 __device__ __forceinline__ uint64_t col_eval_table(const FlatView& f, uint32_t id, const uint64_t* __restrict__ v, size_t n, size_t r) {
+    if (id & zkstark::FLAT_CELL) return v[(size_t)(id & ~zkstark::FLAT_CELL) * n + r];
     const ColRec c = f.cols[id];
     uint64_t acc = c.constant;
     for (uint32_t t = c.lin_begin; t < c.lin_end; t++) acc = gl_add(acc, gl_mul(v[(size_t)f.term_col[t] * n + r], f.term_coef[t]));

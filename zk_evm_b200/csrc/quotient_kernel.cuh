@@ -50,13 +50,14 @@ struct QuotKernelArgs {
 // Arithmetic and Cpu evaluators hold long-lived limb arrays (168 registers); the others are small and run best at high occupancy.
 // Letting ptxas take 255 registers (min blocks = 1) made Cpu 25 % and Arithmetic 34 % slower.
 constexpr int quotient_min_blocks(uint32_t table) {
-    return table == T_KECCAK ? 4 : (table == T_ARITHMETIC || table == T_CPU) ? 3 : table == T_MEMORY ? 7 : 8;
+    return table == T_KECCAK ? 4 : (table == T_ARITHMETIC || table == T_CPU) ? 3 : table == T_MEMORY ? 3 : 8;
 }
 // 128-thread blocks everywhere.  Measured alternative (profiles/r1m): ONE 384-thread block per SM for the Arithmetic / Cpu evaluators
 // (12 warps in lock-step sharing the instruction stream) is no faster in isolation (Cpu 14.6 vs 14.7 ms, Arithmetic 7.7 vs 6.7 ms) and,
 // with two segments in flight, a block that needs the whole register file of an SM starves behind the other stream's small blocks
 // (two-stream step 593 -> 1040 ms).
-constexpr unsigned quotient_block_threads(uint32_t) { return 128; }
+// (Memory: 256-thread blocks at 85 registers — a quarter of an SM — for the same code sharing; its constraint code is descriptor loops.)
+constexpr unsigned quotient_block_threads(uint32_t table) { return table == T_MEMORY ? 256 : 128; }
 
 template <uint32_t TABLE>
 __global__ void __launch_bounds__(quotient_block_threads(TABLE), quotient_min_blocks(TABLE)) quotient_kernel(QuotKernelArgs a) {

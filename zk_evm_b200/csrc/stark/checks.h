@@ -12,6 +12,7 @@ namespace zkstark {
 // already far larger than the instruction cache.
 template <class P, class V>
 ZKS_HD P flat_eval_col(const FlatView& f, uint32_t id, const V& lv, const V& nv) {
+    if (id & FLAT_CELL) return lv[id & ~FLAT_CELL];
     const ColRec r = f.cols[id];
     P acc = P::from_u64(r.constant);
     for (uint32_t t = r.lin_begin; t < r.lin_end; t++) {
@@ -66,6 +67,7 @@ ZKS_HD void flat_eval_helpers(const FlatView& f, uint32_t entry_begin, uint32_t 
 template <class P, class V, class A, class CC>
 ZKS_HD void flat_eval_lookups(const FlatView& f, const P* betas, const V& lv, const V& nv, const A& aux_lv, const A& aux_nv, CC& yc) {
     for (uint32_t li = 0; li < f.n_lookups; li++) {
+        ZKS_SYNC();   // descriptor-driven loops: every thread of the block runs the same iterations, so the warps can share the fetched code
         const LookupRec l = f.lookups[li];
         P ch = betas[l.challenge];
         flat_eval_helpers<P>(f, l.entry_begin, l.entry_end, l.num_helpers, l.helper_begin, P::one(), ch, lv, nv, aux_lv, yc);
@@ -83,6 +85,7 @@ template <class P, class V, class A, class CC>
 ZKS_HD void flat_eval_ctls(const FlatView& f, const P* betas, const P* gammas, const V& lv, const V& nv, const A& aux_lv,
                            const A& aux_nv, CC& yc) {
     for (uint32_t zi = 0; zi < f.n_ctl_zs; zi++) {
+        ZKS_SYNC();
         const CtlZRec c = f.ctl_zs[zi];
         P beta = betas[c.challenge], gamma = gammas[c.challenge];
         P local_z = aux_lv[c.z_col], next_z = aux_nv[c.z_col];

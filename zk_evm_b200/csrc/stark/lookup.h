@@ -148,6 +148,7 @@ inline std::vector<CtlZItem> table_ctl_items(uint32_t table, const std::vector<C
 // ---------------------------------------------------------------------------------------------------------------
 // Flat (POD) form: what the CUDA kernels interpret.  All index ranges are half-open.
 // ---------------------------------------------------------------------------------------------------------------
+static const uint32_t FLAT_CELL = 0x80000000u;
 struct ColRec { uint32_t lin_begin, lin_end, next_begin, next_end; uint64_t constant; };
 struct FilterRec { uint32_t prod_begin, prod_end;     // prod_ids[2k], prod_ids[2k+1] are ColRec ids
                    uint32_t const_begin, const_end; };   // const_ids[k] are ColRec ids
@@ -175,7 +176,11 @@ struct Flat {
     uint32_t num_lookup_cols = 0, num_ctl_helpers = 0, num_ctl_zs = 0;
     uint32_t num_aux() const { return num_lookup_cols + num_ctl_helpers + num_ctl_zs; }
 
+    // Column id: most CTL / lookup columns are a plain cell of the local row (coefficient 1, no constant); those are encoded in
+    // the id itself (FLAT_CELL | column index) and cost the evaluators one load instead of a descriptor walk
     uint32_t add_column(const Column& c) {
+        if (c.lin.size() == 1 && c.next.empty() && canon(c.constant) == 0 && canon(c.lin[0].second) == 1 && c.lin[0].first < FLAT_CELL)
+            return FLAT_CELL | c.lin[0].first;
         ColRec r;
         r.lin_begin = (uint32_t)term_col.size();
         for (auto& p : c.lin) { term_col.push_back(p.first); term_coef.push_back(canon(p.second)); }
