@@ -77,33 +77,15 @@ void poseidon_states(Ctx& c, uint64_t* dev_states, size_t count) {
     c.check_launch("poseidon_states_kernel");
 }
 
-// Resident 128-thread blocks per SM for a leaf-hash launch of `blocks` blocks.  Every thread does the same work (one row,
-// ceil(w/8) permutations — milliseconds for a wide table), so the blocks of a launch finish in synchronised waves and a launch of
-// 1.54 waves (Keccak, 2^18 rows: 2048 blocks on 148 x 9 slots) runs its second wave with the SMs half empty, below the ~7 warps per
-// sub-partition the permutation needs to keep the integer pipes busy.  Fewer resident blocks (dynamic shared memory is only a
-// limiter here, the kernel does not use it) make the waves even: 2048 blocks on 148 x 7 slots = 1.98 waves.
-static unsigned leaf_blocks_per_sm(Ctx& c, size_t blocks) {
-    static const char* env = getenv("ZKGPU_LEAF_BLOCKS");
-    if (env && *env) return (unsigned)atoi(env);
-    // relative permutation throughput of an SM with b resident blocks (4 b warps), tools/pbench-style measurement
-    static const double eff[10] = {0, 0, 0, 0, 0, 0.80, 0.90, 0.96, 0.99, 1.0};
-    unsigned best = 9; double best_t = 1e300;
-    for (unsigned b = 9; b >= 5; b--) {
-        size_t slots = (size_t)c.num_sms * b;
-        size_t waves = (blocks + slots - 1) / slots;
-        double t = (double)waves * b / eff[b];      // time ~ waves x (work per wave ~ b) / efficiency
-        if (t < best_t * 0.999) { best_t = t; best = b; }
-    }
-    return best;
-}
-
+// Resident blocks per SM: 9 (56 registers x 128 threads).  Measured with a shared-memory occupancy limiter (tools/leafbench.py,
+// profiles/r1o_leafbench.jsonl): throughput falls only 3 % from 9 to 5 resident blocks, i.e. five warps per sub-partition already
+// keep the integer pipes busy, so uneven waves (Keccak: 2048 blocks on 148 x 9 slots) cost nothing and 9 is best for every shape.
 void leaf_hash(Ctx& c, const uint64_t* data, size_t stride, size_t ncols, size_t nrows, uint64_t* digests) {
     KernelScope ks(c, KF_LEAF_HASH, (8.0 * ncols + 32.0) * nrows);
-    const size_t blocks = (nrows + 127) / 128;
-    const unsigned b = ncols > 4 ? leaf_blocks_per_sm(c, blocks) : 9;
-    // 9 blocks fit by registers (56 x 128 x 9); b < 9: ask for just over 1/(b+1) of the SM's 227 KB of shared memory per block
-    const size_t smem = b >= 9 ? 0 : (size_t)(227 * 1024) / (b + 1) + 1024;
-    leaf_hash_kernel<<<(unsigned)blocks, 128, smem, c.stream>>>(data, stride, ncols, nrows, digests);
+    static const char* env = getenv("ZKGPU_LEAF_BLOCKS");     // experiment knob of tools/leafbench.py: 5..8 resident blocks per SM
+    const unsigned b = env && *env ? (unsigned)atoi(env) : 9;
+    const size_t smem = b >= 9 || b < 1 ? 0 : (size_t)(227 * 1024) / (b + 1) + 1024;
+    leaf_hash_kernel<<<(unsigned)((nrows + 127) / 128), 128, smem, c.stream>>>(data, stride, ncols, nrows, digests);
     c.count_launch();
     c.check_launch("leaf_hash_kernel");
 }

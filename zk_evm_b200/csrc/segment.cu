@@ -9,7 +9,24 @@
 #include <string.h>
 #include <algorithm>
 
+#include <mutex>
+#include <condition_variable>
+
 struct zkgpu_challenger { zk::Challenger ch; };
+
+namespace zk {
+// One host->device upload chain at a time per device.  With several segments in flight (one context + host thread each) their
+// trace uploads would otherwise interleave on the one H2D copy engine: every segment then waits ~N times longer for its first
+// tables and all of them reach the compute phase together.  Serialised, the first segment's tables arrive at full PCIe speed and
+// the next segment uploads underneath the first one's commitments (measured, two segments in flight: 645-915 ms -> see profiles/).
+struct UploadGate { std::mutex mu; std::condition_variable cv; bool busy = false; };
+static UploadGate g_upload_gate[16];
+static void CUDART_CB upload_gate_release(void* p) {
+    UploadGate* g = static_cast<UploadGate*>(p);
+    { std::lock_guard<std::mutex> l(g->mu); g->busy = false; }
+    g->cv.notify_one();
+}
+}  // namespace zk
 
 namespace zk {
 
@@ -169,12 +186,25 @@ int zkgpu_prove_segment(zkgpu_ctx* h, const zkgpu_table_trace* traces, int mem_k
         cudaEvent_t allocated = events.make();
         ZK_CUDA(cudaEventRecord(allocated, c.stream));
         ZK_CUDA(cudaStreamWaitEvent(c.copy_stream, allocated, 0));
-        for (uint32_t t : order) {
-            Batch& b = tb[t]->b;
-            ZK_CUDA(cudaMemcpyAsync(b.values.get(), traces[t].cols, b.ncols * b.n * 8,
-                                    mem_kind == ZKGPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.copy_stream));
-            uploaded[t] = events.make();
-            ZK_CUDA(cudaEventRecord(uploaded[t], c.copy_stream));
+        UploadGate* gate = mem_kind == ZKGPU_MEM_DEVICE ? nullptr : &g_upload_gate[c.device & 15];
+        if (gate) {
+            std::unique_lock<std::mutex> l(gate->mu);
+            gate->cv.wait(l, [&] { return !gate->busy; });
+            gate->busy = true;
+        }
+        try {
+            for (uint32_t t : order) {
+                Batch& b = tb[t]->b;
+                ZK_CUDA(cudaMemcpyAsync(b.values.get(), traces[t].cols, b.ncols * b.n * 8,
+                                        mem_kind == ZKGPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.copy_stream));
+                uploaded[t] = events.make();
+                ZK_CUDA(cudaEventRecord(uploaded[t], c.copy_stream));
+            }
+            // the gate opens when the last copy of this chain has executed (host callback in copy-stream order)
+            if (gate) ZK_CUDA(cudaLaunchHostFunc(c.copy_stream, upload_gate_release, gate));
+        } catch (...) {
+            if (gate) upload_gate_release(gate);
+            throw;
         }
     }
     struct CopyDrain {   // on any exit (errors included) the copy stream is drained before the buffers it writes are freed
