@@ -157,17 +157,6 @@ def run_ours(args):
         return zk.prove_with_traces(cx, None, PUBLIC_VALUES, cfg, labels, device_ptrs=ptrs)
 
     def step(host, single=False):
-        if nstreams > 1 and not single:
-            res = [None] * nstreams
-            ths = [threading.Thread(target=lambda i=i: res.__setitem__(i, one_segment(ctxs[i], host))) for i in range(nstreams)]
-            for th in ths:
-                th.start()
-            for th in ths:
-                th.join()
-            if any(r is None for r in res):
-                raise RuntimeError("a segment stream failed")
-            d2h[0] = sum(8 * len(p) for r in res for p in r.stark_proofs if p is not None)
-            return res[0]
         if sharded:
             ap = zk.prove_with_traces_sharded(backend, comm, host_traces if host else ptrs, in_use, PUBLIC_VALUES, owner=owner, gather=False)
         elif host:
@@ -176,6 +165,35 @@ def run_ours(args):
             ap = zk.prove_with_traces(ctx, None, PUBLIC_VALUES, cfg, labels, device_ptrs=ptrs)
         d2h[0] = sum(8 * len(p) for p in ap.stark_proofs if p is not None)
         return ap
+
+    def run_steps(host, steps, single=False):
+        """`steps` segment proofs on every stream.  With several streams each one is a host thread that proves its segments back to
+        back (a stream of segments, as a prover node would see it); stream i starts i * stagger later so that the latency-bound phases
+        of one segment (small Merkle levels, transcript round trips) fall under the throughput-bound phases of another.  With host
+        traces the library's upload gate already staggers the streams (one H2D chain at a time)."""
+        if nstreams == 1 or single:
+            for _ in range(steps):
+                step(host)
+            return
+        errs = []
+
+        def worker(i):
+            try:
+                if not host and args.stagger_ms > 0:
+                    time.sleep(i * args.stagger_ms / 1e3)
+                for _ in range(steps):
+                    r = one_segment(ctxs[i], host)
+                    if i == 0:
+                        d2h[0] = nstreams * sum(8 * len(p) for p in r.stark_proofs if p is not None)
+            except Exception as e:      # noqa: BLE001
+                errs.append(e)
+        ths = [threading.Thread(target=worker, args=(i,)) for i in range(nstreams)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        if errs:
+            raise RuntimeError("a segment stream failed: %r" % (errs[0],))
 
     def barrier():
         torch.cuda.synchronize()
@@ -196,8 +214,7 @@ def run_ours(args):
         else:
             ctx.timer_start()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            step(host, single)
+        run_steps(host, steps, single)
         if multi:
             for cx in ctxs:
                 cx.sync()
@@ -214,8 +231,7 @@ def run_ours(args):
             ms, wall = float(t[0]), float(t[1])
         return ms, wall
 
-    for _ in range(args.warmup):
-        step(False)
+    run_steps(False, args.warmup)
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = sum(cx.stats()["kernel_launches"] for cx in ctxs)
@@ -227,8 +243,7 @@ def run_ours(args):
     ms1, wall1 = (ms, wall) if False else timed(False, args.steps, single=True)
     kst = kernel_stats(zk, ctx)
     zk._lib.check(zk.lib().zkgpu_ctx_set_profiling(ctx._h, 0))
-    for _ in range(min(args.warmup, 1)):
-        step(True)
+    run_steps(True, min(args.warmup, 1))
     e_ms, e_wall = timed(True, args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -276,7 +291,8 @@ def run_ours(args):
                 "config": {"workload": ("segment proof (AllStark, 9 tables, heights of witness_b19807080's CI ranges): " if args.workload == "segment"
                                         else "single-table prove (BASELINE config #2): ") + describe(log_ns) + "; standard_fast_config",
                            "parallelism": ("tables of one segment sharded over %d GPUs (owner %s)" % (world, owner)) if sharded
-                           else ("%d independent segment(s) in flight, %d per GPU (one context + CUDA stream + host thread each)" % (world * nstreams, nstreams)),
+                           else ("%d independent segment(s) in flight, %d per GPU (one context + CUDA stream + host thread each, each proving its segments back to back%s)"
+                                 % (world * nstreams, nstreams, ", stream i started %g ms after stream i-1 inside the timed region" % args.stagger_ms if nstreams > 1 else "")),
                            "l2": "inputs larger than L2 (%.2f GB of trace per segment)" % (sum(8 * NUM_COLUMNS[t] * (1 << log_ns[t]) for t in range(9) if in_use[t]) / 1e9),
                            "timing": "CUDA events on the library stream, max over ranks"},
                 "wall_ms_per_step": wall / args.steps,
@@ -358,6 +374,7 @@ def main():
     ap.add_argument("--shrink", type=int, default=0, help="segment workload: make every table 2^shrink times shorter (smoke runs)")
     ap.add_argument("--cpu-shrink", type=int, default=5, help="CPU legs prove tables 2^k times shorter and scale the time")
     ap.add_argument("--streams", type=int, default=2, help="segments in flight per GPU (parallelism=segments)")
+    ap.add_argument("--stagger-ms", type=float, default=80.0, help="start offset between the segment streams of a GPU (inside the timed region)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiler runs)")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not bracket kernel families with CUDA events")
     args = ap.parse_args()

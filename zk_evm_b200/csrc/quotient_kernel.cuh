@@ -15,6 +15,7 @@
 // nine large kernels compile in parallel), quotient.cu holds the launcher.
 #pragma once
 #include "stark_dev.h"
+#include <stdlib.h>
 
 namespace zk {
 
@@ -59,8 +60,10 @@ constexpr int quotient_min_blocks(uint32_t table) {
 // (Memory: 256-thread blocks at 85 registers — a quarter of an SM — for the same code sharing; its constraint code is descriptor loops.)
 constexpr unsigned quotient_block_threads(uint32_t table) { return table == T_MEMORY ? 256 : 128; }
 
-template <uint32_t TABLE>
-__global__ void __launch_bounds__(quotient_block_threads(TABLE), quotient_min_blocks(TABLE)) quotient_kernel(QuotKernelArgs a) {
+// MINB: resident blocks per SM the kernel is compiled for (0 = quotient_min_blocks(TABLE)); the Arithmetic and Cpu kernels are also
+// built at 5 and 8 (96 / 64 registers, a few hundred bytes of spills) and ZKGPU_QUOT_MINB selects one at run time (tuning knob)
+template <uint32_t TABLE, int MINB = 0>
+__global__ void __launch_bounds__(quotient_block_threads(TABLE), MINB ? MINB : quotient_min_blocks(TABLE)) quotient_kernel(QuotKernelArgs a) {
     // every thread runs the whole evaluator (the constraint code contains block-wide barriers, ZKS_SYNC): threads past the end of
     // the domain recompute the last point and skip the store
     const size_t j0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -108,10 +111,20 @@ struct DomArgs { uint64_t* dom; size_t N; unsigned log_N; uint64_t w_N, last, c_
 
 // one launcher per table, defined in quotient_t<N>.cu
 template <uint32_t TABLE> void launch_quotient(const QuotKernelArgs& a, cudaStream_t stream);
+inline int quotient_minb_override() {
+    static const int v = [] { const char* e = getenv("ZKGPU_QUOT_MINB"); return e && *e ? atoi(e) : 0; }();
+    return v;
+}
 #define ZK_INSTANTIATE_QUOTIENT(TABLE)                                                                       \
     template <> void launch_quotient<TABLE>(const QuotKernelArgs& a, cudaStream_t stream) {                  \
         constexpr unsigned T = quotient_block_threads(TABLE);                                                \
-        quotient_kernel<TABLE><<<(unsigned)((a.N + T - 1) / T), T, 0, stream>>>(a);                          \
+        const unsigned blocks = (unsigned)((a.N + T - 1) / T);                                               \
+        if constexpr (TABLE == T_ARITHMETIC || TABLE == T_CPU) {                                             \
+            const int mb = quotient_minb_override();                                                         \
+            if (mb == 5) { quotient_kernel<TABLE, 5><<<blocks, T, 0, stream>>>(a); return; }                 \
+            if (mb == 8) { quotient_kernel<TABLE, 8><<<blocks, T, 0, stream>>>(a); return; }                 \
+        }                                                                                                    \
+        quotient_kernel<TABLE><<<blocks, T, 0, stream>>>(a);                                                 \
     }
 
 }  // namespace zk
