@@ -176,12 +176,15 @@ def run_ours(args):
                 step(host)
             return
         errs = []
+        step_barrier = threading.Barrier(nstreams)
 
         def worker(i):
             try:
                 if not host and args.stagger_ms > 0:
                     time.sleep(i * args.stagger_ms / 1e3)
-                for _ in range(steps):
+                for k in range(steps):
+                    if args.stream_sync == "step" and k > 0:
+                        step_barrier.wait()          # all streams start every step together (no drift between them)
                     r = one_segment(ctxs[i], host)
                     if i == 0:
                         d2h[0] = nstreams * sum(8 * len(p) for p in r.stark_proofs if p is not None)
@@ -374,6 +377,8 @@ def main():
     ap.add_argument("--shrink", type=int, default=0, help="segment workload: make every table 2^shrink times shorter (smoke runs)")
     ap.add_argument("--cpu-shrink", type=int, default=5, help="CPU legs prove tables 2^k times shorter and scale the time")
     ap.add_argument("--streams", type=int, default=2, help="segments in flight per GPU (parallelism=segments)")
+    ap.add_argument("--stream-sync", default="run", choices=["run", "step"],
+                    help="segment streams of a GPU run their K segments back to back (run) or start every step together (step)")
     ap.add_argument("--stagger-ms", type=float, default=80.0, help="start offset between the segment streams of a GPU (inside the timed region)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiler runs)")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not bracket kernel families with CUDA events")

@@ -135,6 +135,15 @@ int zkgpu_ctx_create(int device, zkgpu_ctx** out) {
                                           " (libzkgpu has no CPU path)");
     ZK_REQUIRE(device >= 0 && device < count, "device index out of range");
     ZK_CUDA(cudaSetDevice(device));
+    {
+        // Keep the device's local-memory (stack / spill) backing at its high-water mark.  The Arithmetic quotient kernel needs 1.8 KB
+        // of stack per thread, the others ~0.5 KB; by default the driver shrinks the backing store after the big kernel and grows
+        // it again at its next launch, which needs the whole context idle — with two segments in flight that showed up as sporadic
+        // stalls of hundreds of milliseconds (profiles/r1q: 559 vs 852 ms for the same step).
+        unsigned flags = 0;
+        if (cudaGetDeviceFlags(&flags) == cudaSuccess && !(flags & cudaDeviceLmemResizeToMax))
+            if (cudaSetDeviceFlags(flags | cudaDeviceLmemResizeToMax) != cudaSuccess) cudaGetLastError();   // older drivers: best effort
+    }
     zkgpu_ctx* h = new zkgpu_ctx();
     Ctx& c = h->c;
     c.device = device;

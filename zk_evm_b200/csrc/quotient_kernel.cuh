@@ -48,10 +48,12 @@ struct QuotKernelArgs {
 
 // 128-thread blocks per SM the kernel is compiled for (i.e. its register budget, 65536 / (128 * blocks)).  Measured (profiles/r1h,
 // r1k): the Keccak kernel is a load stream (2431 columns per point) and wants ~40 loads in flight per thread at 128 registers; the
-// Arithmetic and Cpu evaluators hold long-lived limb arrays (168 registers); the others are small and run best at high occupancy.
-// Letting ptxas take 255 registers (min blocks = 1) made Cpu 25 % and Arithmetic 34 % slower.
+// Arithmetic and Cpu evaluators are instruction-fetch bound and gain from more resident warps: measured family time 38.3 ms at 3 blocks
+// (168 registers), 36.2 ms at 5 (96 registers, ~200 bytes of spills), 37.3 ms at 8 (64 registers) — profiles/r1q_bench_minb*.json;
+// letting ptxas take 255 registers (min blocks = 1) made Cpu 25 % and Arithmetic 34 % slower.  The others are small and run best at
+// high occupancy.
 constexpr int quotient_min_blocks(uint32_t table) {
-    return table == T_KECCAK ? 4 : (table == T_ARITHMETIC || table == T_CPU) ? 3 : table == T_MEMORY ? 3 : 8;
+    return table == T_KECCAK ? 4 : (table == T_ARITHMETIC || table == T_CPU) ? 5 : table == T_MEMORY ? 3 : 8;
 }
 // 128-thread blocks everywhere.  Measured alternative (profiles/r1m): ONE 384-thread block per SM for the Arithmetic / Cpu evaluators
 // (12 warps in lock-step sharing the instruction stream) is no faster in isolation (Cpu 14.6 vs 14.7 ms, Arithmetic 7.7 vs 6.7 ms) and,
@@ -60,10 +62,8 @@ constexpr int quotient_min_blocks(uint32_t table) {
 // (Memory: 256-thread blocks at 85 registers — a quarter of an SM — for the same code sharing; its constraint code is descriptor loops.)
 constexpr unsigned quotient_block_threads(uint32_t table) { return table == T_MEMORY ? 256 : 128; }
 
-// MINB: resident blocks per SM the kernel is compiled for (0 = quotient_min_blocks(TABLE)); the Arithmetic and Cpu kernels are also
-// built at 5 and 8 (96 / 64 registers, a few hundred bytes of spills) and ZKGPU_QUOT_MINB selects one at run time (tuning knob)
-template <uint32_t TABLE, int MINB = 0>
-__global__ void __launch_bounds__(quotient_block_threads(TABLE), MINB ? MINB : quotient_min_blocks(TABLE)) quotient_kernel(QuotKernelArgs a) {
+template <uint32_t TABLE>
+__global__ void __launch_bounds__(quotient_block_threads(TABLE), quotient_min_blocks(TABLE)) quotient_kernel(QuotKernelArgs a) {
     // every thread runs the whole evaluator (the constraint code contains block-wide barriers, ZKS_SYNC): threads past the end of
     // the domain recompute the last point and skip the store
     const size_t j0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,20 +111,10 @@ struct DomArgs { uint64_t* dom; size_t N; unsigned log_N; uint64_t w_N, last, c_
 
 // one launcher per table, defined in quotient_t<N>.cu
 template <uint32_t TABLE> void launch_quotient(const QuotKernelArgs& a, cudaStream_t stream);
-inline int quotient_minb_override() {
-    static const int v = [] { const char* e = getenv("ZKGPU_QUOT_MINB"); return e && *e ? atoi(e) : 0; }();
-    return v;
-}
 #define ZK_INSTANTIATE_QUOTIENT(TABLE)                                                                       \
     template <> void launch_quotient<TABLE>(const QuotKernelArgs& a, cudaStream_t stream) {                  \
         constexpr unsigned T = quotient_block_threads(TABLE);                                                \
-        const unsigned blocks = (unsigned)((a.N + T - 1) / T);                                               \
-        if constexpr (TABLE == T_ARITHMETIC || TABLE == T_CPU) {                                             \
-            const int mb = quotient_minb_override();                                                         \
-            if (mb == 5) { quotient_kernel<TABLE, 5><<<blocks, T, 0, stream>>>(a); return; }                 \
-            if (mb == 8) { quotient_kernel<TABLE, 8><<<blocks, T, 0, stream>>>(a); return; }                 \
-        }                                                                                                    \
-        quotient_kernel<TABLE><<<blocks, T, 0, stream>>>(a);                                                 \
+        quotient_kernel<TABLE><<<(unsigned)((a.N + T - 1) / T), T, 0, stream>>>(a);                          \
     }
 
 }  // namespace zk
