@@ -16,7 +16,7 @@ void set_last_error(const std::string& m) { g_last_error = m; }
 
 DevBuf::DevBuf(Ctx* c, size_t nbytes) : ctx(c), bytes(nbytes ? nbytes : 8) {
     void* q = nullptr;
-    cudaError_t e = cudaMallocAsync(&q, bytes, c->stream);
+    cudaError_t e = cudaMallocFromPoolAsync(&q, bytes, c->pool, c->stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
         throw ZkError(e == cudaErrorMemoryAllocation ? ZKGPU_ERR_NOMEM : ZKGPU_ERR_CUDA,
@@ -150,9 +150,20 @@ int zkgpu_ctx_create(int device, zkgpu_ctx** out) {
     ZK_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     ZK_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     ZK_CUDA(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, device));
-    ZK_CUDA(cudaDeviceGetDefaultMemPool(&c.pool, device));
-    uint64_t thresh = UINT64_MAX;
-    ZK_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    // One memory pool PER CONTEXT, never trimmed.  With the device's default pool shared by several contexts (segments in flight),
+    // a block freed stream-ordered by one context can be handed to another whose work then waits for the first stream to reach
+    // that free — an invisible cross-stream dependency that made two-stream steps take anything from 550 to 1350 ms
+    // (profiles/r1s).  Own pools: allocations and frees of a context are ordered on its one stream only.
+    {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        ZK_CUDA(cudaMemPoolCreate(&c.pool, &props));
+        uint64_t thresh = UINT64_MAX;
+        ZK_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    }
     *out = h;
     ZK_API_END
 }
@@ -169,6 +180,7 @@ void zkgpu_ctx_destroy(zkgpu_ctx* h) {
     if (h->c.ev0) { cudaEventDestroy(h->c.ev0); cudaEventDestroy(h->c.ev1); }
     cudaStreamDestroy(h->c.stream);
     cudaStreamDestroy(h->c.copy_stream);
+    if (h->c.pool) cudaMemPoolDestroy(h->c.pool);
     delete h;
 }
 
