@@ -312,11 +312,19 @@ def run_ours(args):
 
 
 # ---- CPU side: the oracle (C++17 + OpenMP restatement of the plonky2 / starky prover) ----------------------------------------
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def oracle_segment_time(log_ns, threads=None):
     from tests import oracle_lib
     orc = oracle_lib.load()
-    if threads:
-        orc.lib.orc_set_num_threads(int(threads))
+    # all the host threads the process may use — torchrun exports OMP_NUM_THREADS=1 to its workers, which is not what "the box's host
+    # cores" means for the CPU arm
+    orc.lib.orc_set_num_threads(int(threads or host_threads()))
     rng = np.random.default_rng(4)
     traces = [None if lg is None else rng.integers(0, 2 ** 63 - 1, size=(NUM_COLUMNS[t], 1 << lg), dtype=np.uint64) for t, lg in enumerate(log_ns)]
     t0 = time.perf_counter()

@@ -55,10 +55,10 @@ struct QuotKernelArgs {
 constexpr int quotient_min_blocks(uint32_t table) {
     return table == T_KECCAK ? 4 : (table == T_ARITHMETIC || table == T_CPU) ? 5 : table == T_MEMORY ? 3 : 8;
 }
-// 128-thread blocks everywhere.  Measured alternative (profiles/r1m): ONE 384-thread block per SM for the Arithmetic / Cpu evaluators
-// (12 warps in lock-step sharing the instruction stream) is no faster in isolation (Cpu 14.6 vs 14.7 ms, Arithmetic 7.7 vs 6.7 ms) and,
-// with two segments in flight, a block that needs the whole register file of an SM starves behind the other stream's small blocks
-// (two-stream step 593 -> 1040 ms).
+// 128-thread blocks (Memory: 256).  Measured alternative (profiles/r1m): ONE 384-thread block per SM for the Arithmetic / Cpu evaluators
+// (12 warps in lock-step sharing the instruction stream) is no faster in isolation (Cpu 14.6 vs 14.7 ms, Arithmetic 7.7 vs 6.7 ms), and a
+// block that needs the whole register file of an SM can only start on an empty SM, which is the wrong shape when a second segment's
+// small blocks are in flight.  (The 1040 ms two-stream step measured with it was later traced to the shared memory pool, see api.cu.)
 // (Memory: 256-thread blocks at 85 registers — a quarter of an SM — for the same code sharing; its constraint code is descriptor loops.)
 constexpr unsigned quotient_block_threads(uint32_t table) { return table == T_MEMORY ? 256 : 128; }
 
