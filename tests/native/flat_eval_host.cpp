@@ -13,6 +13,7 @@ static zkstark::FlatView view_of(const zkstark::Flat& f) {
     v.ctl_zs = f.ctl_zs.data(); v.lookups = f.lookups.data();
     v.n_ctl_zs = (uint32_t)f.ctl_zs.size(); v.n_lookups = (uint32_t)f.lookups.size();
     v.num_lookup_cols = f.num_lookup_cols; v.num_ctl_helpers = f.num_ctl_helpers; v.num_ctl_zs = f.num_ctl_zs;
+    v.ctl_num_constraints = f.ctl_num_constraints; v.ctl_paired = f.ctl_paired;
     return v;
 }
 
@@ -27,7 +28,7 @@ extern "C" int flat_eval_agrees(uint32_t table, uint32_t num_challenges, const u
     AuxShape sh = aux_shape(table, ctls, num_challenges, cd);
     zkstark::Flat flat = zkstark::build_table_flat(zkstark::table_lookups(table), zkstark::table_ctl_items(table, ctls, num_challenges),
                                                   num_challenges, cd);
-    if (num_aux_out) *num_aux_out = flat.num_aux();
+    if (num_aux_out) *num_aux_out = flat.num_aux() | (flat.ctl_paired ? 0x80000000u : 0u);
     if (flat.num_aux() != sh.num_aux()) return -1;
     zkstark::TableParams prm = {labels[0], labels[1], labels[2], labels[3]};
     ConsumerT<OF> a, b;

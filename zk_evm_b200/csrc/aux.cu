@@ -43,7 +43,21 @@ __device__ __forceinline__ uint64_t combine_table(const FlatView& f, const Entry
     return gl_add(acc, gamma);
 }
 
-struct HelperJob { uint32_t entry_begin, entry_end, out_col, pad; uint64_t beta, gamma; };
+// out_col2 != NO_COL: the same (columns, filter) pairs under a second challenge (beta2, gamma2) -> second output column; the filters
+// and the column values are then evaluated once for both
+struct HelperJob { uint32_t entry_begin, entry_end, out_col, out_col2; uint64_t beta, gamma, beta2, gamma2; };
+static constexpr uint32_t NO_COL = 0xFFFFFFFFu;
+__device__ __forceinline__ void combine_table2(const FlatView& f, const EntryRec& e, const HelperJob& j, const uint64_t* __restrict__ v, size_t n,
+                                               size_t r, uint64_t& c0, uint64_t& c1) {
+    uint64_t a0 = 0, a1 = 0;
+    for (uint32_t k = e.col_end; k-- > e.col_begin;) {
+        const uint64_t x = col_eval_table(f, f.col_ids[k], v, n, r);
+        a0 = gl_add(gl_mul(a0, j.beta), x);
+        a1 = gl_add(gl_mul(a1, j.beta2), x);
+    }
+    c0 = gl_add(a0, j.gamma);
+    c1 = gl_add(a1, j.gamma2);
+}
 
 static constexpr int AUX_ROWS = 8;
 // inv[i] = 1 / d[i] for the rows < cnt (0 where d[i] == 0, as gl_inv(0) = 0): one inversion for the whole batch
@@ -65,6 +79,40 @@ __global__ void __launch_bounds__(256) helper_kernel(FlatView f, const HelperJob
     const HelperJob j = jobs[blockIdx.y];
     const size_t r0 = (size_t)blockIdx.x * (256 * AUX_ROWS) + threadIdx.x;
     uint64_t num[AUX_ROWS], den[AUX_ROWS], inv[AUX_ROWS];
+    if (j.out_col2 != NO_COL) {
+        // two challenges: AUX_ROWS / 2 rows x 2 denominators share the inversion; rows r0 + i*256, i < AUX_ROWS/2, and the second
+        // half of the block's row range is taken by the threads' upper slots (r0 + (AUX_ROWS/2 + i) * 256) in a second sweep
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+#pragma unroll
+            for (int i = 0; i < AUX_ROWS / 2; i++) {
+                const size_t r = r0 + (size_t)(half * (AUX_ROWS / 2) + i) * 256;
+                num[2 * i] = num[2 * i + 1] = 0; den[2 * i] = den[2 * i + 1] = 1;
+                if (r >= n) continue;
+                uint64_t fs[2] = {0, 0}, c0[2] = {1, 1}, c1[2] = {1, 1};
+                for (uint32_t e = j.entry_begin; e < j.entry_end; e++) {
+                    const EntryRec er = f.entries[e];
+                    const uint64_t fv = filter_eval_table(f, er.filter, values, n, r);
+                    fs[e - j.entry_begin] = fv;
+                    if (fv) combine_table2(f, er, j, values, n, r, c0[e - j.entry_begin], c1[e - j.entry_begin]);
+                }
+                den[2 * i] = gl_mul(c0[0], c0[1]);
+                num[2 * i] = gl_add(gl_mul(fs[0], c0[1]), gl_mul(fs[1], c0[0]));
+                den[2 * i + 1] = gl_mul(c1[0], c1[1]);
+                num[2 * i + 1] = gl_add(gl_mul(fs[0], c1[1]), gl_mul(fs[1], c1[0]));
+            }
+            batch_inverse(den, inv);
+#pragma unroll
+            for (int i = 0; i < AUX_ROWS / 2; i++) {
+                const size_t r = r0 + (size_t)(half * (AUX_ROWS / 2) + i) * 256;
+                if (r < n) {
+                    out[(size_t)j.out_col * n + r] = gl_mul(num[2 * i], inv[2 * i]);
+                    out[(size_t)j.out_col2 * n + r] = gl_mul(num[2 * i + 1], inv[2 * i + 1]);
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < AUX_ROWS; i++) {
         const size_t r = r0 + (size_t)i * 256;
@@ -261,22 +309,28 @@ void ctl_columns(Ctx& c, const TableDev& t, const uint64_t* values, size_t n, co
     std::vector<ZJob> zj;
     std::vector<ScanJob> sj;
     for (const zkstark::CtlZRec& z : f.ctl_zs) {
+        // with two challenges an item and its twin (same entries, other challenge) share their helper jobs
+        const bool paired = f.ctl_paired && z.twin != zkstark::NO_TWIN;
+        const zkstark::CtlZRec* tw = paired ? &f.ctl_zs[z.twin] : nullptr;
+        const bool second = paired && z.challenge != 0;     // its columns are produced by the twin's jobs
         if (z.num_helpers) {
-            for (uint32_t h = 0; h < z.num_helpers; h++) {
+            for (uint32_t h = 0; h < z.num_helpers && !second; h++) {
                 HelperJob j;
                 j.entry_begin = z.entry_begin + 2 * h;
                 j.entry_end = std::min(z.entry_end, j.entry_begin + 2);
-                j.out_col = z.helper_begin - base + h; j.pad = 0;
-                j.beta = betas[z.challenge]; j.gamma = gammas[z.challenge];
+                j.out_col = z.helper_begin - base + h; j.out_col2 = NO_COL;
+                j.beta = betas[z.challenge]; j.gamma = gammas[z.challenge]; j.beta2 = j.gamma2 = 0;
+                if (paired) { j.out_col2 = tw->helper_begin - base + h; j.beta2 = betas[tw->challenge]; j.gamma2 = gammas[tw->challenge]; }
                 hj.push_back(j);
             }
             ZJob q; q.kind = 0; q.helper_begin = z.helper_begin - base; q.num_helpers = z.num_helpers; q.out_col = z.z_col - base;
             q.table_col = q.freq_col = 0; q.challenge = 0;
             zj.push_back(q);
-        } else {
+        } else if (!second) {
             HelperJob j;   // single pair: filter/combined goes straight into the Z column
-            j.entry_begin = z.entry_begin; j.entry_end = z.entry_end; j.out_col = z.z_col - base; j.pad = 0;
-            j.beta = betas[z.challenge]; j.gamma = gammas[z.challenge];
+            j.entry_begin = z.entry_begin; j.entry_end = z.entry_end; j.out_col = z.z_col - base; j.out_col2 = NO_COL;
+            j.beta = betas[z.challenge]; j.gamma = gammas[z.challenge]; j.beta2 = j.gamma2 = 0;
+            if (paired) { j.out_col2 = tw->z_col - base; j.beta2 = betas[tw->challenge]; j.gamma2 = gammas[tw->challenge]; }
             hj.push_back(j);
         }
         sj.push_back({z.z_col - base, 1u});
@@ -297,8 +351,8 @@ void lookup_columns(Ctx& c, const TableDev& t, const uint64_t* values, size_t n,
             HelperJob j;
             j.entry_begin = l.entry_begin + 2 * h;
             j.entry_end = std::min(l.entry_end, j.entry_begin + 2);
-            j.out_col = l.helper_begin + h; j.pad = 0;
-            j.beta = 1; j.gamma = betas[l.challenge];
+            j.out_col = l.helper_begin + h; j.out_col2 = NO_COL;
+            j.beta = 1; j.gamma = betas[l.challenge]; j.beta2 = j.gamma2 = 0;
             hj.push_back(j);
         }
         ZJob q; q.kind = 1; q.helper_begin = l.helper_begin; q.num_helpers = l.num_helpers; q.out_col = l.z_col;
@@ -349,6 +403,7 @@ const TableDev& get_table_dev(Ctx& c, uint32_t table, unsigned num_challenges) {
     v.ctl_zs = (const zkstark::CtlZRec*)(d + o_cz); v.lookups = (const zkstark::LookupRec*)(d + o_lk);
     v.n_ctl_zs = (uint32_t)f.ctl_zs.size(); v.n_lookups = (uint32_t)f.lookups.size();
     v.num_lookup_cols = f.num_lookup_cols; v.num_ctl_helpers = f.num_ctl_helpers; v.num_ctl_zs = f.num_ctl_zs;
+    v.ctl_num_constraints = f.ctl_num_constraints; v.ctl_paired = f.ctl_paired;
     c.stark_tables[key] = td;
     return *td;
 }

@@ -81,9 +81,73 @@ ZKS_HD void flat_eval_lookups(const FlatView& f, const P* betas, const V& lv, co
     }
 }
 
+// GrandProductChallenge::combine for both challenges at once: the column values are walked once
+template <class P, class V>
+ZKS_HD_NOINLINE void flat_combine2(const FlatView& f, const EntryRec& e, const P* betas, const P* gammas, const V& lv, const V& nv, P& c0, P& c1) {
+    P a0 = P::zero(), a1 = P::zero();
+    for (uint32_t k = e.col_end; k-- > e.col_begin;) {
+        const P v = flat_eval_col<P>(f, f.col_ids[k], lv, nv);
+        a0 = a0 * betas[0] + v;
+        a1 = a1 * betas[1] + v;
+    }
+    c0 = a0 + gammas[0];
+    c1 = a1 + gammas[1];
+}
+
+// The CTL section with two challenges: an item and its twin (same columns and filters, other challenge) are evaluated together —
+// one walk over the columns and filters instead of two — and their constraints go to their own positions of the section through
+// the index-addressed block of the consumer (block_put), so the result is the one the sequential emission gives.
+template <class P, class V, class A, class CC>
+ZKS_HD void flat_eval_ctls_paired(const FlatView& f, const P* betas, const P* gammas, const V& lv, const V& nv, const A& aux_lv,
+                                  const A& aux_nv, CC& yc) {
+    if (f.n_ctl_zs == 0) return;
+    yc.block_begin(f.ctl_num_constraints);
+    for (uint32_t zi = 0; zi < f.n_ctl_zs; zi++) {
+        ZKS_SYNC();
+        const CtlZRec c = f.ctl_zs[zi];
+        if (c.challenge != 0) continue;
+        const CtlZRec d = f.ctl_zs[c.twin];
+        const P lz0 = aux_lv[c.z_col], nz0 = aux_nv[c.z_col], lz1 = aux_lv[d.z_col], nz1 = aux_nv[d.z_col];
+        if (c.num_helpers) {
+            P hs0 = P::zero(), hs1 = P::zero();
+            for (uint32_t t = 0; t < c.num_helpers; t++) {
+                const uint32_t e0 = c.entry_begin + 2 * t;
+                const P h0 = aux_lv[c.helper_begin + t], h1 = aux_lv[d.helper_begin + t];
+                P a0, a1;
+                flat_combine2<P>(f, f.entries[e0], betas, gammas, lv, nv, a0, a1);
+                const P f0 = flat_eval_filter<P>(f, f.entries[e0].filter, lv, nv);
+                if (e0 + 1 < c.entry_end) {
+                    P b0, b1;
+                    flat_combine2<P>(f, f.entries[e0 + 1], betas, gammas, lv, nv, b0, b1);
+                    const P f1 = flat_eval_filter<P>(f, f.entries[e0 + 1].filter, lv, nv);
+                    yc.block_put(c.cons_begin + t, b0 * a0 * h0 - f0 * b0 - f1 * a0);
+                    yc.block_put(d.cons_begin + t, b1 * a1 * h1 - f0 * b1 - f1 * a1);
+                } else {
+                    yc.block_put(c.cons_begin + t, a0 * h0 - f0);
+                    yc.block_put(d.cons_begin + t, a1 * h1 - f0);
+                }
+                hs0 = hs0 + h0; hs1 = hs1 + h1;
+            }
+            yc.block_put(c.cons_begin + c.num_helpers, (lz0 - hs0) * yc.lagrange_last);
+            yc.block_put(c.cons_begin + c.num_helpers + 1, (lz0 - nz0 - hs0) * yc.z_last);
+            yc.block_put(d.cons_begin + d.num_helpers, (lz1 - hs1) * yc.lagrange_last);
+            yc.block_put(d.cons_begin + d.num_helpers + 1, (lz1 - nz1 - hs1) * yc.z_last);
+        } else {
+            P a0, a1;
+            flat_combine2<P>(f, f.entries[c.entry_begin], betas, gammas, lv, nv, a0, a1);
+            const P f0 = flat_eval_filter<P>(f, f.entries[c.entry_begin].filter, lv, nv);
+            yc.block_put(c.cons_begin, (a0 * lz0 - f0) * yc.lagrange_last);
+            yc.block_put(c.cons_begin + 1, (a0 * (lz0 - nz0) - f0) * yc.z_last);
+            yc.block_put(d.cons_begin, (a1 * lz1 - f0) * yc.lagrange_last);
+            yc.block_put(d.cons_begin + 1, (a1 * (lz1 - nz1) - f0) * yc.z_last);
+        }
+    }
+}
+
 template <class P, class V, class A, class CC>
 ZKS_HD void flat_eval_ctls(const FlatView& f, const P* betas, const P* gammas, const V& lv, const V& nv, const A& aux_lv,
                            const A& aux_nv, CC& yc) {
+    if (f.ctl_paired) { flat_eval_ctls_paired<P>(f, betas, gammas, lv, nv, aux_lv, aux_nv, yc); return; }
     for (uint32_t zi = 0; zi < f.n_ctl_zs; zi++) {
         ZKS_SYNC();
         const CtlZRec c = f.ctl_zs[zi];

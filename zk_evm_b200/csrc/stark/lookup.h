@@ -156,7 +156,11 @@ struct FilterRec { uint32_t prod_begin, prod_end;     // prod_ids[2k], prod_ids[
 struct EntryRec { uint32_t col_begin, col_end; uint32_t filter; uint32_t pad; };
 // one CtlZData of a table: entries [entry_begin, entry_end); helper columns live at aux index helper_begin..+num_helpers,
 // the running sum Z at aux index z_col
-struct CtlZRec { uint32_t entry_begin, entry_end; uint32_t num_helpers; uint32_t challenge; uint32_t helper_begin; uint32_t z_col; };
+struct CtlZRec { uint32_t entry_begin, entry_end; uint32_t num_helpers; uint32_t challenge; uint32_t helper_begin; uint32_t z_col;
+                 // position of this item's first constraint inside the table's CTL section (num_helpers + 2 constraints, or 2), and
+                 // the index of the item that differs from this one only by the challenge (NO_TWIN if there is none)
+                 uint32_t cons_begin; uint32_t twin; };
+static const uint32_t NO_TWIN = 0xFFFFFFFFu;
 // one in-table Lookup for one challenge: single-column entries [entry_begin, entry_end); helpers at aux index
 // helper_begin..+num_helpers, Z at z_col
 struct LookupRec { uint32_t entry_begin, entry_end; uint32_t table_col, freq_col; uint32_t num_helpers; uint32_t challenge;
@@ -174,6 +178,8 @@ struct Flat {
     std::vector<CtlZRec> ctl_zs;
     std::vector<LookupRec> lookups;
     uint32_t num_lookup_cols = 0, num_ctl_helpers = 0, num_ctl_zs = 0;
+    uint32_t ctl_num_constraints = 0;   // constraints of the CTL section
+    uint32_t ctl_paired = 0;            // 1: two challenges and every item has its twin -> the evaluators share the column walks
     uint32_t num_aux() const { return num_lookup_cols + num_ctl_helpers + num_ctl_zs; }
 
     // Column id: most CTL / lookup columns are a plain cell of the local row (coefficient 1, no constant); those are encoded in
@@ -254,7 +260,31 @@ inline Flat build_table_flat(const std::vector<Lookup>& lookups, const std::vect
         r.challenge = it.challenge;
         r.helper_begin = hpos; hpos += r.num_helpers;
         r.z_col = zpos++;
+        r.cons_begin = f.ctl_num_constraints;
+        f.ctl_num_constraints += r.num_helpers ? r.num_helpers + 2 : 2;
+        r.twin = NO_TWIN;
         f.ctl_zs.push_back(r);
+    }
+    // twins: same CTL, same position inside the (CTL, challenge) group, other challenge
+    if (num_challenges == 2) {
+        f.ctl_paired = 1;
+        for (size_t i = 0; i < items.size(); i++) {
+            if (items[i].challenge != 0) continue;
+            size_t ord = 0;
+            for (size_t k = 0; k < i; k++) if (items[k].ctl_index == items[i].ctl_index && items[k].challenge == 0) ord++;
+            size_t seen = 0;
+            for (size_t k = 0; k < items.size(); k++) {
+                if (items[k].ctl_index != items[i].ctl_index || items[k].challenge != 1) continue;
+                if (seen++ == ord) {
+                    if (items[k].entries.size() == items[i].entries.size() && items[k].looked == items[i].looked) {
+                        f.ctl_zs[i].twin = (uint32_t)k; f.ctl_zs[k].twin = (uint32_t)i;
+                    }
+                    break;
+                }
+            }
+            if (f.ctl_zs[i].twin == NO_TWIN) f.ctl_paired = 0;
+        }
+        for (const CtlZRec& r : f.ctl_zs) if (r.twin == NO_TWIN) f.ctl_paired = 0;
     }
     return f;
 }
@@ -265,6 +295,7 @@ struct FlatView {
     const uint32_t* prod_ids; const uint32_t* const_ids; const FilterRec* filters; const EntryRec* entries;
     const CtlZRec* ctl_zs; const LookupRec* lookups;
     uint32_t n_ctl_zs, n_lookups, num_lookup_cols, num_ctl_helpers, num_ctl_zs;
+    uint32_t ctl_num_constraints, ctl_paired;
 };
 
 }  // namespace zkstark
