@@ -166,28 +166,43 @@ def run_ours(args):
         d2h[0] = sum(8 * len(p) for p in ap.stark_proofs if p is not None)
         return ap
 
+    def prove_stream(cx, host, steps, first_barrier=None):
+        """`steps` segment proofs back to back on one context.  Host traces: the uploads of segment s+1 are queued before segment s is
+        proved (zkgpu_segment_upload / zkgpu_prove_segment_uploaded), so every H2D chain but the first runs under the previous proof."""
+        r = None
+        if host and not sharded:
+            nxt = zk.upload_traces(cx, host_traces, cfg)
+            for k in range(steps):
+                cur, nxt = nxt, (zk.upload_traces(cx, host_traces, cfg) if k + 1 < steps else None)
+                r = zk.prove_with_traces(cx, None, PUBLIC_VALUES, cfg, labels, upload=cur)
+        else:
+            for k in range(steps):
+                r = one_segment(cx, host)
+        return r
+
     def run_steps(host, steps, single=False):
         """`steps` segment proofs on every stream.  With several streams each one is a host thread that proves its segments back to
         back (a stream of segments, as a prover node would see it); stream i starts i * stagger later so that the latency-bound phases
         of one segment (small Merkle levels, transcript round trips) fall under the throughput-bound phases of another.  With host
         traces the library's upload gate already staggers the streams (one H2D chain at a time)."""
-        if nstreams == 1 or single:
+        if sharded:
             for _ in range(steps):
                 step(host)
             return
+        if nstreams == 1 or single:
+            r = prove_stream(ctx, host, steps)
+            if r is not None:
+                d2h[0] = sum(8 * len(p) for p in r.stark_proofs if p is not None)
+            return
         errs = []
-        step_barrier = threading.Barrier(nstreams)
 
         def worker(i):
             try:
                 if not host and args.stagger_ms > 0:
                     time.sleep(i * args.stagger_ms / 1e3)
-                for k in range(steps):
-                    if args.stream_sync == "step" and k > 0:
-                        step_barrier.wait()          # all streams start every step together (no drift between them)
-                    r = one_segment(ctxs[i], host)
-                    if i == 0:
-                        d2h[0] = nstreams * sum(8 * len(p) for p in r.stark_proofs if p is not None)
+                r = prove_stream(ctxs[i], host, steps)
+                if i == 0 and r is not None:
+                    d2h[0] = nstreams * sum(8 * len(p) for p in r.stark_proofs if p is not None)
             except Exception as e:      # noqa: BLE001
                 errs.append(e)
         ths = [threading.Thread(target=worker, args=(i,)) for i in range(nstreams)]
@@ -385,8 +400,6 @@ def main():
     ap.add_argument("--shrink", type=int, default=0, help="segment workload: make every table 2^shrink times shorter (smoke runs)")
     ap.add_argument("--cpu-shrink", type=int, default=5, help="CPU legs prove tables 2^k times shorter and scale the time")
     ap.add_argument("--streams", type=int, default=2, help="segments in flight per GPU (parallelism=segments)")
-    ap.add_argument("--stream-sync", default="run", choices=["run", "step"],
-                    help="segment streams of a GPU run their K segments back to back (run) or start every step together (step)")
     ap.add_argument("--stagger-ms", type=float, default=80.0, help="start offset between the segment streams of a GPU (inside the timed region)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiler runs)")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not bracket kernel families with CUDA events")

@@ -192,6 +192,20 @@ int zkgpu_prove_segment(zkgpu_ctx* ctx, const zkgpu_table_trace* traces /*[ZKGPU
                         const uint64_t* forced_pow_witnesses, volatile const int* abort_flag, zkgpu_proof** proofs_out /*[ZKGPU_NUM_TABLES]*/,
                         uint64_t* ctl_challenges_out, uint64_t* trace_caps_out);
 
+/* The same call in two halves, for a stream of segments (zero/src/prover.rs:224-236 feeds segments one after the other): queue the
+ * uploads of segment s+1 BEFORE proving segment s and the whole H2D chain of s+1 runs under the proof of s (its buffers are
+ * allocated in stream order at the point of the call).  The traces must stay valid until zkgpu_prove_segment_uploaded returns
+ * (pinned host memory, or the copies are staged synchronously).  An upload is consumed by exactly one prove call and freed with
+ * zkgpu_upload_free (also when it was never proved).  zkgpu_prove_segment == upload + prove_uploaded. */
+typedef struct zkgpu_upload zkgpu_upload;
+int zkgpu_segment_upload(zkgpu_ctx* ctx, const zkgpu_table_trace* traces /*[ZKGPU_NUM_TABLES]*/, int mem_kind, const zkgpu_stark_config* config,
+                         zkgpu_upload** out);
+int zkgpu_prove_segment_uploaded(zkgpu_ctx* ctx, zkgpu_upload* upload, const uint64_t* public_values, size_t n_public_values,
+                                 const zkgpu_kernel_labels* labels, const zkgpu_stark_config* config, const uint64_t* forced_pow_witnesses,
+                                 volatile const int* abort_flag, zkgpu_proof** proofs_out /*[ZKGPU_NUM_TABLES]*/, uint64_t* ctl_challenges_out,
+                                 uint64_t* trace_caps_out);
+void zkgpu_upload_free(zkgpu_upload* upload);
+
 /* ---- stage-by-stage parity hooks (tests) ---------------------------------------------------------------------- */
 /* when on, proofs retain their auxiliary / quotient PolynomialBatch and the FRI input values */
 int zkgpu_ctx_set_debug(zkgpu_ctx* ctx, int on);

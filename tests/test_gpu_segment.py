@@ -67,3 +67,26 @@ def test_missing_mandatory_table_is_an_error(ctx):
     tr[traces.T_CPU] = None
     with pytest.raises(zk.ZkGpuError):
         zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, zk.StarkConfig(*TEST_CONFIG), zk.KernelLabels(*DEFAULT_LABELS))
+
+
+def test_upload_ahead_of_prove_gives_the_same_proofs(ctx, oracle):
+    """zkgpu_segment_upload for segment s+1 queued before zkgpu_prove_segment_uploaded for segment s (the prefetch pattern of a
+    stream of segments): same proofs as the one-call form, uploads consumed exactly once, an unused upload can be dropped"""
+    cfg = zk.StarkConfig(*TEST_CONFIG)
+    lab = zk.KernelLabels(*DEFAULT_LABELS)
+    segs = [traces.valid_segment(seed=31), traces.valid_segment(seed=32, k=17), traces.valid_segment(seed=33, k=29)]
+    want = [zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, cfg, lab) for tr in segs]
+    got = []
+    nxt = zk.upload_traces(ctx, segs[0], cfg)
+    for s in range(len(segs)):
+        cur, nxt = nxt, (zk.upload_traces(ctx, segs[s + 1], cfg) if s + 1 < len(segs) else None)
+        got.append(zk.prove_with_traces(ctx, None, PUBLIC_VALUES, cfg, lab, upload=cur))
+        with pytest.raises(Exception):
+            zk.prove_with_traces(ctx, None, PUBLIC_VALUES, cfg, lab, upload=cur)      # consumed
+    for a, b in zip(got, want):
+        _same(a, b.stark_proofs, b.ctl_challenges, b.trace_caps)
+    zk.upload_traces(ctx, segs[1], cfg).free()                                          # never proved
+    # another StarkConfig than the one the upload was made for is refused
+    up = zk.upload_traces(ctx, segs[0], cfg)
+    with pytest.raises(zk.ZkGpuError):
+        zk.prove_with_traces(ctx, None, PUBLIC_VALUES, zk.StarkConfig(*(TEST_CONFIG[:3] + (3,) + TEST_CONFIG[4:])), lab, upload=up)

@@ -10,22 +10,17 @@
 #include <algorithm>
 
 #include <mutex>
-#include <condition_variable>
 
 struct zkgpu_challenger { zk::Challenger ch; };
 
 namespace zk {
-// One host->device upload chain at a time per device.  With several segments in flight (one context + host thread each) their
-// trace uploads would otherwise interleave on the one H2D copy engine: every segment then waits ~N times longer for its first
-// tables and all of them reach the compute phase together.  Serialised, the first segment's tables arrive at full PCIe speed and
-// the next segment uploads underneath the first one's commitments (measured, two segments in flight: 645-915 ms -> see profiles/).
-struct UploadGate { std::mutex mu; std::condition_variable cv; bool busy = false; };
+// One host->device upload chain at a time per device, ordered ON THE DEVICE.  With several segments in flight (one context + host
+// thread each) their trace uploads would otherwise interleave on the one H2D copy engine: every segment then waits ~N times longer
+// for its first tables.  Each chain's first copy waits (cudaStreamWaitEvent on the context's copy stream) for the event that ends
+// the previously queued chain of the device; the host never blocks, so a thread can queue the uploads of its next segment and go
+// straight on to prove the current one.
+struct UploadGate { std::mutex mu; cudaEvent_t last = nullptr; };
 static UploadGate g_upload_gate[16];
-static void CUDART_CB upload_gate_release(void* p) {
-    UploadGate* g = static_cast<UploadGate*>(p);
-    { std::lock_guard<std::mutex> l(g->mu); g->busy = false; }
-    g->cv.notify_one();
-}
 }  // namespace zk
 
 namespace zk {
@@ -144,76 +139,91 @@ void zkgpu_table_job_free(zkgpu_table_job* job) {
 }
 
 // ---- prove_with_traces on one device ---------------------------------------------------------------------------------------
-int zkgpu_prove_segment(zkgpu_ctx* h, const zkgpu_table_trace* traces, int mem_kind, const uint64_t* public_values, size_t n_public_values,
-                        const zkgpu_kernel_labels* labels, const zkgpu_stark_config* config, const uint64_t* forced_pow_witnesses,
-                        volatile const int* abort_flag, zkgpu_proof** proofs_out, uint64_t* ctl_challenges_out, uint64_t* trace_caps_out) {
-    ZK_API_BEGIN
-    ZK_REQUIRE(h && traces && config && proofs_out && (public_values || n_public_values == 0), "null argument");
-    Ctx& c = h->c;
-    ZK_CUDA(cudaSetDevice(c.device));
-    const zkstark::Config cfg = config_from(config);
+}  // extern "C"
+
+// the traces of one segment on their way to (or already in) device memory: one values buffer + one "uploaded" event per table
+struct zkgpu_upload {
+    zk::Ctx* ctx = nullptr;
+    std::unique_ptr<zkgpu_batch> tb[ZKGPU_NUM_TABLES];
+    uint8_t in_use[ZKGPU_NUM_TABLES] = {0};
+    std::vector<uint32_t> order;                       // tables in upload / commit order (smallest first)
+    cudaEvent_t uploaded[ZKGPU_NUM_TABLES] = {nullptr};
+    std::vector<cudaEvent_t> events;
+    uint32_t rate_bits = 0, cap_height = 0;
+    cudaEvent_t make_event() { cudaEvent_t e; ZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); events.push_back(e); return e; }
+    ~zkgpu_upload() {
+        // the copy stream is drained before the buffers it writes are freed (errors included)
+        if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->copy_stream); }
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+    }
+};
+
+namespace zk {
+
+// Queue the uploads of all tables on the copy stream (smallest table first, one event per table).  The caps enter the transcript in
+// Table order only after every table is committed, so the commit order is free: the upload of table k+1 runs under the commitment
+// of table k — hashing a trace takes longer than moving it over PCIe, so after the first (smallest) table the copies are hidden.
+// Called one segment AHEAD (zkgpu_segment_upload for segment s+1 before zkgpu_prove_segment_uploaded for segment s) the whole chain
+// runs under the previous segment's proof.
+static void segment_upload(Ctx& c, const zkgpu_table_trace* traces, int mem_kind, const zkstark::Config& cfg, zkgpu_upload& u) {
+    u.ctx = &c; u.rate_bits = cfg.rate_bits; u.cap_height = cfg.cap_height;
+    for (uint32_t t = 0; t < ZKGPU_NUM_TABLES; t++) {
+        u.in_use[t] = traces[t].cols != nullptr;
+        if (!u.in_use[t]) {
+            ZK_REQUIRE(zkstark::table_is_optional(t), "only optional tables may be left out (all_stark.rs:110-117)");
+            continue;
+        }
+        u.tb[t].reset(new zkgpu_batch());
+        Batch& b = u.tb[t]->b;
+        init_batch(c, b, zkstark::table_num_columns(t), traces[t].n, cfg.rate_bits, cfg.cap_height);
+        b.values = DevBuf(&c, b.ncols * b.n * 8);
+        u.order.push_back(t);
+    }
+    std::stable_sort(u.order.begin(), u.order.end(),
+                     [&](uint32_t x, uint32_t y) { return u.tb[x]->b.ncols * u.tb[x]->b.n < u.tb[y]->b.ncols * u.tb[y]->b.n; });
+    // the buffers are stream-ordered allocations of c.stream: the copy stream may touch them only after that point
+    cudaEvent_t allocated = u.make_event();
+    ZK_CUDA(cudaEventRecord(allocated, c.stream));
+    ZK_CUDA(cudaStreamWaitEvent(c.copy_stream, allocated, 0));
+    UploadGate* gate = mem_kind == ZKGPU_MEM_DEVICE ? nullptr : &g_upload_gate[c.device & 15];
+    std::unique_lock<std::mutex> lock;
+    if (gate) {
+        lock = std::unique_lock<std::mutex>(gate->mu);      // held while the chain is queued only
+        if (gate->last) ZK_CUDA(cudaStreamWaitEvent(c.copy_stream, gate->last, 0));
+    }
+    for (uint32_t t : u.order) {
+        Batch& b = u.tb[t]->b;
+        ZK_CUDA(cudaMemcpyAsync(b.values.get(), traces[t].cols, b.ncols * b.n * 8,
+                                mem_kind == ZKGPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.copy_stream));
+        u.uploaded[t] = u.make_event();
+        ZK_CUDA(cudaEventRecord(u.uploaded[t], c.copy_stream));
+    }
+    if (gate) {
+        // the next chain of this device starts after the last copy of this one (the old event is released once it has completed)
+        cudaEvent_t end;
+        ZK_CUDA(cudaEventCreateWithFlags(&end, cudaEventDisableTiming));
+        ZK_CUDA(cudaEventRecord(end, c.copy_stream));
+        if (gate->last) cudaEventDestroy(gate->last);
+        gate->last = end;
+    }
+}
+
+static void segment_prove(Ctx& c, zkgpu_upload& u, const uint64_t* public_values, size_t n_public_values, const zkgpu_kernel_labels* labels,
+                          const zkstark::Config& cfg, const uint64_t* forced_pow_witnesses, volatile const int* abort_flag,
+                          zkgpu_proof** proofs_out, uint64_t* ctl_challenges_out, uint64_t* trace_caps_out) {
+    ZK_REQUIRE(u.ctx == &c, "the upload belongs to another context");
+    ZK_REQUIRE(u.rate_bits == cfg.rate_bits && u.cap_height == cfg.cap_height, "the upload was made for another StarkConfig");
     const zkstark::TableParams prm = params_from(labels);
     const size_t cap_words = (size_t)4 << cfg.cap_height;
     for (uint32_t t = 0; t < ZKGPU_NUM_TABLES; t++) proofs_out[t] = nullptr;
 
-    // 1. trace commitments (prover.rs:92-116).  The caps enter the transcript in Table order only after every table is
-    // committed, so the tables are uploaded and committed smallest first: all uploads are queued on the copy stream up front
-    // (one event per table) and the upload of table k+1 runs under the commitment of table k — hashing a trace takes longer than
-    // moving it over PCIe, so after the first (smallest) table the copies are hidden.
+    // 1. trace commitments (prover.rs:92-116)
     StageLog lg(c);
-    std::unique_ptr<zkgpu_batch> tb[ZKGPU_NUM_TABLES];
     std::vector<uint64_t> caps(ZKGPU_NUM_TABLES * cap_words, 0);
-    uint8_t in_use[ZKGPU_NUM_TABLES];
-    std::vector<uint32_t> order;
-    for (uint32_t t = 0; t < ZKGPU_NUM_TABLES; t++) {
-        in_use[t] = traces[t].cols != nullptr;
-        if (!in_use[t]) continue;
-        tb[t].reset(new zkgpu_batch());
-        Batch& b = tb[t]->b;
-        init_batch(c, b, zkstark::table_num_columns(t), traces[t].n, cfg.rate_bits, cfg.cap_height);
-        b.values = DevBuf(&c, b.ncols * b.n * 8);
-        order.push_back(t);
-    }
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return tb[x]->b.ncols * tb[x]->b.n < tb[y]->b.ncols * tb[y]->b.n; });
-    struct EventGuard {
-        std::vector<cudaEvent_t> ev;
-        ~EventGuard() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
-        cudaEvent_t make() { cudaEvent_t e; ZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); ev.push_back(e); return e; }
-    } events;
-    cudaEvent_t uploaded[ZKGPU_NUM_TABLES] = {nullptr};
-    {
-        // the buffers are stream-ordered allocations of c.stream: the copy stream may touch them only after that point
-        cudaEvent_t allocated = events.make();
-        ZK_CUDA(cudaEventRecord(allocated, c.stream));
-        ZK_CUDA(cudaStreamWaitEvent(c.copy_stream, allocated, 0));
-        UploadGate* gate = mem_kind == ZKGPU_MEM_DEVICE ? nullptr : &g_upload_gate[c.device & 15];
-        if (gate) {
-            std::unique_lock<std::mutex> l(gate->mu);
-            gate->cv.wait(l, [&] { return !gate->busy; });
-            gate->busy = true;
-        }
-        try {
-            for (uint32_t t : order) {
-                Batch& b = tb[t]->b;
-                ZK_CUDA(cudaMemcpyAsync(b.values.get(), traces[t].cols, b.ncols * b.n * 8,
-                                        mem_kind == ZKGPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.copy_stream));
-                uploaded[t] = events.make();
-                ZK_CUDA(cudaEventRecord(uploaded[t], c.copy_stream));
-            }
-            // the gate opens when the last copy of this chain has executed (host callback in copy-stream order)
-            if (gate) ZK_CUDA(cudaLaunchHostFunc(c.copy_stream, upload_gate_release, gate));
-        } catch (...) {
-            if (gate) upload_gate_release(gate);
-            throw;
-        }
-    }
-    struct CopyDrain {   // on any exit (errors included) the copy stream is drained before the buffers it writes are freed
-        Ctx& c; ~CopyDrain() { cudaStreamSynchronize(c.copy_stream); }
-    } drain{c};
-    for (uint32_t t : order) {
+    for (uint32_t t : u.order) {
         if (abort_flag && *abort_flag) throw ZkError(ZKGPU_ERR_ABORTED, "abort signal observed (prover.rs:346-354)");
-        Batch& b = tb[t]->b;
-        ZK_CUDA(cudaStreamWaitEvent(c.stream, uploaded[t], 0));
+        Batch& b = u.tb[t]->b;
+        ZK_CUDA(cudaStreamWaitEvent(c.stream, u.uploaded[t], 0));
         lg.mark("trace upload");
         commit_from_device_values(c, b, true);
         lg.mark(zkstark::table_name(t));
@@ -224,7 +234,7 @@ int zkgpu_prove_segment(zkgpu_ctx* h, const zkgpu_table_trace* traces, int mem_k
     // 2. transcript: caps, public values, CTL challenges (prover.rs:118-144)
     Challenger ch;
     uint64_t bg[4] = {0, 0, 0, 0};
-    segment_transcript(ch, caps.data(), in_use, cap_words, public_values, n_public_values, cfg.num_challenges, bg);
+    segment_transcript(ch, caps.data(), u.in_use, cap_words, public_values, n_public_values, cfg.num_challenges, bg);
     if (ctl_challenges_out) memcpy(ctl_challenges_out, bg, 2 * cfg.num_challenges * 8);
     ch.compact();
     uint64_t st[12];
@@ -233,17 +243,59 @@ int zkgpu_prove_segment(zkgpu_ctx* h, const zkgpu_table_trace* traces, int mem_k
     // 3. per table: CTL data, then the proof, chained through the transcript state in Table order (prover.rs:251-259)
     std::unique_ptr<zkgpu_proof> proofs[ZKGPU_NUM_TABLES];
     for (uint32_t t = 0; t < ZKGPU_NUM_TABLES; t++) {
-        if (!in_use[t]) continue;
+        if (!u.in_use[t]) continue;
         Ctl ctl;
         lg.mark("--");
-        make_ctl_data(c, t, tb[t]->b, bg, cfg.num_challenges, ctl);
+        make_ctl_data(c, t, u.tb[t]->b, bg, cfg.num_challenges, ctl);
         lg.mark("ctl data");
         proofs[t].reset(new zkgpu_proof());
-        prove_table(c, t, prm, cfg, tb[t]->b, ctl, st, forced_pow_witnesses ? &forced_pow_witnesses[t] : nullptr, abort_flag, proofs[t]->p);
-        tb[t].reset();   // release the table's device memory before the next one
+        prove_table(c, t, prm, cfg, u.tb[t]->b, ctl, st, forced_pow_witnesses ? &forced_pow_witnesses[t] : nullptr, abort_flag, proofs[t]->p);
+        u.tb[t].reset();   // release the table's device memory before the next one
         lg.mark(zkstark::table_name(t));
     }
     for (uint32_t t = 0; t < ZKGPU_NUM_TABLES; t++) proofs_out[t] = proofs[t].release();
+}
+
+}  // namespace zk
+
+extern "C" {
+
+int zkgpu_segment_upload(zkgpu_ctx* h, const zkgpu_table_trace* traces, int mem_kind, const zkgpu_stark_config* config, zkgpu_upload** out) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(h && traces && config && out, "null argument");
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    std::unique_ptr<zkgpu_upload> u(new zkgpu_upload());
+    segment_upload(c, traces, mem_kind, config_from(config), *u);
+    *out = u.release();
+    ZK_API_END
+}
+void zkgpu_upload_free(zkgpu_upload* u) { delete u; }
+
+int zkgpu_prove_segment_uploaded(zkgpu_ctx* h, zkgpu_upload* upload, const uint64_t* public_values, size_t n_public_values,
+                                 const zkgpu_kernel_labels* labels, const zkgpu_stark_config* config, const uint64_t* forced_pow_witnesses,
+                                 volatile const int* abort_flag, zkgpu_proof** proofs_out, uint64_t* ctl_challenges_out, uint64_t* trace_caps_out) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(h && upload && config && proofs_out && (public_values || n_public_values == 0), "null argument");
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    segment_prove(c, *upload, public_values, n_public_values, labels, config_from(config), forced_pow_witnesses, abort_flag, proofs_out,
+                  ctl_challenges_out, trace_caps_out);
+    ZK_API_END
+}
+
+int zkgpu_prove_segment(zkgpu_ctx* h, const zkgpu_table_trace* traces, int mem_kind, const uint64_t* public_values, size_t n_public_values,
+                        const zkgpu_kernel_labels* labels, const zkgpu_stark_config* config, const uint64_t* forced_pow_witnesses,
+                        volatile const int* abort_flag, zkgpu_proof** proofs_out, uint64_t* ctl_challenges_out, uint64_t* trace_caps_out) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(h && traces && config && proofs_out && (public_values || n_public_values == 0), "null argument");
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    const zkstark::Config cfg = config_from(config);
+    zkgpu_upload u;
+    segment_upload(c, traces, mem_kind, cfg, u);
+    segment_prove(c, u, public_values, n_public_values, labels, cfg, forced_pow_witnesses, abort_flag, proofs_out, ctl_challenges_out,
+                  trace_caps_out);
     ZK_API_END
 }
 

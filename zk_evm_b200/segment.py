@@ -94,9 +94,7 @@ class _Trace(C.Structure):
     _fields_ = [("cols", u64p), ("n", C.c_size_t)]
 
 
-def prove_with_traces(ctx, traces, public_values, config, labels=None, forced_pow_witnesses=None, abort_flag=None, device_ptrs=None):
-    """prove_with_traces on one device.  traces: list of 9 (ncols, n) uint64 arrays, None for an optional table not in use.
-    device_ptrs: instead of host arrays, list of 9 (device address, n) or None (traces already resident in HBM)."""
+def _trace_array(traces, device_ptrs, config):
     arr = (_Trace * NUM_TABLES)()
     keep = []
     in_use = [False] * NUM_TABLES
@@ -115,15 +113,58 @@ def prove_with_traces(ctx, traces, public_values, config, labels=None, forced_po
             arr[t].cols = _ptr(a)
             arr[t].n = a.shape[1]
             in_use[t] = True
+    return arr, keep, in_use
+
+
+class SegmentUpload:
+    """The traces of one segment queued for (or already in) device memory: `upload_traces` for segment s+1 BEFORE
+    `prove_with_traces(..., upload=...)` for segment s puts the whole H2D chain of s+1 under the proof of s."""
+
+    def __init__(self, ctx, handle, keep, in_use):
+        self.ctx, self._h, self._keep, self.in_use = ctx, handle, keep, in_use
+        ctx._children.add(self)
+
+    def free(self):
+        if self._h:
+            lib().zkgpu_upload_free(self._h)
+            self._h = C.c_void_p()
+            self._keep = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def upload_traces(ctx, traces, config, device_ptrs=None):
+    arr, keep, in_use = _trace_array(traces, device_ptrs, config)
+    h = C.c_void_p()
+    check(lib().zkgpu_segment_upload(ctx._h, arr, 1 if device_ptrs is not None else 0, C.byref(config), C.byref(h)))
+    return SegmentUpload(ctx, h, keep, in_use)
+
+
+def prove_with_traces(ctx, traces, public_values, config, labels=None, forced_pow_witnesses=None, abort_flag=None, device_ptrs=None,
+                      upload=None):
+    """prove_with_traces on one device.  traces: list of 9 (ncols, n) uint64 arrays, None for an optional table not in use.
+    device_ptrs: instead of host arrays, list of 9 (device address, n) or None (traces already resident in HBM).
+    upload: a SegmentUpload made earlier by upload_traces (consumed by this call) instead of traces / device_ptrs."""
     pv = np.ascontiguousarray(public_values, dtype=np.uint64).ravel()
     fp = None if forced_pow_witnesses is None else np.ascontiguousarray(forced_pow_witnesses, dtype=np.uint64)
     outs = (C.c_void_p * NUM_TABLES)()
     bg = np.zeros(4, dtype=np.uint64)
     caps = np.zeros((NUM_TABLES, 1 << config.cap_height, 4), dtype=np.uint64)
-    check(lib().zkgpu_prove_segment(ctx._h, arr, 1 if device_ptrs is not None else 0, _ptr(pv), C.c_size_t(pv.size),
-                                    C.byref(labels) if labels is not None else None, C.byref(config),
-                                    _ptr(fp) if fp is not None else None, C.byref(abort_flag) if abort_flag is not None else None,
-                                    outs, _ptr(bg), _ptr(caps)))
+    tail = (_ptr(pv), C.c_size_t(pv.size), C.byref(labels) if labels is not None else None, C.byref(config),
+            _ptr(fp) if fp is not None else None, C.byref(abort_flag) if abort_flag is not None else None, outs, _ptr(bg), _ptr(caps))
+    if upload is not None:
+        in_use = upload.in_use
+        try:
+            check(lib().zkgpu_prove_segment_uploaded(ctx._h, upload._h, *tail))
+        finally:
+            upload.free()
+    else:
+        arr, keep, in_use = _trace_array(traces, device_ptrs, config)
+        check(lib().zkgpu_prove_segment(ctx._h, arr, 1 if device_ptrs is not None else 0, *tail))
     proofs = []
     for t in range(NUM_TABLES):
         if outs[t]:
