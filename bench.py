@@ -170,7 +170,7 @@ def run_ours(args):
         """`steps` segment proofs back to back on one context.  Host traces: the uploads of segment s+1 are queued before segment s is
         proved (zkgpu_segment_upload / zkgpu_prove_segment_uploaded), so every H2D chain but the first runs under the previous proof."""
         r = None
-        if host and not sharded:
+        if host and not sharded and args.prefetch:
             nxt = zk.upload_traces(cx, host_traces, cfg)
             for k in range(steps):
                 cur, nxt = nxt, (zk.upload_traces(cx, host_traces, cfg) if k + 1 < steps else None)
@@ -400,6 +400,7 @@ def main():
     ap.add_argument("--shrink", type=int, default=0, help="segment workload: make every table 2^shrink times shorter (smoke runs)")
     ap.add_argument("--cpu-shrink", type=int, default=5, help="CPU legs prove tables 2^k times shorter and scale the time")
     ap.add_argument("--streams", type=int, default=2, help="segments in flight per GPU (parallelism=segments)")
+    ap.add_argument("--prefetch", type=int, default=0, help="e2e: queue the uploads of segment s+1 before proving segment s (1) or upload inside each prove call (0)")
     ap.add_argument("--stagger-ms", type=float, default=80.0, help="start offset between the segment streams of a GPU (inside the timed region)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiler runs)")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not bracket kernel families with CUDA events")

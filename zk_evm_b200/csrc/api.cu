@@ -35,10 +35,40 @@ void DevBuf::release() {
     }
 }
 
+// Small transfers between pageable host memory and the device go through a pinned staging buffer of the context: a pageable
+// cudaMemcpyAsync is staged by the driver and ordered against every other copy in flight, so the proof's many small read-backs
+// (caps, openings, PoW results) would queue behind the multi-GB trace uploads of the next segment.
+static void* ctx_staging(Ctx& c, size_t bytes) {
+    if (bytes > c.staging_bytes) {
+        if (c.staging) { cudaStreamSynchronize(c.stream); cudaFreeHost(c.staging); c.staging = nullptr; c.staging_bytes = 0; }
+        size_t want = bytes < ((size_t)1 << 20) ? ((size_t)1 << 20) : bytes;
+        ZK_CUDA(cudaHostAlloc(&c.staging, want, cudaHostAllocDefault));
+        c.staging_bytes = want;
+    }
+    return c.staging;
+}
+static constexpr size_t STAGING_MAX = (size_t)64 << 20;
+
 void Ctx::h2d(void* dst, const void* src, size_t bytes) {
+    if (bytes && bytes <= STAGING_MAX) {
+        // the staging buffer is reused by the next small transfer: wait for earlier users, then copy through it
+        ZK_CUDA(cudaStreamSynchronize(stream));
+        void* st = ctx_staging(*this, bytes);
+        memcpy(st, src, bytes);
+        ZK_CUDA(cudaMemcpyAsync(dst, st, bytes, cudaMemcpyHostToDevice, stream));
+        ZK_CUDA(cudaStreamSynchronize(stream));
+        return;
+    }
     ZK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
 }
 void Ctx::d2h(void* dst, const void* src, size_t bytes) {
+    if (bytes && bytes <= STAGING_MAX) {
+        void* st = ctx_staging(*this, bytes);
+        ZK_CUDA(cudaMemcpyAsync(st, src, bytes, cudaMemcpyDeviceToHost, stream));
+        ZK_CUDA(cudaStreamSynchronize(stream));
+        memcpy(dst, st, bytes);
+        return;
+    }
     ZK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
     ZK_CUDA(cudaStreamSynchronize(stream));
 }
@@ -181,6 +211,7 @@ void zkgpu_ctx_destroy(zkgpu_ctx* h) {
     cudaStreamDestroy(h->c.stream);
     cudaStreamDestroy(h->c.copy_stream);
     if (h->c.pool) cudaMemPoolDestroy(h->c.pool);
+    if (h->c.staging) cudaFreeHost(h->c.staging);
     delete h;
 }
 
