@@ -399,8 +399,11 @@ def main():
     ap.add_argument("--log-n", type=int, default=20, help="cpu_table workload: log2 of the trace length (BASELINE config #2: 20)")
     ap.add_argument("--shrink", type=int, default=0, help="segment workload: make every table 2^shrink times shorter (smoke runs)")
     ap.add_argument("--cpu-shrink", type=int, default=5, help="CPU legs prove tables 2^k times shorter and scale the time")
-    ap.add_argument("--streams", type=int, default=2, help="segments in flight per GPU (parallelism=segments)")
-    ap.add_argument("--prefetch", type=int, default=0, help="e2e: queue the uploads of segment s+1 before proving segment s (1) or upload inside each prove call (0)")
+    ap.add_argument("--streams", type=int, default=3, help="segments in flight per GPU (parallelism=segments); measured 1: 3.34, 2: 3.78, 3: 3.95, 4: 3.86 proofs/s")
+    ap.add_argument("--prefetch", type=int, default=0,
+                    help="e2e: queue the uploads of segment s+1 before proving segment s (1) or upload inside each prove call (0); measured "
+                         "(profiles/r1w): upload-ahead is slower on this box (3 streams 2.94 vs 3.87 proofs/s), the per-call upload chain "
+                         "already hides under the other segments' kernels")
     ap.add_argument("--stagger-ms", type=float, default=80.0, help="start offset between the segment streams of a GPU (inside the timed region)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiler runs)")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not bracket kernel families with CUDA events")
