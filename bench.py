@@ -4,8 +4,9 @@
   python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the zkgpu C ABI)
   python bench.py --impl reference --gpus N ...            # reference arm: the CPU restatement (oracle) on all host cores
 
-Metric (BASELINE.json): segment proofs/sec.  A step = ONE segment proof = prove_with_traces over all nine STARK tables of a
-synthetic segment with the table heights of the `witness_b19807080` CI ranges: per table the trace
+Metric (BASELINE.json): segment proofs/sec.  A step = one segment proof PER SEGMENT STREAM (--streams S, default 3: S segments in
+flight per GPU, each on its own context + CUDA stream + host thread, proving its segments back to back); a segment proof =
+prove_with_traces over all nine STARK tables of a synthetic segment with the table heights of the `witness_b19807080` CI ranges: per table the trace
 commitment, CTL / lookup auxiliary columns + commitment, fused quotient evaluation + commitment, openings, FRI commit phase,
 proof of work and query answers, all tables chained through one Fiat-Shamir transcript.
   value : proofs/s with the traces already resident in HBM, device time (CUDA events on the library's stream), max over ranks

@@ -48,12 +48,12 @@ struct QuotKernelArgs {
 
 // 128-thread blocks per SM the kernel is compiled for (i.e. its register budget, 65536 / (128 * blocks)).  Measured (profiles/r1h,
 // r1k): the Keccak kernel is a load stream (2431 columns per point) and wants ~40 loads in flight per thread at 128 registers; the
-// Arithmetic and Cpu evaluators are instruction-fetch bound and gain from more resident warps: measured family time 38.3 ms at 3 blocks
-// (168 registers), 36.2 ms at 5 (96 registers, ~200 bytes of spills), 37.3 ms at 8 (64 registers) — profiles/r1q_bench_minb*.json;
-// letting ptxas take 255 registers (min blocks = 1) made Cpu 25 % and Arithmetic 34 % slower.  The others are small and run best at
-// high occupancy.
+// Cpu evaluator is instruction-fetch bound and gains from more resident warps: 12.8 ms at 3 blocks (168 registers), 8.0 ms at 5
+// (96 registers, ~200 bytes of spills); the Arithmetic evaluator keeps long-lived limb arrays and does not: 6.9 ms at 3 blocks, 8.6 ms at
+// 5 (2.2 KB of stack per thread) — profiles/r1p, r1x ncu rows; letting ptxas take 255 registers (min blocks = 1) made Cpu 25 % and
+// Arithmetic 34 % slower.  The others are small and run best at high occupancy.
 constexpr int quotient_min_blocks(uint32_t table) {
-    return table == T_KECCAK ? 4 : (table == T_ARITHMETIC || table == T_CPU) ? 5 : table == T_MEMORY ? 3 : 8;
+    return table == T_KECCAK ? 4 : table == T_CPU ? 5 : table == T_ARITHMETIC ? 3 : table == T_MEMORY ? 3 : 8;
 }
 // 128-thread blocks (Memory: 256).  Measured alternative (profiles/r1m): ONE 384-thread block per SM for the Arithmetic / Cpu evaluators
 // (12 warps in lock-step sharing the instruction stream) is no faster in isolation (Cpu 14.6 vs 14.7 ms, Arithmetic 7.7 vs 6.7 ms), and a
