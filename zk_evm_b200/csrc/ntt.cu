@@ -3,13 +3,15 @@
 // Replaces plonky2_field 1.0.0 fft.rs (`PolynomialValues::ifft`, `PolynomialCoeffs::{lde, coset_fft, coset_ifft}`),
 // reached from /root/reference/evm_arithmetization/src/prover.rs:100-107 through PolynomialBatch::from_values.
 //
-// One kernel family: decimation-in-frequency, natural order in -> bit-reversed order out, mixed radix.
-// A transform of size 2^L is cut into passes over index digits (most significant first).  A pass stages a tile of
-// 2^r (digit) x 2^t (contiguous 8-byte elements, coalesced) in shared memory, runs the r radix-2 stages there with
-// pure w_{2^r} twiddles, multiplies by the inter-pass twiddle w_M^(j'*kd) (a cached table, coalesced) and writes
-// the tile back in place.  Natural-order results (coefficients) are produced by a tiled bit-reversal permutation
-// that also applies the 1/n (and coset) scaling.  The LDE with blow-up 2 is two size-n coset transforms
-// (shifts g and g*w_2n) read from the same coefficient column: lde_br[h*n + p] = DIF_n(c_j (g w_2n^h)^j)[p].
+// One kernel family: decimation-in-frequency, natural order in -> bit-reversed order out.  A transform of size 2^L is cut into
+// passes over index digits (most significant first): strided passes of 8 bits (tile = 2^8 digit values x 16 contiguous 8-byte
+// elements) until <= 12 bits remain for the final contiguous pass.  Inside a pass the digit is processed in rounds of four radix-2
+// stages on 16 registers whose twiddles are powers of two (w_16 = 2^12 in Goldilocks: shifts, no multiplier), with one general
+// twiddle per element between rounds and the inter-pass twiddle w_M^(j'*kd) (a cached table) on the way out — all of it in
+// ntt_tile.cuh, which is host+device so that tests/test_ntt_tile_host.py runs the same tile code on the CPU.  Natural-order results
+// (coefficients) are produced by a tiled bit-reversal permutation that also applies the 1/n (and coset) scaling.  The LDE with
+// blow-up 2 is two size-n coset transforms (shifts g and g*w_2n) read from the same coefficient column:
+// lde_br[h*n + p] = DIF_n(c_j (g w_2n^h)^j)[p].
 #include "internal.h"
 #include "ntt.h"
 #include "ntt_tile.cuh"
