@@ -306,7 +306,7 @@ def run_ours(args):
         cpu = None if args.no_cpu_baseline else cpu_baseline(args, log_ns)
         line = {"metric": METRIC, "value": segs / (ms / 1e3), "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
-                "dtype": "u64 (Goldilocks, exact)", "data": "synthetic",
+                "dtype": "u64", "data": "synthetic",
                 "config": {"workload": ("segment proof (AllStark, 9 tables, heights of witness_b19807080's CI ranges): " if args.workload == "segment"
                                         else "single-table prove (BASELINE config #2): ") + describe(log_ns) + "; standard_fast_config",
                            "parallelism": ("tables of one segment sharded over %d GPUs (owner %s)" % (world, owner)) if sharded
@@ -380,7 +380,7 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64 (Goldilocks, exact)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": ("segment proof (AllStark, 9 tables): " if args.workload == "segment" else "single-table prove: ") + describe(log_ns)
                                + "; standard_fast_config; CPU restatement (oracle/, C++17 + OpenMP) of the plonky2/starky prover — the Rust "
                                  "reference cannot be built here (no cargo/rustc, crates not vendored)"},
