@@ -1,0 +1,89 @@
+"""CPU: the device instruction streams of the product's hot arithmetic — as nvcc emits them, inline-PTX carry chains included —
+executed by the PTX interpreter in tools/ptx_emu.py (one thread, integer subset) and compared with exact big-integer arithmetic and
+the oracle: Goldilocks field forms (gl.cuh), the lazy forms + the fast Poseidon permutation (poseidon_fast.cuh), the compile-time
+power-of-two multiplications and the radix-16 butterfly network of the NTT (ntt_tile.cuh).  Needs nvcc (no GPU); what stays for
+the GPU tests is ptxas' translation of this PTX."""
+import os
+import shutil
+import subprocess
+import sys
+import numpy as np
+import pytest
+from tests import oracle_lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+CSRC = os.path.join(ROOT, "zk_evm_b200", "csrc")
+SRC = os.path.join(HERE, "native", "ptx_kernels.cu")
+PTX = os.path.join(HERE, "native", "ptx_kernels.ptx")
+P = oracle_lib.P
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+pytestmark = pytest.mark.skipif(not os.path.exists(NVCC), reason="nvcc not available")
+IN, OUT = 0x10000000, 0x20000000
+EDGE = [0, 1, 2, 0xFFFFFFFF, 0x100000000, 0xFFFFFFFF00000000, P - 1, P - 2, 2 ** 63, 0x8000000080000000 % P]
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from ptx_emu import PtxEmu
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("gl.cuh", "poseidon.cuh", "poseidon_fast.cuh", "ntt_tile.cuh")]
+    if not os.path.exists(PTX) or any(os.path.getmtime(d) > os.path.getmtime(PTX) for d in deps):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", CSRC, "-ptx", "-o", PTX, SRC])
+    return PtxEmu(open(PTX).read())
+
+
+def run(emu, kernel, words, nout, extra=()):
+    mem = {IN + 8 * i: int(w) for i, w in enumerate(words)}
+    emu.run(kernel, [IN, OUT] + list(extra), mem)
+    return [mem[OUT + 8 * i] for i in range(nout)]
+
+
+def test_field_forms(emu):
+    rng = np.random.default_rng(5)
+    vals = EDGE + [int(v) for v in oracle_lib.rand_field(rng, (6,))]
+    for a in vals:
+        for b in vals:
+            add, sub, mul, neg, red = run(emu, "k_field", [a, b], 5)
+            assert (add, sub, mul, neg) == ((a + b) % P, (a - b) % P, a * b % P, (-a) % P), (a, b)
+            assert red == (a + (b << 64)) % P, (a, b)
+
+
+def test_lazy_forms_accept_any_u64(emu):
+    rng = np.random.default_rng(6)
+    vals = EDGE + [P, P + 1, 2 ** 64 - 1, 0xFFFFFFFEFFFFFFFF] + [int(v) for v in rng.integers(0, 2 ** 64, size=6, dtype=np.uint64)]
+    for a in vals:
+        for b in vals[:8]:
+            mul, sqr, sbox, addc = run(emu, "k_lazy", [a, b], 4)
+            assert (mul, sqr, sbox, addc) == (a * b % P, a * a % P, pow(a, 7, P), (a + b) % P), (a, b)
+
+
+def test_power_of_two_multiplications(emu):
+    shifts = [1, 12, 24, 31, 32, 36, 48, 60, 63, 64, 72, 84, 95]
+    rng = np.random.default_rng(7)
+    for a in EDGE + [int(v) for v in oracle_lib.rand_field(rng, (10,))]:
+        got = run(emu, "k_pow2", [a], len(shifts))
+        assert got == [a * pow(2, s, P) % P for s in shifts], a
+
+
+def test_fast_permutation_ptx(emu):
+    orc = oracle_lib.load()
+    rng = np.random.default_rng(8)
+    x = oracle_lib.rand_field(rng, (4, 12))
+    x[1] = 0
+    x[2] = P - 1
+    want = orc.poseidon(x)
+    for i in range(4):
+        assert run(emu, "k_perm", x[i], 12) == [int(v) for v in want[i]]
+
+
+def test_radix16_butterfly_network(emu):
+    """ntt_dft_regs<4>: natural order in, bit-reversed order out, root w_16 = 2^12 (inverse: 2^-12)"""
+    rng = np.random.default_rng(9)
+    x = [int(v) for v in oracle_lib.rand_field(rng, (16,))]
+    rev = [int("{:04b}".format(i)[::-1], 2) for i in range(16)]
+    for inverse in (0, 1):
+        w = pow(2, 12, P) if not inverse else pow(pow(2, 12, P), P - 2, P)
+        got = run(emu, "k_dft16", x, 16, extra=[inverse])
+        want = [sum(x[j] * pow(w, j * k, P) for j in range(16)) % P for k in range(16)]
+        assert [got[rev[k]] for k in range(16)] == want

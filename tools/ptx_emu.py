@@ -1,0 +1,205 @@
+#!/usr/bin/env python3
+"""A small PTX interpreter for the integer subset our kernels use (development tool: there is no GPU in the build container).
+
+Runs ONE thread of ONE kernel from a `nvcc -ptx` file on the CPU: add/sub with carry flags, mul/mad.wide, shifts, funnel shifts, logic,
+setp/selp, predicated branches, ld/st.global, ld.const, ld.param.  Enough to execute the Poseidon permutation, the field arithmetic and
+the NTT butterflies exactly as nvcc emitted them (inline PTX included), so that device code can be compared with the oracle before any
+GPU time is spent.  What it cannot see is ptxas (PTX -> SASS); the GPU parity tests remain the judge of that.
+
+usage (library):  emu = PtxEmu(open("k.ptx").read()); emu.run("kernel_name_substring", params=[...], mem={addr: u64}, tid=0, ctaid=0, ntid=128)
+"""
+import re
+
+M32, M64 = (1 << 32) - 1, (1 << 64) - 1
+
+
+class PtxEmu:
+    def __init__(self, text):
+        self.consts = {}
+        for m in re.finditer(r"\.const\s+\.align\s+\d+\s+\.b8\s+(\S+)\[(\d+)\]\s*=\s*\{([^}]*)\}", text):
+            data = bytes(int(x) for x in m.group(3).split(","))
+            self.consts[m.group(1)] = data + bytes(int(m.group(2)) - len(data))       # trailing zeros are not written out
+        # constant arrays get fake base addresses so that pointer arithmetic on them works
+        self.const_base = {n: (1 << 56) + (i << 32) for i, n in enumerate(self.consts)}
+        self.kernels = {}
+        for m in re.finditer(r"\.entry\s+(\S+)\(\s*(.*?)\)\s*(?:\.\w+[^\{]*)?\{(.*?)\n\}", text, re.S):
+            name, params, body = m.group(1), m.group(2), m.group(3)
+            pnames = [p.strip().split()[-1] for p in params.split(",") if p.strip()]
+            self.kernels[name] = (pnames, self._parse(body))
+
+    @staticmethod
+    def _parse(body):
+        body = re.sub(r"//[^\n]*", "", body)
+        ins, labels = [], {}
+        for raw in body.replace("\n", " ").split(";"):
+            line = raw.strip()
+            while True:
+                m = re.match(r"(\$\w+):\s*(.*)", line)
+                if not m:
+                    break
+                labels[m.group(1)] = len(ins)
+                line = m.group(2).strip()
+            if not line or line.startswith(".") or line in ("{", "}"):
+                # declarations (.reg ...) carry no semantics here
+                m = re.match(r"[{}\s]*(.*)", line)
+                line = m.group(1) if m else ""
+                if not line or line.startswith("."):
+                    continue
+            line = line.strip("{} \t")
+            pred = None
+            m = re.match(r"@(!?)(%p\d+)\s+(.*)", line)
+            if m:
+                pred, line = (m.group(2), m.group(1) == "!"), m.group(3)
+            parts = line.split(None, 1)
+            op = parts[0]
+            args = []
+            if len(parts) > 1:
+                depth, cur = 0, ""
+                for ch in parts[1]:
+                    if ch == "{":
+                        depth += 1
+                    if ch == "}":
+                        depth -= 1
+                    if ch == "," and depth == 0:
+                        args.append(cur.strip()); cur = ""
+                    else:
+                        cur += ch
+                if cur.strip():
+                    args.append(cur.strip())
+            ins.append((pred, op, args))
+        return ins, labels
+
+    # ---- execution ---------------------------------------------------------------------------------------------
+    def run(self, kernel, params, mem, tid=0, ctaid=0, ntid=128, max_steps=50_000_000):
+        name = [k for k in self.kernels if kernel in k]
+        assert len(name) == 1, name
+        pnames, (ins, labels) = self.kernels[name[0]]
+        pval = dict(zip(pnames, params))
+        R, cc = {}, 0
+
+        def val(a, bits=64):
+            a = a.strip()
+            if a.startswith("%"):
+                if a == "%tid.x":
+                    return tid
+                if a == "%ctaid.x":
+                    return ctaid
+                if a == "%ntid.x":
+                    return ntid
+                return R[a]
+            if a in self.const_base:
+                return self.const_base[a]
+            if a.startswith("0x") or a.startswith("-0x"):
+                return int(a, 16) & ((1 << bits) - 1)
+            if a.endswith("U"):
+                a = a[:-1]
+            return int(a) & ((1 << bits) - 1)
+
+        def addr(a):
+            m = re.match(r"\[(.+?)(?:\+(-?\d+))?\]", a)
+            base, off = m.group(1), int(m.group(2) or 0)
+            return base, off
+
+        pc, steps = 0, 0
+        while pc < len(ins):
+            steps += 1
+            assert steps < max_steps, "step limit"
+            pred, op, a = ins[pc]
+            pc += 1
+            if pred is not None and bool(R[pred[0]]) == pred[1]:
+                continue
+            o = op.split(".")
+            base = o[0]
+            if op == "ret":
+                break
+            if base == "bra":
+                pc = labels[a[0]]
+                continue
+            bits = 64 if o[-1] in ("u64", "s64", "b64") else 32
+            mask = (1 << bits) - 1
+            if base == "mov":
+                if a[0].startswith("{"):      # mov.b64 {lo, hi}, x
+                    lo, hi = [x.strip() for x in a[0].strip("{}").split(",")]
+                    v = val(a[1]); R[lo], R[hi] = v & M32, v >> 32
+                elif a[1].startswith("{"):    # mov.b64 x, {lo, hi}
+                    lo, hi = [x.strip() for x in a[1].strip("{}").split(",")]
+                    R[a[0]] = (val(lo) & M32) | ((val(hi) & M32) << 32)
+                elif o[-1] == "pred":
+                    R[a[0]] = val(a[1])
+                else:
+                    R[a[0]] = val(a[1], bits) & mask
+            elif base == "ld":
+                b, off = addr(a[1])
+                if o[1] == "param":
+                    R[a[0]] = pval[b]
+                elif o[1] == "const":
+                    if b in self.consts:
+                        data = self.consts[b]
+                    else:                     # register-relative: find the array the address falls into
+                        ad = val(b) + off
+                        nm = [n for n, ba in self.const_base.items() if ba <= ad < ba + len(self.consts[n])]
+                        assert len(nm) == 1, hex(ad)
+                        data, off = self.consts[nm[0]], ad - self.const_base[nm[0]]
+                    assert 0 <= off and off + bits // 8 <= len(data)
+                    R[a[0]] = int.from_bytes(data[off:off + bits // 8], "little")
+                else:
+                    R[a[0]] = mem[(val(b) + off) & M64]
+            elif base == "st":
+                b, off = addr(a[0])
+                mem[(val(b) + off) & M64] = val(a[1]) & mask
+            elif base == "cvta":
+                R[a[0]] = val(a[1])
+            elif base == "cvt":
+                R[a[0]] = val(a[1]) & (M32 if o[-1] == "u32" else M64) if o[1] != "s64" else val(a[1])
+            elif base in ("add", "sub", "addc", "subc"):
+                x, y = val(a[1], bits), val(a[2], bits)
+                cin = cc if base in ("addc", "subc") else 0
+                if base in ("add", "addc"):
+                    r = x + y + cin
+                    cout = r >> bits
+                else:
+                    r = x - y - cin
+                    cout = 1 if r < 0 else 0
+                if "cc" in o:
+                    cc = cout
+                R[a[0]] = r & mask
+            elif base == "neg":
+                R[a[0]] = (-val(a[1], bits)) & mask
+            elif base == "mul":
+                if o[1] == "wide":
+                    R[a[0]] = (val(a[1], 32) * val(a[2], 32)) & M64
+                elif o[1] == "lo":
+                    R[a[0]] = (val(a[1], bits) * val(a[2], bits)) & mask
+                else:
+                    raise NotImplementedError(op)
+            elif base == "mad":
+                assert o[1] == "wide", op
+                R[a[0]] = (val(a[1], 32) * val(a[2], 32) + val(a[3], 64)) & M64
+            elif base == "shl":
+                s = val(a[2], 32)
+                R[a[0]] = (val(a[1], bits) << s) & mask if s < bits else 0
+            elif base == "shr":
+                s = val(a[2], 32)
+                assert o[-1] in ("u32", "u64", "b32", "b64"), op
+                R[a[0]] = (val(a[1], bits) >> s) if s < bits else 0
+            elif base == "shf":           # shf.{l,r}.wrap.b32 d, lo, hi, c
+                lo, hi, c = val(a[1], 32), val(a[2], 32), val(a[3], 32) & 31
+                v = (hi << 32) | lo
+                R[a[0]] = ((v << c) >> 32) & M32 if o[1] == "l" else (v >> c) & M32
+            elif base in ("and", "or", "xor"):
+                x, y = val(a[1], bits), val(a[2], bits)
+                R[a[0]] = (x & y) if base == "and" else (x | y) if base == "or" else (x ^ y)
+            elif base == "not":
+                R[a[0]] = 0 if val(a[1]) else 1
+            elif base == "setp":
+                x, y = val(a[1], bits), val(a[2], bits)
+                if o[-1].startswith("s"):
+                    sx = x - (1 << bits) if x >> (bits - 1) else x
+                    sy = y - (1 << bits) if y >> (bits - 1) else y
+                    x, y = sx, sy
+                R[a[0]] = int({"gt": x > y, "ge": x >= y, "lt": x < y, "le": x <= y, "eq": x == y, "ne": x != y}[o[1]])
+            elif base == "selp":
+                R[a[0]] = val(a[1], bits) if R[a[3]] else val(a[2], bits)
+            else:
+                raise NotImplementedError(op)
+        return mem

@@ -15,25 +15,54 @@
 
 namespace zk {
 
+// The file is device code; a plain C++ compiler sees the same functions with portable bodies where the device ones are inline PTX
+// (tests/native/poseidon_fast_host.cpp runs the permutation's algorithm — lazy reductions, limb-domain MDS, round loop — on the CPU).
 #if defined(__CUDACC__)
+#define PF_FN __device__ __forceinline__
+#else
+#define PF_FN inline
+#endif
 
 struct U64 { uint32_t lo, hi; };
 
-__device__ __forceinline__ uint64_t pf_pack(uint32_t lo, uint32_t hi) {
+#if defined(__CUDA_ARCH__)
+PF_FN uint64_t pf_pack(uint32_t lo, uint32_t hi) {
     uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r;
 }
-__device__ __forceinline__ void pf_unpack(uint64_t x, uint32_t& lo, uint32_t& hi) {
+PF_FN void pf_unpack(uint64_t x, uint32_t& lo, uint32_t& hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x));
 }
-__device__ __forceinline__ uint64_t pf_mulwide(uint32_t a, uint32_t b) {
+PF_FN uint64_t pf_mulwide(uint32_t a, uint32_t b) {
     uint64_t r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r;
 }
-__device__ __forceinline__ uint64_t pf_madwide(uint32_t a, uint32_t b, uint64_t c) {
+PF_FN uint64_t pf_madwide(uint32_t a, uint32_t b, uint64_t c) {
     uint64_t r; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r;
 }
+#else
+PF_FN uint64_t pf_pack(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+PF_FN void pf_unpack(uint64_t x, uint32_t& lo, uint32_t& hi) { lo = (uint32_t)x; hi = (uint32_t)(x >> 32); }
+PF_FN uint64_t pf_mulwide(uint32_t a, uint32_t b) { return (uint64_t)a * b; }
+PF_FN uint64_t pf_madwide(uint32_t a, uint32_t b, uint64_t c) { return (uint64_t)a * b + c; }
+PF_FN uint32_t pf_funnelshift_r(uint32_t lo, uint32_t hi, unsigned s) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> s); }
+PF_FN uint32_t pf_funnelshift_l(uint32_t lo, uint32_t hi, unsigned s) { return (uint32_t)(((((uint64_t)hi << 32) | lo) << s) >> 32); }
+#endif
+#if defined(__CUDA_ARCH__)
+#define pf_funnelshift_r __funnelshift_r
+#define pf_funnelshift_l __funnelshift_l
+#endif
 
 // w0 + 2^32 w1 + 2^64 w2 + 2^96 w3  ->  some u64 congruent to it mod p
-__device__ __forceinline__ uint64_t pf_reduce128(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+PF_FN uint64_t pf_reduce128(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+#if !defined(__CUDA_ARCH__)
+    // the same steps with 64-bit words: t = (w1:w0) - w3 (wrap: -EPS), u = w2 EPS, r = t + u (wrap: +EPS)
+    const uint64_t lo = pf_pack(w0, w1);
+    uint64_t t = lo - w3;
+    if (lo < w3) t -= GL_EPS;
+    const uint64_t u = ((uint64_t)w2 << 32) - w2;
+    uint64_t r = t + u;
+    if (r < t) r += GL_EPS;
+    return r;
+#else
     uint32_t t0, t1, m, u0, u1;
     // t = (w1:w0) - w3 ; a borrow wrapped by 2^64 == EPS, so take EPS off again (cannot borrow twice)
     asm("sub.cc.u32 %0, %3, %5;\n\t"
@@ -54,9 +83,10 @@ __device__ __forceinline__ uint64_t pf_reduce128(uint32_t w0, uint32_t w1, uint3
     asm("add.cc.u32 %0, %0, %2;\n\t"
         "addc.u32 %1, %1, 0;\n\t" : "+r"(t0), "+r"(t1) : "r"(m));
     return pf_pack(t0, t1);
+#endif
 }
 
-__device__ __forceinline__ uint64_t pf_mul(uint64_t a, uint64_t b) {
+PF_FN uint64_t pf_mul(uint64_t a, uint64_t b) {
     uint32_t a0, a1, b0, b1;
     pf_unpack(a, a0, a1); pf_unpack(b, b0, b1);
     uint64_t p00 = pf_mulwide(a0, b0);
@@ -70,7 +100,7 @@ __device__ __forceinline__ uint64_t pf_mul(uint64_t a, uint64_t b) {
     return pf_reduce128(w0, w1, w2, w3);
 }
 
-__device__ __forceinline__ uint64_t pf_sqr(uint64_t a) {
+PF_FN uint64_t pf_sqr(uint64_t a) {
     uint32_t a0, a1;
     pf_unpack(a, a0, a1);
     uint64_t p00 = pf_mulwide(a0, a0);
@@ -79,20 +109,29 @@ __device__ __forceinline__ uint64_t pf_sqr(uint64_t a) {
     // a^2 = p00 + 2^33 p01 + 2^64 p11
     uint32_t w0, w1, w2, w3, q0, q1;
     pf_unpack(p00, w0, w1); pf_unpack(p11, w2, w3); pf_unpack(p01, q0, q1);
-    uint32_t s0 = q0 << 1, s1 = __funnelshift_l(q0, q1, 1), s2 = q1 >> 31;
+    uint32_t s0 = q0 << 1, s1 = pf_funnelshift_l(q0, q1, 1), s2 = q1 >> 31;
+#if defined(__CUDA_ARCH__)
     asm("add.cc.u32 %0, %0, %3;\n\t"
         "addc.cc.u32 %1, %1, %4;\n\t"
         "addc.u32 %2, %2, %5;\n\t" : "+r"(w1), "+r"(w2), "+r"(w3) : "r"(s0), "r"(s1), "r"(s2));
+#else
+    { uint64_t c = (uint64_t)w1 + s0; w1 = (uint32_t)c; c = (uint64_t)w2 + s1 + (c >> 32); w2 = (uint32_t)c; w3 = w3 + s2 + (uint32_t)(c >> 32); }
+#endif
     return pf_reduce128(w0, w1, w2, w3);
 }
 
-__device__ __forceinline__ uint64_t pf_sbox7(uint64_t x) {
+PF_FN uint64_t pf_sbox7(uint64_t x) {
     uint64_t x2 = pf_sqr(x), x4 = pf_sqr(x2), x3 = pf_mul(x, x2);
     return pf_mul(x3, x4);
 }
 
 // x + c for canonical c (x any u64): result any u64 congruent
-__device__ __forceinline__ uint64_t pf_add_canon(uint64_t x, uint64_t c) {
+PF_FN uint64_t pf_add_canon(uint64_t x, uint64_t c) {
+#if !defined(__CUDA_ARCH__)
+    uint64_t r = x + c;
+    if (r < x) r += GL_EPS;
+    return r;
+#else
     uint32_t x0, x1, c0, c1, m;
     pf_unpack(x, x0, x1); pf_unpack(c, c0, c1);
     asm("add.cc.u32 %0, %0, %3;\n\t"
@@ -102,13 +141,15 @@ __device__ __forceinline__ uint64_t pf_add_canon(uint64_t x, uint64_t c) {
     asm("add.cc.u32 %0, %0, %2;\n\t"
         "addc.u32 %1, %1, 0;\n\t" : "+r"(x0), "+r"(x1) : "r"(m));
     return pf_pack(x0, x1);
+#endif
 }
 
-__device__ __forceinline__ uint64_t pf_canon(uint64_t x) { return x >= GL_P ? x - GL_P : x; }
+PF_FN uint64_t pf_canon(uint64_t x) { return x >= GL_P ? x - GL_P : x; }
 
-// MDS layer + constants of the following round (rc == nullptr: none).  In/out non-canonical.
+#if defined(__CUDACC__)
+// MDS layer + constants of the following round (rc == nullptr: none).  In/out non-canonical.  (dense form, micro-benchmark only)
 template <bool ADD_RC>
-__device__ __forceinline__ void pf_mds(uint64_t s[12], const uint64_t* __restrict__ rc) {
+PF_FN void pf_mds(uint64_t s[12], const uint64_t* __restrict__ rc) {
     constexpr uint32_t C[12] = ZK_POSEIDON_MDS_CIRC_INIT;
     uint32_t lo[12], hi[12];
 #pragma unroll
@@ -136,6 +177,7 @@ __device__ __forceinline__ void pf_mds(uint64_t s[12], const uint64_t* __restric
         s[r] = pf_pack(t0, t1);
     }
 }
+#endif
 
 // ---- MDS layer in the frequency domain, on three 22/22/20-bit limbs with wrap-around 32-bit arithmetic ----------------
 // The circulant part of the MDS matrix is a cyclic convolution of length 12.  Splitting the index as j = b + 3a and taking
@@ -155,19 +197,27 @@ constexpr PfRc3 pf_make_rc3() {
     }
     return r;
 }
+#if defined(__CUDACC__)
 static __device__ __constant__ PfRc3 POSEIDON_RC3_DEV = pf_make_rc3();
+#endif
+#if defined(__CUDA_ARCH__)
+#define PF_RC3 POSEIDON_RC3_DEV.v
+#else
+static const PfRc3 POSEIDON_RC3_HOST = pf_make_rc3();
+#define PF_RC3 POSEIDON_RC3_HOST.v
+#endif
 
-__device__ __forceinline__ void pf_mds_fft_limb(const uint32_t s[12], uint32_t o[12]) { poseidon_mds_freq<uint32_t>(s, o); }
+PF_FN void pf_mds_fft_limb(const uint32_t s[12], uint32_t o[12]) { poseidon_mds_freq<uint32_t>(s, o); }
 
 // rc3: the next round's constants pre-split into the same limbs ([12][3]), or nullptr
 template <bool ADD_RC>
-__device__ __forceinline__ void pf_mds_fft(uint64_t s[12], const uint32_t* __restrict__ rc3) {
+PF_FN void pf_mds_fft(uint64_t s[12], const uint32_t* __restrict__ rc3) {
     uint32_t a0[12], a1[12], a2[12], o0[12], o1[12], o2[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         uint32_t lo, hi; pf_unpack(s[i], lo, hi);
         a0[i] = lo & 0x3FFFFFu;
-        a1[i] = __funnelshift_r(lo, hi, 22) & 0x3FFFFFu;
+        a1[i] = pf_funnelshift_r(lo, hi, 22) & 0x3FFFFFu;
         a2[i] = hi >> 12;
     }
     pf_mds_fft_limb(a0, o0); pf_mds_fft_limb(a1, o1); pf_mds_fft_limb(a2, o2);
@@ -181,6 +231,17 @@ __device__ __forceinline__ void pf_mds_fft(uint64_t s[12], const uint32_t* __res
         uint32_t t0, t1, m;
         // t = x0 + 2^22 x1 - h   (>= 0 because x1 >= 2^10 h)
         uint32_t s0 = x1 << 22, s1 = x1 >> 10;
+#if !defined(__CUDA_ARCH__)
+        {   // the same steps with 64-bit words
+            (void)t0; (void)t1; (void)m;
+            uint64_t t = (uint64_t)x0 + pf_pack(s0, s1) - h;
+            const uint64_t add = (uint64_t)(l << 12) << 32;
+            uint64_t r = t + add;
+            if (r < t) r += GL_EPS;
+            s[i] = r;
+            continue;
+        }
+#else
         asm("add.cc.u32 %0, %2, %3;\n\t"
             "addc.u32 %1, %4, 0;\n\t" : "=r"(t0), "=r"(t1) : "r"(x0), "r"(s0), "r"(s1));
         asm("sub.cc.u32 %0, %0, %2;\n\t"
@@ -192,6 +253,7 @@ __device__ __forceinline__ void pf_mds_fft(uint64_t s[12], const uint32_t* __res
         asm("add.cc.u32 %0, %0, %2;\n\t"
             "addc.u32 %1, %1, 0;\n\t" : "+r"(t0), "+r"(t1) : "r"(m));
         s[i] = pf_pack(t0, t1);
+#endif
     }
 }
 
@@ -201,9 +263,9 @@ __device__ __forceinline__ void pf_mds_fft(uint64_t s[12], const uint32_t* __res
 // 32 KB L1.5 instruction cache, and ncu showed warps stalled on instruction fetch ("no_instructions") for most cycles.
 // So there is ONE round loop: the full S-box layer is 3 iterations of "4 S-boxes + rotate the state by 4 lanes" (static
 // register indices, 24 moves per iteration), the MDS layer (with the next round's constants folded in) appears once.
-__device__ __forceinline__ void pf_permute(uint64_t s[12]) {
+PF_FN void pf_permute(uint64_t s[12]) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = pf_add_canon(s[i], POSEIDON_RC_DEV[i]);
+    for (int i = 0; i < 12; i++) s[i] = pf_add_canon(s[i], poseidon_rc(i));
 #pragma unroll 1
     for (int r = 0; r < 30; r++) {
         if (r < 4 || r >= 26) {
@@ -217,13 +279,14 @@ __device__ __forceinline__ void pf_permute(uint64_t s[12]) {
         } else {
             s[0] = pf_sbox7(s[0]);
         }
-        pf_mds_fft<true>(s, POSEIDON_RC3_DEV.v + 36 * (r + 1));
+        pf_mds_fft<true>(s, PF_RC3 + 36 * (r + 1));
     }
 }
 
+#if defined(__CUDACC__)
 // the fully unrolled / dense-MDS forms, kept for the micro-benchmark (tools/pbench.cu)
 template <int MDS>
-__device__ __forceinline__ void pf_permute_unrolled(uint64_t s[12]) {
+PF_FN void pf_permute_unrolled(uint64_t s[12]) {
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = pf_add_canon(s[i], POSEIDON_RC_DEV[i]);
 #pragma unroll 1
@@ -248,6 +311,6 @@ __device__ __forceinline__ void pf_permute_unrolled(uint64_t s[12]) {
     if (MDS == 0) pf_mds<false>(s, nullptr); else pf_mds_fft<false>(s, nullptr);
 }
 
-#endif  // __CUDACC__
+#endif  // __CUDACC__ (micro-benchmark forms)
 
 }  // namespace zk
