@@ -5,6 +5,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "poseidon_fast.cuh"
+#include "pf_limb_variant.cuh"
 using namespace zk;
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
@@ -18,7 +19,7 @@ __global__ void __launch_bounds__(128) perm_kernel(const uint64_t* __restrict__ 
     for (int k = 0; k < 12; k++) s[k] = in[k * count + i];
     for (int r = 0; r < reps; r++) {
         if (V == 0) poseidon_permute(s);
-        else { if (V == 1) pf_permute_unrolled<0>(s); else if (V == 2) pf_permute_unrolled<1>(s); else pf_permute(s);
+        else { if (V == 1) pf_permute_unrolled<0>(s); else if (V == 2) pf_permute_unrolled<1>(s); else if (V == 3) pf_permute(s); else pf_permute_limb(s);
 #pragma unroll
             for (int k = 0; k < 12; k++) s[k] = pf_canon(s[k]); }
     }
@@ -58,18 +59,19 @@ int main(int argc, char** argv) {
     for (auto& v : h) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; v = x % GL_P; }
     // edge values in the first states
     for (int k = 0; k < 12; k++) { h[k * count + 0] = 0; h[k * count + 1] = GL_P - 1; h[k * count + 2] = 0xFFFFFFFFull; h[k * count + 3] = 0xFFFFFFFF00000000ull; }
-    uint64_t *din, *d0, *d1, *d2, *d3;
-    CK(cudaMalloc(&din, 12 * count * 8)); CK(cudaMalloc(&d0, 12 * count * 8)); CK(cudaMalloc(&d1, 12 * count * 8)); CK(cudaMalloc(&d2, 12 * count * 8)); CK(cudaMalloc(&d3, 12 * count * 8));
+    uint64_t *din, *d0, *d1, *d2, *d3, *d4;
+    CK(cudaMalloc(&din, 12 * count * 8)); CK(cudaMalloc(&d0, 12 * count * 8)); CK(cudaMalloc(&d1, 12 * count * 8)); CK(cudaMalloc(&d2, 12 * count * 8)); CK(cudaMalloc(&d3, 12 * count * 8)); CK(cudaMalloc(&d4, 12 * count * 8));
     CK(cudaMemcpy(din, h.data(), 12 * count * 8, cudaMemcpyHostToDevice));
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     unsigned blocks = (unsigned)((count + 127) / 128);
     float ms;
-    for (int v = 0; v < 4; v++) {
+    for (int v = 0; v < 5; v++) {
         for (int w = 0; w < 3; w++) {
             cudaEventRecord(e0);
             if (v == 0) perm_kernel<0><<<blocks, 128>>>(din, d0, count, reps); else if (v == 1) perm_kernel<1><<<blocks, 128>>>(din, d1, count, reps);
             else if (v == 2) perm_kernel<2><<<blocks, 128>>>(din, d2, count, reps);
-            else perm_kernel<3><<<blocks, 128>>>(din, d3, count, reps);
+            else if (v == 3) perm_kernel<3><<<blocks, 128>>>(din, d3, count, reps);
+            else perm_kernel<4><<<blocks, 128>>>(din, d4, count, reps);
             cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1);
         }
         printf("variant %d: %.3f ms for %zu x %d perms -> %.1f Mperm/s\n", v, ms, count, reps, count * (double)reps / ms / 1e3);
@@ -78,6 +80,8 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(r0.data(), d0, 12 * count * 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(r1.data(), d1, 12 * count * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(r2.data(), d2, 12 * count * 8, cudaMemcpyDeviceToHost));
     size_t bad = 0;
+    CK(cudaMemcpy(r1.data(), d4, 12 * count * 8, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < 12 * count; i++) if (r0[i] != r1[i]) { if (bad < 5) printf("v4 (limb-form partial rounds, tools/pf_limb_variant.cuh) mismatch at %zu\n", i); bad++; }
     CK(cudaMemcpy(r1.data(), d3, 12 * count * 8, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < 12 * count; i++) if (r0[i] != r1[i]) { if (bad < 5) printf("v3 mismatch at %zu\n", i); bad++; }
     CK(cudaMemcpy(r1.data(), d1, 12 * count * 8, cudaMemcpyDeviceToHost));
