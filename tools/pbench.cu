@@ -1,5 +1,5 @@
 // Standalone micro-benchmark of Poseidon permutation variants + integer pipe throughput (development tool).
-// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I zk_evm_b200/csrc tools/pbench.cu -o tools/pbench
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I zk_evm_b200/csrc -I tools tools/pbench.cu -o tools/pbench
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
