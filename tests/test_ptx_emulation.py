@@ -87,3 +87,46 @@ def test_radix16_butterfly_network(emu):
         got = run(emu, "k_dft16", x, 16, extra=[inverse])
         want = [sum(x[j] * pow(w, j * k, P) for j in range(16)) % P for k in range(16)]
         assert [got[rev[k]] for k in range(16)] == want
+
+
+# ---- the production Merkle kernels themselves (csrc/merkle.cu compiled to PTX, one thread emulated) ---------------------------------
+MERKLE_PTX = os.path.join(HERE, "native", "merkle.ptx")
+
+
+@pytest.fixture(scope="module")
+def merkle_emu():
+    from ptx_emu import PtxEmu
+    src = os.path.join(CSRC, "merkle.cu")
+    deps = [src] + [os.path.join(CSRC, f) for f in ("gl.cuh", "poseidon.cuh", "poseidon_fast.cuh", "internal.h", "merkle.h")]
+    if not os.path.exists(MERKLE_PTX) or any(os.path.getmtime(d) > os.path.getmtime(MERKLE_PTX) for d in deps):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", CSRC, "-ptx", "-o", MERKLE_PTX, src])
+    return PtxEmu(open(MERKLE_PTX).read())
+
+
+@pytest.mark.parametrize("ncols", [1, 3, 4, 5, 8, 9, 16, 21])
+def test_leaf_hash_kernel_one_row(merkle_emu, ncols):
+    """leaf_hash_kernel: thread j hashes LDE row j = data[c * stride + j] over the columns (hash_or_noop: <= 4 columns are copied,
+    zero padded; wider rows go through the overwrite-mode sponge, 8 columns per permutation)"""
+    orc = oracle_lib.load()
+    rng = np.random.default_rng(20 + ncols)
+    nrows, stride, j = 3, 5, 1
+    data = oracle_lib.rand_field(rng, (ncols, stride))
+    mem = {IN + 8 * (c * stride + r): int(data[c, r]) for c in range(ncols) for r in range(stride)}
+    merkle_emu.run("leaf_hash_kernel", [IN, stride, ncols, nrows, OUT], mem, tid=j, ctaid=0, ntid=128)
+    got = [mem[OUT + 8 * (4 * j + k)] for k in range(4)]
+    assert got == [int(v) for v in orc.hash_or_noop(data[:, j])]
+    # a thread past the last row writes nothing
+    mem2 = dict(mem)
+    merkle_emu.run("leaf_hash_kernel", [IN, stride, ncols, nrows, OUT + 0x1000], mem2, tid=nrows, ctaid=0, ntid=128)
+    assert not any(a >= OUT + 0x1000 for a in mem2)
+
+
+def test_merkle_level_kernel_one_node(merkle_emu):
+    orc = oracle_lib.load()
+    rng = np.random.default_rng(30)
+    kids = oracle_lib.rand_field(rng, (6, 4))           # three nodes: (0,1), (2,3), (4,5)
+    mem = {IN + 8 * i: int(v) for i, v in enumerate(kids.ravel())}
+    for node in range(3):
+        merkle_emu.run("merkle_level_kernel", [IN, OUT, 3], mem, tid=node, ctaid=0, ntid=128)
+        got = [mem[OUT + 8 * (4 * node + k)] for k in range(4)]
+        assert got == [int(v) for v in orc.two_to_one(kids[2 * node], kids[2 * node + 1])]

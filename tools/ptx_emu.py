@@ -142,11 +142,18 @@ class PtxEmu:
                         data, off = self.consts[nm[0]], ad - self.const_base[nm[0]]
                     assert 0 <= off and off + bits // 8 <= len(data)
                     R[a[0]] = int.from_bytes(data[off:off + bits // 8], "little")
+                elif a[0].startswith("{"):        # vector load: consecutive elements
+                    for i, d in enumerate(x.strip() for x in a[0].strip("{}").split(",")):
+                        R[d] = mem[(val(b) + off + i * bits // 8) & M64]
                 else:
                     R[a[0]] = mem[(val(b) + off) & M64]
             elif base == "st":
                 b, off = addr(a[0])
-                mem[(val(b) + off) & M64] = val(a[1]) & mask
+                if a[1].startswith("{"):
+                    for i, d in enumerate(x.strip() for x in a[1].strip("{}").split(",")):
+                        mem[(val(b) + off + i * bits // 8) & M64] = val(d) & mask
+                else:
+                    mem[(val(b) + off) & M64] = val(a[1]) & mask
             elif base == "cvta":
                 R[a[0]] = val(a[1])
             elif base == "cvt":
