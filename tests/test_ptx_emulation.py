@@ -130,3 +130,78 @@ def test_merkle_level_kernel_one_node(merkle_emu):
         merkle_emu.run("merkle_level_kernel", [IN, OUT, 3], mem, tid=node, ctaid=0, ntid=128)
         got = [mem[OUT + 8 * (4 * node + k)] for k in range(4)]
         assert got == [int(v) for v in orc.two_to_one(kids[2 * node], kids[2 * node + 1])]
+
+
+# ---- the production NTT pass kernel: a whole 32-thread block with its barriers and shared-memory tile -----------------------------
+NTT_PTX = os.path.join(HERE, "native", "ntt.ptx")
+
+
+@pytest.fixture(scope="module")
+def ntt_emu():
+    from ptx_emu import PtxEmu
+    src = os.path.join(CSRC, "ntt.cu")
+    deps = [src] + [os.path.join(CSRC, f) for f in ("gl.cuh", "ntt_tile.cuh", "ntt.h", "internal.h")]
+    if not os.path.exists(NTT_PTX) or any(os.path.getmtime(d) > os.path.getmtime(NTT_PTX) for d in deps):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", CSRC, "-ptx", "-o", NTT_PTX, src])
+    return PtxEmu(open(NTT_PTX).read())
+
+
+def _pass_params(src, dst, n, log_n, m, r, t, strided, roots, interpass=0, prescale0=0):
+    import struct
+    # PassParams of csrc/ntt_tile.cuh: src, dst, src_stride, dst_stride, src_shift, log_n, m, r, t, strided, roots, interpass,
+    # prescale0, prescale1, prescale_mask (+ padding) = 96 bytes
+    return struct.pack("<QQQQIIIIIIQQQQII", src, dst, n, n, 0, log_n, m, r, t, strided, roots, interpass, prescale0, 0, 0, 0)
+
+
+@pytest.mark.parametrize("lg,inverse", [(6, False), (6, True), (9, False), (5, True)])
+def test_ntt_pass_kernel_block(ntt_emu, lg, inverse):
+    """single-pass transforms (L <= 12: one final contiguous pass, tile = the whole transform, 32 threads): the kernel's PTX for a whole
+    block — global loads fused into the first round, radix-16 rounds through the padded shared-memory tile, barriers — against the
+    oracle's fft / ifft (DIF: natural order in, bit-reversed order out; the inverse leaves out the 1/n)"""
+    orc = oracle_lib.load()
+    rng = np.random.default_rng(40 + lg)
+    n = 1 << lg
+    x = oracle_lib.rand_field(rng, (n,))
+    w = int(orc.lib.orc_root_of_unity(12))
+    if inverse:
+        w = pow(w, P - 2, P)
+    ROOTS, SRC, DST = 0x30000000, IN, OUT
+    mem = {ROOTS + 8 * k: pow(w, k, P) for k in range(4096)}
+    mem.update({SRC + 8 * i: int(v) for i, v in enumerate(x)})
+    params = _pass_params(SRC, DST, n, lg, lg, lg, 0, 0, ROOTS)
+    ntt_emu.run_block("ntt_pass_kernelILi32ELb%dE" % int(inverse), [params], mem, ntid=32, ctaid=(0, 0))
+    got = [mem[DST + 8 * i] for i in range(n)]
+    rev = [int(("{:0%db}" % lg).format(i)[::-1], 2) for i in range(n)]
+    want = orc.ntt(x, 1 if inverse else 0)[0]
+    if inverse:
+        want = [int(v) * n % P for v in want]                 # the kernel leaves the 1/n to the bit-reversal pass
+    assert [got[rev[k]] for k in range(n)] == [int(v) for v in want]
+
+
+def test_ntt_two_pass_coset_transform_blocks(ntt_emu):
+    """L = 13, the launcher's plan [8, 5]: a strided pass (tiles of 2^8 digit values x 16 contiguous elements, coset prescale on the
+    first load, inter-pass twiddle on the store straight from the last round) and the final contiguous pass (128 sub-transforms of 32
+    per tile), every block of both passes emulated with 256 threads; against the oracle's coset_fft"""
+    orc = oracle_lib.load()
+    lg, n = 13, 1 << 13
+    G = 14293326489335486720
+    rng = np.random.default_rng(50)
+    x = oracle_lib.rand_field(rng, (n,))
+    w12 = int(orc.lib.orc_root_of_unity(12))
+    wN = int(orc.lib.orc_root_of_unity(lg))
+    ROOTS, PRE, IP, BUF = 0x30000000, 0x40000000, 0x50000000, IN
+    mem = {ROOTS + 8 * k: pow(w12, k, P) for k in range(4096)}
+    mem.update({PRE + 8 * j: pow(G, j, P) for j in range(n)})
+    mp = lg - 8
+    mem.update({IP + 8 * ((kd << mp) + jp): pow(wN, (kd * jp) % n, P) for kd in range(256) for jp in range(1 << mp)})
+    mem.update({BUF + 8 * i: int(v) for i, v in enumerate(x)})
+    p1 = _pass_params(BUF, BUF, n, lg, lg, 8, 4, 1, ROOTS, interpass=IP, prescale0=PRE)          # in place, like ntt_dif
+    for tile in range(n >> 12):
+        ntt_emu.run_block("ntt_pass_kernelILi256ELb0E", [p1], mem, ntid=256, ctaid=(tile, 0))
+    p2 = _pass_params(BUF, BUF, n, lg, lg - 8, lg - 8, 7, 0, ROOTS)
+    for tile in range(n >> 12):
+        ntt_emu.run_block("ntt_pass_kernelILi256ELb0E", [p2], mem, ntid=256, ctaid=(tile, 0))
+    got = [mem[BUF + 8 * i] for i in range(n)]
+    rev = [int("{:013b}".format(i)[::-1], 2) for i in range(n)]
+    want = orc.ntt(x, 2, G)[0]
+    assert [got[rev[k]] for k in range(n)] == [int(v) for v in want]

@@ -1,12 +1,14 @@
 #!/usr/bin/env python3
 """A small PTX interpreter for the integer subset our kernels use (development tool: there is no GPU in the build container).
 
-Runs ONE thread of ONE kernel from a `nvcc -ptx` file on the CPU: add/sub with carry flags, mul/mad.wide, shifts, funnel shifts, logic,
-setp/selp, predicated branches, ld/st.global, ld.const, ld.param.  Enough to execute the Poseidon permutation, the field arithmetic and
+Runs ONE thread (run) or one whole thread block with its barriers and shared memory (run_block) of a kernel from a `nvcc -ptx` file on
+the CPU: add/sub with carry flags, mul/mad.wide, shifts, funnel shifts, brev, logic, setp/selp, predicated branches, ld/st.global,
+ld/st.shared, bar.sync, ld.const, ld.param (scalars or a by-value struct given as bytes).  Enough to execute the Poseidon permutation, the field arithmetic and
 the NTT butterflies exactly as nvcc emitted them (inline PTX included), so that device code can be compared with the oracle before any
 GPU time is spent.  What it cannot see is ptxas (PTX -> SASS); the GPU parity tests remain the judge of that.
 
 usage (library):  emu = PtxEmu(open("k.ptx").read()); emu.run("kernel_name_substring", params=[...], mem={addr: u64}, tid=0, ctaid=0, ntid=128)
+                  emu.run_block("kernel", params, mem, ntid=32, ctaid=(bx, by))     # all threads, lock-step at bar.sync
 """
 import re
 
@@ -21,10 +23,16 @@ class PtxEmu:
             self.consts[m.group(1)] = data + bytes(int(m.group(2)) - len(data))       # trailing zeros are not written out
         # constant arrays get fake base addresses so that pointer arithmetic on them works
         self.const_base = {n: (1 << 56) + (i << 32) for i, n in enumerate(self.consts)}
+        # shared arrays (extern or static): offsets in one per-block shared window; extern arrays start at 0
+        self.shared_base, off = {}, 0
+        for m in re.finditer(r"\.shared\s+\.align\s+(\d+)\s+\.b8\s+(\w+)\[(\d*)\]", text):
+            self.shared_base[m.group(2)] = 0 if not m.group(3) else off
+            if m.group(3):
+                off += (int(m.group(3)) + 15) // 16 * 16
         self.kernels = {}
         for m in re.finditer(r"\.entry\s+(\S+)\(\s*(.*?)\)\s*(?:\.\w+[^\{]*)?\{(.*?)\n\}", text, re.S):
             name, params, body = m.group(1), m.group(2), m.group(3)
-            pnames = [p.strip().split()[-1] for p in params.split(",") if p.strip()]
+            pnames = [re.sub(r"\[\d+\]$", "", p.strip().split()[-1]) for p in params.split(",") if p.strip()]
             self.kernels[name] = (pnames, self._parse(body))
 
     @staticmethod
@@ -71,6 +79,30 @@ class PtxEmu:
 
     # ---- execution ---------------------------------------------------------------------------------------------
     def run(self, kernel, params, mem, tid=0, ctaid=0, ntid=128, max_steps=50_000_000):
+        """one thread; barriers are ignored (single-thread kernels or kernels whose barriers only order other threads' data)"""
+        for _ in self._exec(kernel, params, mem, {}, tid, ctaid, ntid, max_steps):
+            pass
+        return mem
+
+    def run_block(self, kernel, params, mem, ntid, ctaid=0, max_steps=50_000_000):
+        """all `ntid` threads of one block: every thread runs to its next bar.sync (or to its end), then the next phase starts"""
+        smem = {}
+        threads = [self._exec(kernel, params, mem, smem, t, ctaid, ntid, max_steps) for t in range(ntid)]
+        live = list(range(ntid))
+        while live:
+            nxt = []
+            for t in live:
+                try:
+                    next(threads[t])
+                    nxt.append(t)
+                except StopIteration:
+                    pass
+            assert not nxt or len(nxt) == len(live), "threads disagree on a barrier"
+            live = nxt
+        return mem
+
+    def _exec(self, kernel, params, mem, smem, tid, ctaid, ntid, max_steps):
+        cx, cy = (ctaid, 0) if isinstance(ctaid, int) else ctaid
         name = [k for k in self.kernels if kernel in k]
         assert len(name) == 1, name
         pnames, (ins, labels) = self.kernels[name[0]]
@@ -83,12 +115,16 @@ class PtxEmu:
                 if a == "%tid.x":
                     return tid
                 if a == "%ctaid.x":
-                    return ctaid
+                    return cx
+                if a == "%ctaid.y":
+                    return cy
                 if a == "%ntid.x":
                     return ntid
                 return R[a]
             if a in self.const_base:
                 return self.const_base[a]
+            if a in self.shared_base:
+                return self.shared_base[a]
             if a.startswith("0x") or a.startswith("-0x"):
                 return int(a, 16) & ((1 << bits) - 1)
             if a.endswith("U"):
@@ -112,6 +148,9 @@ class PtxEmu:
             base = o[0]
             if op == "ret":
                 break
+            if base == "bar":
+                yield
+                continue
             if base == "bra":
                 pc = labels[a[0]]
                 continue
@@ -131,7 +170,18 @@ class PtxEmu:
             elif base == "ld":
                 b, off = addr(a[1])
                 if o[1] == "param":
-                    R[a[0]] = pval[b]
+                    pv = pval[b]
+                    if isinstance(pv, (bytes, bytearray)):          # by-value struct
+                        n = bits // 8
+                        if a[0].startswith("{"):
+                            for i, d in enumerate(x.strip() for x in a[0].strip("{}").split(",")):
+                                R[d] = int.from_bytes(pv[off + i * n:off + (i + 1) * n], "little")
+                        else:
+                            R[a[0]] = int.from_bytes(pv[off:off + n], "little")
+                    else:
+                        R[a[0]] = pv
+                elif o[1] == "shared":
+                    R[a[0]] = smem[(val(b) + off) & M32]
                 elif o[1] == "const":
                     if b in self.consts:
                         data = self.consts[b]
@@ -147,6 +197,9 @@ class PtxEmu:
                         R[d] = mem[(val(b) + off + i * bits // 8) & M64]
                 else:
                     R[a[0]] = mem[(val(b) + off) & M64]
+            elif base == "st" and o[1] == "shared":
+                b, off = addr(a[0])
+                smem[(val(b) + off) & M32] = val(a[1]) & mask
             elif base == "st":
                 b, off = addr(a[0])
                 if a[1].startswith("{"):
@@ -170,6 +223,8 @@ class PtxEmu:
                 if "cc" in o:
                     cc = cout
                 R[a[0]] = r & mask
+            elif base == "brev":
+                R[a[0]] = int("{:032b}".format(val(a[1], 32))[::-1], 2)
             elif base == "neg":
                 R[a[0]] = (-val(a[1], bits)) & mask
             elif base == "mul":
@@ -197,7 +252,7 @@ class PtxEmu:
                 x, y = val(a[1], bits), val(a[2], bits)
                 R[a[0]] = (x & y) if base == "and" else (x | y) if base == "or" else (x ^ y)
             elif base == "not":
-                R[a[0]] = 0 if val(a[1]) else 1
+                R[a[0]] = (0 if val(a[1]) else 1) if o[-1] == "pred" else (~val(a[1], bits)) & mask
             elif base == "setp":
                 x, y = val(a[1], bits), val(a[2], bits)
                 if o[-1].startswith("s"):
@@ -209,4 +264,3 @@ class PtxEmu:
                 R[a[0]] = val(a[1], bits) if R[a[3]] else val(a[2], bits)
             else:
                 raise NotImplementedError(op)
-        return mem
