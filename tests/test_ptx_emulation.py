@@ -205,3 +205,127 @@ def test_ntt_two_pass_coset_transform_blocks(ntt_emu):
     rev = [int("{:013b}".format(i)[::-1], 2) for i in range(n)]
     want = orc.ntt(x, 2, G)[0]
     assert [got[rev[k]] for k in range(n)] == [int(v) for v in want]
+
+
+# ---- more production kernels through the interpreter -------------------------------------------------------------------------------
+def _ptx_of(name, extra_deps=()):
+    from ptx_emu import PtxEmu
+    src = os.path.join(CSRC, name + ".cu")
+    out = os.path.join(HERE, "native", name + ".ptx")
+    deps = [src] + [os.path.join(CSRC, f) for f in ("gl.cuh", "internal.h", "stark_dev.h") + tuple(extra_deps)]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", CSRC, "-ptx", "-o", out, src])
+    return PtxEmu(open(out).read())
+
+
+@pytest.fixture(scope="module")
+def quotient_emu():
+    return _ptx_of("quotient", ("quotient_kernel.cuh",))
+
+
+@pytest.fixture(scope="module")
+def fri_emu():
+    return _ptx_of("fri", ("poseidon_fast.cuh", "poseidon.cuh"))
+
+
+@pytest.fixture(scope="module")
+def aux_emu():
+    return _ptx_of("aux")
+
+
+def _inv(x):
+    return pow(x, P - 2, P)
+
+
+def test_quotient_domain_table(quotient_emu):
+    """quotient_domain_kernel: per LDE point x = g w_N^bitrev(j) the three selectors the fused evaluators multiply by — x - w_n^-1
+    (vanishes on the last row), L_first(x) and L_last(x) — against their closed forms (Z_H(x) / n) / (x - 1), (Z_H(x) w_n^-1 / n) / (x - w_n^-1)"""
+    import struct
+    orc = oracle_lib.load()
+    k = 5
+    n, N, logN = 1 << k, 2 << k, k + 1
+    G = 14293326489335486720
+    wN, wn = int(orc.lib.orc_root_of_unity(logN)), int(orc.lib.orc_root_of_unity(k))
+    last, ninv = _inv(wn), _inv(n)
+    gn = pow(G, n, P)
+    zh = [(gn - 1) % P, (-gn - 1) % P]
+    c_first = [z * ninv % P for z in zh]
+    c_last = [z * last % P * ninv % P for z in zh]
+    args = struct.pack("<QQIIQQQQQQ", OUT, N, logN, 0, wN, last, c_first[0], c_first[1], c_last[0], c_last[1])
+    mem = {}
+    for j in range(N):
+        quotient_emu.run("quotient_domain_kernel", [args], mem, tid=j % 128, ctaid=j // 128, ntid=128)
+    for j in range(N):
+        i = int(("{:0%db}" % logN).format(j)[::-1], 2)
+        x = G * pow(wN, i, P) % P
+        z = (pow(x, n, P) - 1) % P
+        assert mem[OUT + 8 * j] == (x - last) % P
+        assert mem[OUT + 8 * (N + j)] == z * ninv % P * _inv((x - 1) % P) % P
+        assert mem[OUT + 8 * (2 * N + j)] == z * last % P * ninv % P * _inv((x - last) % P) % P
+
+
+def _ext_mul(a, b):
+    return ((a[0] * b[0] + 7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def test_fri_fold_and_leaves_kernels(fri_emu):
+    """fri_fold_kernel: out[i] = sum_t beta^t in[16 i + t] over the quadratic extension (coefficient-space folding of a commit-phase
+    layer); fri_leaves_kernel: the column-major leaf matrix of a layer (16 extension elements = 32 words per leaf)"""
+    rng = np.random.default_rng(60)
+    M, ab = 64, 4
+    re, im = oracle_lib.rand_field(rng, (M,)), oracle_lib.rand_field(rng, (M,))
+    beta = (int(oracle_lib.rand_field(rng, (1,))[0]), int(oracle_lib.rand_field(rng, (1,))[0]))
+    RE, IM, ORE, OIM = IN, IN + 0x10000, OUT, OUT + 0x10000
+    mem = {RE + 8 * i: int(v) for i, v in enumerate(re)}
+    mem.update({IM + 8 * i: int(v) for i, v in enumerate(im)})
+    out_len = M >> ab
+    import struct
+    for i in range(out_len):
+        fri_emu.run("fri_fold_kernel", [RE, IM, out_len, ab, struct.pack("<QQ", *beta), ORE, OIM], mem, tid=i, ctaid=0, ntid=256)
+    for i in range(out_len):
+        acc, bp = (0, 0), (1, 0)
+        for t in range(1 << ab):
+            term = _ext_mul(bp, (int(re[16 * i + t]), int(im[16 * i + t])))
+            acc = ((acc[0] + term[0]) % P, (acc[1] + term[1]) % P)
+            bp = _ext_mul(bp, beta)
+        assert (mem[ORE + 8 * i], mem[OIM + 8 * i]) == acc
+    rows, width = M >> ab, 2 << ab
+    LEAVES = OUT + 0x40000
+    for idx in range(rows * width):
+        fri_emu.run("fri_leaves_kernel", [RE, IM, rows, ab, LEAVES], mem, tid=idx % 256, ctaid=idx // 256, ntid=256)
+    for kcol in range(width):
+        for r in range(rows):
+            src = im if kcol & 1 else re
+            assert mem[LEAVES + 8 * (kcol * rows + r)] == int(src[(r << ab) + (kcol >> 1)])
+
+
+def test_modular_scan_kernels(aux_emu):
+    """the three scan kernels of the running-sum (Z) columns: per-tile inclusive scan (256 threads x 8 items, Hillis-Steele on the thread
+    sums), exclusive scan of the tile totals, offset add — prefix sums for the logUp columns, suffix sums (reverse) for the CTL columns"""
+    import struct
+    rng = np.random.default_rng(61)
+    n, ncols = 2500, 2
+    data = oracle_lib.rand_field(rng, (ncols, n))
+    DATA, JOBS, TOT = IN, IN + 0x100000, IN + 0x200000
+    mem = {DATA + 8 * (c * n + i): int(data[c, i]) for c in range(ncols) for i in range(n)}
+    # ScanJob {uint32 col; uint32 reverse}: job 0 = prefix sums of column 0, job 1 = suffix sums of column 1
+    # (the interpreter's memory is keyed by address at the width of the access: the two u32 fields are stored separately)
+    mem[JOBS], mem[JOBS + 4] = 0, 0
+    mem[JOBS + 8], mem[JOBS + 12] = 1, 1
+    ntiles = (n + 2047) // 2048
+    for job in range(2):
+        for tile in range(ntiles):
+            aux_emu.run_block("scan_tiles_kernel", [JOBS, DATA, n, TOT, ntiles], mem, ntid=256, ctaid=(tile, job))
+    for job in range(2):
+        aux_emu.run_block("scan_totals_kernel", [TOT, ntiles], mem, ntid=256, ctaid=(job, 0))
+    for job in range(2):
+        for tile in range(ntiles):
+            aux_emu.run_block("scan_add_kernel", [JOBS, DATA, n, TOT, ntiles], mem, ntid=256, ctaid=(tile, job))
+    acc = 0
+    for i in range(n):
+        acc = (acc + int(data[0, i])) % P
+        assert mem[DATA + 8 * i] == acc, i
+    acc = 0
+    for i in range(n - 1, -1, -1):
+        acc = (acc + int(data[1, i])) % P
+        assert mem[DATA + 8 * (n + i)] == acc, i

@@ -13,6 +13,7 @@ usage (library):  emu = PtxEmu(open("k.ptx").read()); emu.run("kernel_name_subst
 import re
 
 M32, M64 = (1 << 32) - 1, (1 << 64) - 1
+LOCAL_BASE = 1 << 60          # per-thread stack (".local" depot): addresses at and above this go to a thread-private store
 
 
 class PtxEmu:
@@ -108,6 +109,10 @@ class PtxEmu:
         pnames, (ins, labels) = self.kernels[name[0]]
         pval = dict(zip(pnames, params))
         R, cc = {}, 0
+        lmem = {}
+
+        def space(ad):
+            return lmem if ad >= LOCAL_BASE else mem
 
         def val(a, bits=64):
             a = a.strip()
@@ -125,6 +130,8 @@ class PtxEmu:
                 return self.const_base[a]
             if a in self.shared_base:
                 return self.shared_base[a]
+            if a.startswith("__local_depot"):
+                return LOCAL_BASE
             if a.startswith("0x") or a.startswith("-0x"):
                 return int(a, 16) & ((1 << bits) - 1)
             if a.endswith("U"):
@@ -194,9 +201,11 @@ class PtxEmu:
                     R[a[0]] = int.from_bytes(data[off:off + bits // 8], "little")
                 elif a[0].startswith("{"):        # vector load: consecutive elements
                     for i, d in enumerate(x.strip() for x in a[0].strip("{}").split(",")):
-                        R[d] = mem[(val(b) + off + i * bits // 8) & M64]
+                        ad = (val(b) + off + i * bits // 8) & M64
+                        R[d] = space(ad)[ad]
                 else:
-                    R[a[0]] = mem[(val(b) + off) & M64]
+                    ad = (val(b) + off) & M64
+                    R[a[0]] = space(ad)[ad]
             elif base == "st" and o[1] == "shared":
                 b, off = addr(a[0])
                 smem[(val(b) + off) & M32] = val(a[1]) & mask
@@ -204,9 +213,11 @@ class PtxEmu:
                 b, off = addr(a[0])
                 if a[1].startswith("{"):
                     for i, d in enumerate(x.strip() for x in a[1].strip("{}").split(",")):
-                        mem[(val(b) + off + i * bits // 8) & M64] = val(d) & mask
+                        ad = (val(b) + off + i * bits // 8) & M64
+                        space(ad)[ad] = val(d) & mask
                 else:
-                    mem[(val(b) + off) & M64] = val(a[1]) & mask
+                    ad = (val(b) + off) & M64
+                    space(ad)[ad] = val(a[1]) & mask
             elif base == "cvta":
                 R[a[0]] = val(a[1])
             elif base == "cvt":
@@ -223,6 +234,10 @@ class PtxEmu:
                 if "cc" in o:
                     cc = cout
                 R[a[0]] = r & mask
+            elif base in ("div", "rem"):
+                assert o[-1][0] == "u", op
+                x, y = val(a[1], bits), val(a[2], bits)
+                R[a[0]] = (x // y if base == "div" else x % y) if y else mask
             elif base == "brev":
                 R[a[0]] = int("{:032b}".format(val(a[1], 32))[::-1], 2)
             elif base == "neg":
