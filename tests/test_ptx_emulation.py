@@ -309,9 +309,8 @@ def test_modular_scan_kernels(aux_emu):
     DATA, JOBS, TOT = IN, IN + 0x100000, IN + 0x200000
     mem = {DATA + 8 * (c * n + i): int(data[c, i]) for c in range(ncols) for i in range(n)}
     # ScanJob {uint32 col; uint32 reverse}: job 0 = prefix sums of column 0, job 1 = suffix sums of column 1
-    # (the interpreter's memory is keyed by address at the width of the access: the two u32 fields are stored separately)
-    mem[JOBS], mem[JOBS + 4] = 0, 0
-    mem[JOBS + 8], mem[JOBS + 12] = 1, 1
+    mem[JOBS] = 0 | (0 << 32)
+    mem[JOBS + 8] = 1 | (1 << 32)
     ntiles = (n + 2047) // 2048
     for job in range(2):
         for tile in range(ntiles):

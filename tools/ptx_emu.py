@@ -111,6 +111,15 @@ class PtxEmu:
         R, cc = {}, 0
         lmem = {}
 
+        # memories are dicts of little-endian 8-byte words keyed by their (8-aligned) byte address; accesses are naturally aligned
+        def rd(d, ad, nbytes):
+            w = d[ad & ~7]
+            return (w >> ((ad & 7) * 8)) & ((1 << (8 * nbytes)) - 1)
+
+        def wr(d, ad, nbytes, v):
+            sh, m = (ad & 7) * 8, (1 << (8 * nbytes)) - 1
+            d[ad & ~7] = (d.get(ad & ~7, 0) & ~(m << sh) & M64) | ((v & m) << sh)
+
         def space(ad):
             return lmem if ad >= LOCAL_BASE else mem
 
@@ -161,7 +170,8 @@ class PtxEmu:
             if base == "bra":
                 pc = labels[a[0]]
                 continue
-            bits = 64 if o[-1] in ("u64", "s64", "b64") else 32
+            mt = re.match(r"[usbf](\d+)$", o[-1])
+            bits = int(mt.group(1)) if mt else 32
             mask = (1 << bits) - 1
             if base == "mov":
                 if a[0].startswith("{"):      # mov.b64 {lo, hi}, x
@@ -188,7 +198,7 @@ class PtxEmu:
                     else:
                         R[a[0]] = pv
                 elif o[1] == "shared":
-                    R[a[0]] = smem[(val(b) + off) & M32]
+                    R[a[0]] = rd(smem, (val(b) + off) & M32, bits // 8)
                 elif o[1] == "const":
                     if b in self.consts:
                         data = self.consts[b]
@@ -202,22 +212,22 @@ class PtxEmu:
                 elif a[0].startswith("{"):        # vector load: consecutive elements
                     for i, d in enumerate(x.strip() for x in a[0].strip("{}").split(",")):
                         ad = (val(b) + off + i * bits // 8) & M64
-                        R[d] = space(ad)[ad]
+                        R[d] = rd(space(ad), ad, bits // 8)
                 else:
                     ad = (val(b) + off) & M64
-                    R[a[0]] = space(ad)[ad]
+                    R[a[0]] = rd(space(ad), ad, bits // 8)
             elif base == "st" and o[1] == "shared":
                 b, off = addr(a[0])
-                smem[(val(b) + off) & M32] = val(a[1]) & mask
+                wr(smem, (val(b) + off) & M32, bits // 8, val(a[1]))
             elif base == "st":
                 b, off = addr(a[0])
                 if a[1].startswith("{"):
                     for i, d in enumerate(x.strip() for x in a[1].strip("{}").split(",")):
                         ad = (val(b) + off + i * bits // 8) & M64
-                        space(ad)[ad] = val(d) & mask
+                        wr(space(ad), ad, bits // 8, val(d))
                 else:
                     ad = (val(b) + off) & M64
-                    space(ad)[ad] = val(a[1]) & mask
+                    wr(space(ad), ad, bits // 8, val(a[1]))
             elif base == "cvta":
                 R[a[0]] = val(a[1])
             elif base == "cvt":
