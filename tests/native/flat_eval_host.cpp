@@ -52,3 +52,32 @@ extern "C" int flat_eval_agrees(uint32_t table, uint32_t num_challenges, const u
     }
     return ok;
 }
+
+// ---- for tests/test_ptx_emulation.py: the flat descriptors of a table as the bytes the device sees ---------------------------------
+// Packs the arrays like get_table_dev (aux.cu): each section 16-byte aligned inside `buf`; offs[10] = byte offsets of term_col,
+// term_coef, cols, col_ids, prod_ids, const_ids, filters, entries, ctl_zs, lookups; scalars[7] = n_ctl_zs, n_lookups, num_lookup_cols,
+// num_ctl_helpers, num_ctl_zs, ctl_num_constraints, ctl_paired.  Returns the number of bytes needed (call with buf = NULL first).
+extern "C" size_t flat_pack(uint32_t table, uint32_t num_challenges, uint8_t* buf, size_t cap, uint64_t offs[10], uint32_t scalars[7]) {
+    auto ctls = zkstark::all_cross_table_lookups();
+    zkstark::Flat f = zkstark::build_table_flat(zkstark::table_lookups(table), zkstark::table_ctl_items(table, ctls, num_challenges),
+                                               num_challenges, zkstark::CONSTRAINT_DEGREE);
+    size_t off = 0;
+    auto place = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+    const size_t o[10] = {place(f.term_col.size() * 4), place(f.term_coef.size() * 8), place(f.cols.size() * sizeof(zkstark::ColRec)),
+                          place(f.col_ids.size() * 4), place(f.prod_ids.size() * 4), place(f.const_ids.size() * 4),
+                          place(f.filters.size() * sizeof(zkstark::FilterRec)), place(f.entries.size() * sizeof(zkstark::EntryRec)),
+                          place(f.ctl_zs.size() * sizeof(zkstark::CtlZRec)), place(f.lookups.size() * sizeof(zkstark::LookupRec))};
+    const size_t need = off + 16;
+    if (!buf || cap < need) return need;
+    memset(buf, 0, need);
+    auto put = [&](size_t at, const void* p, size_t bytes) { if (bytes) memcpy(buf + at, p, bytes); };
+    put(o[0], f.term_col.data(), f.term_col.size() * 4); put(o[1], f.term_coef.data(), f.term_coef.size() * 8);
+    put(o[2], f.cols.data(), f.cols.size() * sizeof(zkstark::ColRec)); put(o[3], f.col_ids.data(), f.col_ids.size() * 4);
+    put(o[4], f.prod_ids.data(), f.prod_ids.size() * 4); put(o[5], f.const_ids.data(), f.const_ids.size() * 4);
+    put(o[6], f.filters.data(), f.filters.size() * sizeof(zkstark::FilterRec)); put(o[7], f.entries.data(), f.entries.size() * sizeof(zkstark::EntryRec));
+    put(o[8], f.ctl_zs.data(), f.ctl_zs.size() * sizeof(zkstark::CtlZRec)); put(o[9], f.lookups.data(), f.lookups.size() * sizeof(zkstark::LookupRec));
+    for (int i = 0; i < 10; i++) offs[i] = o[i];
+    scalars[0] = (uint32_t)f.ctl_zs.size(); scalars[1] = (uint32_t)f.lookups.size(); scalars[2] = f.num_lookup_cols;
+    scalars[3] = f.num_ctl_helpers; scalars[4] = f.num_ctl_zs; scalars[5] = f.ctl_num_constraints; scalars[6] = f.ctl_paired;
+    return need;
+}

@@ -328,3 +328,92 @@ def test_modular_scan_kernels(aux_emu):
     for i in range(n - 1, -1, -1):
         acc = (acc + int(data[1, i])) % P
         assert mem[DATA + 8 * (n + i)] == acc, i
+
+
+# ---- the fused quotient kernels, one LDE point at a time, against the oracle's evaluator -------------------------------------------------
+import ctypes as C
+
+QUOT_TABLES = {7: "MemBefore / MemAfter", 6: "Memory", 5: "Logic", 1: "BytePacking", 4: "KeccakSponge", 3: "Keccak", 0: "Arithmetic", 2: "Cpu"}
+NUM_COLUMNS = (116, 71, 85, 2431, 438, 523, 30, 12, 12)
+APOW_MAX = 1023
+
+
+@pytest.fixture(scope="module")
+def flat_host():
+    src = os.path.join(HERE, "native", "flat_eval_host.cpp")
+    lib = os.path.join(HERE, "native", "libflat_eval_host.so")
+    oracle_dir = os.path.join(ROOT, "oracle")
+    deps = [src] + [os.path.join(CSRC, "stark", f) for f in os.listdir(os.path.join(CSRC, "stark"))] + \
+           [os.path.join(oracle_dir, f) for f in os.listdir(oracle_dir) if f.endswith(".h")]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-fopenmp", "-Wno-unknown-pragmas", "-I", CSRC, "-I", oracle_dir,
+                               "-o", lib, src])
+    h = C.CDLL(lib)
+    h.flat_pack.restype = C.c_size_t
+    return h
+
+
+def _load_bytes(mem, base, data):
+    data = bytes(data) + bytes(-len(data) % 8)
+    for i in range(0, len(data), 8):
+        mem[base + i] = int.from_bytes(data[i:i + 8], "little")
+
+
+@pytest.mark.parametrize("table", sorted(QUOT_TABLES))
+def test_fused_quotient_kernel_point(flat_host, table):
+    """quotient_kernel<TABLE> (csrc/quotient_kernel.cuh + the table's single-source evaluator + the CTL / lookup interpreter, as PTX): one
+    thread = one LDE point.  The inputs are arbitrary field elements in the kernel's own layout (column-major LDEs with bit-reversed
+    rows, domain table, alpha-power table, packed descriptors), so the kernel is checked as the FUNCTION it is — rows i and i+2, the
+    selectors, two challenges — against the oracle's eval_vanishing_poly on the same rows (times 1 / Z_H)."""
+    import struct
+    from ptx_emu import PtxEmu
+    src = os.path.join(CSRC, "quotient_t%d.cu" % table)
+    ptx = os.path.join(HERE, "native", "quotient_t%d.ptx" % table)
+    deps = [src, os.path.join(CSRC, "quotient_kernel.cuh")] + [os.path.join(CSRC, "stark", f) for f in os.listdir(os.path.join(CSRC, "stark"))]
+    if not os.path.exists(ptx) or any(os.path.getmtime(d) > os.path.getmtime(ptx) for d in deps):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", CSRC, "-ptx", "-o", ptx, src])
+    emu = PtxEmu(open(ptx).read())
+    rng = np.random.default_rng(70 + table)
+    u64p = C.POINTER(C.c_uint64)
+    nc = NUM_COLUMNS[table]
+    logN, N = 3, 8
+    # descriptors
+    offs, scal = (C.c_uint64 * 10)(), (C.c_uint32 * 7)()
+    need = flat_host.flat_pack(C.c_uint32(table), C.c_uint32(2), None, C.c_size_t(0), offs, scal)
+    buf = (C.c_uint8 * need)()
+    flat_host.flat_pack(C.c_uint32(table), C.c_uint32(2), buf, C.c_size_t(need), offs, scal)
+    naux = scal[2] + scal[3] + scal[4]
+    TR, AUX, DOM, APOW, FLAT, QOUT = 0x100000000, 0x200000000, 0x300000000, 0x310000000, 0x320000000, 0x330000000
+    trace = oracle_lib.rand_field(rng, (nc, N))
+    aux = oracle_lib.rand_field(rng, (max(naux, 1), N))
+    dom = oracle_lib.rand_field(rng, (3, N))
+    al, be, ga, zh = (oracle_lib.rand_field(rng, (2,)) for _ in range(4))
+    labels = np.array(oracle_lib.DEFAULT_LABELS, dtype=np.uint64)
+    mem = {}
+    _load_bytes(mem, TR, trace.tobytes())
+    _load_bytes(mem, AUX, aux.tobytes())
+    _load_bytes(mem, DOM, dom.tobytes())
+    apow = np.array([[pow(int(a), e, P) for e in range(APOW_MAX + 1)] for a in al], dtype=np.uint64)
+    _load_bytes(mem, APOW, apow.tobytes())
+    _load_bytes(mem, FLAT, bytes(buf))
+    args = struct.pack("<QQQQII", TR, AUX, QOUT, N, logN, 2) + struct.pack("<6Q", *(int(v) for v in list(al) + list(be) + list(ga))) + \
+        struct.pack("<Q", DOM) + struct.pack("<2Q", int(zh[0]), int(zh[1])) + struct.pack("<Q", APOW) + \
+        struct.pack("<10Q", *(FLAT + int(o) for o in offs)) + struct.pack("<7I", *scal) + b"\0" * 4 + struct.pack("<4Q", *(int(v) for v in labels))
+    assert len(args) == 264
+    kernel = "quotient_kernelILj%dEE" % table
+    nthreads = 256 if table == 6 else 128
+    p = lambda a: a.ctypes.data_as(u64p)
+    for j in (1, 6):
+        emu.run(kernel, [args], mem, tid=j, ctaid=0, ntid=nthreads)
+        i = int("{:03b}".format(j)[::-1], 2)
+        jn = int("{:03b}".format((i + 2) % N)[::-1], 2)
+        lv, nv = np.ascontiguousarray(trace[:, j]), np.ascontiguousarray(trace[:, jn])
+        alv, anv = np.ascontiguousarray(aux[:, j]), np.ascontiguousarray(aux[:, jn])
+        sel = np.ascontiguousarray(dom[:, j])
+        a, b = np.zeros(2, np.uint64), np.zeros(2, np.uint64)
+        na = C.c_uint32()
+        r = flat_host.flat_eval_agrees(C.c_uint32(table), C.c_uint32(2), p(lv), p(nv), p(alv), p(anv), p(al), p(be), p(ga), p(sel), p(labels),
+                                       p(a), p(b), C.byref(na))
+        assert r == 1
+        for k in range(2):
+            assert mem[QOUT + 8 * (k * N + i)] == int(a[k]) * int(zh[i & 1]) % P, (table, j, k)
