@@ -35,7 +35,9 @@ typedef enum {
     ZKGPU_ERR_NOMEM = -5
 } zkgpu_status;
 
-enum { ZKGPU_MEM_HOST = 0, ZKGPU_MEM_DEVICE = 1 };
+/* ZKGPU_MEM_AUTO (segment calls only): each table's pointer is host or device memory on its own (unified addressing decides), e.g. a
+ * Keccak trace finished on the device (zkgpu_keccak_generate_trace) next to host traces of the other tables */
+enum { ZKGPU_MEM_HOST = 0, ZKGPU_MEM_DEVICE = 1, ZKGPU_MEM_AUTO = 2 };
 
 /* Table ids == `Table` enum, evm_arithmetization/src/all_stark.rs:74-86 */
 enum {
@@ -87,9 +89,10 @@ int zkgpu_ctx_stats(zkgpu_ctx* ctx, uint64_t* kernel_launches, uint64_t* bytes_i
 /* In-library profiler for bench.py's roofline numbers: while on, every launch group of a kernel family is bracketed by CUDA
  * events on the context's stream (the stream the kernels run on) and accounted with its ALGORITHMIC bytes.
  * family: 0 leaf_hash (Poseidon sponge over LDE rows), 1 merkle inner levels, 2 NTT / LDE passes, 3 quotient evaluation,
- * 4 CTL + lookup auxiliary columns, 5 openings, 6 FRI combine / fold / layer leaves, 7 proof-of-work grind. */
+ * 4 CTL + lookup auxiliary columns, 5 openings, 6 FRI combine / fold / layer leaves, 7 proof-of-work grind,
+ * 8 device-side trace finishing (zkgpu_keccak_generate_trace). */
 enum { ZKGPU_KF_LEAF_HASH = 0, ZKGPU_KF_MERKLE_LEVELS, ZKGPU_KF_NTT, ZKGPU_KF_QUOTIENT, ZKGPU_KF_AUX, ZKGPU_KF_OPENINGS, ZKGPU_KF_FRI,
-       ZKGPU_KF_POW, ZKGPU_KF_COUNT };
+       ZKGPU_KF_POW, ZKGPU_KF_TRACE_GEN, ZKGPU_KF_COUNT };
 int zkgpu_ctx_set_profiling(zkgpu_ctx* ctx, int on);   /* on: also resets the counters */
 int zkgpu_ctx_kernel_stats(zkgpu_ctx* ctx, uint32_t family, uint64_t* launches, double* ms_total, double* algorithmic_bytes);
 
@@ -205,6 +208,22 @@ int zkgpu_prove_segment_uploaded(zkgpu_ctx* ctx, zkgpu_upload* upload, const uin
                                  volatile const int* abort_flag, zkgpu_proof** proofs_out /*[ZKGPU_NUM_TABLES]*/, uint64_t* ctl_challenges_out,
                                  uint64_t* trace_caps_out);
 void zkgpu_upload_free(zkgpu_upload* upload);
+
+/* ---- device-side trace finishing (the data-parallel tail of trace generation) --------------------------------------- */
+/* KeccakStark::generate_trace (keccak/keccak_stark.rs:70-250, called from witness/traces.rs into_tables): `inputs` = num_perms x 25
+ * words (lane y*5 + x of each permutation's input state), `timestamps` = one per permutation, both host memory (borrowed for the call;
+ * pinned memory must stay valid until the context is synchronised).  The trace is built in device memory: 2431 columns x n rows,
+ * column-major, n = max(24 * num_perms, min_rows).next_power_of_two(), rows past 24 * num_perms all zero — bit for bit what
+ * trace_rows_to_poly_values(generate_trace_rows(..)) holds.  The result is ordered on the context's stream: hand zkgpu_dev_trace_ptr to
+ * zkgpu_prove_segment / zkgpu_segment_upload (ZKGPU_MEM_DEVICE or ZKGPU_MEM_AUTO) or zkgpu_commit_values_contig of the SAME context, or
+ * zkgpu_ctx_sync first.  The 2431-column trace (2.5 GB at 2^17 rows) never crosses PCIe: 208 bytes per permutation do. */
+typedef struct zkgpu_dev_trace zkgpu_dev_trace;
+int zkgpu_keccak_generate_trace(zkgpu_ctx* ctx, const uint64_t* inputs, const uint64_t* timestamps, size_t num_perms, size_t min_rows,
+                                zkgpu_dev_trace** out);
+int zkgpu_dev_trace_dims(const zkgpu_dev_trace* t, size_t* ncols, size_t* n);
+const uint64_t* zkgpu_dev_trace_ptr(const zkgpu_dev_trace* t);             /* device address of column 0 (column c at + c*n) */
+int zkgpu_dev_trace_export(const zkgpu_dev_trace* t, uint64_t* host_out);  /* ncols * n words (parity tests) */
+void zkgpu_dev_trace_free(zkgpu_dev_trace* t);
 
 /* ---- stage-by-stage parity hooks (tests) ---------------------------------------------------------------------- */
 /* when on, proofs retain their auxiliary / quotient PolynomialBatch and the FRI input values */

@@ -1,0 +1,63 @@
+"""GPU parity of the device-side trace finishing: zkgpu_keccak_generate_trace == the restated
+KeccakStark::generate_trace (keccak_stark.rs:70-250; tests/traces.py), bit for bit, and a segment proved from the device-resident
+Keccak trace next to host traces of the other tables (ZKGPU_MEM_AUTO) == the oracle's proofs from the host trace."""
+import numpy as np
+import pytest
+from tests import traces
+from tests.oracle_lib import orc_prove_segment, orc_prove_table, orc_verify_table, TEST_CONFIG, DEFAULT_LABELS
+import zk_evm_b200 as zk
+
+pytestmark = pytest.mark.gpu
+PUBLIC_VALUES = np.arange(1000, 1000 + 37, dtype=np.uint64)
+
+
+@pytest.mark.parametrize("nperm,min_rows,log_n", [(1, 0, 5), (5, 0, 7), (10, 16, 8), (2, 256, 8), (0, 16, 4), (170, 0, 12)])
+def test_keccak_trace_matches_reference_restatement(ctx, nperm, min_rows, log_n):
+    rng = np.random.default_rng(300 + nperm)
+    inputs = rng.integers(0, 1 << 64, size=(nperm, 25), dtype=np.uint64)
+    ts = rng.integers(1, 1 << 40, size=(nperm,), dtype=np.uint64)
+    dt = zk.keccak_generate_trace(ctx, inputs, ts, min_rows)
+    assert (dt.ncols, dt.n) == (2431, 1 << log_n)
+    got = dt.export()
+    dt.free()
+    want = traces.keccak_trace(log_n, inputs, ts)[0] if nperm else np.zeros((2431, 1 << log_n), dtype=np.uint64)
+    assert np.array_equal(got, want)
+
+
+def test_segment_from_device_finished_keccak_trace(ctx, oracle):
+    rng = np.random.default_rng(9)
+    inputs = rng.integers(0, 1 << 64, size=(5, 25), dtype=np.uint64)
+    ts = np.arange(1, 6, dtype=np.uint64) * np.uint64(7)
+    tr = traces.valid_segment(seed=13, k=17)
+    host_keccak, _ = traces.keccak_trace(7, inputs, ts)
+    cfg = zk.StarkConfig(*TEST_CONFIG)
+    dt = zk.keccak_generate_trace(ctx, inputs, ts)
+    tr_dev = list(tr)
+    tr_dev[traces.T_KECCAK] = dt
+    ap = zk.prove_with_traces(ctx, tr_dev, PUBLIC_VALUES, cfg, zk.KernelLabels(*DEFAULT_LABELS))
+    dt.free()
+    tr_host = list(tr)
+    tr_host[traces.T_KECCAK] = host_keccak
+    want, bg, caps = orc_prove_segment(oracle, TEST_CONFIG, tr_host, PUBLIC_VALUES)
+    assert np.array_equal(ap.ctl_challenges, bg) and np.array_equal(ap.trace_caps, caps)
+    for t in range(9):
+        assert (ap.stark_proofs[t] is None) == (want[t] is None)
+        assert want[t] is None or np.array_equal(ap.stark_proofs[t], want[t]), "table %s proof differs" % zk.TABLE_NAMES[t]
+
+
+def test_device_finished_keccak_trace_proves_and_verifies(ctx, oracle):
+    """commit straight from the device trace, prove the table, the oracle's verifier accepts (the constraints hold on generated rows)"""
+    rng = np.random.default_rng(10)
+    inputs = rng.integers(0, 1 << 64, size=(2, 25), dtype=np.uint64)
+    ts = np.array([4, 8], dtype=np.uint64)
+    cfg = zk.StarkConfig(*TEST_CONFIG)
+    dt = zk.keccak_generate_trace(ctx, inputs, ts)
+    batch = zk.PolynomialBatch.from_device_values(ctx, dt.device_ptr, dt.ncols, dt.n, cfg.rate_bits, cfg.cap_height, keep_values=True)
+    dt.free()
+    bg = np.array([11, 22], dtype=np.uint64)
+    st0 = np.arange(12, dtype=np.uint64)
+    ctl = zk.get_ctl_data(ctx, traces.T_KECCAK, batch, bg, cfg.num_challenges)
+    proof, st = zk.prove_single_table(ctx, traces.T_KECCAK, cfg, batch, ctl, st0, zk.KernelLabels(*DEFAULT_LABELS))
+    ok, err, st2 = orc_verify_table(oracle, traces.T_KECCAK, TEST_CONFIG, proof.words, bg, st0)
+    assert ok, err
+    assert np.array_equal(st, st2)

@@ -417,3 +417,31 @@ def test_fused_quotient_kernel_point(flat_host, table):
         assert r == 1
         for k in range(2):
             assert mem[QOUT + 8 * (k * N + i)] == int(a[k]) * int(zh[i & 1]) % P, (table, j, k)
+
+
+# ---- device-side trace finishing: the Keccak row kernel ----------------------------------------------------------------------------------
+def test_keccak_trace_kernel_rows():
+    """keccak_trace_kernel (csrc/trace_gen.cu, as PTX), one thread = one trace row: first / middle / last round of a permutation, the last
+    permutation and a padding row, against the Python restatement of keccak_stark.rs generate_trace_rows (tests/traces.py)."""
+    from ptx_emu import PtxEmu
+    from tests import traces
+    src = os.path.join(CSRC, "trace_gen.cu")
+    ptx = os.path.join(HERE, "native", "trace_gen.ptx")
+    deps = [src, os.path.join(CSRC, "stark", "keccak_trace.h"), os.path.join(CSRC, "stark", "table_keccak.h")]
+    if not os.path.exists(ptx) or any(os.path.getmtime(d) > os.path.getmtime(ptx) for d in deps):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", CSRC, "-ptx", "-o", ptx, src])
+    emu = PtxEmu(open(ptx).read())
+    rng = np.random.default_rng(41)
+    nperm, log_n = 3, 7
+    n = 1 << log_n
+    inputs = rng.integers(0, 1 << 64, size=(nperm, 25), dtype=np.uint64)
+    ts = rng.integers(1, 1 << 40, size=(nperm,), dtype=np.uint64)
+    want, _ = traces.keccak_trace(log_n, inputs, ts)
+    TSA, TR = IN + 8 * 25 * nperm, 0x100000000
+    mem = {IN + 8 * i: int(w) for i, w in enumerate(inputs.ravel())}
+    mem.update({TSA + 8 * i: int(w) for i, w in enumerate(ts)})
+    for row in (0, 1, 11, 23, 24, 24 * 2 + 17, 24 * 3 - 1, 24 * 3, n - 1):
+        emu.run("keccak_trace_kernel", [IN, TSA, nperm, n, TR], mem, tid=row % 128, ctaid=row // 128, ntid=128)
+        got = [mem.get(TR + 8 * (c * n + row)) for c in range(2431)]
+        assert got == [int(v) for v in want[:, row]], row
+    assert len([a for a in mem if a >= TR]) == 9 * 2431      # nothing written outside the rows' own cells

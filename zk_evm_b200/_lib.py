@@ -60,7 +60,10 @@ def lib():
         _lib.zkgpu_version.restype = C.c_char_p
         _lib.zkgpu_ctx_destroy.restype = None
         _lib.zkgpu_batch_free.restype = None
-        for name in ("zkgpu_ctl_free", "zkgpu_proof_free", "zkgpu_challenger_free", "zkgpu_table_job_free", "zkgpu_upload_free"):
+        if hasattr(_lib, "zkgpu_dev_trace_ptr"):
+            _lib.zkgpu_dev_trace_ptr.restype = C.c_void_p
+        for name in ("zkgpu_ctl_free", "zkgpu_proof_free", "zkgpu_challenger_free", "zkgpu_table_job_free", "zkgpu_upload_free",
+                     "zkgpu_dev_trace_free"):
             if hasattr(_lib, name):
                 getattr(_lib, name).restype = None
     return _lib

@@ -86,7 +86,7 @@ struct NttTables {
 };
 
 // kernel families the in-library profiler accounts for (zkgpu_ctx_kernel_stats)
-enum KernelFamily { KF_LEAF_HASH = 0, KF_MERKLE_LEVELS, KF_NTT, KF_QUOTIENT, KF_AUX, KF_OPENINGS, KF_FRI, KF_POW, KF_COUNT };
+enum KernelFamily { KF_LEAF_HASH = 0, KF_MERKLE_LEVELS, KF_NTT, KF_QUOTIENT, KF_AUX, KF_OPENINGS, KF_FRI, KF_POW, KF_TRACE_GEN, KF_COUNT };
 
 struct ProfRec { int fam; cudaEvent_t e0, e1; double bytes; uint64_t launches; };
 

@@ -194,7 +194,8 @@ static void segment_upload(Ctx& c, const zkgpu_table_trace* traces, int mem_kind
     for (uint32_t t : u.order) {
         Batch& b = u.tb[t]->b;
         ZK_CUDA(cudaMemcpyAsync(b.values.get(), traces[t].cols, b.ncols * b.n * 8,
-                                mem_kind == ZKGPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.copy_stream));
+                                mem_kind == ZKGPU_MEM_DEVICE ? cudaMemcpyDeviceToDevice
+                                : mem_kind == ZKGPU_MEM_AUTO ? cudaMemcpyDefault : cudaMemcpyHostToDevice, c.copy_stream));
         u.uploaded[t] = u.make_event();
         ZK_CUDA(cudaEventRecord(u.uploaded[t], c.copy_stream));
     }

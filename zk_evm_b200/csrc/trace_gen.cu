@@ -1,0 +1,97 @@
+// GPU-side trace finishing: the data-parallel tail of trace generation runs on the device, so that the widest trace of a
+// segment never crosses PCIe — KeccakStark is 2431 columns (2.5 GB at 2^17 rows, 65 % of a config-#4 segment's upload) generated from
+// 208 bytes per permutation.
+//
+// Replaces /root/reference/evm_arithmetization/src/keccak/keccak_stark.rs:70-250 (KeccakStark::generate_trace: generate_trace_rows +
+// trace_rows_to_poly_values), called from witness/traces.rs:243-258 (`into_tables`).  The row code is stark/keccak_trace.h (host + device).
+//
+// keccak_trace_kernel: one thread per trace ROW.  Rows are independent given the permutation's input (keccak_trace.h), the trace is
+// column-major, so a warp stores 32 consecutive rows of one column per instruction: 256 contiguous bytes.  Write-bound: 8 * 2431 bytes per
+// row against ~1.5 k word operations; algorithmic bytes = 8 * 2431 * n written + 208 * num_perms read.
+#include "internal.h"
+#include "stark/keccak_trace.h"
+
+namespace zk {
+
+struct ColStore {
+    uint64_t* out; size_t n;     // out already points at the thread's row
+    __device__ __forceinline__ void operator()(uint32_t col, uint64_t v) const { out[(size_t)col * n] = v; }
+};
+
+__global__ void __launch_bounds__(128) keccak_trace_kernel(const uint64_t* __restrict__ inputs, const uint64_t* __restrict__ timestamps,
+                                                           uint64_t num_perms, size_t n, uint64_t* __restrict__ out) {
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    ColStore st{out + row, n};
+    zkstark::keccak::generate_row(inputs, timestamps, num_perms, row, st);
+}
+
+}  // namespace zk
+
+struct zkgpu_dev_trace {
+    zk::DevBuf buf;
+    size_t ncols = 0, n = 0;
+};
+
+extern "C" {
+
+int zkgpu_keccak_generate_trace(zkgpu_ctx* h, const uint64_t* inputs, const uint64_t* timestamps, size_t num_perms, size_t min_rows,
+                                zkgpu_dev_trace** out) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(h && out && ((inputs && timestamps) || num_perms == 0), "null argument");
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    // num_rows = max(24 * len, min_rows).next_power_of_two()   (keccak_stark.rs:76-78)
+    ZK_REQUIRE(num_perms <= ((size_t)1 << 40) && min_rows <= ((size_t)1 << 40), "too many rows");
+    size_t want = num_perms * zkstark::keccak::NUM_ROUNDS;
+    if (want < min_rows) want = min_rows;
+    size_t n = 1;
+    while (n < want) n <<= 1;
+    std::unique_ptr<zkgpu_dev_trace> t(new zkgpu_dev_trace());
+    t->ncols = zkstark::keccak::NUM_COLUMNS;
+    t->n = n;
+    t->buf = DevBuf(&c, t->ncols * n * 8);
+    DevBuf in(&c, (num_perms ? num_perms : 1) * 26 * 8);      // 25 input words per permutation, then the timestamps
+    if (num_perms) {
+        c.h2d(in.get(), inputs, num_perms * 25 * 8);
+        c.h2d(in.get() + num_perms * 25, timestamps, num_perms * 8);
+    }
+    {
+        KernelScope ks(c, KF_TRACE_GEN, 8.0 * (double)t->ncols * (double)n + 208.0 * (double)num_perms);
+        const unsigned T = 128;
+        keccak_trace_kernel<<<(unsigned)((n + T - 1) / T), T, 0, c.stream>>>(in.get(), in.get() + num_perms * 25, num_perms, n, t->buf.get());
+        c.count_launch();
+        c.check_launch("keccak_trace_kernel");
+    }
+    // `in` is released in stream order (after the kernel); pageable inputs were staged synchronously by h2d
+    *out = t.release();
+    ZK_API_END
+}
+
+int zkgpu_dev_trace_dims(const zkgpu_dev_trace* t, size_t* ncols, size_t* n) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(t, "null argument");
+    if (ncols) *ncols = t->ncols;
+    if (n) *n = t->n;
+    ZK_API_END
+}
+
+const uint64_t* zkgpu_dev_trace_ptr(const zkgpu_dev_trace* t) { return t ? t->buf.get() : nullptr; }
+
+int zkgpu_dev_trace_export(const zkgpu_dev_trace* t, uint64_t* host_out) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(t && host_out, "null argument");
+    zk::Ctx& c = *t->buf.ctx;
+    ZK_CUDA(cudaSetDevice(c.device));
+    c.d2h(host_out, t->buf.get(), t->ncols * t->n * 8);
+    ZK_API_END
+}
+
+void zkgpu_dev_trace_free(zkgpu_dev_trace* t) {
+    if (!t) return;
+    if (t->buf.ctx) cudaSetDevice(t->buf.ctx->device);
+    delete t;
+}
+
+}  // extern "C"

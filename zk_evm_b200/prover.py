@@ -229,6 +229,48 @@ class StarkProof:
             pass
 
 
+class DeviceTrace:
+    """A table's trace finished in device memory (zkgpu_dev_trace): ncols x n, column-major.  Goes into `prove_with_traces` /
+    `upload_traces` in place of a host array, or into PolynomialBatch.from_device_values via `device_ptr`."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+        ctx._children.add(self)
+        nc, n = C.c_size_t(), C.c_size_t()
+        check(lib().zkgpu_dev_trace_dims(self._h, C.byref(nc), C.byref(n)))
+        self.ncols, self.n = nc.value, n.value
+        self.device_ptr = int(lib().zkgpu_dev_trace_ptr(self._h) or 0)
+
+    def export(self):
+        out = np.empty((self.ncols, self.n), dtype=np.uint64)
+        check(lib().zkgpu_dev_trace_export(self._h, _ptr(out)))
+        return out
+
+    def free(self):
+        if self._h:
+            lib().zkgpu_dev_trace_free(self._h)
+            self._h = C.c_void_p()
+            self.device_ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def keccak_generate_trace(ctx, inputs, timestamps, min_rows=0):
+    """KeccakStark::generate_trace on the device (keccak_stark.rs:70-250): inputs (num_perms, 25) uint64 (lane y*5 + x), one timestamp
+    per permutation -> DeviceTrace of 2431 columns x max(24 * num_perms, min_rows).next_power_of_two() rows."""
+    a = np.ascontiguousarray(inputs, dtype=np.uint64).reshape(-1, 25)
+    ts = np.ascontiguousarray(timestamps, dtype=np.uint64).ravel()
+    if ts.size != a.shape[0]:
+        raise ValueError("one timestamp per permutation")
+    h = C.c_void_p()
+    check(lib().zkgpu_keccak_generate_trace(ctx._h, _ptr(a), _ptr(ts), C.c_size_t(a.shape[0]), C.c_size_t(min_rows), C.byref(h)))
+    return DeviceTrace(ctx, h)
+
+
 def table_info(table, num_challenges):
     a, b, c_, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
     check(lib().zkgpu_table_info(C.c_uint32(table), C.c_uint32(num_challenges), C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))

@@ -104,6 +104,14 @@ def _trace_array(traces, device_ptrs, config):
                 arr[t].cols = C.cast(C.c_void_p(int(device_ptrs[t][0])), u64p)
                 arr[t].n = int(device_ptrs[t][1])
                 in_use[t] = True
+        elif isinstance(traces[t], _p.DeviceTrace):      # finished on the device (keccak_generate_trace)
+            info = _p.table_info(t, config.num_challenges)
+            if traces[t].ncols != info["num_columns"]:
+                raise ValueError("table %s: expected %d columns" % (TABLE_NAMES[t], info["num_columns"]))
+            keep.append(traces[t])
+            arr[t].cols = C.cast(C.c_void_p(traces[t].device_ptr), u64p)
+            arr[t].n = traces[t].n
+            in_use[t] = True
         elif traces[t] is not None:
             a = np.ascontiguousarray(traces[t], dtype=np.uint64)
             info = _p.table_info(t, config.num_challenges)
@@ -137,16 +145,24 @@ class SegmentUpload:
             pass
 
 
+def _mem_kind(traces, device_ptrs):
+    """ZKGPU_MEM_DEVICE for device_ptrs, ZKGPU_MEM_AUTO when a DeviceTrace sits among host arrays, else ZKGPU_MEM_HOST"""
+    if device_ptrs is not None:
+        return 1
+    return 2 if any(isinstance(t, _p.DeviceTrace) for t in traces) else 0
+
+
 def upload_traces(ctx, traces, config, device_ptrs=None):
     arr, keep, in_use = _trace_array(traces, device_ptrs, config)
     h = C.c_void_p()
-    check(lib().zkgpu_segment_upload(ctx._h, arr, 1 if device_ptrs is not None else 0, C.byref(config), C.byref(h)))
+    check(lib().zkgpu_segment_upload(ctx._h, arr, _mem_kind(traces, device_ptrs), C.byref(config), C.byref(h)))
     return SegmentUpload(ctx, h, keep, in_use)
 
 
 def prove_with_traces(ctx, traces, public_values, config, labels=None, forced_pow_witnesses=None, abort_flag=None, device_ptrs=None,
                       upload=None):
-    """prove_with_traces on one device.  traces: list of 9 (ncols, n) uint64 arrays, None for an optional table not in use.
+    """prove_with_traces on one device.  traces: list of 9 (ncols, n) uint64 arrays (or DeviceTrace objects: traces finished on the
+    device, e.g. keccak_generate_trace), None for an optional table not in use.
     device_ptrs: instead of host arrays, list of 9 (device address, n) or None (traces already resident in HBM).
     upload: a SegmentUpload made earlier by upload_traces (consumed by this call) instead of traces / device_ptrs."""
     pv = np.ascontiguousarray(public_values, dtype=np.uint64).ravel()
@@ -164,7 +180,7 @@ def prove_with_traces(ctx, traces, public_values, config, labels=None, forced_po
             upload.free()
     else:
         arr, keep, in_use = _trace_array(traces, device_ptrs, config)
-        check(lib().zkgpu_prove_segment(ctx._h, arr, 1 if device_ptrs is not None else 0, *tail))
+        check(lib().zkgpu_prove_segment(ctx._h, arr, _mem_kind(traces, device_ptrs), *tail))
     proofs = []
     for t in range(NUM_TABLES):
         if outs[t]:
