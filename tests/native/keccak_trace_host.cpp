@@ -1,8 +1,9 @@
-// Host build of the single-source Keccak row generator (zk_evm_b200/csrc/stark/keccak_trace.h) for tests/test_trace_gen_host.py:
+// Host build of the single-source Keccak / Logic row generators (zk_evm_b200/csrc/stark/{keccak,logic}_trace.h) for tests/test_trace_gen_host.py:
 // the same code the device kernel keccak_trace_kernel runs, one "thread" per row, writing the column-major trace.
 #include <stdint.h>
 #include <stddef.h>
 #include "stark/keccak_trace.h"
+#include "stark/logic_trace.h"
 
 struct HostStore {
     uint64_t* out; size_t n; uint32_t count;
@@ -22,3 +23,14 @@ extern "C" uint32_t keccak_trace_rows(const uint64_t* inputs, const uint64_t* ti
 }
 
 extern "C" void keccak_permutation_output(const uint64_t* input, uint64_t* out) { zkstark::keccak::permutation_output(input, out); }
+
+extern "C" uint32_t logic_trace_rows(const uint64_t* ops, uint64_t num_ops, size_t n, uint64_t* out) {
+    uint32_t cells = 0;
+    for (size_t row = 0; row < n; row++) {
+        HostStore st{out + row, n, 0};
+        zkstark::logic::generate_row(ops, num_ops, row, st);
+        if (row && st.count != cells) return 0;
+        cells = st.count;
+    }
+    return cells;
+}

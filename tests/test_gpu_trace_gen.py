@@ -1,6 +1,6 @@
 """GPU parity of the device-side trace finishing: zkgpu_keccak_generate_trace == the restated
-KeccakStark::generate_trace (keccak_stark.rs:70-250; tests/traces.py), bit for bit, and a segment proved from the device-resident
-Keccak trace next to host traces of the other tables (ZKGPU_MEM_AUTO) == the oracle's proofs from the host trace."""
+KeccakStark::generate_trace (keccak_stark.rs:70-250; tests/traces.py) and zkgpu_logic_generate_trace == LogicStark::generate_trace
+(logic.rs:165-237), bit for bit, and a segment proved from the device-resident Keccak / Logic traces next to host traces of the other tables (ZKGPU_MEM_AUTO) == the oracle's proofs from the host trace."""
 import numpy as np
 import pytest
 from tests import traces
@@ -24,20 +24,42 @@ def test_keccak_trace_matches_reference_restatement(ctx, nperm, min_rows, log_n)
     assert np.array_equal(got, want)
 
 
-def test_segment_from_device_finished_keccak_trace(ctx, oracle):
+@pytest.mark.parametrize("nops,min_rows,log_n", [(1, 0, 0), (5, 0, 3), (200, 0, 8), (3, 64, 6), (0, 4, 2), (5000, 0, 13)])
+def test_logic_trace_matches_reference_restatement(ctx, nops, min_rows, log_n):
+    ops = traces.logic_ops(nops, 400 + nops)
+    dt = zk.logic_generate_trace(ctx, ops, min_rows)
+    assert (dt.ncols, dt.n) == (523, 1 << log_n)
+    got = dt.export()
+    dt.free()
+    assert np.array_equal(got, traces.logic_trace_from_ops(log_n, ops))
+
+
+def test_logic_trace_rejects_unknown_operator(ctx):
+    ops = traces.logic_ops(4, 1)
+    ops[2, 0] = 3
+    with pytest.raises(zk.ZkGpuError):
+        zk.logic_generate_trace(ctx, ops)
+
+
+def test_segment_from_device_finished_keccak_and_logic_traces(ctx, oracle):
     rng = np.random.default_rng(9)
     inputs = rng.integers(0, 1 << 64, size=(5, 25), dtype=np.uint64)
     ts = np.arange(1, 6, dtype=np.uint64) * np.uint64(7)
     tr = traces.valid_segment(seed=13, k=17)
     host_keccak, _ = traces.keccak_trace(7, inputs, ts)
     cfg = zk.StarkConfig(*TEST_CONFIG)
+    ops = traces.logic_ops(50, 2)
     dt = zk.keccak_generate_trace(ctx, inputs, ts)
+    dl = zk.logic_generate_trace(ctx, ops)
     tr_dev = list(tr)
     tr_dev[traces.T_KECCAK] = dt
+    tr_dev[traces.T_LOGIC] = dl
     ap = zk.prove_with_traces(ctx, tr_dev, PUBLIC_VALUES, cfg, zk.KernelLabels(*DEFAULT_LABELS))
     dt.free()
+    dl.free()
     tr_host = list(tr)
     tr_host[traces.T_KECCAK] = host_keccak
+    tr_host[traces.T_LOGIC] = traces.logic_trace_from_ops(6, ops)
     want, bg, caps = orc_prove_segment(oracle, TEST_CONFIG, tr_host, PUBLIC_VALUES)
     assert np.array_equal(ap.ctl_challenges, bg) and np.array_equal(ap.trace_caps, caps)
     for t in range(9):

@@ -427,7 +427,7 @@ def test_keccak_trace_kernel_rows():
     from tests import traces
     src = os.path.join(CSRC, "trace_gen.cu")
     ptx = os.path.join(HERE, "native", "trace_gen.ptx")
-    deps = [src, os.path.join(CSRC, "stark", "keccak_trace.h"), os.path.join(CSRC, "stark", "table_keccak.h")]
+    deps = [src] + [os.path.join(CSRC, "stark", f) for f in ("keccak_trace.h", "table_keccak.h", "logic_trace.h", "table_logic.h")]
     if not os.path.exists(ptx) or any(os.path.getmtime(d) > os.path.getmtime(ptx) for d in deps):
         subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", CSRC, "-ptx", "-o", ptx, src])
     emu = PtxEmu(open(ptx).read())
@@ -445,3 +445,25 @@ def test_keccak_trace_kernel_rows():
         got = [mem.get(TR + 8 * (c * n + row)) for c in range(2431)]
         assert got == [int(v) for v in want[:, row]], row
     assert len([a for a in mem if a >= TR]) == 9 * 2431      # nothing written outside the rows' own cells
+
+
+def test_logic_trace_kernel_rows():
+    """logic_trace_kernel (csrc/trace_gen.cu, as PTX), one thread = one row: the three operators and a padding row"""
+    from ptx_emu import PtxEmu
+    from tests import traces
+    src = os.path.join(CSRC, "trace_gen.cu")
+    ptx = os.path.join(HERE, "native", "trace_gen.ptx")
+    deps = [src] + [os.path.join(CSRC, "stark", f) for f in ("keccak_trace.h", "table_keccak.h", "logic_trace.h", "table_logic.h")]
+    if not os.path.exists(ptx) or any(os.path.getmtime(d) > os.path.getmtime(ptx) for d in deps):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", CSRC, "-ptx", "-o", ptx, src])
+    emu = PtxEmu(open(ptx).read())
+    nops, log_n = 6, 3
+    n = 1 << log_n
+    ops = traces.logic_ops(nops, 77)
+    ops[:3, 0] = [0, 1, 2]
+    want = traces.logic_trace_from_ops(log_n, ops)
+    TR = 0x100000000
+    mem = {IN + 8 * i: int(w) for i, w in enumerate(ops.ravel())}
+    for row in (0, 1, 2, 5, 6, 7):
+        emu.run("logic_trace_kernel", [IN, nops, n, TR], mem, tid=row, ctaid=0, ntid=128)
+        assert [mem.get(TR + 8 * (c * n + row)) for c in range(523)] == [int(v) for v in want[:, row]], row

@@ -22,11 +22,12 @@ u64p = C.POINTER(C.c_uint64)
 def host():
     src = os.path.join(HERE, "native", "keccak_trace_host.cpp")
     lib = os.path.join(HERE, "native", "libkeccak_trace_host.so")
-    deps = [src, os.path.join(CSRC, "stark", "keccak_trace.h"), os.path.join(CSRC, "stark", "table_keccak.h")]
+    deps = [src] + [os.path.join(CSRC, "stark", f) for f in ("keccak_trace.h", "table_keccak.h", "logic_trace.h", "table_logic.h")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", CSRC, "-o", lib, src])
     h = C.CDLL(lib)
     h.keccak_trace_rows.restype = C.c_uint32
+    h.logic_trace_rows.restype = C.c_uint32
     return h
 
 
@@ -74,5 +75,36 @@ def test_generated_keccak_trace_proves_and_verifies(host):
     st0 = np.arange(12, dtype=np.uint64)
     proof, st = oracle_lib.orc_prove_table(orc, traces.T_KECCAK, oracle_lib.TEST_CONFIG, tr, bg, st0)
     ok, err, st2 = oracle_lib.orc_verify_table(orc, traces.T_KECCAK, oracle_lib.TEST_CONFIG, proof, bg, st0)
+    assert ok, err
+    assert np.array_equal(st, st2)
+
+
+# ---- LogicStark ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nops,log_n", [(1, 0), (5, 3), (200, 8), (0, 2)])
+def test_logic_rows_match_reference_restatement(host, nops, log_n):
+    ops = traces.logic_ops(nops, 50 + nops)
+    n = 1 << log_n
+    out = np.full((523, n), 0xDEADBEEF, dtype=np.uint64)
+    assert host.logic_trace_rows(ops.ctypes.data_as(u64p), C.c_uint64(nops), C.c_size_t(n), out.ctypes.data_as(u64p)) == 523
+    assert np.array_equal(out, traces.logic_trace_from_ops(log_n, ops))
+    # and operation by operation against Python integers (Op::result, logic.rs:131-139)
+    for i in range(min(nops, 20)):
+        a = sum(int(ops[i, 1 + l]) << (64 * l) for l in range(4))
+        b = sum(int(ops[i, 5 + l]) << (64 * l) for l in range(4))
+        r = (a & b, a | b, a ^ b)[int(ops[i, 0])]
+        assert sum(int(out[515 + k, i]) << (32 * k) for k in range(8)) == r
+        assert sum(int(out[3 + k, i]) << k for k in range(256)) == a and sum(int(out[259 + k, i]) << k for k in range(256)) == b
+
+
+def test_generated_logic_trace_proves_and_verifies(host):
+    from tests import oracle_lib
+    orc = oracle_lib.load()
+    ops = traces.logic_ops(40, 3)
+    out = np.zeros((523, 64), dtype=np.uint64)
+    assert host.logic_trace_rows(ops.ctypes.data_as(u64p), C.c_uint64(40), C.c_size_t(64), out.ctypes.data_as(u64p)) == 523
+    bg = np.array([11, 22], dtype=np.uint64)
+    st0 = np.arange(12, dtype=np.uint64)
+    proof, st = oracle_lib.orc_prove_table(orc, traces.T_LOGIC, oracle_lib.TEST_CONFIG, out, bg, st0)
+    ok, err, st2 = oracle_lib.orc_verify_table(orc, traces.T_LOGIC, oracle_lib.TEST_CONFIG, proof, bg, st0)
     assert ok, err
     assert np.array_equal(st, st2)

@@ -46,6 +46,32 @@ def logic_trace(log_n, seed, fill=0.8):
     return t
 
 
+def logic_ops(nops, seed):
+    """random operations in the layout zkgpu_logic_generate_trace takes: (nops, 9) uint64 = operator, input0 limbs, input1 limbs"""
+    rng = np.random.default_rng(seed)
+    ops = rng.integers(0, 1 << 64, size=(nops, 9), dtype=np.uint64)
+    ops[:, 0] = rng.integers(0, 3, size=nops).astype(np.uint64)
+    return ops
+
+
+def logic_trace_from_ops(log_n, ops):
+    """LogicStark::generate_trace (logic.rs:165-237) from explicit operations (same layout as logic_ops)"""
+    ops = np.ascontiguousarray(ops, dtype=np.uint64).reshape(-1, 9)
+    n, nops = 1 << log_n, ops.shape[0]
+    assert nops <= n
+    t = np.zeros((523, n), dtype=np.uint64)
+    for k in range(3):
+        t[k, :nops] = (ops[:, 0] == k)
+    for l in range(4):
+        a, b = ops[:, 1 + l], ops[:, 5 + l]
+        t[3 + 64 * l:3 + 64 * l + 64, :nops] = _bits(a)
+        t[259 + 64 * l:259 + 64 * l + 64, :nops] = _bits(b)
+        r = np.where(ops[:, 0] == 0, a & b, np.where(ops[:, 0] == 1, a | b, a ^ b))
+        t[515 + 2 * l, :nops] = r & np.uint64(0xFFFFFFFF)
+        t[515 + 2 * l + 1, :nops] = r >> np.uint64(32)
+    return t
+
+
 def memory_trace_simple(log_n):
     """A valid MemoryStark trace made of dummy reads at (0, 0, r), timestamp 0: every ordering, initialisation and
     range-check constraint holds with range_check == 0 and all frequencies on counter 0."""

@@ -5,11 +5,14 @@
 // Replaces /root/reference/evm_arithmetization/src/keccak/keccak_stark.rs:70-250 (KeccakStark::generate_trace: generate_trace_rows +
 // trace_rows_to_poly_values), called from witness/traces.rs:243-258 (`into_tables`).  The row code is stark/keccak_trace.h (host + device).
 //
+// and src/logic.rs:165-237 (LogicStark::generate_trace: 523 columns from 72 bytes per operation; stark/logic_trace.h).
+//
 // keccak_trace_kernel: one thread per trace ROW.  Rows are independent given the permutation's input (keccak_trace.h), the trace is
 // column-major, so a warp stores 32 consecutive rows of one column per instruction: 256 contiguous bytes.  Write-bound: 8 * 2431 bytes per
 // row against ~1.5 k word operations; algorithmic bytes = 8 * 2431 * n written + 208 * num_perms read.
 #include "internal.h"
 #include "stark/keccak_trace.h"
+#include "stark/logic_trace.h"
 
 namespace zk {
 
@@ -24,6 +27,21 @@ __global__ void __launch_bounds__(128) keccak_trace_kernel(const uint64_t* __res
     if (row >= n) return;
     ColStore st{out + row, n};
     zkstark::keccak::generate_row(inputs, timestamps, num_perms, row, st);
+}
+
+// logic_trace_kernel: one thread per row as well (each row is one operation); 8 * 523 bytes written per row
+__global__ void __launch_bounds__(128) logic_trace_kernel(const uint64_t* __restrict__ ops, uint64_t num_ops, size_t n, uint64_t* __restrict__ out) {
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    ColStore st{out + row, n};
+    zkstark::logic::generate_row(ops, num_ops, row, st);
+}
+
+static size_t padded_rows(size_t rows, size_t min_rows) {
+    ZK_REQUIRE(rows <= ((size_t)1 << 40) && min_rows <= ((size_t)1 << 40), "too many rows");
+    size_t want = rows < min_rows ? min_rows : rows, n = 1;
+    while (n < want) n <<= 1;
+    return n;
 }
 
 }  // namespace zk
@@ -43,11 +61,8 @@ int zkgpu_keccak_generate_trace(zkgpu_ctx* h, const uint64_t* inputs, const uint
     Ctx& c = h->c;
     ZK_CUDA(cudaSetDevice(c.device));
     // num_rows = max(24 * len, min_rows).next_power_of_two()   (keccak_stark.rs:76-78)
-    ZK_REQUIRE(num_perms <= ((size_t)1 << 40) && min_rows <= ((size_t)1 << 40), "too many rows");
-    size_t want = num_perms * zkstark::keccak::NUM_ROUNDS;
-    if (want < min_rows) want = min_rows;
-    size_t n = 1;
-    while (n < want) n <<= 1;
+    ZK_REQUIRE(num_perms <= ((size_t)1 << 40), "too many rows");
+    const size_t n = padded_rows(num_perms * zkstark::keccak::NUM_ROUNDS, min_rows);
     std::unique_ptr<zkgpu_dev_trace> t(new zkgpu_dev_trace());
     t->ncols = zkstark::keccak::NUM_COLUMNS;
     t->n = n;
@@ -65,6 +80,33 @@ int zkgpu_keccak_generate_trace(zkgpu_ctx* h, const uint64_t* inputs, const uint
         c.check_launch("keccak_trace_kernel");
     }
     // `in` is released in stream order (after the kernel); pageable inputs were staged synchronously by h2d
+    *out = t.release();
+    ZK_API_END
+}
+
+int zkgpu_logic_generate_trace(zkgpu_ctx* h, const uint64_t* ops, size_t num_ops, size_t min_rows, zkgpu_dev_trace** out) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(h && out && (ops || num_ops == 0), "null argument");
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    const size_t W = zkstark::logic::OP_WORDS;
+    for (size_t i = 0; i < num_ops; i++) ZK_REQUIRE(ops[i * W] <= 2, "operator must be 0 (AND), 1 (OR) or 2 (XOR)");
+    // padded_len = len.max(min_rows).next_power_of_two()   (logic.rs:218-220)
+    const size_t n = padded_rows(num_ops, min_rows);
+    std::unique_ptr<zkgpu_dev_trace> t(new zkgpu_dev_trace());
+    t->ncols = zkstark::logic::NUM_COLUMNS;
+    t->n = n;
+    t->buf = DevBuf(&c, t->ncols * n * 8);
+    DevBuf in(&c, (num_ops ? num_ops : 1) * W * 8);
+    if (num_ops) c.h2d(in.get(), ops, num_ops * W * 8);
+    {
+        KernelScope ks(c, KF_TRACE_GEN, 8.0 * (double)t->ncols * (double)n + 8.0 * W * (double)num_ops);
+        const unsigned T = 128;
+        logic_trace_kernel<<<(unsigned)((n + T - 1) / T), T, 0, c.stream>>>(in.get(), num_ops, n, t->buf.get());
+        c.count_launch();
+        c.check_launch("logic_trace_kernel");
+    }
     *out = t.release();
     ZK_API_END
 }

@@ -271,6 +271,15 @@ def keccak_generate_trace(ctx, inputs, timestamps, min_rows=0):
     return DeviceTrace(ctx, h)
 
 
+def logic_generate_trace(ctx, ops, min_rows=0):
+    """LogicStark::generate_trace on the device (logic.rs:165-237): ops (num_ops, 9) uint64 = operator (0 AND, 1 OR, 2 XOR), input0 and
+    input1 as 4 little-endian u64 limbs each -> DeviceTrace of 523 columns x max(num_ops, min_rows).next_power_of_two() rows."""
+    a = np.ascontiguousarray(ops, dtype=np.uint64).reshape(-1, 9)
+    h = C.c_void_p()
+    check(lib().zkgpu_logic_generate_trace(ctx._h, _ptr(a), C.c_size_t(a.shape[0]), C.c_size_t(min_rows), C.byref(h)))
+    return DeviceTrace(ctx, h)
+
+
 def table_info(table, num_challenges):
     a, b, c_, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
     check(lib().zkgpu_table_info(C.c_uint32(table), C.c_uint32(num_challenges), C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
