@@ -152,7 +152,35 @@ def run_ours(args):
     backend = zk.ZkGpuBackend(ctx, cfg, labels)
     d2h = [0]
 
+    # --finish-on-device: the Keccak and Logic traces (72 % of a segment's bytes) are not uploaded but finished on the device from the
+    # permutation inputs / operations (zkgpu_keccak_generate_trace, zkgpu_logic_generate_trace), inside the timed region
+    T_KECCAK, T_LOGIC = 3, 5
+    fin_rng = np.random.default_rng(40 + rank)
+    fin_keccak = fin_logic = None
+    if args.finish_on_device and not sharded:
+        if mine[T_KECCAK]:
+            nperm = (1 << log_ns[T_KECCAK]) // 24
+            fin_keccak = (fin_rng.integers(0, 1 << 64, size=(nperm, 25), dtype=np.uint64), np.arange(1, nperm + 1, dtype=np.uint64))
+        if mine[T_LOGIC]:
+            fin_logic = fin_rng.integers(0, 1 << 64, size=(1 << log_ns[T_LOGIC], 9), dtype=np.uint64)
+            fin_logic[:, 0] %= np.uint64(3)
+    fin_h2d_bytes = h2d_bytes - sum(8 * NUM_COLUMNS[t] * (1 << log_ns[t]) for t, f in ((T_KECCAK, fin_keccak), (T_LOGIC, fin_logic)) if f is not None) \
+        + (fin_keccak[0].nbytes + fin_keccak[1].nbytes if fin_keccak is not None else 0) + (fin_logic.nbytes if fin_logic is not None else 0)
+
     def one_segment(cx, host):
+        if host == 2:
+            tr, made = list(host_traces), []
+            if fin_keccak is not None:
+                tr[T_KECCAK] = zk.keccak_generate_trace(cx, fin_keccak[0], fin_keccak[1], 1 << log_ns[T_KECCAK])
+                made.append(tr[T_KECCAK])
+            if fin_logic is not None:
+                tr[T_LOGIC] = zk.logic_generate_trace(cx, fin_logic, 1 << log_ns[T_LOGIC])
+                made.append(tr[T_LOGIC])
+            try:
+                return zk.prove_with_traces(cx, tr, PUBLIC_VALUES, cfg, labels)
+            finally:
+                for m in made:
+                    m.free()
         if host:
             return zk.prove_with_traces(cx, host_traces, PUBLIC_VALUES, cfg, labels)
         return zk.prove_with_traces(cx, None, PUBLIC_VALUES, cfg, labels, device_ptrs=ptrs)
@@ -171,7 +199,7 @@ def run_ours(args):
         """`steps` segment proofs back to back on one context.  Host traces: the uploads of segment s+1 are queued before segment s is
         proved (zkgpu_segment_upload / zkgpu_prove_segment_uploaded), so every H2D chain but the first runs under the previous proof."""
         r = None
-        if host and not sharded and args.prefetch:
+        if host == 1 and not sharded and args.prefetch:
             nxt = zk.upload_traces(cx, host_traces, cfg)
             for k in range(steps):
                 cur, nxt = nxt, (zk.upload_traces(cx, host_traces, cfg) if k + 1 < steps else None)
@@ -264,6 +292,10 @@ def run_ours(args):
     zk._lib.check(zk.lib().zkgpu_ctx_set_profiling(ctx._h, 0))
     run_steps(True, min(args.warmup, 1))
     e_ms, e_wall = timed(True, args.steps)
+    f_ms = f_wall = None
+    if args.finish_on_device and not sharded:
+        run_steps(2, min(args.warmup, 1))
+        f_ms, f_wall = timed(2, args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -318,6 +350,11 @@ def run_ours(args):
                 "e2e": {"value": segs / (e_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": h2d_bytes * nstreams, "d2h_bytes_per_step": d2h[0],
                         "ms_per_step": e_ms / args.steps, "wall_ms_per_step": e_wall / args.steps},
                 "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
+        if f_ms is not None:
+            line["e2e_finish_on_device"] = {"value": segs / (f_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": fin_h2d_bytes * nstreams,
+                                            "ms_per_step": f_ms / args.steps, "wall_ms_per_step": f_wall / args.steps,
+                                            "what": "as e2e, but the Keccak and Logic traces are finished on the device from permutation inputs / operations "
+                                                    "(generation inside the timed region) instead of being uploaded"}
     for cx in ctxs:
         cx.close()
     if dist is not None:
@@ -406,6 +443,8 @@ def main():
                          "(profiles/r1w): upload-ahead is slower on this box (3 streams 2.94 vs 3.87 proofs/s), the per-call upload chain "
                          "already hides under the other segments' kernels")
     ap.add_argument("--stagger-ms", type=float, default=80.0, help="start offset between the segment streams of a GPU (inside the timed region)")
+    ap.add_argument("--finish-on-device", action="store_true",
+                    help="extra e2e leg: Keccak / Logic traces finished on the device from their inputs instead of uploaded (e2e_finish_on_device)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiler runs)")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not bracket kernel families with CUDA events")
     args = ap.parse_args()
