@@ -90,7 +90,8 @@ int zkgpu_ctx_stats(zkgpu_ctx* ctx, uint64_t* kernel_launches, uint64_t* bytes_i
  * events on the context's stream (the stream the kernels run on) and accounted with its ALGORITHMIC bytes.
  * family: 0 leaf_hash (Poseidon sponge over LDE rows), 1 merkle inner levels, 2 NTT / LDE passes, 3 quotient evaluation,
  * 4 CTL + lookup auxiliary columns, 5 openings, 6 FRI combine / fold / layer leaves, 7 proof-of-work grind,
- * 8 device-side trace finishing (zkgpu_keccak_generate_trace, zkgpu_logic_generate_trace). */
+ * 8 device-side trace finishing (zkgpu_keccak_generate_trace, zkgpu_logic_generate_trace,
+ * zkgpu_arithmetic_generate_range_checks). */
 enum { ZKGPU_KF_LEAF_HASH = 0, ZKGPU_KF_MERKLE_LEVELS, ZKGPU_KF_NTT, ZKGPU_KF_QUOTIENT, ZKGPU_KF_AUX, ZKGPU_KF_OPENINGS, ZKGPU_KF_FRI,
        ZKGPU_KF_POW, ZKGPU_KF_TRACE_GEN, ZKGPU_KF_COUNT };
 int zkgpu_ctx_set_profiling(zkgpu_ctx* ctx, int on);   /* on: also resets the counters */
@@ -223,6 +224,13 @@ int zkgpu_keccak_generate_trace(zkgpu_ctx* ctx, const uint64_t* inputs, const ui
 /* LogicStark::generate_trace (logic.rs:165-237): `ops` = num_ops x 9 words (host): operator (0 AND, 1 OR, 2 XOR), input0 and input1 as 4
  * little-endian u64 limbs each (U256).  523 columns x n rows, n = max(num_ops, min_rows).next_power_of_two(), padding rows zero. */
 int zkgpu_logic_generate_trace(zkgpu_ctx* ctx, const uint64_t* ops, size_t num_ops, size_t min_rows, zkgpu_dev_trace** out);
+/* A host trace (ncols x n contiguous column-major words) moved to the device as a zkgpu_dev_trace, for the in-place finishing steps */
+int zkgpu_dev_trace_upload(zkgpu_ctx* ctx, const uint64_t* cols, size_t ncols, size_t n, zkgpu_dev_trace** out);
+/* ArithmeticStark::generate_range_checks (arithmetic/arithmetic_stark.rs:130-156) in place on a device-resident Arithmetic trace
+ * (116 columns x n >= 2^16 rows, as generate_trace pads it): RANGE_COUNTER[i] = min(i, 2^16 - 1); RC_FREQUENCIES[x] = number of cells
+ * of the 96 shared columns equal to x.  What the two columns held before is ignored.  ZKGPU_ERR_INVALID if a shared cell is >= 2^16
+ * (the reference asserts). */
+int zkgpu_arithmetic_generate_range_checks(zkgpu_ctx* ctx, zkgpu_dev_trace* trace);
 int zkgpu_dev_trace_dims(const zkgpu_dev_trace* t, size_t* ncols, size_t* n);
 const uint64_t* zkgpu_dev_trace_ptr(const zkgpu_dev_trace* t);             /* device address of column 0 (column c at + c*n) */
 int zkgpu_dev_trace_export(const zkgpu_dev_trace* t, uint64_t* host_out);  /* ncols * n words (parity tests) */

@@ -41,6 +41,31 @@ def test_logic_trace_rejects_unknown_operator(ctx):
         zk.logic_generate_trace(ctx, ops)
 
 
+@pytest.mark.parametrize("log_n", [16, 17])
+def test_arithmetic_range_checks_match_reference_restatement(ctx, log_n):
+    want = traces.arithmetic_addcy_trace(log_n, seed=log_n, nops=3000)
+    tr = want.copy()
+    tr[114] = 12345          # whatever the two columns held is ignored
+    tr[115] = 678
+    dt = zk.arithmetic_generate_range_checks(ctx, zk.upload_trace(ctx, tr))
+    got = dt.export()
+    dt.free()
+    assert np.array_equal(got, want)
+
+
+def test_arithmetic_range_checks_reject_large_values_and_short_traces(ctx):
+    tr = traces.arithmetic_addcy_trace(16, seed=1, nops=10)
+    tr[40, 999] = 1 << 16
+    dt = zk.upload_trace(ctx, tr)
+    with pytest.raises(zk.ZkGpuError):
+        zk.arithmetic_generate_range_checks(ctx, dt)
+    dt.free()
+    dt = zk.upload_trace(ctx, np.zeros((116, 1 << 10), dtype=np.uint64))
+    with pytest.raises(zk.ZkGpuError):
+        zk.arithmetic_generate_range_checks(ctx, dt)
+    dt.free()
+
+
 def test_segment_from_device_finished_keccak_and_logic_traces(ctx, oracle):
     rng = np.random.default_rng(9)
     inputs = rng.integers(0, 1 << 64, size=(5, 25), dtype=np.uint64)
@@ -51,12 +76,15 @@ def test_segment_from_device_finished_keccak_and_logic_traces(ctx, oracle):
     ops = traces.logic_ops(50, 2)
     dt = zk.keccak_generate_trace(ctx, inputs, ts)
     dl = zk.logic_generate_trace(ctx, ops)
+    da = zk.arithmetic_generate_range_checks(ctx, zk.upload_trace(ctx, tr[traces.T_ARITHMETIC]))
     tr_dev = list(tr)
+    tr_dev[traces.T_ARITHMETIC] = da
     tr_dev[traces.T_KECCAK] = dt
     tr_dev[traces.T_LOGIC] = dl
     ap = zk.prove_with_traces(ctx, tr_dev, PUBLIC_VALUES, cfg, zk.KernelLabels(*DEFAULT_LABELS))
     dt.free()
     dl.free()
+    da.free()
     tr_host = list(tr)
     tr_host[traces.T_KECCAK] = host_keccak
     tr_host[traces.T_LOGIC] = traces.logic_trace_from_ops(6, ops)

@@ -467,3 +467,38 @@ def test_logic_trace_kernel_rows():
     for row in (0, 1, 2, 5, 6, 7):
         emu.run("logic_trace_kernel", [IN, nops, n, TR], mem, tid=row, ctaid=0, ntid=128)
         assert [mem.get(TR + 8 * (c * n + row)) for c in range(523)] == [int(v) for v in want[:, row]], row
+
+
+def test_arithmetic_range_check_kernels():
+    """arith_rc_init_kernel + arith_rc_hist_kernel (csrc/trace_gen.cu, as PTX): every thread of a small grid, one after the other, against
+    ArithmeticStark::generate_range_checks restated with numpy (arithmetic_stark.rs:130-156); a cell >= 2^16 raises the flag."""
+    from ptx_emu import PtxEmu
+    src = os.path.join(CSRC, "trace_gen.cu")
+    ptx = os.path.join(HERE, "native", "trace_gen.ptx")
+    if not os.path.exists(ptx) or os.path.getmtime(src) > os.path.getmtime(ptx):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", CSRC, "-ptx", "-o", ptx, src])
+    emu = PtxEmu(open(ptx).read())
+    rng = np.random.default_rng(3)
+    cells = 300
+    vals = rng.integers(0, 1 << 16, size=cells, dtype=np.uint64)
+    vals[rng.integers(0, cells, size=120)] = 0                     # sparse, as real traces are
+    vals[:4] = [65535, 1, 1, 65535]
+    FREQ, BAD = 0x200000000, 0x300000000
+    mem = {IN + 8 * i: int(v) for i, v in enumerate(vals)}
+    mem[BAD] = 0
+    ntid, nblocks = 8, 3
+    for b in range(nblocks):
+        for t in range(ntid):
+            emu.run("arith_rc_hist_kernel", [IN, cells, FREQ, BAD], mem, tid=t, ctaid=b, ntid=ntid, nctaid=nblocks)
+    want = np.bincount(vals.astype(np.int64), minlength=1 << 16)
+    assert all(mem.get(FREQ + 8 * x, 0) == int(want[x]) for x in range(1 << 16))
+    assert mem[BAD] == 0
+    mem[IN + 8 * 7] = 1 << 16
+    emu.run("arith_rc_hist_kernel", [IN, cells, FREQ, BAD], mem, tid=7, ctaid=0, ntid=ntid, nctaid=nblocks)
+    assert mem[BAD] & 0xFFFFFFFF == 1
+    # counter / zeroed frequencies
+    CNT, FRQ2, n = 0x400000000, 0x500000000, 1 << 17
+    for i in (0, 1, 65534, 65535, 65536, 65537, n - 1):
+        mem[FRQ2 + 8 * i] = 99
+        emu.run("arith_rc_init_kernel", [CNT, FRQ2, n], mem, tid=i % 256, ctaid=i // 256, ntid=256)
+        assert mem[CNT + 8 * i] == min(i, 65535) and mem[FRQ2 + 8 * i] == 0

@@ -87,7 +87,8 @@ class PtxEmu:
         return ins, labels
 
     # ---- execution ---------------------------------------------------------------------------------------------
-    def run(self, kernel, params, mem, tid=0, ctaid=0, ntid=128, max_steps=50_000_000):
+    def run(self, kernel, params, mem, tid=0, ctaid=0, ntid=128, max_steps=50_000_000, nctaid=1):
+        self.nctaid = nctaid
         """one thread; barriers are ignored (single-thread kernels or kernels whose barriers only order other threads' data)"""
         for _ in self._exec(kernel, params, mem, {}, tid, ctaid, ntid, max_steps):
             pass
@@ -161,6 +162,8 @@ class PtxEmu:
                     return cy
                 if a == "%ntid.x":
                     return ntid
+                if a == "%nctaid.x":
+                    return getattr(self, "nctaid", 1)
                 return R[a]
             if a in self.const_base:
                 return self.const_base[a]
@@ -255,6 +258,15 @@ class PtxEmu:
                         if o[-1][0] == "s" and v >> (bits - 1):       # ld.s32 into a 64-bit register sign-extends
                             v = (v - (1 << bits)) & (M64 if a[0].startswith("%rd") else M32)
                         R[a[0]] = v
+                elif base == "atom":              # atom.global.{add,or,...}.{u64,b32,...} d, [a], b   (threads run one after the other)
+                    b, off = addr(a[1])
+                    ad = (val(b) + off) & M64
+                    old_v = rd(space(ad), ad, bits // 8) if (ad & ~7) in space(ad) else 0
+                    y = val(a[2], bits)
+                    new_v = {"add": old_v + y, "or": old_v | y, "and": old_v & y, "xor": old_v ^ y, "max": max(old_v, y), "min": min(old_v, y),
+                             "exch": y}[o[2]]
+                    wr(space(ad), ad, bits // 8, new_v & mask)
+                    R[a[0]] = old_v
                 elif base == "st" and o[1] == "param":
                     b, off = addr(a[0])
                     buf = ptemp.setdefault(b, bytearray())

@@ -7,12 +7,16 @@
 //
 // and src/logic.rs:165-237 (LogicStark::generate_trace: 523 columns from 72 bytes per operation; stark/logic_trace.h).
 //
+// and arithmetic/arithmetic_stark.rs:130-156 (ArithmeticStark::generate_range_checks: the RANGE_COUNTER column and the RC_FREQUENCIES histogram
+// of the 96 shared columns, in place on a device-resident trace).
+//
 // keccak_trace_kernel: one thread per trace ROW.  Rows are independent given the permutation's input (keccak_trace.h), the trace is
 // column-major, so a warp stores 32 consecutive rows of one column per instruction: 256 contiguous bytes.  Write-bound: 8 * 2431 bytes per
 // row against ~1.5 k word operations; algorithmic bytes = 8 * 2431 * n written + 208 * num_perms read.
 #include "internal.h"
 #include "stark/keccak_trace.h"
 #include "stark/logic_trace.h"
+#include "stark/table_arithmetic.h"
 
 namespace zk {
 
@@ -35,6 +39,32 @@ __global__ void __launch_bounds__(128) logic_trace_kernel(const uint64_t* __rest
     if (row >= n) return;
     ColStore st{out + row, n};
     zkstark::logic::generate_row(ops, num_ops, row, st);
+}
+
+// ArithmeticStark::generate_range_checks.  RANGE_MAX = 2^16 (arithmetic_stark.rs:126).
+static constexpr uint64_t ARITH_RANGE_MAX = 1ull << 16;
+__global__ void arith_rc_init_kernel(uint64_t* __restrict__ counter, uint64_t* __restrict__ freq, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    counter[i] = i < ARITH_RANGE_MAX ? i : ARITH_RANGE_MAX - 1;     // :136-141
+    freq[i] = 0;
+}
+// Histogram of the shared columns into freq[x] (:144-155).  A thread walks its cells with a grid stride (consecutive threads read
+// consecutive rows of a column) and counts ZERO cells privately — padding rows and unused registers make zero the bin nearly every
+// cell of a sparse trace falls into — adding that count once at the end; the other values go to the L2 as reductions (red.add.u64;
+// a count never reaches p, so the field addition of the reference is a plain integer addition).  A cell >= 2^16 raises *bad (the
+// reference asserts).
+__global__ void __launch_bounds__(256) arith_rc_hist_kernel(const uint64_t* __restrict__ shared_cols, size_t cells, uint64_t* __restrict__ freq,
+                                                            unsigned* __restrict__ bad) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    unsigned long long zeros = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride) {
+        const uint64_t x = shared_cols[i];
+        if (x == 0) zeros++;
+        else if (x < ARITH_RANGE_MAX) atomicAdd((unsigned long long*)&freq[x], 1ull);
+        else atomicOr(bad, 1u);
+    }
+    if (zeros) atomicAdd((unsigned long long*)&freq[0], zeros);
 }
 
 static size_t padded_rows(size_t rows, size_t min_rows) {
@@ -108,6 +138,53 @@ int zkgpu_logic_generate_trace(zkgpu_ctx* h, const uint64_t* ops, size_t num_ops
         c.check_launch("logic_trace_kernel");
     }
     *out = t.release();
+    ZK_API_END
+}
+
+int zkgpu_dev_trace_upload(zkgpu_ctx* h, const uint64_t* cols, size_t ncols, size_t n, zkgpu_dev_trace** out) {
+    ZK_API_BEGIN
+    using namespace zk;
+    ZK_REQUIRE(h && cols && out && ncols && n, "null argument");
+    log2_exact(n);
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    std::unique_ptr<zkgpu_dev_trace> t(new zkgpu_dev_trace());
+    t->ncols = ncols;
+    t->n = n;
+    t->buf = DevBuf(&c, ncols * n * 8);
+    c.h2d(t->buf.get(), cols, ncols * n * 8);
+    *out = t.release();
+    ZK_API_END
+}
+
+int zkgpu_arithmetic_generate_range_checks(zkgpu_ctx* h, zkgpu_dev_trace* t) {
+    ZK_API_BEGIN
+    using namespace zk;
+    namespace ar = zkstark::arithmetic;
+    ZK_REQUIRE(h && t, "null argument");
+    Ctx& c = h->c;
+    ZK_REQUIRE(t->buf.ctx == &c, "the trace belongs to another context");
+    ZK_REQUIRE(t->ncols == ar::NUM_COLUMNS, "not an Arithmetic trace (116 columns)");
+    ZK_REQUIRE(t->n >= ARITH_RANGE_MAX, "the Arithmetic trace needs at least 2^16 rows (arithmetic_stark.rs:171-180)");
+    ZK_CUDA(cudaSetDevice(c.device));
+    const size_t n = t->n, cells = (size_t)ar::NUM_SHARED_COLS * n;
+    uint64_t* counter = t->buf.get() + (size_t)ar::RANGE_COUNTER * n;
+    uint64_t* freq = t->buf.get() + (size_t)ar::RC_FREQUENCIES * n;
+    DevBuf bad(&c, 8);
+    ZK_CUDA(cudaMemsetAsync(bad.get(), 0, 8, c.stream));
+    {
+        KernelScope ks(c, KF_TRACE_GEN, 8.0 * (double)(cells + 2 * n));
+        arith_rc_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(counter, freq, n);
+        // the SHARED_COLS are one contiguous block of the column-major trace
+        const size_t want = (cells + 256 * 64 - 1) / (256 * 64);
+        const unsigned blocks = (unsigned)(want < 1 ? 1 : want > (size_t)c.num_sms * 8 ? (size_t)c.num_sms * 8 : want);
+        arith_rc_hist_kernel<<<blocks, 256, 0, c.stream>>>(t->buf.get() + (size_t)ar::START_SHARED_COLS * n, cells, freq, (unsigned*)bad.get());
+        c.count_launch(2);
+        c.check_launch("arith_rc kernels");
+    }
+    uint64_t flag = 0;
+    c.d2h(&flag, bad.get(), 8);
+    ZK_REQUIRE((flag & 0xFFFFFFFFull) == 0, "a shared column value exceeds the max range value 65536 (arithmetic_stark.rs:147-152)");
     ZK_API_END
 }
 

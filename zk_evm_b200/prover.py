@@ -280,6 +280,21 @@ def logic_generate_trace(ctx, ops, min_rows=0):
     return DeviceTrace(ctx, h)
 
 
+def upload_trace(ctx, trace):
+    """a host trace (ncols, n) moved to the device as a DeviceTrace (for the in-place finishing steps)"""
+    a = _as_cols(trace)
+    h = C.c_void_p()
+    check(lib().zkgpu_dev_trace_upload(ctx._h, _ptr(a), C.c_size_t(a.shape[0]), C.c_size_t(a.shape[1]), C.byref(h)))
+    ctx.sync()          # `a` may be a temporary
+    return DeviceTrace(ctx, h)
+
+
+def arithmetic_generate_range_checks(ctx, device_trace):
+    """ArithmeticStark::generate_range_checks (arithmetic_stark.rs:130-156) in place on a device-resident Arithmetic trace"""
+    check(lib().zkgpu_arithmetic_generate_range_checks(ctx._h, device_trace._h))
+    return device_trace
+
+
 def table_info(table, num_challenges):
     a, b, c_, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
     check(lib().zkgpu_table_info(C.c_uint32(table), C.c_uint32(num_challenges), C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
