@@ -91,7 +91,7 @@ int zkgpu_ctx_stats(zkgpu_ctx* ctx, uint64_t* kernel_launches, uint64_t* bytes_i
  * family: 0 leaf_hash (Poseidon sponge over LDE rows), 1 merkle inner levels, 2 NTT / LDE passes, 3 quotient evaluation,
  * 4 CTL + lookup auxiliary columns, 5 openings, 6 FRI combine / fold / layer leaves, 7 proof-of-work grind,
  * 8 device-side trace finishing (zkgpu_keccak_generate_trace, zkgpu_logic_generate_trace,
- * zkgpu_arithmetic_generate_range_checks). */
+ * zkgpu_arithmetic_generate_range_checks, zkgpu_memory_finish_trace). */
 enum { ZKGPU_KF_LEAF_HASH = 0, ZKGPU_KF_MERKLE_LEVELS, ZKGPU_KF_NTT, ZKGPU_KF_QUOTIENT, ZKGPU_KF_AUX, ZKGPU_KF_OPENINGS, ZKGPU_KF_FRI,
        ZKGPU_KF_POW, ZKGPU_KF_TRACE_GEN, ZKGPU_KF_COUNT };
 int zkgpu_ctx_set_profiling(zkgpu_ctx* ctx, int on);   /* on: also resets the counters */
@@ -231,6 +231,15 @@ int zkgpu_dev_trace_upload(zkgpu_ctx* ctx, const uint64_t* cols, size_t ncols, s
  * of the 96 shared columns equal to x.  What the two columns held before is ignored.  ZKGPU_ERR_INVALID if a shared cell is >= 2^16
  * (the reference asserts). */
 int zkgpu_arithmetic_generate_range_checks(zkgpu_ctx* ctx, zkgpu_dev_trace* trace);
+/* The data-parallel tail of MemoryStark::generate_trace (memory/memory_stark.rs:407-462).  `ops` (host): 14 x n words, column-major —
+ * filter, timestamp, is_read, addr_context, addr_segment, addr_virtual, value_limbs[0..8] of every row AFTER the host's sort, fill_gaps
+ * and pad_memory_ops (:215-236; n a power of two); `stale_contexts`: the list insert_stale_contexts takes (:387-404).  The device
+ * derives the other 16 columns: timestamp_inv (into_row :104-131), the first-change flags, range_check, preinitialized_segments[_aux],
+ * initialize_aux (generate_first_change_flags_and_rc :134-213), stale_contexts, is_pruned, and counter, frequencies,
+ * stale_context_frequencies, is_stale, maybe_in_mem_after, mem_after_filter (generate_trace_col_major :240-294).  30 columns x n.
+ * ZKGPU_ERR_INVALID if a range-checked difference does not fit the table (the reference asserts). */
+int zkgpu_memory_finish_trace(zkgpu_ctx* ctx, const uint64_t* ops, size_t n, const uint64_t* stale_contexts, size_t num_stale,
+                              zkgpu_dev_trace** out);
 int zkgpu_dev_trace_dims(const zkgpu_dev_trace* t, size_t* ncols, size_t* n);
 const uint64_t* zkgpu_dev_trace_ptr(const zkgpu_dev_trace* t);             /* device address of column 0 (column c at + c*n) */
 int zkgpu_dev_trace_export(const zkgpu_dev_trace* t, uint64_t* host_out);  /* ncols * n words (parity tests) */

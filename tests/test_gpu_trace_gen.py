@@ -66,6 +66,39 @@ def test_arithmetic_range_checks_reject_large_values_and_short_traces(ctx):
     dt.free()
 
 
+@pytest.mark.parametrize("seed,log_n,nops,stale", [(1, 6, 40, ()), (2, 6, 40, (2,)), (3, 10, 900, (1, 2)), (4, 5, 20, (0, 1, 2))])
+def test_memory_finish_matches_reference_restatement(ctx, seed, log_n, nops, stale):
+    ops = traces.memory_sorted_ops(log_n, seed, nops=nops)
+    dt = zk.memory_finish_trace(ctx, ops, stale)
+    assert (dt.ncols, dt.n) == (30, 1 << log_n)
+    got = dt.export()
+    dt.free()
+    want = traces.memory_finish_reference(ops, stale)
+    assert np.array_equal(got, want), [c for c in range(30) if not np.array_equal(got[c], want[c])]
+
+
+def test_memory_finish_rejects_unsorted_operations(ctx):
+    ops = traces.memory_sorted_ops(6, 5)
+    ops[1, 10] += 1000
+    with pytest.raises(zk.ZkGpuError):
+        zk.memory_finish_trace(ctx, ops)
+    with pytest.raises(zk.ZkGpuError):
+        zk.memory_finish_trace(ctx, traces.memory_sorted_ops(6, 5), stale_contexts=(64,))
+
+
+def test_device_finished_memory_trace_proves_and_verifies(ctx, oracle):
+    cfg = zk.StarkConfig(*TEST_CONFIG)
+    dt = zk.memory_finish_trace(ctx, traces.memory_sorted_ops(6, 8), (2,))
+    batch = zk.PolynomialBatch.from_device_values(ctx, dt.device_ptr, dt.ncols, dt.n, cfg.rate_bits, cfg.cap_height, keep_values=True)
+    dt.free()
+    bg = np.array([11, 22], dtype=np.uint64)
+    st0 = np.arange(12, dtype=np.uint64)
+    ctl = zk.get_ctl_data(ctx, traces.T_MEMORY, batch, bg, cfg.num_challenges)
+    proof, st = zk.prove_single_table(ctx, traces.T_MEMORY, cfg, batch, ctl, st0, zk.KernelLabels(*DEFAULT_LABELS))
+    ok, err, st2 = orc_verify_table(oracle, traces.T_MEMORY, TEST_CONFIG, proof.words, bg, st0)
+    assert ok, err
+
+
 def test_segment_from_device_finished_keccak_and_logic_traces(ctx, oracle):
     rng = np.random.default_rng(9)
     inputs = rng.integers(0, 1 << 64, size=(5, 25), dtype=np.uint64)

@@ -502,3 +502,37 @@ def test_arithmetic_range_check_kernels():
         mem[FRQ2 + 8 * i] = 99
         emu.run("arith_rc_init_kernel", [CNT, FRQ2, n], mem, tid=i % 256, ctaid=i // 256, ntid=256)
         assert mem[CNT + 8 * i] == min(i, 65535) and mem[FRQ2 + 8 * i] == 0
+
+
+def test_memory_finish_kernels():
+    """memory_stale_kernel + memory_finish_kernel (csrc/trace_gen.cu, as PTX; finish_row incl. the Fermat inversion of the timestamp and the
+    histogram reductions), every thread of the grid one after the other, against the restated MemoryStark finishing (tests/traces.py)."""
+    from ptx_emu import PtxEmu
+    from tests import traces
+    src = os.path.join(CSRC, "trace_gen.cu")
+    ptx = os.path.join(HERE, "native", "trace_gen.ptx")
+    deps = [src, os.path.join(CSRC, "gl.cuh")] + [os.path.join(CSRC, "stark", f) for f in ("memory_trace.h", "table_memory.h")]
+    if not os.path.exists(ptx) or any(os.path.getmtime(d) > os.path.getmtime(ptx) for d in deps):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I", CSRC, "-ptx", "-o", ptx, src])
+    emu = PtxEmu(open(ptx).read())
+    log_n, stale = 5, (1, 2)
+    n = 1 << log_n
+    ops = traces.memory_sorted_ops(log_n, 21, nops=25)
+    want = traces.memory_finish_reference(ops, stale)
+    T, BAD, ST = 0x100000000, 0x300000000, 0x310000000
+    mem = {BAD: 0}
+    for k, c in enumerate(traces.MEM_OP_COLS):
+        for i in range(n):
+            mem[T + 8 * (c * n + i)] = int(ops[k, i])
+    for c in (21, 22, 23, 29):                       # the library zero-fills the accumulated columns (cudaMemsetAsync)
+        for i in range(n):
+            mem[T + 8 * (c * n + i)] = 0
+    for k, ctx in enumerate(stale):
+        mem[ST + 8 * k] = ctx
+    for k in range(len(stale)):
+        emu.run("memory_stale_kernel", [ST, len(stale), n, T], mem, tid=k, ctaid=0, ntid=256)
+    for i in range(n):
+        emu.run("memory_finish_kernel", [T, n, BAD], mem, tid=i, ctaid=0, ntid=256)
+    assert mem[BAD] == 0
+    got = np.array([[mem[T + 8 * (c * n + i)] for i in range(n)] for c in range(30)], dtype=np.uint64)
+    assert np.array_equal(got, want), [c for c in range(30) if not np.array_equal(got[c], want[c])]

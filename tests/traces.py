@@ -231,6 +231,92 @@ def arithmetic_addcy_trace(log_n, seed, nops=1000):
     return t
 
 
+# ---- MemoryStark from operations (memory_stark.rs:104-462) -------------------------------------------------------------------------
+MEM_OP_COLS = (0, 1, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14)       # filter, timestamp, is_read, context, segment, virtual, 8 value limbs
+
+
+def memory_sorted_ops(log_n, seed, nops=40, stale=()):
+    """A consistent random memory history in the form the host hands to the finishing step: operations sorted by (context, segment,
+    virtual, timestamp), the (0, 0, 0) dummy read of fill_gaps in front, pad_memory_ops padding behind -> (14, n) uint64.
+    Reads return the last value written (zero before any write); contexts 0..2, a few segments incl. the preinitialised 0 and 12."""
+    rng = np.random.default_rng(seed)
+    n = 1 << log_n
+    mem, ops = {}, []
+    for k in range(nops):
+        addr = (int(rng.integers(0, 3)), int(rng.choice([0, 1, 2, 12])), int(rng.integers(0, 6)))
+        ts = 2 + k
+        if rng.integers(0, 2) or addr not in mem:
+            val = [int(x) for x in rng.integers(0, 1 << 32, size=8)] if rng.integers(0, 4) else [0] * 8
+            mem[addr] = val
+            ops.append((addr, ts, 0, 1, val))
+        else:
+            ops.append((addr, ts, 1, 1, mem[addr]))
+    ops.sort(key=lambda o: (o[0], o[1]))
+    if ops[0][0][2] != 0 or ops[0][0][:2] != (0, 0):
+        ops.insert(0, ((0, 0, 0), 1, 1, 0, [0] * 8))
+    last = ops[-1]
+    while len(ops) < n:
+        ops.append(((last[0][0], last[0][1], last[0][2] + 1), last[1] + 1, 1, 0, [0] * 8))
+    assert len(ops) == n
+    t = np.zeros((14, n), dtype=np.uint64)
+    for i, (addr, ts, is_read, filt, val) in enumerate(ops):
+        t[:6, i] = [filt, ts, is_read, addr[0], addr[1], addr[2]]
+        t[6:, i] = val
+    return t
+
+
+def memory_finish_reference(ops, stale=()):
+    """Restatement of MemoryOp::into_row (timestamp_inv), generate_first_change_flags_and_rc, insert_stale_contexts and
+    generate_trace_col_major (memory_stark.rs:104-131, 134-213, 387-404, 240-294) on sorted / padded operations (14, n) -> (30, n)."""
+    ops = np.asarray(ops, dtype=np.uint64)
+    n = ops.shape[1]
+    t = [[0] * n for _ in range(30)]
+    for k, c in enumerate(MEM_OP_COLS):
+        t[c] = [int(v) for v in ops[k]]
+    for i in range(n):
+        j = 0 if i == n - 1 else i + 1
+        t[2][i] = pow(t[1][i], P - 2, P) if t[1][i] else 0
+        cfc = t[4][i] != t[4][j]
+        sfc = t[5][i] != t[5][j] and not cfc
+        vfc = t[6][i] != t[6][j] and not sfc and not cfc
+        t[15][i], t[16][i], t[17][i] = int(cfc), int(sfc), int(vfc)
+        if i == n - 1:
+            rc = 0
+        elif cfc:
+            rc = (t[4][j] - t[4][i] - 1) % P
+        elif sfc:
+            rc = (t[5][j] - t[5][i] - 1) % P
+        elif vfc:
+            rc = (t[6][j] - t[6][i] - 1) % P
+        else:
+            rc = (t[1][j] - t[1][i]) % P
+        t[27][i] = rc
+        assert rc < n
+        t[20][i] = (t[5][j] - 34) * (t[5][j] - 35) % P
+        t[19][i] = (t[5][j] - 0) * (t[5][j] - 12) * t[20][i] % P
+        t[18][i] = t[19][i] * (t[15][i] + t[16][i] + t[17][i]) * t[3][j] % P
+    for ctx in stale:
+        t[21][ctx] = ctx + 1
+        t[22][ctx] = 1
+    t[28] = list(range(n))
+    for i in range(n):
+        t[29][t[27][i]] += 1
+        if t[15][i] == 1 or t[16][i] == 1:
+            if i < n - 1:
+                t[29][t[6][i + 1]] += 1
+            else:
+                t[29][0] += 1
+        ctx = t[4][i]
+        if ctx + 1 == t[21][ctx]:
+            t[24][i] = 1
+            t[23][ctx] += 1
+        elif t[0][i] == 1 and (t[15][i] == 1 or t[16][i] == 1 or t[17][i] == 1):
+            t[25][i] = 1
+            if any(t[7 + l][i] for l in range(8)) or t[5][i] in (0, 12, 34, 35):
+                t[26][i] = 1
+    return np.array(t, dtype=np.uint64)
+
+
 # ---- a VALID multi-table segment: CPU padding + empty Arithmetic + Memory initialised from MemBefore, final state in MemAfter ----
 def memory_trace_from_mem_before(log_n, addrs, values):
     """MemoryStark trace whose only real operations are the timestamp-0 initialisation writes of `mem_before`

@@ -10,6 +10,9 @@
 // and arithmetic/arithmetic_stark.rs:130-156 (ArithmeticStark::generate_range_checks: the RANGE_COUNTER column and the RC_FREQUENCIES histogram
 // of the 96 shared columns, in place on a device-resident trace).
 //
+// and memory/memory_stark.rs:104-213,240-294,387-404 (MemoryStark::generate_trace after the host's sort / fill_gaps / padding: 16 of the 30
+// columns derived on the device from the 14 operation columns; stark/memory_trace.h).
+//
 // keccak_trace_kernel: one thread per trace ROW.  Rows are independent given the permutation's input (keccak_trace.h), the trace is
 // column-major, so a warp stores 32 consecutive rows of one column per instruction: 256 contiguous bytes.  Write-bound: 8 * 2431 bytes per
 // row against ~1.5 k word operations; algorithmic bytes = 8 * 2431 * n written + 208 * num_perms read.
@@ -17,6 +20,7 @@
 #include "stark/keccak_trace.h"
 #include "stark/logic_trace.h"
 #include "stark/table_arithmetic.h"
+#include "stark/memory_trace.h"
 
 namespace zk {
 
@@ -65,6 +69,27 @@ __global__ void __launch_bounds__(256) arith_rc_hist_kernel(const uint64_t* __re
         else atomicOr(bad, 1u);
     }
     if (zeros) atomicAdd((unsigned long long*)&freq[0], zeros);
+}
+
+// MemoryStark: the stale-context list into its two columns (insert_stale_contexts), then one thread per row (memory_trace.h) with the
+// two histogram columns accumulated by reductions into the L2
+__global__ void memory_stale_kernel(const uint64_t* __restrict__ stale, size_t num_stale, size_t n, uint64_t* __restrict__ t) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= num_stale) return;
+    const uint64_t ctx = stale[k];
+    t[(size_t)zkstark::memory::STALE_CONTEXTS * n + ctx] = ctx + 1;
+    t[(size_t)zkstark::memory::IS_PRUNED * n + ctx] = 1;
+}
+__global__ void __launch_bounds__(256) memory_finish_kernel(uint64_t* __restrict__ t, size_t n, unsigned* __restrict__ bad) {
+    namespace mem = zkstark::memory;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mem::RowCounts rc;
+    if (!mem::finish_row(t, n, i, rc)) { atomicOr(bad, 1u); return; }
+    unsigned long long* freq = (unsigned long long*)(t + (size_t)mem::FREQUENCIES * n);
+    atomicAdd(&freq[rc.freq_a], 1ull);
+    if (rc.freq_b != mem::NONE) atomicAdd(&freq[rc.freq_b], 1ull);
+    if (rc.stale_ctx != mem::NONE) atomicAdd((unsigned long long*)(t + (size_t)mem::STALE_CONTEXT_FREQUENCIES * n) + rc.stale_ctx, 1ull);
 }
 
 static size_t padded_rows(size_t rows, size_t min_rows) {
@@ -185,6 +210,47 @@ int zkgpu_arithmetic_generate_range_checks(zkgpu_ctx* h, zkgpu_dev_trace* t) {
     uint64_t flag = 0;
     c.d2h(&flag, bad.get(), 8);
     ZK_REQUIRE((flag & 0xFFFFFFFFull) == 0, "a shared column value exceeds the max range value 65536 (arithmetic_stark.rs:147-152)");
+    ZK_API_END
+}
+
+int zkgpu_memory_finish_trace(zkgpu_ctx* h, const uint64_t* ops, size_t n, const uint64_t* stale_contexts, size_t num_stale,
+                              zkgpu_dev_trace** out) {
+    ZK_API_BEGIN
+    using namespace zk;
+    namespace mem = zkstark::memory;
+    ZK_REQUIRE(h && ops && out && n && (stale_contexts || num_stale == 0), "null argument");
+    log2_exact(n);
+    for (size_t k = 0; k < num_stale; k++) ZK_REQUIRE(stale_contexts[k] < n, "stale context past the end of the trace (memory_stark.rs:401)");
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    std::unique_ptr<zkgpu_dev_trace> t(new zkgpu_dev_trace());
+    t->ncols = mem::NUM_COLUMNS;
+    t->n = n;
+    t->buf = DevBuf(&c, t->ncols * n * 8);
+    uint64_t* d = t->buf.get();
+    // the 14 operation columns: filter, timestamp | is_read, context, segment, virtual, 8 value limbs
+    c.h2d(d + (size_t)mem::FILTER * n, ops, 2 * n * 8);
+    c.h2d(d + (size_t)mem::IS_READ * n, ops + 2 * n, 12 * n * 8);
+    ZK_CUDA(cudaMemsetAsync(d + (size_t)mem::STALE_CONTEXTS * n, 0, 3 * n * 8, c.stream));      // stale_contexts, is_pruned, stale_context_frequencies
+    ZK_CUDA(cudaMemsetAsync(d + (size_t)mem::FREQUENCIES * n, 0, n * 8, c.stream));
+    DevBuf aux(&c, (num_stale + 1) * 8);          // [0] = error flag, then the stale list
+    ZK_CUDA(cudaMemsetAsync(aux.get(), 0, 8, c.stream));
+    if (num_stale) c.h2d(aux.get() + 1, stale_contexts, num_stale * 8);
+    {
+        KernelScope ks(c, KF_TRACE_GEN, 8.0 * 30.0 * (double)n);
+        if (num_stale) {
+            memory_stale_kernel<<<(unsigned)((num_stale + 255) / 256), 256, 0, c.stream>>>(aux.get() + 1, num_stale, n, d);
+            c.count_launch();
+        }
+        memory_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(d, n, (unsigned*)aux.get());
+        c.count_launch();
+        c.check_launch("memory_finish_kernel");
+    }
+    uint64_t flag = 0;
+    c.d2h(&flag, aux.get(), 8);
+    ZK_REQUIRE((flag & 0xFFFFFFFFull) == 0, "a range-checked difference does not fit the table: the operations are not sorted / gap-filled "
+                                            "(memory_stark.rs:190-194)");
+    *out = t.release();
     ZK_API_END
 }
 

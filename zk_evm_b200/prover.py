@@ -295,6 +295,19 @@ def arithmetic_generate_range_checks(ctx, device_trace):
     return device_trace
 
 
+def memory_finish_trace(ctx, ops, stale_contexts=()):
+    """The data-parallel tail of MemoryStark::generate_trace on the device (memory_stark.rs:104-294): ops (14, n) uint64 = filter,
+    timestamp, is_read, context, segment, virtual, 8 value limbs of the sorted / gap-filled / padded operations; stale_contexts as
+    insert_stale_contexts takes them -> DeviceTrace of 30 columns x n."""
+    a = _as_cols(ops)
+    if a.shape[0] != 14:
+        raise ValueError("expected the 14 operation columns")
+    st = np.ascontiguousarray(list(stale_contexts), dtype=np.uint64)
+    h = C.c_void_p()
+    check(lib().zkgpu_memory_finish_trace(ctx._h, _ptr(a), C.c_size_t(a.shape[1]), _ptr(st) if st.size else None, C.c_size_t(st.size), C.byref(h)))
+    return DeviceTrace(ctx, h)
+
+
 def table_info(table, num_challenges):
     a, b, c_, d = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
     check(lib().zkgpu_table_info(C.c_uint32(table), C.c_uint32(num_challenges), C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
