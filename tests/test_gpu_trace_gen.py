@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 PUBLIC_VALUES = np.arange(1000, 1000 + 37, dtype=np.uint64)
 
 
-@pytest.mark.parametrize("nperm,min_rows,log_n", [(1, 0, 5), (5, 0, 7), (10, 16, 8), (2, 256, 8), (0, 16, 4), (170, 0, 12)])
+@pytest.mark.parametrize("nperm,min_rows,log_n", [(1, 0, 5), (5, 0, 7), (10, 16, 8), (2, 256, 8), (0, 16, 4), (170, 0, 12), (1365, 0, 15)])
 def test_keccak_trace_matches_reference_restatement(ctx, nperm, min_rows, log_n):
     rng = np.random.default_rng(300 + nperm)
     inputs = rng.integers(0, 1 << 64, size=(nperm, 25), dtype=np.uint64)
