@@ -29,20 +29,22 @@ static const uint64_t EPS = 0xFFFFFFFFULL;  // 2^32 - 1 = 2^64 mod p
 // ---------------------------------------------------------------------------------------------
 // Goldilocks base field, canonical representatives only (book/src/framework/field.md:3-20).
 // ---------------------------------------------------------------------------------------------
+// (branch-free forms: the comparisons of modular arithmetic on pseudo-random values are unpredictable branches)
 static inline uint64_t gl_add(uint64_t a, uint64_t b) {
     uint64_t s = a + b;
-    if (s < a || s >= P) s -= P;
-    return s;
+    return s - ((uint64_t)(-(int64_t)((s < a) | (s >= P))) & P);
 }
-static inline uint64_t gl_sub(uint64_t a, uint64_t b) { return a >= b ? a - b : a + (P - b); }
+static inline uint64_t gl_sub(uint64_t a, uint64_t b) { return a - b + ((uint64_t)(-(int64_t)(a < b)) & P); }
 static inline uint64_t gl_neg(uint64_t a) { return a ? P - a : 0; }
 // n = n0 + 2^64 n1 + 2^96 n2  ->  n0 + (2^32-1) n1 - n2   (field.md:9-20)
 static inline uint64_t gl_reduce128(u128 x) {
     uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
     uint64_t n1 = hi & EPS, n2 = hi >> 32;
-    uint64_t t = lo >= P ? lo - P : lo;
-    t = gl_sub(t, n2);                 // n2 < 2^32 < p
-    return gl_add(t, n1 * EPS);        // n1*EPS < 2^64 - 2^33 + 1 < p
+    uint64_t t = lo - n2;                                   // a borrow means + 2^64 = + EPS (mod p) too much
+    t -= (uint64_t)(-(int64_t)(lo < n2)) & EPS;
+    uint64_t r = t + n1 * EPS;                              // n1*EPS < 2^64 - 2^33 + 1; a carry means 2^64 = EPS (mod p) is missing
+    r += (uint64_t)(-(int64_t)(r < t)) & EPS;
+    return r - ((uint64_t)(-(int64_t)(r >= P)) & P);
 }
 static inline uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_reduce128((u128)a * b); }
 static inline uint64_t gl_pow(uint64_t b, uint64_t e) {
@@ -101,10 +103,11 @@ static inline uint64_t sbox7(uint64_t x) {
     return gl_mul(x3, x4);
 }
 static inline void mds_layer(uint64_t s[12]) {
-    uint64_t out[12];
+    uint64_t d[24], out[12];
+    memcpy(d, s, 96); memcpy(d + 12, s, 96);                // d[i + r] = s[(i + r) % 12]
     for (int r = 0; r < 12; r++) {
         u128 acc = 0;
-        for (int i = 0; i < 12; i++) acc += (u128)s[(i + r) % 12] * MDS_CIRC[i];
+        for (int i = 0; i < 12; i++) acc += (u128)d[i + r] * MDS_CIRC[i];
         if (r == 0) acc += (u128)s[0] * ZK_POSEIDON_MDS_DIAG0;
         out[r] = gl_reduce128(acc);
     }
