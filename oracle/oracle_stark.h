@@ -546,11 +546,19 @@ static inline StarkProofData prove_table(uint32_t table, const Config& cfg, cons
         uint64_t w = 0;
         if (forced_pow) w = *forced_pow;
         else {
-            for (;; w++) {
-                Challenger t = base;
-                t.observe(w);
-                uint64_t r = t.challenge();
-                if (cfg.pow_bits == 0 || (r >> (64 - cfg.pow_bits)) == 0) break;
+            // candidates in blocks, all host threads per block (the reference grinds with rayon), smallest valid one of the first
+            // block that holds any
+            const uint64_t BLOCK = 1 << 12;
+            for (uint64_t w0 = 0;; w0 += BLOCK) {
+                uint64_t best = ~0ull;
+                #pragma omp parallel for reduction(min : best) schedule(static)
+                for (uint64_t k = 0; k < BLOCK; k++) {
+                    Challenger t = base;
+                    t.observe(w0 + k);
+                    uint64_t r = t.challenge();
+                    if ((cfg.pow_bits == 0 || (r >> (64 - cfg.pow_bits)) == 0) && w0 + k < best) best = w0 + k;
+                }
+                if (best != ~0ull) { w = best; break; }
             }
         }
         ch.observe(w);
