@@ -1,0 +1,291 @@
+// C++17 host side over the C ABI (include/zkgpu.h): the reference's interface for the proving path, name for name.
+//
+// The reference is compiled code (Rust); its toolchain is not in this image, so this header is the compiled-language host mirror: the
+// same call shapes as evm_arithmetization/src/prover.rs — prove_with_traces (:72-194), prove_single_table (:301-341),
+// PolynomialBatch::from_values (:100-107), get_ctl_data (:137-143), Challenger (:118-129, 320), check_abort_signal (:346-354) — and the
+// same types: StarkProof / StarkProofWithMetadata / AllProof (proof.rs:29-54, prover.rs:335-338), MemCap (prover.rs:261-271),
+// StarkConfig::standard_fast_config (zero/src/prover_state/mod.rs:283).  Rust's Result<T> is an exception here (zkgpu::Error carries
+// the zkgpu_status); Option<Arc<AtomicBool>> is a `const std::atomic<int>*`.  Header-only; link with -lzkgpu.  No arithmetic lives here:
+// every computation is a call into libzkgpu.so (CUDA), and there is no CPU fallback — without a usable device the calls throw
+// Error{ZKGPU_ERR_CUDA}.
+#pragma once
+#include <array>
+#include <atomic>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+#include "zkgpu.h"
+#include "../zk_evm_b200/csrc/stark/proof.h"   // StarkProofData: the typed StarkProof fields + the canonical word layout (plain data)
+
+namespace zkgpu {
+
+using F = uint64_t;                                   // GoldilocksField: canonical u64 (#[repr(transparent)] over u64)
+constexpr size_t NUM_TABLES = ZKGPU_NUM_TABLES;       // all_stark.rs:74-86
+enum class Table : uint32_t { Arithmetic = 0, BytePacking, Cpu, Keccak, KeccakSponge, Logic, Memory, MemBefore, MemAfter };
+constexpr std::array<uint32_t, 5> OPTIONAL_TABLE_INDICES = {1, 3, 4, 5, 8};   // all_stark.rs:110-117
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc) {
+    if (rc != ZKGPU_OK) throw Error(rc, zkgpu_last_error());
+}
+
+struct StarkConfig : zkgpu_stark_config {
+    static StarkConfig standard_fast_config() { return StarkConfig{{100, 2, 1, 4, 16, 4, 5, 84}}; }
+    static StarkConfig test_config() { return StarkConfig{{1, 1, 1, 4, 1, 4, 5, 1}}; }          // TEST_STARK_CONFIG, testing_utils.rs:41-52
+};
+using KernelLabels = zkgpu_kernel_labels;
+using AbortSignal = const std::atomic<int>*;           // Option<Arc<AtomicBool>>: nullptr = None
+inline volatile const int* abort_ptr(AbortSignal a) {
+    static_assert(sizeof(std::atomic<int>) == sizeof(int), "atomic<int> must be layout-compatible with int");
+    return reinterpret_cast<volatile const int*>(a);
+}
+
+// PolynomialValues<F>: one column of evaluations
+using PolynomialValues = std::vector<F>;
+
+class Context {
+public:
+    explicit Context(int device = 0) { check(zkgpu_ctx_create(device, &h_)); }
+    ~Context() { if (h_) zkgpu_ctx_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    void sync() { check(zkgpu_ctx_sync(h_)); }
+    zkgpu_ctx* handle() const { return h_; }
+private:
+    zkgpu_ctx* h_ = nullptr;
+};
+
+using Hash = std::array<F, 4>;
+using MerkleCap = std::vector<Hash>;                   // plonky2 MerkleCap<F, PoseidonHash>
+inline MerkleCap cap_from_words(const uint64_t* w, size_t n_words) {
+    MerkleCap c(n_words / 4);
+    for (size_t i = 0; i < c.size(); i++) for (int k = 0; k < 4; k++) c[i][k] = w[4 * i + k];
+    return c;
+}
+
+// PolynomialBatch<F, C, D>: resident on the device; the host fields are filled on request (export_fields)
+class PolynomialBatch {
+public:
+    struct HostFields {                                // PolynomialBatch{polynomials, merkle_tree{leaves, digests, cap}}
+        std::vector<F> polynomials;                    // ncols x n coefficients, column-major
+        std::vector<F> leaves;                         // (n << rate_bits) rows x ncols, row-major, row j = LDE row bitrev(j)
+        std::vector<F> digests;                        // plonky2's recursive layout
+        MerkleCap cap;
+    };
+    // PolynomialBatch::from_values(values, rate_bits, blinding = false, cap_height, timing, fft_root_table = None)
+    static PolynomialBatch from_values(Context& ctx, const std::vector<PolynomialValues>& values, uint32_t rate_bits, uint32_t cap_height,
+                                       bool keep_values = true) {
+        if (values.empty()) throw Error(ZKGPU_ERR_INVALID, "no columns");
+        std::vector<const uint64_t*> cols(values.size());
+        for (size_t c = 0; c < values.size(); c++) {
+            if (values[c].size() != values[0].size()) throw Error(ZKGPU_ERR_INVALID, "columns of different lengths");
+            cols[c] = values[c].data();
+        }
+        zkgpu_batch* b = nullptr;
+        check(zkgpu_commit_values(ctx.handle(), cols.data(), cols.size(), values[0].size(), rate_bits, cap_height, ZKGPU_MEM_HOST, keep_values, &b));
+        return PolynomialBatch(b);
+    }
+    // one contiguous column-major block (host, or device with mem_kind = ZKGPU_MEM_DEVICE)
+    static PolynomialBatch from_values_contig(Context& ctx, const F* base, size_t ncols, size_t n, uint32_t rate_bits, uint32_t cap_height,
+                                              int mem_kind = ZKGPU_MEM_HOST, bool keep_values = true) {
+        zkgpu_batch* b = nullptr;
+        check(zkgpu_commit_values_contig(ctx.handle(), base, ncols, n, rate_bits, cap_height, mem_kind, keep_values, &b));
+        return PolynomialBatch(b);
+    }
+    // PolynomialBatch::from_coeffs
+    static PolynomialBatch from_coeffs(Context& ctx, const std::vector<std::vector<F>>& coeffs, uint32_t rate_bits, uint32_t cap_height) {
+        if (coeffs.empty()) throw Error(ZKGPU_ERR_INVALID, "no columns");
+        std::vector<const uint64_t*> cols(coeffs.size());
+        for (size_t c = 0; c < coeffs.size(); c++) cols[c] = coeffs[c].data();
+        zkgpu_batch* b = nullptr;
+        check(zkgpu_commit_coeffs(ctx.handle(), cols.data(), cols.size(), coeffs[0].size(), rate_bits, cap_height, ZKGPU_MEM_HOST, &b));
+        return PolynomialBatch(b);
+    }
+    size_t num_polys() const { return dims().ncols; }
+    size_t degree() const { return dims().n; }
+    MerkleCap cap() const {                            // merkle_tree.cap
+        const Dims d = dims();
+        std::vector<uint64_t> w((size_t)4 << d.cap_height);
+        check(zkgpu_batch_cap(h_.get(), w.data()));
+        return cap_from_words(w.data(), w.size());
+    }
+    HostFields export_fields() const {
+        const Dims d = dims();
+        const size_t N = d.n << d.rate_bits;
+        HostFields f;
+        f.polynomials.resize(d.ncols * d.n);
+        f.leaves.resize(N * d.ncols);
+        f.digests.resize(2 * (N - ((size_t)1 << d.cap_height)) * 4);
+        check(zkgpu_batch_export(h_.get(), f.polynomials.data(), f.leaves.data(), f.digests.empty() ? nullptr : f.digests.data()));
+        f.cap = cap();
+        return f;
+    }
+    const zkgpu_batch* handle() const { return h_.get(); }
+private:
+    struct Dims { size_t ncols, n; uint32_t rate_bits, cap_height; };
+    Dims dims() const { Dims d{}; check(zkgpu_batch_dims(h_.get(), &d.ncols, &d.n, &d.rate_bits, &d.cap_height)); return d; }
+    struct Del { void operator()(zkgpu_batch* b) const { zkgpu_batch_free(b); } };
+    explicit PolynomialBatch(zkgpu_batch* b) : h_(b) {}
+    std::unique_ptr<zkgpu_batch, Del> h_;
+};
+
+// GrandProductChallengeSet: (beta, gamma) per challenge, flattened [beta_0, gamma_0, beta_1, gamma_1]
+struct GrandProductChallengeSet { std::vector<F> beta_gamma; };
+
+// plonky2 Challenger<F, PoseidonHash>
+class Challenger {
+public:
+    Challenger() { check(zkgpu_challenger_new(&h_)); }
+    ~Challenger() { if (h_) zkgpu_challenger_free(h_); }
+    Challenger(const Challenger&) = delete;
+    Challenger& operator=(const Challenger&) = delete;
+    static std::unique_ptr<Challenger> from_state(const std::array<F, 12>& st) {
+        auto c = std::make_unique<Challenger>();
+        check(zkgpu_challenger_set_state(c->h_, st.data()));
+        return c;
+    }
+    void observe_element(F x) { check(zkgpu_challenger_observe(h_, &x, 1)); }
+    void observe_elements(const std::vector<F>& xs) { check(zkgpu_challenger_observe(h_, xs.data(), xs.size())); }
+    void observe_cap(const MerkleCap& cap) { for (const Hash& hsh : cap) check(zkgpu_challenger_observe(h_, hsh.data(), 4)); }
+    F get_challenge() { F x; check(zkgpu_challenger_get_challenges(h_, &x, 1)); return x; }
+    std::vector<F> get_n_challenges(size_t n) { std::vector<F> v(n); check(zkgpu_challenger_get_challenges(h_, v.data(), n)); return v; }
+    std::array<F, 12> compact() { std::array<F, 12> st; check(zkgpu_challenger_compact(h_, st.data())); return st; }
+    void set_state(const std::array<F, 12>& st) { check(zkgpu_challenger_set_state(h_, st.data())); }
+private:
+    zkgpu_challenger* h_ = nullptr;
+};
+
+// CtlData<F> of one table (device-resident helper and Z columns)
+class CtlData {
+public:
+    const zkgpu_ctl* handle() const { return h_.get(); }
+private:
+    friend CtlData get_ctl_data(Context&, Table, const PolynomialBatch&, const GrandProductChallengeSet&, uint32_t);
+    struct Del { void operator()(zkgpu_ctl* c) const { zkgpu_ctl_free(c); } };
+    explicit CtlData(zkgpu_ctl* c) : h_(c) {}
+    std::unique_ptr<zkgpu_ctl, Del> h_;
+};
+// the per-table slice of starky get_ctl_data (prover.rs:137-143); the trace batch must have been committed with keep_values
+inline CtlData get_ctl_data(Context& ctx, Table table, const PolynomialBatch& trace, const GrandProductChallengeSet& ch, uint32_t num_challenges) {
+    if (ch.beta_gamma.size() != 2 * (size_t)num_challenges) throw Error(ZKGPU_ERR_INVALID, "beta_gamma must hold 2 * num_challenges elements");
+    zkgpu_ctl* c = nullptr;
+    check(zkgpu_ctl_data(ctx.handle(), (uint32_t)table, trace.handle(), ch.beta_gamma.data(), num_challenges, &c));
+    return CtlData(c);
+}
+
+// StarkProofWithMetadata{proof: StarkProof{trace_cap, auxiliary_polys_cap, quotient_polys_cap, openings, opening_proof}, init_challenger_state}
+// as typed fields (zkstark::StarkProofData, stark/proof.h) plus the canonical words they were decoded from
+struct StarkProofWithMetadata {
+    zkstark::StarkProofData proof;
+    std::vector<uint64_t> words;
+};
+inline StarkProofWithMetadata take_proof(zkgpu_proof* p) {
+    std::unique_ptr<zkgpu_proof, void (*)(zkgpu_proof*)> own(p, zkgpu_proof_free);
+    size_t len = 0;
+    check(zkgpu_proof_serialize(p, nullptr, &len));
+    StarkProofWithMetadata out;
+    out.words.resize(len);
+    check(zkgpu_proof_serialize(p, out.words.data(), &len));
+    out.proof = zkstark::deserialize_proof(out.words.data(), out.words.size());
+    return out;
+}
+
+// prove_single_table (prover.rs:301-341): the shared challenger is compacted, handed over as its 12-word state and restored
+inline StarkProofWithMetadata prove_single_table(Context& ctx, Table table, const StarkConfig& config, const PolynomialBatch& trace_commitment,
+                                                 const CtlData& ctl_data, Challenger& challenger, const KernelLabels* labels = nullptr,
+                                                 AbortSignal abort_signal = nullptr, const F* forced_pow_witness = nullptr) {
+    std::array<F, 12> st = challenger.compact();
+    zkgpu_proof* p = nullptr;
+    check(zkgpu_prove_table(ctx.handle(), (uint32_t)table, labels, &config, trace_commitment.handle(), ctl_data.handle(), st.data(),
+                            forced_pow_witness, abort_ptr(abort_signal), &p));
+    challenger.set_state(st);
+    return take_proof(p);
+}
+
+// AllProof / MultiProof (proof.rs:29-54): stark_proofs[t] is None for an optional table that is not in use
+struct AllProof {
+    std::array<std::optional<StarkProofWithMetadata>, NUM_TABLES> stark_proofs;
+    GrandProductChallengeSet ctl_challenges;
+    std::array<MerkleCap, NUM_TABLES> trace_caps;
+    const MerkleCap& mem_before_cap() const { return trace_caps[(size_t)Table::MemBefore]; }       // MemCap, prover.rs:261-271
+    const MerkleCap& mem_after_cap() const { return trace_caps[(size_t)Table::MemAfter]; }
+};
+
+// one table's trace: Vec<PolynomialValues<F>> as one contiguous column-major block (column c at data + c*n); empty = table not in use
+struct TableTrace {
+    const F* cols = nullptr;
+    size_t n = 0;
+};
+
+// prove_with_traces (prover.rs:72-194).  public_values: the elements observe_public_values feeds the challenger, in order
+// (get_challenges.rs:202-227).  mem_kind: ZKGPU_MEM_HOST, ZKGPU_MEM_DEVICE or ZKGPU_MEM_AUTO (per-table pointers of either kind).
+inline AllProof prove_with_traces(Context& ctx, const std::array<TableTrace, NUM_TABLES>& trace_poly_values, const std::vector<F>& public_values,
+                                  const StarkConfig& config, const KernelLabels& labels, AbortSignal abort_signal = nullptr,
+                                  int mem_kind = ZKGPU_MEM_HOST, const std::array<F, NUM_TABLES>* forced_pow_witnesses = nullptr) {
+    std::array<zkgpu_table_trace, NUM_TABLES> tr;
+    for (size_t t = 0; t < NUM_TABLES; t++) tr[t] = {trace_poly_values[t].cols, trace_poly_values[t].n};
+    std::array<zkgpu_proof*, NUM_TABLES> proofs{};
+    const size_t cap_words = (size_t)4 << config.cap_height;
+    std::vector<uint64_t> bg(4, 0), caps(NUM_TABLES * cap_words, 0);
+    check(zkgpu_prove_segment(ctx.handle(), tr.data(), mem_kind, public_values.data(), public_values.size(), &labels, &config,
+                              forced_pow_witnesses ? forced_pow_witnesses->data() : nullptr, abort_ptr(abort_signal), proofs.data(), bg.data(),
+                              caps.data()));
+    AllProof out;
+    out.ctl_challenges.beta_gamma.assign(bg.begin(), bg.begin() + 2 * config.num_challenges);
+    for (size_t t = 0; t < NUM_TABLES; t++) {
+        out.trace_caps[t] = cap_from_words(&caps[t * cap_words], cap_words);
+        if (proofs[t]) out.stark_proofs[t] = take_proof(proofs[t]);
+    }
+    return out;
+}
+
+// a trace finished in device memory (zkgpu_dev_trace): KeccakStark / LogicStark generate_trace, the Arithmetic range-check columns,
+// the derived Memory columns (include/zkgpu.h "device-side trace finishing")
+class DeviceTrace {
+public:
+    // KeccakStark::generate_trace(inputs_and_timestamps, min_rows)   keccak/keccak_stark.rs:70-250
+    static DeviceTrace keccak_generate_trace(Context& ctx, const std::vector<std::pair<std::array<uint64_t, 25>, size_t>>& inputs_and_timestamps,
+                                             size_t min_rows) {
+        std::vector<uint64_t> in(inputs_and_timestamps.size() * 25), ts(inputs_and_timestamps.size());
+        for (size_t i = 0; i < ts.size(); i++) {
+            for (int k = 0; k < 25; k++) in[25 * i + k] = inputs_and_timestamps[i].first[k];
+            ts[i] = inputs_and_timestamps[i].second;
+        }
+        zkgpu_dev_trace* t = nullptr;
+        check(zkgpu_keccak_generate_trace(ctx.handle(), in.data(), ts.data(), ts.size(), min_rows, &t));
+        ctx.sync();                                     // `in` / `ts` are temporaries
+        return DeviceTrace(t);
+    }
+    // LogicStark::generate_trace(operations, min_rows)   logic.rs:165-237; one operation = {operator, input0 limbs, input1 limbs}
+    static DeviceTrace logic_generate_trace(Context& ctx, const std::vector<std::array<uint64_t, 9>>& operations, size_t min_rows) {
+        zkgpu_dev_trace* t = nullptr;
+        check(zkgpu_logic_generate_trace(ctx.handle(), operations.empty() ? nullptr : operations[0].data(), operations.size(), min_rows, &t));
+        ctx.sync();
+        return DeviceTrace(t);
+    }
+    TableTrace as_table_trace() const {
+        size_t nc = 0, n = 0;
+        check(zkgpu_dev_trace_dims(h_.get(), &nc, &n));
+        return TableTrace{zkgpu_dev_trace_ptr(h_.get()), n};
+    }
+    std::vector<F> to_host() const {
+        size_t nc = 0, n = 0;
+        check(zkgpu_dev_trace_dims(h_.get(), &nc, &n));
+        std::vector<F> v(nc * n);
+        check(zkgpu_dev_trace_export(h_.get(), v.data()));
+        return v;
+    }
+    zkgpu_dev_trace* handle() const { return h_.get(); }
+private:
+    struct Del { void operator()(zkgpu_dev_trace* t) const { zkgpu_dev_trace_free(t); } };
+    explicit DeviceTrace(zkgpu_dev_trace* t) : h_(t) {}
+    std::unique_ptr<zkgpu_dev_trace, Del> h_;
+};
+
+}  // namespace zkgpu

@@ -1,0 +1,141 @@
+// C++ host harness over include/zkgpu.hpp (the compiled-language mirror of the reference interface).  Driven by tests/test_host_mirror.py:
+//   host_mirror nodevice                         Context(0) must throw Error{ZKGPU_ERR_CUDA} on a box without a GPU (no CPU path)
+//   host_mirror challenger <n>                   observe 1..n, draw 3 challenges, compact -> prints the challenges and the state
+//   host_mirror decode <proof.words>             typed StarkProof fields of a serialised proof, and re-serialisation equality
+//   host_mirror prove <segment.trace> <out> [test|fast]   prove_with_traces on cuda:0 from a segment trace file (zk_evm_b200/trace_file.py
+//                                                layout) -> writes ctl challenges, trace caps and every table's proof words to <out>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <fstream>
+#include <iostream>
+#include "zkgpu.hpp"
+
+using namespace zkgpu;
+
+static std::vector<uint64_t> read_words(const char* path) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+    const size_t bytes = (size_t)f.tellg();
+    std::vector<uint64_t> w(bytes / 8);
+    f.seekg(0);
+    f.read((char*)w.data(), (std::streamsize)(w.size() * 8));
+    return w;
+}
+
+// segment trace container (trace_file.py): header "ZKSEGTR1", u32 version, u32 num_tables, u64 n_public, u64 labels[4], then per table
+// u32 in_use, u32 num_columns, u64 n, u64 offset; public values at the next 64-byte boundary; column-major blocks at `offset`
+struct Segment {
+    std::vector<uint8_t> bytes;
+    std::array<TableTrace, NUM_TABLES> traces;
+    std::vector<F> public_values;
+    KernelLabels labels;
+};
+static Segment load_segment(const char* path) {
+    Segment s;
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+    s.bytes.resize((size_t)f.tellg());
+    f.seekg(0);
+    f.read((char*)s.bytes.data(), (std::streamsize)s.bytes.size());
+    const uint8_t* b = s.bytes.data();
+    if (s.bytes.size() < 56 + 24 * NUM_TABLES || memcmp(b, "ZKSEGTR1", 8)) throw std::runtime_error("not a segment trace file");
+    uint32_t version, ntab; uint64_t npv, lab[4];
+    memcpy(&version, b + 8, 4); memcpy(&ntab, b + 12, 4); memcpy(&npv, b + 16, 8); memcpy(lab, b + 24, 32);
+    if (version != 1 || ntab != NUM_TABLES) throw std::runtime_error("unsupported trace file version");
+    s.labels = KernelLabels{lab[0], lab[1], lab[2], lab[3]};
+    const size_t dir = 56, pv_off = (dir + 24 * NUM_TABLES + 63) / 64 * 64;
+    s.public_values.resize(npv);
+    memcpy(s.public_values.data(), b + pv_off, npv * 8);
+    for (size_t t = 0; t < NUM_TABLES; t++) {
+        uint32_t in_use, nc; uint64_t n, off;
+        memcpy(&in_use, b + dir + 24 * t, 4); memcpy(&nc, b + dir + 24 * t + 4, 4); memcpy(&n, b + dir + 24 * t + 8, 8); memcpy(&off, b + dir + 24 * t + 16, 8);
+        if (in_use) {
+            if (off + 8 * (uint64_t)nc * n > s.bytes.size()) throw std::runtime_error("truncated trace file");
+            s.traces[t] = TableTrace{(const F*)(b + off), (size_t)n};
+        }
+    }
+    return s;
+}
+
+int main(int argc, char** argv) {
+    try {
+        const std::string mode = argc > 1 ? argv[1] : "";
+        if (mode == "nodevice") {
+            try {
+                Context ctx(0);
+                printf("device present\n");
+                return 0;
+            } catch (const Error& e) {
+                printf("error %d: %s\n", e.code, e.what());
+                return e.code == ZKGPU_ERR_CUDA ? 0 : 1;
+            }
+        }
+        if (mode == "challenger" && argc > 2) {
+            Challenger ch;
+            std::vector<F> xs;
+            for (int i = 1; i <= atoi(argv[2]); i++) xs.push_back((F)i);
+            ch.observe_elements(xs);
+            for (F c : ch.get_n_challenges(3)) printf("%llu\n", (unsigned long long)c);
+            ch.observe_element(7);
+            for (F c : ch.compact()) printf("%llu\n", (unsigned long long)c);
+            auto ch2 = Challenger::from_state(ch.compact());
+            printf("%llu\n", (unsigned long long)ch2->get_challenge());
+            return 0;
+        }
+        if (mode == "decode" && argc > 2) {
+            const std::vector<uint64_t> w = read_words(argv[2]);
+            size_t used = 0;
+            const zkstark::StarkProofData p = zkstark::deserialize_proof(w.data(), w.size(), &used);
+            const bool same = zkstark::serialize_proof(p) == w && used == w.size();
+            printf("table %llu degree_bits %llu trace_cap %zu aux_cap %zu quotient_cap %zu local %zu next %zu aux %zu ctl_zs_first %zu quotient %zu "
+                   "layers %zu queries %zu final_poly %zu pow %llu roundtrip %d\n",
+                   (unsigned long long)p.table_id, (unsigned long long)p.degree_bits, p.trace_cap.size() / 4, p.aux_cap.size() / 4,
+                   p.quotient_cap.size() / 4, p.local_values.size() / 2, p.next_values.size() / 2, p.aux_polys.size() / 2, p.ctl_zs_first.size(),
+                   p.quotient_polys.size() / 2, p.commit_phase_caps.size(), p.queries.size(), p.final_poly.size() / 2,
+                   (unsigned long long)p.pow_witness, (int)same);
+            return same ? 0 : 1;
+        }
+        if (mode == "prove" && argc > 3) {
+            const Segment seg = load_segment(argv[2]);
+            const StarkConfig cfg = (argc > 4 && std::string(argv[4]) == "fast") ? StarkConfig::standard_fast_config() : StarkConfig::test_config();
+            Context ctx(0);
+            std::atomic<int> abort_signal{0};
+            const AllProof ap = prove_with_traces(ctx, seg.traces, seg.public_values, cfg, seg.labels, &abort_signal);
+            // the same Cpu trace through the per-table seam: from_values on its columns gives the cap prove_with_traces observed
+            {
+                const TableTrace& ct = seg.traces[(size_t)Table::Cpu];
+                std::vector<PolynomialValues> cols(85);
+                for (size_t c = 0; c < cols.size(); c++) cols[c].assign(ct.cols + c * ct.n, ct.cols + (c + 1) * ct.n);
+                const PolynomialBatch batch = PolynomialBatch::from_values(ctx, cols, cfg.rate_bits, cfg.cap_height);
+                if (batch.cap() != ap.trace_caps[(size_t)Table::Cpu]) { printf("from_values cap differs from the segment's\n"); return 1; }
+                if (batch.num_polys() != 85 || batch.degree() != ct.n) { printf("batch dims\n"); return 1; }
+            }
+            // an abort signal that is already raised stops the proof with ZKGPU_ERR_ABORTED (check_abort_signal, prover.rs:346-354)
+            abort_signal = 1;
+            try {
+                prove_with_traces(ctx, seg.traces, seg.public_values, cfg, seg.labels, &abort_signal);
+                printf("abort signal ignored\n");
+                return 1;
+            } catch (const Error& e) {
+                if (e.code != ZKGPU_ERR_ABORTED) throw;
+            }
+            std::ofstream out(argv[3], std::ios::binary);
+            auto put = [&](const std::vector<uint64_t>& v) { uint64_t l = v.size(); out.write((const char*)&l, 8); out.write((const char*)v.data(), (std::streamsize)(8 * v.size())); };
+            put(ap.ctl_challenges.beta_gamma);
+            for (size_t t = 0; t < NUM_TABLES; t++) {
+                std::vector<uint64_t> cap;
+                for (const Hash& h : ap.trace_caps[t]) cap.insert(cap.end(), h.begin(), h.end());
+                put(cap);
+                put(ap.stark_proofs[t] ? ap.stark_proofs[t]->words : std::vector<uint64_t>());
+            }
+            printf("proved %zu tables\n", (size_t)std::count_if(ap.stark_proofs.begin(), ap.stark_proofs.end(), [](const auto& p) { return p.has_value(); }));
+            return 0;
+        }
+        fprintf(stderr, "usage: host_mirror nodevice | challenger <n> | decode <proof.words> | prove <segment.trace> <out> [test|fast]\n");
+        return 2;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "host_mirror: %s\n", e.what());
+        return 1;
+    }
+}

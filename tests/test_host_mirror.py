@@ -1,0 +1,102 @@
+"""The compiled-language host side: include/zkgpu.hpp (C++17 mirror of the reference interface over the C ABI) through the harness
+tests/native/host_mirror.cpp.  CPU: it builds and links against libzkgpu.so, fails loudly without a device (no CPU path), its Challenger
+agrees with the oracle's, its typed StarkProof decoder round-trips oracle proofs.  GPU: prove_with_traces / PolynomialBatch::from_values /
+the abort signal from C++ on a segment handed over as a trace file, proofs bit for bit against the oracle."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import traces
+from tests.oracle_lib import orc_prove_segment, orc_prove_table, TEST_CONFIG, STANDARD_FAST, DEFAULT_LABELS
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "native", "host_mirror.cpp")
+BIN = os.path.join(HERE, "native", "host_mirror")
+LIBDIR = os.path.join(ROOT, "zk_evm_b200")
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not available")
+
+
+@pytest.fixture(scope="module")
+def harness():
+    import zk_evm_b200
+    zk_evm_b200.lib()                      # libzkgpu.so must exist (built by __graft_entry__.build())
+    deps = [SRC, os.path.join(ROOT, "include", "zkgpu.hpp"), os.path.join(ROOT, "include", "zkgpu.h"),
+            os.path.join(LIBDIR, "csrc", "stark", "proof.h")]
+    if not os.path.exists(BIN) or any(os.path.getmtime(d) > os.path.getmtime(BIN) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", BIN, SRC,
+                               "-L", LIBDIR, "-lzkgpu", "-Wl,-rpath," + LIBDIR])
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = ":".join(p for p in (env.get("LD_LIBRARY_PATH"), "/usr/local/cuda/lib64") if p)
+
+    def run(*args, ok=True):
+        r = subprocess.run([BIN] + [str(a) for a in args], capture_output=True, text=True, env=env, timeout=900)
+        if ok:
+            assert r.returncode == 0, (r.stdout, r.stderr)
+        return r
+    return run
+
+
+def test_cpp_host_builds_and_has_no_cpu_path(harness):
+    import torch
+    out = harness("nodevice").stdout
+    if not torch.cuda.is_available():
+        assert out.startswith("error -2"), out            # ZKGPU_ERR_CUDA
+
+
+def test_cpp_challenger_matches_oracle(harness, oracle):
+    words = [int(x) for x in harness("challenger", 20).stdout.split()]
+    ops = [("o", v) for v in range(1, 21)] + [("c",)] * 3 + [("o", 7), ("k",)]
+    ch, st = oracle.challenger_run(ops)
+    assert words[:3] == [int(c) for c in ch[:3]]
+    assert words[3:15] == [int(x) for x in st]
+    ch2, _ = oracle.challenger_run(ops + [("c",)])
+    assert words[15] == int(ch2[3])
+
+
+@pytest.mark.parametrize("table,lg,cfg", [(traces.T_MEM_AFTER, 7, TEST_CONFIG), (traces.T_LOGIC, 6, STANDARD_FAST)])
+def test_cpp_proof_decoder_on_oracle_proofs(harness, oracle, tmp_path, table, lg, cfg):
+    tr = traces.memcont_trace(lg, 3) if table == traces.T_MEM_AFTER else traces.logic_trace(lg, 3)
+    bg = np.array([5, 6, 7, 8], dtype=np.uint64)[:2 * cfg[1]]
+    proof, _ = orc_prove_table(oracle, table, cfg, tr, bg, np.arange(12, dtype=np.uint64))
+    path = tmp_path / "proof.words"
+    proof.astype("<u8").tofile(path)
+    out = harness("decode", path).stdout.split()
+    f = dict(zip(out[0::2], out[1::2]))
+    assert int(f["table"]) == table and int(f["degree_bits"]) == lg and int(f["roundtrip"]) == 1
+    assert int(f["trace_cap"]) == int(f["quotient_cap"]) == 1 << cfg[3]
+    assert int(f["local"]) == int(f["next"]) == traces.NUM_COLUMNS[table]
+    assert int(f["quotient"]) == 2 * cfg[1] and int(f["queries"]) == cfg[7] and int(f["pow"]) == int(proof[-1])
+    # a truncated proof is refused, not misread
+    proof[:-5].astype("<u8").tofile(path)
+    assert harness("decode", path, ok=False).returncode != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,cfg", [("test", TEST_CONFIG), ("fast", STANDARD_FAST)])
+def test_cpp_prove_with_traces_matches_oracle(harness, oracle, tmp_path, name, cfg):
+    from zk_evm_b200 import trace_file
+    tr = traces.valid_segment(seed=21, k=19)
+    pv = np.arange(1000, 1037, dtype=np.uint64)
+    seg, out = tmp_path / "segment.trace", tmp_path / "proofs.bin"
+    trace_file.save(seg, tr, pv, DEFAULT_LABELS)
+    r = harness("prove", seg, out, name)
+    assert "proved 5 tables" in r.stdout, (r.stdout, r.stderr)
+    want, bg, caps = orc_prove_segment(oracle, cfg, tr, pv)
+    w = np.fromfile(out, dtype="<u8")
+    pos = 0
+
+    def take():
+        nonlocal pos
+        n = int(w[pos]); v = w[pos + 1:pos + 1 + n]; pos += 1 + n
+        return v
+    assert np.array_equal(take(), bg)
+    for t in range(9):
+        assert np.array_equal(take(), caps[t].ravel()), "table %d cap" % t
+        p = take()
+        assert (p.size == 0) == (want[t] is None)
+        assert want[t] is None or np.array_equal(p, want[t]), "table %d proof differs from the oracle" % t
+    assert pos == w.size
