@@ -208,6 +208,65 @@ inline StarkProofWithMetadata prove_single_table(Context& ctx, Table table, cons
     return take_proof(p);
 }
 
+// prove_single_table split where the shared transcript is first needed (tables of one segment on several GPUs): begin = auxiliary
+// polynomials + their commitment (needs only the CTL challenges), finish = everything that consumes the transcript
+class TableJob {
+public:
+    static TableJob begin(Context& ctx, Table table, const StarkConfig& config, const PolynomialBatch& trace_commitment, const CtlData& ctl_data,
+                          const KernelLabels* labels = nullptr, AbortSignal abort_signal = nullptr) {
+        zkgpu_table_job* j = nullptr;
+        check(zkgpu_table_job_begin(ctx.handle(), (uint32_t)table, labels, &config, trace_commitment.handle(), ctl_data.handle(),
+                                    abort_ptr(abort_signal), &j));
+        return TableJob(j);
+    }
+    StarkProofWithMetadata finish(std::array<F, 12>& challenger_state, AbortSignal abort_signal = nullptr, const F* forced_pow_witness = nullptr) {
+        zkgpu_proof* p = nullptr;
+        check(zkgpu_table_job_finish(h_.get(), challenger_state.data(), forced_pow_witness, abort_ptr(abort_signal), &p));
+        return take_proof(p);
+    }
+private:
+    struct Del { void operator()(zkgpu_table_job* j) const { zkgpu_table_job_free(j); } };
+    explicit TableJob(zkgpu_table_job* j) : h_(j) {}
+    std::unique_ptr<zkgpu_table_job, Del> h_;
+};
+
+// prover.rs:118-144: a fresh challenger observes the nine trace caps in Table order (a zero cap for an optional table that is not in
+// use, :120-123) and the public values (observe_public_values), then draws the CTL challenges; returns them and leaves `challenger`
+// where get_ctl_data leaves the reference's
+inline GrandProductChallengeSet segment_challenges(Challenger& challenger, const std::array<std::optional<MerkleCap>, NUM_TABLES>& trace_caps,
+                                                   const std::vector<F>& public_values, const StarkConfig& config) {
+    const size_t cap_words = (size_t)4 << config.cap_height;
+    std::vector<uint64_t> caps(NUM_TABLES * cap_words, 0);
+    std::array<uint8_t, NUM_TABLES> in_use{};
+    for (size_t t = 0; t < NUM_TABLES; t++) {
+        in_use[t] = trace_caps[t].has_value();
+        if (!in_use[t]) continue;
+        if (trace_caps[t]->size() * 4 != cap_words) throw Error(ZKGPU_ERR_INVALID, "cap of the wrong height");
+        for (size_t i = 0; i < trace_caps[t]->size(); i++) for (int k = 0; k < 4; k++) caps[t * cap_words + 4 * i + k] = (*trace_caps[t])[i][k];
+    }
+    GrandProductChallengeSet ch;
+    ch.beta_gamma.resize(2 * config.num_challenges);
+    std::array<F, 12> st;
+    check(zkgpu_segment_challenges(caps.data(), in_use.data(), config.cap_height, public_values.data(), public_values.size(), config.num_challenges,
+                                   ch.beta_gamma.data(), st.data()));
+    challenger.set_state(st);
+    return ch;
+}
+
+// prove_with_commitments (prover.rs:211-293): the tables in Table order, one shared challenger (:251-259); None for a table not in use
+inline std::array<std::optional<StarkProofWithMetadata>, NUM_TABLES>
+prove_with_commitments(Context& ctx, const StarkConfig& config, const std::array<const PolynomialBatch*, NUM_TABLES>& trace_commitments,
+                       const std::array<const CtlData*, NUM_TABLES>& ctl_data_per_table, Challenger& challenger, const KernelLabels& labels,
+                       AbortSignal abort_signal = nullptr) {
+    std::array<std::optional<StarkProofWithMetadata>, NUM_TABLES> proofs;
+    for (size_t t = 0; t < NUM_TABLES; t++) {
+        if (!trace_commitments[t]) continue;
+        if (!ctl_data_per_table[t]) throw Error(ZKGPU_ERR_INVALID, "a table in use needs its CtlData");
+        proofs[t] = prove_single_table(ctx, (Table)t, config, *trace_commitments[t], *ctl_data_per_table[t], challenger, &labels, abort_signal);
+    }
+    return proofs;
+}
+
 // AllProof / MultiProof (proof.rs:29-54): stark_proofs[t] is None for an optional table that is not in use
 struct AllProof {
     std::array<std::optional<StarkProofWithMetadata>, NUM_TABLES> stark_proofs;

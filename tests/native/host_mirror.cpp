@@ -111,6 +111,37 @@ int main(int argc, char** argv) {
                 if (batch.cap() != ap.trace_caps[(size_t)Table::Cpu]) { printf("from_values cap differs from the segment's\n"); return 1; }
                 if (batch.num_polys() != 85 || batch.degree() != ct.n) { printf("batch dims\n"); return 1; }
             }
+            // the same segment through the reference's seams: from_values per table (S1) -> transcript + CTL challenges -> get_ctl_data (S2)
+            // -> prove_with_commitments (S3, one shared challenger) must give the proofs of the one-call path, word for word
+            {
+                std::vector<std::unique_ptr<PolynomialBatch>> batches(NUM_TABLES);
+                std::vector<std::unique_ptr<CtlData>> ctls(NUM_TABLES);
+                std::array<std::optional<MerkleCap>, NUM_TABLES> caps;
+                const uint32_t widths[NUM_TABLES] = {116, 71, 85, 2431, 438, 523, 30, 12, 12};
+                for (size_t t = 0; t < NUM_TABLES; t++) {
+                    if (!seg.traces[t].cols) continue;
+                    batches[t] = std::make_unique<PolynomialBatch>(PolynomialBatch::from_values_contig(ctx, seg.traces[t].cols, widths[t], seg.traces[t].n,
+                                                                                                       cfg.rate_bits, cfg.cap_height));
+                    caps[t] = batches[t]->cap();
+                }
+                Challenger challenger;
+                const GrandProductChallengeSet ctl_challenges = segment_challenges(challenger, caps, seg.public_values, cfg);
+                if (ctl_challenges.beta_gamma != ap.ctl_challenges.beta_gamma) { printf("CTL challenges differ\n"); return 1; }
+                std::array<const PolynomialBatch*, NUM_TABLES> bp{};
+                std::array<const CtlData*, NUM_TABLES> cp{};
+                for (size_t t = 0; t < NUM_TABLES; t++) {
+                    if (!batches[t]) continue;
+                    ctls[t] = std::make_unique<CtlData>(get_ctl_data(ctx, (Table)t, *batches[t], ctl_challenges, cfg.num_challenges));
+                    bp[t] = batches[t].get(); cp[t] = ctls[t].get();
+                }
+                const auto proofs = prove_with_commitments(ctx, cfg, bp, cp, challenger, seg.labels);
+                for (size_t t = 0; t < NUM_TABLES; t++) {
+                    if (proofs[t].has_value() != ap.stark_proofs[t].has_value() || (proofs[t] && proofs[t]->words != ap.stark_proofs[t]->words)) {
+                        printf("prove_with_commitments differs from prove_with_traces on table %zu\n", t);
+                        return 1;
+                    }
+                }
+            }
             // an abort signal that is already raised stops the proof with ZKGPU_ERR_ABORTED (check_abort_signal, prover.rs:346-354)
             abort_signal = 1;
             try {
