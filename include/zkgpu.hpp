@@ -304,6 +304,90 @@ inline AllProof prove_with_traces(Context& ctx, const std::array<TableTrace, NUM
     return out;
 }
 
+// ---- PublicValues -> the elements observe_public_values feeds the challenger (get_challenges.rs:11-227) --------------------------------
+// proof.rs:68-91, 314-321, 357-364, 398-425, 471-488.  H256 / Address are big-endian byte strings, U256 is four little-endian u64 limbs
+// (ethereum_types).  2217 elements with the default eth_mainnet feature (24 * 2 + 97 + 2056 + 16, proof.rs:652-655); the registers and
+// the memory caps are not observed.
+using H256 = std::array<uint8_t, 32>;
+using Address = std::array<uint8_t, 20>;
+struct U256 {
+    std::array<uint64_t, 4> limbs{};                   // U256.0
+    U256() = default;
+    U256(uint64_t x) { limbs[0] = x; }
+    static U256 from_big_endian(const uint8_t* b, size_t len) {
+        U256 r;
+        for (size_t i = 0; i < len; i++) r.limbs[(len - 1 - i) / 8] |= (uint64_t)b[i] << (8 * ((len - 1 - i) % 8));
+        return r;
+    }
+};
+struct TrieRoots { H256 state_root{}, transactions_root{}, receipts_root{}; };
+struct BlockMetadata {
+    Address block_beneficiary{};
+    U256 block_timestamp, block_number, block_difficulty;
+    H256 block_random{};
+    U256 block_gaslimit, block_chain_id, block_base_fee, block_gas_used, block_blob_gas_used, block_excess_blob_gas;
+    H256 parent_beacon_block_root{};
+    std::array<U256, 8> block_bloom;
+};
+struct BlockHashes { std::vector<H256> prev_hashes = std::vector<H256>(256); H256 cur_hash{}; };
+struct ExtraBlockData {
+    H256 checkpoint_state_trie_root{};
+    std::array<F, 4> checkpoint_consolidated_hash{};
+    U256 txn_number_before, txn_number_after, gas_used_before, gas_used_after;
+};
+struct PublicValues {
+    TrieRoots trie_roots_before, trie_roots_after;
+    BlockMetadata block_metadata;
+    BlockHashes block_hashes;
+    ExtraBlockData extra_block_data;
+    std::optional<U256> burn_addr;                     // cdk_erigon only
+};
+namespace detail {
+inline void u256_limbs(std::vector<F>& o, const U256& x, size_t count = 8) {                     // util.rs:101-113
+    for (size_t i = 0; i < count; i++) o.push_back((x.limbs[i / 2] >> (32 * (i % 2))) & 0xFFFFFFFFull);
+}
+inline void h256_limbs(std::vector<F>& o, const H256& h) { u256_limbs(o, U256::from_big_endian(h.data(), 32)); }   // util.rs:116-126, observe_root
+inline void u256_to_u32(std::vector<F>& o, const U256& x) {                                      // util.rs:40-46
+    if (x.limbs[1] | x.limbs[2] | x.limbs[3] | (x.limbs[0] >> 32)) throw Error(ZKGPU_ERR_INVALID, "IntegerTooLarge: public value does not fit 32 bits");
+    o.push_back(x.limbs[0]);
+}
+inline void u256_to_u64(std::vector<F>& o, const U256& x) {                                      // util.rs:50-59
+    if (x.limbs[1] | x.limbs[2] | x.limbs[3]) throw Error(ZKGPU_ERR_INVALID, "IntegerTooLarge: public value does not fit 64 bits");
+    o.push_back(x.limbs[0] & 0xFFFFFFFFull);
+    o.push_back(x.limbs[0] >> 32);
+}
+inline void trie_roots(std::vector<F>& o, const TrieRoots& r) { h256_limbs(o, r.state_root); h256_limbs(o, r.transactions_root); h256_limbs(o, r.receipts_root); }
+}  // namespace detail
+// observe_public_values (get_challenges.rs:202-227) as the list of observed elements, ready for prove_with_traces
+inline std::vector<F> flatten_public_values(const PublicValues& pv, bool eth_mainnet = true, bool cdk_erigon = false) {
+    using namespace detail;
+    std::vector<F> o;
+    o.reserve(2232);
+    trie_roots(o, pv.trie_roots_before);
+    trie_roots(o, pv.trie_roots_after);
+    const BlockMetadata& m = pv.block_metadata;                                                  // observe_block_metadata, :45-81
+    u256_limbs(o, U256::from_big_endian(m.block_beneficiary.data(), 20), 5);
+    u256_to_u32(o, m.block_timestamp); u256_to_u32(o, m.block_number); u256_to_u32(o, m.block_difficulty);
+    h256_limbs(o, m.block_random);
+    u256_to_u32(o, m.block_gaslimit); u256_to_u32(o, m.block_chain_id);
+    u256_to_u64(o, m.block_base_fee);
+    u256_to_u32(o, m.block_gas_used);
+    if (eth_mainnet) { u256_to_u64(o, m.block_blob_gas_used); u256_to_u64(o, m.block_excess_blob_gas); h256_limbs(o, m.parent_beacon_block_root); }
+    for (const U256& w : m.block_bloom) u256_limbs(o, w);
+    if (pv.block_hashes.prev_hashes.size() != 256) throw Error(ZKGPU_ERR_INVALID, "256 previous block hashes");   // observe_block_hashes, :172-184
+    for (const H256& h : pv.block_hashes.prev_hashes) h256_limbs(o, h);
+    h256_limbs(o, pv.block_hashes.cur_hash);
+    const ExtraBlockData& e = pv.extra_block_data;                                               // observe_extra_block_data, :108-123
+    h256_limbs(o, e.checkpoint_state_trie_root);
+    for (F x : e.checkpoint_consolidated_hash) o.push_back(x);
+    u256_to_u32(o, e.txn_number_before); u256_to_u32(o, e.txn_number_after); u256_to_u32(o, e.gas_used_before); u256_to_u32(o, e.gas_used_after);
+    if (cdk_erigon) {
+        if (!pv.burn_addr) throw Error(ZKGPU_ERR_INVALID, "There should be an address set in cdk_erigon.");
+        u256_limbs(o, *pv.burn_addr);
+    }
+    return o;
+}
+
 // a trace finished in device memory (zkgpu_dev_trace): KeccakStark / LogicStark generate_trace, the Arithmetic range-check columns,
 // the derived Memory columns (include/zkgpu.h "device-side trace finishing")
 class DeviceTrace {

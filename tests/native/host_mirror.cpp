@@ -1,6 +1,7 @@
 // C++ host harness over include/zkgpu.hpp (the compiled-language mirror of the reference interface).  Driven by tests/test_host_mirror.py:
 //   host_mirror nodevice                         Context(0) must throw Error{ZKGPU_ERR_CUDA} on a box without a GPU (no CPU path)
 //   host_mirror challenger <n>                   observe 1..n, draw 3 challenges, compact -> prints the challenges and the state
+//   host_mirror pubvals <file>                   PublicValues read from a packed byte file -> the flattened elements observe_public_values feeds
 //   host_mirror decode <proof.words>             typed StarkProof fields of a serialised proof, and re-serialisation equality
 //   host_mirror prove <segment.trace> <out> [test|fast]   prove_with_traces on cuda:0 from a segment trace file (zk_evm_b200/trace_file.py
 //                                                layout) -> writes ctl challenges, trace caps and every table's proof words to <out>
@@ -9,6 +10,7 @@
 #include <algorithm>
 #include <fstream>
 #include <iostream>
+#include <iterator>
 #include "zkgpu.hpp"
 
 using namespace zkgpu;
@@ -81,6 +83,30 @@ int main(int argc, char** argv) {
             for (F c : ch.compact()) printf("%llu\n", (unsigned long long)c);
             auto ch2 = Challenger::from_state(ch.compact());
             printf("%llu\n", (unsigned long long)ch2->get_challenge());
+            return 0;
+        }
+        if (mode == "pubvals" && argc > 2) {
+            std::ifstream f(argv[2], std::ios::binary);
+            std::vector<uint8_t> b((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+            size_t pos = 0;
+            auto h256 = [&]() { H256 h; memcpy(h.data(), &b.at(pos + 31) - 31, 32); pos += 32; return h; };
+            auto u256 = [&]() { U256 x = U256::from_big_endian(&b.at(pos + 31) - 31, 32); pos += 32; return x; };
+            PublicValues pv;
+            for (TrieRoots* r : {&pv.trie_roots_before, &pv.trie_roots_after}) { r->state_root = h256(); r->transactions_root = h256(); r->receipts_root = h256(); }
+            BlockMetadata& m = pv.block_metadata;
+            memcpy(m.block_beneficiary.data(), &b.at(pos + 19) - 19, 20); pos += 20;
+            m.block_timestamp = u256(); m.block_number = u256(); m.block_difficulty = u256(); m.block_random = h256();
+            m.block_gaslimit = u256(); m.block_chain_id = u256(); m.block_base_fee = u256(); m.block_gas_used = u256();
+            m.block_blob_gas_used = u256(); m.block_excess_blob_gas = u256(); m.parent_beacon_block_root = h256();
+            for (U256& w : m.block_bloom) w = u256();
+            for (H256& h : pv.block_hashes.prev_hashes) h = h256();
+            pv.block_hashes.cur_hash = h256();
+            ExtraBlockData& e = pv.extra_block_data;
+            e.checkpoint_state_trie_root = h256();
+            memcpy(e.checkpoint_consolidated_hash.data(), &b.at(pos + 31) - 31, 32); pos += 32;
+            e.txn_number_before = u256(); e.txn_number_after = u256(); e.gas_used_before = u256(); e.gas_used_after = u256();
+            if (pos != b.size()) throw std::runtime_error("trailing bytes");
+            for (F x : flatten_public_values(pv)) printf("%llu\n", (unsigned long long)x);
             return 0;
         }
         if (mode == "decode" && argc > 2) {

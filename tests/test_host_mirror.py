@@ -57,6 +57,55 @@ def test_cpp_challenger_matches_oracle(harness, oracle):
     assert words[15] == int(ch2[3])
 
 
+def _random_public_values(seed):
+    from zk_evm_b200 import public_values as pvm
+    rng = np.random.default_rng(seed)
+    h = lambda: rng.bytes(32)
+    r = lambda bits: int.from_bytes(rng.bytes(bits // 8), "big")
+    return pvm.PublicValues(
+        pvm.TrieRoots(h(), h(), h()), pvm.TrieRoots(h(), h(), h()),
+        pvm.BlockMetadata(rng.bytes(20), r(32), r(32), r(32), h(), r(32), r(32), r(64), r(32), r(64), r(64), h(), [r(256) for _ in range(8)]),
+        pvm.BlockHashes([h() for _ in range(256)], h()),
+        pvm.ExtraBlockData(h(), [int(x) for x in rng.integers(0, 0xFFFFFFFF00000001, size=4, dtype=np.uint64)], r(32), r(32), r(32), r(32)))
+
+
+def _pack_public_values(pv):
+    be = lambda x: int(x).to_bytes(32, "big")
+    m, e = pv.block_metadata, pv.extra_block_data
+    out = b"".join(bytes(x) for rr in (pv.trie_roots_before, pv.trie_roots_after) for x in (rr.state_root, rr.transactions_root, rr.receipts_root))
+    out += bytes(m.block_beneficiary) + be(m.block_timestamp) + be(m.block_number) + be(m.block_difficulty) + bytes(m.block_random)
+    out += be(m.block_gaslimit) + be(m.block_chain_id) + be(m.block_base_fee) + be(m.block_gas_used) + be(m.block_blob_gas_used)
+    out += be(m.block_excess_blob_gas) + bytes(m.parent_beacon_block_root) + b"".join(be(w) for w in m.block_bloom)
+    out += b"".join(bytes(x) for x in pv.block_hashes.prev_hashes) + bytes(pv.block_hashes.cur_hash)
+    out += bytes(e.checkpoint_state_trie_root) + np.array(e.checkpoint_consolidated_hash, dtype="<u8").tobytes()
+    out += be(e.txn_number_before) + be(e.txn_number_after) + be(e.gas_used_before) + be(e.gas_used_after)
+    return out
+
+
+def test_public_values_flattening_python_and_cpp(harness, tmp_path):
+    """observe_public_values as an element list (get_challenges.rs:202-227): the reference's own sizes, a hand-derived root, and the
+    C++ and Python host mirrors against each other on random values"""
+    from zk_evm_b200 import public_values as pvm
+    pv = pvm.PublicValues()
+    assert len(pvm.flatten_public_values(pv)) == 24 * 2 + 97 + 2056 + 16          # proof.rs:652-655, 981, 1193, 1382, 1469
+    assert len(pvm.flatten_public_values(pv, eth_mainnet=False)) == 24 * 2 + 85 + 2056 + 16
+    pv.trie_roots_before.state_root = bytes(range(32))
+    # observe_root (get_challenges.rs:11-19): root.into_uint().0 = little-endian u64 limbs of the big-endian integer, low half first
+    assert [int(x) for x in pvm.flatten_public_values(pv)[:8]] == [0x1c1d1e1f, 0x18191a1b, 0x14151617, 0x10111213, 0x0c0d0e0f, 0x08090a0b,
+                                                                   0x04050607, 0x00010203]
+    pv = _random_public_values(17)
+    path = tmp_path / "pv.bin"
+    path.write_bytes(_pack_public_values(pv))
+    got = np.array([int(x) for x in harness("pubvals", path).stdout.split()], dtype=np.uint64)
+    assert np.array_equal(got, pvm.flatten_public_values(pv))
+    # u256_to_u32 refuses what does not fit (ProgramError::IntegerTooLarge), on both sides
+    pv.block_metadata.block_timestamp = 1 << 32
+    with pytest.raises(pvm.IntegerTooLarge):
+        pvm.flatten_public_values(pv)
+    path.write_bytes(_pack_public_values(pv))
+    assert harness("pubvals", path, ok=False).returncode != 0
+
+
 @pytest.mark.parametrize("table,lg,cfg", [(traces.T_MEM_AFTER, 7, TEST_CONFIG), (traces.T_LOGIC, 6, STANDARD_FAST)])
 def test_cpp_proof_decoder_on_oracle_proofs(harness, oracle, tmp_path, table, lg, cfg):
     tr = traces.memcont_trace(lg, 3) if table == traces.T_MEM_AFTER else traces.logic_trace(lg, 3)

@@ -4,3 +4,4 @@ from .prover import (Context, PolynomialBatch, CtlData, StarkProof, table_info, 
                      set_debug, DeviceTrace, keccak_generate_trace, logic_generate_trace, upload_trace, arithmetic_generate_range_checks, memory_finish_trace)
 from .segment import (Challenger, AllProof, prove_with_traces, upload_traces, SegmentUpload, prove_with_traces_sharded, ZkGpuBackend, TorchComm, LocalComm,  # noqa: F401
                       default_owner, segment_challenges, NUM_TABLES, TABLE_NAMES, OPTIONAL_TABLES)
+from .public_values import PublicValues, flatten_public_values  # noqa: F401,E402
