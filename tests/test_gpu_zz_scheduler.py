@@ -1,0 +1,34 @@
+"""GPU: the segment scheduler's product path (zk_evm_b200/scheduler.py: one Context per worker thread, prove_with_traces through the C ABI)
+on a stream of small segments, two in flight, against the oracle; the abort signal reaches the running proofs.
+(File name: sorts after the GPU files whose code already ran on a B200 in round 1 — this one has not yet.)"""
+import threading
+
+import numpy as np
+import pytest
+from tests import traces
+from tests.oracle_lib import orc_prove_segment, TEST_CONFIG, DEFAULT_LABELS
+import zk_evm_b200 as zk
+from zk_evm_b200.scheduler import SegmentProver, SegmentAborted
+
+pytestmark = pytest.mark.gpu
+PV = np.arange(1000, 1037, dtype=np.uint64)
+
+
+def test_stream_of_segments_two_in_flight_matches_oracle(oracle):
+    segs = [(traces.random_segment([7, 6, 8, 5, 6, 6, 9, 7, 6 + i % 2], seed=60 + i), PV + np.uint64(i)) for i in range(6)]
+    prover = SegmentProver(device=0, streams=2, config=zk.StarkConfig(*TEST_CONFIG), labels=DEFAULT_LABELS)
+    got = prover.prove_all(iter(segs))
+    assert len(got) == 6
+    for (tr, pv), ap in zip(segs, got):
+        want, bg, caps = orc_prove_segment(oracle, TEST_CONFIG, tr, pv)
+        assert np.array_equal(ap.ctl_challenges, bg) and np.array_equal(ap.trace_caps, caps)
+        for t in range(9):
+            assert np.array_equal(ap.stark_proofs[t], want[t]), "table %s" % zk.TABLE_NAMES[t]
+
+
+def test_abort_stops_the_stream():
+    prover = SegmentProver(device=0, streams=2, config=zk.StarkConfig(*TEST_CONFIG), labels=DEFAULT_LABELS)
+    seg = (traces.random_segment([10, 9, 12, 8, 8, 9, 13, 10, 9], seed=70), PV)
+    threading.Timer(0.2, prover.abort).start()
+    with pytest.raises(SegmentAborted):
+        prover.prove_all(seg for _ in range(400))
