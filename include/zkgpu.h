@@ -97,6 +97,15 @@ enum { ZKGPU_KF_LEAF_HASH = 0, ZKGPU_KF_MERKLE_LEVELS, ZKGPU_KF_NTT, ZKGPU_KF_QU
 int zkgpu_ctx_set_profiling(zkgpu_ctx* ctx, int on);   /* on: also resets the counters */
 int zkgpu_ctx_kernel_stats(zkgpu_ctx* ctx, uint32_t family, uint64_t* launches, double* ms_total, double* algorithmic_bytes);
 
+/* ---- pinned host memory (for hosts that do not link the CUDA runtime themselves) ------------------------------------------- */
+/* Trace uploads run at PCIe speed and asynchronously only from page-locked memory.  register: page-lock an
+ * existing allocation in place (e.g. the Vec<u64> of a PolynomialValues) until unregister; alloc / free: a page-locked buffer.
+ * Process-wide (any context / device may use the memory). */
+int zkgpu_host_register(const void* ptr, size_t bytes);
+int zkgpu_host_unregister(const void* ptr);
+int zkgpu_host_alloc(size_t bytes, void** out);
+int zkgpu_host_free(void* ptr);
+
 /* ---- S1: commitments ------------------------------------------------------------------------------------- */
 /* PolynomialBatch::from_values(values, rate_bits, blinding=false, cap_height): per column ifft -> zero-pad ->
  * coset FFT (shift = MULTIPLICATIVE_GROUP_GENERATOR) -> bit-reversed rows -> Poseidon Merkle tree.

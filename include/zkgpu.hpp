@@ -61,6 +61,21 @@ private:
     zkgpu_ctx* h_ = nullptr;
 };
 
+// a page-locked host buffer of field elements (zkgpu_host_alloc): uploads from it run at PCIe speed and asynchronously
+class PinnedBuffer {
+public:
+    explicit PinnedBuffer(size_t n) : n_(n) { void* p = nullptr; check(zkgpu_host_alloc(n * sizeof(F), &p)); p_ = (F*)p; }
+    ~PinnedBuffer() { zkgpu_host_free(p_); }
+    PinnedBuffer(const PinnedBuffer&) = delete;
+    PinnedBuffer& operator=(const PinnedBuffer&) = delete;
+    F* data() { return p_; }
+    const F* data() const { return p_; }
+    size_t size() const { return n_; }
+private:
+    F* p_ = nullptr;
+    size_t n_;
+};
+
 using Hash = std::array<F, 4>;
 using MerkleCap = std::vector<Hash>;                   // plonky2 MerkleCap<F, PoseidonHash>
 inline MerkleCap cap_from_words(const uint64_t* w, size_t n_words) {

@@ -32,3 +32,29 @@ def test_abort_stops_the_stream():
     threading.Timer(0.2, prover.abort).start()
     with pytest.raises(SegmentAborted):
         prover.prove_all(seg for _ in range(400))
+
+
+def test_pinned_host_memory_through_the_abi(ctx, oracle):
+    """zkgpu_host_alloc / zkgpu_host_register: a host that does not link the CUDA runtime pins its trace buffers through the library"""
+    tr = traces.random_segment([7, 6, 8, 5, 6, 6, 9, 7, 6], seed=80)
+    cfg = zk.StarkConfig(*TEST_CONFIG)
+    want, bg, caps = orc_prove_segment(oracle, TEST_CONFIG, tr, PV)
+    pinned = []
+    for t in tr:
+        p = zk.PinnedArray(t.shape)
+        p.array[...] = t
+        pinned.append(p)
+    ap = zk.prove_with_traces(ctx, [p.array for p in pinned], PV, cfg, zk.KernelLabels(*DEFAULT_LABELS))
+    for t in range(9):
+        assert np.array_equal(ap.stark_proofs[t], want[t])
+    for p in pinned:
+        p.free()
+    big = np.ascontiguousarray(tr[6])
+    zk.host_register(big)
+    try:
+        tr2 = list(tr)
+        tr2[6] = big
+        ap = zk.prove_with_traces(ctx, tr2, PV, cfg, zk.KernelLabels(*DEFAULT_LABELS))
+        assert np.array_equal(ap.stark_proofs[6], want[6])
+    finally:
+        zk.host_unregister(big)

@@ -1,7 +1,7 @@
 """zk_evm_b200 — B200-native STARK proving path for zk_evm's evm_arithmetization (host-side mirror over libzkgpu)."""
 from ._lib import ZkGpuError, StarkConfig, KernelLabels, lib, declared_symbols  # noqa: F401
 from .prover import (Context, PolynomialBatch, CtlData, StarkProof, table_info, get_ctl_data, prove_single_table,  # noqa: F401
-                     set_debug, DeviceTrace, keccak_generate_trace, logic_generate_trace, upload_trace, arithmetic_generate_range_checks, memory_finish_trace)
+                     set_debug, DeviceTrace, keccak_generate_trace, logic_generate_trace, upload_trace, arithmetic_generate_range_checks, memory_finish_trace, PinnedArray, host_register, host_unregister)
 from .segment import (Challenger, AllProof, prove_with_traces, upload_traces, SegmentUpload, prove_with_traces_sharded, ZkGpuBackend, TorchComm, LocalComm,  # noqa: F401
                       default_owner, segment_challenges, NUM_TABLES, TABLE_NAMES, OPTIONAL_TABLES)
 from .public_values import PublicValues, flatten_public_values  # noqa: F401,E402

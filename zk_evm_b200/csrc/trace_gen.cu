@@ -273,6 +273,31 @@ int zkgpu_dev_trace_export(const zkgpu_dev_trace* t, uint64_t* host_out) {
     ZK_API_END
 }
 
+// pinned host memory for hosts that do not link the CUDA runtime (include/zkgpu.h)
+int zkgpu_host_register(const void* ptr, size_t bytes) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ptr && bytes, "null argument");
+    ZK_CUDA(cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable));
+    ZK_API_END
+}
+int zkgpu_host_unregister(const void* ptr) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(ptr, "null argument");
+    ZK_CUDA(cudaHostUnregister(const_cast<void*>(ptr)));
+    ZK_API_END
+}
+int zkgpu_host_alloc(size_t bytes, void** out) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(out && bytes, "null argument");
+    ZK_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    ZK_API_END
+}
+int zkgpu_host_free(void* ptr) {
+    ZK_API_BEGIN
+    if (ptr) ZK_CUDA(cudaFreeHost(ptr));
+    ZK_API_END
+}
+
 void zkgpu_dev_trace_free(zkgpu_dev_trace* t) {
     if (!t) return;
     if (t->buf.ctx) cudaSetDevice(t->buf.ctx->device);

@@ -229,6 +229,38 @@ class StarkProof:
             pass
 
 
+class PinnedArray:
+    """A page-locked (ncols, n) uint64 host array (zkgpu_host_alloc): trace uploads from it run at PCIe speed, asynchronously.
+    `array` is a numpy view of the buffer; keep the PinnedArray alive while the view is in use."""
+
+    def __init__(self, shape):
+        self._p = C.c_void_p()
+        nbytes = int(np.prod(shape)) * 8
+        check(lib().zkgpu_host_alloc(C.c_size_t(nbytes), C.byref(self._p)))
+        self.array = np.ctypeslib.as_array(C.cast(self._p, u64p), shape=(int(np.prod(shape)),)).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib().zkgpu_host_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def host_register(a):
+    """page-lock an existing contiguous numpy array in place (zkgpu_host_register); pair with host_unregister"""
+    check(lib().zkgpu_host_register(C.c_void_p(a.ctypes.data), C.c_size_t(a.nbytes)))
+
+
+def host_unregister(a):
+    check(lib().zkgpu_host_unregister(C.c_void_p(a.ctypes.data)))
+
+
 class DeviceTrace:
     """A table's trace finished in device memory (zkgpu_dev_trace): ncols x n, column-major.  Goes into `prove_with_traces` /
     `upload_traces` in place of a host array, or into PolynomialBatch.from_device_values via `device_ptr`."""
