@@ -97,6 +97,16 @@ enum { ZKGPU_KF_LEAF_HASH = 0, ZKGPU_KF_MERKLE_LEVELS, ZKGPU_KF_NTT, ZKGPU_KF_QU
 int zkgpu_ctx_set_profiling(zkgpu_ctx* ctx, int on);   /* on: also resets the counters */
 int zkgpu_ctx_kernel_stats(zkgpu_ctx* ctx, uint32_t family, uint64_t* launches, double* ms_total, double* algorithmic_bytes);
 
+/* Stage spans, the counterpart of the reference's TimingTree (`timed!` sections of prover.rs:92-116,137-143,296-341 and of starky's
+ * prove_with_commitment): while on, every stage boundary of the prover records a CUDA event on the context's stream (no host
+ * synchronisation, unlike ZKGPU_TRACE=1).  report: synchronises the stream and writes one "name<TAB>milliseconds" line per span, in
+ * order — per segment "trace upload", one line per table commitment, "ctl data", then per table "aux columns", "aux commit",
+ * "quotient eval", "quotient intt", "quotient commit", "openings eval", "observe openings (host)", "fri combine + intt",
+ * "fri commit phase", "pow", "queries" and the table's name for the remainder.  *len in: capacity of buf, out: bytes needed (with
+ * the terminating NUL); buf may be NULL to query.  set_timing (on or off) clears the recorded spans. */
+int zkgpu_ctx_set_timing(zkgpu_ctx* ctx, int on);
+int zkgpu_ctx_timing_report(zkgpu_ctx* ctx, char* buf, size_t* len);
+
 /* ---- pinned host memory (for hosts that do not link the CUDA runtime themselves) ------------------------------------------- */
 /* Trace uploads run at PCIe speed and asynchronously only from page-locked memory.  register: page-lock an
  * existing allocation in place (e.g. the Vec<u64> of a PolynomialValues) until unregister; alloc / free: a page-locked buffer.

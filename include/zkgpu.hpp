@@ -56,6 +56,23 @@ public:
     Context(const Context&) = delete;
     Context& operator=(const Context&) = delete;
     void sync() { check(zkgpu_ctx_sync(h_)); }
+    // stage spans, the counterpart of the reference's TimingTree: (stage name, milliseconds) in order since set_timing(true)
+    void set_timing(bool on) { check(zkgpu_ctx_set_timing(h_, on)); }
+    std::vector<std::pair<std::string, double>> timing_report() {
+        size_t len = 0;
+        check(zkgpu_ctx_timing_report(h_, nullptr, &len));
+        std::string buf(len, '\0');
+        check(zkgpu_ctx_timing_report(h_, buf.data(), &len));
+        std::vector<std::pair<std::string, double>> spans;
+        size_t pos = 0;
+        for (;;) {
+            const size_t tab = buf.find('\t', pos), nl = buf.find('\n', pos);
+            if (tab == std::string::npos || nl == std::string::npos) break;
+            spans.emplace_back(buf.substr(pos, tab - pos), std::stod(buf.substr(tab + 1, nl - tab - 1)));
+            pos = nl + 1;
+        }
+        return spans;
+    }
     zkgpu_ctx* handle() const { return h_; }
 private:
     zkgpu_ctx* h_ = nullptr;

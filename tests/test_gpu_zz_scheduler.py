@@ -58,3 +58,19 @@ def test_pinned_host_memory_through_the_abi(ctx, oracle):
         assert np.array_equal(ap.stark_proofs[6], want[6])
     finally:
         zk.host_unregister(big)
+
+
+def test_stage_spans(ctx):
+    """zkgpu_ctx_set_timing / zkgpu_ctx_timing_report: the TimingTree counterpart"""
+    tr = traces.random_segment([7, 6, 8, 5, 6, 6, 9, 7, 6], seed=81)
+    ctx.set_timing(True)
+    try:
+        zk.prove_with_traces(ctx, tr, PV, zk.StarkConfig(*TEST_CONFIG), zk.KernelLabels(*DEFAULT_LABELS))
+        spans = ctx.timing_report()
+    finally:
+        ctx.set_timing(False)
+    names = [n for n, _ in spans]
+    assert names.count("trace upload") == 9 and names.count("ctl data") == 9 and names.count("quotient eval") == 9
+    assert names.count("fri commit phase") == 9 and names.count("pow") == 9
+    assert all(ms >= 0 for _, ms in spans) and sum(ms for _, ms in spans) > 0
+    assert ctx.timing_report() == []

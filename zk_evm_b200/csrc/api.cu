@@ -73,8 +73,18 @@ void Ctx::d2h(void* dst, const void* src, size_t bytes) {
     ZK_CUDA(cudaStreamSynchronize(stream));
 }
 double StageLog::now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
-StageLog::StageLog(Ctx& c_) : c(c_) { const char* e = getenv("ZKGPU_TRACE"); on = e && *e == '1'; t0 = on ? now() : 0; }
+static void timing_mark(Ctx& c, const char* what) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, c.stream);
+    c.timing_marks.emplace_back(what, e);
+}
+StageLog::StageLog(Ctx& c_) : c(c_) {
+    const char* e = getenv("ZKGPU_TRACE"); on = e && *e == '1'; t0 = on ? now() : 0;
+    if (c.timing) timing_mark(c, "");          // an empty name starts a chain of spans
+}
 void StageLog::mark(const char* what) {
+    if (c.timing) timing_mark(c, what);
     if (!on) return;
     double a = now();
     cudaStreamSynchronize(c.stream);
@@ -260,6 +270,37 @@ int zkgpu_ctx_set_profiling(zkgpu_ctx* h, int on) {
     c.prof_collect();
     c.profiling = on != 0;
     if (on) for (int i = 0; i < KF_COUNT; i++) { c.prof_ms[i] = 0; c.prof_bytes[i] = 0; c.prof_launches[i] = 0; }
+    ZK_API_END
+}
+int zkgpu_ctx_set_timing(zkgpu_ctx* h, int on) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(h, "null argument");
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    for (auto& m : c.timing_marks) cudaEventDestroy(m.second);
+    c.timing_marks.clear();
+    c.timing = on != 0;
+    ZK_API_END
+}
+int zkgpu_ctx_timing_report(zkgpu_ctx* h, char* buf, size_t* len) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(h && len, "null argument");
+    Ctx& c = h->c;
+    ZK_CUDA(cudaSetDevice(c.device));
+    ZK_CUDA(cudaStreamSynchronize(c.stream));
+    std::string out;
+    for (size_t i = 0; i < c.timing_marks.size(); i++) {
+        const auto& m = c.timing_marks[i];
+        if (m.first.empty() || i == 0) continue;                 // chain start
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c.timing_marks[i - 1].second, m.second) != cudaSuccess) ms = 0;
+        char line[160];
+        snprintf(line, sizeof line, "%s\t%.6f\n", m.first.c_str(), ms);
+        out += line;
+    }
+    const size_t need = out.size() + 1;
+    if (buf && *len >= need) memcpy(buf, out.c_str(), need);
+    *len = need;
     ZK_API_END
 }
 int zkgpu_ctx_kernel_stats(zkgpu_ctx* h, uint32_t family, uint64_t* launches, double* ms_total, double* algorithmic_bytes) {

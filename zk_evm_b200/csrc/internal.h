@@ -112,6 +112,9 @@ struct Ctx {
     uint64_t prof_launches[KF_COUNT] = {0};
     void prof_collect();   // resolve finished event pairs (synchronises the stream)
     size_t evalpow_n = 0; uint64_t evalpow_zeta[2] = {0, 0};   // key of the cached zeta-power table (fri.cu eval_columns)
+    // stage spans (zkgpu_ctx_set_timing): every StageLog mark records an event on `stream`; resolved by zkgpu_ctx_timing_report
+    bool timing = false;
+    std::vector<std::pair<std::string, cudaEvent_t>> timing_marks;
     bool debug = false;   // proofs keep their aux / quotient batches and FRI input values for stage-by-stage parity tests
     // pinned staging buffer for H2D / D2H of pageable memory
     void* staging = nullptr;

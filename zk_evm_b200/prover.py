@@ -48,6 +48,18 @@ class Context:
     def sync(self):
         check(lib().zkgpu_ctx_sync(self._h))
 
+    def set_timing(self, on=True):
+        """stage spans (the reference's TimingTree): record a CUDA event at every stage boundary of the prover"""
+        check(lib().zkgpu_ctx_set_timing(self._h, int(bool(on))))
+
+    def timing_report(self):
+        """-> [(stage name, milliseconds)] in order, for everything proved since set_timing(True)"""
+        n = C.c_size_t(0)
+        check(lib().zkgpu_ctx_timing_report(self._h, None, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        check(lib().zkgpu_ctx_timing_report(self._h, buf, C.byref(n)))
+        return [(name, float(ms)) for name, ms in (line.split("\t") for line in buf.value.decode().splitlines())]
+
     def timer_start(self):
         check(lib().zkgpu_ctx_timer_start(self._h))
 
