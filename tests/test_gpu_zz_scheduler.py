@@ -15,7 +15,7 @@ PV = np.arange(1000, 1037, dtype=np.uint64)
 
 
 def test_stream_of_segments_two_in_flight_matches_oracle(oracle):
-    segs = [(traces.random_segment([7, 6, 8, 5, 6, 6, 9, 7, 6 + i % 2], seed=60 + i), PV + np.uint64(i)) for i in range(6)]
+    segs = [(traces.random_segment([7, 6, 8, 6, 6, 6, 9, 7, 6 + i % 2], seed=60 + i), PV + np.uint64(i)) for i in range(6)]
     prover = SegmentProver(device=0, streams=2, config=zk.StarkConfig(*TEST_CONFIG), labels=DEFAULT_LABELS)
     got = prover.prove_all(iter(segs))
     assert len(got) == 6
@@ -36,7 +36,7 @@ def test_abort_stops_the_stream():
 
 def test_pinned_host_memory_through_the_abi(ctx, oracle):
     """zkgpu_host_alloc / zkgpu_host_register: a host that does not link the CUDA runtime pins its trace buffers through the library"""
-    tr = traces.random_segment([7, 6, 8, 5, 6, 6, 9, 7, 6], seed=80)
+    tr = traces.random_segment([7, 6, 8, 6, 6, 6, 9, 7, 6], seed=80)
     cfg = zk.StarkConfig(*TEST_CONFIG)
     want, bg, caps = orc_prove_segment(oracle, TEST_CONFIG, tr, PV)
     pinned = []
@@ -62,7 +62,7 @@ def test_pinned_host_memory_through_the_abi(ctx, oracle):
 
 def test_stage_spans(ctx):
     """zkgpu_ctx_set_timing / zkgpu_ctx_timing_report: the TimingTree counterpart"""
-    tr = traces.random_segment([7, 6, 8, 5, 6, 6, 9, 7, 6], seed=81)
+    tr = traces.random_segment([7, 6, 8, 6, 6, 6, 9, 7, 6], seed=81)
     ctx.set_timing(True)
     try:
         zk.prove_with_traces(ctx, tr, PV, zk.StarkConfig(*TEST_CONFIG), zk.KernelLabels(*DEFAULT_LABELS))
