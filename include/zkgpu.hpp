@@ -11,6 +11,11 @@
 #pragma once
 #include <array>
 #include <atomic>
+#include <exception>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <thread>
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -418,6 +423,78 @@ inline std::vector<F> flatten_public_values(const PublicValues& pv, bool eth_mai
         u256_limbs(o, *pv.burn_addr);
     }
     return o;
+}
+
+// ---- a stream of segments, several in flight on one GPU (zero/src/prover.rs:205-236 dispatches every segment as its own proving job and
+// collects the proofs by index; zero/src/ops.rs:24-66 is the job) ---------------------------------------------------------------------
+// `streams` worker threads, each with its own worker state (default: a Context = own CUDA stream, copy stream and memory pool; three in
+// flight is the measured optimum on a B200).  next() is called under a lock and returns std::nullopt at the end of the stream, so the
+// source is consumed lazily: at most `streams` segments are alive at a time.  A failing segment raises the abort signal the running
+// proofs poll and its exception is rethrown by prove_all; abort() does the same from outside (-> Error{ZKGPU_ERR_ABORTED}).
+template <class Segment, class Proof, class Worker>
+class SegmentStream {
+public:
+    using MakeWorker = std::function<std::unique_ptr<Worker>()>;
+    using Prove = std::function<Proof(Worker&, const Segment&, AbortSignal)>;
+    SegmentStream(unsigned streams, MakeWorker make_worker, Prove prove) : streams_(streams ? streams : 1), make_worker_(std::move(make_worker)), prove_(std::move(prove)) {}
+    void abort() { abort_.store(1); }
+    // proofs in segment order
+    std::vector<Proof> prove_all(const std::function<std::optional<Segment>()>& next) {
+        abort_.store(0);
+        std::mutex mu;
+        std::map<size_t, Proof> results;
+        std::exception_ptr first_error;
+        size_t count = 0;
+        bool done = false;
+        auto worker = [&]() {
+            try {
+                std::unique_ptr<Worker> w = make_worker_();
+                for (;;) {
+                    std::optional<Segment> seg;
+                    size_t idx;
+                    {
+                        std::lock_guard<std::mutex> g(mu);
+                        if (done || abort_.load()) return;
+                        seg = next();
+                        if (!seg) { done = true; return; }
+                        idx = count++;
+                    }
+                    Proof p = prove_(*w, *seg, &abort_);
+                    std::lock_guard<std::mutex> g(mu);
+                    results.emplace(idx, std::move(p));
+                }
+            } catch (...) {
+                std::lock_guard<std::mutex> g(mu);
+                if (!first_error) first_error = std::current_exception();
+                abort_.store(1);
+            }
+        };
+        std::vector<std::thread> threads;
+        for (unsigned i = 0; i < streams_; i++) threads.emplace_back(worker);
+        for (std::thread& t : threads) t.join();
+        if (first_error) std::rethrow_exception(first_error);
+        if (abort_.load()) throw Error(ZKGPU_ERR_ABORTED, "abort signal observed");
+        std::vector<Proof> out;
+        for (auto& kv : results) out.push_back(std::move(kv.second));
+        return out;
+    }
+private:
+    unsigned streams_;
+    MakeWorker make_worker_;
+    Prove prove_;
+    std::atomic<int> abort_{0};
+};
+
+// the product instance: segments as trace blocks + flattened public values, proved by prove_with_traces on `device`
+struct SegmentInput {
+    std::array<TableTrace, NUM_TABLES> traces;
+    std::vector<F> public_values;
+    int mem_kind = ZKGPU_MEM_HOST;
+};
+inline SegmentStream<SegmentInput, AllProof, Context> segment_prover(int device, unsigned streams, StarkConfig config, KernelLabels labels) {
+    return SegmentStream<SegmentInput, AllProof, Context>(
+        streams, [device]() { return std::make_unique<Context>(device); },
+        [config, labels](Context& ctx, const SegmentInput& s, AbortSignal a) { return prove_with_traces(ctx, s.traces, s.public_values, config, labels, a, s.mem_kind); });
 }
 
 // a trace finished in device memory (zkgpu_dev_trace): KeccakStark / LogicStark generate_trace, the Arithmetic range-check columns,

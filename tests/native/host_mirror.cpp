@@ -2,12 +2,14 @@
 //   host_mirror nodevice                         Context(0) must throw Error{ZKGPU_ERR_CUDA} on a box without a GPU (no CPU path)
 //   host_mirror challenger <n>                   observe 1..n, draw 3 challenges, compact -> prints the challenges and the state
 //   host_mirror pubvals <file>                   PublicValues read from a packed byte file -> the flattened elements observe_public_values feeds
+//   host_mirror stream                           SegmentStream (the scheduler template) with a stand-in prover: order, laziness, failure, abort
 //   host_mirror decode <proof.words>             typed StarkProof fields of a serialised proof, and re-serialisation equality
 //   host_mirror prove <segment.trace> <out> [test|fast]   prove_with_traces on cuda:0 from a segment trace file (zk_evm_b200/trace_file.py
 //                                                layout) -> writes ctl challenges, trace caps and every table's proof words to <out>
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <fstream>
 #include <iostream>
 #include <iterator>
@@ -109,6 +111,41 @@ int main(int argc, char** argv) {
             for (F x : flatten_public_values(pv)) printf("%llu\n", (unsigned long long)x);
             return 0;
         }
+        if (mode == "stream") {
+            // the scheduling logic without a device: the "proof" of segment k is k * k, the workers count what they were given
+            struct W { int made = 0; };
+            std::atomic<int> workers{0}, alive{0}, max_alive{0};
+            SegmentStream<int, long, W> st(3, [&]() { workers++; return std::make_unique<W>(); },
+                                           [&](W&, const int& k, AbortSignal a) -> long {
+                                               int now = ++alive, m = max_alive.load();
+                                               while (now > m && !max_alive.compare_exchange_weak(m, now)) {}
+                                               for (int i = 0; i < 20; i++) {
+                                                   if (a->load()) { alive--; throw Error(ZKGPU_ERR_ABORTED, "aborted"); }
+                                                   std::this_thread::sleep_for(std::chrono::milliseconds(1));
+                                               }
+                                               if (k == 1000) { alive--; throw std::runtime_error("segment 1000 is broken"); }
+                                               alive--;
+                                               return (long)k * k;
+                                           });
+            int produced = 0;
+            auto src = [&](int n, int poison) { produced = 0; return [&produced, n, poison]() -> std::optional<int> {
+                if (produced >= n) return std::nullopt;
+                int k = produced++;
+                return k == poison ? 1000 : k; }; };
+            const std::vector<long> got = st.prove_all(src(17, -1));
+            bool ok = got.size() == 17 && workers == 3 && max_alive <= 3;
+            for (size_t k = 0; k < got.size(); k++) ok = ok && got[k] == (long)(k * k);
+            printf("order %d\n", (int)ok);
+            bool failed = false;
+            try { st.prove_all(src(500, 5)); } catch (const std::runtime_error& e) { failed = std::string(e.what()).find("1000") != std::string::npos; }
+            printf("failure %d consumed_at_most %d\n", (int)failed, produced);
+            std::thread killer([&]() { std::this_thread::sleep_for(std::chrono::milliseconds(50)); st.abort(); });
+            bool aborted = false;
+            try { st.prove_all(src(100000, -1)); } catch (const Error& e) { aborted = e.code == ZKGPU_ERR_ABORTED; }
+            killer.join();
+            printf("abort %d consumed_at_most %d\n", (int)aborted, produced);
+            return ok && failed && aborted ? 0 : 1;
+        }
         if (mode == "decode" && argc > 2) {
             const std::vector<uint64_t> w = read_words(argv[2]);
             size_t used = 0;
@@ -167,6 +204,22 @@ int main(int argc, char** argv) {
                         return 1;
                     }
                 }
+            }
+            // a stream of four copies of the segment, two in flight (segment_prover = SegmentStream over Context + prove_with_traces)
+            {
+                auto sp = segment_prover(0, 2, cfg, seg.labels);
+                int left = 4;
+                const std::vector<AllProof> all = sp.prove_all([&]() -> std::optional<SegmentInput> {
+                    if (left-- <= 0) return std::nullopt;
+                    return SegmentInput{seg.traces, seg.public_values, ZKGPU_MEM_HOST};
+                });
+                if (all.size() != 4) { printf("segment stream returned %zu proofs\n", all.size()); return 1; }
+                for (const AllProof& a : all)
+                    for (size_t t = 0; t < NUM_TABLES; t++)
+                        if (a.stark_proofs[t].has_value() != ap.stark_proofs[t].has_value() || (a.stark_proofs[t] && a.stark_proofs[t]->words != ap.stark_proofs[t]->words)) {
+                            printf("segment stream differs from prove_with_traces on table %zu\n", t);
+                            return 1;
+                        }
             }
             // an abort signal that is already raised stops the proof with ZKGPU_ERR_ABORTED (check_abort_signal, prover.rs:346-354)
             abort_signal = 1;

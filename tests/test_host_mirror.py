@@ -28,7 +28,7 @@ def harness():
             os.path.join(LIBDIR, "csrc", "stark", "proof.h")]
     if not os.path.exists(BIN) or any(os.path.getmtime(d) > os.path.getmtime(BIN) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", BIN, SRC,
-                               "-L", LIBDIR, "-lzkgpu", "-Wl,-rpath," + LIBDIR])
+                               "-L", LIBDIR, "-lzkgpu", "-lpthread", "-Wl,-rpath," + LIBDIR])
     env = dict(os.environ)
     env["LD_LIBRARY_PATH"] = ":".join(p for p in (env.get("LD_LIBRARY_PATH"), "/usr/local/cuda/lib64") if p)
 
@@ -55,6 +55,15 @@ def test_cpp_challenger_matches_oracle(harness, oracle):
     assert words[3:15] == [int(x) for x in st]
     ch2, _ = oracle.challenger_run(ops + [("c",)])
     assert words[15] == int(ch2[3])
+
+
+def test_cpp_segment_stream_scheduling_logic(harness):
+    """zkgpu::SegmentStream with a stand-in prover: proofs in segment order from 3 workers, at most 3 segments alive, a failing segment
+    and abort() stop the stream early (the product instance, segment_prover(), plugs Context + prove_with_traces into the same template)"""
+    out = harness("stream").stdout.split()
+    f = dict(zip(out[0::2], out[1::2]))
+    assert f["order"] == "1" and f["failure"] == "1" and f["abort"] == "1"
+    assert int(out[out.index("failure") + 3]) < 500 and int(out[out.index("abort") + 3]) < 100000
 
 
 def _random_public_values(seed):
