@@ -4,7 +4,7 @@ KeccakStark::generate_trace (keccak_stark.rs:70-250; tests/traces.py) and zkgpu_
 import numpy as np
 import pytest
 from tests import traces
-from tests.oracle_lib import orc_prove_segment, orc_prove_table, orc_verify_table, TEST_CONFIG, DEFAULT_LABELS
+from tests.oracle_lib import orc_prove_segment, orc_prove_table, orc_verify_table, TEST_CONFIG, STANDARD_FAST, DEFAULT_LABELS
 import zk_evm_b200 as zk
 
 pytestmark = pytest.mark.gpu
@@ -96,6 +96,25 @@ def test_device_finished_memory_trace_proves_and_verifies(ctx, oracle):
     ctl = zk.get_ctl_data(ctx, traces.T_MEMORY, batch, bg, cfg.num_challenges)
     proof, st = zk.prove_single_table(ctx, traces.T_MEMORY, cfg, batch, ctl, st0, zk.KernelLabels(*DEFAULT_LABELS))
     ok, err, st2 = orc_verify_table(oracle, traces.T_MEMORY, TEST_CONFIG, proof.words, bg, st0)
+    assert ok, err
+
+
+@pytest.mark.parametrize("cfg", [TEST_CONFIG, STANDARD_FAST])
+def test_valid_keccak_sponge_trace_on_gpu_verifies(ctx, oracle, cfg):
+    """KeccakSpongeStark on a VALID trace (tests/traces.py keccak_sponge_trace = the restated generate_trace): the GPU proof equals the
+    oracle's and the restated verifier accepts it (the sponge cases of test_gpu_stark.py are random traces)"""
+    rng = np.random.default_rng(6)
+    ops = [(1, 2, 100, 7, b""), (0, 3, 5, 9, rng.bytes(135)), (2, 1, 0, 11, rng.bytes(136)), (0, 0, 50, 13, rng.bytes(300)), (0, 2, 7, 21, b"abc")]
+    tr, _ = traces.keccak_sponge_trace(8, ops)
+    c = zk.StarkConfig(*cfg)
+    bg = np.array([11, 22, 33, 44], dtype=np.uint64)[:2 * cfg[1]]
+    st0 = np.arange(12, dtype=np.uint64)
+    batch = zk.PolynomialBatch.from_values(ctx, tr, c.rate_bits, c.cap_height, keep_values=True)
+    ctl = zk.get_ctl_data(ctx, traces.T_KECCAK_SPONGE, batch, bg, c.num_challenges)
+    proof, st = zk.prove_single_table(ctx, traces.T_KECCAK_SPONGE, c, batch, ctl, st0, zk.KernelLabels(*DEFAULT_LABELS))
+    want, st_want = orc_prove_table(oracle, traces.T_KECCAK_SPONGE, cfg, tr, bg, st0)
+    assert np.array_equal(proof.words, want) and np.array_equal(st, st_want)
+    ok, err, _ = orc_verify_table(oracle, traces.T_KECCAK_SPONGE, cfg, proof.words, bg, st0)
     assert ok, err
 
 

@@ -231,6 +231,68 @@ def arithmetic_addcy_trace(log_n, seed, nops=1000):
     return t
 
 
+# ---- KeccakSpongeStark (keccak_sponge_stark.rs:253-543) -------------------------------------------------------------------------------
+def _keccakf_u32s(state):
+    """keccakf_u32s (cpu/kernel/keccak_util.rs:7-19): 50 u32 = 25 little-endian (lo, hi) lanes, lane i = x + 5y"""
+    lanes = np.array([[int(state[2 * i]) | (int(state[2 * i + 1]) << 32) for i in range(25)]], dtype=np.uint64)
+    out = keccak_trace(5, lanes)[1][0]
+    res = []
+    for i in range(25):
+        res += [int(out[i]) & 0xFFFFFFFF, int(out[i]) >> 32]
+    return res
+
+
+def keccak_sponge_trace(log_n, ops):
+    """KeccakSpongeStark::generate_trace.  ops: list of (context, segment, virt, timestamp, input bytes).
+    Returns (trace (438, n), digests: the 32-byte Keccak-256 of every input as the rows compute it)."""
+    n = 1 << log_n
+    assert n >= 256
+    rows, digests = [], []
+    for ctx, seg, virt, ts, data in ops:
+        data = bytes(data)
+        state = [0] * 50
+        absorbed = 0
+        nblocks = len(data) // 136 + 1
+        for b in range(nblocks):
+            row = [0] * 438
+            final = b == nblocks - 1
+            block = list(data[136 * b:136 * b + 136])
+            if final:                                          # generate_final_row: pad10*1, is_padding_byte
+                k = len(block)
+                block += [0] * (136 - k)
+                if k == 135:
+                    block[135] = 0b10000001
+                else:
+                    block[k] = 1
+                    block[135] = 0b10000000
+                for i in range(k, 136):
+                    row[6 + i] = 1
+            else:
+                row[0] = 1                                     # is_full_input_block
+            row[1:6] = [ctx, seg, virt, ts, absorbed]
+            row[142:176] = state[:34]                          # original_rate_u32s
+            row[176:192] = state[34:]                          # original_capacity_u32s
+            row[192:328] = block                               # block_bytes
+            for i in range(34):
+                state[i] ^= int.from_bytes(bytes(block[4 * i:4 * i + 4]), "little")
+            row[328:362] = state[:34]                          # xored_rate_u32s
+            state = _keccakf_u32s(state)
+            row[362:404] = state[8:]                           # partial_updated_state_u32s
+            for l in range(8):
+                for i in range(4):
+                    row[404 + 4 * l + i] = (state[l] >> (8 * i)) & 0xFF      # updated_digest_state_bytes
+            rows.append(row)
+            absorbed += 136
+        digests.append(b"".join(int(x).to_bytes(4, "little") for x in state[:8]))
+    assert len(rows) <= n
+    t = np.zeros((438, n), dtype=np.uint64)
+    if rows:
+        t[:, :len(rows)] = np.array(rows, dtype=np.uint64).T
+    t[436] = np.minimum(np.arange(n), 255).astype(np.uint64)                 # range_counter
+    t[437, :256] = np.bincount(t[192:328].astype(np.int64).ravel(), minlength=256).astype(np.uint64)   # rc_frequencies
+    return t, digests
+
+
 # ---- MemoryStark from operations (memory_stark.rs:104-462) -------------------------------------------------------------------------
 MEM_OP_COLS = (0, 1, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14)       # filter, timestamp, is_read, context, segment, virtual, 8 value limbs
 
