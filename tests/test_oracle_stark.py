@@ -187,3 +187,33 @@ def test_corrupted_keccak_sponge_trace_is_rejected(oracle, col, row):
     proof, _ = orc_prove_table(oracle, traces.T_KECCAK_SPONGE, TEST_CONFIG, tr, bg, STATE0)
     ok, _, _ = orc_verify_table(oracle, traces.T_KECCAK_SPONGE, TEST_CONFIG, proof, bg, STATE0)
     assert not ok
+
+
+# ---- ArithmeticStark MUL rows (the addcy generator covers ADD / SUB / LT / GT only) -----------------------------------------------------
+def test_valid_arithmetic_mul_trace_verifies_and_wrong_product_is_rejected(oracle):
+    tr = traces.arithmetic_mul_trace(16, 3, nops=100)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, tr, bg, STATE0)
+    ok, err, _ = orc_verify_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, proof, bg, STATE0)
+    assert ok, err
+    tr[66, 7] ^= np.uint64(1)               # a wrong product limb, range-check frequencies kept consistent
+    tr[115, :65536] = np.bincount(tr[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
+    proof, _ = orc_prove_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, tr, bg, STATE0)
+    ok, _, _ = orc_verify_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, proof, bg, STATE0)
+    assert not ok
+
+
+def test_valid_arithmetic_modular_trace_verifies_and_corruptions_are_rejected(oracle):
+    """ADDMOD / MULMOD / DIV / MOD (two-row operations, modular.rs + divmod.rs), incl. modulus / denominator 0 and 1, maximal operands"""
+    tr = traces.arithmetic_modular_trace(16, 3, nops=40)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, tr, bg, STATE0)
+    ok, err, _ = orc_verify_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, proof, bg, STATE0)
+    assert ok, err
+    # ADDMOD aux input (second row); DIV remainder; MOD result   (each case is a 2^16-row proof: three of them)
+    for col, row in ((35, 13), (82, 20), (66, 28)):
+        t2 = tr.copy()
+        t2[col, row] ^= np.uint64(1)
+        t2[115, :65536] = np.bincount(t2[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
+        proof, _ = orc_prove_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, t2, bg, STATE0)
+        assert not orc_verify_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, proof, bg, STATE0)[0], (col, row)

@@ -379,6 +379,146 @@ def memory_finish_reference(ops, stale=()):
     return np.array(t, dtype=np.uint64)
 
 
+def arithmetic_mul_rows(a, b):
+    """mul.rs:70-120 generate_mul for 256-bit a, b -> (output limbs, aux_lo limbs, aux_hi limbs), 16 x 16-bit each"""
+    al = [(a >> (16 * i)) & 0xFFFF for i in range(16)]
+    bl = [(b >> (16 * i)) & 0xFFFF for i in range(16)]
+    prod = [sum(al[i] * bl[k - i] for i in range(k + 1)) for k in range(16)]          # pol_mul_lo
+    out, cy = [], 0
+    for k in range(16):
+        t = prod[k] + cy
+        cy = t >> 16
+        out.append(t & 0xFFFF)
+    d = [prod[k] - out[k] for k in range(16)]                                         # pol_sub_assign
+    q = [0] * 16                                                                      # pol_remove_root_2exp
+    q[0] = -(d[0] >> 16)
+    for k in range(1, 15):
+        q[k] = (q[k - 1] - d[k]) >> 16
+    q[15] = -cy
+    q = [c + (1 << 20) for c in q]                                                    # + AUX_COEFF_ABS_MAX
+    assert all(0 <= c < (1 << 32) for c in q)
+    return out, [c & 0xFFFF for c in q], [c >> 16 for c in q]
+
+
+def arithmetic_mul_trace(log_n, seed, nops=200):
+    """ArithmeticStark trace of MUL operations (arithmetic_stark.rs:158-190 + mul.rs generate), incl. edge operands"""
+    rng = np.random.default_rng(seed)
+    n = 1 << log_n
+    assert n >= 1 << 16
+    t = np.zeros((116, n), dtype=np.uint64)
+    M = (1 << 256) - 1
+    vals = [(0, 0), (1, M), (M, M), (M, 2), (1 << 255, 2), (0xFFFF, 0xFFFF)] + \
+           [(int.from_bytes(rng.bytes(32), "little"), int.from_bytes(rng.bytes(32), "little")) for _ in range(nops)]
+    for k, (a, b) in enumerate(vals):
+        out, lo, hi = arithmetic_mul_rows(a, b)
+        assert sum(o << (16 * i) for i, o in enumerate(out)) == (a * b) & M
+        t[1, k] = 1                                                                   # IS_MUL
+        t[18:34, k] = [(a >> (16 * i)) & 0xFFFF for i in range(16)]
+        t[34:50, k] = [(b >> (16 * i)) & 0xFFFF for i in range(16)]
+        t[66:82, k] = out
+        t[82:98, k] = lo
+        t[98:114, k] = hi
+    t[114] = np.minimum(np.arange(n), 65535).astype(np.uint64)
+    t[115, :65536] = np.bincount(t[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
+    return t
+
+
+def _limbs(x, k=16):
+    return [(x >> (16 * i)) & 0xFFFF for i in range(k)]
+
+
+def _modular_op(pol, m, is_div):
+    """modular.rs:200-338 generate_modular_op: pol = the 31 input coefficients, m = the modulus (DIV: the denominator).
+    -> (output, quotient limbs (32), second row)"""
+    constr = list(pol) + [0]
+    modulus, mod_limbs, mod_is_zero = m, _limbs(m), 0
+    if m == 0:
+        mod_is_zero = 1
+        if is_div:
+            modulus = 1 << 256                     # "modulus_limbs don't play a role below": the quotient is zero
+        else:
+            modulus = 1
+            mod_limbs[0] = 1
+    inp = sum(c << (16 * i) for i, c in enumerate(constr))                                   # columns_to_bigint
+    out = inp % modulus
+    quot = (inp - out) // modulus
+    out_l, quot_l = _limbs(out), _limbs(quot, 32)
+    out_aux_red = _limbs((1 << 256) - modulus + out)
+    for i in range(16):
+        constr[i] -= out_l[i]
+    prod = [sum(quot_l[i] * mod_limbs[k - i] for i in range(32) if 0 <= k - i < 16) for k in range(47)]   # pol_mul_wide2
+    assert all(x == 0 for x in prod[32:])
+    for i in range(32):
+        constr[i] -= prod[i]
+    q = [0] * 32                                                                              # pol_remove_root_2exp
+    q[0] = -(constr[0] >> 16)
+    for k in range(1, 31):
+        q[k] = (q[k - 1] - constr[k]) >> 16
+    q = [c + (1 << 20) for c in q]
+    assert all(0 <= c < (1 << 32) for c in q)
+    row2 = [0] * 116
+    row2[18:34] = out_aux_red                                                                 # MODULAR_OUT_AUX_RED
+    row2[34] = mod_is_zero                                                                    # MODULAR_MOD_IS_ZERO
+    row2[35:66] = [c & 0xFFFF for c in q[:31]]                                                # MODULAR_AUX_INPUT_LO
+    row2[66:97] = [c >> 16 for c in q[:31]]                                                   # MODULAR_AUX_INPUT_HI
+    row2[97] = mod_is_zero if is_div else 0                                                   # MODULAR_DIV_DENOM_IS_ZERO
+    return out, quot_l, row2
+
+
+def arithmetic_modular_rows(op, a, b, m):
+    """ADDMOD / MULMOD (modular.rs:343-383 generate) and DIV / MOD (divmod.rs:24-87; m unused) -> (row1, row2, result)"""
+    al, bl = _limbs(a), _limbs(b)
+    row1 = [0] * 116
+    row1[18:34], row1[34:50] = al, bl
+    if op in ("addmod", "mulmod"):
+        if op == "addmod":
+            pol = [al[i] + bl[i] for i in range(16)] + [0] * 15                              # pol_add
+        else:
+            pol = [sum(al[i] * bl[k - i] for i in range(16) if 0 <= k - i < 16) for k in range(31)]   # pol_mul_wide
+        out, quot_l, row2 = _modular_op(pol, m, False)
+        row1[5 if op == "addmod" else 6] = 1                                                  # IS_ADDMOD / IS_MULMOD
+        row1[50:66] = _limbs(m)
+        row1[66:82] = _limbs(out)                                                             # MODULAR_OUTPUT
+        row1[82:114] = quot_l                                                                 # MODULAR_QUO_INPUT
+        return row1, row2, out
+    out, quot_l, row2 = _modular_op(al + [0] * 15, b, op == "div")                            # pol_extend(numerator), modulus = denominator
+    assert all(x == 0 for x in quot_l[16:])
+    result = sum(c << (16 * i) for i, c in enumerate(quot_l[:16])) if op == "div" else out
+    row1[3 if op == "div" else 4] = 1                                                         # IS_DIV / IS_MOD
+    row1[66:82] = _limbs(result)                                                              # OUTPUT_REGISTER
+    row1[82:98] = _limbs(out) if op == "div" else quot_l[:16]                                 # AUX_INPUT_REGISTER_0: the other of (quotient, remainder)
+    return row1, row2, result
+
+
+def arithmetic_modular_trace(log_n, seed, nops=60):
+    """ArithmeticStark trace of ADDMOD / MULMOD / DIV / MOD operations (two rows each), incl. modulus / denominator 0 and 1 and maximal operands"""
+    rng = np.random.default_rng(seed)
+    n = 1 << log_n
+    assert n >= 1 << 16
+    t = np.zeros((116, n), dtype=np.uint64)
+    M = (1 << 256) - 1
+    r = lambda: int.from_bytes(rng.bytes(32), "little")
+    cases = [("addmod", M, M, M), ("mulmod", M, M, M), ("mulmod", M, M, M - 1), ("addmod", 5, 6, 0), ("mulmod", 5, 6, 0), ("mulmod", r(), r(), 1),
+             ("addmod", 1, 2, 7), ("mulmod", 0, r(), r()), ("div", r(), 0, 0), ("mod", r(), 0, 0), ("div", M, 1, 0), ("mod", M, M, 0), ("div", 7, 9, 0),
+             ("div", M, 3, 0), ("mod", 1 << 255, (1 << 128) + 1, 0)] + \
+            [(("addmod", "mulmod", "div", "mod")[k % 4], r(), r() >> int(rng.integers(0, 200)) if k % 4 >= 2 else r(), r() >> int(rng.integers(0, 200)))
+             for k in range(nops)]
+    for k, (op, a, b, m) in enumerate(cases):
+        row1, row2, out = arithmetic_modular_rows(op, a, b, m)
+        if op == "div":
+            want = 0 if b == 0 else a // b
+        elif op == "mod":
+            want = 0 if b == 0 else a % b
+        else:
+            want = 0 if m == 0 else ((a + b) % m if op == "addmod" else (a * b) % m)
+        assert out == want, (op, a, b, m)
+        t[:, 2 * k] = row1
+        t[:, 2 * k + 1] = row2
+    t[114] = np.minimum(np.arange(n), 65535).astype(np.uint64)
+    t[115, :65536] = np.bincount(t[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
+    return t
+
+
 # ---- a VALID multi-table segment: CPU padding + empty Arithmetic + Memory initialised from MemBefore, final state in MemAfter ----
 def memory_trace_from_mem_before(log_n, addrs, values):
     """MemoryStark trace whose only real operations are the timestamp-0 initialisation writes of `mem_before`
