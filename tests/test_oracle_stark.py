@@ -190,21 +190,26 @@ def test_corrupted_keccak_sponge_trace_is_rejected(oracle, col, row):
 
 
 # ---- ArithmeticStark MUL rows (the addcy generator covers ADD / SUB / LT / GT only) -----------------------------------------------------
-def test_valid_arithmetic_mul_trace_verifies_and_wrong_product_is_rejected(oracle):
+def test_valid_arithmetic_mul_shl_byte_trace_verifies_and_corruptions_are_rejected(oracle):
+    """MUL (mul.rs), SHL (shift.rs, incl. shifts >= 256) and BYTE (byte.rs, incl. indices >= 32 and with high limbs) rows"""
     tr = traces.arithmetic_mul_trace(16, 3, nops=100)
     bg = BG2[:2]
     proof, _ = orc_prove_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, tr, bg, STATE0)
     ok, err, _ = orc_verify_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, proof, bg, STATE0)
     assert ok, err
-    tr[66, 7] ^= np.uint64(1)               # a wrong product limb, range-check frequencies kept consistent
-    tr[115, :65536] = np.bincount(tr[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
-    proof, _ = orc_prove_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, tr, bg, STATE0)
-    ok, _, _ = orc_verify_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, proof, bg, STATE0)
-    assert not ok
+    byte_row = 106 + 7 + 8                  # a BYTE row with a random index / value
+    assert tr[13, byte_row] == 1 and tr[1, 7] == 1
+    for col, row in ((66, 7), (66, byte_row)):          # a wrong product limb; a wrong selected byte (range-check frequencies kept consistent)
+        t2 = tr.copy()
+        t2[col, row] ^= np.uint64(1)
+        t2[115, :65536] = np.bincount(t2[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
+        proof, _ = orc_prove_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, t2, bg, STATE0)
+        assert not orc_verify_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, proof, bg, STATE0)[0], (col, row)
 
 
 def test_valid_arithmetic_modular_trace_verifies_and_corruptions_are_rejected(oracle):
-    """ADDMOD / MULMOD / DIV / MOD (two-row operations, modular.rs + divmod.rs), incl. modulus / denominator 0 and 1, maximal operands"""
+    """ADDMOD / MULMOD / SUBMOD / the three FP254 operations / DIV / MOD / SHR (two-row operations: modular.rs, divmod.rs, shift.rs), incl.
+    modulus / denominator 0 and 1, negative SUBMOD quotients, shifts >= 256, maximal operands"""
     tr = traces.arithmetic_modular_trace(16, 3, nops=40)
     bg = BG2[:2]
     proof, _ = orc_prove_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, tr, bg, STATE0)

@@ -401,7 +401,7 @@ def arithmetic_mul_rows(a, b):
 
 
 def arithmetic_mul_trace(log_n, seed, nops=200):
-    """ArithmeticStark trace of MUL operations (arithmetic_stark.rs:158-190 + mul.rs generate), incl. edge operands"""
+    """ArithmeticStark trace of MUL, SHL and BYTE operations (arithmetic_stark.rs:158-190 + mul.rs / shift.rs / byte.rs generate), incl. edge operands"""
     rng = np.random.default_rng(seed)
     n = 1 << log_n
     assert n >= 1 << 16
@@ -418,6 +418,50 @@ def arithmetic_mul_trace(log_n, seed, nops=200):
         t[66:82, k] = out
         t[82:98, k] = lo
         t[98:114, k] = hi
+    # BYTE (byte.rs:108-200): index decomposition, the multiplexer tree over the value's limbs, the inverse of the high-limb sum
+    kb = len(vals) + 7
+    byte_cases = [(0, M), (31, 0x1234), (32, M), (1 << 16, M), ((1 << 255) + 3, M), (5 + (7 << 5), M)] + \
+                 [(int(rng.integers(0, 40)), int.from_bytes(rng.bytes(32), "little")) for _ in range(40)]
+    for j, (idx, val) in enumerate(byte_cases):
+        k = kb + j
+        row = [0] * 116
+        row[13] = 1                                                                   # IS_BYTE
+        il = [(idx >> (16 * i)) & 0xFFFF for i in range(16)]
+        row[18:34], row[34:50] = il, [(val >> (16 * i)) & 0xFFFF for i in range(16)]
+        for i in range(5):
+            row[82 + i] = (idx >> i) & 1                                              # BYTE_IDX_DECOMP
+        row[87] = il[0] >> 5                                                          # BYTE_IDX_DECOMP_HI
+        hi_sum = (row[87] + sum(il[1:])) % P
+        inv = pow(hi_sum, P - 2, P) if hi_sum else 1
+        row[91:95] = [(inv >> (16 * i)) & 0xFFFF for i in range(4)]                   # BYTE_IDX_HI_LIMB_SUM_INV_0..3
+        row[90] = int(hi_sum != 0)                                                    # BYTE_IDX_IS_LARGE
+        lvl, src, dest = 3, 34, 98
+        while True:
+            ln = 1 << lvl
+            src += (0 if (idx >> (lvl + 1)) & 1 else 1) * ln
+            row[dest:dest + ln] = row[src:src + ln]
+            if lvl == 0:
+                break
+            src, dest, lvl = dest, dest + ln, lvl - 1
+        lo, hi = row[dest] & 0xFF, row[dest] >> 8
+        row[88], row[89] = lo << 8, hi                                                # BYTE_LAST_LIMB_LO (stored * 256), _HI
+        row[113] = lo if idx & 1 else hi                                              # tree[15]
+        out = row[113] if idx < 32 else 0
+        assert out == ((val >> (8 * (31 - idx))) & 0xFF if idx < 32 else 0)
+        row[66:82] = [(out >> (16 * i)) & 0xFFFF for i in range(16)]
+        t[:, k] = row
+    # SHL (shift.rs:41-76): (shift, input, 1 << shift or 0) in the three input registers, the MUL machinery on registers 1 and 2
+    L = lambda x: [(x >> (16 * i)) & 0xFFFF for i in range(16)]
+    k0 = len(vals)
+    for j, (sh, x) in enumerate([(0, M), (1, M), (255, 3), (256, 5), (1 << 200, 7), (17, int.from_bytes(rng.bytes(32), "little")),
+                                 (200, int.from_bytes(rng.bytes(32), "little"))]):
+        disp = 0 if sh > 255 else 1 << sh
+        out, lo, hi = arithmetic_mul_rows(x, disp)
+        assert sum(o << (16 * i) for i, o in enumerate(out)) == ((x << sh) & M if sh < 256 else 0)
+        k = k0 + j
+        t[14, k] = 1                                                                  # IS_SHL
+        t[18:34, k], t[34:50, k], t[50:66, k] = L(sh), L(x), L(disp)
+        t[66:82, k], t[82:98, k], t[98:114, k] = out, lo, hi
     t[114] = np.minimum(np.arange(n), 65535).astype(np.uint64)
     t[115, :65536] = np.bincount(t[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
     return t
@@ -427,7 +471,7 @@ def _limbs(x, k=16):
     return [(x >> (16 * i)) & 0xFFFF for i in range(k)]
 
 
-def _modular_op(pol, m, is_div):
+def _modular_op(pol, m, is_div, is_sub=False):
     """modular.rs:200-338 generate_modular_op: pol = the 31 input coefficients, m = the modulus (DIV: the denominator).
     -> (output, quotient limbs (32), second row)"""
     constr = list(pol) + [0]
@@ -442,7 +486,8 @@ def _modular_op(pol, m, is_div):
     inp = sum(c << (16 * i) for i, c in enumerate(constr))                                   # columns_to_bigint
     out = inp % modulus
     quot = (inp - out) // modulus
-    out_l, quot_l = _limbs(out), _limbs(quot, 32)
+    out_l = _limbs(out)
+    quot_l = _limbs(quot, 32) if quot >= 0 else [-c for c in _limbs(-quot, 32)]              # bigint_to_columns: sign on every limb
     out_aux_red = _limbs((1 << 256) - modulus + out)
     for i in range(16):
         constr[i] -= out_l[i]
@@ -462,7 +507,14 @@ def _modular_op(pol, m, is_div):
     row2[35:66] = [c & 0xFFFF for c in q[:31]]                                                # MODULAR_AUX_INPUT_LO
     row2[66:97] = [c >> 16 for c in q[:31]]                                                   # MODULAR_AUX_INPUT_HI
     row2[97] = mod_is_zero if is_div else 0                                                   # MODULAR_DIV_DENOM_IS_ZERO
+    if is_sub:                                                                                # :297-322: a negative quotient is stored offset, its sign after it
+        assert all(c == 0 for c in quot_l[16:]) and all(abs(c) <= 0xFFFF for c in quot_l[:16])
+        if quot < 0:
+            quot_l = [c + 0xFFFF for c in quot_l[:16]] + [1] + [0] * 15
     return out, quot_l, row2
+
+
+BN_BASE = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47        # extension_tower.rs:25-30
 
 
 def arithmetic_modular_rows(op, a, b, m):
@@ -470,17 +522,31 @@ def arithmetic_modular_rows(op, a, b, m):
     al, bl = _limbs(a), _limbs(b)
     row1 = [0] * 116
     row1[18:34], row1[34:50] = al, bl
-    if op in ("addmod", "mulmod"):
-        if op == "addmod":
+    flags = {"addmod": 5, "mulmod": 6, "addfp254": 7, "mulfp254": 8, "subfp254": 9, "submod": 10}
+    if op in flags:
+        if op.endswith("fp254"):
+            m = BN_BASE
+        if op.startswith("add"):
             pol = [al[i] + bl[i] for i in range(16)] + [0] * 15                              # pol_add
+        elif op.startswith("sub"):
+            pol = [al[i] - bl[i] for i in range(16)] + [0] * 15                              # pol_sub
         else:
             pol = [sum(al[i] * bl[k - i] for i in range(16) if 0 <= k - i < 16) for k in range(31)]   # pol_mul_wide
-        out, quot_l, row2 = _modular_op(pol, m, False)
-        row1[5 if op == "addmod" else 6] = 1                                                  # IS_ADDMOD / IS_MULMOD
+        out, quot_l, row2 = _modular_op(pol, m, False, is_sub=op.startswith("sub"))
+        row1[flags[op]] = 1
         row1[50:66] = _limbs(m)
         row1[66:82] = _limbs(out)                                                             # MODULAR_OUTPUT
         row1[82:114] = quot_l                                                                 # MODULAR_QUO_INPUT
         return row1, row2, out
+    if op == "shr":                                                                           # shift.rs:41-83: a = shift, b = input
+        disp = 0 if a > 255 else 1 << a
+        out, quot_l, row2 = _modular_op(bl + [0] * 15, disp, True)                            # divmod on registers 1 and 2, filter IS_SHR
+        result = sum(c << (16 * i) for i, c in enumerate(quot_l[:16]))
+        row1[15] = 1                                                                          # IS_SHR
+        row1[50:66] = _limbs(disp)
+        row1[66:82] = _limbs(result)
+        row1[82:98] = _limbs(out)
+        return row1, row2, result
     out, quot_l, row2 = _modular_op(al + [0] * 15, b, op == "div")                            # pol_extend(numerator), modulus = denominator
     assert all(x == 0 for x in quot_l[16:])
     result = sum(c << (16 * i) for i, c in enumerate(quot_l[:16])) if op == "div" else out
@@ -500,17 +566,24 @@ def arithmetic_modular_trace(log_n, seed, nops=60):
     r = lambda: int.from_bytes(rng.bytes(32), "little")
     cases = [("addmod", M, M, M), ("mulmod", M, M, M), ("mulmod", M, M, M - 1), ("addmod", 5, 6, 0), ("mulmod", 5, 6, 0), ("mulmod", r(), r(), 1),
              ("addmod", 1, 2, 7), ("mulmod", 0, r(), r()), ("div", r(), 0, 0), ("mod", r(), 0, 0), ("div", M, 1, 0), ("mod", M, M, 0), ("div", 7, 9, 0),
-             ("div", M, 3, 0), ("mod", 1 << 255, (1 << 128) + 1, 0)] + \
+             ("div", M, 3, 0), ("mod", 1 << 255, (1 << 128) + 1, 0), ("submod", 3, 5, 7), ("submod", 5, 3, 7), ("submod", 0, M, M - 1), ("submod", 9, 9, 0),
+             ("addfp254", BN_BASE - 1, BN_BASE - 1, 0), ("mulfp254", BN_BASE - 1, BN_BASE - 2, 0), ("subfp254", 1, BN_BASE - 1, 0),
+             ("submod", r(), r(), r()), ("submod", r() >> 100, r(), r() >> 3), ("shr", 0, M, 0), ("shr", 255, M, 0), ("shr", 256, M, 0), ("shr", 1 << 77, 5, 0),
+             ("shr", 13, r(), 0)] + \
             [(("addmod", "mulmod", "div", "mod")[k % 4], r(), r() >> int(rng.integers(0, 200)) if k % 4 >= 2 else r(), r() >> int(rng.integers(0, 200)))
              for k in range(nops)]
     for k, (op, a, b, m) in enumerate(cases):
         row1, row2, out = arithmetic_modular_rows(op, a, b, m)
-        if op == "div":
+        if op == "shr":
+            want = b >> a if a < 256 else 0
+        elif op == "div":
             want = 0 if b == 0 else a // b
         elif op == "mod":
             want = 0 if b == 0 else a % b
         else:
-            want = 0 if m == 0 else ((a + b) % m if op == "addmod" else (a * b) % m)
+            mm = BN_BASE if op.endswith("fp254") else m
+            f = (lambda x, y: x + y) if op.startswith("add") else (lambda x, y: x - y) if op.startswith("sub") else (lambda x, y: x * y)
+            want = 0 if mm == 0 else f(a, b) % mm
         assert out == want, (op, a, b, m)
         t[:, 2 * k] = row1
         t[:, 2 * k + 1] = row2
