@@ -118,6 +118,22 @@ def test_valid_keccak_sponge_trace_on_gpu_verifies(ctx, oracle, cfg):
     assert ok, err
 
 
+@pytest.mark.parametrize("table,cfg", [(traces.T_CPU, TEST_CONFIG), (traces.T_CPU, STANDARD_FAST), (traces.T_ARITHMETIC, TEST_CONFIG)])
+def test_valid_traces_with_active_rows_on_gpu(ctx, oracle, table, cfg):
+    """CpuStark with active instruction rows, ArithmeticStark with MUL / SHL / BYTE rows: GPU proof == oracle proof, the restated verifier accepts"""
+    tr = traces.cpu_program_trace(7, "JP0PJ00PPJ0PJ", halt_final=DEFAULT_LABELS[0]) if table == traces.T_CPU else traces.arithmetic_mul_trace(16, 9, nops=60)
+    c = zk.StarkConfig(*cfg)
+    bg = np.array([11, 22, 33, 44], dtype=np.uint64)[:2 * cfg[1]]
+    st0 = np.arange(12, dtype=np.uint64)
+    batch = zk.PolynomialBatch.from_values(ctx, tr, c.rate_bits, c.cap_height, keep_values=True)
+    ctl = zk.get_ctl_data(ctx, table, batch, bg, c.num_challenges)
+    proof, st = zk.prove_single_table(ctx, table, c, batch, ctl, st0, zk.KernelLabels(*DEFAULT_LABELS))
+    want, st_want = orc_prove_table(oracle, table, cfg, tr, bg, st0)
+    assert np.array_equal(proof.words, want) and np.array_equal(st, st_want)
+    ok, err, _ = orc_verify_table(oracle, table, cfg, proof.words, bg, st0)
+    assert ok, err
+
+
 def test_segment_from_device_finished_keccak_and_logic_traces(ctx, oracle):
     rng = np.random.default_rng(9)
     inputs = rng.integers(0, 1 << 64, size=(5, 25), dtype=np.uint64)

@@ -222,3 +222,29 @@ def test_valid_arithmetic_modular_trace_verifies_and_corruptions_are_rejected(or
         t2[115, :65536] = np.bincount(t2[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
         proof, _ = orc_prove_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, t2, bg, STATE0)
         assert not orc_verify_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, proof, bg, STATE0)[0], (col, row)
+
+
+# ---- CpuStark with ACTIVE rows (the other valid Cpu traces of this repo are all-padding rows) -------------------------------------------
+@pytest.mark.parametrize("program", ["J", "P", "0", "JP0PJ00PPJ"])
+def test_cpu_program_rows_verify(oracle, program):
+    """a straight-line kernel program of JUMPDEST / PC / PUSH0 running into halt_final: decode, control flow, gas, clock, the stack's push
+    and no-op behaviours (cached top, partial-channel write of the old top, stack_inv), pc.rs, push0.rs, halt.rs with operation flags set"""
+    tr = traces.cpu_program_trace(6, program)
+    bg = BG2[:2]
+    proof, st = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    ok, err, st2 = orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)
+    assert ok, err
+    assert np.array_equal(st, st2)
+
+
+@pytest.mark.parametrize("what,col,row,delta", [
+    ("gas after JUMPDEST", 5, 1, 1), ("pc skips an instruction", 2, 3, 1), ("PC pushes another value", 46, 2, 1), ("PUSH0 pushes non-zero", 46, 3, 1),
+    ("old top not written to memory", 80, 3, -1), ("partial channel address", 84, 3, 1), ("opcode bit", 26, 1, 1), ("stack_len after a push", 3, 2, 1),
+    ("top changes over JUMPDEST", 46, 5, 1), ("two operation flags", 13, 1, 1), ("clock", 40, 4, 1), ("kernel mode dropped", 4, 2, -1),
+    ("stack_inv_aux", 37, 3, -1)])
+def test_cpu_program_corruptions_are_rejected(oracle, what, col, row, delta):
+    tr = traces.cpu_program_trace(6, "JP0PJ00PPJ")
+    tr[col, row] = np.uint64(int(tr[col, row]) + delta)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what

@@ -98,6 +98,43 @@ def cpu_padding_trace(log_n, halt_final=0x1234):
     return t
 
 
+def cpu_program_trace(log_n, program, halt_final=0x1234, stack_len0=0, gas0=50):
+    """CpuStark trace with ACTIVE rows: a straight-line kernel-mode program of JUMPDEST / PC / PUSH0 instructions that runs into
+    `halt_final`, then the padding rows.  Exercises decode.rs, control_flow.rs, gas.rs, clock.rs, stack.rs (push and no-op behaviours,
+    the cached top of the stack, the partial-channel write of the old top, stack_inv / stack_inv_aux), pc.rs, push0.rs, membus.rs,
+    halt.rs with non-zero operation flags.  program: string of 'J' (JUMPDEST 0x5b), 'P' (PC 0x58), '0' (PUSH0 0x5f)."""
+    n = 1 << log_n
+    k = len(program)
+    assert 0 < k < n
+    t = np.zeros((85, n), dtype=np.uint64)
+    t[4] = 1                                           # is_kernel_mode
+    t[40] = np.arange(1, n + 1, dtype=np.uint64)       # clock
+    opcode = {"J": 0x5b, "P": 0x58, "0": 0x5f}
+    pc, sl, gas, top = halt_final - k, stack_len0, gas0, [0] * 8
+    for r, ins in enumerate(program):
+        t[2, r], t[3, r], t[5, r] = pc, sl, gas
+        t[46:54, r] = top                              # mem_channels[0].value: the cached top of the stack
+        for b in range(8):
+            t[24 + b, r] = (opcode[ins] >> b) & 1      # opcode_bits, little endian
+        if ins == "J":
+            t[13, r] = 1                               # op.jumpdest_keccak_general
+            gas += 1                                   # G_JUMPDEST
+        else:
+            t[21, r] = 1                               # op.pc_push0
+            if sl > 0:                                 # the old top goes to memory through the partial channel
+                t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, 0, 1, sl - 1      # used, write, context, Segment::Stack, stack_len - 1
+                t[36, r], t[37, r] = pow(sl, P - 2, P), 1                                   # general.stack(): stack_inv, stack_inv_aux
+            top = [pc if ins == "P" else 0] + [0] * 7
+            sl += 1
+            gas += 2                                   # G_BASE
+        pc += 1
+    assert pc == halt_final
+    t[2, k:], t[3, k:], t[5, k:] = halt_final, sl, gas
+    for l in range(8):
+        t[46 + l, k:] = top[l]
+    return t
+
+
 # ---- KeccakStark (keccak_stark.rs:70-250) ---------------------------------------------------------------------------------
 KECCAK_RC = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B,
              0x0000000080000001, 0x8000000080008081, 0x8000000000008009, 0x000000000000008A, 0x0000000000000088,
