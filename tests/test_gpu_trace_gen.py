@@ -121,7 +121,7 @@ def test_valid_keccak_sponge_trace_on_gpu_verifies(ctx, oracle, cfg):
 @pytest.mark.parametrize("table,cfg", [(traces.T_CPU, TEST_CONFIG), (traces.T_CPU, STANDARD_FAST), (traces.T_ARITHMETIC, TEST_CONFIG)])
 def test_valid_traces_with_active_rows_on_gpu(ctx, oracle, table, cfg):
     """CpuStark with active instruction rows, ArithmeticStark with MUL / SHL / BYTE rows: GPU proof == oracle proof, the restated verifier accepts"""
-    tr = traces.cpu_program_trace(7, "JP0PJ00PPJ0PJ", halt_final=DEFAULT_LABELS[0]) if table == traces.T_CPU else traces.arithmetic_mul_trace(16, 9, nops=60)
+    tr = traces.cpu_program_trace(7, "PPNEZ0PAXNJPPPMXXXJ0PJ", halt_final=DEFAULT_LABELS[0]) if table == traces.T_CPU else traces.arithmetic_mul_trace(16, 9, nops=60)
     c = zk.StarkConfig(*cfg)
     bg = np.array([11, 22, 33, 44], dtype=np.uint64)[:2 * cfg[1]]
     st0 = np.arange(12, dtype=np.uint64)

@@ -225,10 +225,11 @@ def test_valid_arithmetic_modular_trace_verifies_and_corruptions_are_rejected(or
 
 
 # ---- CpuStark with ACTIVE rows (the other valid Cpu traces of this repo are all-padding rows) -------------------------------------------
-@pytest.mark.parametrize("program", ["J", "P", "0", "JP0PJ00PPJ"])
+@pytest.mark.parametrize("program", ["J", "P", "0", "JP0PJ00PPJ", "PN", "PX", "PPXJ", "PZ", "0Z", "PPE", "P0E", "PPA", "PPM", "PPNEZ0PAXNJPPPMXXXJ"])
 def test_cpu_program_rows_verify(oracle, program):
-    """a straight-line kernel program of JUMPDEST / PC / PUSH0 running into halt_final: decode, control flow, gas, clock, the stack's push
-    and no-op behaviours (cached top, partial-channel write of the old top, stack_inv), pc.rs, push0.rs, halt.rs with operation flags set"""
+    """a straight-line kernel program (JUMPDEST, PC, PUSH0, NOT, POP, ISZERO, EQ, ADD, MUL) running into halt_final: decode, control flow,
+    gas, clock, every StackBehavior shape (cached top, partial-channel write of the old top, second-operand and new-top reads, stack_inv*),
+    pc.rs, push0.rs, simple_logic/{not,eq_iszero}.rs, halt.rs with operation flags set"""
     tr = traces.cpu_program_trace(6, program)
     bg = BG2[:2]
     proof, st = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
@@ -245,6 +246,21 @@ def test_cpu_program_rows_verify(oracle, program):
 def test_cpu_program_corruptions_are_rejected(oracle, what, col, row, delta):
     tr = traces.cpu_program_trace(6, "JP0PJ00PPJ")
     tr[col, row] = np.uint64(int(tr[col, row]) + delta)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what
+
+
+PROGRAM2 = "PPNEZ0PAXNJPPPMXXXJ"      # rows: 0 P, 1 P, 2 N, 3 E, 4 Z, 5 0, 6 P, 7 A, 8 X, 9 N, 10 J, 11 P, 12 P, 13 P, 14 M, 15 X, 16 X, 17 X, 18 J
+
+
+@pytest.mark.parametrize("what,col,row,delta", [
+    ("NOT result limb", 46 + 3, 3, 1), ("EQ result", 46, 4, 1), ("EQ diff_pinv", 32, 3, 1), ("EQ second operand address", 58, 3, 1),
+    ("EQ second operand not read", 54, 3, -1), ("ISZERO result", 46, 5, 1), ("ADD gas", 5, 8, 1), ("MUL gas", 5, 15, -2),
+    ("stack_len after ADD", 3, 8, 1), ("POP new-top read missing", 41, 16, -1), ("POP new-top address", 45, 16, 1), ("stack_inv_aux_2", 38, 15, -1)])
+def test_cpu_program_corruptions_of_pops_and_logic_are_rejected(oracle, what, col, row, delta):
+    tr = traces.cpu_program_trace(6, PROGRAM2)
+    tr[col, row] = np.uint64((int(tr[col, row]) + delta) % traces.P)
     bg = BG2[:2]
     proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
     assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what

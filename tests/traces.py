@@ -98,40 +98,83 @@ def cpu_padding_trace(log_n, halt_final=0x1234):
     return t
 
 
-def cpu_program_trace(log_n, program, halt_final=0x1234, stack_len0=0, gas0=50):
-    """CpuStark trace with ACTIVE rows: a straight-line kernel-mode program of JUMPDEST / PC / PUSH0 instructions that runs into
-    `halt_final`, then the padding rows.  Exercises decode.rs, control_flow.rs, gas.rs, clock.rs, stack.rs (push and no-op behaviours,
-    the cached top of the stack, the partial-channel write of the old top, stack_inv / stack_inv_aux), pc.rs, push0.rs, membus.rs,
-    halt.rs with non-zero operation flags.  program: string of 'J' (JUMPDEST 0x5b), 'P' (PC 0x58), '0' (PUSH0 0x5f)."""
+def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
+    """CpuStark trace with ACTIVE rows: a straight-line kernel-mode program that runs into `halt_final`, then the padding rows.
+    program: string of  J JUMPDEST 0x5b | P PC 0x58 | 0 PUSH0 0x5f | N NOT 0x19 | X POP 0x50 | Z ISZERO 0x15 | E EQ 0x14 | A ADD 0x01 |
+    M MUL 0x02 | R = PUSH0 whose pushed word is replaced by a random one in the stack MODEL only (never used: PUSH0 must push 0).
+    The stack starts empty; the model keeps the 256-bit words so that the cached top (mem_channels[0]), the second-operand reads
+    (mem_channels[1]), the partial-channel write of the old top and the new-top read after POP carry consistent values.
+    Exercises decode.rs, control_flow.rs, gas.rs, clock.rs, stack.rs (every StackBehavior shape: push, no-op, unary, binary, pop with and
+    without a new-top read, stack_inv / stack_inv_aux / stack_inv_aux_2), pc.rs, push0.rs, simple_logic/{not,eq_iszero}.rs, membus.rs,
+    halt.rs with operation flags set.  (ADD / MUL results are checked by the Arithmetic table through a cross-table lookup only.)"""
     n = 1 << log_n
     k = len(program)
     assert 0 < k < n
     t = np.zeros((85, n), dtype=np.uint64)
     t[4] = 1                                           # is_kernel_mode
     t[40] = np.arange(1, n + 1, dtype=np.uint64)       # clock
-    opcode = {"J": 0x5b, "P": 0x58, "0": 0x5f}
-    pc, sl, gas, top = halt_final - k, stack_len0, gas0, [0] * 8
+    opcode = {"J": 0x5b, "P": 0x58, "0": 0x5f, "N": 0x19, "X": 0x50, "Z": 0x15, "E": 0x14, "A": 0x01, "M": 0x02}
+    flag = {"J": 13, "P": 21, "0": 21, "N": 11, "X": 11, "Z": 9, "E": 9, "A": 6, "M": 6}
+    cost = {"J": 1, "P": 2, "0": 2, "N": 3, "X": 2, "Z": 3, "E": 3, "A": 3, "M": 5}
+    limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+    M256 = (1 << 256) - 1
+    pc, gas, stack = halt_final - k, gas0, []
+    read_top_next = False                              # the previous instruction was a POP that left a non-empty stack
     for r, ins in enumerate(program):
+        sl = len(stack)
         t[2, r], t[3, r], t[5, r] = pc, sl, gas
-        t[46:54, r] = top                              # mem_channels[0].value: the cached top of the stack
+        if stack:
+            t[46:54, r] = limbs(stack[-1])             # mem_channels[0].value: the cached top of the stack
+        if read_top_next:                              # ... read from memory at the start of this row (stack.rs:371-386)
+            t[41, r], t[42, r], t[43, r], t[44, r], t[45, r] = 1, 1, 0, 1, sl - 1
+            read_top_next = False
         for b in range(8):
             t[24 + b, r] = (opcode[ins] >> b) & 1      # opcode_bits, little endian
-        if ins == "J":
-            t[13, r] = 1                               # op.jumpdest_keccak_general
-            gas += 1                                   # G_JUMPDEST
-        else:
-            t[21, r] = 1                               # op.pc_push0
+        t[flag[ins], r] = 1
+        if ins in "P0":                                # push only
             if sl > 0:                                 # the old top goes to memory through the partial channel
-                t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, 0, 1, sl - 1      # used, write, context, Segment::Stack, stack_len - 1
+                t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, 0, 1, sl - 1
                 t[36, r], t[37, r] = pow(sl, P - 2, P), 1                                   # general.stack(): stack_inv, stack_inv_aux
-            top = [pc if ins == "P" else 0] + [0] * 7
-            sl += 1
-            gas += 2                                   # G_BASE
+            stack.append(pc if ins == "P" else 0)
+        elif ins in "NX":                              # not_pop: stack_inv / stack_inv_aux refer to stack_len - 1
+            assert sl >= 1
+            aux = int(sl != 1)
+            t[36, r], t[37, r] = (pow(sl - 1, P - 2, P) if aux else 0), aux
+            if ins == "N":
+                stack[-1] ^= M256
+            else:
+                t[38, r] = aux                         # stack_inv_aux_2 = stack_inv_aux * (1 - opcode_bits[0])
+                stack.pop()
+                read_top_next = bool(aux)
+        elif ins == "Z":
+            assert sl >= 1
+            x = limbs(stack[-1])
+            nz = [l for l in x if l]
+            for i, l in enumerate(x):                  # general.logic().diff_pinv (eq_iszero.rs:25-42)
+                t[32 + i, r] = pow(l, P - 2, P) * pow(len(nz), P - 2, P) % P if l else 0
+            stack[-1] = int(stack[-1] == 0)
+        elif ins in "EAM":                             # two operands: the second one is read through mem_channels[1]
+            assert sl >= 2
+            a, b = stack.pop(), stack.pop()
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2
+            t[59:67, r] = limbs(b)
+            if ins == "E":
+                d = [(x - y) % P for x, y in zip(limbs(a), limbs(b))]
+                nz = [x for x in d if x]
+                for i, x in enumerate(d):
+                    t[32 + i, r] = pow(x, P - 2, P) * pow(len(nz), P - 2, P) % P if x else 0
+                stack.append(int(a == b))
+            else:
+                stack.append((a + b) & M256 if ins == "A" else (a * b) & M256)
+        gas += cost[ins]
         pc += 1
     assert pc == halt_final
-    t[2, k:], t[3, k:], t[5, k:] = halt_final, sl, gas
-    for l in range(8):
-        t[46 + l, k:] = top[l]
+    t[2, k:], t[3, k:], t[5, k:] = halt_final, len(stack), gas
+    if stack:
+        for l, v in enumerate(limbs(stack[-1])):
+            t[46 + l, k:] = v
+    # a POP that leaves a non-empty stack reads the new top on the NEXT row, and a halt row may not use a memory channel (halt.rs:33-41)
+    assert not read_top_next, "the program must not end with a POP that leaves a non-empty stack"
     return t
 
 
