@@ -225,9 +225,11 @@ def test_valid_arithmetic_modular_trace_verifies_and_corruptions_are_rejected(or
 
 
 # ---- CpuStark with ACTIVE rows (the other valid Cpu traces of this repo are all-padding rows) -------------------------------------------
-@pytest.mark.parametrize("program", ["J", "P", "0", "JP0PJ00PPJ", "PN", "PX", "PPXJ", "PZ", "0Z", "PPE", "P0E", "PPA", "PPM", "PPNEZ0PAXNJPPPMXXXJ"])
+@pytest.mark.parametrize("program", ["J", "P", "0", "JP0PJ00PPJ", "PN", "PX", "PPXJ", "PZ", "0Z", "PPE", "P0E", "PPA", "PPM", "PPNEZ0PAXNJPPPMXXXJ",
+                                     "PPPa", "PPPm", "PPPPPPPPSDOLGPPB&|^PPaPPmXJ"])
 def test_cpu_program_rows_verify(oracle, program):
-    """a straight-line kernel program (JUMPDEST, PC, PUSH0, NOT, POP, ISZERO, EQ, ADD, MUL) running into halt_final: decode, control flow,
+    """a straight-line kernel program (JUMPDEST, PC, PUSH0, NOT, POP, ISZERO, EQ, the eight binary arithmetic instructions, AND / OR / XOR,
+    ADDMOD, MULMOD) running into halt_final: decode, control flow,
     gas, clock, every StackBehavior shape (cached top, partial-channel write of the old top, second-operand and new-top reads, stack_inv*),
     pc.rs, push0.rs, simple_logic/{not,eq_iszero}.rs, halt.rs with operation flags set"""
     tr = traces.cpu_program_trace(6, program)
@@ -260,6 +262,22 @@ PROGRAM2 = "PPNEZ0PAXNJPPPMXXXJ"      # rows: 0 P, 1 P, 2 N, 3 E, 4 Z, 5 0, 6 P,
     ("stack_len after ADD", 3, 8, 1), ("POP new-top read missing", 41, 16, -1), ("POP new-top address", 45, 16, 1), ("stack_inv_aux_2", 38, 15, -1)])
 def test_cpu_program_corruptions_of_pops_and_logic_are_rejected(oracle, what, col, row, delta):
     tr = traces.cpu_program_trace(6, PROGRAM2)
+    tr[col, row] = np.uint64((int(tr[col, row]) + delta) % traces.P)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what
+
+
+PROGRAM3 = "PPPPPPPPSDOLGPPB&|^PPaPPmXJ"     # rows 8 S, 9 D, 10 O, 11 L, 12 G, 15 B, 16 &, 17 |, 18 ^, 21 a, 24 m
+
+
+@pytest.mark.parametrize("what,col,row,delta", [
+    ("DIV gas", 5, 10, -2), ("LT gas", 5, 12, 2), ("AND gas", 5, 17, 1), ("ADDMOD gas", 5, 22, -8), ("ADDMOD third operand not read", 67, 21, -1),
+    ("MULMOD third operand address", 71, 24, 1), ("stack_len after MULMOD", 3, 25, 1), ("ADDMOD second operand address", 58, 21, 1), ("XOR with the OR flag too", 6, 18, 1)])
+def test_cpu_program_corruptions_of_arithmetic_and_logic_rows_are_rejected(oracle, what, col, row, delta):
+    """(which of the arithmetic opcodes a binary_op row carries is NOT an in-table constraint: decode.rs leaves it to the cross-table
+    lookup with the Arithmetic table, so an opcode-bit flip on such a row is deliberately not among the cases)"""
+    tr = traces.cpu_program_trace(6, PROGRAM3)
     tr[col, row] = np.uint64((int(tr[col, row]) + delta) % traces.P)
     bg = BG2[:2]
     proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)

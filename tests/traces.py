@@ -101,23 +101,31 @@ def cpu_padding_trace(log_n, halt_final=0x1234):
 def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
     """CpuStark trace with ACTIVE rows: a straight-line kernel-mode program that runs into `halt_final`, then the padding rows.
     program: string of  J JUMPDEST 0x5b | P PC 0x58 | 0 PUSH0 0x5f | N NOT 0x19 | X POP 0x50 | Z ISZERO 0x15 | E EQ 0x14 | A ADD 0x01 |
-    M MUL 0x02 | R = PUSH0 whose pushed word is replaced by a random one in the stack MODEL only (never used: PUSH0 must push 0).
+    M MUL 0x02 | S SUB 0x03 | D DIV 0x04 | O MOD 0x06 | L LT 0x10 | G GT 0x11 | B BYTE 0x1a | & AND 0x16 | "|" OR 0x17 | ^ XOR 0x18 |
+    a ADDMOD 0x08 | m MULMOD 0x09.
     The stack starts empty; the model keeps the 256-bit words so that the cached top (mem_channels[0]), the second-operand reads
     (mem_channels[1]), the partial-channel write of the old top and the new-top read after POP carry consistent values.
     Exercises decode.rs, control_flow.rs, gas.rs, clock.rs, stack.rs (every StackBehavior shape: push, no-op, unary, binary, pop with and
     without a new-top read, stack_inv / stack_inv_aux / stack_inv_aux_2), pc.rs, push0.rs, simple_logic/{not,eq_iszero}.rs, membus.rs,
-    halt.rs with operation flags set.  (ADD / MUL results are checked by the Arithmetic table through a cross-table lookup only.)"""
+    halt.rs with operation flags set.  (The results of the arithmetic and logic instructions are checked by the Arithmetic / Logic
+    tables through cross-table lookups only; in this table they meet the decode, gas and stack constraints.)"""
     n = 1 << log_n
     k = len(program)
     assert 0 < k < n
+    M256 = (1 << 256) - 1
     t = np.zeros((85, n), dtype=np.uint64)
     t[4] = 1                                           # is_kernel_mode
     t[40] = np.arange(1, n + 1, dtype=np.uint64)       # clock
-    opcode = {"J": 0x5b, "P": 0x58, "0": 0x5f, "N": 0x19, "X": 0x50, "Z": 0x15, "E": 0x14, "A": 0x01, "M": 0x02}
-    flag = {"J": 13, "P": 21, "0": 21, "N": 11, "X": 11, "Z": 9, "E": 9, "A": 6, "M": 6}
-    cost = {"J": 1, "P": 2, "0": 2, "N": 3, "X": 2, "Z": 3, "E": 3, "A": 3, "M": 5}
+    opcode = {"J": 0x5b, "P": 0x58, "0": 0x5f, "N": 0x19, "X": 0x50, "Z": 0x15, "E": 0x14, "A": 0x01, "M": 0x02,
+              "S": 0x03, "D": 0x04, "O": 0x06, "L": 0x10, "G": 0x11, "B": 0x1a, "&": 0x16, "|": 0x17, "^": 0x18, "a": 0x08, "m": 0x09}
+    flag = {"J": 13, "P": 21, "0": 21, "N": 11, "X": 11, "Z": 9, "E": 9, "A": 6, "M": 6,
+            "S": 6, "D": 6, "O": 6, "L": 6, "G": 6, "B": 6, "&": 10, "|": 10, "^": 10, "a": 7, "m": 7}
+    cost = {"J": 1, "P": 2, "0": 2, "N": 3, "X": 2, "Z": 3, "E": 3, "A": 3, "M": 5,
+            "S": 3, "D": 5, "O": 5, "L": 3, "G": 3, "B": 3, "&": 3, "|": 3, "^": 3, "a": 8, "m": 8}
+    binary = {"A": lambda a, b: (a + b) & M256, "M": lambda a, b: (a * b) & M256, "S": lambda a, b: (a - b) & M256,
+              "D": lambda a, b: a // b if b else 0, "O": lambda a, b: a % b if b else 0, "L": lambda a, b: int(a < b), "G": lambda a, b: int(a > b),
+              "B": lambda a, b: (b >> (8 * (31 - a))) & 0xFF if a < 32 else 0, "&": lambda a, b: a & b, "|": lambda a, b: a | b, "^": lambda a, b: a ^ b}
     limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
-    M256 = (1 << 256) - 1
     pc, gas, stack = halt_final - k, gas0, []
     read_top_next = False                              # the previous instruction was a POP that left a non-empty stack
     for r, ins in enumerate(program):
@@ -153,7 +161,15 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
             for i, l in enumerate(x):                  # general.logic().diff_pinv (eq_iszero.rs:25-42)
                 t[32 + i, r] = pow(l, P - 2, P) * pow(len(nz), P - 2, P) % P if l else 0
             stack[-1] = int(stack[-1] == 0)
-        elif ins in "EAM":                             # two operands: the second one is read through mem_channels[1]
+        elif ins in "am":                              # three operands: the second and third are read through mem_channels[1], [2]
+            assert sl >= 3
+            a, b, c = stack.pop(), stack.pop(), stack.pop()
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2
+            t[59:67, r] = limbs(b)
+            t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 1, 0, 1, sl - 3
+            t[72:80, r] = limbs(c)
+            stack.append(0 if c == 0 else ((a + b) % c if ins == "a" else (a * b) % c))
+        elif ins in "EAMSDOLGB&|^":                    # two operands: the second one is read through mem_channels[1]
             assert sl >= 2
             a, b = stack.pop(), stack.pop()
             t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2
@@ -165,7 +181,7 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
                     t[32 + i, r] = pow(x, P - 2, P) * pow(len(nz), P - 2, P) % P if x else 0
                 stack.append(int(a == b))
             else:
-                stack.append((a + b) & M256 if ins == "A" else (a * b) & M256)
+                stack.append(binary[ins](a, b))
         gas += cost[ins]
         pc += 1
     assert pc == halt_final
