@@ -226,10 +226,11 @@ def test_valid_arithmetic_modular_trace_verifies_and_corruptions_are_rejected(or
 
 # ---- CpuStark with ACTIVE rows (the other valid Cpu traces of this repo are all-padding rows) -------------------------------------------
 @pytest.mark.parametrize("program", ["J", "P", "0", "JP0PJ00PPJ", "PN", "PX", "PPXJ", "PZ", "0Z", "PPE", "P0E", "PPA", "PPM", "PPNEZ0PAXNJPPPMXXXJ",
-                                     "PPPa", "PPPm", "PPPPPPPPSDOLGPPB&|^PPaPPmXJ"])
+                                     "PPPa", "PPPm", "PPPPPPPPSDOLGPPB&|^PPaPPmXJ",
+                                     "Pu", "PPv", "PPs", "PPPt", "P" * 17 + "qyJ", "PPPuvwstNXJ"])
 def test_cpu_program_rows_verify(oracle, program):
     """a straight-line kernel program (JUMPDEST, PC, PUSH0, NOT, POP, ISZERO, EQ, the eight binary arithmetic instructions, AND / OR / XOR,
-    ADDMOD, MULMOD) running into halt_final: decode, control flow,
+    ADDMOD, MULMOD, DUP1/2/3/16, SWAP1/2/16) running into halt_final: decode, control flow,
     gas, clock, every StackBehavior shape (cached top, partial-channel write of the old top, second-operand and new-top reads, stack_inv*),
     pc.rs, push0.rs, simple_logic/{not,eq_iszero}.rs, halt.rs with operation flags set"""
     tr = traces.cpu_program_trace(6, program)
@@ -278,6 +279,21 @@ def test_cpu_program_corruptions_of_arithmetic_and_logic_rows_are_rejected(oracl
     """(which of the arithmetic opcodes a binary_op row carries is NOT an in-table constraint: decode.rs leaves it to the cross-table
     lookup with the Arithmetic table, so an opcode-bit flip on such a row is deliberately not among the cases)"""
     tr = traces.cpu_program_trace(6, PROGRAM3)
+    tr[col, row] = np.uint64((int(tr[col, row]) + delta) % traces.P)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what
+
+
+PROGRAM4 = "PPPuvwstNXJ"     # rows 3 u DUP1, 4 v DUP2, 5 w DUP3, 6 s SWAP1, 7 t SWAP2
+
+
+@pytest.mark.parametrize("what,col,row,delta", [
+    ("DUP2 reads another element", 71, 4, 1), ("DUP2 new top differs from the element read", 46, 5, 1), ("DUP1 old top not written", 54, 3, -1),
+    ("DUP3 written value differs from the top", 59, 5, 1), ("SWAP1 write address", 71, 6, 1), ("SWAP2 value written differs from the top", 72, 7, 1),
+    ("SWAP2 new top differs from the element read", 46, 8, 1), ("stack_len after DUP", 3, 4, 1), ("DUP gas", 5, 4, 1), ("SWAP marked as a read", 68, 6, 1)])
+def test_cpu_program_corruptions_of_dup_swap_rows_are_rejected(oracle, what, col, row, delta):
+    tr = traces.cpu_program_trace(6, PROGRAM4)
     tr[col, row] = np.uint64((int(tr[col, row]) + delta) % traces.P)
     bg = BG2[:2]
     proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)

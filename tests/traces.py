@@ -102,7 +102,7 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
     """CpuStark trace with ACTIVE rows: a straight-line kernel-mode program that runs into `halt_final`, then the padding rows.
     program: string of  J JUMPDEST 0x5b | P PC 0x58 | 0 PUSH0 0x5f | N NOT 0x19 | X POP 0x50 | Z ISZERO 0x15 | E EQ 0x14 | A ADD 0x01 |
     M MUL 0x02 | S SUB 0x03 | D DIV 0x04 | O MOD 0x06 | L LT 0x10 | G GT 0x11 | B BYTE 0x1a | & AND 0x16 | "|" OR 0x17 | ^ XOR 0x18 |
-    a ADDMOD 0x08 | m MULMOD 0x09.
+    a ADDMOD 0x08 | m MULMOD 0x09 | u v w q DUP1 DUP2 DUP3 DUP16 | s t y SWAP1 SWAP2 SWAP16.
     The stack starts empty; the model keeps the 256-bit words so that the cached top (mem_channels[0]), the second-operand reads
     (mem_channels[1]), the partial-channel write of the old top and the new-top read after POP carry consistent values.
     Exercises decode.rs, control_flow.rs, gas.rs, clock.rs, stack.rs (every StackBehavior shape: push, no-op, unary, binary, pop with and
@@ -122,6 +122,11 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
             "S": 6, "D": 6, "O": 6, "L": 6, "G": 6, "B": 6, "&": 10, "|": 10, "^": 10, "a": 7, "m": 7}
     cost = {"J": 1, "P": 2, "0": 2, "N": 3, "X": 2, "Z": 3, "E": 3, "A": 3, "M": 5,
             "S": 3, "D": 5, "O": 5, "L": 3, "G": 3, "B": 3, "&": 3, "|": 3, "^": 3, "a": 8, "m": 8}
+    dup, swap = {"u": 0, "v": 1, "w": 2, "q": 15}, {"s": 0, "t": 1, "y": 15}          # DUP1 / DUP2 / DUP3 / DUP16, SWAP1 / SWAP2 / SWAP16
+    for c, i in dup.items():
+        opcode[c], flag[c], cost[c] = 0x80 + i, 16, 3
+    for c, i in swap.items():
+        opcode[c], flag[c], cost[c] = 0x90 + i, 16, 3
     binary = {"A": lambda a, b: (a + b) & M256, "M": lambda a, b: (a * b) & M256, "S": lambda a, b: (a - b) & M256,
               "D": lambda a, b: a // b if b else 0, "O": lambda a, b: a % b if b else 0, "L": lambda a, b: int(a < b), "G": lambda a, b: int(a > b),
               "B": lambda a, b: (b >> (8 * (31 - a))) & 0xFF if a < 32 else 0, "&": lambda a, b: a & b, "|": lambda a, b: a | b, "^": lambda a, b: a ^ b}
@@ -161,6 +166,22 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
             for i, l in enumerate(x):                  # general.logic().diff_pinv (eq_iszero.rs:25-42)
                 t[32 + i, r] = pow(l, P - 2, P) * pow(len(nz), P - 2, P) % P if l else 0
             stack[-1] = int(stack[-1] == 0)
+        elif ins in dup:                               # dup_swap.rs:112-141: the top goes to memory (channel 1), element n is read (channel 2)
+            i = dup[ins]
+            assert sl > i
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 0, 0, 1, sl - 1
+            t[59:67, r] = limbs(stack[-1])
+            t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 1, 0, 1, sl - 1 - i
+            t[72:80, r] = limbs(stack[-1 - i])
+            stack.append(stack[-1 - i])
+        elif ins in swap:                              # dup_swap.rs:207-244: element n+1 is read (channel 1), the top is written there (channel 2)
+            i = swap[ins]
+            assert sl > i + 1
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2 - i
+            t[59:67, r] = limbs(stack[-2 - i])
+            t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 0, 0, 1, sl - 2 - i
+            t[72:80, r] = limbs(stack[-1])
+            stack[-1], stack[-2 - i] = stack[-2 - i], stack[-1]
         elif ins in "am":                              # three operands: the second and third are read through mem_channels[1], [2]
             assert sl >= 3
             a, b, c = stack.pop(), stack.pop(), stack.pop()
