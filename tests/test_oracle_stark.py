@@ -227,10 +227,12 @@ def test_valid_arithmetic_modular_trace_verifies_and_corruptions_are_rejected(or
 # ---- CpuStark with ACTIVE rows (the other valid Cpu traces of this repo are all-padding rows) -------------------------------------------
 @pytest.mark.parametrize("program", ["J", "P", "0", "JP0PJ00PPJ", "PN", "PX", "PPXJ", "PZ", "0Z", "PPE", "P0E", "PPA", "PPM", "PPNEZ0PAXNJPPPMXXXJ",
                                      "PPPa", "PPPm", "PPPPPPPPSDOLGPPB&|^PPaPPmXJ",
-                                     "Pu", "PPv", "PPs", "PPPt", "P" * 17 + "qyJ", "PPPuvwstNXJ"])
+                                     "Pu", "PPv", "PPs", "PPPt", "P" * 17 + "qyJ", "PPPuvwstNXJ",
+                                     "PPSuAuAPAjNJ", "0PPSuAuAPAjNJ", "0PPSuAuAPAiJJ", "PPPSuAuAPAiNJ", "00PPSuAuAPAiJJ", "0PPPSuAuAPAiNJ"])
 def test_cpu_program_rows_verify(oracle, program):
     """a straight-line kernel program (JUMPDEST, PC, PUSH0, NOT, POP, ISZERO, EQ, the eight binary arithmetic instructions, AND / OR / XOR,
-    ADDMOD, MULMOD, DUP1/2/3/16, SWAP1/2/16) running into halt_final: decode, control flow,
+    ADDMOD, MULMOD, DUP1/2/3/16, SWAP1/2/16, JUMP and JUMPI taken and not taken — the destinations are computed on the stack from PC values)
+    running into halt_final: decode, control flow,
     gas, clock, every StackBehavior shape (cached top, partial-channel write of the old top, second-operand and new-top reads, stack_inv*),
     pc.rs, push0.rs, simple_logic/{not,eq_iszero}.rs, halt.rs with operation flags set"""
     tr = traces.cpu_program_trace(6, program)
@@ -294,6 +296,25 @@ PROGRAM4 = "PPPuvwstNXJ"     # rows 3 u DUP1, 4 v DUP2, 5 w DUP3, 6 s SWAP1, 7 t
     ("SWAP2 new top differs from the element read", 46, 8, 1), ("stack_len after DUP", 3, 4, 1), ("DUP gas", 5, 4, 1), ("SWAP marked as a read", 68, 6, 1)])
 def test_cpu_program_corruptions_of_dup_swap_rows_are_rejected(oracle, what, col, row, delta):
     tr = traces.cpu_program_trace(6, PROGRAM4)
+    tr[col, row] = np.uint64((int(tr[col, row]) + delta) % traces.P)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what
+
+
+PROGRAM5 = "0PPPSuAuAPAiNJ"     # rows 0..10 build [0, cond, dst]; row 11 = JUMPI taken to the J at +13, skipping the N at +12; one element stays
+
+
+@pytest.mark.parametrize("what,col,row,delta", [
+    ("JUMPI lands elsewhere", 2, 12, -1), ("should_jump cleared", 32, 11, -1), ("cond_sum_pinv", 33, 11, 1),
+    ("JUMPDEST-bit channel segment", 70, 11, 1), ("JUMPDEST-bit channel address", 71, 11, 1), ("JUMPDEST-bit channel used in kernel mode", 67, 11, 1),
+    ("new top not read after the jump", 41, 12, -1), ("stack_len after JUMPI", 3, 12, 1), ("JUMPI gas", 5, 12, -2)])
+def test_cpu_program_corruptions_of_jump_rows_are_rejected(oracle, what, col, row, delta):
+    """(the `used` flag and address of the channel JUMPI reads its condition through are not constrained in this table by the reference
+    either — stack.rs defines JUMPI_OP but STACK_BEHAVIORS.jumps is None and jumps.rs only disables the channel for JUMP — so clearing
+    that flag is deliberately not among the cases)"""
+    tr = traces.cpu_program_trace(6, PROGRAM5)
+    assert tr[14, 11] == 1 and tr[24, 11] == 1          # row 11 is the JUMPI
     tr[col, row] = np.uint64((int(tr[col, row]) + delta) % traces.P)
     bg = BG2[:2]
     proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)

@@ -99,10 +99,12 @@ def cpu_padding_trace(log_n, halt_final=0x1234):
 
 
 def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
-    """CpuStark trace with ACTIVE rows: a straight-line kernel-mode program that runs into `halt_final`, then the padding rows.
+    """CpuStark trace with ACTIVE rows: a kernel-mode program that runs into `halt_final`, then the padding rows.
     program: string of  J JUMPDEST 0x5b | P PC 0x58 | 0 PUSH0 0x5f | N NOT 0x19 | X POP 0x50 | Z ISZERO 0x15 | E EQ 0x14 | A ADD 0x01 |
     M MUL 0x02 | S SUB 0x03 | D DIV 0x04 | O MOD 0x06 | L LT 0x10 | G GT 0x11 | B BYTE 0x1a | & AND 0x16 | "|" OR 0x17 | ^ XOR 0x18 |
-    a ADDMOD 0x08 | m MULMOD 0x09 | u v w q DUP1 DUP2 DUP3 DUP16 | s t y SWAP1 SWAP2 SWAP16.
+    a ADDMOD 0x08 | m MULMOD 0x09 | u v w q DUP1 DUP2 DUP3 DUP16 | s t y SWAP1 SWAP2 SWAP16 | j JUMP 0x56 | i JUMPI 0x57.
+    The string is the CODE (instruction c at address halt_final - len + c); execution starts at its first instruction and follows the
+    jumps until it reaches halt_final (jump targets are built on the stack from PC values, e.g. "PPS" pushes 1).
     The stack starts empty; the model keeps the 256-bit words so that the cached top (mem_channels[0]), the second-operand reads
     (mem_channels[1]), the partial-channel write of the old top and the new-top read after POP carry consistent values.
     Exercises decode.rs, control_flow.rs, gas.rs, clock.rs, stack.rs (every StackBehavior shape: push, no-op, unary, binary, pop with and
@@ -117,11 +119,12 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
     t[4] = 1                                           # is_kernel_mode
     t[40] = np.arange(1, n + 1, dtype=np.uint64)       # clock
     opcode = {"J": 0x5b, "P": 0x58, "0": 0x5f, "N": 0x19, "X": 0x50, "Z": 0x15, "E": 0x14, "A": 0x01, "M": 0x02,
-              "S": 0x03, "D": 0x04, "O": 0x06, "L": 0x10, "G": 0x11, "B": 0x1a, "&": 0x16, "|": 0x17, "^": 0x18, "a": 0x08, "m": 0x09}
+              "S": 0x03, "D": 0x04, "O": 0x06, "L": 0x10, "G": 0x11, "B": 0x1a, "&": 0x16, "|": 0x17, "^": 0x18, "a": 0x08, "m": 0x09,
+              "j": 0x56, "i": 0x57}
     flag = {"J": 13, "P": 21, "0": 21, "N": 11, "X": 11, "Z": 9, "E": 9, "A": 6, "M": 6,
-            "S": 6, "D": 6, "O": 6, "L": 6, "G": 6, "B": 6, "&": 10, "|": 10, "^": 10, "a": 7, "m": 7}
+            "S": 6, "D": 6, "O": 6, "L": 6, "G": 6, "B": 6, "&": 10, "|": 10, "^": 10, "a": 7, "m": 7, "j": 14, "i": 14}
     cost = {"J": 1, "P": 2, "0": 2, "N": 3, "X": 2, "Z": 3, "E": 3, "A": 3, "M": 5,
-            "S": 3, "D": 5, "O": 5, "L": 3, "G": 3, "B": 3, "&": 3, "|": 3, "^": 3, "a": 8, "m": 8}
+            "S": 3, "D": 5, "O": 5, "L": 3, "G": 3, "B": 3, "&": 3, "|": 3, "^": 3, "a": 8, "m": 8, "j": 8, "i": 10}
     dup, swap = {"u": 0, "v": 1, "w": 2, "q": 15}, {"s": 0, "t": 1, "y": 15}          # DUP1 / DUP2 / DUP3 / DUP16, SWAP1 / SWAP2 / SWAP16
     for c, i in dup.items():
         opcode[c], flag[c], cost[c] = 0x80 + i, 16, 3
@@ -131,9 +134,15 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
               "D": lambda a, b: a // b if b else 0, "O": lambda a, b: a % b if b else 0, "L": lambda a, b: int(a < b), "G": lambda a, b: int(a > b),
               "B": lambda a, b: (b >> (8 * (31 - a))) & 0xFF if a < 32 else 0, "&": lambda a, b: a & b, "|": lambda a, b: a | b, "^": lambda a, b: a ^ b}
     limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
-    pc, gas, stack = halt_final - k, gas0, []
-    read_top_next = False                              # the previous instruction was a POP that left a non-empty stack
-    for r, ins in enumerate(program):
+    base = halt_final - k                              # the program occupies the addresses base .. halt_final - 1
+    pc, gas, stack = base, gas0, []
+    read_top_next = False                              # the previous instruction was a POP / JUMP / JUMPI that left a non-empty stack
+    r = -1
+    while pc != halt_final:
+        r += 1
+        assert base <= pc < halt_final and r < n - 1, "the program left its code or does not halt"
+        ins = program[pc - base]
+        next_pc = pc + 1
         sl = len(stack)
         t[2, r], t[3, r], t[5, r] = pc, sl, gas
         if stack:
@@ -166,6 +175,27 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
             for i, l in enumerate(x):                  # general.logic().diff_pinv (eq_iszero.rs:25-42)
                 t[32 + i, r] = pow(l, P - 2, P) * pow(len(nz), P - 2, P) % P if l else 0
             stack[-1] = int(stack[-1] == 0)
+        elif ins in "ji":                              # jumps.rs:67-175 JUMP(dst) = JUMPI(dst, 1); kernel mode: the JUMPDEST bit is not read
+            npop = 1 if ins == "j" else 2
+            assert sl >= npop
+            dst = stack.pop()
+            if ins == "j":
+                cond = 1
+                t[59, r] = 1                           # mem_channels[1].value = 1 with the channel unused
+            else:
+                cond = stack.pop()
+                t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2
+                t[59:67, r] = limbs(cond)
+            csum = sum(limbs(cond)) % P
+            t[32, r], t[33, r] = int(cond != 0), (pow(csum, P - 2, P) if csum else 0)          # general.jumps(): should_jump, cond_sum_pinv
+            aux = int(sl != npop)
+            t[36, r], t[37, r] = (pow(sl - npop, P - 2, P) if aux else 0), aux                 # general.stack(): stack_inv, stack_inv_aux
+            t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 0, 1, 0, 14, dst & 0xFFFFFFFF   # JUMPDEST-bit channel: unused in kernel mode
+            t[72, r] = 1
+            read_top_next = bool(aux)
+            if cond:
+                assert dst < (1 << 32)
+                next_pc = dst
         elif ins in dup:                               # dup_swap.rs:112-141: the top goes to memory (channel 1), element n is read (channel 2)
             i = dup[ins]
             assert sl > i
@@ -204,8 +234,8 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
             else:
                 stack.append(binary[ins](a, b))
         gas += cost[ins]
-        pc += 1
-    assert pc == halt_final
+        pc = next_pc
+    k = r + 1                                          # executed rows
     t[2, k:], t[3, k:], t[5, k:] = halt_final, len(stack), gas
     if stack:
         for l, v in enumerate(limbs(stack[-1])):
