@@ -228,10 +228,12 @@ def test_valid_arithmetic_modular_trace_verifies_and_corruptions_are_rejected(or
 @pytest.mark.parametrize("program", ["J", "P", "0", "JP0PJ00PPJ", "PN", "PX", "PPXJ", "PZ", "0Z", "PPE", "P0E", "PPA", "PPM", "PPNEZ0PAXNJPPPMXXXJ",
                                      "PPPa", "PPPm", "PPPPPPPPSDOLGPPB&|^PPaPPmXJ",
                                      "Pu", "PPv", "PPs", "PPPt", "P" * 17 + "qyJ", "PPPuvwstNXJ",
-                                     "PPSuAuAPAjNJ", "0PPSuAuAPAjNJ", "0PPSuAuAPAiJJ", "PPPSuAuAPAiNJ", "00PPSuAuAPAiJJ", "0PPPSuAuAPAiNJ"])
+                                     "PPSuAuAPAjNJ", "0PPSuAuAPAjNJ", "0PPSuAuAPAiJJ", "PPPSuAuAPAiNJ", "00PPSuAuAPAiJJ", "0PPPSuAuAPAiNJ",
+                                     "I", "IIf", "IIg", "IIh", "IIK", "IIE", "INZ", "IIIIAm", "IIIfNKXJ"])
 def test_cpu_program_rows_verify(oracle, program):
     """a straight-line kernel program (JUMPDEST, PC, PUSH0, NOT, POP, ISZERO, EQ, the eight binary arithmetic instructions, AND / OR / XOR,
-    ADDMOD, MULMOD, DUP1/2/3/16, SWAP1/2/16, JUMP and JUMPI taken and not taken — the destinations are computed on the stack from PC values)
+    ADDMOD, MULMOD, DUP1/2/3/16, SWAP1/2/16, JUMP and JUMPI taken and not taken — the destinations are computed on the stack from PC values —, the FP254 operations, KECCAK_GENERAL,
+    PROVER_INPUT pushing random 256-bit words)
     running into halt_final: decode, control flow,
     gas, clock, every StackBehavior shape (cached top, partial-channel write of the old top, second-operand and new-top reads, stack_inv*),
     pc.rs, push0.rs, simple_logic/{not,eq_iszero}.rs, halt.rs with operation flags set"""
@@ -315,6 +317,17 @@ def test_cpu_program_corruptions_of_jump_rows_are_rejected(oracle, what, col, ro
     that flag is deliberately not among the cases)"""
     tr = traces.cpu_program_trace(6, PROGRAM5)
     assert tr[14, 11] == 1 and tr[24, 11] == 1          # row 11 is the JUMPI
+    tr[col, row] = np.uint64((int(tr[col, row]) + delta) % traces.P)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what
+
+
+@pytest.mark.parametrize("what,col,row,delta", [
+    ("FP254 modulus limb", 72 + 2, 3, 1), ("FP254 operation charged gas", 5, 4, 1), ("PROVER_INPUT charged gas", 5, 1, 3),
+    ("KECCAK_GENERAL stack_len", 3, 6, 1), ("NOT of a random word", 46 + 5, 5, 1), ("PROVER_INPUT old top not written", 80, 1, -1)])
+def test_cpu_program_corruptions_of_kernel_only_rows_are_rejected(oracle, what, col, row, delta):
+    tr = traces.cpu_program_trace(6, "IIIfNKXJ")      # rows 0-2 I, 3 f ADDFP254, 4 N, 5 K, 6 X, 7 J
     tr[col, row] = np.uint64((int(tr[col, row]) + delta) % traces.P)
     bg = BG2[:2]
     proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
