@@ -332,3 +332,34 @@ def test_cpu_program_corruptions_of_kernel_only_rows_are_rejected(oracle, what, 
     bg = BG2[:2]
     proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
     assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what
+
+
+def _addr(ctx, seg, virt):
+    return virt | (seg << 32) | (ctx << 64)
+
+
+MEMIO_PROGRAM, MEMIO_INPUTS = "IIIIrlXJ", [_addr(9, 9, 9), 1, _addr(2, 5, 77), 123]      # rows 0-3 I, 4 r MSTORE_GENERAL, 5 l MLOAD_GENERAL, 6 X, 7 J
+
+
+@pytest.mark.parametrize("program,inputs", [("Il", [_addr(3, 7, 100)]), ("IIl", [5, _addr(0, 2, 9)]), ("IIIl", [5, 6, _addr(1, 1, 0)]),
+                                            ("IIr", [_addr(2, 5, 77), 123]), ("IIIrJ", [9, _addr(2, 5, 77), 123]), (MEMIO_PROGRAM, MEMIO_INPUTS)])
+def test_cpu_memio_rows_verify(oracle, program, inputs):
+    """MLOAD_GENERAL / MSTORE_GENERAL (memio.rs): the address word's limbs drive the load channel / the partial store channel"""
+    tr = traces.cpu_program_trace(6, program, inputs=inputs)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    ok, err, _ = orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)
+    assert ok, err
+
+
+@pytest.mark.parametrize("what,col,row,delta", [
+    ("store segment differs from the address word", 83, 4, 1), ("store marked as a read", 81, 4, 1), ("store address word not read", 54, 4, -1),
+    ("new top not read after the store", 41, 5, -1), ("load context differs from the address word", 56, 5, 1), ("loaded word is not the new top", 46 + 1, 6, 1),
+    ("load through a second channel too", 67, 5, 1), ("stack_inv_aux_2 on a load", 38, 5, 1)])
+def test_cpu_memio_corruptions_are_rejected(oracle, what, col, row, delta):
+    tr = traces.cpu_program_trace(6, MEMIO_PROGRAM, inputs=MEMIO_INPUTS)
+    assert tr[20, 4] == 1 and tr[20, 5] == 1 and tr[24, 5] == 1
+    tr[col, row] = np.uint64((int(tr[col, row]) + delta) % traces.P)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what

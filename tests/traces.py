@@ -98,12 +98,13 @@ def cpu_padding_trace(log_n, halt_final=0x1234):
     return t
 
 
-def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
+def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs=()):
     """CpuStark trace with ACTIVE rows: a kernel-mode program that runs into `halt_final`, then the padding rows.
     program: string of  J JUMPDEST 0x5b | P PC 0x58 | 0 PUSH0 0x5f | N NOT 0x19 | X POP 0x50 | Z ISZERO 0x15 | E EQ 0x14 | A ADD 0x01 |
     M MUL 0x02 | S SUB 0x03 | D DIV 0x04 | O MOD 0x06 | L LT 0x10 | G GT 0x11 | B BYTE 0x1a | & AND 0x16 | "|" OR 0x17 | ^ XOR 0x18 |
     a ADDMOD 0x08 | m MULMOD 0x09 | u v w q DUP1 DUP2 DUP3 DUP16 | s t y SWAP1 SWAP2 SWAP16 | j JUMP 0x56 | i JUMPI 0x57 |
-    f g h ADDFP254 MULFP254 SUBFP254 0x0c-0x0e | K KECCAK_GENERAL 0x21 | I PROVER_INPUT 0xee (a random word).
+    f g h ADDFP254 MULFP254 SUBFP254 0x0c-0x0e | K KECCAK_GENERAL 0x21 | I PROVER_INPUT 0xee (the next word of `inputs`,
+    else a random word) | l MLOAD_GENERAL 0xfb | r MSTORE_GENERAL 0xfc (address word = virtual | segment << 32 | context << 64).
     The string is the CODE (instruction c at address halt_final - len + c); execution starts at its first instruction and follows the
     jumps until it reaches halt_final (jump targets are built on the stack from PC values, e.g. "PPS" pushes 1).
     The stack starts empty; the model keeps the 256-bit words so that the cached top (mem_channels[0]), the second-operand reads
@@ -131,7 +132,7 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
         opcode[c], flag[c], cost[c] = 0x80 + i, 16, 3
     for c, i in swap.items():
         opcode[c], flag[c], cost[c] = 0x90 + i, 16, 3
-    for c, (oc, fl) in {"f": (0x0c, 8), "g": (0x0d, 8), "h": (0x0e, 8), "K": (0x21, 13), "I": (0xee, 15)}.items():   # kernel-only: no gas
+    for c, (oc, fl) in {"f": (0x0c, 8), "g": (0x0d, 8), "h": (0x0e, 8), "K": (0x21, 13), "I": (0xee, 15), "l": (0xfb, 20), "r": (0xfc, 20)}.items():   # kernel-only: no gas
         opcode[c], flag[c], cost[c] = oc, fl, 0
     binary = {"f": lambda a, b: (a + b) % BN_BASE, "g": lambda a, b: (a * b) % BN_BASE, "h": lambda a, b: (a - b) % BN_BASE,
               "K": lambda a, b: (a * 0x9E3779B97F4A7C15 + b) & M256,         # KECCAK_GENERAL: the digest comes from the sponge table (CTL)
@@ -139,6 +140,7 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
               "D": lambda a, b: a // b if b else 0, "O": lambda a, b: a % b if b else 0, "L": lambda a, b: int(a < b), "G": lambda a, b: int(a > b),
               "B": lambda a, b: (b >> (8 * (31 - a))) & 0xFF if a < 32 else 0, "&": lambda a, b: a & b, "|": lambda a, b: a | b, "^": lambda a, b: a ^ b}
     limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+    inputs = list(inputs)                              # words PROVER_INPUT supplies, in order (random words once exhausted)
     base = halt_final - k                              # the program occupies the addresses base .. halt_final - 1
     pc, gas, stack = base, gas0, []
     read_top_next = False                              # the previous instruction was a POP / JUMP / JUMPI that left a non-empty stack
@@ -225,11 +227,31 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0):
             t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 1, 0, 1, sl - 3
             t[72:80, r] = limbs(c)
             stack.append(0 if c == 0 else ((a + b) % c if ins == "a" else (a * b) % c))
+        elif ins == "l":                               # MLOAD_GENERAL (memio.rs:22-57): the address word on top, the loaded word replaces it
+            assert sl >= 1
+            virt, seg, ctx = limbs(stack[-1])[:3]      # get_addr (cpu_stark.rs:318-323)
+            val = int.from_bytes(np.random.default_rng(seed + 1000 + r).bytes(32), "little")
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, ctx, seg, virt
+            t[59:67, r] = limbs(val)
+            aux = int(sl != 2)                         # the stack view of every m_op_general row refers to stack_len - 2 (memio.rs:170-176)
+            t[36, r], t[37, r] = (pow((sl - 2) % P, P - 2, P) if aux else 0), aux
+            stack[-1] = val
+        elif ins == "r":                               # MSTORE_GENERAL (memio.rs:137-200): value on top, address word below it
+            assert sl >= 2
+            stack.pop()
+            addr = stack.pop()
+            virt, seg, ctx = limbs(addr)[:3]
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2
+            t[59:67, r] = limbs(addr)
+            t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, ctx, seg, virt       # the store goes through the partial channel
+            aux = int(sl != 2)
+            t[36, r], t[37, r], t[38, r] = (pow(sl - 2, P - 2, P) if aux else 0), aux, aux
+            read_top_next = bool(aux)
         elif ins == "I":                               # PROVER_INPUT: pushes whatever the prover supplies (push behaviour; is_not_kernel = 0)
             if sl > 0:
                 t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, 0, 1, sl - 1
                 t[36, r], t[37, r] = pow(sl, P - 2, P), 1
-            stack.append(int.from_bytes(np.random.default_rng(seed + r).bytes(32), "little"))
+            stack.append(inputs.pop(0) if inputs else int.from_bytes(np.random.default_rng(seed + r).bytes(32), "little"))
         elif ins in "EAMSDOLGB&|^fghK":                # two operands: the second one is read through mem_channels[1]
             assert sl >= 2
             a, b = stack.pop(), stack.pop()
