@@ -363,3 +363,26 @@ def test_cpu_memio_corruptions_are_rejected(oracle, what, col, row, delta):
     bg = BG2[:2]
     proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
     assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what
+
+
+@pytest.mark.parametrize("program,inputs", [("II<", [0xABCDEF, 5]), ("II>", [1 << 200, 199]), ("II<", [7, 256]), ("II>", [7, 1 << 40]),
+                                            ("II<", [7, (1 << 255) + 3]), ("III<>XJ", [3, 1 << 100, 64])])
+def test_cpu_shift_rows_verify(oracle, program, inputs):
+    """SHL / SHR (cpu/shift.rs): 2^d read from the kernel's shift table, not read when the displacement has high limbs"""
+    tr = traces.cpu_program_trace(6, program, inputs=inputs)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    ok, err, _ = orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)
+    assert ok, err
+
+
+@pytest.mark.parametrize("what,inputs,col,delta", [
+    ("shift-table address", [7, 5], 71, 1), ("shift-table segment", [7, 5], 70, 1), ("shift table not read", [7, 5], 67, -1),
+    ("table read although the displacement has high limbs", [7, 1 << 40], 67, 1), ("high_limb_sum_inv", [7, 1 << 40], 32, 1), ("shift gas", [7, 5], 5, 1)])
+def test_cpu_shift_corruptions_are_rejected(oracle, what, inputs, col, delta):
+    tr = traces.cpu_program_trace(6, "II<J", inputs=inputs)
+    row = 3 if col == 5 else 2
+    tr[col, row] = np.uint64((int(tr[col, row]) + delta) % traces.P)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what

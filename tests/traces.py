@@ -104,7 +104,7 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
     M MUL 0x02 | S SUB 0x03 | D DIV 0x04 | O MOD 0x06 | L LT 0x10 | G GT 0x11 | B BYTE 0x1a | & AND 0x16 | "|" OR 0x17 | ^ XOR 0x18 |
     a ADDMOD 0x08 | m MULMOD 0x09 | u v w q DUP1 DUP2 DUP3 DUP16 | s t y SWAP1 SWAP2 SWAP16 | j JUMP 0x56 | i JUMPI 0x57 |
     f g h ADDFP254 MULFP254 SUBFP254 0x0c-0x0e | K KECCAK_GENERAL 0x21 | I PROVER_INPUT 0xee (the next word of `inputs`,
-    else a random word) | l MLOAD_GENERAL 0xfb | r MSTORE_GENERAL 0xfc (address word = virtual | segment << 32 | context << 64).
+    else a random word) | < SHL 0x1b | > SHR 0x1c (displacement on top) | l MLOAD_GENERAL 0xfb | r MSTORE_GENERAL 0xfc (address word = virtual | segment << 32 | context << 64).
     The string is the CODE (instruction c at address halt_final - len + c); execution starts at its first instruction and follows the
     jumps until it reaches halt_final (jump targets are built on the stack from PC values, e.g. "PPS" pushes 1).
     The stack starts empty; the model keeps the 256-bit words so that the cached top (mem_channels[0]), the second-operand reads
@@ -134,7 +134,10 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
         opcode[c], flag[c], cost[c] = 0x90 + i, 16, 3
     for c, (oc, fl) in {"f": (0x0c, 8), "g": (0x0d, 8), "h": (0x0e, 8), "K": (0x21, 13), "I": (0xee, 15), "l": (0xfb, 20), "r": (0xfc, 20)}.items():   # kernel-only: no gas
         opcode[c], flag[c], cost[c] = oc, fl, 0
-    binary = {"f": lambda a, b: (a + b) % BN_BASE, "g": lambda a, b: (a * b) % BN_BASE, "h": lambda a, b: (a - b) % BN_BASE,
+    opcode["<"], flag["<"], cost["<"] = 0x1b, 12, 3    # SHL
+    opcode[">"], flag[">"], cost[">"] = 0x1c, 12, 3    # SHR
+    binary = {"<": lambda a, b: (b << a) & M256 if a < 256 else 0, ">": lambda a, b: b >> a if a < 256 else 0,
+              "f": lambda a, b: (a + b) % BN_BASE, "g": lambda a, b: (a * b) % BN_BASE, "h": lambda a, b: (a - b) % BN_BASE,
               "K": lambda a, b: (a * 0x9E3779B97F4A7C15 + b) & M256,         # KECCAK_GENERAL: the digest comes from the sponge table (CTL)
               "A": lambda a, b: (a + b) & M256, "M": lambda a, b: (a * b) & M256, "S": lambda a, b: (a - b) & M256,
               "D": lambda a, b: a // b if b else 0, "O": lambda a, b: a % b if b else 0, "L": lambda a, b: int(a < b), "G": lambda a, b: int(a > b),
@@ -252,7 +255,7 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
                 t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, 0, 1, sl - 1
                 t[36, r], t[37, r] = pow(sl, P - 2, P), 1
             stack.append(inputs.pop(0) if inputs else int.from_bytes(np.random.default_rng(seed + r).bytes(32), "little"))
-        elif ins in "EAMSDOLGB&|^fghK":                # two operands: the second one is read through mem_channels[1]
+        elif ins in "EAMSDOLGB&|^fghK<>":              # two operands: the second one is read through mem_channels[1]
             assert sl >= 2
             a, b = stack.pop(), stack.pop()
             t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2
@@ -264,6 +267,12 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
                     t[32 + i, r] = pow(x, P - 2, P) * pow(len(nz), P - 2, P) % P if x else 0
                 stack.append(int(a == b))
             else:
+                if ins in "<>":                        # shift.rs:14-60: 2^d is read from the kernel's shift table unless d >= 2^32
+                    hi = sum(limbs(a)[1:]) % P
+                    t[32, r] = pow(hi, P - 2, P) if hi else 0                                   # general.shift().high_limb_sum_inv
+                    t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = int(hi == 0), int(hi == 0), 0, 13, a & 0xFFFFFFFF
+                    if hi == 0:
+                        t[72:80, r] = limbs((1 << a) if a < 256 else 0)
                 if ins in "fgh":                       # modfp254.rs: the BN254 prime sits where the modulus of the general operations goes
                     t[72:80, r] = limbs(BN_BASE)
                 stack.append(binary[ins](a, b))
