@@ -386,3 +386,22 @@ def test_cpu_shift_corruptions_are_rejected(oracle, what, inputs, col, delta):
     bg = BG2[:2]
     proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
     assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what
+
+
+@pytest.mark.parametrize("program", ["C", "IC", "IICZXJ"])
+def test_cpu_get_context_rows_verify(oracle, program):
+    tr = traces.cpu_program_trace(6, program)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    ok, err, _ = orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)
+    assert ok, err
+
+
+@pytest.mark.parametrize("what,col,row,delta", [("old top not written", 67, 2, -1), ("write address", 71, 2, 1), ("pushed context", 46 + 2, 3, 1),
+                                                ("stack_len after GET_CONTEXT", 3, 3, 1), ("write marked as a read", 68, 2, 1)])
+def test_cpu_get_context_corruptions_are_rejected(oracle, what, col, row, delta):
+    tr = traces.cpu_program_trace(6, "IICZXJ")          # row 2 = GET_CONTEXT (contextops.rs)
+    tr[col, row] = np.uint64((int(tr[col, row]) + delta) % traces.P)
+    bg = BG2[:2]
+    proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
+    assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what

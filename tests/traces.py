@@ -104,7 +104,7 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
     M MUL 0x02 | S SUB 0x03 | D DIV 0x04 | O MOD 0x06 | L LT 0x10 | G GT 0x11 | B BYTE 0x1a | & AND 0x16 | "|" OR 0x17 | ^ XOR 0x18 |
     a ADDMOD 0x08 | m MULMOD 0x09 | u v w q DUP1 DUP2 DUP3 DUP16 | s t y SWAP1 SWAP2 SWAP16 | j JUMP 0x56 | i JUMPI 0x57 |
     f g h ADDFP254 MULFP254 SUBFP254 0x0c-0x0e | K KECCAK_GENERAL 0x21 | I PROVER_INPUT 0xee (the next word of `inputs`,
-    else a random word) | < SHL 0x1b | > SHR 0x1c (displacement on top) | l MLOAD_GENERAL 0xfb | r MSTORE_GENERAL 0xfc (address word = virtual | segment << 32 | context << 64).
+    else a random word) | C GET_CONTEXT 0xf6 | < SHL 0x1b | > SHR 0x1c (displacement on top) | l MLOAD_GENERAL 0xfb | r MSTORE_GENERAL 0xfc (address word = virtual | segment << 32 | context << 64).
     The string is the CODE (instruction c at address halt_final - len + c); execution starts at its first instruction and follows the
     jumps until it reaches halt_final (jump targets are built on the stack from PC values, e.g. "PPS" pushes 1).
     The stack starts empty; the model keeps the 256-bit words so that the cached top (mem_channels[0]), the second-operand reads
@@ -134,6 +134,7 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
         opcode[c], flag[c], cost[c] = 0x90 + i, 16, 3
     for c, (oc, fl) in {"f": (0x0c, 8), "g": (0x0d, 8), "h": (0x0e, 8), "K": (0x21, 13), "I": (0xee, 15), "l": (0xfb, 20), "r": (0xfc, 20)}.items():   # kernel-only: no gas
         opcode[c], flag[c], cost[c] = oc, fl, 0
+    opcode["C"], flag["C"], cost["C"] = 0xf6, 17, 0    # GET_CONTEXT (kernel-only)
     opcode["<"], flag["<"], cost["<"] = 0x1b, 12, 3    # SHL
     opcode[">"], flag[">"], cost[">"] = 0x1c, 12, 3    # SHR
     binary = {"<": lambda a, b: (b << a) & M256 if a < 256 else 0, ">": lambda a, b: b >> a if a < 256 else 0,
@@ -230,6 +231,12 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
             t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 1, 0, 1, sl - 3
             t[72:80, r] = limbs(c)
             stack.append(0 if c == 0 else ((a + b) % c if ins == "a" else (a * b) % c))
+        elif ins == "C":                               # GET_CONTEXT (contextops.rs:82-102, 277-301): pushes context << 64; the old top goes out through channel 2
+            if sl > 0:
+                t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 0, 0, 1, sl - 1
+                t[72:80, r] = limbs(stack[-1])
+                t[36, r], t[37, r] = pow(sl, P - 2, P), 1
+            stack.append(0)                            # the trace runs in context 0
         elif ins == "l":                               # MLOAD_GENERAL (memio.rs:22-57): the address word on top, the loaded word replaces it
             assert sl >= 1
             virt, seg, ctx = limbs(stack[-1])[:3]      # get_addr (cpu_stark.rs:318-323)
