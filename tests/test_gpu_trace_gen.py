@@ -118,10 +118,18 @@ def test_valid_keccak_sponge_trace_on_gpu_verifies(ctx, oracle, cfg):
     assert ok, err
 
 
-@pytest.mark.parametrize("table,cfg", [(traces.T_CPU, TEST_CONFIG), (traces.T_CPU, STANDARD_FAST), (traces.T_ARITHMETIC, TEST_CONFIG)])
+@pytest.mark.parametrize("table,cfg", [(traces.T_CPU, TEST_CONFIG), (traces.T_CPU, STANDARD_FAST), (traces.T_ARITHMETIC, TEST_CONFIG),
+                                       (traces.T_ARITHMETIC + 100, TEST_CONFIG)])
 def test_valid_traces_with_active_rows_on_gpu(ctx, oracle, table, cfg):
-    """CpuStark with active instruction rows, ArithmeticStark with MUL / SHL / BYTE rows: GPU proof == oracle proof, the restated verifier accepts"""
-    tr = traces.cpu_program_trace(7, "PPNEZ0PAXNJPPPMXXXJ0PJ", halt_final=DEFAULT_LABELS[0]) if table == traces.T_CPU else traces.arithmetic_mul_trace(16, 9, nops=60)
+    """CpuStark with active instruction rows, ArithmeticStark with MUL / SHL / BYTE rows and with the two-row modular / division
+    operations: GPU proof == oracle proof, the restated verifier accepts"""
+    if table == traces.T_CPU:
+        program, inputs = traces.cpu_demo_program()          # 72 executed rows: every instruction family cpu_program_trace knows
+        tr = traces.cpu_program_trace(7, program, halt_final=DEFAULT_LABELS[0], inputs=inputs)
+    elif table == traces.T_ARITHMETIC:
+        tr = traces.arithmetic_mul_trace(16, 9, nops=60)
+    else:                                                     # the two-row operations: ADDMOD ... DIV, MOD, SHR
+        table, tr = traces.T_ARITHMETIC, traces.arithmetic_modular_trace(16, 9, nops=30)
     c = zk.StarkConfig(*cfg)
     bg = np.array([11, 22, 33, 44], dtype=np.uint64)[:2 * cfg[1]]
     st0 = np.arange(12, dtype=np.uint64)

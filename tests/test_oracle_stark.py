@@ -405,3 +405,16 @@ def test_cpu_get_context_corruptions_are_rejected(oracle, what, col, row, delta)
     bg = BG2[:2]
     proof, _ = orc_prove_table(oracle, traces.T_CPU, TEST_CONFIG, tr, bg, STATE0)
     assert not orc_verify_table(oracle, traces.T_CPU, TEST_CONFIG, proof, bg, STATE0)[0], what
+
+
+@pytest.mark.parametrize("cfg", [TEST_CONFIG, STANDARD_FAST])
+def test_cpu_demo_program_verifies(oracle, cfg):
+    """72 executed rows mixing every instruction family cpu_program_trace knows (the GPU parity test proves the same trace)"""
+    program, inputs = traces.cpu_demo_program()
+    tr = traces.cpu_program_trace(7, program, inputs=inputs)
+    assert int((tr[6:24].sum(axis=0) > 0).sum()) == 72
+    bg = BG2[:2 * cfg[1]]
+    proof, st = orc_prove_table(oracle, traces.T_CPU, cfg, tr, bg, STATE0)
+    ok, err, st2 = orc_verify_table(oracle, traces.T_CPU, cfg, proof, bg, STATE0)
+    assert ok, err
+    assert np.array_equal(st, st2)

@@ -295,6 +295,19 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
     return t
 
 
+def cpu_demo_program():
+    """a longer mix of every instruction cpu_program_trace knows -> (program, inputs)"""
+    A = lambda c, sg, v: v | (sg << 32) | (c << 64)
+    program = ("0PPPSuAuAPAiNJ"            # JUMPI taken over the N, [0] stays
+               "X" "IIIIrlXJ" "X"          # MSTORE_GENERAL, MLOAD_GENERAL
+               "II<I>" "C" "Z" "&"         # SHL, SHR, GET_CONTEXT, ISZERO, AND
+               "IIfIgIh" "IK"              # FP254 operations, KECCAK_GENERAL
+               "PPvwstuE|^" "IIIam"        # DUP / SWAP, EQ, OR, XOR, ADDMOD, MULMOD
+               "IDIOILIGIBISIM" "NXJ")     # DIV MOD LT GT BYTE SUB MUL, NOT, POP
+    inputs = [A(9, 9, 9), 1, A(2, 5, 77), 123, 0xABCDEF, 5, 3]
+    return program, inputs
+
+
 # ---- KeccakStark (keccak_stark.rs:70-250) ---------------------------------------------------------------------------------
 KECCAK_RC = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B,
              0x0000000080000001, 0x8000000080008081, 0x8000000000008009, 0x000000000000008A, 0x0000000000000088,
