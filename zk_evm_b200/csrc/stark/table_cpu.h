@@ -25,7 +25,8 @@ enum : uint32_t {
     PARTIAL_CHANNEL = 80,
     NUM_COLUMNS = 85
 };
-static const uint32_t NUM_GP_CHANNELS = 3, NUM_CHANNELS = 4, VALUE_LIMBS = 8, CHANNEL_WIDTH = 13;
+// NUM_CHANNELS = channel_indices::GP.end + 1 (membus.rs:11-39): the code channel, the three general-purpose channels and the partial channel
+static const uint32_t NUM_GP_CHANNELS = 3, NUM_CHANNELS = 5, VALUE_LIMBS = 8, CHANNEL_WIDTH = 13;
 // general-column views (columns/general.rs)
 enum : uint32_t {
     G_EXC_CODE_BITS = GENERAL,          // exception: 3
