@@ -142,6 +142,22 @@ def test_valid_traces_with_active_rows_on_gpu(ctx, oracle, table, cfg):
     assert ok, err
 
 
+@pytest.mark.parametrize("cfg", [TEST_CONFIG, STANDARD_FAST])
+def test_valid_cpu_segment_on_gpu_matches_oracle_and_verifies(ctx, oracle, cfg):
+    """the valid multi-table segment around an executing Cpu program (tests/traces.py cpu_segment: Cpu -> Memory / Arithmetic / Logic
+    lookups, MemBefore / MemAfter): GPU proofs == oracle proofs, verify_proof incl. the cross-table-lookup sums accepts"""
+    from tests.oracle_lib import orc_verify_segment
+    tr, labels = traces.cpu_segment(traces.CPU_SEGMENT_PROGRAM)
+    ap = zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, zk.StarkConfig(*cfg), zk.KernelLabels(*labels))
+    want, bg, caps = orc_prove_segment(oracle, cfg, tr, PUBLIC_VALUES, labels=labels)
+    assert np.array_equal(ap.ctl_challenges, bg) and np.array_equal(ap.trace_caps, caps)
+    for t in range(9):
+        assert (ap.stark_proofs[t] is None) == (want[t] is None)
+        assert want[t] is None or np.array_equal(ap.stark_proofs[t], want[t]), "table %s proof differs" % zk.TABLE_NAMES[t]
+    ok, err = orc_verify_segment(oracle, cfg, ap.stark_proofs, PUBLIC_VALUES, labels=labels)
+    assert ok, err
+
+
 def test_segment_from_device_finished_keccak_and_logic_traces(ctx, oracle):
     rng = np.random.default_rng(9)
     inputs = rng.integers(0, 1 << 64, size=(5, 25), dtype=np.uint64)
