@@ -288,6 +288,8 @@ int orc_verify_segment(const uint32_t cfgw[8], const uint64_t* proofs, const siz
             if (in_use[t]) zs[t] = ps[t].ctl_zs_first;
             else zs[t].assign(aux_shape(t, ctls, cfg.num_challenges, zkstark::CONSTRAINT_DEGREE).ctl_entries.size(), 0);   // verifier.rs:283-293
         }
+        std::vector<size_t> failed;          // every failing lookup is reported (the reference stops at the first one): tests of partial instances
+        std::string first_msg;
         for (size_t ci = 0; ci < ctls.size(); ci++) {
             std::vector<uint32_t> lookers;
             for (auto& l : ctls[ci].looking_tables) { bool seen = false; for (uint32_t x : lookers) seen |= x == l.table; if (!seen) lookers.push_back(l.table); }
@@ -297,8 +299,16 @@ int orc_verify_segment(const uint32_t cfgw[8], const uint64_t* proofs, const siz
                 uint32_t lt = ctls[ci].looked_table.table;
                 if (pos[lt] >= zs[lt].size()) throw std::runtime_error("ctl_zs_first too short");
                 uint64_t looked = zs[lt][pos[lt]++];
-                if (sum != looked) { g_orc_err = "Cross-table lookup " + std::to_string(ci) + " verification failed (challenge " + std::to_string(c) + ")"; return 0; }
+                if (sum != looked) {
+                    if (failed.empty()) first_msg = "Cross-table lookup " + std::to_string(ci) + " verification failed (challenge " + std::to_string(c) + ")";
+                    if (failed.empty() || failed.back() != ci) failed.push_back(ci);
+                }
             }
+        }
+        if (!failed.empty()) {
+            g_orc_err = first_msg + "; failing lookups:";
+            for (size_t ci : failed) g_orc_err += " " + std::to_string(ci);
+            return 0;
         }
         for (uint32_t t = 0; t < 9; t++) if (pos[t] != zs[t].size()) throw std::runtime_error("unused ctl_zs_first entries");
         g_orc_err.clear();

@@ -449,3 +449,21 @@ def test_cpu_segment_with_four_channel_timestamps_is_rejected(oracle):
     """the check that found the NUM_CHANNELS transcription error: memory timestamps computed with 4 channels do not match the lookups"""
     ok, err = _segment_verifies(oracle, "PPMXJ", num_channels=4)
     assert not ok and "lookup 6" in err
+
+
+def test_keccak_sponge_lookups_into_keccak_logic_and_memory_balance(oracle):
+    """KeccakSponge operations next to the executing Cpu program: the sponge rows' permutations are found in the Keccak table (lookups 3 and
+    4: inputs and outputs), their xors in the Logic table (5), their input bytes in Memory (6).  No Cpu row asked for these operations
+    (a KECCAK_GENERAL row needs PROVER_INPUT pushes, which look up Arithmetic range-check rows this generator does not build), so lookup 2
+    (Cpu -> KeccakSponge) is the ONLY one that does not balance — the oracle's verifier lists every failing lookup."""
+    rng = np.random.default_rng(3)
+    sponge_ops = [(1, 0, 10, 7, rng.bytes(5)), (1, 0, 40, 9, rng.bytes(140)), (1, 0, 200, 11, b"")]
+    tr, labels = traces.cpu_segment("PPMXJ", sponge_ops=sponge_ops, log_mem=10)
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    assert not ok and err.endswith("failing lookups: 2"), err
+    # and the lookups do depend on the sponge's data: another timestamp in the Keccak table unbalances 3 and 4 as well
+    tr[traces.T_KECCAK][24, :24] += np.uint64(1)
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    assert not ok and err.endswith("failing lookups: 2 3 4"), err

@@ -864,7 +864,7 @@ def valid_segment(seed=0, log_cpu=6, log_mem=6, log_memcont=7, k=40, halt_final=
     return tr
 
 
-def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=0, k_before=6, num_channels=5):
+def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=0, k_before=6, num_channels=5, sponge_ops=None):
     """A VALID multi-table segment around an executing Cpu program (no PROVER_INPUT, shifts, general memory or Keccak instructions: their
     lookups need more tables): Cpu (cpu_program_trace), Arithmetic (a row pair / row per MUL, DIV, MOD, ADDMOD, MULMOD executed), Logic (a row
     per AND / OR / XOR), Memory (every memory operation the Cpu rows send: the opcode fetch of every cycle, the general-purpose channels,
@@ -893,6 +893,29 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
                 ops.append((row[o + 2], row[o + 3], row[o + 4], ts(1 + c), row[o + 1], 1, row[o + 5:o + 13]))
         if row[80]:
             ops.append((row[82], row[83], row[84], ts(4), row[81], 1, row[46:54]))          # partial channel: the value of mem_channels[0]
+    logic_ops = []
+    sponge = keccak = None
+    if sponge_ops:
+        # KeccakSponge operations that no Cpu row asked for (lookup 2, Cpu -> KeccakSponge, stays unbalanced): the sponge rows send
+        # their permutations to the Keccak table (lookups 3, 4), their xors to the Logic table (5), their input bytes to Memory (6)
+        sponge, _ = keccak_sponge_trace(8, sponge_ops)
+        nrows = sum(len(o[4]) // 136 + 1 for o in sponge_ops)
+        lanes, stamps = [], []
+        for i in range(nrows):
+            row = [int(v) for v in sponge[:, i]]
+            st32 = row[328:362] + row[176:192]                                              # xored rate ++ original capacity
+            lanes.append([st32[2 * w] | (st32[2 * w + 1] << 32) for w in range(25)])
+            stamps.append(row[4])
+            block32 = [int.from_bytes(bytes(row[192 + 4 * w:196 + 4 * w]), "little") for w in range(34)]
+            for c in range(5):                                                              # num_logic_ctls (keccak_sponge_stark.rs:137-186)
+                in0 = (row[142:176] + [0] * 6)[8 * c:8 * c + 8]
+                in1 = (block32 + [0] * 6)[8 * c:8 * c + 8]
+                pack = lambda w: [w[2 * l] | (w[2 * l + 1] << 32) for l in range(4)]
+                logic_ops.append([2] + pack(in0) + pack(in1))
+            nread = 136 if row[0] else row[6:142].index(1)                                  # full block, or the input bytes of the final block
+            for b in range(nread):
+                ops.append((row[1], row[2], row[3] + row[5] + b, row[4], 1, 1, [row[192 + b]] + [0] * 7))   # ctl_looking_memory(b), :106-134
+        keccak, _ = keccak_trace(max(5, (24 * nrows - 1).bit_length()), np.array(lanes, dtype=np.uint64), np.array(stamps, dtype=np.uint64))
     before_addrs = [(0, 5, 100 + i) for i in range(k_before)]
     before_vals = rng.integers(1, 1 << 32, size=(k_before, 8), dtype=np.uint64)
     for a, v in zip(before_addrs, before_vals):
@@ -916,7 +939,6 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
     arith = np.zeros((116, 1 << 16), dtype=np.uint64)
     r = 0
     names = {"D": "div", "O": "mod", "a": "addmod", "m": "mulmod"}
-    logic_ops = []
     for e in log:
         if e[0] == "M":
             out, lo, hi = arithmetic_mul_rows(e[1], e[2])
@@ -953,9 +975,10 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
     tr = [None] * 9
     tr[T_ARITHMETIC], tr[T_CPU], tr[T_MEMORY] = arith, cpu, memory
     if logic_ops:
-        tr[T_LOGIC] = logic_trace_from_ops(log_logic, np.array(logic_ops, dtype=np.uint64))
+        tr[T_LOGIC] = logic_trace_from_ops(max(log_logic, (len(logic_ops) - 1).bit_length()), np.array(logic_ops, dtype=np.uint64))
+    tr[T_KECCAK_SPONGE], tr[T_KECCAK] = sponge, keccak
     tr[T_MEM_BEFORE] = memcont_trace_from(log_memcont, before_addrs, before_vals)
-    tr[T_MEM_AFTER] = memcont_trace_from(log_memcont, after, after_vals)
+    tr[T_MEM_AFTER] = memcont_trace_from(max(log_memcont, (len(after) - 1).bit_length()), after, after_vals)
     return tr, labels
 
 
