@@ -467,3 +467,14 @@ def test_keccak_sponge_lookups_into_keccak_logic_and_memory_balance(oracle):
     proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=labels)
     ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
     assert not ok and err.endswith("failing lookups: 2 3 4"), err
+
+
+def test_byte_packing_lookups_into_memory_balance(oracle):
+    """BytePacking operations (three unpacking writes, one packing read of a pre-initialised segment) next to the executing Cpu program:
+    their bytes are found in Memory at virt + len - 1 - i (lookup 6); only Cpu -> BytePacking (1), which nobody asked for, stays open"""
+    rng = np.random.default_rng(4)
+    packing_ops = [(0, 2, 3, 0, 5, rng.bytes(32)), (0, 2, 3, 40, 6, rng.bytes(1)), (1, 2, 0, 10, 7, rng.bytes(17)), (0, 2, 3, 80, 9, rng.bytes(5))]
+    tr, labels = traces.cpu_segment("PPMXJ", packing_ops=packing_ops, log_mem=10)
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    assert not ok and err.endswith("failing lookups: 1"), err

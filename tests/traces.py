@@ -864,7 +864,7 @@ def valid_segment(seed=0, log_cpu=6, log_mem=6, log_memcont=7, k=40, halt_final=
     return tr
 
 
-def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=0, k_before=6, num_channels=5, sponge_ops=None):
+def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=0, k_before=6, num_channels=5, sponge_ops=None, packing_ops=None):
     """A VALID multi-table segment around an executing Cpu program (no PROVER_INPUT, shifts, general memory or Keccak instructions: their
     lookups need more tables): Cpu (cpu_program_trace), Arithmetic (a row pair / row per MUL, DIV, MOD, ADDMOD, MULMOD executed), Logic (a row
     per AND / OR / XOR), Memory (every memory operation the Cpu rows send: the opcode fetch of every cycle, the general-purpose channels,
@@ -916,6 +916,21 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
             for b in range(nread):
                 ops.append((row[1], row[2], row[3] + row[5] + b, row[4], 1, 1, [row[192 + b]] + [0] * 7))   # ctl_looking_memory(b), :106-134
         keccak, _ = keccak_trace(max(5, (24 * nrows - 1).bit_length()), np.array(lanes, dtype=np.uint64), np.array(stamps, dtype=np.uint64))
+    packing = None
+    if packing_ops:
+        # BytePacking operations nobody asked for either (lookup 1, Cpu -> BytePacking, stays unbalanced): byte i of a sequence of length L
+        # lives at virt + L - 1 - i (byte_packing_stark.rs:105-148)
+        packing = np.zeros((71, 256), dtype=np.uint64)
+        for j, (is_read, ctx, seg, virt, t_, data) in enumerate(packing_ops):
+            L = len(data)
+            assert 1 <= L <= 32
+            packing[0, j], packing[L, j] = is_read, 1                                        # is_read, index_len[L - 1]
+            packing[33:37, j] = [ctx, seg, virt, t_]
+            packing[37:37 + L, j] = list(data)
+            for i in range(L):
+                ops.append((ctx, seg, virt + L - 1 - i, t_, is_read, 1, [data[i]] + [0] * 7))
+        packing[69] = np.minimum(np.arange(256), 255).astype(np.uint64)
+        packing[70, :256] = np.bincount(packing[37:69].astype(np.int64).ravel(), minlength=256).astype(np.uint64)
     before_addrs = [(0, 5, 100 + i) for i in range(k_before)]
     before_vals = rng.integers(1, 1 << 32, size=(k_before, 8), dtype=np.uint64)
     for a, v in zip(before_addrs, before_vals):
@@ -976,7 +991,7 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
     tr[T_ARITHMETIC], tr[T_CPU], tr[T_MEMORY] = arith, cpu, memory
     if logic_ops:
         tr[T_LOGIC] = logic_trace_from_ops(max(log_logic, (len(logic_ops) - 1).bit_length()), np.array(logic_ops, dtype=np.uint64))
-    tr[T_KECCAK_SPONGE], tr[T_KECCAK] = sponge, keccak
+    tr[T_KECCAK_SPONGE], tr[T_KECCAK], tr[T_BYTE_PACKING] = sponge, keccak, packing
     tr[T_MEM_BEFORE] = memcont_trace_from(log_memcont, before_addrs, before_vals)
     tr[T_MEM_AFTER] = memcont_trace_from(max(log_memcont, (len(after) - 1).bit_length()), after, after_vals)
     return tr, labels
