@@ -430,7 +430,7 @@ def _segment_verifies(oracle, program, cfg=TEST_CONFIG, **kw):
     return orc_verify_segment(oracle, cfg, proofs, PV37, labels=labels)
 
 
-@pytest.mark.parametrize("program", ["PP|PP^PPaXXXJ", "0PPPSuAuAPAiNJ"])       # (each case proves a 2^16-row Arithmetic table)
+@pytest.mark.parametrize("program", ["PP|PP^PPaXXJ", "0PPPSuAuAPAiNJ"])       # (each case proves a 2^16-row Arithmetic table)
 def test_cpu_segment_cross_table_lookups_verify(oracle, program):
     """every memory operation the Cpu rows send (opcode fetch, general-purpose channels, partial channel; timestamps clock * 5 + channel - 4)
     is found by the Memory table, every arithmetic / logic instruction by the Arithmetic / Logic tables, MemBefore / MemAfter close the
