@@ -478,3 +478,21 @@ def test_byte_packing_lookups_into_memory_balance(oracle):
     proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=labels)
     ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
     assert not ok and err.endswith("failing lookups: 1"), err
+
+
+def test_cpu_segment_with_keccak_general_and_prover_input_verifies(oracle):
+    """eight tables in use: the program pushes (length, address) pairs with PROVER_INPUT (range-checked by Arithmetic rows, IS_RANGE_CHECK)
+    and hashes two memory ranges with KECCAK_GENERAL; the KeccakSponge table holds exactly the operations the Cpu rows ask for (timestamp
+    (clock - 1) * 5 + 1, digest as the pushed word), Keccak their permutations, Logic their xors, Memory their byte reads: all ten lookups
+    balance, incl. Cpu -> KeccakSponge (2), which the hand-placed sponge operations of the test above leave open"""
+    rng = np.random.default_rng(5)
+    addr = lambda c, sg, v: v | (sg << 32) | (c << 64)
+    data = {(1, 0, 10): rng.bytes(150), (1, 0, 300): b"abc"}
+    tr, labels = traces.cpu_segment("IIKIIKXXJ", inputs=[150, addr(1, 0, 10), 3, addr(1, 0, 300)], keccak_inputs=data, log_mem=10)
+    assert [t is not None for t in tr] == [True, False, True, True, True, True, True, True, True]
+    # the second digest is keccak256("abc"), pushed as a big-endian word: row 6 holds it as the cached top of the stack
+    top = sum(int(tr[traces.T_CPU][46 + l, 6]) << (32 * l) for l in range(8))
+    assert top == 0x4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    assert ok, err

@@ -98,7 +98,7 @@ def cpu_padding_trace(log_n, halt_final=0x1234):
     return t
 
 
-def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs=(), log=None):
+def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs=(), log=None, keccak=None):
     """CpuStark trace with ACTIVE rows: a kernel-mode program that runs into `halt_final`, then the padding rows.
     program: string of  J JUMPDEST 0x5b | P PC 0x58 | 0 PUSH0 0x5f | N NOT 0x19 | X POP 0x50 | Z ISZERO 0x15 | E EQ 0x14 | A ADD 0x01 |
     M MUL 0x02 | S SUB 0x03 | D DIV 0x04 | O MOD 0x06 | L LT 0x10 | G GT 0x11 | B BYTE 0x1a | & AND 0x16 | "|" OR 0x17 | ^ XOR 0x18 |
@@ -265,6 +265,8 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
                 t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, 0, 1, sl - 1
                 t[36, r], t[37, r] = pow(sl, P - 2, P), 1
             stack.append(inputs.pop(0) if inputs else int.from_bytes(np.random.default_rng(seed + r).bytes(32), "little"))
+            if log is not None:
+                log.append(("I", stack[-2] if len(stack) > 1 else 0, stack[-1]))
         elif ins in "EAMSDOLGB&|^fghK<>":              # two operands: the second one is read through mem_channels[1]
             assert sl >= 2
             a, b = stack.pop(), stack.pop()
@@ -276,6 +278,8 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
                 for i, x in enumerate(d):
                     t[32 + i, r] = pow(x, P - 2, P) * pow(len(nz), P - 2, P) % P if x else 0
                 stack.append(int(a == b))
+            elif ins == "K" and keccak is not None:    # the digest of the bytes at address word a, length b (callback: the sponge operation)
+                stack.append(keccak(a, b, r + 1))
             else:
                 if log is not None:
                     log.append((ins, a, b, binary[ins](a, b)))
@@ -864,7 +868,7 @@ def valid_segment(seed=0, log_cpu=6, log_mem=6, log_memcont=7, k=40, halt_final=
     return tr
 
 
-def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=0, k_before=6, num_channels=5, sponge_ops=None, packing_ops=None):
+def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=0, k_before=6, num_channels=5, sponge_ops=None, packing_ops=None, inputs=(), keccak_inputs=None):
     """A VALID multi-table segment around an executing Cpu program (no PROVER_INPUT, shifts, general memory or Keccak instructions: their
     lookups need more tables): Cpu (cpu_program_trace), Arithmetic (a row pair / row per MUL, DIV, MOD, ADDMOD, MULMOD executed), Logic (a row
     per AND / OR / XOR), Memory (every memory operation the Cpu rows send: the opcode fetch of every cycle, the general-purpose channels,
@@ -876,7 +880,17 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
     halt_final = len(program) + 8
     labels = (halt_final, 3, 0x4000, 0x5000)
     log = []
-    cpu = cpu_program_trace(log_cpu, program, halt_final=halt_final, log=log)
+    sponge_ops = list(sponge_ops or [])
+
+    def keccak(addr_word, length, clock):
+        # KECCAK_GENERAL (cpu_stark.rs:33-56): the Cpu row sends (context, segment, virt, len, (clock - 1) * NUM_CHANNELS + 1, digest)
+        virt, seg, ctx = [(addr_word >> (32 * i)) & 0xFFFFFFFF for i in range(3)]
+        data = keccak_inputs[(ctx, seg, virt)]
+        assert len(data) == length
+        op = (ctx, seg, virt, (clock - 1) * num_channels + 1, data)
+        sponge_ops.append(op)
+        return int.from_bytes(keccak_sponge_trace(8, [op])[1][0], "big")
+    cpu = cpu_program_trace(log_cpu, program, halt_final=halt_final, log=log, inputs=inputs, keccak=keccak if keccak_inputs is not None else None)
     limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
     NUM_CHANNELS = num_channels                     # 5 in the reference; the parameter exists for the negative test
     ops = []                                        # (ctx, seg, virt, timestamp, is_read, filter, value limbs)
@@ -960,6 +974,10 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
             arith[1, r] = 1
             arith[18:34, r], arith[34:50, r] = _limbs(e[1]), _limbs(e[2])
             arith[66:82, r], arith[82:98, r], arith[98:114, r] = out, lo, hi
+            r += 1
+        elif e[0] == "I":                              # PROVER_INPUT is range-checked by the Arithmetic table (arithmetic/mod.rs:343-359)
+            arith[16, r], arith[17, r] = 1, 0xee       # IS_RANGE_CHECK, OPCODE_COL
+            arith[18:34, r], arith[66:82, r] = _limbs(e[1]), _limbs(e[2])
             r += 1
         elif e[0] in "ASLG":                           # addcy.rs: ADD in0 + in1 = out + cy 2^256; SUB / LT / GT by rearranging it
             a, b, M = e[1], e[2], 1 << 256
