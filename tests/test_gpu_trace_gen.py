@@ -142,6 +142,24 @@ def test_valid_traces_with_active_rows_on_gpu(ctx, oracle, table, cfg):
     assert ok, err
 
 
+def test_valid_eight_table_segment_on_gpu_matches_oracle_and_verifies(ctx, oracle):
+    """PROVER_INPUT + KECCAK_GENERAL program: Arithmetic, Cpu, Keccak, KeccakSponge, Logic, Memory, MemBefore, MemAfter in use, all ten
+    lookups balanced (tests/test_oracle_stark.py::test_cpu_segment_with_keccak_general_and_prover_input_verifies)"""
+    from tests.oracle_lib import orc_verify_segment
+    rng = np.random.default_rng(5)
+    addr = lambda c, sg, v: v | (sg << 32) | (c << 64)
+    data = {(1, 0, 10): rng.bytes(150), (1, 0, 300): b"abc"}
+    tr, labels = traces.cpu_segment("IIKIIKXXJ", inputs=[150, addr(1, 0, 10), 3, addr(1, 0, 300)], keccak_inputs=data, log_mem=10)
+    ap = zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, zk.StarkConfig(*TEST_CONFIG), zk.KernelLabels(*labels))
+    want, bg, caps = orc_prove_segment(oracle, TEST_CONFIG, tr, PUBLIC_VALUES, labels=labels)
+    assert np.array_equal(ap.ctl_challenges, bg) and np.array_equal(ap.trace_caps, caps)
+    for t in range(9):
+        assert (ap.stark_proofs[t] is None) == (want[t] is None)
+        assert want[t] is None or np.array_equal(ap.stark_proofs[t], want[t]), "table %s proof differs" % zk.TABLE_NAMES[t]
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, ap.stark_proofs, PUBLIC_VALUES, labels=labels)
+    assert ok, err
+
+
 @pytest.mark.parametrize("cfg", [TEST_CONFIG, STANDARD_FAST])
 def test_valid_cpu_segment_on_gpu_matches_oracle_and_verifies(ctx, oracle, cfg):
     """the valid multi-table segment around an executing Cpu program (tests/traces.py cpu_segment: Cpu -> Memory / Arithmetic / Logic
