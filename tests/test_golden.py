@@ -30,7 +30,7 @@ def test_oracle_reproduces_golden_commit_and_ntt(oracle):
     assert fp(oracle.ntt(x, 2, oracle_lib.GENERATOR)) == OV["ntt_65536_seed1"]["coset_fft"]
 
 
-@pytest.mark.parametrize("case", TABLE_CASES[:3], ids=lambda c: c[0])
+@pytest.mark.parametrize("case", TABLE_CASES, ids=lambda c: c[0])
 def test_oracle_reproduces_golden_proofs(oracle, case):
     name, table, lg, cfgname, kind = case
     cfg = STANDARD_FAST if cfgname == "std" else TEST_CONFIG

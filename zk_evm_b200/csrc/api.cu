@@ -74,6 +74,11 @@ void Ctx::d2h(void* dst, const void* src, size_t bytes) {
 }
 double StageLog::now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 static void timing_mark(Ctx& c, const char* what) {
+    // bounded: a caller that never asks for the report does not grow the list for ever (the oldest spans are dropped)
+    if (c.timing_marks.size() >= 65536) {
+        for (size_t i = 0; i < 32768; i++) cudaEventDestroy(c.timing_marks[i].second);
+        c.timing_marks.erase(c.timing_marks.begin(), c.timing_marks.begin() + 32768);
+    }
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
     cudaEventRecord(e, c.stream);
@@ -218,6 +223,10 @@ void zkgpu_ctx_destroy(zkgpu_ctx* h) {
     h->c.ntt.roots_inv.release();
     cudaStreamSynchronize(h->c.stream);
     if (h->c.ev0) { cudaEventDestroy(h->c.ev0); cudaEventDestroy(h->c.ev1); }
+    for (auto& m : h->c.timing_marks) cudaEventDestroy(m.second);
+    h->c.timing_marks.clear();
+    for (auto& r : h->c.prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (cudaEvent_t e : h->c.prof_free_events) cudaEventDestroy(e);
     cudaStreamDestroy(h->c.stream);
     cudaStreamDestroy(h->c.copy_stream);
     if (h->c.pool) cudaMemPoolDestroy(h->c.pool);

@@ -69,6 +69,7 @@ void quotient_values(Ctx& c, const TableDev& t, const QuotientArgs& q) {
     a.prm = q.prm;
     // powers of the alphas for the index-addressed constraint blocks (2 x 1024 elements, rebuilt per proof: alpha is fresh)
     static_assert(zkstark::keccak::MIDDLE_CONSTRAINTS <= APOW_MAX, "alpha power table too short");
+    ZK_REQUIRE(t.flat.ctl_num_constraints <= APOW_MAX, "CTL constraint section longer than the alpha power table (APOW_MAX)");
     DevBuf apow(&c, 2 * (size_t)(APOW_MAX + 1) * 8);
     for (unsigned i = 0; i < 2; i++) fill_powers(c, apow.get() + i * (size_t)(APOW_MAX + 1), APOW_MAX + 1, a.alphas[i], 1);
     a.apow = apow.get();

@@ -35,9 +35,12 @@ static void segment_transcript(Challenger& ch, const uint64_t* caps /*[9][cap_le
             ZK_REQUIRE(zkstark::table_is_optional(t), "only optional tables may be left out (all_stark.rs:110-117)");
             for (size_t i = 0; i < cap_words; i++) ch.observe(0);
         } else {
+            for (size_t i = 0; i < cap_words; i++) ZK_REQUIRE(caps[(size_t)t * cap_words + i] < GL_P, "cap element is not canonical");
             ch.observe_n(caps + (size_t)t * cap_words, cap_words);
         }
     }
+    // the same rule as zkgpu_challenger_observe: a non-canonical word would give a transcript no reference verifier reproduces
+    for (size_t i = 0; i < n_public; i++) ZK_REQUIRE(public_values[i] < GL_P, "public value is not canonical");
     ch.observe_n(public_values, n_public);
     for (unsigned i = 0; i < num_challenges; i++) { beta_gamma[2 * i] = ch.challenge(); beta_gamma[2 * i + 1] = ch.challenge(); }
 }
@@ -150,6 +153,7 @@ struct zkgpu_upload {
     cudaEvent_t uploaded[ZKGPU_NUM_TABLES] = {nullptr};
     std::vector<cudaEvent_t> events;
     uint32_t rate_bits = 0, cap_height = 0;
+    bool consumed = false;                             // set by the one prove call that takes the buffers (zkgpu.h contract)
     cudaEvent_t make_event() { cudaEvent_t e; ZK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); events.push_back(e); return e; }
     ~zkgpu_upload() {
         // the copy stream is drained before the buffers it writes are freed (errors included)
@@ -214,6 +218,8 @@ static void segment_prove(Ctx& c, zkgpu_upload& u, const uint64_t* public_values
                           zkgpu_proof** proofs_out, uint64_t* ctl_challenges_out, uint64_t* trace_caps_out) {
     ZK_REQUIRE(u.ctx == &c, "the upload belongs to another context");
     ZK_REQUIRE(u.rate_bits == cfg.rate_bits && u.cap_height == cfg.cap_height, "the upload was made for another StarkConfig");
+    ZK_REQUIRE(!u.consumed, "the upload was already consumed by a prove call (its table buffers are released as the tables are proved)");
+    u.consumed = true;
     const zkstark::TableParams prm = params_from(labels);
     const size_t cap_words = (size_t)4 << cfg.cap_height;
     for (uint32_t t = 0; t < ZKGPU_NUM_TABLES; t++) proofs_out[t] = nullptr;

@@ -256,7 +256,9 @@ class TorchComm:
 
     def broadcast(self, a, src):
         t = self._t(a)
-        self.dist.broadcast(t, src=src, group=self.group)
+        # `src` is a rank of this communicator's group; torch.distributed.broadcast wants the global rank
+        gsrc = src if self.group is None else self.dist.get_global_rank(self.group, src)
+        self.dist.broadcast(t, src=gsrc, group=self.group)
         return t.cpu().numpy().view(np.uint64)
 
     def gather_proofs(self, proofs, owner):
@@ -300,9 +302,11 @@ def default_owner(world, weights=None):
 
 
 def prove_with_traces_sharded(backend, comm, traces, table_in_use, public_values, owner=None, forced_pow_witnesses=None,
-                              gather=True, cap_height=4):
+                              gather=True, cap_height=None):
     """traces[t] is needed on owner[t] only (host array or (device address, n)); table_in_use must agree on every rank."""
     owner = owner if owner is not None else default_owner(comm.world)
+    if cap_height is None:
+        cap_height = getattr(getattr(backend, "config", None), "cap_height", 4)
     cap_words = 4 << cap_height
     # phase 1: commitments of the local tables
     handles = {}

@@ -79,8 +79,9 @@ def save(path, traces, public_values, labels):
         f.truncate(off)
 
 
-def load(path, mmap=True, check_canonical=False):
-    """-> SegmentTraces; with mmap the column blocks are read-only views of the file."""
+def load(path, mmap=True, check_canonical=True):
+    """-> SegmentTraces; with mmap the column blocks are read-only views of the file.  check_canonical=False only for a trusted
+    producer: the device field forms assume every element is < p, a larger word silently changes commitments and proofs."""
     with open(path, "rb") as f:
         head = f.read(_HEAD.size)
         if len(head) < _HEAD.size:
