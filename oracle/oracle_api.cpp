@@ -209,6 +209,15 @@ extern "C" {
 
 // traces[t]: ncols(t)*n[t] column-major, or null (table not in use).  Proof words of table t are written at
 // out[offsets[t] .. offsets[t+1]) (empty for unused tables).  Returns total words (needed if > out_cap), negative on failure.
+// "stage\tseconds\n" lines accumulated since the last call with reset != 0 (main-thread wall clock of the prover's stages)
+size_t orc_stage_report(char* buf, size_t cap, int reset) {
+    std::string out;
+    for (auto& kv : StageClock::acc()) { char line[128]; snprintf(line, sizeof line, "%s\t%.4f\n", kv.first.c_str(), kv.second); out += line; }
+    if (reset) StageClock::acc().clear();
+    if (buf && cap) { size_t l = out.size() < cap - 1 ? out.size() : cap - 1; memcpy(buf, out.data(), l); buf[l] = 0; }
+    return out.size();
+}
+
 long orc_prove_segment(const uint32_t cfgw[8], const uint64_t* const* traces, const size_t* ns, const uint64_t* public_values, size_t npv,
                        const uint64_t labels[4], const uint64_t* forced_pows, uint64_t* out, size_t out_cap, size_t offsets[10],
                        uint64_t* beta_gamma_out, uint64_t* caps_out) {
@@ -226,7 +235,7 @@ long orc_prove_segment(const uint32_t cfgw[8], const uint64_t* const* traces, co
             size_t nc = zkstark::table_num_columns(t);
             cols[t].resize(nc);
             for (size_t c = 0; c < nc; c++) cols[t][c] = traces[t] + c * ns[t];
-            commits[t].from_values(cols[t].data(), nc, ns[t], cfg.rate_bits, cfg.cap_height);
+            { ORC_STAGE("trace commit"); commits[t].from_values(cols[t].data(), nc, ns[t], cfg.rate_bits, cfg.cap_height); }
             caps[t] = cap_words(commits[t].tree);
         }
         if (caps_out) for (uint32_t t = 0; t < 9; t++) memcpy(caps_out + t * capw, caps[t].data(), capw * 8);
@@ -237,7 +246,8 @@ long orc_prove_segment(const uint32_t cfgw[8], const uint64_t* const* traces, co
         std::vector<Words> proofs(9);
         for (uint32_t t = 0; t < 9; t++) {
             if (!in_use[t]) continue;
-            CtlData ctl = ctl_data_for_table(t, cols[t].data(), ns[t], ctls, betas, gammas, zkstark::CONSTRAINT_DEGREE);
+            CtlData ctl;
+            { ORC_STAGE("ctl data"); ctl = ctl_data_for_table(t, cols[t].data(), ns[t], ctls, betas, gammas, zkstark::CONSTRAINT_DEGREE); }
             StarkProofData p = prove_table(t, cfg, cols[t].data(), ns[t], commits[t], ctl, betas, gammas, ch, params_from(labels),
                                            forced_pows ? &forced_pows[t] : nullptr, ctls, nullptr);
             proofs[t] = zkstark::serialize_proof(p);

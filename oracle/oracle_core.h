@@ -20,7 +20,22 @@
 #include <stdexcept>
 #include "poseidon_constants.h"
 
+#include <map>
+#include <string>
+#include <chrono>
+#include <atomic>
+
 namespace orc {
+
+// wall-clock stage accounting of the prover (main thread only; read through orc_stage_report): where the CPU baseline spends its time
+struct StageClock {
+    static std::map<std::string, double>& acc() { static std::map<std::string, double> m; return m; }
+    static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    const char* name; double t0;
+    explicit StageClock(const char* n) : name(n), t0(now()) {}
+    ~StageClock() { acc()[name] += now() - t0; }
+};
+#define ORC_STAGE(name) orc::StageClock _stage_clock_##__LINE__(name)
 
 typedef unsigned __int128 u128;
 static const uint64_t P = 0xFFFFFFFF00000001ULL;
@@ -150,23 +165,50 @@ static inline Hash two_to_one(const Hash& l, const Hash& r) {
 // FFT (plonky2_field fft.rs semantics: natural order in, natural order out)
 // ---------------------------------------------------------------------------------------------
 static inline size_t bitrev(size_t x, unsigned bits) {
-    size_t r = 0;
-    for (unsigned i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; }
-    return r;
+    if (!bits) return 0;
+    uint64_t v = x;
+    v = ((v >> 1) & 0x5555555555555555ull) | ((v & 0x5555555555555555ull) << 1);
+    v = ((v >> 2) & 0x3333333333333333ull) | ((v & 0x3333333333333333ull) << 2);
+    v = ((v >> 4) & 0x0F0F0F0F0F0F0F0Full) | ((v & 0x0F0F0F0F0F0F0F0Full) << 4);
+    v = __builtin_bswap64(v);
+    return (size_t)(v >> (64 - bits));
 }
 // out[i] = sum_j in[j] w^(ij), w = primitive_root_of_unity(log_n)   (textbook iterative radix-2 DIT)
+// Twiddles: one table per transform size, w^j for j < n/2, built once and shared by every column and thread (the stage of
+// span m uses every (n/m)-th entry), as plonky2's fft_root_table does.
+struct FftRoots {
+    std::vector<uint64_t> w[33];
+    std::atomic<bool> ready[33];
+    FftRoots() { for (auto& r : ready) r.store(false); }
+    const uint64_t* get(unsigned log_n) {
+        if (!log_n) return nullptr;
+        if (!ready[log_n].load(std::memory_order_acquire)) {
+            #pragma omp critical(orc_fft_roots)
+            if (!ready[log_n].load(std::memory_order_relaxed)) {
+                std::vector<uint64_t> t((size_t)1 << (log_n - 1));
+                uint64_t r = gl_root_of_unity(log_n), x = 1;
+                for (auto& e : t) { e = x; x = gl_mul(x, r); }
+                w[log_n].swap(t);
+                ready[log_n].store(true, std::memory_order_release);
+            }
+        }
+        return w[log_n].data();
+    }
+};
+static inline FftRoots& fft_roots() { static FftRoots r; return r; }
 static inline void fft_inplace(uint64_t* a, unsigned log_n) {
     size_t n = (size_t)1 << log_n;
     for (size_t i = 0; i < n; i++) { size_t j = bitrev(i, log_n); if (i < j) { uint64_t t = a[i]; a[i] = a[j]; a[j] = t; } }
+    const uint64_t* tw = fft_roots().get(log_n);
     for (unsigned s = 1; s <= log_n; s++) {
-        size_t m = (size_t)1 << s, half = m >> 1;
-        uint64_t wm = gl_root_of_unity(s);
-        std::vector<uint64_t> tw(half);
-        uint64_t w = 1;
-        for (size_t j = 0; j < half; j++) { tw[j] = w; w = gl_mul(w, wm); }
+        size_t m = (size_t)1 << s, half = m >> 1, step = n >> s;
+        if (half == 1) {
+            for (size_t k = 0; k < n; k += 2) { uint64_t u = a[k], t = a[k + 1]; a[k] = gl_add(u, t); a[k + 1] = gl_sub(u, t); }
+            continue;
+        }
         for (size_t k = 0; k < n; k += m)
             for (size_t j = 0; j < half; j++) {
-                uint64_t t = gl_mul(tw[j], a[k + j + half]), u = a[k + j];
+                uint64_t t = gl_mul(tw[j * step], a[k + j + half]), u = a[k + j];
                 a[k + j] = gl_add(u, t);
                 a[k + j + half] = gl_sub(u, t);
             }

@@ -3,6 +3,7 @@
 // /root/reference/evm_arithmetization/src/prover.rs:100-107 and verifier.rs:69-76.
 // Parity unpinned (no golden vectors in the reference); validated by the restated verifier.
 #pragma once
+#include <algorithm>
 #include "oracle_core.h"
 
 namespace orc {
@@ -24,22 +25,36 @@ struct PolyBatch {
         log_n = 0; while (((size_t)1 << log_n) < n) log_n++;
         if (((size_t)1 << log_n) != n) throw std::runtime_error("n must be a power of two");
         size_t N = lde_size(); unsigned log_N = log_n + rate_bits;
+        StageClock* sc_l = new StageClock(" lde + transpose");
         std::vector<uint64_t> rows(N * ncols);
+        // columns in blocks of 8: the transposed, bit-reversed rows are then written one 64-byte line at a time
+        const size_t CB = 8, nblocks = (ncols + CB - 1) / CB;
         #pragma omp parallel
         {
-            std::vector<uint64_t> tmp(N);
+            std::vector<uint64_t> tmp(CB * N);
             #pragma omp for schedule(dynamic, 1)
-            for (size_t c = 0; c < ncols; c++) {
-                memcpy(tmp.data(), &coeffs[c * n], n * 8);
-                memset(tmp.data() + n, 0, (N - n) * 8);
-                coset_fft_inplace(tmp.data(), log_N, GL_GENERATOR);
-                for (size_t j = 0; j < N; j++) rows[j * ncols + c] = tmp[bitrev(j, log_N)];
+            for (size_t blk = 0; blk < nblocks; blk++) {
+                const size_t c0 = blk * CB, nb = std::min(CB, ncols - c0);
+                for (size_t b = 0; b < nb; b++) {
+                    uint64_t* t = tmp.data() + b * N;
+                    memcpy(t, &coeffs[(c0 + b) * n], n * 8);
+                    memset(t + n, 0, (N - n) * 8);
+                    coset_fft_inplace(t, log_N, GL_GENERATOR);
+                }
+                for (size_t j = 0; j < N; j++) {
+                    const size_t src = bitrev(j, log_N);
+                    uint64_t* dst = &rows[j * ncols + c0];
+                    for (size_t b = 0; b < nb; b++) dst[b] = tmp[b * N + src];
+                }
             }
         }
+        delete sc_l;
+        ORC_STAGE(" merkle tree");
         tree.build(std::move(rows), N, ncols, cap_height);
     }
     // from_values: per-column ifft first
     void from_values(const uint64_t* const* cols, size_t ncols_, size_t n_, unsigned rate_bits_, unsigned cap_height) {
+        StageClock* sc_i = new StageClock(" ifft");
         std::vector<uint64_t> cf(ncols_ * n_);
         unsigned lg = 0; while (((size_t)1 << lg) < n_) lg++;
         #pragma omp parallel for schedule(dynamic, 1)
@@ -47,6 +62,7 @@ struct PolyBatch {
             memcpy(&cf[c * n_], cols[c], n_ * 8);
             ifft_inplace(&cf[c * n_], lg);
         }
+        delete sc_i;
         from_coeffs(std::move(cf), ncols_, n_, rate_bits_, cap_height);
     }
     // evaluate column c at an extension point (PolynomialCoeffs::to_extension().eval)

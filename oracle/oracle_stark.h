@@ -362,6 +362,7 @@ static inline StarkProofData prove_table(uint32_t table, const Config& cfg, cons
 
     // 1. auxiliary polynomials: lookup columns, CTL helpers, CTL Zs
     std::vector<std::vector<uint64_t>> aux;
+    { ORC_STAGE("aux columns");
     for (const Lookup& l : sh.lookups)
         for (unsigned c = 0; c < cfg.num_challenges; c++) {
             auto cols = lookup_helper_columns(l, trace, n, betas[c], cd);
@@ -370,11 +371,13 @@ static inline StarkProofData prove_table(uint32_t table, const Config& cfg, cons
     if (ctl.size() != sh.ctl_entries.size()) throw std::runtime_error("ctl data does not match the table's CTL shape");
     for (auto& z : ctl) for (auto& h : z.helpers) aux.push_back(h);
     for (auto& z : ctl) aux.push_back(z.z);
+    }
     const size_t na = aux.size();
     if (na != sh.num_aux()) throw std::runtime_error("aux column count mismatch");
     if (dbg) dbg->aux_values = aux;
     PolyBatch aux_commit;
     if (na) {
+        ORC_STAGE("aux commit");
         std::vector<const uint64_t*> ptr(na);
         for (size_t i = 0; i < na; i++) ptr[i] = aux[i].data();
         aux_commit.from_values(ptr.data(), na, n, rate_bits, cfg.cap_height);
@@ -410,6 +413,7 @@ static inline StarkProofData prove_table(uint32_t table, const Config& cfg, cons
     for (auto g : gammas) gammasP.push_back(OF(g));
     std::vector<std::vector<uint64_t>> qvals(cfg.num_challenges, std::vector<uint64_t>(N));
     std::vector<uint64_t> xs(N);
+    { ORC_STAGE("quotient eval");
     { uint64_t x = GL_GENERATOR; for (size_t i = 0; i < N; i++) { xs[i] = x; x = gl_mul(x, wN); } }
     #pragma omp parallel for schedule(static)
     for (size_t i = 0; i < N; i++) {
@@ -424,8 +428,10 @@ static inline StarkProofData prove_table(uint32_t table, const Config& cfg, cons
         eval_vanishing_poly<OF>(table, sh, betasP, gammasP, lv, nv, alv, anv, yc, prm, cd);
         for (unsigned j = 0; j < cfg.num_challenges; j++) qvals[j][i] = gl_mul(yc.acc[j].v, zh_inv[i & 1]);
     }
+    }
     const size_t nq = 2 * cfg.num_challenges;
     std::vector<uint64_t> qcoeffs(nq * n);
+    StageClock* sc_q = new StageClock("quotient commit");
     for (unsigned j = 0; j < cfg.num_challenges; j++) {
         coset_ifft_inplace(qvals[j].data(), logN, GL_GENERATOR);
         memcpy(&qcoeffs[(2 * j) * n], qvals[j].data(), n * 8);
@@ -436,8 +442,10 @@ static inline StarkProofData prove_table(uint32_t table, const Config& cfg, cons
     quot_commit.from_coeffs(std::move(qcoeffs), nq, n, rate_bits, cfg.cap_height);
     proof.quotient_cap = cap_words(quot_commit.tree);
     observe_words(ch, proof.quotient_cap);
+    delete sc_q;
 
     // 4. zeta and the openings
+    StageClock* sc_o = new StageClock("openings");
     Ext zeta = ch.ext_challenge();
     if (ext_pow(zeta, n) == Ext(1, 0)) throw std::runtime_error("Opening point is in the subgroup.");
     Ext zeta_next = ext_scalar(zeta, wn);
@@ -462,7 +470,9 @@ static inline StarkProofData prove_table(uint32_t table, const Config& cfg, cons
     observe_words(ch, proof.next_values); observe_words(ch, proof.aux_polys_next);
     for (uint64_t v : proof.ctl_zs_first) { ch.observe(v); ch.observe(0); }
 
+    delete sc_o;
     // 5./6. FRI batch reduction in coefficient space (PolynomialBatch::prove_openings)
+    StageClock* sc_f = new StageClock("fri batch reduce");
     Ext alpha = ch.ext_challenge();
     struct PolyRef { const PolyBatch* b; size_t c; };
     std::vector<PolyRef> all_trace, all_aux, all_quot, zs;
@@ -479,13 +489,18 @@ static inline StarkProofData prove_table(uint32_t table, const Config& cfg, cons
     for (auto& bt : batches) {
         const Ext z = bt.first;
         const auto& polys = bt.second;
-        // composition = sum_j alpha^j f_j
-        std::vector<Ext> comp(n, Ext(0, 0));
-        Ext apow(1, 0);
-        for (auto& pr : polys) {
-            const uint64_t* cf = pr.b->col(pr.c);
-            for (size_t i = 0; i < n; i++) comp[i] = comp[i] + ext_scalar(apow, cf[i]);
-            apow = apow * alpha;
+        // composition = sum_j alpha^j f_j  (rows split over the threads; the alpha powers are tabulated first)
+        std::vector<Ext> comp(n, Ext(0, 0)), apows(polys.size());
+        { Ext apow(1, 0); for (size_t j = 0; j < polys.size(); j++) { apows[j] = apow; apow = apow * alpha; } }
+        const size_t CH = 1024;
+        #pragma omp parallel for schedule(static)
+        for (size_t i0 = 0; i0 < n; i0 += CH) {
+            const size_t i1 = std::min(n, i0 + CH);
+            for (size_t j = 0; j < polys.size(); j++) {
+                const uint64_t* cf = polys[j].b->col(polys[j].c);
+                const Ext ap = apows[j];
+                for (size_t i = i0; i < i1; i++) comp[i] = comp[i] + ext_scalar(ap, cf[i]);
+            }
         }
         // divide_by_linear(z): synthetic division, remainder dropped, padded back to n
         std::vector<Ext> quo(n, Ext(0, 0));
@@ -499,8 +514,10 @@ static inline StarkProofData prove_table(uint32_t table, const Config& cfg, cons
     std::copy(final_poly.begin(), final_poly.end(), coeffs.begin());
     std::vector<Ext> values = coeffs;
     ext_coset_fft(values, logN, GL_GENERATOR);
+    delete sc_f;
 
     // 7. FRI commit phase (fri_committed_trees)
+    StageClock* sc_c = new StageClock("fri commit phase");
     std::vector<MerkleTree> trees;
     uint64_t shift = GL_GENERATOR;
     bool first_layer = true;
@@ -540,6 +557,8 @@ static inline StarkProofData prove_table(uint32_t table, const Config& cfg, cons
     for (auto& e : coeffs) push_ext(proof.final_poly, e);
     observe_words(ch, proof.final_poly);
 
+    delete sc_c;
+    ORC_STAGE("pow + queries");
     // 8. proof of work: smallest witness (the reference takes any: rayon find_any), or the forced one
     {
         Challenger base = ch;

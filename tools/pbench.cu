@@ -5,7 +5,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "poseidon_fast.cuh"
-#include "pf_limb_variant.cuh"
+
 using namespace zk;
 
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(128) perm_kernel(const uint64_t* __restrict__ 
     for (int k = 0; k < 12; k++) s[k] = in[k * count + i];
     for (int r = 0; r < reps; r++) {
         if (V == 0) poseidon_permute(s);
-        else { if (V == 1) pf_permute_unrolled<0>(s); else if (V == 2) pf_permute_unrolled<1>(s); else if (V == 3) pf_permute(s); else pf_permute_limb(s);
+        else { if (V == 1) pf_permute_unrolled<0>(s); else if (V == 2) pf_permute_unrolled<1>(s); else if (V == 3) pf_permute_r1(s); else pf_permute(s);
 #pragma unroll
             for (int k = 0; k < 12; k++) s[k] = pf_canon(s[k]); }
     }
@@ -81,7 +81,7 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(r2.data(), d2, 12 * count * 8, cudaMemcpyDeviceToHost));
     size_t bad = 0;
     CK(cudaMemcpy(r1.data(), d4, 12 * count * 8, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < 12 * count; i++) if (r0[i] != r1[i]) { if (bad < 5) printf("v4 (limb-form partial rounds, tools/pf_limb_variant.cuh) mismatch at %zu\n", i); bad++; }
+    for (size_t i = 0; i < 12 * count; i++) if (r0[i] != r1[i]) { if (bad < 5) printf("v4 (limb-form partial rounds, poseidon_fast.cuh pf_permute) mismatch at %zu\n", i); bad++; }
     CK(cudaMemcpy(r1.data(), d3, 12 * count * 8, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < 12 * count; i++) if (r0[i] != r1[i]) { if (bad < 5) printf("v3 mismatch at %zu\n", i); bad++; }
     CK(cudaMemcpy(r1.data(), d1, 12 * count * 8, cudaMemcpyDeviceToHost));

@@ -257,13 +257,89 @@ PF_FN void pf_mds_fft(uint64_t s[12], const uint32_t* __restrict__ rc3) {
     }
 }
 
+// ---- partial rounds with lanes 1..11 kept in limb form ------------------------------------------------------------------
+// Only lane 0 goes through the S-box in a partial round, so only lane 0 has to be a 64-bit word there: lanes 1..11 stay in the
+// three 22/22/20-bit limbs across all 22 partial rounds and are merely re-normalised (carries pushed up, the bits above 2^64
+// folded back through 2^64 == 2^32 - 1) instead of folded to 64 bits and split again every round.
+// (Round 1's first version of this mis-compiled: ptxas folded a negation into the funnel shift of h (2^32 - 1), `LEA.HI Rd, -Ra, ..`.
+// The limb is written without a negated shifted operand here: (h (2^32 - 1)) >> 22 = (h << 10) - [h != 0].  Checked on a B200 against
+// the 64-bit form on 4 Mi random states, profiles/r2a_pbench.txt: 1126 -> 1179 M perm/s.)
+PF_FN void pfl_split(uint64_t v, uint32_t& x0, uint32_t& x1, uint32_t& x2) {
+    uint32_t lo, hi; pf_unpack(v, lo, hi);
+    x0 = lo & 0x3FFFFFu;
+    x1 = pf_funnelshift_r(lo, hi, 22) & 0x3FFFFFu;
+    x2 = hi >> 12;
+}
+// x0 + 2^22 x1 + 2^44 x2 (x0 < 2^32, x1 + 2^10 (x2 >> 20) < 2^32) -> some u64 congruent mod p (the same steps as pf_mds_fft's fold)
+PF_FN uint64_t pfl_fold(uint32_t x0, uint32_t x1, uint32_t x2) {
+    const uint32_t h = x2 >> 20, l = x2 & 0xFFFFFu;
+    x1 += h << 10;
+    const uint64_t t = (uint64_t)x0 + (((uint64_t)x1) << 22) - h;      // >= 0 because x1 >= 2^10 h; < 2^55
+    return pf_add_canon(t, (uint64_t)l << 44);                           // l 2^44 < p: a canonical addend
+}
+// limbs < 2^32 (x2 < 2^30) -> x0 < 2^23, x1 < 2^22 + 2^19, x2 < 2^20, same value mod p, every limb >= 0
+PF_FN void pfl_norm(uint32_t& x0, uint32_t& x1, uint32_t& x2) {
+    x1 += x0 >> 22; x0 &= 0x3FFFFFu;
+    x2 += x1 >> 22; x1 &= 0x3FFFFFu;
+    const uint32_t h = x2 >> 20; x2 &= 0xFFFFFu;
+    // 2^64 h == h (2^32 - 1) = 2^22 ((h << 10) - [h != 0]) + ((2^22 - h) mod 2^22)
+    x0 += (0x400000u - h) & 0x3FFFFFu;
+    x1 += (h << 10) - (h != 0 ? 1u : 0u);
+}
+PF_FN void pfl_partial_rounds(uint64_t s[12]) {
+    uint32_t a0[12], a1[12], a2[12];
+#pragma unroll
+    for (int i = 1; i < 12; i++) pfl_split(s[i], a0[i], a1[i], a2[i]);
+    uint64_t s0 = s[0];
+#pragma unroll 1
+    for (int r = 4; r < 26; r++) {
+        s0 = pf_sbox7(s0);
+        pfl_split(s0, a0[0], a1[0], a2[0]);
+        uint32_t o0[12], o1[12], o2[12];
+        pf_mds_fft_limb(a0, o0); pf_mds_fft_limb(a1, o1); pf_mds_fft_limb(a2, o2);
+        const uint32_t* __restrict__ rc3 = PF_RC3 + 36 * (r + 1);
+        s0 = pfl_fold(o0[0] + rc3[0], o1[0] + rc3[1], o2[0] + rc3[2]);
+#pragma unroll
+        for (int i = 1; i < 12; i++) {
+            a0[i] = o0[i] + rc3[3 * i]; a1[i] = o1[i] + rc3[3 * i + 1]; a2[i] = o2[i] + rc3[3 * i + 2];
+            pfl_norm(a0[i], a1[i], a2[i]);
+        }
+    }
+    s[0] = s0;
+#pragma unroll
+    for (int i = 1; i < 12; i++) s[i] = pfl_fold(a0[i], a1[i], a2[i]);
+}
+
 // s: canonical or not on input; NON-canonical on output (apply pf_canon to the words that are stored).
 //
 // Code size matters more than instruction count here: the fully unrolled 30-round body is ~90 KB of SASS, far beyond the
 // 32 KB L1.5 instruction cache, and ncu showed warps stalled on instruction fetch ("no_instructions") for most cycles.
-// So there is ONE round loop: the full S-box layer is 3 iterations of "4 S-boxes + rotate the state by 4 lanes" (static
-// register indices, 24 moves per iteration), the MDS layer (with the next round's constants folded in) appears once.
+// So the full rounds are ONE loop body used by both halves: the full S-box layer is 3 iterations of "4 S-boxes + rotate the state
+// by 4 lanes" (static register indices, 24 moves per iteration), the MDS layer (with the next round's constants folded in) appears
+// once; the partial rounds are the second loop (pfl_partial_rounds).
 PF_FN void pf_permute(uint64_t s[12]) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = pf_add_canon(s[i], poseidon_rc(i));
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            const int r = half * 26 + q;
+#pragma unroll 1
+            for (int k = 0; k < 3; k++) {
+                uint64_t t0 = pf_sbox7(s[0]), t1 = pf_sbox7(s[1]), t2 = pf_sbox7(s[2]), t3 = pf_sbox7(s[3]);
+#pragma unroll
+                for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+                s[8] = t0; s[9] = t1; s[10] = t2; s[11] = t3;
+            }
+            pf_mds_fft<true>(s, PF_RC3 + 36 * (r + 1));
+        }
+        if (half == 0) pfl_partial_rounds(s);
+    }
+}
+
+// the round-1 form (every lane folded to 64 bits after every MDS layer), kept for the micro-benchmark (tools/pbench.cu variant 3)
+PF_FN void pf_permute_r1(uint64_t s[12]) {
 #pragma unroll
     for (int i = 0; i < 12; i++) s[i] = pf_add_canon(s[i], poseidon_rc(i));
 #pragma unroll 1
