@@ -80,6 +80,9 @@ const char* zkgpu_version(void);
 int zkgpu_ctx_create(int device, zkgpu_ctx** out);
 void zkgpu_ctx_destroy(zkgpu_ctx* ctx);
 int zkgpu_ctx_sync(zkgpu_ctx* ctx);
+/* the context's CUDA stream (a cudaStream_t), so that a caller's own device work — e.g. the NCCL collectives of a table-sharded
+ * segment — can be ordered with the library's kernels on the device instead of through host synchronisation */
+int zkgpu_ctx_stream(zkgpu_ctx* ctx, void** stream_out);
 /* CUDA-event stopwatch on the context's stream: device milliseconds between start and stop */
 int zkgpu_ctx_timer_start(zkgpu_ctx* ctx);
 int zkgpu_ctx_timer_stop(zkgpu_ctx* ctx, float* ms);
@@ -138,6 +141,30 @@ int zkgpu_batch_cap(const zkgpu_batch* b, uint64_t* out_cap);
  *   leaves  (n<<rate_bits)*ncols  merkle_tree.leaves, row-major, row j = LDE row bitrev(j)
  *   digests 2*((n<<rate_bits) - (1<<cap_height))*4   merkle_tree.digests in plonky2's recursive layout */
 int zkgpu_batch_export(const zkgpu_batch* b, uint64_t* coeffs, uint64_t* leaves, uint64_t* digests);
+
+/* ---- S1 split over several devices (the table-sharded layout of one segment) --------------------------------------
+ * PolynomialBatch::from_values (prover.rs:100-107) of ONE table computed by k devices.  The transforms are per column and the leaf
+ * sponge absorbs a row's columns in order, so: every device takes a column slice through ifft + LDE (zkgpu_lde_slice), the slices
+ * are exchanged between the devices (the caller's collective: NCCL all-gather over NVLink), every device hashes the rows of one of
+ * k equal blocks of leaves and builds the Merkle levels under that block's cap entries (zkgpu_merkle_block), the packed digests are
+ * exchanged, and the owner of the table assembles the batch (zkgpu_batch_assemble).  The result is bit-identical to
+ * zkgpu_commit_values on one device.  All buffers here are DEVICE memory owned by the caller, column-major. */
+/* values: ncols x n (mem_kind: host or device).  Writes coeffs_out (ncols x n) and lde_out (ncols x (n << rate_bits), bit-reversed
+ * rows, the layout of a batch); values_out (nullable) receives a device copy of the values when they came from the host. */
+int zkgpu_lde_slice(zkgpu_ctx* ctx, const uint64_t* values, int mem_kind, size_t ncols, size_t n, uint32_t rate_bits,
+                    uint64_t* values_out, uint64_t* coeffs_out, uint64_t* lde_out);
+/* number of u64 words of one block's packed digests: sum over the levels (leaf digests up to the cap level) of 4 * count / nblocks */
+int zkgpu_merkle_block_words(size_t nleaves, uint32_t cap_height, uint32_t nblocks, size_t* words);
+/* digests of the leaves [block * nleaves / nblocks, (block + 1) * nleaves / nblocks) of the column-major LDE `lde` (column c at
+ * lde + c * stride) and every Merkle level above them down to the cap level, packed level after level.  nblocks must divide the
+ * cap (1 << cap_height). */
+int zkgpu_merkle_block(zkgpu_ctx* ctx, const uint64_t* lde, size_t stride, size_t ncols, size_t nleaves, uint32_t cap_height,
+                       uint32_t nblocks, uint32_t block, uint64_t* packed_out);
+/* A batch over caller-owned device buffers (borrowed until zkgpu_batch_free; values may be NULL): coeffs ncols x n with column
+ * pitch coeff_pitch, lde ncols x N with column pitch N; packed = nblocks packed digest blocks of `zkgpu_merkle_block_words` words
+ * each, unpacked into the batch's own digest levels. */
+int zkgpu_batch_assemble(zkgpu_ctx* ctx, const uint64_t* values, const uint64_t* coeffs, const uint64_t* lde, const uint64_t* packed,
+                         uint32_t nblocks, size_t ncols, size_t n, uint32_t rate_bits, uint32_t cap_height, zkgpu_batch** out);
 
 /* ---- S2: cross-table-lookup data of one table -------------------------------------------------------------- */
 /* Shape of a table under the AllStark registry (all_stark.rs:153-172): trace width and the auxiliary-column layout

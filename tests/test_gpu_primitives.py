@@ -30,7 +30,19 @@ def test_empty_consolidated_blockhash_on_gpu(ctx):
     assert list(out[0]) == [5498946765822202150, 10724662260254836878, 9161393967331872654, 5704373722058976135]
 
 
-@pytest.mark.parametrize("lg", [0, 1, 2, 3, 4, 7, 10, 12, 13, 14, 16, 17, 20])
+def test_reference_bytecode_and_smt_kats_on_gpu(ctx):
+    # smt_trie/src/code.rs:71-84 (non-zero multi-block sponge input) and smt_trie/src/smt_test.rs:30-47 through the DEVICE permutation
+    from tests.test_oracle_kats import SOME_CODE, SOME_CODE_HASH, SMT_SINGLE_LEAF_ROOT, _hash_contract_bytecode, smt_single_leaf_root
+
+    class Dev:      # the two helpers only need .poseidon(state) -> states
+        @staticmethod
+        def poseidon(st):
+            return ctx.poseidon_permute(np.ascontiguousarray(st, dtype=np.uint64).reshape(-1, 12))
+    assert _hash_contract_bytecode(Dev, SOME_CODE) == SOME_CODE_HASH
+    assert smt_single_leaf_root(Dev.poseidon, [1, 0, 0, 0], 2) == SMT_SINGLE_LEAF_ROOT
+
+
+@pytest.mark.parametrize("lg", [0, 1, 2, 3, 4, 7, 10, 12, 13, 14, 16, 17, 20, 21, 22])
 def test_ntt_all_kinds(ctx, oracle, lg):
     rng = np.random.default_rng(lg)
     ncols = 3 if lg >= 16 else 9

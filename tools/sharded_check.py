@@ -1,0 +1,78 @@
+#!/usr/bin/env python3
+"""Parity of the table-sharded layout, run under torchrun on N >= 2 GPUs of one node:
+     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/sharded_check.py [--full]
+Every rank takes part in `prove_with_traces_sharded` with a plan that splits the trace commitments over all ranks; rank 0 also proves
+the same segment alone (`prove_with_traces`) and the two AllProofs must agree word for word (proofs, CTL challenges, trace caps).
+Small valid segment (restated verifier's input, tests/traces.py) with every table split, then (--full) the bench segment with the
+default plan, traces resident in HBM and from host memory."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    import zk_evm_b200 as zk
+    import bench
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = zk.Context(local)
+    comm = zk.TorchComm(device=dev)
+    labels = zk.KernelLabels(*bench.LABELS)
+    ok = True
+
+    def compare(name, ap, ref):
+        nonlocal ok
+        same = np.array_equal(ap.ctl_challenges, ref.ctl_challenges) and np.array_equal(np.asarray(ap.trace_caps).ravel(), np.asarray(ref.trace_caps).ravel())
+        for t in range(9):
+            a, b = ap.stark_proofs[t], ref.stark_proofs[t]
+            same = same and ((a is None) == (b is None)) and (a is None or np.array_equal(a, b))
+        print("[sharded_check] %-60s %s" % (name, "identical to the one-GPU proof" if same else "MISMATCH"), flush=True)
+        ok = ok and same
+
+    # 1. small valid segment, every table split over all ranks
+    from tests import traces
+    for cfgw, cname in ((bench.TEST_CONFIG, "test config"), (bench.STANDARD_FAST, "standard_fast")):
+        cfg = zk.StarkConfig(*cfgw)
+        tr = traces.valid_segment(seed=5, k=9)
+        in_use = [x is not None for x in tr]
+        log_ns = [None if x is None else int(np.log2(x.shape[1])) for x in tr]
+        plan = zk.shard_plan(world, log_ns, split_min_bytes=0)
+        be = zk.ZkGpuBackend(ctx, cfg, labels)
+        pv = np.arange(1000, 1037, dtype=np.uint64)
+        ap = zk.prove_with_traces_sharded(be, comm, tr, in_use, pv, plan=plan, gather=True)
+        if rank == 0:
+            compare("valid segment 2^9 (%s), all tables split over %d GPUs" % (cname, world), ap, zk.prove_with_traces(ctx, tr, pv, cfg, labels))
+    # 2. the bench segment
+    if args.full:
+        cfg = zk.StarkConfig(*bench.STANDARD_FAST)
+        log_ns = list(bench.SEGMENT_LOG_NS)
+        plan = zk.shard_plan(world, log_ns)
+        rig = bench.Rig(torch, dev, log_ns, seed=4, mine=[True] * 9 if rank == 0 else plan.needs(rank), common_seed=True)
+        be = zk.ZkGpuBackend(ctx, cfg, labels)
+        for host in (False, True):
+            tr = rig.host_traces if host else rig.ptrs
+            ap = zk.prove_with_traces_sharded(be, comm, tr, rig.in_use, bench.PUBLIC_VALUES, plan=plan, gather=True)
+            if rank == 0:
+                ref = zk.prove_with_traces(ctx, None, bench.PUBLIC_VALUES, cfg, labels, device_ptrs=rig.ptrs)
+                compare("bench segment, %s traces, plan %s" % ("host" if host else "resident", plan.describe()), ap, ref)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, src=0)
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag[0]) else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,7 @@ DevBuf::DevBuf(Ctx* c, size_t nbytes) : ctx(c), bytes(nbytes ? nbytes : 8) {
     if (c->bytes_in_use > c->bytes_peak) c->bytes_peak = c->bytes_in_use;
 }
 void DevBuf::release() {
+    if (p && !ctx) { p = nullptr; bytes = 0; return; }     // borrowed view
     if (p) {
         cudaFreeAsync(p, ctx->stream);
         ctx->bytes_in_use -= bytes;
@@ -232,6 +233,13 @@ void zkgpu_ctx_destroy(zkgpu_ctx* h) {
     if (h->c.pool) cudaMemPoolDestroy(h->c.pool);
     if (h->c.staging) cudaFreeHost(h->c.staging);
     delete h;
+}
+
+int zkgpu_ctx_stream(zkgpu_ctx* h, void** stream_out) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(h && stream_out, "null argument");
+    *stream_out = (void*)h->c.stream;
+    ZK_API_END
 }
 
 int zkgpu_ctx_sync(zkgpu_ctx* h) {

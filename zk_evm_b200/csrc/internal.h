@@ -76,6 +76,8 @@ struct DevBuf {
     }
     ~DevBuf() { release(); }
     void release();
+    // a view of caller-owned device memory (never freed here)
+    static DevBuf borrowed(const uint64_t* q, size_t nbytes) { DevBuf d; d.p = const_cast<uint64_t*>(q); d.bytes = nbytes; return d; }
     uint64_t* get() const { return p; }
 };
 

@@ -48,6 +48,12 @@ class Context:
     def sync(self):
         check(lib().zkgpu_ctx_sync(self._h))
 
+    def stream_handle(self):
+        """the context's cudaStream_t as an integer (torch.cuda.ExternalStream(handle) orders a caller's device work with the library's)"""
+        p = C.c_void_p()
+        check(lib().zkgpu_ctx_stream(self._h, C.byref(p)))
+        return int(p.value or 0)
+
     def set_timing(self, on=True):
         """stage spans (the reference's TimingTree): record a CUDA event at every stage boundary of the prover"""
         check(lib().zkgpu_ctx_set_timing(self._h, int(bool(on))))

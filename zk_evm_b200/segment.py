@@ -209,6 +209,19 @@ class ZkGpuBackend:
     def cap(self, handle):
         return handle.cap
 
+    def torch_stream(self):
+        """the context's stream as torch sees it (collectives issued under it are ordered with the library's kernels on the device)"""
+        if getattr(self, "_tstream", None) is None:
+            import torch
+            self._tstream = torch.cuda.ExternalStream(self.ctx.stream_handle(), device=torch.device("cuda", self.ctx.device))
+        return self._tstream
+
+    def split_commit(self, comm, table, trace):
+        return SplitCommit(self, comm, table, trace)
+
+    def sync(self):
+        self.ctx.sync()
+
     def segment_challenges(self, caps, in_use, public_values):
         return segment_challenges(caps, in_use, self.config.cap_height, public_values, self.config.num_challenges)
 
@@ -261,6 +274,10 @@ class TorchComm:
         self.dist.broadcast(t, src=gsrc, group=self.group)
         return t.cpu().numpy().view(np.uint64)
 
+    def all_gather_device(self, out, inp):
+        """NCCL all-gather of device tensors (inp may be the rank's own slot of out: in place); returns the async work handle"""
+        return self.dist.all_gather_into_tensor(out, inp, group=self.group, async_op=True)
+
     def gather_proofs(self, proofs, owner):
         """every rank ends up with all proofs (object all-gather: proofs are a few hundred kB)"""
         mine = {t: p for t, p in enumerate(proofs) if p is not None and owner[t] == self.rank}
@@ -287,6 +304,122 @@ class LocalComm:
         return proofs
 
 
+NUM_COLUMNS = (116, 71, 85, 2431, 438, 523, 30, 12, 12)       # trace widths (zkgpu_table_info), for planning only
+# auxiliary columns with two challenges: the per-row weight of phases 2-3 is ~ (c + a)
+_NUM_AUX2 = (100, 70, 24, 4, 290, 2, 16, 4, 2)
+
+
+class ShardPlan:
+    """Who does what when the tables of ONE segment are spread over `world` GPUs.
+    owner[t]  the rank that proves table t (auxiliary polynomials, quotient, openings, FRI: everything after the trace commitment);
+    split[t]  True: the trace commitment of table t is computed by ALL ranks — column slices through ifft + LDE, NCCL all-gather of
+              the slices over NVLink, every rank hashes one block of leaves and builds the Merkle levels under its cap entries,
+              all-gather of the digests, the owner assembles the batch (include/zkgpu.h "S1 split over several devices").
+              False: the owner commits the table alone."""
+
+    def __init__(self, world, log_ns, owner, split):
+        self.world, self.log_ns, self.owner, self.split = world, list(log_ns), list(owner), list(split)
+
+    def needs(self, rank):
+        """tables whose trace (for split tables: a column slice of it) rank `rank` reads"""
+        return [lg is not None and (self.split[t] or self.owner[t] == rank) for t, lg in enumerate(self.log_ns)]
+
+    def describe(self):
+        return {"owner": list(self.owner), "split_over_all_gpus": [TABLE_NAMES[t] for t in range(NUM_TABLES) if self.split[t]]}
+
+
+def shard_plan(world, log_ns, split_min_bytes=32 << 20):
+    """Split the trace commitment of every table whose trace has at least split_min_bytes (the all-gather of a small table costs more
+    than hashing it alone); owners by longest-processing-time packing of the per-table weight of the phases that stay with the owner."""
+    in_use = [lg is not None for lg in log_ns]
+    rows = [(1 << lg) if lg is not None else 0 for lg in log_ns]
+    split = [world > 1 and in_use[t] and 8 * NUM_COLUMNS[t] * rows[t] >= split_min_bytes for t in range(NUM_TABLES)]
+    w = []
+    for t in range(NUM_TABLES):
+        own = rows[t] * (NUM_COLUMNS[t] + _NUM_AUX2[t] + 4) * 2.0                       # phases 2-3: streaming passes over trace + aux + quotient
+        own += rows[t] * ((_NUM_AUX2[t] + 7) // 8) * 40.0                               # aux leaf hashing
+        if not split[t]:
+            own += rows[t] * ((NUM_COLUMNS[t] + 7) // 8) * 40.0 + rows[t] * NUM_COLUMNS[t] * 3.0   # the whole trace commitment as well
+        w.append(own if in_use[t] else 0.0)
+    return ShardPlan(world, log_ns, default_owner(world, weights=w), split)
+
+
+class SplitCommit:
+    """The trace commitment of one table computed by all ranks of the communicator (see ShardPlan.split).  Every device step is
+    enqueued on the context's own stream and the NCCL collectives are ordered against it on the device (torch sees the stream as an
+    ExternalStream): begin() of the next table runs while the all-gather of this one is in flight."""
+
+    def __init__(self, backend, comm, table, trace):
+        import torch
+        self.torch, self.be, self.comm, self.table = torch, backend, comm, table
+        ctx, cfg = backend.ctx, backend.config
+        k, r = comm.world, comm.rank
+        self.ncols = ncols = NUM_COLUMNS[table]
+        device = isinstance(trace, tuple)
+        self.n = n = int(trace[1]) if device else int(trace.shape[1])
+        self.N = N = n << cfg.rate_bits
+        self.cpr = cpr = -(-ncols // k)
+        c0, c1 = min(ncols, r * cpr), min(ncols, (r + 1) * cpr)
+        dev = torch.device("cuda", ctx.device)
+        self.stream = backend.torch_stream()
+        with torch.cuda.stream(self.stream):
+            self.lde = torch.empty((k * cpr, N), dtype=torch.int64, device=dev)
+            self.coef = torch.empty((k * cpr, n), dtype=torch.int64, device=dev)
+            # values: resident tables stay where they are (the owner reads its own copy); host tables are uploaded slice by slice —
+            # 1/k of the PCIe time per device — and gathered like the rest
+            self.vals = None if device else torch.empty((k * cpr, n), dtype=torch.int64, device=dev)
+            self.values_ptr = int(trace[0]) if device else self.vals.data_ptr()
+            if device:
+                src = int(trace[0]) + 8 * c0 * n
+            else:
+                a = trace if (trace.dtype == np.uint64 and trace.flags.c_contiguous) else np.ascontiguousarray(trace, dtype=np.uint64)
+                self._keep = a
+                src = a.ctypes.data + 8 * c0 * n
+            slot = 8 * r * cpr
+            check(lib().zkgpu_lde_slice(ctx._h, C.cast(C.c_void_p(src), u64p), 1 if device else 0, C.c_size_t(c1 - c0), C.c_size_t(n),
+                                        C.c_uint32(cfg.rate_bits),
+                                        None if device else C.cast(C.c_void_p(self.vals.data_ptr() + slot * n), u64p),
+                                        C.cast(C.c_void_p(self.coef.data_ptr() + slot * n), u64p),
+                                        C.cast(C.c_void_p(self.lde.data_ptr() + slot * N), u64p)))
+            self.w_lde = comm.all_gather_device(self.lde, self.lde[r * cpr:(r + 1) * cpr])
+            self.w_rest = [comm.all_gather_device(self.coef, self.coef[r * cpr:(r + 1) * cpr])]
+            if self.vals is not None:
+                self.w_rest.append(comm.all_gather_device(self.vals, self.vals[r * cpr:(r + 1) * cpr]))
+
+    def hash_block(self):
+        torch, ctx, cfg, k, r = self.torch, self.be.ctx, self.be.config, self.comm.world, self.comm.rank
+        words = C.c_size_t()
+        check(lib().zkgpu_merkle_block_words(C.c_size_t(self.N), C.c_uint32(cfg.cap_height), C.c_uint32(k), C.byref(words)))
+        with torch.cuda.stream(self.stream):
+            self.w_lde.wait()
+            self.packed = torch.empty((k, words.value), dtype=torch.int64, device=self.lde.device)
+            check(lib().zkgpu_merkle_block(ctx._h, C.cast(C.c_void_p(self.lde.data_ptr()), u64p), C.c_size_t(self.N), C.c_size_t(self.ncols),
+                                           C.c_size_t(self.N), C.c_uint32(cfg.cap_height), C.c_uint32(k), C.c_uint32(r),
+                                           C.cast(C.c_void_p(self.packed.data_ptr() + 8 * r * words.value), u64p)))
+            self.w_packed = self.comm.all_gather_device(self.packed, self.packed[r])
+
+    def finish(self, is_owner):
+        """-> the assembled PolynomialBatch on the owner (it borrows the gathered buffers), None elsewhere"""
+        torch, ctx, cfg = self.torch, self.be.ctx, self.be.config
+        with torch.cuda.stream(self.stream):
+            for w in self.w_rest + [self.w_packed]:
+                w.wait()
+            if not is_owner:
+                return None
+            h = C.c_void_p()
+            check(lib().zkgpu_batch_assemble(ctx._h, C.cast(C.c_void_p(self.values_ptr), u64p), C.cast(C.c_void_p(self.coef.data_ptr()), u64p),
+                                             C.cast(C.c_void_p(self.lde.data_ptr()), u64p), C.cast(C.c_void_p(self.packed.data_ptr()), u64p),
+                                             C.c_uint32(self.comm.world), C.c_size_t(self.ncols), C.c_size_t(self.n), C.c_uint32(cfg.rate_bits),
+                                             C.c_uint32(cfg.cap_height), C.byref(h)))
+        b = _p.PolynomialBatch(ctx, h)
+        b._keepalive = (self.lde, self.coef, self.vals, self.packed, getattr(self, "_keep", None))
+        return b
+
+
+def _rows(trace):
+    return 0 if trace is None else int(trace[1]) if isinstance(trace, tuple) else int(trace.shape[1])
+
+
 def default_owner(world, weights=None):
     """table -> rank.  Longest-processing-time bin packing on per-table weights (default: a static cost model
     rows-independent ~ columns * ceil(columns / 8), dominated by Keccak, KeccakSponge, Logic, Arithmetic, Cpu)."""
@@ -302,28 +435,60 @@ def default_owner(world, weights=None):
 
 
 def prove_with_traces_sharded(backend, comm, traces, table_in_use, public_values, owner=None, forced_pow_witnesses=None,
-                              gather=True, cap_height=None):
-    """traces[t] is needed on owner[t] only (host array or (device address, n)); table_in_use must agree on every rank."""
+                              gather=True, cap_height=None, plan=None):
+    """traces[t] is needed on owner[t] (and, for the tables the plan splits, on every rank: a column slice of it is read); host array
+    or (device address, n); table_in_use must agree on every rank.  plan: a ShardPlan (shard_plan(world, log_ns)); without one the
+    tables are only distributed whole (owner, default: default_owner)."""
+    import time as _time
+    if plan is not None:
+        owner = plan.owner
     owner = owner if owner is not None else default_owner(comm.world)
+    split = plan.split if plan is not None and comm.world > 1 else [False] * NUM_TABLES
     if cap_height is None:
         cap_height = getattr(getattr(backend, "config", None), "cap_height", 4)
     cap_words = 4 << cap_height
-    # phase 1: commitments of the local tables
+    phases = getattr(backend, "phase_ms", None)
+    t_mark = [_time.perf_counter()]
+
+    def mark(name):
+        if phases is None:
+            return
+        backend.sync()
+        now = _time.perf_counter()
+        phases[name] = phases.get(name, 0.0) + (now - t_mark[0]) * 1e3
+        t_mark[0] = now
+    # phase 1: trace commitments — the split tables by all ranks (largest first, so that the all-gather of one runs under the LDE of
+    # the next), then the tables this rank commits alone
     handles = {}
     caps = np.zeros((NUM_TABLES, cap_words), dtype=np.uint64)
+    order = sorted((t for t in range(NUM_TABLES) if table_in_use[t] and split[t]), key=lambda t: -NUM_COLUMNS[t] * _rows(traces[t]))
+    for t in order:
+        if traces[t] is None:
+            raise ValueError("rank %d takes part in the commitment of table %s but has no trace for it" % (comm.rank, TABLE_NAMES[t]))
+    jobs1 = [backend.split_commit(comm, t, traces[t]) for t in order]
+    for j in jobs1:
+        j.hash_block()
     for t in range(NUM_TABLES):
-        if table_in_use[t] and owner[t] == comm.rank:
+        if table_in_use[t] and not split[t] and owner[t] == comm.rank:
             if traces[t] is None:
                 raise ValueError("rank %d owns table %s but has no trace for it" % (comm.rank, TABLE_NAMES[t]))
             handles[t] = backend.commit(t, traces[t])
-            caps[t] = np.asarray(backend.cap(handles[t]), dtype=np.uint64).ravel()
+    for j in jobs1:
+        b = j.finish(owner[j.table] == comm.rank)
+        if b is not None:
+            handles[j.table] = b
+    for t, hnd in handles.items():
+        caps[t] = np.asarray(backend.cap(hnd), dtype=np.uint64).ravel()
+    mark("phase 1: trace commitments")
     # exchange 1: all-gather of the caps; row t of the result comes from the owner of table t
     allcaps = comm.all_gather(caps)
     caps = np.stack([allcaps[owner[t], t] for t in range(NUM_TABLES)])
     # transcript replay (identical on every rank)
     beta_gamma, state = backend.segment_challenges(caps, table_in_use, public_values)
+    mark("exchange: caps + transcript")
     # phase 2: auxiliary polynomials of the local tables
     jobs = {t: backend.begin(t, h, beta_gamma) for t, h in handles.items()}
+    mark("phase 2: auxiliary commitments")
     # phase 3: relay of the transcript state in Table order
     proofs = [None] * NUM_TABLES
     for t in range(NUM_TABLES):
@@ -333,6 +498,7 @@ def prove_with_traces_sharded(backend, comm, traces, table_in_use, public_values
             fp = None if forced_pow_witnesses is None else int(forced_pow_witnesses[t])
             proofs[t], state = backend.finish(jobs.pop(t), state, fp)
         state = comm.broadcast(state, src=owner[t])
+    mark("phase 3: transcript relay")
     if gather:
         proofs = comm.gather_proofs(proofs, owner)
     return AllProof(proofs, np.asarray(beta_gamma), caps.reshape(NUM_TABLES, -1, 4), list(table_in_use))
