@@ -304,8 +304,31 @@ def run_ours(args):
     fin_h2d_bytes = rig.h2d_bytes - sum(8 * NUM_COLUMNS[t] * (1 << log_ns[t]) for t, f in ((T_KECCAK, fin_keccak), (T_LOGIC, fin_logic)) if f is not None) \
         + (fin_keccak[0].nbytes + fin_keccak[1].nbytes if fin_keccak is not None else 0) + (fin_logic.nbytes if fin_logic is not None else 0)
 
+    BG = np.array([0x1111111111, 0x2222222222, 0x3333333333, 0x4444444444], dtype=np.uint64)
+    STATE0 = np.arange(1, 13, dtype=np.uint64)
+
+    class TableProofs:      # what one_table returns: looks like an AllProof to proof_bytes()
+        def __init__(self, words):
+            self.stark_proofs = [words]
+
+    def one_table(cx, host, r, c):
+        """BASELINE config #2: PolynomialBatch::from_values + get_ctl_data + prove_single_table of the one table of the rig
+        (prover.rs:100-107, 137-143, 301-341), CTL challenges and transcript state fixed"""
+        t = r.in_use.index(True)
+        if host:
+            tb = zk.PolynomialBatch.from_values(cx, r.host_traces[t], c.rate_bits, c.cap_height, keep_values=True)
+        else:
+            tb = zk.PolynomialBatch.from_device_values(cx, r.ptrs[t][0], NUM_COLUMNS[t], r.ptrs[t][1], c.rate_bits, c.cap_height, keep_values=True)
+        ctl = zk.get_ctl_data(cx, t, tb, BG[:2 * c.num_challenges], c.num_challenges)
+        proof, _ = zk.prove_single_table(cx, t, c, tb, ctl, STATE0, labels=labels)
+        words = proof.words
+        proof.free(); ctl.free(); tb.free()
+        return TableProofs(words)
+
     def one_segment(cx, host, r=None, c=None):
         r, c = r or rig, c or cfg
+        if sum(r.in_use) == 1:
+            return one_table(cx, 1 if host else 0, r, c)
         if host == 2:
             tr, made = list(r.host_traces), []
             if fin_keccak is not None:
@@ -555,7 +578,12 @@ def oracle_segment_time(log_ns, threads=None, stark_config=STANDARD_FAST):
     rng = np.random.default_rng(4)
     traces = [None if lg is None else rng.integers(0, 2 ** 63 - 1, size=(NUM_COLUMNS[t], 1 << lg), dtype=np.uint64) for t, lg in enumerate(log_ns)]
     t0 = time.perf_counter()
-    oracle_lib.orc_prove_segment(orc, stark_config, traces, PUBLIC_VALUES, labels=LABELS)
+    if sum(tr is not None for tr in traces) == 1:        # BASELINE config #2: one table through commit + ctl data + prove_single_table
+        t = [tr is not None for tr in traces].index(True)
+        bg = np.array([0x1111111111, 0x2222222222, 0x3333333333, 0x4444444444], dtype=np.uint64)
+        oracle_lib.orc_prove_table(orc, t, stark_config, traces[t], bg[:2 * stark_config[1]], np.arange(1, 13, dtype=np.uint64))
+    else:
+        oracle_lib.orc_prove_segment(orc, stark_config, traces, PUBLIC_VALUES, labels=LABELS)
     return time.perf_counter() - t0, orc.lib.orc_num_threads()
 
 

@@ -18,6 +18,7 @@
 #include <vector>
 #include <array>
 #include <stdexcept>
+#include <stdlib.h>
 #include "poseidon_constants.h"
 
 #include <map>
@@ -242,6 +243,11 @@ static inline void coset_ifft_inplace(uint64_t* a, unsigned log_n, uint64_t shif
 // We keep digests level by level (level 0 = leaf digests); `digests_plonky2_layout` re-creates the
 // host layout of MerkleTree::digests for the PolynomialBatch export.
 // ---------------------------------------------------------------------------------------------
+// eight-at-a-time forms (poseidon_avx512.h), used when the CPU has AVX-512
+static inline bool have_avx512();
+static inline void hash_no_pad_x8(const uint64_t* const rows[8], size_t len, Hash out[8]);
+static inline void two_to_one_x8(const Hash* children, Hash* out);
+
 struct MerkleTree {
     size_t num_leaves = 0, leaf_len = 0;
     unsigned cap_height = 0;
@@ -256,13 +262,28 @@ struct MerkleTree {
         if (((size_t)1 << cap_h) > n_leaves) throw std::runtime_error("cap height too large for tree");
         levels.clear();
         levels.emplace_back(n_leaves);
-        #pragma omp parallel for schedule(static)
-        for (size_t i = 0; i < n_leaves; i++) levels[0][i] = hash_or_noop(&leaves[i * len], len);
+        const bool x8 = have_avx512();
+        if (x8 && len > 4 && n_leaves >= 8) {
+            #pragma omp parallel for schedule(static)
+            for (size_t i = 0; i < n_leaves; i += 8) {
+                const uint64_t* rows8[8];
+                for (int k = 0; k < 8; k++) rows8[k] = &leaves[(i + k) * len];
+                hash_no_pad_x8(rows8, len, &levels[0][i]);
+            }
+        } else {
+            #pragma omp parallel for schedule(static)
+            for (size_t i = 0; i < n_leaves; i++) levels[0][i] = hash_or_noop(&leaves[i * len], len);
+        }
         while (levels.back().size() > ((size_t)1 << cap_h)) {
             const std::vector<Hash>& prev = levels.back();
             std::vector<Hash> next(prev.size() / 2);
-            #pragma omp parallel for schedule(static)
-            for (size_t i = 0; i < next.size(); i++) next[i] = two_to_one(prev[2 * i], prev[2 * i + 1]);
+            if (x8 && next.size() >= 8) {
+                #pragma omp parallel for schedule(static)
+                for (size_t i = 0; i < next.size(); i += 8) two_to_one_x8(&prev[2 * i], &next[i]);
+            } else {
+                #pragma omp parallel for schedule(static)
+                for (size_t i = 0; i < next.size(); i++) next[i] = two_to_one(prev[2 * i], prev[2 * i + 1]);
+            }
             levels.push_back(std::move(next));
         }
     }
@@ -330,3 +351,5 @@ struct Challenger {
 };
 
 }  // namespace orc
+
+#include "poseidon_avx512.h"

@@ -113,19 +113,42 @@ static inline std::vector<std::vector<uint64_t>> get_helper_cols(const uint64_t*
     size_t chunk = constraint_degree - 1;
     size_t nh = (cf.size() + chunk - 1) / chunk;
     std::vector<std::vector<uint64_t>> helpers(nh, std::vector<uint64_t>(n, 0));
+    // denominators of one (helper, term) for a block of rows, inverted together (Montgomery's trick, as the reference's
+    // batch_multiplicative_inverse does); rows whose filter is 0 contribute nothing and are skipped as before
+    const size_t BLK = 4096;
     for (size_t h = 0; h < nh; h++) {
-        #pragma omp parallel for schedule(static)
-        for (size_t r = 0; r < n; r++) {
-            uint64_t acc = 0;
-            for (size_t k = h * chunk; k < std::min(cf.size(), (h + 1) * chunk); k++) {
-                uint64_t f = filter_eval_table(cf[k].second, trace, n, r);
-                if (f == 0) continue;
-                uint64_t comb = 0;
-                for (size_t i = cf[k].first.size(); i-- > 0;) comb = gl_add(gl_mul(comb, beta), col_eval_table(cf[k].first[i], trace, n, r));
-                comb = gl_add(comb, gamma);
-                acc = gl_add(acc, gl_mul(f, gl_inv(comb)));
+        #pragma omp parallel
+        {
+            std::vector<uint64_t> den(BLK), fil(BLK), pre(BLK);
+            #pragma omp for schedule(static)
+            for (size_t r0 = 0; r0 < n; r0 += BLK) {
+                const size_t cnt = std::min(BLK, n - r0);
+                for (size_t k = h * chunk; k < std::min(cf.size(), (h + 1) * chunk); k++) {
+                    for (size_t i = 0; i < cnt; i++) {
+                        const size_t r = r0 + i;
+                        uint64_t f = filter_eval_table(cf[k].second, trace, n, r);
+                        fil[i] = f;
+                        uint64_t comb = 1;
+                        if (f != 0) {
+                            comb = 0;
+                            for (size_t j = cf[k].first.size(); j-- > 0;) comb = gl_add(gl_mul(comb, beta), col_eval_table(cf[k].first[j], trace, n, r));
+                            comb = gl_add(comb, gamma);
+                        }
+                        den[i] = comb;
+                    }
+                    // prefix products over the non-zero denominators (inverse(0) = 0 as Field::inverse_or_zero would not be hit here:
+                    // a zero denominator keeps its slot out of the chain and yields 0)
+                    uint64_t acc = 1;
+                    for (size_t i = 0; i < cnt; i++) { pre[i] = acc; if (den[i] != 0) acc = gl_mul(acc, den[i]); }
+                    uint64_t inv = gl_inv(acc);
+                    for (size_t i = cnt; i-- > 0;) {
+                        if (den[i] == 0) continue;
+                        const uint64_t di = gl_mul(inv, pre[i]);
+                        inv = gl_mul(inv, den[i]);
+                        if (fil[i] != 0) helpers[h][r0 + i] = gl_add(helpers[h][r0 + i], gl_mul(fil[i], di));
+                    }
+                }
             }
-            helpers[h][r] = acc;
         }
     }
     return helpers;
@@ -180,12 +203,28 @@ static inline std::vector<std::vector<uint64_t>> lookup_helper_columns(const Loo
     std::vector<ColumnsFilter> cf;
     for (size_t i = 0; i < l.columns.size(); i++) cf.push_back({{l.columns[i]}, l.filter_columns[i]});
     auto cols = get_helper_cols(trace, n, cf, 1, challenge, constraint_degree);
-    std::vector<uint64_t> z(n, 0);
+    std::vector<uint64_t> z(n, 0), tinv(n);
+    #pragma omp parallel for schedule(static)
+    for (size_t r0 = 0; r0 < n; r0 += 4096) {
+        const size_t cnt = std::min((size_t)4096, n - r0);
+        std::vector<uint64_t> den(cnt), pre(cnt);
+        uint64_t acc = 1;
+        for (size_t i = 0; i < cnt; i++) {
+            den[i] = gl_add(challenge, col_eval_table(l.table_column, trace, n, r0 + i));
+            pre[i] = acc;
+            if (den[i] != 0) acc = gl_mul(acc, den[i]);
+        }
+        uint64_t inv = gl_inv(acc);
+        for (size_t i = cnt; i-- > 0;) {
+            if (den[i] == 0) { tinv[r0 + i] = 0; continue; }
+            tinv[r0 + i] = gl_mul(inv, pre[i]);
+            inv = gl_mul(inv, den[i]);
+        }
+    }
     for (size_t r = 0; r + 1 < n; r++) {
         uint64_t x = 0;
         for (auto& h : cols) x = gl_add(x, h[r]);
-        uint64_t tinv = gl_inv(gl_add(challenge, col_eval_table(l.table_column, trace, n, r)));
-        x = gl_sub(x, gl_mul(col_eval_table(l.frequencies_column, trace, n, r), tinv));
+        x = gl_sub(x, gl_mul(col_eval_table(l.frequencies_column, trace, n, r), tinv[r]));
         z[r + 1] = gl_add(z[r], x);
     }
     cols.push_back(std::move(z));

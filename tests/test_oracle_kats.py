@@ -166,3 +166,18 @@ def test_merkle_layout_and_proofs(oracle):
         assert np.array_equal(buf[half], l) and np.array_equal(buf[half + 1], r)
         return oracle.two_to_one(l, r)
     assert np.array_equal(root(sub, 0, per), cap[0])
+
+
+def test_avx512_poseidon_equals_scalar_form(oracle):
+    # oracle/poseidon_avx512.h (eight permutations per call, used by the Merkle trees of the CPU baseline) against the scalar 30-round
+    # form that the reference's known answers pin; skipped silently where the CPU has no AVX-512
+    import ctypes as C
+    st = rand_field(np.random.default_rng(99), (8 * 37 + 5, 12))
+    st[0] = 0
+    st[1] = P - 1
+    st[2, :6] = P - 1
+    a = oracle.poseidon(st)
+    b = np.ascontiguousarray(st.copy())
+    if oracle.lib.orc_poseidon_x8(b.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_size_t(len(b))):
+        assert np.array_equal(a, b)
+        assert list(b[0][:4]) == [4330397376401421145, 14124799381142128323, 8742572140681234676, 14345658006221440202]   # HASH_ZEROS

@@ -17,6 +17,7 @@ import numpy as np  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--time", type=int, default=0, help="with --full: time this many sharded proofs and print the phase breakdown of the last")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -66,6 +67,44 @@ def main():
             if rank == 0:
                 ref = zk.prove_with_traces(ctx, None, bench.PUBLIC_VALUES, cfg, labels, device_ptrs=rig.ptrs)
                 compare("bench segment, %s traces, plan %s" % ("host" if host else "resident", plan.describe()), ap, ref)
+        if args.time:
+            import time
+            for host in ((False,) if os.environ.get("ZK_SHARD_BEGIN") else (False, True)):
+                tr = rig.host_traces if host else rig.ptrs
+                for _ in range(2):
+                    zk.prove_with_traces_sharded(be, comm, tr, rig.in_use, bench.PUBLIC_VALUES, plan=plan, gather=False)
+                torch.cuda.synchronize(); dist.barrier()
+                t0 = time.perf_counter()
+                each = []
+                phs = []
+                for _ in range(args.time):
+                    t1 = time.perf_counter()
+                    be.phase_ms = {"__nosync__": 1}
+                    zk.prove_with_traces_sharded(be, comm, tr, rig.in_use, bench.PUBLIC_VALUES, plan=plan, gather=False)
+                    each.append(round((time.perf_counter() - t1) * 1e3, 1))
+                    phs.append([round(v, 1) for k, v in be.phase_ms.items() if k != "__nosync__"])
+                    be.phase_ms = None
+                if rank == 0:
+                    for row in phs:
+                        print("[sharded_check]    host ms between marks:", row, flush=True)
+                torch.cuda.synchronize(); dist.barrier()
+                dt = (time.perf_counter() - t0) / args.time * 1e3
+                print("[sharded_check] rank %d back-to-back proofs, no barrier between: %s" % (rank, each), flush=True)
+                be.phase_ms = {}
+                zk.prove_with_traces_sharded(be, comm, tr, rig.in_use, bench.PUBLIC_VALUES, plan=plan, gather=False)
+                ph, be.phase_ms = be.phase_ms, None
+                walls = []
+                for _ in range(3):
+                    be.phase_ms = {"__nosync__": 1}
+                    torch.cuda.synchronize(); dist.barrier()
+                    t1 = time.perf_counter()
+                    zk.prove_with_traces_sharded(be, comm, tr, rig.in_use, bench.PUBLIC_VALUES, plan=plan, gather=False)
+                    walls.append((time.perf_counter() - t1) * 1e3)
+                    ph2, be.phase_ms = be.phase_ms, None
+                ph2.pop("__nosync__")
+                print("[sharded_check] rank %d %s: walls %s; host time between marks WITHOUT syncs: %s" % (rank, "host" if host else "resident", [round(w, 1) for w in walls], {k: round(v, 1) for k, v in ph2.items()}), flush=True)
+                print("[sharded_check] rank %d %s traces: %.1f ms per proof (wall, %d proofs); phases of one more proof with a sync at every mark: %s"
+                      % (rank, "host" if host else "resident", dt, args.time, {k: round(v, 1) for k, v in ph.items()}), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)
     ctx.close()

@@ -341,6 +341,21 @@ __global__ void gather_kernel(const uint64_t* __restrict__ src, const uint64_t* 
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < cnt) out[i] = src[offs[i]];
 }
+__global__ void gather_addr_kernel(const uint64_t* const* __restrict__ addrs, size_t cnt, uint64_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) out[i] = *addrs[i];
+}
+// out_host[i] = *addrs[i] for device addresses: every leaf and every Merkle sibling the query rounds of one table open, from all its
+// oracles, in ONE launch and one round trip
+void gather_addrs(Ctx& c, const std::vector<const uint64_t*>& addrs, uint64_t* out_host) {
+    if (addrs.empty()) return;
+    DevBuf o(&c, addrs.size() * 8), d(&c, addrs.size() * 8);
+    c.h2d(o.get(), addrs.data(), addrs.size() * 8);
+    gather_addr_kernel<<<(unsigned)((addrs.size() + 255) / 256), 256, 0, c.stream>>>(reinterpret_cast<const uint64_t* const*>(o.get()), addrs.size(), d.get());
+    c.count_launch();
+    c.check_launch("gather_addr_kernel");
+    c.d2h(out_host, d.get(), addrs.size() * 8);
+}
 void gather_words(Ctx& c, const uint64_t* src, const std::vector<uint64_t>& offsets, uint64_t* out_host) {
     if (offsets.empty()) return;
     DevBuf o(&c, offsets.size() * 8), d(&c, offsets.size() * 8);

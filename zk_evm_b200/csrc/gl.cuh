@@ -98,15 +98,16 @@ ZK_HD uint64_t gl_add(uint64_t a, uint64_t b) {
     return gld_add(a, b);
 #endif
     uint64_t s = a + b;
-    // a, b < p so the true sum is < 2p: one conditional subtraction
-    return (s < a || s >= GL_P) ? s - GL_P : s;
+    // a, b < p so the true sum is < 2p: one conditional subtraction (mask form: on pseudo-random values the comparison is an
+    // unpredictable branch, and this is the host transcript's inner loop)
+    return s - ((uint64_t)(-(int64_t)((s < a) | (s >= GL_P))) & GL_P);
 }
 ZK_HD uint64_t gl_sub(uint64_t a, uint64_t b) {
 #if defined(__CUDA_ARCH__)
     return gld_sub(a, b);
 #endif
     uint64_t d = a - b;
-    return (a < b) ? d + GL_P : d;
+    return d + ((uint64_t)(-(int64_t)(a < b)) & GL_P);
 }
 ZK_HD uint64_t gl_neg(uint64_t a) {
 #if defined(__CUDA_ARCH__)
@@ -123,11 +124,11 @@ ZK_HD uint64_t gl_reduce128(uint64_t lo, uint64_t hi) {
 #endif
     uint64_t hi_hi = hi >> 32, hi_lo = hi & GL_EPS;
     uint64_t t0 = lo - hi_hi;
-    if (lo < hi_hi) t0 -= GL_EPS;           // borrowed 2^64 == EPS (mod p)
-    uint64_t t1 = hi_lo * GL_EPS;           // < 2^64 - 2^33 + 1
+    t0 -= (uint64_t)(-(int64_t)(lo < hi_hi)) & GL_EPS;      // borrowed 2^64 == EPS (mod p)
+    uint64_t t1 = (hi_lo << 32) - hi_lo;                    // hi_lo * EPS < 2^64 - 2^33 + 1
     uint64_t t2 = t0 + t1;
-    if (t2 < t1) t2 += GL_EPS;              // carried 2^64 == EPS; cannot carry again
-    return t2 >= GL_P ? t2 - GL_P : t2;
+    t2 += (uint64_t)(-(int64_t)(t2 < t1)) & GL_EPS;         // carried 2^64 == EPS; cannot carry again
+    return t2 - ((uint64_t)(-(int64_t)(t2 >= GL_P)) & GL_P);
 }
 ZK_HD uint64_t gl_mul(uint64_t a, uint64_t b) {
 #if defined(__CUDA_ARCH__)
@@ -138,10 +139,10 @@ ZK_HD uint64_t gl_mul(uint64_t a, uint64_t b) {
 ZK_HD uint64_t gl_sqr(uint64_t a) { return gl_mul(a, a); }
 // reduce a 96-bit value lo + 2^64 * hi32 (hi32 < 2^32)
 ZK_HD uint64_t gl_reduce96(uint64_t lo, uint32_t hi32) {
-    uint64_t t1 = (uint64_t)hi32 * GL_EPS;
+    uint64_t t1 = ((uint64_t)hi32 << 32) - hi32;
     uint64_t t2 = lo + t1;
-    if (t2 < t1) t2 += GL_EPS;
-    return t2 >= GL_P ? t2 - GL_P : t2;
+    t2 += (uint64_t)(-(int64_t)(t2 < t1)) & GL_EPS;
+    return t2 - ((uint64_t)(-(int64_t)(t2 >= GL_P)) & GL_P);
 }
 ZK_HD uint64_t gl_pow(uint64_t b, uint64_t e) {
     uint64_t r = 1;

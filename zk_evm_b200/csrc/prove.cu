@@ -36,26 +36,31 @@ static void check_abort(volatile const int* flag) {
 static Words cap_words(const Batch& b) { return b.cap_host; }
 static void push_ext(Words& w, uint64_t a, uint64_t b) { w.push_back(a); w.push_back(b); }
 
-// leaf row x (bit-reversed index) of a batch and its Merkle path, for many x at once
-static void query_batch(Ctx& c, const uint64_t* lde, size_t ncols, size_t N, const DevBuf& digests, const std::vector<size_t>& level_off,
-                        const std::vector<size_t>& xs, std::vector<Words>& leaves, std::vector<Words>& paths) {
-    std::vector<uint64_t> offs;
-    for (size_t x : xs) for (size_t col = 0; col < ncols; col++) offs.push_back(col * N + x);
-    std::vector<uint64_t> vals(offs.size());
-    gather_words(c, lde, offs, vals.data());
-    leaves.assign(xs.size(), Words());
-    for (size_t q = 0; q < xs.size(); q++) leaves[q].assign(vals.begin() + q * ncols, vals.begin() + (q + 1) * ncols);
-    size_t nlev = level_off.size() - 1;   // siblings per path
-    offs.clear();
-    for (size_t x : xs) {
-        size_t idx = x;
-        for (size_t l = 0; l < nlev; l++) { for (int w = 0; w < 4; w++) offs.push_back(level_off[l] + 4 * (idx ^ 1) + w); idx >>= 1; }
+// The query answers of one table are collected in two steps: every oracle appends the device addresses of the words it opens
+// (leaf row x of a column-major batch, the siblings of its Merkle path), ONE gather brings them all to the host, and the words are
+// dealt out in the same order.
+struct QueryPlan {
+    std::vector<const uint64_t*> addrs;
+    struct Part { size_t ncols, nlev, first; };
+    std::vector<Part> parts;
+    // leaf row xs[q] and its path, for every q, of the oracle (lde: ncols x N column-major, digests with level offsets level_off)
+    void add(const uint64_t* lde, size_t ncols, size_t N, const uint64_t* digests, const std::vector<size_t>& level_off, const std::vector<size_t>& xs) {
+        const size_t nlev = level_off.size() - 1;   // siblings per path
+        parts.push_back({ncols, nlev, addrs.size()});
+        for (size_t x : xs) {
+            for (size_t col = 0; col < ncols; col++) addrs.push_back(lde + col * N + x);
+            size_t idx = x;
+            for (size_t l = 0; l < nlev; l++) { for (int w = 0; w < 4; w++) addrs.push_back(digests + level_off[l] + 4 * (idx ^ 1) + w); idx >>= 1; }
+        }
     }
-    vals.assign(offs.size(), 0);
-    gather_words(c, digests.get(), offs, vals.data());
-    paths.assign(xs.size(), Words());
-    for (size_t q = 0; q < xs.size(); q++) paths[q].assign(vals.begin() + q * nlev * 4, vals.begin() + (q + 1) * nlev * 4);
-}
+    // words of query q of part `part`: leaf then path
+    void take(const std::vector<uint64_t>& vals, size_t part, size_t q, Words& leaf, Words& path) const {
+        const Part& p = parts[part];
+        const uint64_t* v = vals.data() + p.first + q * (p.ncols + 4 * p.nlev);
+        leaf.assign(v, v + p.ncols);
+        path.assign(v + p.ncols, v + p.ncols + 4 * p.nlev);
+    }
+};
 
 struct FriLayer {
     DevBuf leaves;    // column-major (2*arity) x rows
@@ -289,21 +294,24 @@ void prove_table_finish(Ctx& c, TableJob& job, uint64_t challenger_state[12], co
         std::vector<const Batch*> oracles = {&trace};
         if (na) oracles.push_back(&aux);
         oracles.push_back(&quot);
-        for (const Batch* b : oracles) {
-            std::vector<Words> leaves, paths;
-            query_batch(c, b->lde.get(), b->ncols, b->N, b->digests, b->level_off, xs, leaves, paths);
-            for (size_t q = 0; q < xs.size(); q++) {
-                zkstark::FriInitialProof ip; ip.leaf = std::move(leaves[q]); ip.path = std::move(paths[q]);
-                p.queries[q].initial.push_back(std::move(ip));
-            }
-        }
+        QueryPlan qp;
+        for (const Batch* b : oracles) qp.add(b->lde.get(), b->ncols, b->N, b->digests.get(), b->level_off, xs);
         std::vector<size_t> cur = xs;
         for (size_t li = 0; li < layers.size(); li++) {
             for (auto& x : cur) x >>= arities[li];
-            std::vector<Words> leaves, paths;
-            query_batch(c, layers[li].leaves.get(), layers[li].width, layers[li].rows, layers[li].digests, layers[li].off, cur, leaves, paths);
-            for (size_t q = 0; q < xs.size(); q++) {
-                zkstark::FriQueryStep st; st.evals = std::move(leaves[q]); st.path = std::move(paths[q]);
+            qp.add(layers[li].leaves.get(), layers[li].width, layers[li].rows, layers[li].digests.get(), layers[li].off, cur);
+        }
+        std::vector<uint64_t> vals(qp.addrs.size());
+        gather_addrs(c, qp.addrs, vals.data());
+        for (size_t q = 0; q < xs.size(); q++) {
+            for (size_t o = 0; o < oracles.size(); o++) {
+                zkstark::FriInitialProof ip;
+                qp.take(vals, o, q, ip.leaf, ip.path);
+                p.queries[q].initial.push_back(std::move(ip));
+            }
+            for (size_t li = 0; li < layers.size(); li++) {
+                zkstark::FriQueryStep st;
+                qp.take(vals, oracles.size() + li, q, st.evals, st.path);
                 p.queries[q].steps.push_back(std::move(st));
             }
         }

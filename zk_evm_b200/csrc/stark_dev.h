@@ -98,6 +98,7 @@ void fri_fold(Ctx& c, const uint64_t* re, const uint64_t* im, size_t M, unsigned
 uint64_t pow_grind(Ctx& c, const uint64_t state[12], unsigned pos, unsigned bits);
 // out[i] = src[offsets[i]] (device gather of scattered words)
 void gather_words(Ctx& c, const uint64_t* src, const std::vector<uint64_t>& offsets, uint64_t* out_host);
+void gather_addrs(Ctx& c, const std::vector<const uint64_t*>& addrs, uint64_t* out_host);
 
 // ---- api.cu ---------------------------------------------------------------------------------------------------
 void commit_from_device_values(Ctx& c, Batch& b, bool keep_values);

@@ -198,6 +198,7 @@ class ZkGpuBackend:
 
     def __init__(self, ctx, config, labels=None):
         self.ctx, self.config, self.labels = ctx, config, labels
+        self.phase_ms = None      # a dict: prove_with_traces_sharded adds the wall time of its phases (synchronising at every mark)
 
     def commit(self, table, trace):
         if isinstance(trace, tuple):      # (device address, n)
@@ -215,6 +216,16 @@ class ZkGpuBackend:
             import torch
             self._tstream = torch.cuda.ExternalStream(self.ctx.stream_handle(), device=torch.device("cuda", self.ctx.device))
         return self._tstream
+
+    def buffer(self, key, shape):
+        """a persistent int64 device buffer of this backend (one per key; reallocated when the shape changes)"""
+        import torch
+        bufs = self.__dict__.setdefault("_bufs", {})
+        t = bufs.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            with torch.cuda.stream(self.torch_stream()):
+                t = bufs[key] = torch.empty(tuple(shape), dtype=torch.int64, device=torch.device("cuda", self.ctx.device))
+        return t
 
     def split_commit(self, comm, table, trace):
         return SplitCommit(self, comm, table, trace)
@@ -248,31 +259,59 @@ class ZkGpuBackend:
 
 
 class TorchComm:
-    """torch.distributed plumbing of the two exchanges (NCCL on GPUs, gloo in the CPU tests)."""
+    """torch.distributed plumbing of the exchanges.  Two kinds of data move between the ranks of a table-sharded segment:
+      * host data — the 9 trace caps (512 B each) and the 12-word transcript state of the relay: these go over a HOST channel (a gloo
+        group next to the NCCL one).  They are host values on both sides (the transcript is host code, as in the reference), and a
+        NCCL collective for them means an H2D copy, a kernel that spins on the device until the peer arrives, and a D2H copy — with the
+        receiver's kernel spinning while that rank launches the auxiliary-polynomial work of its next table (measured: sporadic
+        stalls of 0.1 - 1.8 s per proof, profiles/r2i);
+      * device data — the LDE / coefficient / digest slices of the split commitments: NCCL all-gathers over NVLink
+        (all_gather_device), ordered on the library's stream."""
 
-    def __init__(self, group=None, device=None):
+    def __init__(self, group=None, device=None, host_group=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist, self.group, self.device = torch, dist, group, device
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.hgroup = host_group
+        if self.hgroup is None and device is not None and dist.get_backend(group) != "gloo":
+            ranks = None if group is None else dist.get_process_group_ranks(group)
+            self.hgroup = dist.new_group(ranks=ranks, backend="gloo")      # collective: every rank builds its TorchComm at the same point
+        if self.hgroup is None:
+            self.hgroup = group
 
     def _t(self, a):
-        return self.torch.from_numpy(np.ascontiguousarray(a).view(np.int64).copy()).to(self.device) if self.device is not None \
-            else self.torch.from_numpy(np.ascontiguousarray(a).view(np.int64).copy())
+        return self.torch.from_numpy(np.ascontiguousarray(a).view(np.int64).copy())
+
+    def _gsrc(self, src):
+        # `src` is a rank of this communicator's group; torch.distributed wants the global rank
+        return src if self.group is None else self.dist.get_global_rank(self.group, src)
 
     def all_gather(self, a):
         """(world, *a.shape) uint64"""
         t = self._t(a)
         out = [self.torch.empty_like(t) for _ in range(self.world)]
-        self.dist.all_gather(out, t, group=self.group)
-        return np.stack([o.cpu().numpy().view(np.uint64) for o in out])
+        self.dist.all_gather(out, t, group=self.hgroup)
+        return np.stack([o.numpy().view(np.uint64) for o in out])
 
     def broadcast(self, a, src):
         t = self._t(a)
-        # `src` is a rank of this communicator's group; torch.distributed.broadcast wants the global rank
-        gsrc = src if self.group is None else self.dist.get_global_rank(self.group, src)
-        self.dist.broadcast(t, src=gsrc, group=self.group)
-        return t.cpu().numpy().view(np.uint64)
+        self.dist.broadcast(t, src=self._gsrc(src), group=self.hgroup)
+        return t.numpy().view(np.uint64)
+
+    def broadcast_async(self, a, src):
+        """the same broadcast, not waited for: .done() polls, .result() waits and returns the array"""
+        t = self._t(a)
+        work = self.dist.broadcast(t, src=self._gsrc(src), group=self.hgroup, async_op=True)
+
+        class Pending:
+            def done(self_):
+                return work.is_completed()
+
+            def result(self_):
+                work.wait()
+                return t.numpy().view(np.uint64)
+        return Pending()
 
     def all_gather_device(self, out, inp):
         """NCCL all-gather of device tensors (inp may be the rank's own slot of out: in place); returns the async work handle"""
@@ -363,11 +402,14 @@ class SplitCommit:
         dev = torch.device("cuda", ctx.device)
         self.stream = backend.torch_stream()
         with torch.cuda.stream(self.stream):
-            self.lde = torch.empty((k * cpr, N), dtype=torch.int64, device=dev)
-            self.coef = torch.empty((k * cpr, n), dtype=torch.int64, device=dev)
+            # the exchange buffers persist in the backend from proof to proof (backend.buffer): a fresh torch allocation per proof is
+            # held back by the collectives' record_stream bookkeeping, the caching allocator then grows by ~10 GB per proof until it
+            # has to cudaFree — measured as sporadic stalls of 80 ms to 1 s (profiles/r2h)
+            self.lde = backend.buffer(("lde", table), (k * cpr, N))
+            self.coef = backend.buffer(("coef", table), (k * cpr, n))
             # values: resident tables stay where they are (the owner reads its own copy); host tables are uploaded slice by slice —
             # 1/k of the PCIe time per device — and gathered like the rest
-            self.vals = None if device else torch.empty((k * cpr, n), dtype=torch.int64, device=dev)
+            self.vals = None if device else backend.buffer(("vals", table), (k * cpr, n))
             self.values_ptr = int(trace[0]) if device else self.vals.data_ptr()
             if device:
                 src = int(trace[0]) + 8 * c0 * n
@@ -392,7 +434,7 @@ class SplitCommit:
         check(lib().zkgpu_merkle_block_words(C.c_size_t(self.N), C.c_uint32(cfg.cap_height), C.c_uint32(k), C.byref(words)))
         with torch.cuda.stream(self.stream):
             self.w_lde.wait()
-            self.packed = torch.empty((k, words.value), dtype=torch.int64, device=self.lde.device)
+            self.packed = self.be.buffer(("packed", self.table), (k, words.value))
             check(lib().zkgpu_merkle_block(ctx._h, C.cast(C.c_void_p(self.lde.data_ptr()), u64p), C.c_size_t(self.N), C.c_size_t(self.ncols),
                                            C.c_size_t(self.N), C.c_uint32(cfg.cap_height), C.c_uint32(k), C.c_uint32(r),
                                            C.cast(C.c_void_p(self.packed.data_ptr() + 8 * r * words.value), u64p)))
@@ -453,7 +495,8 @@ def prove_with_traces_sharded(backend, comm, traces, table_in_use, public_values
     def mark(name):
         if phases is None:
             return
-        backend.sync()
+        if not phases.get("__nosync__"):
+            backend.sync()
         now = _time.perf_counter()
         phases[name] = phases.get(name, 0.0) + (now - t_mark[0]) * 1e3
         t_mark[0] = now
@@ -466,39 +509,70 @@ def prove_with_traces_sharded(backend, comm, traces, table_in_use, public_values
         if traces[t] is None:
             raise ValueError("rank %d takes part in the commitment of table %s but has no trace for it" % (comm.rank, TABLE_NAMES[t]))
     jobs1 = [backend.split_commit(comm, t, traces[t]) for t in order]
+    mark("phase 1a: ifft + LDE of the column slices")
     for j in jobs1:
         j.hash_block()
+    mark("phase 1b: all-gather of the LDEs, leaf blocks + Merkle levels")
     for t in range(NUM_TABLES):
         if table_in_use[t] and not split[t] and owner[t] == comm.rank:
             if traces[t] is None:
                 raise ValueError("rank %d owns table %s but has no trace for it" % (comm.rank, TABLE_NAMES[t]))
             handles[t] = backend.commit(t, traces[t])
+    mark("phase 1c: tables committed alone")
     for j in jobs1:
         b = j.finish(owner[j.table] == comm.rank)
         if b is not None:
             handles[j.table] = b
     for t, hnd in handles.items():
         caps[t] = np.asarray(backend.cap(hnd), dtype=np.uint64).ravel()
-    mark("phase 1: trace commitments")
+    mark("phase 1d: all-gather of coefficients / digests, assembly")
     # exchange 1: all-gather of the caps; row t of the result comes from the owner of table t
     allcaps = comm.all_gather(caps)
     caps = np.stack([allcaps[owner[t], t] for t in range(NUM_TABLES)])
     # transcript replay (identical on every rank)
     beta_gamma, state = backend.segment_challenges(caps, table_in_use, public_values)
     mark("exchange: caps + transcript")
-    # phase 2: auxiliary polynomials of the local tables
-    jobs = {t: backend.begin(t, h, beta_gamma) for t, h in handles.items()}
-    mark("phase 2: auxiliary commitments")
-    # phase 3: relay of the transcript state in Table order
+    # phases 2 + 3.  Phase 3 is the relay of the transcript state in Table order (prover.rs:251-259: one challenger, the tables one
+    # after the other), so at any time ONE rank is finishing a table and the others wait for the state: the auxiliary polynomials
+    # (phase 2, challenger-independent) of a rank's tables are computed in those waits — up front only the first one, so that the
+    # relay starts as early as it can; a table whose turn comes before its auxiliary polynomials exist gets them right then.
+    mine = [t for t in range(NUM_TABLES) if t in handles]
+    jobs, begun = {}, set()
+
+    def begin_next():
+        for t in mine:
+            if t not in begun:
+                begun.add(t)
+                jobs[t] = backend.begin(t, handles[t], beta_gamma)
+                return True
+        return False
+    import os as _os
+    mode = _os.environ.get("ZK_SHARD_BEGIN", "lazy")
+    if mode == "upfront":
+        while begin_next():
+            pass
+    else:
+        begin_next()
+    mark("phase 2: auxiliary commitment of the first local table")
     proofs = [None] * NUM_TABLES
     for t in range(NUM_TABLES):
         if not table_in_use[t]:
             continue
         if owner[t] == comm.rank:
+            if t not in begun:
+                begun.add(t)
+                jobs[t] = backend.begin(t, handles[t], beta_gamma)
             fp = None if forced_pow_witnesses is None else int(forced_pow_witnesses[t])
             proofs[t], state = backend.finish(jobs.pop(t), state, fp)
-        state = comm.broadcast(state, src=owner[t])
-    mark("phase 3: transcript relay")
+            state = comm.broadcast(state, src=owner[t])
+        elif hasattr(comm, "broadcast_async") and mode != "blocking":
+            pending = comm.broadcast_async(state, src=owner[t])
+            while not pending.done() and begin_next():
+                pass
+            state = pending.result()
+        else:
+            state = comm.broadcast(state, src=owner[t])
+        mark("phase 3: relay, " + TABLE_NAMES[t])
     if gather:
         proofs = comm.gather_proofs(proofs, owner)
     return AllProof(proofs, np.asarray(beta_gamma), caps.reshape(NUM_TABLES, -1, 4), list(table_in_use))
