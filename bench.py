@@ -633,7 +633,7 @@ def run_reference(args):
         t, threads = oracle_segment_time(log_ns, stark_config=sc)
         times.append(t)
         spent = time.perf_counter() - t_begin
-        if k + 1 < args.steps and spent + t > args.reference_budget:
+        if k + 1 < args.steps and spent + 1.15 * t > args.reference_budget:      # the next step (and making its traces) would not fit
             break
     per_step = sum(times) / len(times)
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -666,7 +666,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=20, help="cpu_table workload: log2 of the trace length (BASELINE config #2: 20)")
     ap.add_argument("--shrink", type=int, default=0, help="segment workload: make every table 2^shrink times shorter (smoke runs)")
     ap.add_argument("--cpu-shrink", type=int, default=3, help="in-arm cpu_baseline: the sample proves tables 2^k times shorter")
-    ap.add_argument("--reference-budget", type=float, default=240.0, help="reference arm: stop starting new full-size steps after this many seconds")
+    ap.add_argument("--reference-budget", type=float, default=280.0, help="reference arm: stop starting new full-size steps after this many seconds")
     ap.add_argument("--streams", type=int, default=3, help="segments in flight per GPU (parallelism=segments); measured 1: 3.34, 2: 3.78, 3: 3.95, 4: 3.86 proofs/s")
     ap.add_argument("--stagger-ms", type=float, default=80.0, help="start offset between the segment streams of a GPU (inside the timed region)")
     ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (configs #2, #3, #5, table_sharded, e2e_finish_on_device)")

@@ -224,6 +224,47 @@ extern "C" {
 
 // traces[t]: ncols(t)*n[t] column-major, or null (table not in use).  Proof words of table t are written at
 // out[offsets[t] .. offsets[t+1]) (empty for unused tables).  Returns total words (needed if > out_cap), negative on failure.
+// ---- row-level constraint check -----------------------------------------------------------------------------------------------
+// The reference's own generator tests (e.g. logic.rs:426-472, keccak_stark.rs:631-690): evaluate the table's constraints on
+// every pair of consecutive TRACE rows and require all of them to vanish (transition constraints not on the last row, first / last
+// row constraints only there).  Reports every violated (row, constraint index), the index counting yield_constr calls in the
+// evaluator's order — which is what a new trace generator needs in order to be debugged.  Table constraints only (the lookup / CTL
+// checks need the auxiliary columns; the restated verifier covers those).
+struct RowCheckConsumer {
+    size_t row = 0, n = 0;
+    uint32_t idx = 0;
+    std::vector<uint64_t>* out = nullptr;     // pairs (row, constraint index)
+    size_t max_out = 0;
+    void hit(OF c) { if (c.v != 0 && out->size() < 2 * max_out) { out->push_back(row); out->push_back(idx); } idx++; }
+    void constraint(OF c) { hit(c); }
+    void constraint_transition(OF c) { if (row + 1 < n) hit(c); else idx++; }
+    void constraint_first_row(OF c) { if (row == 0) hit(c); else idx++; }
+    void constraint_last_row(OF c) { if (row + 1 == n) hit(c); else idx++; }
+    // index-addressed blocks (the device's reordered evaluators are not used here, but the interface must exist)
+    uint32_t blk_base = 0;
+    void block_begin(uint32_t M) { blk_base = idx; idx += M; }
+    void block_put(uint32_t i, OF c) { if (c.v != 0 && out->size() < 2 * max_out) { out->push_back(row); out->push_back(blk_base + i); } }
+};
+// -> number of violations written (<= max_pairs) as (row, constraint index) pairs; -1 on error
+long orc_check_table_rows(uint32_t table, const uint64_t* trace, size_t ncols, size_t n, const uint64_t labels[4], uint64_t* out_pairs, size_t max_pairs) {
+    try {
+        if (ncols != zkstark::table_num_columns(table)) throw std::runtime_error("trace width does not match the table");
+        std::vector<uint64_t> out;
+        std::vector<uint64_t> lrow(ncols), nrow(ncols);
+        RowCheckConsumer yc;
+        yc.n = n; yc.out = &out; yc.max_out = max_pairs;
+        for (size_t r = 0; r < n; r++) {
+            for (size_t c = 0; c < ncols; c++) { lrow[c] = trace[c * n + r]; nrow[c] = trace[c * n + (r + 1) % n]; }
+            RowOF lv{lrow.data()}, nv{nrow.data()};
+            yc.row = r; yc.idx = 0;
+            zkstark::eval_table<OF>(table, lv, nv, yc, params_from(labels));
+        }
+        size_t k = out.size() / 2 < max_pairs ? out.size() / 2 : max_pairs;
+        if (out_pairs) memcpy(out_pairs, out.data(), 2 * k * 8);
+        return (long)k;
+    } catch (const std::exception& e) { g_orc_err = e.what(); return -1; }
+}
+
 // "stage\tseconds\n" lines accumulated since the last call with reset != 0 (main-thread wall clock of the prover's stages)
 size_t orc_stage_report(char* buf, size_t cap, int reset) {
     std::string out;

@@ -160,6 +160,20 @@ def orc_prove_table(orc, table, cfg, trace, beta_gamma, state, labels=DEFAULT_LA
     return out[:r].copy(), st2
 
 
+def orc_check_table_rows(orc, table, trace, labels=DEFAULT_LABELS, max_pairs=64):
+    """the reference's generator-test pattern: every constraint of the table on every pair of consecutive trace rows ->
+    list of violated (row, constraint index); [] for a valid trace"""
+    t = np.ascontiguousarray(trace, dtype=np.uint64)
+    lab = np.array(labels, dtype=np.uint64)
+    out = np.zeros(2 * max_pairs, dtype=np.uint64)
+    orc.lib.orc_check_table_rows.restype = C.c_long
+    k = orc.lib.orc_check_table_rows(C.c_uint32(table), _ptr(t), C.c_size_t(t.shape[0]), C.c_size_t(t.shape[1]), _ptr(lab), _ptr(out), C.c_size_t(max_pairs))
+    if k < 0:
+        orc.lib.orc_last_error.restype = C.c_char_p
+        raise RuntimeError(orc.lib.orc_last_error().decode())
+    return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(k)]
+
+
 def orc_verify_table(orc, table, cfg, proof, beta_gamma, state, labels=DEFAULT_LABELS):
     lib = orc.lib
     lib.orc_last_error.restype = C.c_char_p

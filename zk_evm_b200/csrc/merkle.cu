@@ -59,6 +59,31 @@ __global__ void __launch_bounds__(128) merkle_level_kernel(const uint64_t* __res
     o[1] = make_ulonglong2(s[2], s[3]);
 }
 
+// The top of the tree in ONE launch: block s finishes cap subtree s from the level that has 2 * blockDim.x of its nodes (or fewer)
+// down to its cap entry.  Small levels are latency-bound — one permutation deep, a handful of warps wide — and there are 7-8 of them
+// per tree and ~54 trees per segment proof: as separate launches they were 557 of a proof's 1136 launches (profiles/r1x).
+struct TailArgs { uint64_t* digests; size_t off[12]; unsigned count0, nlevels; };   // off[l], l = 0 .. nlevels: input level, then outputs
+__global__ void __launch_bounds__(128) merkle_tail_kernel(TailArgs a) {
+    // level k of this subtree: count0 >> k nodes at digests + off[k] + 4 * blockIdx.x * (count0 >> k)
+    for (unsigned k = 1; k <= a.nlevels; k++) {
+        const unsigned cnt = a.count0 >> k;
+        const uint64_t* in = a.digests + a.off[k - 1] + 4 * (size_t)blockIdx.x * (a.count0 >> (k - 1));
+        uint64_t* out = a.digests + a.off[k] + 4 * (size_t)blockIdx.x * cnt;
+        for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const ulonglong2* c = reinterpret_cast<const ulonglong2*>(in + 8 * i);
+            ulonglong2 x = c[0], y = c[1], z = c[2], w = c[3];
+            uint64_t s[12] = {x.x, x.y, y.x, y.y, z.x, z.y, w.x, w.y, 0, 0, 0, 0};
+            pf_permute(s);
+#pragma unroll
+            for (int q = 0; q < 4; q++) s[q] = pf_canon(s[q]);
+            ulonglong2* o = reinterpret_cast<ulonglong2*>(out + 4 * i);
+            o[0] = make_ulonglong2(s[0], s[1]);
+            o[1] = make_ulonglong2(s[2], s[3]);
+        }
+        __syncthreads();      // the level just written is read by other threads of this block only
+    }
+}
+
 __global__ void poseidon_states_kernel(uint64_t* states, size_t count) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
@@ -106,9 +131,22 @@ void merkle_inner_levels(Ctx& c, uint64_t* digests, const std::vector<size_t>& o
     double nodes = 0;
     for (size_t l = 1; l < cnt.size(); l++) nodes += (double)cnt[l];
     KernelScope ks(c, KF_MERKLE_LEVELS, 96.0 * nodes);
-    for (size_t l = 1; l < off.size(); l++) {
-        merkle_level_kernel<<<(unsigned)((cnt[l] + 127) / 128), 128, 0, c.stream>>>(digests + off[l - 1],
-                                                                                     digests + off[l], cnt[l]);
+    const size_t ncap = cnt.back();
+    size_t l = 1;
+    // wide levels: one launch each, one thread per node
+    for (; l < off.size() && cnt[l - 1] / ncap > 256; l++) {
+        merkle_level_kernel<<<(unsigned)((cnt[l] + 127) / 128), 128, 0, c.stream>>>(digests + off[l - 1], digests + off[l], cnt[l]);
+        c.count_launch();
+    }
+    // the rest (each cap subtree has <= 256 nodes on the input level): one launch, one block per cap subtree
+    if (l < off.size()) {
+        TailArgs a;
+        a.digests = digests;
+        a.count0 = (unsigned)(cnt[l - 1] / ncap);
+        a.nlevels = (unsigned)(off.size() - l);
+        ZK_REQUIRE(a.nlevels < 12, "merkle tail: too many levels");
+        for (size_t k = 0; k <= a.nlevels; k++) a.off[k] = off[l - 1 + k];
+        merkle_tail_kernel<<<(unsigned)ncap, 128, 0, c.stream>>>(a);
         c.count_launch();
     }
     c.check_launch("merkle_level_kernel");

@@ -15,6 +15,7 @@
 #include "internal.h"
 #include "ntt.h"
 #include "ntt_tile.cuh"
+#include <stdlib.h>
 
 namespace zk {
 
@@ -28,6 +29,41 @@ template <int THREADS>
 static void launch_pass(dim3 grid, size_t smem, cudaStream_t stream, const PassParams& q, bool inverse) {
     if (inverse) ntt_pass_kernel<THREADS, true><<<grid, THREADS, smem, stream>>>(q);
     else ntt_pass_kernel<THREADS, false><<<grid, THREADS, smem, stream>>>(q);
+}
+
+// ---- the same pass with the tile staged through shared memory by the TMA unit ------------------------------------------------
+// A full tile is 2^12 elements = 256 rows of 16 contiguous elements (128 B): the 2^8 digit values of a strided pass (rows 2^mp
+// elements apart in global memory) or 32 KB of consecutive elements in the final pass.  Thread r asks the TMA unit for row r
+// (`cp.async.bulk.shared::cluster.global`, 128 B, completing on one mbarrier armed with the tile's 32 KB); the tile arrives in shared
+// memory in tile-index order, unpadded (a bulk copy wants 16-byte aligned rows; the first round's reads walk it with consecutive
+// lanes on consecutive words, which needs no padding), and the rounds then run as in ntt_pass_kernel with the padded working tile
+// next to it.  No address arithmetic, no 16 dependent global loads per thread, no registers held across the load latency.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool INV>
+__global__ void __launch_bounds__(256, 3) ntt_pass_tma_kernel(PassParams p) {
+    extern __shared__ __align__(128) uint64_t sm[];
+    uint64_t* stage = sm + NTT_TILE_WORDS + 2;                    // keeps the staging area 16-byte aligned (NTT_TILE_WORDS is even)
+    uint64_t* mbar = sm + NTT_TILE_WORDS;
+    const TileIO io = ntt_tile_io(p, blockIdx.x, blockIdx.y);
+    const uint32_t bar = smem_u32(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8u << NTT_MAX_TILE_LOG) : "memory");
+    {
+        const unsigned row = threadIdx.x;                         // tile indices [16 row, 16 row + 16)
+        const uint64_t* src = io.src + io.gaddr(row << 4);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];"
+                     ::"r"(smem_u32(stage + (row << 4))), "l"(src), "r"(bar) : "memory");
+    }
+    {   // every thread waits for phase 0 of the barrier: all 32 KB have landed
+        asm volatile("{\n\t.reg .pred p;\n\tNTT_TMA_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra NTT_TMA_DONE;\n\tbra NTT_TMA_WAIT;\n\tNTT_TMA_DONE:\n\t}" ::"r"(bar) : "memory");
+    }
+    ntt_pass_rounds<INV>(p, io, sm, threadIdx.x, 256, stage);
 }
 
 // out[j] = c0 * base^j
@@ -178,7 +214,19 @@ void ntt_dif(Ctx& c, const uint64_t* src, size_t src_stride, unsigned src_shift,
             }
             dim3 grid((unsigned)tiles, (unsigned)cnt);
             // one radix-16 item (16 elements) per thread and round
-            if (tile_log >= 12) launch_pass<256>(grid, smem, c.stream, q, inverse);
+            static const bool tma = [] { const char* e = getenv("ZKGPU_NTT_TMA"); return !(e && *e == '0'); }();
+            if (tile_log == NTT_MAX_TILE_LOG && tma && (!q.strided || q.t == NTT_STRIDED_T)) {
+                // full tiles of rows of >= 16 contiguous elements: staged by the TMA unit
+                const size_t smem_tma = 8 * ((size_t)NTT_TILE_WORDS + 2 + (1u << NTT_MAX_TILE_LOG));
+                static bool attr = false;
+                if (!attr) {
+                    ZK_CUDA(cudaFuncSetAttribute(ntt_pass_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+                    ZK_CUDA(cudaFuncSetAttribute(ntt_pass_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tma));
+                    attr = true;
+                }
+                if (inverse) ntt_pass_tma_kernel<true><<<grid, 256, smem_tma, c.stream>>>(q);
+                else ntt_pass_tma_kernel<false><<<grid, 256, smem_tma, c.stream>>>(q);
+            } else if (tile_log >= 12) launch_pass<256>(grid, smem, c.stream, q, inverse);
             else if (tile_log >= 11) launch_pass<128>(grid, smem, c.stream, q, inverse);
             else if (tile_log >= 10) launch_pass<64>(grid, smem, c.stream, q, inverse);
             else launch_pass<32>(grid, smem, c.stream, q, inverse);

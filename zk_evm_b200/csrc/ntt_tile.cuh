@@ -148,7 +148,7 @@ struct TileIO {
 // strided pass, where the 16 lanes of a half-warp still cover one 128-byte row.
 template <int K, bool INV>
 ZK_HD void ntt_round(uint64_t* sm, const uint64_t* __restrict__ roots, int s, unsigned tile_log, unsigned t, unsigned tid, unsigned nthreads,
-                     const TileIO& io, bool from_global, bool to_global) {
+                     const TileIO& io, bool from_global, bool to_global, const uint64_t* stage = nullptr) {
     constexpr int E = 1 << K;
     const int low = s - K + 1;
     const unsigned items = 1u << (tile_log - K);
@@ -158,8 +158,14 @@ ZK_HD void ntt_round(uint64_t* sm, const uint64_t* __restrict__ roots, int s, un
         const unsigned base = ((((hi << K) << low) | lo) << t) + u;
         uint64_t x[E];
         if (from_global) {
+            // `stage`: the tile as the TMA unit laid it down in shared memory (unpadded, tile index order) — see ntt_pass_tma_kernel
+            if (stage) {
 #pragma unroll
-            for (int k = 0; k < E; k++) x[k] = io.src[io.gaddr(base + ((unsigned)k << (low + t)))];
+                for (int k = 0; k < E; k++) x[k] = stage[base + ((unsigned)k << (low + t))];
+            } else {
+#pragma unroll
+                for (int k = 0; k < E; k++) x[k] = io.src[io.gaddr(base + ((unsigned)k << (low + t)))];
+            }
             if (io.prescale) {
 #pragma unroll
                 for (int k = 0; k < E; k++) x[k] = gl_mul(x[k], ntt_ld(io.prescale + io.gaddr(base + ((unsigned)k << (low + t)))));
@@ -204,10 +210,9 @@ ZK_HD void ntt_round(uint64_t* sm, const uint64_t* __restrict__ roots, int s, un
 
 // the whole tile: the rounds of the r-bit digit (first one loading from global memory, last one of a strided pass storing to it),
 // in place: digit position jd ends up holding frequency kd = rev_r(jd)
-template <bool INV>
-ZK_HD void ntt_pass_tile(const PassParams& p, size_t tile, size_t trans, uint64_t* sm, unsigned tid, unsigned nthreads) {
+// where tile `tile` of transform `trans` lives (the TileIO of the pass)
+ZK_HD TileIO ntt_tile_io(const PassParams& p, size_t tile, size_t trans) {
     const unsigned r = p.r, t = p.t, m = p.m;
-    const unsigned tile_log = r + t, tile_elems = 1u << tile_log;
     const unsigned mp = m - r;   // log M'
     TileIO io;
     io.src = p.src + (trans >> p.src_shift) * p.src_stride;
@@ -221,18 +226,28 @@ ZK_HD void ntt_pass_tile(const PassParams& p, size_t tile, size_t trans, uint64_
         io.interpass = p.interpass ? p.interpass + (lo_hi << t) : nullptr;
     } else {
         // final pass (mp == 0): 2^t consecutive sub-transforms of 2^r elements, tile index = u 2^r + jd
-        io.base = tile * (size_t)tile_elems;
+        io.base = tile * ((size_t)1 << (r + t));
         io.interpass = nullptr;
     }
+    return io;
+}
+
+// the whole tile: the rounds of the r-bit digit (first one loading from global memory — or from `stage`, the tile already brought to
+// shared memory by the TMA unit —, last one of a strided pass storing to global memory), in place: digit position jd ends up holding
+// frequency kd = rev_r(jd)
+template <bool INV>
+ZK_HD void ntt_pass_rounds(const PassParams& p, const TileIO& io, uint64_t* sm, unsigned tid, unsigned nthreads, const uint64_t* stage) {
+    const unsigned r = p.r, t = p.t;
+    const unsigned tile_log = r + t, tile_elems = 1u << tile_log;
     const unsigned tt = p.strided ? t : 0;
     int s = (int)r - 1;
     const int first = (r % 4) ? (int)(r % 4) : 4;
     const bool single = first == (int)r;
     const bool last_to_global = p.strided != 0;
-    if (first == 1) ntt_round<1, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, true, single && last_to_global);
-    else if (first == 2) ntt_round<2, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, true, single && last_to_global);
-    else if (first == 3) ntt_round<3, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, true, single && last_to_global);
-    else ntt_round<4, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, true, single && last_to_global);
+    if (first == 1) ntt_round<1, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, true, single && last_to_global, stage);
+    else if (first == 2) ntt_round<2, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, true, single && last_to_global, stage);
+    else if (first == 3) ntt_round<3, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, true, single && last_to_global, stage);
+    else ntt_round<4, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, true, single && last_to_global, stage);
     for (s -= first; s >= 0; s -= 4) {
         NTT_TILE_SYNC();
         ntt_round<4, INV>(sm, p.roots, s, tile_log, tt, tid, nthreads, io, false, s < 4 && last_to_global);
@@ -241,6 +256,12 @@ ZK_HD void ntt_pass_tile(const PassParams& p, size_t tile, size_t trans, uint64_
         NTT_TILE_SYNC();
         for (unsigned e = tid; e < tile_elems; e += nthreads) io.dst[io.base + e] = sm[ntt_pad(e)];
     }
+}
+
+template <bool INV>
+ZK_HD void ntt_pass_tile(const PassParams& p, size_t tile, size_t trans, uint64_t* sm, unsigned tid, unsigned nthreads) {
+    const TileIO io = ntt_tile_io(p, tile, trans);
+    ntt_pass_rounds<INV>(p, io, sm, tid, nthreads, nullptr);
 }
 
 }  // namespace zk
