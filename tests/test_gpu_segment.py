@@ -19,6 +19,18 @@ def _same(ap, want, bg, caps):
             assert np.array_equal(ap.stark_proofs[t], want[t]), "table %s proof differs" % zk.TABLE_NAMES[t]
 
 
+def test_executing_segment_with_32_byte_memory_operations(ctx, oracle):
+    """an executing Cpu program with MLOAD_32BYTES / MSTORE_32BYTES rows, seven tables in use, Cpu -> BytePacking carrying non-zero sums:
+    device proofs == oracle proofs word for word, and the restated verifier (incl. the cross-table-lookup sums) accepts them"""
+    from tests.test_oracle_stark import PACK_PROGRAM, PACK_INPUTS
+    tr, labels = traces.cpu_segment(PACK_PROGRAM, inputs=PACK_INPUTS, log_mem=10)
+    ap = zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, zk.StarkConfig(*STANDARD_FAST), zk.KernelLabels(*labels))
+    want, bg, caps = orc_prove_segment(oracle, STANDARD_FAST, tr, PUBLIC_VALUES, labels=labels)
+    _same(ap, want, bg, caps)
+    ok, err = orc_verify_segment(oracle, STANDARD_FAST, ap.stark_proofs, PUBLIC_VALUES, labels=labels)
+    assert ok, err
+
+
 @pytest.mark.parametrize("cfg", [TEST_CONFIG, STANDARD_FAST])
 def test_valid_segment_matches_oracle_and_verifies(ctx, oracle, cfg):
     tr = traces.valid_segment(seed=11)

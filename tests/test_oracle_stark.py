@@ -2,7 +2,7 @@
 tampered ones.  This is the self-consistency pin for every [UPSTREAM-RECALL] convention."""
 import numpy as np
 import pytest
-from tests import traces
+from tests import traces, oracle_lib
 from tests.oracle_lib import orc_prove_segment, orc_verify_segment, orc_prove_table, orc_verify_table, STANDARD_FAST, TEST_CONFIG, P
 
 BG2 = np.array([0x1111111111, 0x2222222222, 0x3333333333, 0x4444444444], dtype=np.uint64)
@@ -496,3 +496,64 @@ def test_cpu_segment_with_keccak_general_and_prover_input_verifies(oracle):
     proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=labels)
     ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
     assert ok, err
+
+
+# ---- 32-byte memory operations: MLOAD_32BYTES / MSTORE_32BYTES rows, byte_unpacking.rs, and the Cpu -> BytePacking lookup with non-zero sums ----
+PACK_PROGRAM = "IIR" "IIW" "IIV" "IIT" "IIR" "XXXXXJ"
+_ADDR = lambda c, sg, v: v | (sg << 32) | (c << 64)
+PACK_INPUTS = [7, _ADDR(1, 0, 100), 0x1234567890abcdef << 64, _ADDR(0, 2, 50), 0xaabbccddee, _ADDR(0, 2, 200), 0x7f, _ADDR(3, 4, 0), 32, _ADDR(1, 0, 95)]
+
+
+def test_cpu_rows_of_32_byte_memory_operations_satisfy_every_constraint(oracle):
+    """the reference's generator-test pattern (all constraints vanish on consecutive trace rows) on a program with MLOAD_32BYTES and
+    MSTORE_32BYTES_32 / _5 / _1 rows: decode.rs:202-211, stack.rs (two pops, one push), byte_unpacking.rs:11-44 with its filter on"""
+    t = traces.cpu_program_trace(6, PACK_PROGRAM, inputs=PACK_INPUTS)
+    assert oracle_lib.orc_check_table_rows(oracle, traces.T_CPU, t) == []
+    # MSTORE_32BYTES_32 is row 5: the address word it pushes (row 6's cached top) must be the old one + 32 in its virtual limb only
+    for col, what in ((46, "virt advanced by len"), (47, "segment kept"), (48, "context kept"), (49, "upper limbs zero")):
+        bad = t.copy()
+        bad[col, 6] += np.uint64(1)
+        hits = oracle_lib.orc_check_table_rows(oracle, traces.T_CPU, bad)
+        assert hits and hits[0][0] == 5 and hits[0][1] < 8, what      # the byte_unpacking constraints are the first eight of the dispatcher
+    # an MSTORE_32BYTES opcode whose length bits disagree with the advance
+    bad = t.copy()
+    bad[24, 5] = 0                                                   # MSTORE_32BYTES_31 instead of _32
+    assert oracle_lib.orc_check_table_rows(oracle, traces.T_CPU, bad)
+    # the flag on a row whose opcode is neither 0xf8 nor 0xc0..0xdf
+    bad = t.copy()
+    bad[18, 0], bad[15, 0] = 1, 0
+    assert oracle_lib.orc_check_table_rows(oracle, traces.T_CPU, bad)
+
+
+@pytest.mark.parametrize("cfg", [TEST_CONFIG, STANDARD_FAST])
+def test_segment_with_32_byte_memory_operations_verifies(oracle, cfg):
+    """Cpu -> BytePacking (lookup 1) with NON-ZERO sums: two MLOAD_32BYTES (7 and 32 bytes of a code segment, overlapping) and three
+    MSTORE_32BYTES rows ask the BytePacking table for exactly the operations it holds (is_read, address, length, timestamp
+    (clock - 1) * 5 + 1, packed value: cpu_stark.rs:150-223), whose bytes Memory holds (lookup 6): all ten lookups balance"""
+    tr, labels = traces.cpu_segment(PACK_PROGRAM, inputs=PACK_INPUTS, log_mem=10)
+    assert tr[traces.T_BYTE_PACKING] is not None and int(tr[traces.T_BYTE_PACKING][1:33].sum()) == 5
+    for t in (traces.T_CPU, traces.T_BYTE_PACKING, traces.T_MEMORY, traces.T_ARITHMETIC):
+        assert oracle_lib.orc_check_table_rows(oracle, t, tr[t], labels=labels) == []
+    proofs, _, _ = orc_prove_segment(oracle, cfg, tr, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, cfg, proofs, PV37, labels=labels)
+    assert ok, err
+
+
+@pytest.mark.parametrize("what", ["byte", "length", "timestamp", "is_read", "pushed"])
+def test_segment_with_tampered_32_byte_operation_is_rejected(oracle, what):
+    """each field the Cpu row sends to BytePacking is bound by lookup 1"""
+    tr, labels = traces.cpu_segment(PACK_PROGRAM, inputs=PACK_INPUTS, log_mem=10)
+    bp, cpu = tr[traces.T_BYTE_PACKING], tr[traces.T_CPU]
+    if what == "byte":                 # a byte of the first operation in the BytePacking table (and consistently in Memory would still differ from the Cpu's word)
+        bp[37, 0] ^= np.uint64(1)
+    elif what == "length":             # the 7-byte load recorded as 8 bytes
+        bp[7, 0], bp[8, 0] = 0, 1
+    elif what == "timestamp":
+        bp[36, 1] += np.uint64(5)
+    elif what == "is_read":
+        bp[0, 1] = 1
+    else:                              # the word MLOAD_32BYTES pushed (row 3's cached top)
+        cpu[46, 3] ^= np.uint64(2)
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    assert not ok, what

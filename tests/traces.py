@@ -98,13 +98,16 @@ def cpu_padding_trace(log_n, halt_final=0x1234):
     return t
 
 
-def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs=(), log=None, keccak=None):
+def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs=(), log=None, keccak=None, load32=None, store32=None):
     """CpuStark trace with ACTIVE rows: a kernel-mode program that runs into `halt_final`, then the padding rows.
     program: string of  J JUMPDEST 0x5b | P PC 0x58 | 0 PUSH0 0x5f | N NOT 0x19 | X POP 0x50 | Z ISZERO 0x15 | E EQ 0x14 | A ADD 0x01 |
     M MUL 0x02 | S SUB 0x03 | D DIV 0x04 | O MOD 0x06 | L LT 0x10 | G GT 0x11 | B BYTE 0x1a | & AND 0x16 | "|" OR 0x17 | ^ XOR 0x18 |
     a ADDMOD 0x08 | m MULMOD 0x09 | u v w q DUP1 DUP2 DUP3 DUP16 | s t y SWAP1 SWAP2 SWAP16 | j JUMP 0x56 | i JUMPI 0x57 |
     f g h ADDFP254 MULFP254 SUBFP254 0x0c-0x0e | K KECCAK_GENERAL 0x21 | I PROVER_INPUT 0xee (the next word of `inputs`,
-    else a random word) | C GET_CONTEXT 0xf6 | < SHL 0x1b | > SHR 0x1c (displacement on top) | l MLOAD_GENERAL 0xfb | r MSTORE_GENERAL 0xfc (address word = virtual | segment << 32 | context << 64).
+    else a random word) | C GET_CONTEXT 0xf6 | < SHL 0x1b | > SHR 0x1c (displacement on top) | l MLOAD_GENERAL 0xfb | r MSTORE_GENERAL 0xfc (address word = virtual | segment << 32 | context << 64) |
+    R MLOAD_32BYTES 0xf8 (address word on top, length below it; pushes the bytes packed big-endian: load32(address word, length, clock) -> bytes,
+    else random bytes) | W V T MSTORE_32BYTES_32 / _5 / _1 0xdf 0xc4 0xc0 (address word on top, value < 256^n below it; pushes the address
+    word + n; store32(address word, value, n, clock) is told about the write).
     The string is the CODE (instruction c at address halt_final - len + c); execution starts at its first instruction and follows the
     jumps until it reaches halt_final (jump targets are built on the stack from PC values, e.g. "PPS" pushes 1).
     log: a list that receives (instruction, operands..., result) of every arithmetic / logic instruction executed.
@@ -136,6 +139,10 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
     for c, (oc, fl) in {"f": (0x0c, 8), "g": (0x0d, 8), "h": (0x0e, 8), "K": (0x21, 13), "I": (0xee, 15), "l": (0xfb, 20), "r": (0xfc, 20)}.items():   # kernel-only: no gas
         opcode[c], flag[c], cost[c] = oc, fl, 0
     opcode["C"], flag["C"], cost["C"] = 0xf6, 17, 0    # GET_CONTEXT (kernel-only)
+    store_len = {"W": 32, "V": 5, "T": 1}              # MSTORE_32BYTES_n: opcode 0xc0 + n - 1 (decode.rs:206-211), kernel-only: no gas
+    opcode["R"], flag["R"], cost["R"] = 0xf8, 18, 0    # MLOAD_32BYTES
+    for c, ln in store_len.items():
+        opcode[c], flag[c], cost[c] = 0xc0 + ln - 1, 18, 0
     opcode["<"], flag["<"], cost["<"] = 0x1b, 12, 3    # SHL
     opcode[">"], flag[">"], cost[">"] = 0x1c, 12, 3    # SHR
     binary = {"<": lambda a, b: (b << a) & M256 if a < 256 else 0, ">": lambda a, b: b >> a if a < 256 else 0,
@@ -267,7 +274,7 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
             stack.append(inputs.pop(0) if inputs else int.from_bytes(np.random.default_rng(seed + r).bytes(32), "little"))
             if log is not None:
                 log.append(("I", stack[-2] if len(stack) > 1 else 0, stack[-1]))
-        elif ins in "EAMSDOLGB&|^fghK<>":              # two operands: the second one is read through mem_channels[1]
+        elif ins in "EAMSDOLGB&|^fghK<>RWVT":          # two operands: the second one is read through mem_channels[1]
             assert sl >= 2
             a, b = stack.pop(), stack.pop()
             t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2
@@ -280,6 +287,17 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
                 stack.append(int(a == b))
             elif ins == "K" and keccak is not None:    # the digest of the bytes at address word a, length b (callback: the sponge operation)
                 stack.append(keccak(a, b, r + 1))
+            elif ins == "R":                           # MLOAD_32BYTES (operation.rs:893-931): b bytes at address word a, packed big-endian
+                assert 1 <= b <= 32
+                data = load32(a, b, r + 1) if load32 is not None else np.random.default_rng(seed + 2000 + r).bytes(b)
+                assert len(data) == b
+                stack.append(int.from_bytes(data, "big"))
+            elif ins in store_len:                     # MSTORE_32BYTES_n (operation.rs:963-981, byte_unpacking.rs:11-44): pushes the advanced address word
+                ln = store_len[ins]
+                assert b < (1 << (8 * ln)) and (a >> 96) == 0 and (a & 0xFFFFFFFF) + ln < (1 << 32)
+                if store32 is not None:
+                    store32(a, b, ln, r + 1)
+                stack.append(a + ln)
             else:
                 if log is not None:
                     log.append((ins, a, b, binary[ins](a, b)))
@@ -890,7 +908,24 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
         op = (ctx, seg, virt, (clock - 1) * num_channels + 1, data)
         sponge_ops.append(op)
         return int.from_bytes(keccak_sponge_trace(8, [op])[1][0], "big")
-    cpu = cpu_program_trace(log_cpu, program, halt_final=halt_final, log=log, inputs=inputs, keccak=keccak if keccak_inputs is not None else None)
+    packing_ops = list(packing_ops or [])
+    code_bytes = {}                                 # contents of the (pre-initialised) code segments the 32-byte loads read
+
+    def load32(addr_word, length, clock):
+        # MLOAD_32BYTES (cpu_stark.rs:150-172 ctl_data_byte_packing): the Cpu row sends (1, context, segment, virt, len, (clock - 1) * NUM_CHANNELS + 1,
+        # packed value); byte k of the sequence lives at virt + k, the BytePacking row holds them least significant first
+        virt, seg, ctx = [(addr_word >> (32 * i)) & 0xFFFFFFFF for i in range(3)]
+        assert seg == 0, "reads of unwritten memory are only free in a pre-initialised segment (Segment::Code)"
+        data = bytes(code_bytes.setdefault((ctx, seg, virt + k), int(rng.integers(0, 256))) for k in range(length))
+        packing_ops.append((1, ctx, seg, virt, (clock - 1) * num_channels + 1, data[::-1]))
+        return data
+
+    def store32(addr_word, value, ln, clock):
+        # MSTORE_32BYTES_n (cpu_stark.rs:174-223 ctl_data_byte_unpacking): (0, context, segment, virt, len = new offset - virt, timestamp, value)
+        virt, seg, ctx = [(addr_word >> (32 * i)) & 0xFFFFFFFF for i in range(3)]
+        packing_ops.append((0, ctx, seg, virt, (clock - 1) * num_channels + 1, value.to_bytes(ln, "little")))
+    cpu = cpu_program_trace(log_cpu, program, halt_final=halt_final, log=log, inputs=inputs, keccak=keccak if keccak_inputs is not None else None,
+                            load32=load32, store32=store32)
     limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
     NUM_CHANNELS = num_channels                     # 5 in the reference; the parameter exists for the negative test
     ops = []                                        # (ctx, seg, virt, timestamp, is_read, filter, value limbs)
@@ -932,8 +967,9 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
         keccak, _ = keccak_trace(max(5, (24 * nrows - 1).bit_length()), np.array(lanes, dtype=np.uint64), np.array(stamps, dtype=np.uint64))
     packing = None
     if packing_ops:
-        # BytePacking operations nobody asked for either (lookup 1, Cpu -> BytePacking, stays unbalanced): byte i of a sequence of length L
-        # lives at virt + L - 1 - i (byte_packing_stark.rs:105-148)
+        # BytePacking operations: the ones the Cpu's MLOAD_32BYTES / MSTORE_32BYTES rows ask for (load32 / store32 above: lookup 1, Cpu ->
+        # BytePacking, balances for these) and hand-placed ones nobody asked for (`packing_ops` argument: lookup 1 stays open): byte i of a
+        # sequence of length L lives at virt + L - 1 - i (byte_packing_stark.rs:105-148)
         packing = np.zeros((71, 256), dtype=np.uint64)
         for j, (is_read, ctx, seg, virt, t_, data) in enumerate(packing_ops):
             L = len(data)
