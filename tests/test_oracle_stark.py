@@ -557,3 +557,54 @@ def test_segment_with_tampered_32_byte_operation_is_rejected(oracle, what):
     proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=labels)
     ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
     assert not ok, what
+
+
+# ---- syscall, exception and EXIT_KERNEL rows (syscalls_exceptions.rs:23-134, jumps.rs:13-65) ----------------------------------------
+SYS_PROGRAM = "P" "YNJ" "X" "xNNJ" "X" "X" "I" "eNNJ" "J"
+
+
+def _sys_inputs(halt_final):
+    base = halt_final - len(SYS_PROGRAM)
+    return [(base + SYS_PROGRAM.index("e") + 3) | (1 << 32) | (77 << 192)]      # kexit_info: continue at the J after "eNN", kernel mode, gas 77
+
+
+def test_cpu_rows_of_syscall_exception_and_exit_kernel_satisfy_every_constraint(oracle):
+    t = traces.cpu_program_trace(6, SYS_PROGRAM, inputs=_sys_inputs(0x1234))
+    assert oracle_lib.orc_check_table_rows(oracle, traces.T_CPU, t) == []
+    rows = {c: SYS_PROGRAM.index(c) - (0 if c == "Y" else 1 if c == "x" else 3) for c in "Yxe"}   # executed-row index: skipped instructions do not run
+    ry, rx, re = 1, 4, 9
+    assert [int(t[22, ry]), int(t[23, rx]), int(t[19, re])] == [1, 1, 1], rows
+    # after the syscall: kernel mode, gas 0, pc = handler, kexit_info on top = (pc + 1, kernel flag, 0.., gas, 0)
+    assert int(t[5, ry + 1]) == 0 and int(t[47, ry + 1]) == 1 and int(t[52, ry + 1]) == int(t[5, ry]) and int(t[46, ry + 1]) == int(t[2, ry]) + 1
+    # the exception records pc, not pc + 1
+    assert int(t[46, rx + 1]) == int(t[2, rx])
+    # EXIT_KERNEL restores the gas of its kexit_info
+    assert int(t[5, re + 1]) == 77
+    for (row, col, what) in ((ry + 1, 2, "pc after the syscall is the handler"), (ry + 1, 5, "gas after the syscall is 0"), (ry + 1, 46, "kexit_info.pc"),
+                             (ry + 1, 52, "kexit_info.gas"), (ry, 58, "jump-table address"), (rx, 58, "exception jump-table address"),
+                             (rx, 32, "exception code bit"), (re + 1, 2, "pc after EXIT_KERNEL"), (re + 1, 5, "gas after EXIT_KERNEL"),
+                             (ry, 54, "the jump-table channel is not a bus access")):
+        bad = t.copy()
+        bad[col, row] += np.uint64(1)
+        assert oracle_lib.orc_check_table_rows(oracle, traces.T_CPU, bad), what
+
+
+def test_segment_with_syscall_exception_and_exit_kernel_verifies(oracle):
+    """the handler addresses are read from the kernel's jump tables through BytePacking (Cpu -> BytePacking's jumptable entries,
+    cpu_stark.rs:225-262, carry non-zero sums), the pushed kexit_info words are range-checked by Arithmetic rows (operation.rs:777-790)"""
+    hf = len(SYS_PROGRAM) + 8
+    tr, labels = traces.cpu_segment(SYS_PROGRAM, inputs=_sys_inputs(hf), log_mem=15)
+    assert labels[0] == hf and int(tr[traces.T_BYTE_PACKING][3].sum()) == 2                  # two 3-byte reads
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    assert ok, err
+    # the handler the Cpu row jumps to is bound to the jump-table bytes: another handler byte in BytePacking (consistently in Memory) breaks lookup 1
+    bad = [None if t is None else t.copy() for t in tr]
+    bad[traces.T_BYTE_PACKING][37, 0] ^= np.uint64(1)
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, bad, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    assert not ok
+    # a proof made for other jump-table labels does not verify against these
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=(labels[0], labels[1], labels[2] + 3, labels[3]))
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    assert not ok

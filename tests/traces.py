@@ -98,7 +98,8 @@ def cpu_padding_trace(log_n, halt_final=0x1234):
     return t
 
 
-def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs=(), log=None, keccak=None, load32=None, store32=None):
+def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs=(), log=None, keccak=None, load32=None, store32=None,
+                      syscall_jumptable=0x4000, exception_jumptable=0x5000, jumptable=None):
     """CpuStark trace with ACTIVE rows: a kernel-mode program that runs into `halt_final`, then the padding rows.
     program: string of  J JUMPDEST 0x5b | P PC 0x58 | 0 PUSH0 0x5f | N NOT 0x19 | X POP 0x50 | Z ISZERO 0x15 | E EQ 0x14 | A ADD 0x01 |
     M MUL 0x02 | S SUB 0x03 | D DIV 0x04 | O MOD 0x06 | L LT 0x10 | G GT 0x11 | B BYTE 0x1a | & AND 0x16 | "|" OR 0x17 | ^ XOR 0x18 |
@@ -107,7 +108,12 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
     else a random word) | C GET_CONTEXT 0xf6 | < SHL 0x1b | > SHR 0x1c (displacement on top) | l MLOAD_GENERAL 0xfb | r MSTORE_GENERAL 0xfc (address word = virtual | segment << 32 | context << 64) |
     R MLOAD_32BYTES 0xf8 (address word on top, length below it; pushes the bytes packed big-endian: load32(address word, length, clock) -> bytes,
     else random bytes) | W V T MSTORE_32BYTES_32 / _5 / _1 0xdf 0xc4 0xc0 (address word on top, value < 256^n below it; pushes the address
-    word + n; store32(address word, value, n, clock) is told about the write).
+    word + n; store32(address word, value, n, clock) is told about the write) |
+    e EXIT_KERNEL 0xf9 (pops kexit_info = pc | kernel flag << 32 | gas << 192; this model stays in kernel mode) |
+    Y a SYSCALL row (opcode 0x20) and x an EXCEPTION row (exc_stop, code 6 — the one exception a kernel-mode row may raise; faulting opcode
+    0xfe): both read their handler address from the jump table (3 bytes at syscall_jumptable + 3 opcode / exception_jumptable + 3 code,
+    through BytePacking: jumptable(virt, handler, clock) is told), push kexit_info and continue at the handler = the first JUMPDEST at
+    least two instructions further on, in kernel mode with gas 0.
     The string is the CODE (instruction c at address halt_final - len + c); execution starts at its first instruction and follows the
     jumps until it reaches halt_final (jump targets are built on the stack from PC values, e.g. "PPS" pushes 1).
     log: a list that receives (instruction, operands..., result) of every arithmetic / logic instruction executed.
@@ -140,6 +146,9 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
         opcode[c], flag[c], cost[c] = oc, fl, 0
     opcode["C"], flag["C"], cost["C"] = 0xf6, 17, 0    # GET_CONTEXT (kernel-only)
     store_len = {"W": 32, "V": 5, "T": 1}              # MSTORE_32BYTES_n: opcode 0xc0 + n - 1 (decode.rs:206-211), kernel-only: no gas
+    opcode["e"], flag["e"], cost["e"] = 0xf9, 19, 0    # EXIT_KERNEL
+    opcode["Y"], flag["Y"], cost["Y"] = 0x20, 22, 0    # a syscall opcode (decode.rs does not constrain which: the handler checks)
+    opcode["x"], flag["x"], cost["x"] = 0xfe, 23, 0    # exception raised at an invalid opcode
     opcode["R"], flag["R"], cost["R"] = 0xf8, 18, 0    # MLOAD_32BYTES
     for c, ln in store_len.items():
         opcode[c], flag[c], cost[c] = 0xc0 + ln - 1, 18, 0
@@ -241,6 +250,34 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
             stack.append(0 if c == 0 else ((a + b) % c if ins == "a" else (a * b) % c))
             if log is not None:
                 log.append((ins, a, b, c, stack[-1]))
+        elif ins == "e":                               # EXIT_KERNEL (jumps.rs:13-65): pc, kernel flag and gas come from the popped kexit_info
+            assert sl >= 1
+            info = limbs(stack.pop())
+            assert info[1] == 1 and info[7] == 0, "this model stays in kernel mode"
+            aux = int(sl != 1)
+            t[36, r], t[37, r] = (pow(sl - 1, P - 2, P) if aux else 0), aux
+            read_top_next = bool(aux)
+            next_pc, gas = info[0], info[6]
+        elif ins in "Yx":                              # syscalls_exceptions.rs:23-134 (operation.rs:735-810, 983-1080)
+            code = 6 if ins == "x" else None           # exc_stop
+            virt = (exception_jumptable + 3 * code) if ins == "x" else (syscall_jumptable + 3 * opcode[ins])
+            handler = next(base + i for i in range(pc - base + 2, k) if program[i] == "J")
+            if ins == "x":
+                for b in range(3):
+                    t[32 + b, r] = (code >> b) & 1     # general.exception().exc_code_bits
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 0, 1, 0, 0, virt      # the jump-table channel: described, not used (BytePacking reads it)
+            t[59, r] = handler
+            old_top = stack[-1] if stack else 0
+            if sl > 0:                                 # push: the old top goes to memory through the partial channel
+                t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, 0, 1, sl - 1
+                t[36, r], t[37, r] = pow(sl, P - 2, P), 1
+            info = (pc + 1 if ins == "Y" else pc) | (1 << 32) | (gas << 192)
+            stack.append(info)
+            if jumptable is not None:
+                jumptable(virt, handler, r + 1)
+            if log is not None:
+                log.append((ins, opcode[ins], old_top, handler, info))
+            next_pc, gas = handler, 0
         elif ins == "C":                               # GET_CONTEXT (contextops.rs:82-102, 277-301): pushes context << 64; the old top goes out through channel 2
             if sl > 0:
                 t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 0, 0, 1, sl - 1
@@ -924,8 +961,12 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
         # MSTORE_32BYTES_n (cpu_stark.rs:174-223 ctl_data_byte_unpacking): (0, context, segment, virt, len = new offset - virt, timestamp, value)
         virt, seg, ctx = [(addr_word >> (32 * i)) & 0xFFFFFFFF for i in range(3)]
         packing_ops.append((0, ctx, seg, virt, (clock - 1) * num_channels + 1, value.to_bytes(ln, "little")))
+    def jumptable(virt, handler, clock):
+        # syscall / exception rows (cpu_stark.rs:225-262 ctl_data_jumptable_read): (1, 0, Segment::Code, virt, 3, timestamp, handler address);
+        # the three bytes are the kernel's jump-table entry, big-endian (a pre-initialised segment: any content is admissible)
+        packing_ops.append((1, 0, 0, virt, (clock - 1) * num_channels + 1, handler.to_bytes(3, "little")))
     cpu = cpu_program_trace(log_cpu, program, halt_final=halt_final, log=log, inputs=inputs, keccak=keccak if keccak_inputs is not None else None,
-                            load32=load32, store32=store32)
+                            load32=load32, store32=store32, syscall_jumptable=labels[2], exception_jumptable=labels[3], jumptable=jumptable)
     limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
     NUM_CHANNELS = num_channels                     # 5 in the reference; the parameter exists for the negative test
     ops = []                                        # (ctx, seg, virt, timestamp, is_read, filter, value limbs)
@@ -1014,6 +1055,10 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
         elif e[0] == "I":                              # PROVER_INPUT is range-checked by the Arithmetic table (arithmetic/mod.rs:343-359)
             arith[16, r], arith[17, r] = 1, 0xee       # IS_RANGE_CHECK, OPCODE_COL
             arith[18:34, r], arith[66:82, r] = _limbs(e[1]), _limbs(e[2])
+            r += 1
+        elif e[0] in "Yx":                             # syscall / exception rows are range-checked too (operation.rs:777-790): opcode, stack top, handler, 0 -> kexit_info
+            arith[16, r], arith[17, r] = 1, e[1]
+            arith[18:34, r], arith[34:50, r], arith[66:82, r] = _limbs(e[2]), _limbs(e[3]), _limbs(e[4])
             r += 1
         elif e[0] in "ASLG":                           # addcy.rs: ADD in0 + in1 = out + cy 2^256; SUB / LT / GT by rearranging it
             a, b, M = e[1], e[2], 1 << 256
