@@ -608,3 +608,100 @@ def test_segment_with_syscall_exception_and_exit_kernel_verifies(oracle):
     proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=(labels[0], labels[1], labels[2] + 3, labels[3]))
     ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
     assert not ok
+
+
+# ---- SET_CONTEXT and context pruning (contextops.rs:150-215, cpu_stark.rs:391-431, all_stark.rs ctl_context_pruning) ---------------------
+CTX_PROGRAM = "PP" "Ic" "PCP" "Ic" "XXJ"          # context 0 -> fresh context 5 -> back to 0, pruning 5
+CTX_INPUTS = [5 << 64, (0 << 64) | 1]
+
+
+def test_cpu_rows_of_set_context_satisfy_every_constraint(oracle):
+    stale = []
+    t = traces.cpu_program_trace(6, CTX_PROGRAM, inputs=CTX_INPUTS, stale=stale)
+    assert stale == [5] and [int(x) for x in t[0, :11]] == [0, 0, 0, 0, 5, 5, 5, 5, 5, 0, 0]
+    assert [int(x) for x in t[3, :11]] == [0, 1, 2, 3, 0, 1, 2, 3, 4, 2, 1]        # every context resumes with the stack it was left with
+    assert oracle_lib.orc_check_table_rows(oracle, traces.T_CPU, t) == []
+    # GET_CONTEXT in context 5 pushed 5 << 64 (row 6 -> cached top of row 7)
+    assert int(t[48, 6]) == 5 and int(t[46, 6]) == 0
+    for row, col, what in ((4, 0, "the context after SET_CONTEXT is the popped one"), (8, 32, "pruning flag = low limb of the popped word"),
+                           (9, 46, "the top handed over by channel 2 is the next row's cached top"), (8, 71, "new top read at new_sp - 1"),
+                           (8, 69, "new top read in the new context"), (3, 38, "stack_inv_aux_2"), (6, 48, "GET_CONTEXT pushes the context")):
+        bad = t.copy()
+        bad[col, row] += np.uint64(1)
+        assert oracle_lib.orc_check_table_rows(oracle, traces.T_CPU, bad), what
+
+
+def test_segment_with_set_context_and_pruning_verifies(oracle):
+    """the stack pointers saved in / restored from the ContextMetadata::StackSize cells are Memory operations that only the SET_CONTEXT
+    lookups send (cpu_stark.rs:391-431), and the pruned context is one the Memory table lists as stale (context pruning lookup with a
+    non-zero sum; its cells do not reach MemAfter)"""
+    tr, labels = traces.cpu_segment(CTX_PROGRAM, inputs=CTX_INPUTS, log_mem=10)
+    m = tr[traces.T_MEMORY]
+    assert int(m[22].sum()) == 1 and int(m[21, 5]) == 6 and int(m[24].sum()) > 0       # one stale context: 5
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    assert ok, err
+    # the Cpu prunes a context the Memory table does not list (and the other way round): the pruning lookup fails
+    unlisted = [None if t is None else t.copy() for t in tr]
+    unlisted[traces.T_CPU][32, 8] = 0
+    unlisted[traces.T_CPU][46, 8] = 0                       # keep the Cpu table itself consistent: flag = low limb of the popped word
+    assert oracle_lib.orc_check_table_rows(oracle, traces.T_CPU, unlisted[traces.T_CPU], labels=labels) == []
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, unlisted, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    # lookup 9 is the context pruning one; 0 fails too: the changed word is also what PROVER_INPUT's range-check row recorded
+    assert not ok and err.endswith("failing lookups: 0 9"), err
+    # without pruning the same program verifies with an empty stale list
+    tr0, labels0 = traces.cpu_segment(CTX_PROGRAM, inputs=[5 << 64, 0], log_mem=10)
+    assert int(tr0[traces.T_MEMORY][22].sum()) == 0
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr0, PV37, labels=labels0)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels0)
+    assert ok, err
+    # a restored stack pointer that is not the saved one
+    wrong = [None if t is None else t.copy() for t in tr]
+    wrong[traces.T_CPU][3, 9:] += np.uint64(1)
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, wrong, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    assert not ok
+
+
+# ---- a user-mode excursion: EXIT_KERNEL to user mode, PUSH read through BytePacking, syscall back (cpu_stark.rs:264-304) -----------------
+USER_PROGRAM = "P" "I" "e" "p.." "X" "Y" "N" "J" "X" "X" "J"
+
+
+def _user_inputs(halt_final):
+    base = halt_final - len(USER_PROGRAM)
+    return [(base + USER_PROGRAM.index("p")) | (0 << 32) | (1000 << 192)]       # kexit_info: pc of the PUSH2, USER mode, gas 1000
+
+
+def test_cpu_rows_of_a_user_mode_excursion_satisfy_every_constraint(oracle):
+    t = traces.cpu_program_trace(6, USER_PROGRAM, inputs=_user_inputs(0x1234))
+    assert oracle_lib.orc_check_table_rows(oracle, traces.T_CPU, t) == []
+    assert [int(x) for x in t[4, :8]] == [1, 1, 1, 0, 0, 0, 1, 1]               # kernel, kernel, EXIT_KERNEL | PUSH2, POP, syscall | handler ...
+    assert int(t[32, 3]) == 1 and int(t[5, 4]) - int(t[5, 3]) == 3              # is_not_kernel on the user-mode PUSH; it costs G_VERYLOW
+    assert int(t[2, 4]) - int(t[2, 3]) == 3                                      # and skips its two immediate bytes
+    assert int(t[47, 6]) == 0 and int(t[52, 6]) == 1005                          # the syscall's kexit_info: user mode, the gas used so far
+    for row, col, what in ((3, 32, "is_not_kernel = 1 - is_kernel_mode"), (3, 39, "stack bound check of a user-mode push"), (2, 39, "... and of EXIT_KERNEL"),
+                           (3, 4, "kernel flag after EXIT_KERNEL comes from kexit_info"), (3, 1, "code context = context in user mode"), (6, 4, "a syscall enters kernel mode"),
+                           (6, 47, "kexit_info records the mode the syscall came from")):
+        bad = t.copy()
+        bad[col, row] += np.uint64(1)
+        assert oracle_lib.orc_check_table_rows(oracle, traces.T_CPU, bad), what
+
+
+def test_segment_with_a_user_mode_push_verifies(oracle):
+    """the last Cpu -> BytePacking entry with a non-zero sum: the word a user-mode PUSH2 pushes is the big-endian packing of the two code
+    bytes after it, read by the BytePacking table at (code context, Segment::Code, pc + 1)"""
+    hf = len(USER_PROGRAM) + 8
+    tr, labels = traces.cpu_segment(USER_PROGRAM, inputs=_user_inputs(hf), log_mem=15)
+    bp = tr[traces.T_BYTE_PACKING]
+    assert int(bp[2].sum()) == 1 and int(bp[3].sum()) == 1                       # one 2-byte read (the PUSH), one 3-byte read (the jump table)
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, tr, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    assert ok, err
+    # the pushed word is bound to the code bytes: change it on the Cpu side only (row 4's cached top; POP discards it, nothing else sees it)
+    bad = [None if t is None else t.copy() for t in tr]
+    bad[traces.T_CPU][46, 4] ^= np.uint64(1)
+    assert oracle_lib.orc_check_table_rows(oracle, traces.T_CPU, bad[traces.T_CPU], labels=labels) == []
+    proofs, _, _ = orc_prove_segment(oracle, TEST_CONFIG, bad, PV37, labels=labels)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, proofs, PV37, labels=labels)
+    assert not ok and err.endswith("failing lookups: 1"), err

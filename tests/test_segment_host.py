@@ -78,6 +78,54 @@ class OracleBackend:
         return orc_prove_table(self.orc, table, self.cfg, trace, bg, state, forced_pow=forced_pow)
 
 
+class OracleSplitCommit:
+    """test double for zk_evm_b200.SplitCommit: the same three steps (column slice through ifft + LDE and all-gather; leaf block + Merkle
+    levels under the rank's cap entries and all-gather; assembly on the owner) computed with the oracle's primitives and exchanged over
+    gloo, so that the split branch of prove_with_traces_sharded — ordering of the collectives, slicing, block layout — runs without a GPU"""
+
+    def __init__(self, backend, comm, table, trace):
+        self.be, self.comm, self.table, self.trace = backend, comm, table, np.ascontiguousarray(trace)
+        orc, k, r = backend.orc, comm.world, comm.rank
+        ncols, n = self.trace.shape
+        self.ncols, self.n, self.N = ncols, n, 2 * n
+        cpr = -(-ncols // k)
+        c0, c1 = min(ncols, r * cpr), min(ncols, (r + 1) * cpr)
+        slot = np.zeros((cpr, self.N), dtype=np.uint64)
+        if c1 > c0:
+            coef = orc.ntt(self.trace[c0:c1], 1)                                    # ifft
+            padded = np.concatenate([coef, np.zeros_like(coef)], axis=1)
+            lde = orc.ntt(padded, 2, oracle_lib.GENERATOR)                          # coset fft on g <w_2n>, natural order
+            lg = self.N.bit_length() - 1
+            rev = np.array([int(("{:0%db}" % lg).format(j)[::-1], 2) for j in range(self.N)])
+            slot[:c1 - c0] = lde[:, rev]                                            # rows in bit-reversed order, as the leaves are
+        self.lde = comm.all_gather(slot).reshape(k * cpr, self.N)[:ncols]
+
+    def hash_block(self):
+        orc, k, r = self.be.orc, self.comm.world, self.comm.rank
+        per = self.N // k
+        level = orc.hash_rows_colmajor(np.ascontiguousarray(self.lde[:, r * per:(r + 1) * per]))   # (per, 4) leaf digests of the block
+        packed = [level]
+        while per * k > 16:                                                          # down to the cap level (cap_height 4)
+            level = np.array([orc.two_to_one(level[2 * i], level[2 * i + 1]) for i in range(len(level) // 2)], dtype=np.uint64).reshape(-1, 4)
+            packed.append(level)
+            per //= 2
+        self.sizes = [len(l) for l in packed]
+        self.packed = self.comm.all_gather(np.concatenate(packed))                  # (k, sum of the block's level sizes, 4)
+
+    def finish(self, is_owner):
+        if not is_owner:
+            return None
+        # the cap = last level of every block, block after block; must be the cap of the one-device commitment
+        off = sum(self.sizes[:-1])
+        cap = np.concatenate([self.packed[b, off:off + self.sizes[-1]] for b in range(self.comm.world)])
+        want = self.be.orc.commit(self.trace, self.be.cfg[2], self.be.cfg[3])[3]
+        assert np.array_equal(cap.reshape(-1, 4), want.reshape(-1, 4)), "split commitment of table %d: cap differs" % self.table
+        return (self.table, self.trace)
+
+
+OracleBackend.split_commit = lambda self, comm, table, trace: OracleSplitCommit(self, comm, table, trace)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -99,6 +147,58 @@ def _worker(rank, world, port, q):
         q.put((rank, ap.stark_proofs, ap.ctl_challenges, owner))
     finally:
         dist.destroy_process_group()
+
+
+def _worker_split(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tr = traces.valid_segment(seed=3)
+        in_use = [t is not None for t in tr]
+        log_ns = [None if t is None else t.shape[1].bit_length() - 1 for t in tr]
+        plan = zk.shard_plan(world, log_ns, split_min_bytes=8 * 12 * 128)          # Memory and Cpu are split, the small tables are not
+        local = [t if (t is not None and plan.needs(rank)[i]) else None for i, t in enumerate(tr)]
+        ap = zk.prove_with_traces_sharded(OracleBackend(TEST_CONFIG), zk.TorchComm(), local, in_use, PUBLIC_VALUES, plan=plan)
+        q.put((rank, ap.stark_proofs, ap.ctl_challenges, plan.describe()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_prove_with_split_commitments_two_ranks_gloo(oracle):
+    """the table-sharded layout WITH split trace commitments (ShardPlan.split) on two gloo ranks: proofs == the single-process proofs"""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_split, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=900) for _ in range(world)]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want, bg, _ = orc_prove_segment(oracle, TEST_CONFIG, traces.valid_segment(seed=3), PUBLIC_VALUES)
+    assert len(res[0][3]["split_over_all_gpus"]) >= 2 and len(set(res[0][3]["owner"])) == 2
+    for rank, proofs, ctl_ch, _ in res:
+        assert np.array_equal(ctl_ch, bg)
+        for t in range(9):
+            assert (proofs[t] is None) == (want[t] is None)
+            if want[t] is not None:
+                assert np.array_equal(proofs[t], want[t]), "rank %d table %d differs from the single-process proof" % (rank, t)
+
+
+def test_shard_plan_properties():
+    import bench
+    for w in (1, 2, 4, 8):
+        plan = zk.shard_plan(w, bench.SEGMENT_LOG_NS)
+        assert len(plan.owner) == 9 and set(plan.owner) <= set(range(w))
+        assert (w == 1 and not any(plan.split)) or (w > 1 and plan.split[3] and plan.split[6] and not plan.split[1])   # Keccak, Memory split; BytePacking not
+        for r in range(w):
+            need = plan.needs(r)
+            assert all(need[t] == (plan.split[t] or plan.owner[t] == r) for t in range(9))
+    # an optional table that is not in use is nobody's
+    plan = zk.shard_plan(4, [16, None, 16, None, None, None, 18, 16, None])
+    assert plan.needs(0)[1] is False and not plan.split[1]
 
 
 def test_sharded_prove_two_ranks_gloo(oracle):

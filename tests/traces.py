@@ -99,7 +99,7 @@ def cpu_padding_trace(log_n, halt_final=0x1234):
 
 
 def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs=(), log=None, keccak=None, load32=None, store32=None,
-                      syscall_jumptable=0x4000, exception_jumptable=0x5000, jumptable=None):
+                      syscall_jumptable=0x4000, exception_jumptable=0x5000, jumptable=None, stale=None, push32=None):
     """CpuStark trace with ACTIVE rows: a kernel-mode program that runs into `halt_final`, then the padding rows.
     program: string of  J JUMPDEST 0x5b | P PC 0x58 | 0 PUSH0 0x5f | N NOT 0x19 | X POP 0x50 | Z ISZERO 0x15 | E EQ 0x14 | A ADD 0x01 |
     M MUL 0x02 | S SUB 0x03 | D DIV 0x04 | O MOD 0x06 | L LT 0x10 | G GT 0x11 | B BYTE 0x1a | & AND 0x16 | "|" OR 0x17 | ^ XOR 0x18 |
@@ -113,7 +113,13 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
     Y a SYSCALL row (opcode 0x20) and x an EXCEPTION row (exc_stop, code 6 — the one exception a kernel-mode row may raise; faulting opcode
     0xfe): both read their handler address from the jump table (3 bytes at syscall_jumptable + 3 opcode / exception_jumptable + 3 code,
     through BytePacking: jumptable(virt, handler, clock) is told), push kexit_info and continue at the handler = the first JUMPDEST at
-    least two instructions further on, in kernel mode with gas 0.
+    least two instructions further on, in kernel mode with gas 0. |
+    c SET_CONTEXT 0xf7 (contextops.rs:150-215, operation.rs:371-454): pops new context << 64 | pruning flag; every context has its own stack,
+    whose length is kept in its ContextMetadata::StackSize cell while another context runs; `stale` (a list) receives the pruned contexts. |
+    p.. PUSH2 0x61 with its two immediate bytes (the two characters after it are never executed; their values are drawn from the seed).
+    USER MODE: an EXIT_KERNEL whose kexit_info has kernel flag 0 leaves kernel mode; there p, X, N, J and Y may run (the code is read from
+    (context, Segment::Code), a user-mode PUSH reads its immediate through BytePacking — push32(code context, address, bytes, clock) is
+    told —, pushes are bounds-checked against MAX_USER_STACK_SIZE) until a syscall row Y brings the kernel back.
     The string is the CODE (instruction c at address halt_final - len + c); execution starts at its first instruction and follows the
     jumps until it reaches halt_final (jump targets are built on the stack from PC values, e.g. "PPS" pushes 1).
     log: a list that receives (instruction, operands..., result) of every arithmetic / logic instruction executed.
@@ -128,7 +134,7 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
     assert 0 < k < n
     M256 = (1 << 256) - 1
     t = np.zeros((85, n), dtype=np.uint64)
-    t[4] = 1                                           # is_kernel_mode
+    t[4] = 1                                           # is_kernel_mode (the executed rows set their own below)
     t[40] = np.arange(1, n + 1, dtype=np.uint64)       # clock
     opcode = {"J": 0x5b, "P": 0x58, "0": 0x5f, "N": 0x19, "X": 0x50, "Z": 0x15, "E": 0x14, "A": 0x01, "M": 0x02,
               "S": 0x03, "D": 0x04, "O": 0x06, "L": 0x10, "G": 0x11, "B": 0x1a, "&": 0x16, "|": 0x17, "^": 0x18, "a": 0x08, "m": 0x09,
@@ -146,6 +152,8 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
         opcode[c], flag[c], cost[c] = oc, fl, 0
     opcode["C"], flag["C"], cost["C"] = 0xf6, 17, 0    # GET_CONTEXT (kernel-only)
     store_len = {"W": 32, "V": 5, "T": 1}              # MSTORE_32BYTES_n: opcode 0xc0 + n - 1 (decode.rs:206-211), kernel-only: no gas
+    opcode["p"], flag["p"], cost["p"] = 0x61, 15, 3    # PUSH2 (gas.rs:121-125: G_VERYLOW)
+    opcode["c"], flag["c"], cost["c"] = 0xf7, 17, 0    # SET_CONTEXT
     opcode["e"], flag["e"], cost["e"] = 0xf9, 19, 0    # EXIT_KERNEL
     opcode["Y"], flag["Y"], cost["Y"] = 0x20, 22, 0    # a syscall opcode (decode.rs does not constrain which: the handler checks)
     opcode["x"], flag["x"], cost["x"] = 0xfe, 23, 0    # exception raised at an invalid opcode
@@ -163,7 +171,9 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
     limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
     inputs = list(inputs)                              # words PROVER_INPUT supplies, in order (random words once exhausted)
     base = halt_final - k                              # the program occupies the addresses base .. halt_final - 1
-    pc, gas, stack = base, gas0, []
+    pc, gas, ctx, kernel = base, gas0, 0, 1
+    stacks, saved_sp = {0: []}, {}                     # per context: the stack, and the StackSize cell written when the context was left
+    stack = stacks[0]
     read_top_next = False                              # the previous instruction was a POP / JUMP / JUMPI that left a non-empty stack
     r = -1
     while pc != halt_final:
@@ -172,18 +182,32 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
         ins = program[pc - base]
         next_pc = pc + 1
         sl = len(stack)
-        t[2, r], t[3, r], t[5, r] = pc, sl, gas
+        t[0, r], t[1, r], t[2, r], t[3, r], t[4, r], t[5, r] = ctx, (1 - kernel) * ctx, pc, sl, kernel, gas
+        assert kernel or ins in "pXNJY", "instruction %r is not modelled in user mode" % ins
+        next_kernel = kernel
         if stack:
             t[46:54, r] = limbs(stack[-1])             # mem_channels[0].value: the cached top of the stack
         if read_top_next:                              # ... read from memory at the start of this row (stack.rs:371-386)
-            t[41, r], t[42, r], t[43, r], t[44, r], t[45, r] = 1, 1, 0, 1, sl - 1
+            t[41, r], t[42, r], t[43, r], t[44, r], t[45, r] = 1, 1, ctx, 1, sl - 1
             read_top_next = False
         for b in range(8):
             t[24 + b, r] = (opcode[ins] >> b) & 1      # opcode_bits, little endian
         t[flag[ins], r] = 1
-        if ins in "P0":                                # push only
+        if ins == "p":                                 # PUSH2: is_not_kernel, the immediate, the bounds check of a user-mode push
+            imm = bytes(int(x) for x in np.random.default_rng(seed + 3000 + r).integers(0, 256, size=2))
+            t[32, r] = 1 - kernel                      # general.push().is_not_kernel (control_flow.rs:88-90)
+            if sl > 0:
+                t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, ctx, 1, sl - 1
+                t[36, r], t[37, r] = pow(sl, P - 2, P), 1
+            if not kernel:
+                t[39, r] = pow((sl + 1 - 1025) % P, P - 2, P)                               # stack_len_bounds_aux (stack.rs:328-333)
+                if push32 is not None:
+                    push32((1 - kernel) * ctx, pc + 1, imm, r + 1)
+            stack.append(int.from_bytes(imm, "big"))
+            next_pc = pc + 3
+        elif ins in "P0":                              # push only
             if sl > 0:                                 # the old top goes to memory through the partial channel
-                t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, 0, 1, sl - 1
+                t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, ctx, 1, sl - 1
                 t[36, r], t[37, r] = pow(sl, P - 2, P), 1                                   # general.stack(): stack_inv, stack_inv_aux
             stack.append(pc if ins == "P" else 0)
         elif ins in "NX":                              # not_pop: stack_inv / stack_inv_aux refer to stack_len - 1
@@ -212,13 +236,13 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
                 t[59, r] = 1                           # mem_channels[1].value = 1 with the channel unused
             else:
                 cond = stack.pop()
-                t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2
+                t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, ctx, 1, sl - 2
                 t[59:67, r] = limbs(cond)
             csum = sum(limbs(cond)) % P
             t[32, r], t[33, r] = int(cond != 0), (pow(csum, P - 2, P) if csum else 0)          # general.jumps(): should_jump, cond_sum_pinv
             aux = int(sl != npop)
             t[36, r], t[37, r] = (pow(sl - npop, P - 2, P) if aux else 0), aux                 # general.stack(): stack_inv, stack_inv_aux
-            t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 0, 1, 0, 14, dst & 0xFFFFFFFF   # JUMPDEST-bit channel: unused in kernel mode
+            t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 0, 1, ctx, 14, dst & 0xFFFFFFFF   # JUMPDEST-bit channel: unused in kernel mode
             t[72, r] = 1
             read_top_next = bool(aux)
             if cond:
@@ -227,37 +251,57 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
         elif ins in dup:                               # dup_swap.rs:112-141: the top goes to memory (channel 1), element n is read (channel 2)
             i = dup[ins]
             assert sl > i
-            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 0, 0, 1, sl - 1
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 0, ctx, 1, sl - 1
             t[59:67, r] = limbs(stack[-1])
-            t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 1, 0, 1, sl - 1 - i
+            t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 1, ctx, 1, sl - 1 - i
             t[72:80, r] = limbs(stack[-1 - i])
             stack.append(stack[-1 - i])
         elif ins in swap:                              # dup_swap.rs:207-244: element n+1 is read (channel 1), the top is written there (channel 2)
             i = swap[ins]
             assert sl > i + 1
-            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2 - i
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, ctx, 1, sl - 2 - i
             t[59:67, r] = limbs(stack[-2 - i])
-            t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 0, 0, 1, sl - 2 - i
+            t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 0, ctx, 1, sl - 2 - i
             t[72:80, r] = limbs(stack[-1])
             stack[-1], stack[-2 - i] = stack[-2 - i], stack[-1]
         elif ins in "am":                              # three operands: the second and third are read through mem_channels[1], [2]
             assert sl >= 3
             a, b, c = stack.pop(), stack.pop(), stack.pop()
-            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, ctx, 1, sl - 2
             t[59:67, r] = limbs(b)
-            t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 1, 0, 1, sl - 3
+            t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 1, ctx, 1, sl - 3
             t[72:80, r] = limbs(c)
             stack.append(0 if c == 0 else ((a + b) % c if ins == "a" else (a * b) % c))
             if log is not None:
                 log.append((ins, a, b, c, stack[-1]))
+        elif ins == "c":                               # SET_CONTEXT
+            assert sl >= 1
+            w = limbs(stack.pop())
+            assert w[0] in (0, 1) and not any(w[i] for i in (1, 3, 4, 5, 6, 7))
+            new_ctx = w[2]
+            saved_sp[ctx] = sl - 1                     # old stack pointer -> (ctx, ContextMetadata, StackSize), a CTL-only memory write
+            new_sp = saved_sp.get(new_ctx, 0)          # new stack pointer <- (new_ctx, ContextMetadata, StackSize): 0 for a fresh context
+            new_stack = stacks.setdefault(new_ctx, [])
+            assert len(new_stack) == new_sp
+            t[32, r] = w[0]                            # general.context_pruning().pruning_flag
+            if w[0] and stale is not None:
+                stale.append(ctx)
+            aux = int(new_sp != 0)
+            t[36, r], t[37, r], t[38, r] = (pow(new_sp, P - 2, P) if aux else 0), aux, aux
+            if aux:                                    # the new top is read through channel 2 and handed to the next row's channel 0
+                t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 1, new_ctx, 1, new_sp - 1
+                t[72:80, r] = limbs(new_stack[-1])
+            ctx, stack = new_ctx, new_stack
         elif ins == "e":                               # EXIT_KERNEL (jumps.rs:13-65): pc, kernel flag and gas come from the popped kexit_info
             assert sl >= 1
             info = limbs(stack.pop())
-            assert info[1] == 1 and info[7] == 0, "this model stays in kernel mode"
+            assert info[1] in (0, 1) and info[7] == 0
             aux = int(sl != 1)
             t[36, r], t[37, r] = (pow(sl - 1, P - 2, P) if aux else 0), aux
             read_top_next = bool(aux)
-            next_pc, gas = info[0], info[6]
+            next_pc, gas, next_kernel = info[0], info[6], info[1]
+            if not next_kernel:                        # exit_kernel is in MIGHT_OVERFLOW (stack.rs:23-44): the stack it returns with is bounds-checked
+                t[39, r] = pow((sl - 1 - 1025) % P, P - 2, P)
         elif ins in "Yx":                              # syscalls_exceptions.rs:23-134 (operation.rs:735-810, 983-1080)
             code = 6 if ins == "x" else None           # exc_stop
             virt = (exception_jumptable + 3 * code) if ins == "x" else (syscall_jumptable + 3 * opcode[ins])
@@ -269,26 +313,26 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
             t[59, r] = handler
             old_top = stack[-1] if stack else 0
             if sl > 0:                                 # push: the old top goes to memory through the partial channel
-                t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, 0, 1, sl - 1
+                t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, ctx, 1, sl - 1
                 t[36, r], t[37, r] = pow(sl, P - 2, P), 1
-            info = (pc + 1 if ins == "Y" else pc) | (1 << 32) | (gas << 192)
+            info = (pc + 1 if ins == "Y" else pc) | (kernel << 32) | (gas << 192)
             stack.append(info)
             if jumptable is not None:
                 jumptable(virt, handler, r + 1)
             if log is not None:
                 log.append((ins, opcode[ins], old_top, handler, info))
-            next_pc, gas = handler, 0
+            next_pc, gas, next_kernel = handler, 0, 1
         elif ins == "C":                               # GET_CONTEXT (contextops.rs:82-102, 277-301): pushes context << 64; the old top goes out through channel 2
             if sl > 0:
-                t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 0, 0, 1, sl - 1
+                t[67, r], t[68, r], t[69, r], t[70, r], t[71, r] = 1, 0, ctx, 1, sl - 1
                 t[72:80, r] = limbs(stack[-1])
                 t[36, r], t[37, r] = pow(sl, P - 2, P), 1
-            stack.append(0)                            # the trace runs in context 0
+            stack.append(ctx << 64)
         elif ins == "l":                               # MLOAD_GENERAL (memio.rs:22-57): the address word on top, the loaded word replaces it
             assert sl >= 1
-            virt, seg, ctx = limbs(stack[-1])[:3]      # get_addr (cpu_stark.rs:318-323)
+            virt, seg, actx = limbs(stack[-1])[:3]     # get_addr (cpu_stark.rs:318-323)
             val = int.from_bytes(np.random.default_rng(seed + 1000 + r).bytes(32), "little")
-            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, ctx, seg, virt
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, actx, seg, virt
             t[59:67, r] = limbs(val)
             aux = int(sl != 2)                         # the stack view of every m_op_general row refers to stack_len - 2 (memio.rs:170-176)
             t[36, r], t[37, r] = (pow((sl - 2) % P, P - 2, P) if aux else 0), aux
@@ -297,16 +341,16 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
             assert sl >= 2
             stack.pop()
             addr = stack.pop()
-            virt, seg, ctx = limbs(addr)[:3]
-            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2
+            virt, seg, actx = limbs(addr)[:3]
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, ctx, 1, sl - 2
             t[59:67, r] = limbs(addr)
-            t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, ctx, seg, virt       # the store goes through the partial channel
+            t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, actx, seg, virt      # the store goes through the partial channel
             aux = int(sl != 2)
             t[36, r], t[37, r], t[38, r] = (pow(sl - 2, P - 2, P) if aux else 0), aux, aux
             read_top_next = bool(aux)
         elif ins == "I":                               # PROVER_INPUT: pushes whatever the prover supplies (push behaviour; is_not_kernel = 0)
             if sl > 0:
-                t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, 0, 1, sl - 1
+                t[80, r], t[81, r], t[82, r], t[83, r], t[84, r] = 1, 0, ctx, 1, sl - 1
                 t[36, r], t[37, r] = pow(sl, P - 2, P), 1
             stack.append(inputs.pop(0) if inputs else int.from_bytes(np.random.default_rng(seed + r).bytes(32), "little"))
             if log is not None:
@@ -314,7 +358,7 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
         elif ins in "EAMSDOLGB&|^fghK<>RWVT":          # two operands: the second one is read through mem_channels[1]
             assert sl >= 2
             a, b = stack.pop(), stack.pop()
-            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, 0, 1, sl - 2
+            t[54, r], t[55, r], t[56, r], t[57, r], t[58, r] = 1, 1, ctx, 1, sl - 2
             t[59:67, r] = limbs(b)
             if ins == "E":
                 d = [(x - y) % P for x, y in zip(limbs(a), limbs(b))]
@@ -348,9 +392,9 @@ def cpu_program_trace(log_n, program, halt_final=0x1234, gas0=50, seed=0, inputs
                     t[72:80, r] = limbs(BN_BASE)
                 stack.append(binary[ins](a, b))
         gas += cost[ins]
-        pc = next_pc
+        pc, kernel = next_pc, next_kernel
     k = r + 1                                          # executed rows
-    t[2, k:], t[3, k:], t[5, k:] = halt_final, len(stack), gas
+    t[0, k:], t[2, k:], t[3, k:], t[5, k:] = ctx, halt_final, len(stack), gas
     if stack:
         for l, v in enumerate(limbs(stack[-1])):
             t[46 + l, k:] = v
@@ -961,12 +1005,18 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
         # MSTORE_32BYTES_n (cpu_stark.rs:174-223 ctl_data_byte_unpacking): (0, context, segment, virt, len = new offset - virt, timestamp, value)
         virt, seg, ctx = [(addr_word >> (32 * i)) & 0xFFFFFFFF for i in range(3)]
         packing_ops.append((0, ctx, seg, virt, (clock - 1) * num_channels + 1, value.to_bytes(ln, "little")))
+    def push32(code_ctx, virt, imm, clock):
+        # a user-mode PUSH (cpu_stark.rs:264-304 ctl_data_byte_packing_push): (1, code context, Segment::Code, pc + 1, len, timestamp, pushed word)
+        packing_ops.append((1, code_ctx, 0, virt, (clock - 1) * num_channels + 1, imm[::-1]))
+    stale = []                                      # contexts pruned by SET_CONTEXT rows: the Memory table lists them (context pruning lookup)
+
     def jumptable(virt, handler, clock):
         # syscall / exception rows (cpu_stark.rs:225-262 ctl_data_jumptable_read): (1, 0, Segment::Code, virt, 3, timestamp, handler address);
         # the three bytes are the kernel's jump-table entry, big-endian (a pre-initialised segment: any content is admissible)
         packing_ops.append((1, 0, 0, virt, (clock - 1) * num_channels + 1, handler.to_bytes(3, "little")))
     cpu = cpu_program_trace(log_cpu, program, halt_final=halt_final, log=log, inputs=inputs, keccak=keccak if keccak_inputs is not None else None,
-                            load32=load32, store32=store32, syscall_jumptable=labels[2], exception_jumptable=labels[3], jumptable=jumptable)
+                            load32=load32, store32=store32, syscall_jumptable=labels[2], exception_jumptable=labels[3], jumptable=jumptable,
+                            stale=stale, push32=push32)
     limbs = lambda x: [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
     NUM_CHANNELS = num_channels                     # 5 in the reference; the parameter exists for the negative test
     ops = []                                        # (ctx, seg, virt, timestamp, is_read, filter, value limbs)
@@ -983,6 +1033,11 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
                 ops.append((row[o + 2], row[o + 3], row[o + 4], ts(1 + c), row[o + 1], 1, row[o + 5:o + 13]))
         if row[80]:
             ops.append((row[82], row[83], row[84], ts(4), row[81], 1, row[46:54]))          # partial channel: the value of mem_channels[0]
+        if row[17] and row[24]:
+            # SET_CONTEXT (cpu_stark.rs:391-431): the old stack pointer (stack_len - 1) is written to the old context's
+            # ContextMetadata::StackSize cell at the time of channel 2, the new one (next row's stack_len) read from the new context's at channel 3
+            ops.append((row[0], 6, 11, ts(2), 0, 1, [row[3] - 1] + [0] * 7))
+            ops.append((row[48], 6, 11, ts(3), 1, 1, [int(cpu[3, r + 1])] + [0] * 7))
     logic_ops = []
     sponge = keccak = None
     if sponge_ops:
@@ -1038,7 +1093,7 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
     for i, (ctx, seg, virt, t_, is_read, filt, val) in enumerate(ops):
         m[:6, i] = [filt, t_, is_read, ctx, seg, virt]
         m[6:, i] = val
-    memory = memory_finish_reference(m)
+    memory = memory_finish_reference(m, stale=stale)
     after = [(int(memory[4, i]), int(memory[5, i]), int(memory[6, i])) for i in range(n) if memory[26, i]]
     after_vals = [[int(memory[7 + l, i]) for l in range(8)] for i in range(n) if memory[26, i]]
     # Arithmetic: the rows of the executed operations, then padding and the range-check columns
