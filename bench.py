@@ -276,7 +276,7 @@ def run_ours(args):
             (0 if lg is None else (1 << lg) * NUM_COLUMNS[t] * ((NUM_COLUMNS[t] + 7) // 8 + 6)) for t, lg in enumerate(shape)])
         need = plan.needs(rank) if plan is not None else [shape[t] is not None and owner[t] == rank for t in range(9)]
         r = Rig(torch, dev, shape, seed=4, mine=need, common_seed=True)
-        be = zk.ZkGpuBackend(ctx, cfg, labels)
+        be = zk.ZkGpuBackend(ctx, cfg, labels, precompute_constraints=True)
         return plan, owner, r, be
 
     def sharded_step(plan, owner, r, be, host):

@@ -142,6 +142,13 @@ int zkgpu_batch_cap(const zkgpu_batch* b, uint64_t* out_cap);
  *   digests 2*((n<<rate_bits) - (1<<cap_height))*4   merkle_tree.digests in plonky2's recursive layout */
 int zkgpu_batch_export(const zkgpu_batch* b, uint64_t* coeffs, uint64_t* leaves, uint64_t* digests);
 
+/* Table jobs of this context (zkgpu_table_job_begin) also evaluate, in their challenger-independent first half, every constraint of the
+ * table on the LDE — the values do not depend on the alphas, only their combination does (starky ConstraintConsumer: acc = acc alpha +
+ * c).  zkgpu_table_job_finish then forms the quotient values as a Horner combination of the stored columns instead of running the
+ * evaluator.  Same proofs bit for bit; more memory traffic in total, but the evaluator leaves the serial part of a table-sharded
+ * segment (the tables are finished one after the other, prover.rs:251-259) — use it there, not for one-device proving. */
+int zkgpu_ctx_set_precompute_constraints(zkgpu_ctx* ctx, int on);
+
 /* ---- S1 split over several devices (the table-sharded layout of one segment) --------------------------------------
  * PolynomialBatch::from_values (prover.rs:100-107) of ONE table computed by k devices.  The transforms are per column and the leaf
  * sponge absorbs a row's columns in order, so: every device takes a column slice through ifft + LDE (zkgpu_lde_slice), the slices
@@ -157,7 +164,8 @@ int zkgpu_lde_slice(zkgpu_ctx* ctx, const uint64_t* values, int mem_kind, size_t
 int zkgpu_merkle_block_words(size_t nleaves, uint32_t cap_height, uint32_t nblocks, size_t* words);
 /* digests of the leaves [block * nleaves / nblocks, (block + 1) * nleaves / nblocks) of the column-major LDE `lde` (column c at
  * lde + c * stride) and every Merkle level above them down to the cap level, packed level after level.  nblocks must divide the
- * cap (1 << cap_height). */
+ * cap (1 << cap_height).  Only the rows of the block are read: a device that holds just its block (pitch `stride` = rows per block,
+ * received by an all-to-all) passes lde = block buffer - block * rows_per_block elements. */
 int zkgpu_merkle_block(zkgpu_ctx* ctx, const uint64_t* lde, size_t stride, size_t ncols, size_t nleaves, uint32_t cap_height,
                        uint32_t nblocks, uint32_t block, uint64_t* packed_out);
 /* A batch over caller-owned device buffers (borrowed until zkgpu_batch_free; values may be NULL): coeffs ncols x n with column

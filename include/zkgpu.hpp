@@ -78,6 +78,9 @@ public:
         }
         return spans;
     }
+    // the context's cudaStream_t: a host that issues its own device work (the NCCL all-gathers of a commitment split over several
+    // devices) orders it with the library's kernels on this stream instead of synchronising
+    void* stream() const { void* s = nullptr; check(zkgpu_ctx_stream(h_, &s)); return s; }
     zkgpu_ctx* handle() const { return h_; }
 private:
     zkgpu_ctx* h_ = nullptr;
@@ -164,6 +167,29 @@ public:
         return f;
     }
     const zkgpu_batch* handle() const { return h_.get(); }
+
+    // ---- from_values split over the k devices of a table-sharded segment (include/zkgpu.h "S1 split over several devices") ----
+    // All pointers are DEVICE memory of the caller (the buffers an all-gather fills).  Step 1 on every device: its column slice
+    // through ifft + LDE; exchange the slices; step 2 on every device: the leaf digests and Merkle levels of ITS block of leaves;
+    // exchange the packed digests; step 3 on the owner: the batch over the gathered buffers (borrowed until it is destroyed).
+    static void lde_slice(Context& ctx, const F* values, int mem_kind, size_t ncols, size_t n, uint32_t rate_bits, F* values_out, F* coeffs_out, F* lde_out) {
+        check(zkgpu_lde_slice(ctx.handle(), values, mem_kind, ncols, n, rate_bits, values_out, coeffs_out, lde_out));
+    }
+    static size_t merkle_block_words(size_t nleaves, uint32_t cap_height, uint32_t nblocks) {
+        size_t w = 0;
+        check(zkgpu_merkle_block_words(nleaves, cap_height, nblocks, &w));
+        return w;
+    }
+    static void merkle_block(Context& ctx, const F* lde, size_t stride, size_t ncols, size_t nleaves, uint32_t cap_height, uint32_t nblocks,
+                             uint32_t block, F* packed_out) {
+        check(zkgpu_merkle_block(ctx.handle(), lde, stride, ncols, nleaves, cap_height, nblocks, block, packed_out));
+    }
+    static PolynomialBatch assemble(Context& ctx, const F* values, const F* coeffs, const F* lde, const F* packed, uint32_t nblocks, size_t ncols,
+                                    size_t n, uint32_t rate_bits, uint32_t cap_height) {
+        zkgpu_batch* b = nullptr;
+        check(zkgpu_batch_assemble(ctx.handle(), values, coeffs, lde, packed, nblocks, ncols, n, rate_bits, cap_height, &b));
+        return PolynomialBatch(b);
+    }
 private:
     struct Dims { size_t ncols, n; uint32_t rate_bits, cap_height; };
     Dims dims() const { Dims d{}; check(zkgpu_batch_dims(h_.get(), &d.ncols, &d.n, &d.rate_bits, &d.cap_height)); return d; }

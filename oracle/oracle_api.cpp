@@ -265,6 +265,20 @@ long orc_check_table_rows(uint32_t table, const uint64_t* trace, size_t ncols, s
     } catch (const std::exception& e) { g_orc_err = e.what(); return -1; }
 }
 
+// number of constraints the table's evaluator yields per row pair (its yield_constr calls; lookup / CTL checks not included)
+long orc_table_num_constraints(uint32_t table) {
+    try {
+        const size_t ncols = zkstark::table_num_columns(table);
+        std::vector<uint64_t> row(ncols, 0), out;
+        RowCheckConsumer yc;
+        yc.n = 4; yc.out = &out; yc.max_out = 0;
+        RowOF lv{row.data()}, nv{row.data()};
+        uint64_t labels[4] = {1, 2, 3, 4};
+        zkstark::eval_table<OF>(table, lv, nv, yc, params_from(labels));
+        return (long)yc.idx;
+    } catch (const std::exception& e) { g_orc_err = e.what(); return -1; }
+}
+
 // "stage\tseconds\n" lines accumulated since the last call with reset != 0 (main-thread wall clock of the prover's stages)
 size_t orc_stage_report(char* buf, size_t cap, int reset) {
     std::string out;

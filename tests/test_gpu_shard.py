@@ -63,3 +63,27 @@ def test_split_commit_rejects_bad_blocks(ctx):
     assert lib().zkgpu_merkle_block_words(C.c_size_t(256), C.c_uint32(4), C.c_uint32(8), C.byref(words)) == 0
     # levels 256, 128, 64, 32, 16 digests, an eighth of each
     assert words.value == 4 * (32 + 16 + 8 + 4 + 2)
+
+
+@pytest.mark.parametrize("table", list(range(9)))
+@pytest.mark.parametrize("cfgname", ["test", "std"])
+def test_precomputed_constraint_values_give_the_same_proof(ctx, oracle, table, cfgname):
+    """zkgpu_ctx_set_precompute_constraints: the constraint values recorded in the first half of a table job and Horner-combined with the
+    alphas in the second half give the proof the fused evaluator gives — and that is the oracle's proof, word for word"""
+    import zk_evm_b200 as zk
+    from tests import traces
+    from tests.oracle_lib import STANDARD_FAST, TEST_CONFIG, DEFAULT_LABELS, orc_prove_table
+    cfgw = STANDARD_FAST if cfgname == "std" else TEST_CONFIG
+    cfg, labels = zk.StarkConfig(*cfgw), zk.KernelLabels(*DEFAULT_LABELS)
+    lg = 16 if table == traces.T_ARITHMETIC else 9
+    tr = traces.random_trace(table, lg, 70 + table)
+    bg = np.array([0x1111111111, 0x2222222222, 0x3333333333, 0x4444444444], dtype=np.uint64)[:2 * cfgw[1]]
+    state = np.arange(1, 13, dtype=np.uint64)
+    be = zk.ZkGpuBackend(ctx, cfg, labels, precompute_constraints=True)
+    words, st = be.finish(be.begin(table, be.commit(table, tr), bg), state)
+    want, st_want = orc_prove_table(oracle, table, cfgw, tr, bg, state)
+    assert np.array_equal(words, want) and np.array_equal(st, st_want)
+    # and the flag does not stick to the context: the next ordinary job runs the fused evaluator
+    be2 = zk.ZkGpuBackend(ctx, cfg, labels)
+    words2, _ = be2.finish(be2.begin(table, be2.commit(table, tr), bg), state)
+    assert np.array_equal(words2, want)

@@ -17,6 +17,7 @@ import numpy as np  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--precompute", type=int, default=1, help="evaluate the alpha-independent constraint values ahead of the relay (0: fused evaluator in the relay)")
     ap.add_argument("--time", type=int, default=0, help="with --full: time this many sharded proofs and print the phase breakdown of the last")
     args = ap.parse_args()
     import torch
@@ -49,7 +50,7 @@ def main():
         in_use = [x is not None for x in tr]
         log_ns = [None if x is None else int(np.log2(x.shape[1])) for x in tr]
         plan = zk.shard_plan(world, log_ns, split_min_bytes=0)
-        be = zk.ZkGpuBackend(ctx, cfg, labels)
+        be = zk.ZkGpuBackend(ctx, cfg, labels, precompute_constraints=bool(args.precompute))
         pv = np.arange(1000, 1037, dtype=np.uint64)
         ap = zk.prove_with_traces_sharded(be, comm, tr, in_use, pv, plan=plan, gather=True)
         if rank == 0:
@@ -60,7 +61,7 @@ def main():
         log_ns = list(bench.SEGMENT_LOG_NS)
         plan = zk.shard_plan(world, log_ns)
         rig = bench.Rig(torch, dev, log_ns, seed=4, mine=[True] * 9 if rank == 0 else plan.needs(rank), common_seed=True)
-        be = zk.ZkGpuBackend(ctx, cfg, labels)
+        be = zk.ZkGpuBackend(ctx, cfg, labels, precompute_constraints=bool(args.precompute))
         for host in (False, True):
             tr = rig.host_traces if host else rig.ptrs
             ap = zk.prove_with_traces_sharded(be, comm, tr, rig.in_use, bench.PUBLIC_VALUES, plan=plan, gather=True)

@@ -219,6 +219,7 @@ void zkgpu_ctx_destroy(zkgpu_ctx* h) {
     cudaSetDevice(h->c.device);
     cudaStreamSynchronize(h->c.stream);
     h->c.table_cache.clear();
+    h->c.cons_cache.clear();
     h->c.stark_tables.clear();
     h->c.ntt.roots_fwd.release();
     h->c.ntt.roots_inv.release();

@@ -117,6 +117,10 @@ struct Ctx {
     // stage spans (zkgpu_ctx_set_timing): every StageLog mark records an event on `stream`; resolved by zkgpu_ctx_timing_report
     bool timing = false;
     std::vector<std::pair<std::string, cudaEvent_t>> timing_marks;
+    // per table: the buffer of precomputed constraint values, kept from proof to proof (multi-GB: allocating it per proof makes the pool
+    // grow and remap, measured as 0.1 - 0.7 s stalls, profiles/r2m)
+    std::map<uint32_t, DevBuf> cons_cache;
+    bool precompute = false;   // table jobs evaluate the alpha-independent constraint values in their first half (zkgpu_ctx_set_precompute_constraints)
     bool debug = false;   // proofs keep their aux / quotient batches and FRI input values for stage-by-stage parity tests
     // pinned staging buffer for H2D / D2H of pageable memory
     void* staging = nullptr;

@@ -101,6 +101,21 @@ void prove_table_begin(Ctx& c, uint32_t table, const zkstark::TableParams& prm, 
         commit_from_device_values(c, aux, c.debug);
         lg.mark("aux commit");
     }
+    if (c.precompute) {
+        // everything of the quotient evaluation that does not depend on the alphas, while the transcript is still with another table
+        job.ncons = total_constraints(td);
+        const size_t need = (size_t)job.ncons * trace.N * 8;
+        DevBuf& buf = c.cons_cache[table];
+        if (buf.bytes < need) { buf.release(); buf = DevBuf(&c, need); }
+        job.cons = buf.get();
+        QuotientArgs qa;
+        qa.table = table; qa.trace_lde = trace.lde.get(); qa.aux_lde = na ? aux.lde.get() : nullptr; qa.log_n = trace.log_n;
+        qa.num_challenges = cfg.num_challenges;
+        for (int i = 0; i < 4; i++) { qa.alphas[i] = 0; qa.betas[i] = ctl.betas[i]; qa.gammas[i] = ctl.gammas[i]; }
+        qa.prm = prm; qa.out = nullptr;
+        constraints_record(c, td, qa, job.cons, job.ncons);
+        lg.mark("constraint values");
+    }
     job.begun = true;
 }
 
@@ -157,7 +172,13 @@ void prove_table_finish(Ctx& c, TableJob& job, uint64_t challenger_state[12], co
         qa.num_challenges = cfg.num_challenges;
         for (int i = 0; i < 4; i++) { qa.alphas[i] = alphas[i]; qa.betas[i] = ctl.betas[i]; qa.gammas[i] = ctl.gammas[i]; }
         qa.prm = prm; qa.out = qv.get();
-        quotient_values(c, td, qa);
+        if (job.ncons) {
+            quotient_from_constraints(c, job.cons, job.ncons, k, cfg.num_challenges, alphas, qv.get());
+            job.cons = nullptr;
+            job.ncons = 0;
+        } else {
+            quotient_values(c, td, qa);
+        }
         lg.mark("quotient eval");
         init_batch(c, quot, nq, n, cfg.rate_bits, cfg.cap_height);
         quot.coeffs = DevBuf(&c, nq * n * 8);
@@ -348,6 +369,13 @@ void prove_table(Ctx& c, uint32_t table, const zkstark::TableParams& prm, const 
 using namespace zk;
 
 extern "C" {
+
+int zkgpu_ctx_set_precompute_constraints(zkgpu_ctx* h, int on) {
+    ZK_API_BEGIN
+    ZK_REQUIRE(h, "ctx is null");
+    h->c.precompute = on != 0;
+    ZK_API_END
+}
 
 int zkgpu_ctx_set_debug(zkgpu_ctx* h, int on) {
     ZK_API_BEGIN

@@ -50,6 +50,92 @@ static const uint64_t* get_domain(Ctx& c, unsigned k, const uint64_t zh[2]) {
     return p;
 }
 
+// ---- alpha-independent constraint values + their Horner combination ------------------------------------------------------------------
+// constraints the table's own evaluator yields per point (its yield_constr calls; the oracle counts the same: orc_table_num_constraints)
+static const uint32_t TABLE_CONSTRAINTS[9] = {707, 535, 514, 868, 706, 524, 45, 1, 1};
+uint32_t total_constraints(const TableDev& t) {
+    // + per lookup and challenge: one per helper column, Z(first row) and the Z transition; + the CTL section
+    return TABLE_CONSTRAINTS[t.table] + t.flat.num_lookup_cols + t.view.n_lookups + t.flat.ctl_num_constraints;
+}
+
+void constraints_record(Ctx& c, const TableDev& t, const QuotientArgs& q, uint64_t* cons, uint32_t expect) {
+    const unsigned k = q.log_n;
+    KernelScope ks(c, KF_QUOTIENT, 8.0 * ((size_t)2 << k) * (zkstark::table_num_columns(q.table) + t.flat.num_aux() + expect));
+    RecKernelArgs a;
+    a.trace_lde = q.trace_lde; a.aux_lde = q.aux_lde; a.cons = cons;
+    a.log_N = k + 1; a.N = (size_t)2 << k;
+    for (unsigned i = 0; i < 2; i++) { a.betas[i] = i < q.num_challenges ? q.betas[i] : 0; a.gammas[i] = i < q.num_challenges ? q.gammas[i] : 0; }
+    uint64_t gn = gl_pow(GL_GENERATOR, (uint64_t)1 << k);
+    uint64_t zh[2] = {gl_sub(gn, 1), gl_sub(gl_neg(gn), 1)};
+    a.dom = get_domain(c, k, zh);
+    a.flat = t.view;
+    a.prm = q.prm;
+    // the kernel's own count of what it yielded is checked against the expected width of the buffer once per (table, challenges)
+    const std::string key = "ncons:" + std::to_string(q.table) + ":" + std::to_string(q.num_challenges);
+    const bool verify = c.table_cache.find(key) == c.table_cache.end();
+    DevBuf cnt(&c, 8);
+    a.count_out = reinterpret_cast<uint32_t*>(cnt.get());
+    switch (q.table) {
+        case T_LOGIC: launch_record<T_LOGIC>(a, c.stream); break;
+        case T_MEMORY: launch_record<T_MEMORY>(a, c.stream); break;
+        case T_MEM_BEFORE: case T_MEM_AFTER: launch_record<T_MEM_BEFORE>(a, c.stream); break;
+#if ZKS_ALL_TABLES
+        case T_ARITHMETIC: launch_record<T_ARITHMETIC>(a, c.stream); break;
+        case T_BYTE_PACKING: launch_record<T_BYTE_PACKING>(a, c.stream); break;
+        case T_CPU: launch_record<T_CPU>(a, c.stream); break;
+        case T_KECCAK: launch_record<T_KECCAK>(a, c.stream); break;
+        case T_KECCAK_SPONGE: launch_record<T_KECCAK_SPONGE>(a, c.stream); break;
+#endif
+        default: throw ZkError(ZKGPU_ERR_INVALID, "constraints_record: table id not supported");
+    }
+    c.count_launch();
+    c.check_launch("constraints_record_kernel");
+    if (verify) {
+        uint64_t got = 0;
+        c.d2h(&got, cnt.get(), 8);
+        ZK_REQUIRE((uint32_t)got == expect, "constraints_record: the evaluator yielded " + std::to_string((uint32_t)got) + " constraints, the buffer has " +
+                                                std::to_string(expect) + " columns");
+        c.table_cache.emplace(key, DevBuf(&c, 8));
+    }
+}
+
+// out[k * N + i] = zh_inv[i & 1] * sum_t alpha_k^(T - 1 - t) cons[t * N + j],  i = bitrev(j)
+__global__ void __launch_bounds__(256) quotient_combine_kernel(const uint64_t* __restrict__ cons, uint32_t T, size_t N, unsigned log_N, unsigned nc,
+                                                               uint64_t a0, uint64_t a1, uint64_t zh0, uint64_t zh1, uint64_t* __restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    uint64_t acc0 = 0, acc1 = 0;
+    const uint64_t* p = cons + j;
+    uint32_t t = 0;
+    for (; t + 4 <= T; t += 4) {      // four loads in flight per thread
+        const uint64_t c0 = __ldg(p), c1 = __ldg(p + N), c2 = __ldg(p + 2 * N), c3 = __ldg(p + 3 * N);
+        p += 4 * N;
+        acc0 = gl_add(gl_mul(acc0, a0), c0); acc0 = gl_add(gl_mul(acc0, a0), c1); acc0 = gl_add(gl_mul(acc0, a0), c2); acc0 = gl_add(gl_mul(acc0, a0), c3);
+        if (nc > 1) { acc1 = gl_add(gl_mul(acc1, a1), c0); acc1 = gl_add(gl_mul(acc1, a1), c1); acc1 = gl_add(gl_mul(acc1, a1), c2); acc1 = gl_add(gl_mul(acc1, a1), c3); }
+    }
+    for (; t < T; t++) {
+        const uint64_t cv = __ldg(p);
+        p += N;
+        acc0 = gl_add(gl_mul(acc0, a0), cv);
+        if (nc > 1) acc1 = gl_add(gl_mul(acc1, a1), cv);
+    }
+    const uint32_t i = bitrev32((uint32_t)j, log_N);
+    const uint64_t zh = (i & 1) ? zh1 : zh0;
+    out[i] = gl_mul(acc0, zh);
+    if (nc > 1) out[N + i] = gl_mul(acc1, zh);
+}
+
+void quotient_from_constraints(Ctx& c, const uint64_t* cons, uint32_t T, unsigned log_n, unsigned num_challenges, const uint64_t* alphas, uint64_t* out) {
+    const size_t N = (size_t)2 << log_n;
+    KernelScope ks(c, KF_QUOTIENT, 8.0 * N * (T + num_challenges));
+    uint64_t gn = gl_pow(GL_GENERATOR, (uint64_t)1 << log_n);
+    const uint64_t zh0 = gl_inv(gl_sub(gn, 1)), zh1 = gl_inv(gl_sub(gl_neg(gn), 1));
+    quotient_combine_kernel<<<(unsigned)((N + 255) / 256), 256, 0, c.stream>>>(cons, T, N, log_n + 1, num_challenges, alphas[0],
+                                                                               num_challenges > 1 ? alphas[1] : 0, zh0, zh1, out);
+    c.count_launch();
+    c.check_launch("quotient_combine_kernel");
+}
+
 void quotient_values(Ctx& c, const TableDev& t, const QuotientArgs& q) {
     ZK_REQUIRE(q.num_challenges >= 1 && q.num_challenges <= 2, "num_challenges must be 1 or 2");
     // each LDE row of trace + aux read once, num_challenges values per point written (16n(c+a) + 16n*nc)

@@ -106,6 +106,58 @@ __global__ void __launch_bounds__(quotient_block_threads(TABLE), quotient_min_bl
         for (unsigned k = 0; k < a.nc; k++) a.out[(size_t)k * a.N + i] = gl_mul(yc.acc[k].v, a.zh_inv[i & 1]);
 }
 
+// ---- the alpha-independent half of the same evaluation (RecordConsumer, stark/consumer.h) --------------------------------------
+// Same point <-> thread map, same evaluators; every constraint value goes to its column of a.cons (T x N, point index = storage
+// position j, so a warp writes 32 consecutive words per constraint).  Thread 0 reports the number of constraints it yielded.
+struct RecKernelArgs {
+    const uint64_t* trace_lde;
+    const uint64_t* aux_lde;
+    uint64_t* cons;
+    uint32_t* count_out;
+    size_t N;
+    unsigned log_N;
+    uint64_t betas[2], gammas[2];
+    const uint64_t* dom;
+    FlatView flat;
+    TableParams prm;
+};
+
+template <uint32_t TABLE>
+__global__ void __launch_bounds__(quotient_block_threads(TABLE), quotient_min_blocks(TABLE)) constraints_record_kernel(RecKernelArgs a) {
+    const size_t j0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = j0 < a.N;
+    const size_t j = live ? j0 : a.N - 1;      // threads past the end redo the last point (the evaluators contain block-wide barriers)
+    const uint32_t i = bitrev32((uint32_t)j, a.log_N);
+    const uint32_t inext = (i + 2) & (uint32_t)(a.N - 1);
+    const size_t jn = bitrev32(inext, a.log_N);
+
+    RecordConsumer<Fp> yc;
+    yc.out = a.cons + j; yc.stride = a.N;
+    yc.z_last = Fp(__ldg(a.dom + j));
+    yc.lagrange_first = Fp(__ldg(a.dom + a.N + j));
+    yc.lagrange_last = Fp(__ldg(a.dom + 2 * a.N + j));
+
+    DevRow lv{a.trace_lde + j, a.N}, nv{a.trace_lde + jn, a.N};
+    DevRow alv{a.aux_lde + j, a.N}, anv{a.aux_lde + jn, a.N};
+
+    if constexpr (TABLE == T_LOGIC) logic::eval<Fp>(lv, nv, yc);
+    else if constexpr (TABLE == T_MEMORY) memory::eval<Fp>(lv, nv, yc);
+    else if constexpr (TABLE == T_MEM_BEFORE || TABLE == T_MEM_AFTER) memcont::eval<Fp>(lv, nv, yc);
+#if ZKS_ALL_TABLES
+    else if constexpr (TABLE == T_ARITHMETIC) arithmetic::eval<Fp>(lv, nv, yc);
+    else if constexpr (TABLE == T_BYTE_PACKING) byte_packing::eval<Fp>(lv, nv, yc);
+    else if constexpr (TABLE == T_CPU) cpu::eval<Fp>(lv, nv, yc, a.prm);
+    else if constexpr (TABLE == T_KECCAK) keccak::eval_blocked<Fp>(lv, nv, yc);
+    else if constexpr (TABLE == T_KECCAK_SPONGE) keccak_sponge::eval<Fp>(lv, nv, yc);
+#endif
+
+    Fp betas[2] = {Fp(a.betas[0]), Fp(a.betas[1])}, gammas[2] = {Fp(a.gammas[0]), Fp(a.gammas[1])};
+    flat_eval_lookups<Fp>(a.flat, betas, lv, nv, alv, anv, yc);
+    flat_eval_ctls<Fp>(a.flat, betas, gammas, lv, nv, alv, anv, yc);
+    if (j0 == 0) *a.count_out = yc.idx;
+}
+template <uint32_t TABLE> void launch_record(const RecKernelArgs& a, cudaStream_t stream);
+
 // domain table of the quotient kernels (see QuotKernelArgs::dom)
 struct DomArgs { uint64_t* dom; size_t N; unsigned log_N; uint64_t w_N, last, c_first[2], c_last[2]; };
 
@@ -115,6 +167,10 @@ template <uint32_t TABLE> void launch_quotient(const QuotKernelArgs& a, cudaStre
     template <> void launch_quotient<TABLE>(const QuotKernelArgs& a, cudaStream_t stream) {                  \
         constexpr unsigned T = quotient_block_threads(TABLE);                                                \
         quotient_kernel<TABLE><<<(unsigned)((a.N + T - 1) / T), T, 0, stream>>>(a);                          \
+    }                                                                                                        \
+    template <> void launch_record<TABLE>(const RecKernelArgs& a, cudaStream_t stream) {                    \
+        constexpr unsigned T = quotient_block_threads(TABLE);                                                \
+        constraints_record_kernel<TABLE><<<(unsigned)((a.N + T - 1) / T), T, 0, stream>>>(a);                \
     }
 
 }  // namespace zk

@@ -43,6 +43,8 @@ struct TableJob {
     const Batch* trace = nullptr;
     const Ctl* ctl = nullptr;
     std::unique_ptr<zkgpu_batch> aux;   // committed auxiliary polynomials
+    uint64_t* cons = nullptr;            // alpha-independent constraint values, ncons x N (the context's per-table buffer; only when it precomputes them)
+    uint32_t ncons = 0;
     bool begun = false;
 };
 void prove_table_begin(Ctx& c, uint32_t table, const zkstark::TableParams& prm, const zkstark::Config& cfg, const Batch& trace,
@@ -75,6 +77,11 @@ struct QuotientArgs {
     uint64_t* out;               // num_challenges x N, NATURAL order: out[j*N + i] = quotient_j(g w_N^i)
 };
 void quotient_values(Ctx& c, const TableDev& t, const QuotientArgs& a);
+// the same evaluation split at the alphas: every constraint value to its column of cons (expect x N) ...
+uint32_t total_constraints(const TableDev& t);
+void constraints_record(Ctx& c, const TableDev& t, const QuotientArgs& a, uint64_t* cons, uint32_t expect);
+// ... and the quotient values as their Horner combination in alpha (out: num_challenges x N, natural order)
+void quotient_from_constraints(Ctx& c, const uint64_t* cons, uint32_t T, unsigned log_n, unsigned num_challenges, const uint64_t* alphas, uint64_t* out);
 
 // ---- fri.cu ---------------------------------------------------------------------------------------------------
 // evaluate every coefficient column at zeta and zeta_next (extension) and at 1 (base): out[col] = {z.a,z.b,zn.a,zn.b,one}

@@ -54,6 +54,10 @@ class Context:
         check(lib().zkgpu_ctx_stream(self._h, C.byref(p)))
         return int(p.value or 0)
 
+    def set_precompute_constraints(self, on=True):
+        """table jobs begun on this context evaluate the alpha-independent constraint values ahead of the transcript (table-sharded segments)"""
+        check(lib().zkgpu_ctx_set_precompute_constraints(self._h, int(bool(on))))
+
     def set_timing(self, on=True):
         """stage spans (the reference's TimingTree): record a CUDA event at every stage boundary of the prover"""
         check(lib().zkgpu_ctx_set_timing(self._h, int(bool(on))))

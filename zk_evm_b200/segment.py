@@ -196,8 +196,11 @@ def prove_with_traces(ctx, traces, public_values, config, labels=None, forced_po
 class ZkGpuBackend:
     """The compute steps of one rank on its GPU (through the C ABI)."""
 
-    def __init__(self, ctx, config, labels=None):
+    def __init__(self, ctx, config, labels=None, precompute_constraints=False):
         self.ctx, self.config, self.labels = ctx, config, labels
+        # table-sharded segments: evaluate the alpha-independent constraint values in begin(), i.e. while the transcript is with another
+        # table, so that finish() — the serial relay — only combines them (include/zkgpu.h zkgpu_ctx_set_precompute_constraints)
+        self.precompute_constraints = precompute_constraints
         self.phase_ms = None      # a dict: prove_with_traces_sharded adds the wall time of its phases (synchronising at every mark)
 
     def commit(self, table, trace):
@@ -239,8 +242,12 @@ class ZkGpuBackend:
     def begin(self, table, handle, beta_gamma):
         ctl = _p.get_ctl_data(self.ctx, table, handle, beta_gamma, self.config.num_challenges)
         job = C.c_void_p()
-        check(lib().zkgpu_table_job_begin(self.ctx._h, C.c_uint32(table), C.byref(self.labels) if self.labels is not None else None,
-                                          C.byref(self.config), handle._h, ctl._h, None, C.byref(job)))
+        self.ctx.set_precompute_constraints(self.precompute_constraints)
+        try:
+            check(lib().zkgpu_table_job_begin(self.ctx._h, C.c_uint32(table), C.byref(self.labels) if self.labels is not None else None,
+                                              C.byref(self.config), handle._h, ctl._h, None, C.byref(job)))
+        finally:
+            self.ctx.set_precompute_constraints(False)
         return (job, ctl, handle)
 
     def finish(self, job, state, forced_pow=None):
@@ -312,6 +319,10 @@ class TorchComm:
                 work.wait()
                 return t.numpy().view(np.uint64)
         return Pending()
+
+    def all_to_all_device(self, out, inp):
+        """NCCL all-to-all of device tensors whose first dimension is the rank: out[i] = rank i's inp[my rank]; async work handle"""
+        return self.dist.all_to_all_single(out, inp, group=self.group, async_op=True)
 
     def all_gather_device(self, out, inp):
         """NCCL all-gather of device tensors (inp may be the rank's own slot of out: in place); returns the async work handle"""
@@ -423,8 +434,15 @@ class SplitCommit:
                                         None if device else C.cast(C.c_void_p(self.vals.data_ptr() + slot * n), u64p),
                                         C.cast(C.c_void_p(self.coef.data_ptr() + slot * n), u64p),
                                         C.cast(C.c_void_p(self.lde.data_ptr() + slot * N), u64p)))
-            self.w_lde = comm.all_gather_device(self.lde, self.lde[r * cpr:(r + 1) * cpr])
-            self.w_rest = [comm.all_gather_device(self.coef, self.coef[r * cpr:(r + 1) * cpr])]
+            # what the hashing needs first: every rank's columns of THIS rank's block of rows (1/k of an all-gather, so the leaf hashing starts
+            # almost at once); the all-gathers that give the owner the whole LDE / coefficients / values then run under the hashing
+            self.per = per = N // k
+            send = backend.buffer(("rows_out", table), (k, cpr, per))
+            send.copy_(self.lde[r * cpr:(r + 1) * cpr].view(cpr, k, per).transpose(0, 1))
+            self.rows = backend.buffer(("rows_in", table), (k, cpr, per))
+            self.w_rows = comm.all_to_all_device(self.rows, send)
+            self.w_rest = [comm.all_gather_device(self.lde, self.lde[r * cpr:(r + 1) * cpr]),
+                           comm.all_gather_device(self.coef, self.coef[r * cpr:(r + 1) * cpr])]
             if self.vals is not None:
                 self.w_rest.append(comm.all_gather_device(self.vals, self.vals[r * cpr:(r + 1) * cpr]))
 
@@ -433,9 +451,12 @@ class SplitCommit:
         words = C.c_size_t()
         check(lib().zkgpu_merkle_block_words(C.c_size_t(self.N), C.c_uint32(cfg.cap_height), C.c_uint32(k), C.byref(words)))
         with torch.cuda.stream(self.stream):
-            self.w_lde.wait()
+            self.w_rows.wait()
             self.packed = self.be.buffer(("packed", self.table), (k, words.value))
-            check(lib().zkgpu_merkle_block(ctx._h, C.cast(C.c_void_p(self.lde.data_ptr()), u64p), C.c_size_t(self.N), C.c_size_t(self.ncols),
+            # self.rows is the block's (k * cpr) x per column-major LDE: the library addresses block r of an LDE with column pitch `per`
+            # whose rows start r * per before it
+            base = self.rows.data_ptr() - 8 * r * self.per
+            check(lib().zkgpu_merkle_block(ctx._h, C.cast(C.c_void_p(base), u64p), C.c_size_t(self.per), C.c_size_t(self.ncols),
                                            C.c_size_t(self.N), C.c_uint32(cfg.cap_height), C.c_uint32(k), C.c_uint32(r),
                                            C.cast(C.c_void_p(self.packed.data_ptr() + 8 * r * words.value), u64p)))
             self.w_packed = self.comm.all_gather_device(self.packed, self.packed[r])
