@@ -239,10 +239,11 @@ class ZkGpuBackend:
     def segment_challenges(self, caps, in_use, public_values):
         return segment_challenges(caps, in_use, self.config.cap_height, public_values, self.config.num_challenges)
 
-    def begin(self, table, handle, beta_gamma):
+    def begin(self, table, handle, beta_gamma, on_critical_path=False):
+        """on_critical_path: nobody is ahead of this table in the relay, so there is no wait to hide the constraint recording in"""
         ctl = _p.get_ctl_data(self.ctx, table, handle, beta_gamma, self.config.num_challenges)
         job = C.c_void_p()
-        self.ctx.set_precompute_constraints(self.precompute_constraints)
+        self.ctx.set_precompute_constraints(self.precompute_constraints and not on_critical_path)
         try:
             check(lib().zkgpu_table_job_begin(self.ctx._h, C.c_uint32(table), C.byref(self.labels) if self.labels is not None else None,
                                               C.byref(self.config), handle._h, ctl._h, None, C.byref(job)))
@@ -559,12 +560,18 @@ def prove_with_traces_sharded(backend, comm, traces, table_in_use, public_values
     # relay starts as early as it can; a table whose turn comes before its auxiliary polynomials exist gets them right then.
     mine = [t for t in range(NUM_TABLES) if t in handles]
     jobs, begun = {}, set()
+    first_table = next(t for t in range(NUM_TABLES) if table_in_use[t])
+
+    def begin(t):
+        begun.add(t)
+        if t == first_table and getattr(backend, "precompute_constraints", False):
+            return backend.begin(t, handles[t], beta_gamma, on_critical_path=True)
+        return backend.begin(t, handles[t], beta_gamma)
 
     def begin_next():
         for t in mine:
             if t not in begun:
-                begun.add(t)
-                jobs[t] = backend.begin(t, handles[t], beta_gamma)
+                jobs[t] = begin(t)
                 return True
         return False
     import os as _os
@@ -581,8 +588,7 @@ def prove_with_traces_sharded(backend, comm, traces, table_in_use, public_values
             continue
         if owner[t] == comm.rank:
             if t not in begun:
-                begun.add(t)
-                jobs[t] = backend.begin(t, handles[t], beta_gamma)
+                jobs[t] = begin(t)
             fp = None if forced_pow_witnesses is None else int(forced_pow_witnesses[t])
             proofs[t], state = backend.finish(jobs.pop(t), state, fp)
             state = comm.broadcast(state, src=owner[t])
