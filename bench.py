@@ -58,13 +58,15 @@ STARK_CONFIGS = {"standard_fast": STANDARD_FAST, "test": TEST_CONFIG}
 LABELS = (0x1234, 0x77, 0x4000, 0x5000)
 PUBLIC_VALUES = np.arange(1, 2218, dtype=np.uint64)       # 2217 observed elements (flatten_public_values, get_challenges.rs:202-227), synthetic
 METRIC = "segment proofs/sec"
-# DRAM bytes per algorithmic byte of the dominant kernel (leaf_hash), from the committed `ncu --set full` capture
+# DRAM bytes per algorithmic byte of the dominant kernel (leaf_hash), from the committed `ncu --set full` captures
 # profiles/r1j_ncu_leaf_hash.raw.csv: Keccak trace leaves, dram__bytes_read.sum + dram__bytes_write.sum = 5.1175 GB + 0.0162 GB for
-# (8 * 2431 + 32) * 2^18 = 5.1066 GB algorithmic (every LDE column read once, one digest written per row)
+# (8 * 2431 + 32) * 2^18 = 5.1066 GB algorithmic (every LDE column read once, one digest written per row); the round-2 kernel reads
+# the same way (profiles/r2p_ncu_leaf_merkle_summary.csv: Memory leaves 1.008 + 0.128 GB for 1.141 GB algorithmic)
 LEAF_HASH_TRAFFIC_PER_ALGORITHMIC_BYTE = 5.13375 / 5.10657
 FAMILIES = ("leaf_hash", "merkle_levels", "ntt", "quotient", "aux_columns", "openings", "fri", "pow")
-# thread-instructions per Poseidon permutation of the production kernel (ncu smsp__inst_executed.sum x 32 / permutations)
-INSTR_PER_PERMUTATION = 26.2e3
+# thread-instructions per Poseidon permutation of the production leaf-hash kernel: ncu smsp__inst_executed.sum x 32 / permutations,
+# profiles/r2p_ncu_leaf_merkle_summary.csv (Memory: 13.44e9 warp-instructions for 2^22 leaves x 4 permutations; Cpu: 9.23e9 for 2^20 x 11)
+INSTR_PER_PERMUTATION = 25.6e3
 
 
 def measured_peak():
@@ -479,7 +481,7 @@ def run_ours(args):
             peak_issue = 148 * 4 * 32 * sm_mhz * 1e6
             roof["issue"] = {"bound": "integer issue slots", "achieved": pps * INSTR_PER_PERMUTATION / 1e12, "peak": peak_issue / 1e12, "unit": "T thread-instr/s",
                              "frac": pps * INSTR_PER_PERMUTATION / peak_issue,
-                             "source": "profiles/: %.1f k thread-instructions per permutation (ncu smsp__inst_executed.sum), both integer pipes ~80 %% busy" % (INSTR_PER_PERMUTATION / 1e3)}
+                             "source": "profiles/r2p_ncu_leaf_merkle_summary.csv: %.1f k thread-instructions per permutation (ncu smsp__inst_executed.sum x 32 / permutations), ALU pipe 81 %% busy" % (INSTR_PER_PERMUTATION / 1e3)}
         cpu = None if args.no_cpu_baseline else cpu_baseline(args, log_ns)
         line = {"metric": METRIC, "value": segs / (ms / 1e3), "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,

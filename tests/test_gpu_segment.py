@@ -31,6 +31,28 @@ def test_executing_segment_with_32_byte_memory_operations(ctx, oracle):
     assert ok, err
 
 
+@pytest.mark.parametrize("which", ["syscall_exception_exit_kernel", "set_context_pruning", "user_mode_push"])
+def test_executing_segments_of_the_remaining_cpu_families(ctx, oracle, which):
+    """the executing segments that give the last Cpu constraint families active rows and the last lookups non-zero sums (syscall /
+    exception / EXIT_KERNEL with jump-table reads; SET_CONTEXT with context pruning; a user-mode PUSH read through BytePacking):
+    device proofs == oracle proofs word for word, restated verifier accepts"""
+    from tests import test_oracle_stark as tos
+    if which == "syscall_exception_exit_kernel":
+        prog, log_mem = tos.SYS_PROGRAM, 15
+        inputs = tos._sys_inputs(len(prog) + 8)
+    elif which == "set_context_pruning":
+        prog, inputs, log_mem = tos.CTX_PROGRAM, tos.CTX_INPUTS, 10
+    else:
+        prog, log_mem = tos.USER_PROGRAM, 15
+        inputs = tos._user_inputs(len(prog) + 8)
+    tr, labels = traces.cpu_segment(prog, inputs=inputs, log_mem=log_mem)
+    ap = zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, zk.StarkConfig(*TEST_CONFIG), zk.KernelLabels(*labels))
+    want, bg, caps = orc_prove_segment(oracle, TEST_CONFIG, tr, PUBLIC_VALUES, labels=labels)
+    _same(ap, want, bg, caps)
+    ok, err = orc_verify_segment(oracle, TEST_CONFIG, ap.stark_proofs, PUBLIC_VALUES, labels=labels)
+    assert ok, err
+
+
 @pytest.mark.parametrize("cfg", [TEST_CONFIG, STANDARD_FAST])
 def test_valid_segment_matches_oracle_and_verifies(ctx, oracle, cfg):
     tr = traces.valid_segment(seed=11)
