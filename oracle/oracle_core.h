@@ -197,23 +197,31 @@ struct FftRoots {
     }
 };
 static inline FftRoots& fft_roots() { static FftRoots r; return r; }
+// one radix-2 DIT stage (span m = 2^s) on the elements [lo, hi) of a (hi - lo a multiple of m)
+static inline void fft_stage(uint64_t* a, size_t lo, size_t hi, unsigned s, size_t n, const uint64_t* tw) {
+    const size_t m = (size_t)1 << s, half = m >> 1, step = n >> s;
+    if (half == 1) {
+        for (size_t k = lo; k < hi; k += 2) { uint64_t u = a[k], t = a[k + 1]; a[k] = gl_add(u, t); a[k + 1] = gl_sub(u, t); }
+        return;
+    }
+    for (size_t k = lo; k < hi; k += m)
+        for (size_t j = 0; j < half; j++) {
+            uint64_t t = gl_mul(tw[j * step], a[k + j + half]), u = a[k + j];
+            a[k + j] = gl_add(u, t);
+            a[k + j + half] = gl_sub(u, t);
+        }
+}
 static inline void fft_inplace(uint64_t* a, unsigned log_n) {
     size_t n = (size_t)1 << log_n;
     for (size_t i = 0; i < n; i++) { size_t j = bitrev(i, log_n); if (i < j) { uint64_t t = a[i]; a[i] = a[j]; a[j] = t; } }
     const uint64_t* tw = fft_roots().get(log_n);
-    for (unsigned s = 1; s <= log_n; s++) {
-        size_t m = (size_t)1 << s, half = m >> 1, step = n >> s;
-        if (half == 1) {
-            for (size_t k = 0; k < n; k += 2) { uint64_t u = a[k], t = a[k + 1]; a[k] = gl_add(u, t); a[k + 1] = gl_sub(u, t); }
-            continue;
-        }
-        for (size_t k = 0; k < n; k += m)
-            for (size_t j = 0; j < half; j++) {
-                uint64_t t = gl_mul(tw[j * step], a[k + j + half]), u = a[k + j];
-                a[k + j] = gl_add(u, t);
-                a[k + j + half] = gl_sub(u, t);
-            }
-    }
+    // the stages whose span fits a 32 KB block are done block by block (all of them while the block is in L1), the wider ones sweep the
+    // whole array: the same butterflies in another order
+    const unsigned BLK = 12;
+    const unsigned inner = log_n < BLK ? log_n : BLK;
+    for (size_t b = 0; b < n; b += (size_t)1 << inner)
+        for (unsigned s = 1; s <= inner; s++) fft_stage(a, b, b + ((size_t)1 << inner), s, n, tw);
+    for (unsigned s = inner + 1; s <= log_n; s++) fft_stage(a, 0, n, s, n, tw);
 }
 // ifft(v)[j] = n^-1 sum_i v_i w^(-ij)
 static inline void ifft_inplace(uint64_t* a, unsigned log_n) {

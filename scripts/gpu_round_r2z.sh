@@ -1,0 +1,24 @@
+# r2z: the record of round 2 at HEAD — the driver's own commands: full GPU suite, smoke, both bench arms (--steps 20 --warmup 5)
+set -x
+mkdir -p gpurun_out
+nproc; lscpu | grep "Model name"
+( time timeout 1800 python -m pytest tests -m gpu -q -x > gpurun_out/r2z_pytest_gpu.log 2>&1 ) 2>&1 | grep real; tail -3 gpurun_out/r2z_pytest_gpu.log
+timeout 600 python __graft_entry__.py smoke > gpurun_out/r2z_smoke.log 2>&1; tail -2 gpurun_out/r2z_smoke.log
+( time timeout 1200 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2z_bench.json 2> gpurun_out/r2z_bench.err ) 2>&1 | grep real
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2z_bench.json'))
+f=d['roofline']['families']
+print('value', round(d['value'],3), 'e2e', round(d['e2e']['value'],3), 'fin', round(d['e2e_finish_on_device']['value'],3), 'launches/proof', d['gpu_launches']/d['steps']/3, 'one-stream ms', round(d['single_segment_latency_ms'],1))
+print({k: (round(v['ms_per_step'],2), v['launches_per_step']) for k,v in f.items()})
+print('roofline', {k: d['roofline'][k] for k in ('kernel','achieved','peak','frac','traffic')}, d['roofline'].get('issue'))
+print('cpu_baseline', json.dumps(d['cpu_baseline'])[:300])
+for k in ('config2_cpu_table','config3_b3_b6','config5_stream'):
+    print(k, json.dumps(d[k])[-300:])
+PY
+( time timeout 1500 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2z_bench_reference.json 2> gpurun_out/r2z_bench_reference.err ) 2>&1 | grep real
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/r2z_bench_reference.json'))
+print(d['steps'], d['ms_per_step'], d['steps_note']); print(d['cpu_baseline'])
+PY

@@ -44,3 +44,37 @@ def test_config4_sized_valid_segment_verifies(ctx, oracle):
     ap2 = zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, zk.StarkConfig(*STANDARD_FAST), zk.KernelLabels(*DEFAULT_LABELS))
     ok, err = orc_verify_segment(oracle, STANDARD_FAST, ap2.stark_proofs, PUBLIC_VALUES)
     assert not ok and "Cross-table lookup" in err
+
+
+@pytest.mark.parametrize("cfgname", ["standard_fast", "test"])
+def test_config3_b3_b6_segment_matches_oracle_word_for_word(ctx, oracle, cfgname):
+    """BASELINE config #3 at ITS heights (CI ranges of witness_b3_b6, scripts/prove_stdio.rs:102-114: Arithmetic 2^16, BytePacking 2^10,
+    Cpu 2^16, Keccak 2^12, KeccakSponge 2^8, Logic 2^10, Memory 2^18, MemBefore 2^16, MemAfter 2^7), all nine tables, under
+    standard_fast_config and under TEST_STARK_CONFIG (what CI uses, ci.yml:196): device proofs == oracle proofs, bit for bit"""
+    import bench
+    from tests.oracle_lib import orc_prove_segment, TEST_CONFIG
+    cfg = STANDARD_FAST if cfgname == "standard_fast" else TEST_CONFIG
+    tr = traces.random_segment(list(bench.SEGMENT_CONFIGS["b3_b6"]), seed=3)
+    ap = zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, zk.StarkConfig(*cfg), zk.KernelLabels(*DEFAULT_LABELS))
+    want, bg, caps = orc_prove_segment(oracle, cfg, tr, PUBLIC_VALUES)
+    assert np.array_equal(ap.ctl_challenges, bg) and np.array_equal(ap.trace_caps, caps)
+    for t in range(9):
+        assert np.array_equal(ap.stark_proofs[t], want[t]), "table %d proof differs from the oracle" % t
+
+
+@pytest.mark.parametrize("table,lg", [(traces.T_KECCAK_SPONGE, 13), (traces.T_LOGIC, 16), (traces.T_KECCAK, 17)])
+def test_zz_bench_sized_wide_tables_match_oracle_word_for_word(ctx, oracle, table, lg):
+    """the three wide tables at the heights of the bench segment (config #4: KeccakSponge 2^13 x 438, Logic 2^16 x 523, Keccak 2^17 x 2431 —
+    45 % of a segment's bytes): commitment cap, auxiliary values, quotient chunks and the whole proof == the oracle's, word for word.
+    (The oracle needs about a minute for the Keccak table on 16 host threads; these run last.)"""
+    from tests.oracle_lib import orc_prove_table
+    cfg = STANDARD_FAST
+    tr = traces.random_trace(table, lg, 900 + table)
+    tb = zk.PolynomialBatch.from_values(ctx, tr, rate_bits=cfg[2], cap_height=cfg[3], keep_values=True)
+    ctl = zk.get_ctl_data(ctx, table, tb, BG2, cfg[1])
+    sp, st = zk.prove_single_table(ctx, table, zk.StarkConfig(*cfg), tb, ctl, STATE0, labels=zk.KernelLabels(*DEFAULT_LABELS))
+    got = np.array(sp.words, dtype=np.uint64)
+    sp.free(); ctl.free(); tb.free()
+    want, st_want = orc_prove_table(oracle, table, cfg, tr, BG2, STATE0)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    assert np.array_equal(st, st_want)
