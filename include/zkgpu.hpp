@@ -78,6 +78,9 @@ public:
         }
         return spans;
     }
+    // table jobs begun on this context also evaluate the alpha-independent constraint values (table-sharded segments: the evaluator then runs
+    // while the transcript is with another table, TableJob::finish only combines the stored columns)
+    void set_precompute_constraints(bool on) { check(zkgpu_ctx_set_precompute_constraints(h_, on)); }
     // the context's cudaStream_t: a host that issues its own device work (the NCCL all-gathers of a commitment split over several
     // devices) orders it with the library's kernels on this stream instead of synchronising
     void* stream() const { void* s = nullptr; check(zkgpu_ctx_stream(h_, &s)); return s; }
