@@ -58,14 +58,15 @@ STARK_CONFIGS = {"standard_fast": STANDARD_FAST, "test": TEST_CONFIG}
 LABELS = (0x1234, 0x77, 0x4000, 0x5000)
 PUBLIC_VALUES = np.arange(1, 2218, dtype=np.uint64)       # 2217 observed elements (flatten_public_values, get_challenges.rs:202-227), synthetic
 METRIC = "segment proofs/sec"
-# DRAM bytes per algorithmic byte of the dominant kernel (leaf_hash), from the committed `ncu --set full` captures
-# profiles/r1j_ncu_leaf_hash.raw.csv: Keccak trace leaves, dram__bytes_read.sum + dram__bytes_write.sum = 5.1175 GB + 0.0162 GB for
-# (8 * 2431 + 32) * 2^18 = 5.1066 GB algorithmic (every LDE column read once, one digest written per row); the round-2 kernel reads
-# the same way (profiles/r2p_ncu_leaf_merkle_summary.csv: Memory leaves 1.008 + 0.128 GB for 1.141 GB algorithmic)
-LEAF_HASH_TRAFFIC_PER_ALGORITHMIC_BYTE = 5.13375 / 5.10657
+# DRAM bytes per algorithmic byte of the dominant kernel (leaf_hash), from the committed `ncu --set full` capture of its largest launch with
+# the round-2 permutation, profiles/r2r_ncu_leaf_hash_keccak.raw.csv.gz: Keccak trace leaves (2^18 rows x 2431 columns), 71.0 ms,
+# dram__bytes_read.sum + dram__bytes_write.sum = 5.1152 GB + 0.0150 GB for (8 * 2431 + 32) * 2^18 = 5.1066 GB algorithmic (every LDE
+# column read once, one digest written per row)
+LEAF_HASH_TRAFFIC_PER_ALGORITHMIC_BYTE = (5.115167 + 0.014989) / 5.10657
 FAMILIES = ("leaf_hash", "merkle_levels", "ntt", "quotient", "aux_columns", "openings", "fri", "pow")
-# thread-instructions per Poseidon permutation of the production leaf-hash kernel: ncu smsp__inst_executed.sum x 32 / permutations,
-# profiles/r2p_ncu_leaf_merkle_summary.csv (Memory: 13.44e9 warp-instructions for 2^22 leaves x 4 permutations; Cpu: 9.23e9 for 2^20 x 11)
+# thread-instructions per Poseidon permutation of the production leaf-hash kernel: ncu smsp__inst_executed.sum x 32 / permutations —
+# Keccak: 63.78e9 warp-instructions for 2^18 leaves x 304 permutations (profiles/r2r_ncu_leaf_hash_keccak.raw.csv.gz), the same figure
+# for Memory (2^22 x 4) and Cpu (2^20 x 11) in profiles/r2p_ncu_leaf_merkle_summary.csv
 INSTR_PER_PERMUTATION = 25.6e3
 
 
@@ -465,7 +466,7 @@ def run_ours(args):
             traffic = LEAF_HASH_TRAFFIC_PER_ALGORITHMIC_BYTE * kst[top]["bytes"] / kst[top]["launches"]
         roof = {"bound": "hbm", "kernel": top, "achieved": fam(top)["achieved_GBps"], "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": fam(top)["frac_of_peak"], "traffic": traffic,
-                "traffic_source": "profiles/r1j_ncu_leaf_hash.raw.csv (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch, "
+                "traffic_source": "profiles/r2r_ncu_leaf_hash_keccak.raw.csv.gz (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch, "
                                   "scaled to the average launch of the timed region); bytes" if traffic is not None else None,
                 "how": "CUDA events recorded by the library on its launching stream around every launch group inside a timed region of the same "
                        "K steps run with ONE segment in flight (%.1f ms/step, %.3f proofs/s); achieved = algorithmic bytes of the group "
@@ -481,7 +482,7 @@ def run_ours(args):
             peak_issue = 148 * 4 * 32 * sm_mhz * 1e6
             roof["issue"] = {"bound": "integer issue slots", "achieved": pps * INSTR_PER_PERMUTATION / 1e12, "peak": peak_issue / 1e12, "unit": "T thread-instr/s",
                              "frac": pps * INSTR_PER_PERMUTATION / peak_issue,
-                             "source": "profiles/r2p_ncu_leaf_merkle_summary.csv: %.1f k thread-instructions per permutation (ncu smsp__inst_executed.sum x 32 / permutations), ALU pipe 81 %% busy" % (INSTR_PER_PERMUTATION / 1e3)}
+                             "source": "profiles/r2r_ncu_leaf_hash_keccak.raw.csv.gz: %.1f k thread-instructions per permutation (ncu smsp__inst_executed.sum x 32 / permutations), ALU pipe 81 %% busy" % (INSTR_PER_PERMUTATION / 1e3)}
         cpu = None if args.no_cpu_baseline else cpu_baseline(args, log_ns)
         line = {"metric": METRIC, "value": segs / (ms / 1e3), "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
@@ -492,13 +493,20 @@ def run_ours(args):
                 "wall_ms_per_step": wall / args.steps,
                 "single_segment_latency_ms": single_latency_ms,
                 "e2e": {"value": segs / (e_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": rig.h2d_bytes * nstreams, "d2h_bytes_per_step": d2h_bytes,
-                        "ms_per_step": e_ms / args.steps, "wall_ms_per_step": e_wall / args.steps},
+                        "ms_per_step": e_ms / args.steps, "wall_ms_per_step": e_wall / args.steps,
+                        "mode": "host traces: all nine traces in pinned host memory, uploaded inside the timed region, proofs read back"},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+        line["e2e_host_traces"] = dict(line["e2e"])
         if f_ms is not None:
             line["e2e_finish_on_device"] = {"value": segs / (f_ms / 1e3), "unit": "proofs/s", "h2d_bytes_per_step": fin_h2d_bytes * nstreams,
-                                            "ms_per_step": f_ms / args.steps, "wall_ms_per_step": f_wall / args.steps,
-                                            "what": "as e2e, but the Keccak and Logic traces are finished on the device from permutation inputs / operations "
-                                                    "(generation inside the timed region) instead of being uploaded"}
+                                            "d2h_bytes_per_step": d2h_bytes, "ms_per_step": f_ms / args.steps, "wall_ms_per_step": f_wall / args.steps,
+                                            "mode": "finish on device: the Keccak and Logic traces (72 % of a segment's bytes) are finished on the device from "
+                                                    "host permutation inputs / operations inside the timed region (zkgpu_keccak_generate_trace, "
+                                                    "zkgpu_logic_generate_trace: more device work, fewer PCIe bytes), the other seven traces uploaded, proofs read back"}
+            # the end-to-end number is the better of the two host-facing ways to call the path (both always reported): at one GPU the
+            # uploads hide under the commitments either way, at eight the shared PCIe / host memory path does not keep up with full uploads
+            if line["e2e_finish_on_device"]["value"] > line["e2e"]["value"]:
+                line["e2e"] = dict(line["e2e_finish_on_device"])
         line.update(extras)
     for cx in ctxs:
         cx.close()
