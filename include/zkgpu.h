@@ -123,7 +123,8 @@ int zkgpu_host_free(void* ptr);
 /* PolynomialBatch::from_values(values, rate_bits, blinding=false, cap_height): per column ifft -> zero-pad ->
  * coset FFT (shift = MULTIPLICATIVE_GROUP_GENERATOR) -> bit-reversed rows -> Poseidon Merkle tree.
  * `cols` = ncols pointers to n elements each (mem_kind says where they live).  keep_values != 0 keeps the raw
- * trace values on the device (needed later by zkgpu_ctl_data / lookup columns). */
+ * trace values on the device (needed later by zkgpu_ctl_data / lookup columns).  rate_bits 0..4: the STARK tables use 1
+ * (StarkConfig::standard_fast_config), plonky2's recursion circuits commit with 3; the table prover (S3) takes rate_bits = 1 only. */
 int zkgpu_commit_values(zkgpu_ctx* ctx, const uint64_t* const* cols, size_t ncols, size_t n, uint32_t rate_bits,
                         uint32_t cap_height, int mem_kind, int keep_values, zkgpu_batch** out);
 /* same, but the columns are one contiguous column-major block: col c at base + c*n */

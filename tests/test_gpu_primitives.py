@@ -88,6 +88,20 @@ def test_commit_values_matches_oracle(ctx, oracle, ncols, lg, cap):
     b.free()
 
 
+@pytest.mark.parametrize("rate_bits,ncols,lg,cap", [(0, 5, 8, 4), (2, 9, 7, 4), (3, 12, 10, 4), (3, 135, 12, 4), (3, 3, 3, 1), (4, 7, 6, 2)])
+def test_commit_values_other_blowups_match_oracle(ctx, oracle, rate_bits, ncols, lg, cap):
+    """PolynomialBatch::from_values is not only the STARK's rate_bits = 1: the recursion layer's circuits commit their wires with rate_bits = 3
+    (CircuitConfig::standard_recursion_config; 135 wires in TEST_RECURSION_CONFIG, testing_utils.rs:55-72).  Coefficients, leaves in
+    plonky2's bit-reversed row order, the recursive digest layout and the cap against the oracle for blow-ups 1, 4, 8 and 16."""
+    rng = np.random.default_rng(1000 * rate_bits + ncols)
+    cols = rand_field(rng, (ncols, 1 << lg))
+    b = zk.PolynomialBatch.from_values(ctx, cols, rate_bits=rate_bits, cap_height=cap)
+    co, le, di = b.export()
+    oco, ole, odi, ocap = oracle.commit(cols, rate_bits, cap)
+    assert np.array_equal(co, oco) and np.array_equal(le, ole) and np.array_equal(b.cap, ocap) and np.array_equal(di, odi)
+    b.free()
+
+
 def test_commit_coeffs_matches_oracle(ctx, oracle):
     rng = np.random.default_rng(5)
     cf = rand_field(rng, (4, 1 << 9))

@@ -269,17 +269,29 @@ void intt_natural(Ctx& c, const uint64_t* values, uint64_t* scratch, uint64_t* c
 // lde column stride is N.
 void lde_bitrev(Ctx& c, const uint64_t* coeffs, uint64_t* lde, size_t ncols, unsigned L, unsigned rate_bits,
                 uint64_t shift) {
-    ZK_REQUIRE(rate_bits <= 1, "only blow-up 1 or 2 is implemented (StarkConfig rate_bits = 1)");
+    ZK_REQUIRE(rate_bits <= 4, "blow-up factors up to 16 are implemented (StarkConfig rate_bits = 1, plonky2 recursion configs rate_bits = 3)");
     size_t n = (size_t)1 << L;
     if (rate_bits == 0) {
         const uint64_t* t0 = shift > 1 ? get_power_table(c, shift, 1, n) : nullptr;
         ntt_dif(c, coeffs, n, 0, lde, n, ncols, L, false, t0, nullptr, 0);
         return;
     }
-    // half h evaluates on the coset (shift * w_2n^h) * <w_n>
-    const uint64_t* t0 = get_power_table(c, shift, 1, n);
-    const uint64_t* t1 = get_power_table(c, gl_mul(shift, gl_root_of_unity(L + 1)), 1, n);
-    ntt_dif(c, coeffs, n, 1, lde, n, 2 * ncols, L, false, t0, t1, 1);
+    if (rate_bits == 1) {
+        // half h evaluates on the coset (shift * w_2n^h) * <w_n>: both halves in one launch per pass, read from the same coefficient column
+        const uint64_t* t0 = get_power_table(c, shift, 1, n);
+        const uint64_t* t1 = get_power_table(c, gl_mul(shift, gl_root_of_unity(L + 1)), 1, n);
+        ntt_dif(c, coeffs, n, 1, lde, n, 2 * ncols, L, false, t0, t1, 1);
+        return;
+    }
+    // Blow-up 2^r in general (the widths plonky2's recursion circuits commit with: PolynomialBatch::from_values(.., rate_bits = 3, ..)).
+    // Natural index i = c + 2^r m of the size-N domain is the point (shift w_N^c) w_n^m, and it is stored at bitrev_N(i) = bitrev_r(c) n +
+    // bitrev_n(m): block h of n storage positions is the size-n transform on the coset shift * w_N^bitrev_r(h), natural in, bit-reversed out.
+    const size_t N = n << rate_bits;
+    const uint64_t wN = gl_root_of_unity(L + rate_bits);
+    for (unsigned h = 0; h < (1u << rate_bits); h++) {
+        const uint64_t sh = gl_mul(shift, gl_pow(wN, bitrev32(h, rate_bits)));
+        ntt_dif(c, coeffs, n, 0, lde + (size_t)h * n, N, ncols, L, false, get_power_table(c, sh, 1, n), nullptr, 0);
+    }
 }
 
 }  // namespace zk
