@@ -4,7 +4,7 @@
   python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, through the zkgpu C ABI)
   python bench.py --impl reference --gpus N ...            # reference arm: the CPU restatement (oracle) on all host cores
 
-Metric (BASELINE.json): segment proofs/sec.  A step = one segment proof PER SEGMENT STREAM (--streams S, default 3: S segments in
+Metric (BASELINE.json): segment proofs/sec.  A step = one segment proof PER SEGMENT STREAM (--streams S, default 4: S segments in
 flight per GPU, each on its own context + CUDA stream + host thread, proving its segments back to back); a segment proof =
 prove_with_traces over all nine STARK tables of a synthetic segment with the table heights of the `witness_b19807080` CI ranges
 (SURVEY.md 8d config #4): per table the trace commitment, CTL / lookup auxiliary columns + commitment, fused quotient evaluation +
@@ -677,7 +677,8 @@ def main():
     ap.add_argument("--shrink", type=int, default=0, help="segment workload: make every table 2^shrink times shorter (smoke runs)")
     ap.add_argument("--cpu-shrink", type=int, default=3, help="in-arm cpu_baseline: the sample proves tables 2^k times shorter")
     ap.add_argument("--reference-budget", type=float, default=280.0, help="reference arm: stop starting new full-size steps after this many seconds")
-    ap.add_argument("--streams", type=int, default=3, help="segments in flight per GPU (parallelism=segments); measured 1: 3.34, 2: 3.78, 3: 3.95, 4: 3.86 proofs/s")
+    ap.add_argument("--streams", type=int, default=4, help="segments in flight per GPU (parallelism=segments); measured (profiles/r2t_streams_sweep.jsonl) "
+                                                             "2: 3.94, 3: 4.13, 4: 4.17, 5: 4.18 proofs/s (e2e 3.91, 4.07, 4.14, 4.14); round 1: 1: 3.34, 3: 3.95, 4: 3.86")
     ap.add_argument("--stagger-ms", type=float, default=80.0, help="start offset between the segment streams of a GPU (inside the timed region)")
     ap.add_argument("--no-extras", action="store_true", help="skip the sub-records (configs #2, #3, #5, table_sharded, e2e_finish_on_device)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiler runs)")
