@@ -2,6 +2,7 @@
 #include "oracle_core.h"
 #include "oracle_poly.h"
 #include <omp.h>
+#include <map>
 
 using namespace orc;
 
@@ -276,6 +277,93 @@ long orc_table_num_constraints(uint32_t table) {
         uint64_t labels[4] = {1, 2, 3, 4};
         zkstark::eval_table<OF>(table, lv, nv, yc, params_from(labels));
         return (long)yc.idx;
+    } catch (const std::exception& e) { g_orc_err = e.what(); return -1; }
+}
+
+// starky 1.0.0 stark_testing.rs `test_stark_low_degree`, which the reference runs for every table (cpu_stark.rs:679-703,
+// memory_stark.rs:902-925, logic.rs:400-424, keccak_stark.rs:631-655, keccak_sponge_stark.rs:973-993, byte_packing_stark.rs:453-476,
+// memory_continuation_stark.rs:160-180, arithmetic_stark.rs:334+), restated: a random trace of degree < n is extended to the
+// subgroup of size 4n (rate_bits = log2_ceil(constraint_degree + 1) = 2), the table's constraints are evaluated at every point
+// (next row = 4 points on; x - w_n^-1, L_0, L_{n-1} as the consumer's selectors; Horner in one random alpha) and the values are
+// interpolated.  -> the degree of that polynomial (the reference asserts degree <= 3 n - 1), -2 when it is identically zero, -1 on error.
+long orc_table_constraint_degree(uint32_t table, unsigned log_n, uint64_t seed, const uint64_t labels[4]) {
+    try {
+        const unsigned rate_bits = 2, L = log_n + rate_bits;
+        const size_t n = (size_t)1 << log_n, N = n << rate_bits, ncols = zkstark::table_num_columns(table);
+        if (ncols == 0 || log_n < 1 || L > 20) throw std::runtime_error("bad table or size");
+        uint64_t st = seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+        auto rnd = [&]() { st += 0x9E3779B97F4A7C15ull; uint64_t z = st; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                           return gl_from_u64(z ^ (z >> 31)); };
+        auto extend = [&](std::vector<uint64_t>& v) { ifft_inplace(v.data(), log_n); v.resize(N, 0); fft_inplace(v.data(), L); };
+        std::vector<std::vector<uint64_t>> lde(ncols);
+        for (auto& col : lde) { col.resize(n); for (auto& x : col) x = rnd(); extend(col); }
+        std::vector<uint64_t> first(n, 0), last(n, 0);
+        first[0] = 1; last[n - 1] = 1;
+        extend(first); extend(last);
+        const uint64_t alpha = rnd(), wN = gl_root_of_unity(L), last_pt = gl_inv(gl_root_of_unity(log_n));
+        std::vector<OF> apow(1025);
+        apow[0] = OF(1);
+        for (size_t e = 1; e < apow.size(); e++) apow[e] = apow[e - 1] * OF(alpha);
+        std::vector<uint64_t> evals(N), lrow(ncols), nrow(ncols);
+        uint64_t x = 1;
+        for (size_t i = 0; i < N; i++, x = gl_mul(x, wN)) {
+            const size_t inext = (i + ((size_t)1 << rate_bits)) % N;
+            for (size_t c = 0; c < ncols; c++) { lrow[c] = lde[c][i]; nrow[c] = lde[c][inext]; }
+            zkstark::Consumer<OF, 1> yc;
+            yc.nc = 1; yc.alpha[0] = OF(alpha); yc.acc[0] = OF(0); yc.apow[0] = apow.data();
+            yc.z_last = OF(gl_sub(x, last_pt)); yc.lagrange_first = OF(first[i]); yc.lagrange_last = OF(last[i]);
+            RowOF lv{lrow.data()}, nv{nrow.data()};
+            zkstark::eval_table<OF>(table, lv, nv, yc, params_from(labels));
+            evals[i] = yc.acc[0].v;
+        }
+        ifft_inplace(evals.data(), L);
+        for (size_t d = N; d-- > 0;) if (evals[d] != 0) return (long)d;
+        return -2;
+    } catch (const std::exception& e) { g_orc_err = e.what(); return -1; }
+}
+
+// starky 1.0.0 cross_table_lookup.rs debug_utils `check_ctls`, which the reference runs over the raw traces of every segment when
+// debug assertions are on (prover.rs:165-184; CI builds with -Cdebug-assertions, ci.yml:93), restated: for every cross-table lookup
+// the multiset of rows the looking tables send (rows whose filter is 1) must equal the multiset the looked table holds; the Memory
+// lookup's looking side also gets `extra_rows` (n_extra x 13: get_memory_extra_looking_values, verifier.rs:547-737).  A filter that is
+// neither 0 nor 1 is an error, as there.  -> total number of distinct rows whose multiplicities differ, per lookup in mismatches[10];
+// -1 on error.  Tables left out (null trace) send and hold nothing.
+long orc_check_ctls(const uint64_t* const* traces, const size_t* ns, const uint64_t* extra_rows, size_t n_extra, size_t mismatches[10]) {
+    try {
+        auto ctls = zkstark::all_cross_table_lookups();
+        std::vector<std::vector<const uint64_t*>> cols(9);
+        for (uint32_t t = 0; t < 9; t++) {
+            if (!traces[t]) continue;
+            size_t nc = zkstark::table_num_columns(t);
+            cols[t].resize(nc);
+            for (size_t c = 0; c < nc; c++) cols[t][c] = traces[t] + c * ns[t];
+        }
+        long total = 0;
+        for (size_t ci = 0; ci < ctls.size(); ci++) {
+            std::map<std::vector<uint64_t>, long> diff;
+            auto process = [&](const TableWithColumns& tc, long sign) {
+                if (tc.table >= 9 || !traces[tc.table]) return;
+                const uint64_t* const* tr = cols[tc.table].data();
+                const size_t n = ns[tc.table];
+                std::vector<uint64_t> row(tc.columns.size());
+                for (size_t r = 0; r < n; r++) {
+                    const uint64_t f = filter_eval_table(tc.filter, tr, n, r);
+                    if (f == 0) continue;
+                    if (f != 1) throw std::runtime_error("Non-binary filter? (lookup " + std::to_string(ci) + ", table " + std::to_string(tc.table) + ", row " + std::to_string(r) + ")");
+                    for (size_t k = 0; k < row.size(); k++) row[k] = col_eval_table(tc.columns[k], tr, n, r);
+                    diff[row] += sign;
+                }
+            };
+            for (auto& l : ctls[ci].looking_tables) process(l, +1);
+            process(ctls[ci].looked_table, -1);
+            if (ci == zkstark::MEMORY_CTL_IDX)
+                for (size_t e = 0; e < n_extra; e++) diff[std::vector<uint64_t>(extra_rows + 13 * e, extra_rows + 13 * e + 13)] += 1;
+            size_t bad = 0;
+            for (auto& kv : diff) bad += kv.second != 0;
+            if (mismatches) mismatches[ci] = bad;
+            total += (long)bad;
+        }
+        return total;
     } catch (const std::exception& e) { g_orc_err = e.what(); return -1; }
 }
 

@@ -174,6 +174,34 @@ def orc_check_table_rows(orc, table, trace, labels=DEFAULT_LABELS, max_pairs=64)
     return [(int(out[2 * i]), int(out[2 * i + 1])) for i in range(k)]
 
 
+def orc_table_constraint_degree(orc, table, log_n, seed=1, labels=DEFAULT_LABELS):
+    """starky's test_stark_low_degree restated (oracle_api.cpp): degree of the alpha-combined constraint polynomial of a random
+    degree-<n trace, interpolated over the subgroup of size 4 n; -2 when it is identically zero"""
+    lab = np.array(labels, dtype=np.uint64)
+    orc.lib.orc_table_constraint_degree.restype = C.c_long
+    d = orc.lib.orc_table_constraint_degree(C.c_uint32(table), C.c_uint(log_n), C.c_uint64(seed), _ptr(lab))
+    if d == -1:
+        orc.lib.orc_last_error.restype = C.c_char_p
+        raise RuntimeError(orc.lib.orc_last_error().decode())
+    return int(d)
+
+
+def orc_check_ctls(orc, traces, extra_rows=()):
+    """starky's debug check_ctls restated (prover.rs:165-184): per cross-table lookup, the number of distinct rows whose multiplicity
+    on the looking side (plus `extra_rows` for the Memory lookup) differs from the looked side -> list of 10 counts"""
+    arrs = [None if t is None else np.ascontiguousarray(t, dtype=np.uint64) for t in traces]
+    ptrs = (u64p * 9)(*[None if a is None else _ptr(a) for a in arrs])
+    ns = (C.c_size_t * 9)(*[0 if a is None else a.shape[1] for a in arrs])
+    ex = np.array([list(r) for r in extra_rows], dtype=np.uint64).reshape(-1, 13)
+    out = (C.c_size_t * 10)()
+    orc.lib.orc_check_ctls.restype = C.c_long
+    r = orc.lib.orc_check_ctls(ptrs, ns, _ptr(ex) if ex.size else None, C.c_size_t(ex.shape[0]), out)
+    if r < 0:
+        orc.lib.orc_last_error.restype = C.c_char_p
+        raise RuntimeError(orc.lib.orc_last_error().decode())
+    return [int(x) for x in out]
+
+
 def orc_verify_table(orc, table, cfg, proof, beta_gamma, state, labels=DEFAULT_LABELS):
     lib = orc.lib
     lib.orc_last_error.restype = C.c_char_p

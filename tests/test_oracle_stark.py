@@ -445,6 +445,48 @@ def test_cpu_segment_long_program_verifies(oracle, cfg):
     assert ok, err
 
 
+def test_memory_lookup_with_the_public_value_writes_needs_the_extra_looking_sum(oracle):
+    """verify_proof (verifier.rs:172-313) adds get_memory_extra_looking_sum(public_values, challenge) (:319-512) to the looking side of the
+    Memory lookup: the kernel writes the block metadata, trie roots, bloom filter, 256 block hashes and the registers to memory at
+    timestamp 2 without a Cpu row sending them.  A segment whose Memory table holds those 301 writes verifies WITH the sum computed from
+    the PublicValues and the segment's (beta, gamma), and fails on lookup 6 without it / with the sum of other public values."""
+    from zk_evm_b200.public_values import (PublicValues, RegistersData, flatten_public_values, memory_extra_looking_values,
+                                           memory_extra_looking_sum)
+    rng = np.random.default_rng(11)
+    pv = PublicValues()
+    pv.block_metadata.block_beneficiary = rng.bytes(20)
+    pv.block_metadata.block_timestamp, pv.block_metadata.block_number, pv.block_metadata.block_gas_used = 1700000000, 19807080, 12345678
+    pv.block_metadata.block_random, pv.block_metadata.block_base_fee = rng.bytes(32), 9_000_000_007
+    pv.block_metadata.block_bloom = [int.from_bytes(rng.bytes(32), "big") for _ in range(8)]
+    pv.block_hashes.prev_hashes = [rng.bytes(32) for _ in range(256)]
+    pv.block_hashes.cur_hash = rng.bytes(32)
+    pv.trie_roots_before.state_root, pv.trie_roots_after.receipts_root = rng.bytes(32), rng.bytes(32)
+    pv.extra_block_data.txn_number_after, pv.extra_block_data.gas_used_after = 7, 654321
+    pv.registers_before = RegistersData(program_counter=3, is_kernel=1, stack_len=0, stack_top=0, context=0, gas_used=0)
+    pv.registers_after = RegistersData(program_counter=0x1234, is_kernel=1, stack_len=2, stack_top=1 << 200, context=0, gas_used=77)
+    kernel_hash, kernel_len = rng.bytes(32), 60123
+    rows = memory_extra_looking_values(pv, kernel_hash, kernel_len)
+    assert len(rows) == 25 + 8 + 256 + 12 and all(len(r) == 13 and r[0] == 0 and r[1] == 0 and r[12] == 2 for r in rows)
+    assert len({(r[2], r[3]) for r in rows}) == len(rows)                     # one write per address
+    flat = flatten_public_values(pv)
+    cfg = TEST_CONFIG
+    tr, labels = traces.cpu_segment("PPMXJ", log_mem=10, extra_memory_rows=rows)
+    proofs, bg, _ = orc_prove_segment(oracle, cfg, tr, flat, labels=labels)
+    nc = cfg[1]
+    sums = np.zeros(10 * nc, dtype=np.uint64)
+    for c in range(nc):
+        sums[6 * nc + c] = memory_extra_looking_sum(pv, int(bg[2 * c]), int(bg[2 * c + 1]), kernel_hash, kernel_len)
+    ok, err = orc_verify_segment(oracle, cfg, proofs, flat, labels=labels, extra_looking_sums=sums)
+    assert ok, err
+    ok, err = orc_verify_segment(oracle, cfg, proofs, flat, labels=labels)
+    assert not ok and "lookup 6" in err
+    pv.block_metadata.block_number += 1
+    for c in range(nc):
+        sums[6 * nc + c] = memory_extra_looking_sum(pv, int(bg[2 * c]), int(bg[2 * c + 1]), kernel_hash, kernel_len)
+    ok, err = orc_verify_segment(oracle, cfg, proofs, flat, labels=labels, extra_looking_sums=sums)
+    assert not ok and "lookup 6" in err
+
+
 def test_cpu_segment_with_four_channel_timestamps_is_rejected(oracle):
     """the check that found the NUM_CHANNELS transcription error: memory timestamps computed with 4 channels do not match the lookups"""
     ok, err = _segment_verifies(oracle, "PPMXJ", num_channels=4)

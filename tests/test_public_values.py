@@ -113,3 +113,50 @@ def test_h256_limb_order_is_observe_root_order():
     pv = PublicValues()
     pv.trie_roots_before.state_root = h
     assert [int(v) for v in flatten_public_values(pv)[:8]] == want
+
+
+def test_memory_extra_looking_values_field_by_field():
+    """verifier.rs:547-737: (segment, index inside the segment) of every public-value write, the indices counted by hand from the
+    GlobalMetadata declaration (cpu/kernel/constants/global_metadata.rs:11-115) and memory/segments.rs:10-91"""
+    from zk_evm_b200.public_values import memory_extra_looking_values, memory_extra_looking_sum, RegistersData, GLOBAL_METADATA, P
+    assert len(GLOBAL_METADATA) == len(set(GLOBAL_METADATA)) == 54
+    pv = PublicValues()
+    m, e = pv.block_metadata, pv.extra_block_data
+    m.block_beneficiary = bytes(range(1, 21))
+    m.block_timestamp, m.block_number, m.block_difficulty, m.block_gaslimit, m.block_chain_id = 101, 102, 103, 104, 105
+    m.block_base_fee, m.block_gas_used, m.block_blob_gas_used, m.block_excess_blob_gas = 106, 107, 108, 109
+    m.block_random, m.parent_beacon_block_root = bytes([7] * 32), bytes([8] * 32)
+    m.block_bloom = [200 + i for i in range(8)]
+    pv.block_hashes.prev_hashes = [i.to_bytes(32, "big") for i in range(1000, 1256)]
+    pv.block_hashes.cur_hash = bytes([9] * 32)
+    e.txn_number_before, e.txn_number_after, e.gas_used_before, e.gas_used_after = 110, 111, 112, 113
+    tb, ta = pv.trie_roots_before, pv.trie_roots_after
+    tb.state_root, tb.transactions_root, tb.receipts_root = bytes([1] * 32), bytes([2] * 32), bytes([3] * 32)
+    ta.state_root, ta.transactions_root, ta.receipts_root = bytes([4] * 32), bytes([5] * 32), bytes([6] * 32)
+    pv.registers_before = RegistersData(1, 2, 3, 4, 5, 6)
+    pv.registers_after = RegistersData(11, 12, 13, 14, 15, 1 << 255)
+    rows = memory_extra_looking_values(pv, bytes([10] * 32), 4242)
+    val = lambda r: sum(v << (32 * i) for i, v in enumerate(r[4:12]))
+    got = {(r[2], r[3]): val(r) for r in rows}
+    assert len(got) == len(rows) == 301
+    assert all(r[0] == 0 and r[1] == 0 and r[12] == 2 and all(0 <= v < 1 << 32 for v in r[4:12]) for r in rows)
+    rep = lambda b: int.from_bytes(bytes([b] * 32), "big")
+    want = {6: rep(1), 7: rep(2), 8: rep(3), 9: rep(4), 10: rep(5), 11: rep(6),                   # trie root digests before / after
+            12: int.from_bytes(bytes(range(1, 21)), "big"), 13: 101, 14: 102, 15: 103, 16: rep(7), 17: 104, 18: 105, 19: 106,
+            20: 108, 21: 109, 22: 107, 23: 112, 24: 113, 25: rep(9), 26: rep(8), 42: 110, 43: 111, 45: rep(10), 46: 4242}
+    assert {k[1]: v for k, v in got.items() if k[0] == 5} == want                                   # Segment::GlobalMetadata = 5
+    assert [got[(24, i)] for i in range(8)] == [200 + i for i in range(8)]                          # Segment::GlobalBlockBloom
+    assert [got[(32, i)] for i in range(256)] == list(range(1000, 1256))                            # Segment::BlockHashes
+    assert [got[(33, i)] for i in range(12)] == [1, 2, 3, 4, 5, 6, 11, 12, 13, 14, 15, 1 << 255]    # Segment::RegistersStates
+    # without the eth_mainnet feature the three 4844 / 4788 fields are not written; cdk_erigon adds the burn address (index 53)
+    assert len(memory_extra_looking_values(pv, bytes(32), 1, eth_mainnet=False)) == 298
+    pv.burn_addr = 0xb0b
+    r = memory_extra_looking_values(pv, bytes(32), 1, cdk_erigon=True)
+    assert len(r) == 302 and r[1][:4] == [0, 0, 5, 53] and r[1][4] == 0xb0b
+    # the sum is add_data_write's (verifier.rs:492-512): 1 / (gamma + sum_i row_i beta^i) per row
+    beta, gamma = 0x1234567, 0x7654321
+    s = 0
+    for row in rows:
+        s = (s + pow((sum(v * pow(beta, i, P) for i, v in enumerate(row)) + gamma) % P, P - 2, P)) % P
+    pv.burn_addr = None
+    assert memory_extra_looking_sum(pv, beta, gamma, bytes([10] * 32), 4242) == s

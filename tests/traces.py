@@ -967,13 +967,16 @@ def valid_segment(seed=0, log_cpu=6, log_mem=6, log_memcont=7, k=40, halt_final=
     return tr
 
 
-def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=0, k_before=6, num_channels=5, sponge_ops=None, packing_ops=None, inputs=(), keccak_inputs=None):
+def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=0, k_before=6, num_channels=5, sponge_ops=None, packing_ops=None, inputs=(), keccak_inputs=None,
+                extra_memory_rows=()):
     """A VALID multi-table segment around an executing Cpu program (no PROVER_INPUT, shifts, general memory or Keccak instructions: their
     lookups need more tables): Cpu (cpu_program_trace), Arithmetic (a row pair / row per MUL, DIV, MOD, ADDMOD, MULMOD executed), Logic (a row
     per AND / OR / XOR), Memory (every memory operation the Cpu rows send: the opcode fetch of every cycle, the general-purpose channels,
     the partial channel — plus the MemBefore initialisation writes), MemBefore, MemAfter.  Written from the reference's lookup definitions
     (cpu_stark.rs:324-379 mem_time_and_channel / ctl_data_code_memory / ctl_data_gp_memory / ctl_data_partial_memory with NUM_CHANNELS = 5,
     membus.rs:39; memory_stark.rs:35-95; all_stark.rs:153-417), so that a verifying segment checks OUR descriptors against them.
+    `extra_memory_rows`: memory operations that no table sends — the kernel's writes of the public values (verifier.rs:536-737), each the 13
+    values of the memory lookup; the Memory lookup then balances only with the verifier's extra looking sum (verifier.rs:319-512).
     -> (traces[9], labels)"""
     rng = np.random.default_rng(seed)
     halt_final = len(program) + 8
@@ -1077,6 +1080,8 @@ def cpu_segment(program, log_cpu=7, log_mem=9, log_memcont=7, log_logic=5, seed=
                 ops.append((ctx, seg, virt + L - 1 - i, t_, is_read, 1, [data[i]] + [0] * 7))
         packing[69] = np.minimum(np.arange(256), 255).astype(np.uint64)
         packing[70, :256] = np.bincount(packing[37:69].astype(np.int64).ravel(), minlength=256).astype(np.uint64)
+    for row in extra_memory_rows:                                                           # (is_read, context, segment, virt, value limbs, timestamp)
+        ops.append((row[1], row[2], row[3], row[12], row[0], 1, [int(x) for x in row[4:12]]))
     before_addrs = [(0, 5, 100 + i) for i in range(k_before)]
     before_vals = rng.integers(1, 1 << 32, size=(k_before, 8), dtype=np.uint64)
     for a, v in zip(before_addrs, before_vals):

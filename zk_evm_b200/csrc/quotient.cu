@@ -91,9 +91,9 @@ void constraints_record(Ctx& c, const TableDev& t, const QuotientArgs& q, uint64
     c.count_launch();
     c.check_launch("constraints_record_kernel");
     if (verify) {
-        uint64_t got = 0;
-        c.d2h(&got, cnt.get(), 8);
-        ZK_REQUIRE((uint32_t)got == expect, "constraints_record: the evaluator yielded " + std::to_string((uint32_t)got) + " constraints, the buffer has " +
+        uint32_t got = 0;         // the kernel writes one 32-bit word (initcheck, profiles/r2v: reading 8 bytes here read 4 nobody wrote)
+        c.d2h(&got, cnt.get(), 4);
+        ZK_REQUIRE(got == expect, "constraints_record: the evaluator yielded " + std::to_string(got) + " constraints, the buffer has " +
                                                 std::to_string(expect) + " columns");
         c.table_cache.emplace(key, DevBuf(&c, 8));
     }
