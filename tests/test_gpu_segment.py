@@ -53,6 +53,36 @@ def test_executing_segments_of_the_remaining_cpu_families(ctx, oracle, which):
     assert ok, err
 
 
+def test_segment_with_the_public_value_writes_through_the_whole_boundary(ctx, oracle):
+    """PublicValues -> flatten_public_values (what the transcript observes, all 2217 elements) + the 301 memory writes the kernel makes
+    of them (verifier.rs:547-737) in the Memory table: device proofs == oracle proofs word for word, and the restated verify_proof
+    accepts them with get_memory_extra_looking_sum (verifier.rs:319-512) computed from the same PublicValues and the DEVICE's (beta, gamma)"""
+    from zk_evm_b200.public_values import PublicValues, RegistersData, flatten_public_values, memory_extra_looking_values, memory_extra_looking_sum
+    rng = np.random.default_rng(12)
+    pv = PublicValues()
+    pv.block_metadata.block_beneficiary, pv.block_metadata.block_number, pv.block_metadata.block_random = rng.bytes(20), 19807080, rng.bytes(32)
+    pv.block_metadata.block_bloom = [int.from_bytes(rng.bytes(32), "big") for _ in range(8)]
+    pv.block_hashes.prev_hashes, pv.block_hashes.cur_hash = [rng.bytes(32) for _ in range(256)], rng.bytes(32)
+    pv.trie_roots_before.state_root, pv.trie_roots_after.state_root = rng.bytes(32), rng.bytes(32)
+    pv.registers_after = RegistersData(program_counter=0x1234, is_kernel=1, stack_len=2, stack_top=1 << 200, gas_used=77)
+    kernel_hash, kernel_len = rng.bytes(32), 60123
+    rows = memory_extra_looking_values(pv, kernel_hash, kernel_len)
+    flat = flatten_public_values(pv)
+    tr, labels = traces.cpu_segment("PPMXJ", log_mem=10, extra_memory_rows=rows)
+    cfg = STANDARD_FAST
+    ap = zk.prove_with_traces(ctx, tr, flat, zk.StarkConfig(*cfg), zk.KernelLabels(*labels))
+    want, bg, caps = orc_prove_segment(oracle, cfg, tr, flat, labels=labels)
+    _same(ap, want, bg, caps)
+    nc = cfg[1]
+    sums = np.zeros(10 * nc, dtype=np.uint64)
+    for c in range(nc):
+        sums[6 * nc + c] = memory_extra_looking_sum(pv, int(ap.ctl_challenges[2 * c]), int(ap.ctl_challenges[2 * c + 1]), kernel_hash, kernel_len)
+    ok, err = orc_verify_segment(oracle, cfg, ap.stark_proofs, flat, labels=labels, extra_looking_sums=sums)
+    assert ok, err
+    ok, err = orc_verify_segment(oracle, cfg, ap.stark_proofs, flat, labels=labels)
+    assert not ok and "lookup 6" in err
+
+
 @pytest.mark.parametrize("cfg", [TEST_CONFIG, STANDARD_FAST])
 def test_valid_segment_matches_oracle_and_verifies(ctx, oracle, cfg):
     tr = traces.valid_segment(seed=11)
