@@ -401,12 +401,14 @@ struct ExtraBlockData {
     std::array<F, 4> checkpoint_consolidated_hash{};
     U256 txn_number_before, txn_number_after, gas_used_before, gas_used_after;
 };
+struct RegistersData { U256 program_counter, is_kernel, stack_len, stack_top, context, gas_used; };   // proof.rs:537-550 (written to memory, not observed)
 struct PublicValues {
     TrieRoots trie_roots_before, trie_roots_after;
     BlockMetadata block_metadata;
     BlockHashes block_hashes;
     ExtraBlockData extra_block_data;
     std::optional<U256> burn_addr;                     // cdk_erigon only
+    RegistersData registers_before, registers_after;
 };
 namespace detail {
 inline void u256_limbs(std::vector<F>& o, const U256& x, size_t count = 8) {                     // util.rs:101-113
@@ -452,6 +454,85 @@ inline std::vector<F> flatten_public_values(const PublicValues& pv, bool eth_mai
         u256_limbs(o, *pv.burn_addr);
     }
     return o;
+}
+
+// ---- the memory writes the kernel makes of the public values, which no Cpu row sends (verifier.rs:319-512, 536-737) --------------------
+// The verifier adds them to the looking side of the Memory lookup; a host that builds Memory traces needs the same rows.
+// GlobalMetadata indices inside Segment::GlobalMetadata (cpu/kernel/constants/global_metadata.rs:11-115, `unscale`), segments unscaled
+// (memory/segments.rs:10-91).
+namespace global_metadata {
+enum : uint64_t { StateTrieRootDigestBefore = 6, TransactionTrieRootDigestBefore, ReceiptTrieRootDigestBefore, StateTrieRootDigestAfter,
+                  TransactionTrieRootDigestAfter, ReceiptTrieRootDigestAfter, BlockBeneficiary, BlockTimestamp, BlockNumber, BlockDifficulty,
+                  BlockRandom, BlockGasLimit, BlockChainId, BlockBaseFee, BlockBlobGasUsed, BlockExcessBlobGas, BlockGasUsed, BlockGasUsedBefore,
+                  BlockGasUsedAfter, BlockCurrentHash, ParentBeaconBlockRoot, TxnNumberBefore = 42, TxnNumberAfter, KernelHash = 45, KernelLen,
+                  BurnAddr = 53, COUNT = 54 };
+}
+namespace segment { enum : uint64_t { GlobalMetadata = 5, GlobalBlockBloom = 24, BlockHashes = 32, RegistersStates = 33 }; }
+using MemoryLookupRow = std::array<F, 13>;             // is_read, context, segment, virt, eight 32-bit value limbs, timestamp
+// get_memory_extra_looking_values (verifier.rs:547-737), in its order.  kernel_code_hash / kernel_code_len = KERNEL.code_hash /
+// KERNEL.code.len(): the kernel is assembled by the host, like the four kernel labels.
+inline std::vector<MemoryLookupRow> memory_extra_looking_values(const PublicValues& pv, const H256& kernel_code_hash, uint64_t kernel_code_len,
+                                                                bool eth_mainnet = true, bool cdk_erigon = false) {
+    namespace gm = global_metadata;
+    std::vector<MemoryLookupRow> rows;
+    auto row = [&](uint64_t seg, uint64_t index, const U256& val) {            // add_extra_looking_row, verifier.rs:720-735
+        MemoryLookupRow r{};
+        r[2] = seg; r[3] = index;
+        for (size_t j = 0; j < 8; j++) r[4 + j] = (val.limbs[j / 2] >> (32 * (j % 2))) & 0xFFFFFFFFull;
+        r[12] = 2;
+        rows.push_back(r);
+    };
+    auto h2u = [](const H256& h) { return U256::from_big_endian(h.data(), 32); };
+    auto meta = [&](uint64_t field, const U256& val) { row(segment::GlobalMetadata, field, val); };
+    const BlockMetadata& m = pv.block_metadata;
+    const ExtraBlockData& e = pv.extra_block_data;
+    meta(gm::BlockBeneficiary, U256::from_big_endian(m.block_beneficiary.data(), 20));
+    if (cdk_erigon) {
+        if (!pv.burn_addr) throw Error(ZKGPU_ERR_INVALID, "There should be an address set in cdk_erigon.");
+        meta(gm::BurnAddr, *pv.burn_addr);
+    }
+    meta(gm::BlockTimestamp, m.block_timestamp); meta(gm::BlockNumber, m.block_number); meta(gm::BlockRandom, h2u(m.block_random));
+    meta(gm::BlockDifficulty, m.block_difficulty); meta(gm::BlockGasLimit, m.block_gaslimit); meta(gm::BlockChainId, m.block_chain_id);
+    meta(gm::BlockBaseFee, m.block_base_fee); meta(gm::BlockCurrentHash, h2u(pv.block_hashes.cur_hash)); meta(gm::BlockGasUsed, m.block_gas_used);
+    if (eth_mainnet) {
+        meta(gm::BlockBlobGasUsed, m.block_blob_gas_used); meta(gm::BlockExcessBlobGas, m.block_excess_blob_gas);
+        meta(gm::ParentBeaconBlockRoot, h2u(m.parent_beacon_block_root));
+    }
+    meta(gm::TxnNumberBefore, e.txn_number_before); meta(gm::TxnNumberAfter, e.txn_number_after);
+    meta(gm::BlockGasUsedBefore, e.gas_used_before); meta(gm::BlockGasUsedAfter, e.gas_used_after);
+    meta(gm::StateTrieRootDigestBefore, h2u(pv.trie_roots_before.state_root));
+    meta(gm::TransactionTrieRootDigestBefore, h2u(pv.trie_roots_before.transactions_root));
+    meta(gm::ReceiptTrieRootDigestBefore, h2u(pv.trie_roots_before.receipts_root));
+    meta(gm::StateTrieRootDigestAfter, h2u(pv.trie_roots_after.state_root));
+    meta(gm::TransactionTrieRootDigestAfter, h2u(pv.trie_roots_after.transactions_root));
+    meta(gm::ReceiptTrieRootDigestAfter, h2u(pv.trie_roots_after.receipts_root));
+    meta(gm::KernelHash, h2u(kernel_code_hash)); meta(gm::KernelLen, U256(kernel_code_len));
+    for (size_t i = 0; i < 8; i++) row(segment::GlobalBlockBloom, i, m.block_bloom[i]);
+    if (pv.block_hashes.prev_hashes.size() != 256) throw Error(ZKGPU_ERR_INVALID, "256 previous block hashes");
+    for (size_t i = 0; i < 256; i++) row(segment::BlockHashes, i, h2u(pv.block_hashes.prev_hashes[i]));
+    const RegistersData* regs[2] = {&pv.registers_before, &pv.registers_after};
+    for (size_t k = 0; k < 2; k++) {
+        const U256 v[6] = {regs[k]->program_counter, regs[k]->is_kernel, regs[k]->stack_len, regs[k]->stack_top, regs[k]->context, regs[k]->gas_used};
+        for (size_t i = 0; i < 6; i++) row(segment::RegistersStates, 6 * k + i, v[i]);
+    }
+    return rows;
+}
+namespace detail {
+constexpr F GL_P = 0xFFFFFFFF00000001ull;
+inline F gl_mul(F a, F b) { return (F)((unsigned __int128)a * b % GL_P); }
+inline F gl_add(F a, F b) { return (F)(((unsigned __int128)a + b) % GL_P); }
+inline F gl_inv(F a) { F r = 1, e = GL_P - 2; while (e) { if (e & 1) r = gl_mul(r, a); a = gl_mul(a, a); e >>= 1; } return r; }
+}  // namespace detail
+// get_memory_extra_looking_sum (verifier.rs:319-512) for one challenge: sum over those rows of 1 / (gamma + sum_i row_i beta^i)
+inline F memory_extra_looking_sum(const PublicValues& pv, F beta, F gamma, const H256& kernel_code_hash, uint64_t kernel_code_len,
+                                  bool eth_mainnet = true, bool cdk_erigon = false) {
+    F sum = 0;
+    for (const MemoryLookupRow& r : memory_extra_looking_values(pv, kernel_code_hash, kernel_code_len, eth_mainnet, cdk_erigon)) {
+        F acc = 0;
+        for (size_t i = r.size(); i-- > 0;) acc = detail::gl_add(detail::gl_mul(acc, beta), r[i] % detail::GL_P);
+        sum = detail::gl_add(sum, detail::gl_inv(detail::gl_add(acc, gamma)));
+    }
+    return sum;
 }
 
 // ---- a stream of segments, several in flight on one GPU (zero/src/prover.rs:205-236 dispatches every segment as its own proving job and

@@ -107,8 +107,19 @@ int main(int argc, char** argv) {
             e.checkpoint_state_trie_root = h256();
             memcpy(e.checkpoint_consolidated_hash.data(), &b.at(pos + 31) - 31, 32); pos += 32;
             e.txn_number_before = u256(); e.txn_number_after = u256(); e.gas_used_before = u256(); e.gas_used_after = u256();
+            if (pos == b.size()) {
+                for (F x : flatten_public_values(pv)) printf("%llu\n", (unsigned long long)x);
+                return 0;
+            }
+            // the longer form: registers before / after, kernel hash, kernel length, beta, gamma -> the extra Memory lookup rows and their sum
+            for (RegistersData* r : {&pv.registers_before, &pv.registers_after}) {
+                r->program_counter = u256(); r->is_kernel = u256(); r->stack_len = u256(); r->stack_top = u256(); r->context = u256(); r->gas_used = u256();
+            }
+            H256 kh = h256();
+            uint64_t klen = u256().limbs[0], beta = u256().limbs[0], gamma = u256().limbs[0];
             if (pos != b.size()) throw std::runtime_error("trailing bytes");
-            for (F x : flatten_public_values(pv)) printf("%llu\n", (unsigned long long)x);
+            for (const auto& r : memory_extra_looking_values(pv, kh, klen)) for (F x : r) printf("%llu\n", (unsigned long long)x);
+            printf("%llu\n", (unsigned long long)memory_extra_looking_sum(pv, beta, gamma, kh, klen));
             return 0;
         }
         if (mode == "stream") {

@@ -115,6 +115,30 @@ def test_public_values_flattening_python_and_cpp(harness, tmp_path):
     assert harness("pubvals", path, ok=False).returncode != 0
 
 
+def test_memory_extra_looking_values_python_and_cpp(harness, tmp_path):
+    """get_memory_extra_looking_values / _sum (verifier.rs:319-512, 547-737): the C++ and Python host mirrors against each other on random
+    public values (the Python one is checked field by field in test_public_values.py)"""
+    from zk_evm_b200 import public_values as pvm
+    rng = np.random.default_rng(23)
+    pv = _random_public_values(19)
+    u = lambda: int.from_bytes(rng.bytes(32), "big")
+    pv.registers_before = pvm.RegistersData(u(), 1, u(), u(), u(), u())
+    pv.registers_after = pvm.RegistersData(u(), 0, u(), u(), u(), u())
+    kh, klen, beta, gamma = rng.bytes(32), 61234, int(rng.integers(1, 1 << 62)), int(rng.integers(1, 1 << 62))
+    be = lambda x: int(x).to_bytes(32, "big")
+    blob = _pack_public_values(pv)
+    for r in (pv.registers_before, pv.registers_after):
+        blob += b"".join(be(x) for x in (r.program_counter, r.is_kernel, r.stack_len, r.stack_top, r.context, r.gas_used))
+    blob += kh + be(klen) + be(beta) + be(gamma)
+    path = tmp_path / "pv_extra.bin"
+    path.write_bytes(blob)
+    got = [int(x) for x in harness("pubvals", path).stdout.split()]
+    rows = pvm.memory_extra_looking_values(pv, kh, klen)
+    assert len(got) == 13 * 301 + 1
+    assert got[:-1] == [v for r in rows for v in r]
+    assert got[-1] == pvm.memory_extra_looking_sum(pv, beta, gamma, kh, klen)
+
+
 @pytest.mark.parametrize("table,lg,cfg", [(traces.T_MEM_AFTER, 7, TEST_CONFIG), (traces.T_LOGIC, 6, STANDARD_FAST)])
 def test_cpp_proof_decoder_on_oracle_proofs(harness, oracle, tmp_path, table, lg, cfg):
     tr = traces.memcont_trace(lg, 3) if table == traces.T_MEM_AFTER else traces.logic_trace(lg, 3)
