@@ -367,6 +367,58 @@ long orc_check_ctls(const uint64_t* const* traces, const size_t* ns, const uint6
     } catch (const std::exception& e) { g_orc_err = e.what(); return -1; }
 }
 
+// The reference's second per-table sanity test, starky `test_stark_circuit_constraints`, compares the packed evaluator with the
+// recursion-circuit one; the circuit evaluators are outside this path, but the property it protects — ONE set of constraints, whatever
+// type it is evaluated in — has an analogue here, where the same templates are evaluated over the base field (prover: LDE points) and
+// over the quadratic extension (verifier: at zeta).  On a random frame: (1) evaluating in the extension at base-field points gives the
+// embedded base-field result; (2) the constraints have base-field coefficients, so they commute with the extension's automorphism
+// a + bX -> a - bX: C(conj(frame)) = conj(C(frame)) for a random EXTENSION frame and extension selectors.
+// -> 0 when both hold, bit 0 / bit 1 for a failure of (1) / (2); -1 on error.
+long orc_table_eval_consistency(uint32_t table, uint64_t seed, const uint64_t labels[4]) {
+    try {
+        const size_t ncols = zkstark::table_num_columns(table);
+        if (ncols == 0) throw std::runtime_error("bad table");
+        uint64_t st = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+        auto rnd = [&]() { st += 0x9E3779B97F4A7C15ull; uint64_t z = st; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                           return gl_from_u64(z ^ (z >> 31)); };
+        auto conj = [](Ext x) { return Ext(x.a, gl_neg(x.b)); };
+        const uint64_t alpha = rnd();
+        auto run_ext = [&](const std::vector<Ext>& l, const std::vector<Ext>& n, Ext zl, Ext lf, Ext ll) {
+            std::vector<OE> lv(ncols), nv(ncols);
+            for (size_t c = 0; c < ncols; c++) { lv[c] = OE(l[c]); nv[c] = OE(n[c]); }
+            ConsumerT<OE> yc;
+            yc.alphas.push_back(OE(Ext(alpha, 0))); yc.acc.push_back(OE::zero());
+            yc.z_last = OE(zl); yc.lagrange_first = OE(lf); yc.lagrange_last = OE(ll);
+            RowOE rl{lv.data()}, rn{nv.data()};
+            zkstark::eval_table<OE>(table, rl, rn, yc, params_from(labels));
+            return yc.acc[0].e;
+        };
+        long bad = 0;
+        // (1)
+        std::vector<uint64_t> lb(ncols), nb(ncols);
+        for (auto& x : lb) x = rnd();
+        for (auto& x : nb) x = rnd();
+        const uint64_t zl = rnd(), lf = rnd(), ll = rnd();
+        ConsumerT<OF> yb;
+        yb.alphas.push_back(OF(alpha)); yb.acc.push_back(OF(0));
+        yb.z_last = OF(zl); yb.lagrange_first = OF(lf); yb.lagrange_last = OF(ll);
+        RowOF rl{lb.data()}, rn{nb.data()};
+        zkstark::eval_table<OF>(table, rl, rn, yb, params_from(labels));
+        std::vector<Ext> le(ncols), ne(ncols);
+        for (size_t c = 0; c < ncols; c++) { le[c] = Ext(lb[c], 0); ne[c] = Ext(nb[c], 0); }
+        if (run_ext(le, ne, Ext(zl, 0), Ext(lf, 0), Ext(ll, 0)) != Ext(yb.acc[0].v, 0)) bad |= 1;
+        if (yb.acc[0].v == 0) bad |= 4;      // a random frame does not satisfy the constraints
+        // (2)
+        for (size_t c = 0; c < ncols; c++) { le[c] = Ext(rnd(), rnd()); ne[c] = Ext(rnd(), rnd()); }
+        const Ext ezl(rnd(), rnd()), elf(rnd(), rnd()), ell(rnd(), rnd());
+        const Ext v = run_ext(le, ne, ezl, elf, ell);
+        for (size_t c = 0; c < ncols; c++) { le[c] = conj(le[c]); ne[c] = conj(ne[c]); }
+        if (run_ext(le, ne, conj(ezl), conj(elf), conj(ell)) != conj(v)) bad |= 2;
+        if (v.b == 0) bad |= 4;              // the extension part is really exercised
+        return bad;
+    } catch (const std::exception& e) { g_orc_err = e.what(); return -1; }
+}
+
 // "stage\tseconds\n" lines accumulated since the last call with reset != 0 (main-thread wall clock of the prover's stages)
 size_t orc_stage_report(char* buf, size_t cap, int reset) {
     std::string out;

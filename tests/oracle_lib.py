@@ -186,6 +186,17 @@ def orc_table_constraint_degree(orc, table, log_n, seed=1, labels=DEFAULT_LABELS
     return int(d)
 
 
+def orc_table_eval_consistency(orc, table, seed=1, labels=DEFAULT_LABELS):
+    """base-field vs extension-field evaluation of the same constraint templates (oracle_api.cpp) -> 0 when consistent"""
+    lab = np.array(labels, dtype=np.uint64)
+    orc.lib.orc_table_eval_consistency.restype = C.c_long
+    r = orc.lib.orc_table_eval_consistency(C.c_uint32(table), C.c_uint64(seed), _ptr(lab))
+    if r < 0:
+        orc.lib.orc_last_error.restype = C.c_char_p
+        raise RuntimeError(orc.lib.orc_last_error().decode())
+    return int(r)
+
+
 def orc_check_ctls(orc, traces, extra_rows=()):
     """starky's debug check_ctls restated (prover.rs:165-184): per cross-table lookup, the number of distinct rows whose multiplicity
     on the looking side (plus `extra_rows` for the Memory lookup) differs from the looked side -> list of 10 counts"""

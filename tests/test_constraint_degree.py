@@ -28,3 +28,12 @@ def test_stark_low_degree_other_sizes(oracle, table):
     for lg in (3, 7):
         d = oracle_lib.orc_table_constraint_degree(oracle, table, lg, 3)
         assert (1 << lg) <= d <= 3 * (1 << lg) - 1
+
+
+@pytest.mark.parametrize("table", sorted(EXPECTED))
+def test_base_and_extension_evaluations_agree(oracle, table):
+    """the analogue of starky's `test_stark_circuit_constraints` (same call sites as above) for this path's two evaluation types: the
+    prover evaluates the templates over the base field, the verifier over the quadratic extension; they agree on base-field frames and
+    the extension evaluation commutes with conjugation (the constraints have base-field coefficients)"""
+    for seed in (1, 2, 3):
+        assert oracle_lib.orc_table_eval_consistency(oracle, table, seed) == 0
