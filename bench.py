@@ -483,7 +483,8 @@ def run_ours(args):
             roof["issue"] = {"bound": "integer issue slots", "achieved": pps * INSTR_PER_PERMUTATION / 1e12, "peak": peak_issue / 1e12, "unit": "T thread-instr/s",
                              "frac": pps * INSTR_PER_PERMUTATION / peak_issue,
                              "source": "profiles/r2r_ncu_leaf_hash_keccak.raw.csv.gz: %.1f k thread-instructions per permutation (ncu smsp__inst_executed.sum x 32 / permutations), ALU pipe 81 %% busy" % (INSTR_PER_PERMUTATION / 1e3)}
-        cpu = None if args.no_cpu_baseline else cpu_baseline(args, log_ns)
+        # the CPU baseline is timed at N = 1 only (at N > 1 the other ranks' host threads would share the cores with it)
+        cpu = None if (args.no_cpu_baseline or world > 1) else cpu_baseline(args, log_ns)
         line = {"metric": METRIC, "value": segs / (ms / 1e3), "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
                 "dtype": "u64", "data": "synthetic", "config": config_record(args, log_ns),
