@@ -331,6 +331,7 @@ long orc_table_constraint_degree(uint32_t table, unsigned log_n, uint64_t seed, 
 long orc_check_ctls(const uint64_t* const* traces, const size_t* ns, const uint64_t* extra_rows, size_t n_extra, size_t mismatches[10]) {
     try {
         auto ctls = zkstark::all_cross_table_lookups();
+        if (ctls.size() != zkstark::NUM_CTLS) throw std::runtime_error("all_cross_table_lookups().len() != NUM_CTLS");   // all_stark.rs:451-454 check_num_ctls
         std::vector<std::vector<const uint64_t*>> cols(9);
         for (uint32_t t = 0; t < 9; t++) {
             if (!traces[t]) continue;

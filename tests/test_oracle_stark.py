@@ -165,6 +165,16 @@ def test_keccak_sponge_generator_is_keccak256():
     assert dg[5].hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"      # keccak256("abc")
 
 
+def test_keccak_sponge_test_generation_of_the_reference(oracle):
+    """keccak_sponge_stark.rs:993-1021 `test_generation`: the operation it builds (input [1, 2, 3] at (0, Segment::Code, 0), timestamp 0)
+    gives ONE row whose updated_digest_state_bytes are keccak256([1, 2, 3]) (the well-known digest, written out here)"""
+    tr, dg = traces.keccak_sponge_trace(8, [(0, 0, 0, 0, bytes([1, 2, 3]))])
+    assert int(tr[0, 0]) == 0 and [int(v) for v in tr[6:142, 0]].index(1) == 3      # rows.len() == 1: the first row is already the final one (3 input bytes)
+    assert bytes(int(v) for v in tr[404:436, 0]).hex() == "f1885eda54b7a053318cd41e2093220dab15d65381b1157a3633a83bfd5c9239"
+    assert dg[0].hex() == "f1885eda54b7a053318cd41e2093220dab15d65381b1157a3633a83bfd5c9239"
+    assert oracle_lib.orc_check_table_rows(oracle, traces.T_KECCAK_SPONGE, tr) == []
+
+
 @pytest.mark.parametrize("cfg", [TEST_CONFIG, STANDARD_FAST])
 def test_valid_keccak_sponge_trace_verifies(oracle, cfg):
     """generated rows => all 706 KeccakSponge constraints + the byte range-check lookup hold (the reference's test_generation pattern,
@@ -418,6 +428,22 @@ def test_cpu_demo_program_verifies(oracle, cfg):
     ok, err, st2 = orc_verify_table(oracle, traces.T_CPU, cfg, proof, bg, STATE0)
     assert ok, err
     assert np.array_equal(st, st2)
+
+
+def test_arithmetic_basic_trace_of_the_reference(oracle):
+    """arithmetic_stark.rs:374-451 `basic_trace`, the reference's own expected values: the ten operations it generates, the rows it
+    expects them on (two-row operations included) and the single-word answers it reads from OUTPUT_REGISTER — reproduced by the restated
+    generator; and the transcribed constraints vanish on every row of that trace."""
+    ops = [("add", 123, 456), ("mulmod", 123, 456, 1007), ("addmod", 1234, 567, 1007), ("mul", 123, 456), ("mod", 128, 13),
+           ("lt", 128, 13), ("lt", 13, 128), ("lt", 128, 128), ("div", 128, 13), ("byte", 30, 0xABCD)]
+    t, first = traces.arithmetic_trace_from_operations(ops)
+    assert t.shape == (116, 1 << 16)                                     # NUM_ARITH_COLUMNS x RANGE_MAX
+    expected_output = [(0, 579), (1, 703), (3, 794), (5, 56088), (6, 11), (8, 0), (9, 1), (10, 0), (11, 9), (13, 0xAB)]
+    assert first == [row for row, _ in expected_output]
+    for row, expected in expected_output:
+        assert int(t[66, row]) == expected                               # OUTPUT_REGISTER.start
+        assert not t[67:82, row].any()                                   # "...other registers should be zero"
+    assert oracle_lib.orc_check_table_rows(oracle, traces.T_ARITHMETIC, t) == []
 
 
 # ---- a VALID multi-table segment around an executing Cpu program: the cross-table lookups Cpu -> Memory / Arithmetic / Logic ----------

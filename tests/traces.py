@@ -718,6 +718,37 @@ def arithmetic_mul_rows(a, b):
     return out, [c & 0xFFFF for c in q], [c >> 16 for c in q]
 
 
+def arithmetic_byte_row(idx, val):
+    """BYTE (byte.rs:108-200 generate): index decomposition, the multiplexer tree over the value's limbs, the inverse of the high-limb sum -> the row"""
+    M = (1 << 256) - 1
+    row = [0] * 116
+    row[13] = 1                                                                   # IS_BYTE
+    il = [(idx >> (16 * i)) & 0xFFFF for i in range(16)]
+    row[18:34], row[34:50] = il, [(val >> (16 * i)) & 0xFFFF for i in range(16)]
+    for i in range(5):
+        row[82 + i] = (idx >> i) & 1                                              # BYTE_IDX_DECOMP
+    row[87] = il[0] >> 5                                                          # BYTE_IDX_DECOMP_HI
+    hi_sum = (row[87] + sum(il[1:])) % P
+    inv = pow(hi_sum, P - 2, P) if hi_sum else 1
+    row[91:95] = [(inv >> (16 * i)) & 0xFFFF for i in range(4)]                   # BYTE_IDX_HI_LIMB_SUM_INV_0..3
+    row[90] = int(hi_sum != 0)                                                    # BYTE_IDX_IS_LARGE
+    lvl, src, dest = 3, 34, 98
+    while True:
+        ln = 1 << lvl
+        src += (0 if (idx >> (lvl + 1)) & 1 else 1) * ln
+        row[dest:dest + ln] = row[src:src + ln]
+        if lvl == 0:
+            break
+        src, dest, lvl = dest, dest + ln, lvl - 1
+    lo, hi = row[dest] & 0xFF, row[dest] >> 8
+    row[88], row[89] = lo << 8, hi                                                # BYTE_LAST_LIMB_LO (stored * 256), _HI
+    row[113] = lo if idx & 1 else hi                                              # tree[15]
+    out = row[113] if idx < 32 else 0
+    assert out == ((val >> (8 * (31 - idx))) & 0xFF if idx < 32 else 0)
+    row[66:82] = [(out >> (16 * i)) & 0xFFFF for i in range(16)]
+    return row
+
+
 def arithmetic_mul_trace(log_n, seed, nops=200):
     """ArithmeticStark trace of MUL, SHL and BYTE operations (arithmetic_stark.rs:158-190 + mul.rs / shift.rs / byte.rs generate), incl. edge operands"""
     rng = np.random.default_rng(seed)
@@ -742,31 +773,7 @@ def arithmetic_mul_trace(log_n, seed, nops=200):
                  [(int(rng.integers(0, 40)), int.from_bytes(rng.bytes(32), "little")) for _ in range(40)]
     for j, (idx, val) in enumerate(byte_cases):
         k = kb + j
-        row = [0] * 116
-        row[13] = 1                                                                   # IS_BYTE
-        il = [(idx >> (16 * i)) & 0xFFFF for i in range(16)]
-        row[18:34], row[34:50] = il, [(val >> (16 * i)) & 0xFFFF for i in range(16)]
-        for i in range(5):
-            row[82 + i] = (idx >> i) & 1                                              # BYTE_IDX_DECOMP
-        row[87] = il[0] >> 5                                                          # BYTE_IDX_DECOMP_HI
-        hi_sum = (row[87] + sum(il[1:])) % P
-        inv = pow(hi_sum, P - 2, P) if hi_sum else 1
-        row[91:95] = [(inv >> (16 * i)) & 0xFFFF for i in range(4)]                   # BYTE_IDX_HI_LIMB_SUM_INV_0..3
-        row[90] = int(hi_sum != 0)                                                    # BYTE_IDX_IS_LARGE
-        lvl, src, dest = 3, 34, 98
-        while True:
-            ln = 1 << lvl
-            src += (0 if (idx >> (lvl + 1)) & 1 else 1) * ln
-            row[dest:dest + ln] = row[src:src + ln]
-            if lvl == 0:
-                break
-            src, dest, lvl = dest, dest + ln, lvl - 1
-        lo, hi = row[dest] & 0xFF, row[dest] >> 8
-        row[88], row[89] = lo << 8, hi                                                # BYTE_LAST_LIMB_LO (stored * 256), _HI
-        row[113] = lo if idx & 1 else hi                                              # tree[15]
-        out = row[113] if idx < 32 else 0
-        assert out == ((val >> (8 * (31 - idx))) & 0xFF if idx < 32 else 0)
-        row[66:82] = [(out >> (16 * i)) & 0xFFFF for i in range(16)]
+        row = arithmetic_byte_row(idx, val)
         t[:, k] = row
     # SHL (shift.rs:41-76): (shift, input, 1 << shift or 0) in the three input registers, the MUL machinery on registers 1 and 2
     L = lambda x: [(x >> (16 * i)) & 0xFFFF for i in range(16)]
@@ -872,6 +879,52 @@ def arithmetic_modular_rows(op, a, b, m):
     row1[66:82] = _limbs(result)                                                              # OUTPUT_REGISTER
     row1[82:98] = _limbs(out) if op == "div" else quot_l[:16]                                 # AUX_INPUT_REGISTER_0: the other of (quotient, remainder)
     return row1, row2, result
+
+
+def arithmetic_operation_rows(op, a, b, c=0):
+    """Operation::to_rows (arithmetic/mod.rs:226-340) for one operation -> (list of one or two 116-column rows, result): the same row builders
+    the traces above use, behind the reference's operation names"""
+    M = 1 << 256
+    if op in ("add", "sub", "lt", "gt"):                         # addcy.rs:71-95 generate
+        if op == "add":
+            out, aux = (a + b) % M, (a + b) >> 256
+        elif op == "sub":
+            out, aux = (a - b) % M, int(a < b)
+        elif op == "lt":
+            out, aux = int(a < b), (a - b) % M
+        else:
+            out, aux = int(a > b), (b - a) % M
+        row = [0] * 116
+        row[{"add": 0, "sub": 2, "lt": 11, "gt": 12}[op]] = 1
+        row[18:34], row[34:50], row[66:82], row[82:98] = _limbs(a), _limbs(b), _limbs(out), _limbs(aux)
+        return [row], out
+    if op == "mul":
+        out, lo, hi = arithmetic_mul_rows(a, b)
+        row = [0] * 116
+        row[1] = 1
+        row[18:34], row[34:50], row[66:82], row[82:98], row[98:114] = _limbs(a), _limbs(b), out, lo, hi
+        return [row], sum(o << (16 * i) for i, o in enumerate(out))
+    if op == "byte":
+        row = arithmetic_byte_row(a, b)
+        return [row], sum(o << (16 * i) for i, o in enumerate(row[66:82]))
+    row1, row2, res = arithmetic_modular_rows(op, a, b, c)
+    return [row1, row2], res
+
+
+def arithmetic_trace_from_operations(ops):
+    """ArithmeticStark::generate_trace (arithmetic_stark.rs:158-190): the rows of the operations in order, padded to RANGE_MAX = 2^16 rows,
+    then the range-check counter and frequency columns -> (116 x 2^16 trace, first row of every operation)"""
+    t = np.zeros((116, 1 << 16), dtype=np.uint64)
+    r, first = 0, []
+    for op in ops:
+        rows, _ = arithmetic_operation_rows(*op)
+        first.append(r)
+        for row in rows:
+            t[:, r] = row
+            r += 1
+    t[114] = np.minimum(np.arange(1 << 16), 65535).astype(np.uint64)
+    t[115, :65536] = np.bincount(t[18:114].astype(np.int64).ravel(), minlength=65536).astype(np.uint64)
+    return t, first
 
 
 def arithmetic_modular_trace(log_n, seed, nops=60):
