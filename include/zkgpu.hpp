@@ -537,7 +537,7 @@ inline F memory_extra_looking_sum(const PublicValues& pv, F beta, F gamma, const
 
 // ---- a stream of segments, several in flight on one GPU (zero/src/prover.rs:205-236 dispatches every segment as its own proving job and
 // collects the proofs by index; zero/src/ops.rs:24-66 is the job) ---------------------------------------------------------------------
-// `streams` worker threads, each with its own worker state (default: a Context = own CUDA stream, copy stream and memory pool; three in
+// `streams` worker threads, each with its own worker state (default: a Context = own CUDA stream, copy stream and memory pool; four in
 // flight is the measured optimum on a B200).  next() is called under a lock and returns std::nullopt at the end of the stream, so the
 // source is consumed lazily: at most `streams` segments are alive at a time.  A failing segment raises the abort signal the running
 // proofs poll and its exception is rethrown by prove_all; abort() does the same from outside (-> Error{ZKGPU_ERR_ABORTED}).

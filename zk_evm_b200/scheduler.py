@@ -3,11 +3,11 @@
 The reference dispatches every segment of a batch as an independent proving job and collects the proofs by segment index
 (zero/src/prover.rs:205-236: `Directive::map(IndexedStream::from([segment_data]), &seg_prove_ops)` per segment, results sorted by
 index; the job itself is `SegmentProof::execute`, zero/src/ops.rs:24-66, i.e. `prove_all_segments` -> `prove`).  Here the workers are
-host threads of one process, each with its own `Context` (own CUDA stream, copy stream and memory pool): three segments in flight is
-the measured optimum on a B200 — the latency-bound phases of one segment fall under the throughput-bound
+host threads of one process, each with its own `Context` (own CUDA stream, copy stream and memory pool): four segments in flight is
+the measured optimum on a B200 (2: 3.94, 3: 4.13, 4: 4.17, 5: 4.18 proofs/s) — the latency-bound phases of one segment fall under the throughput-bound
 phases of another, and the library orders the trace uploads of the contexts of one device one chain at a time.
 
-    prover = SegmentProver(device=0, streams=3, config=StarkConfig.standard_fast())
+    prover = SegmentProver(device=0, streams=4, config=StarkConfig.standard_fast())
     proofs = prover.prove_all(segments)            # segments: iterable of SegmentTraces / (traces, public_values[, labels])
 
 The segment source is consumed lazily, at most `streams` segments ahead of the proofs (the bounded channel between the reference's
@@ -34,7 +34,7 @@ def _unpack(segment, default_labels):
 
 
 class SegmentProver:
-    def __init__(self, device=0, streams=3, config=None, labels=None, make_worker=None, prove=None):
+    def __init__(self, device=0, streams=4, config=None, labels=None, make_worker=None, prove=None):
         """make_worker(device) -> per-thread state (default: a zk_evm_b200.Context); prove(state, traces, public_values, labels,
         abort_flag) -> proof (default: prove_with_traces through the C ABI, CUDA only).  The two hooks exist so that the scheduling
         logic can be exercised without a GPU (tests use the oracle as the stand-in); the product path has no CPU fallback."""
