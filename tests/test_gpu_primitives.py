@@ -54,6 +54,25 @@ def test_ntt_all_kinds(ctx, oracle, lg):
     assert np.array_equal(ctx.ntt(x, inverse=True, coset_shift=GENERATOR), oracle.ntt(x, 3, GENERATOR))
 
 
+def test_largest_production_table_height(ctx, oracle):
+    """The tallest trace the reference's default ranges allow is Memory at 2^23 rows (`.env` MEMORY_CIRCUIT_SIZE 17..24, half-open): its
+    transforms have three passes over an 8 + 8 + 7 bit split, its commitment 2^24 leaves.  All four transform kinds and the whole
+    commitment (coefficients, leaves, every digest, cap) against the oracle, on two columns"""
+    lg = 23
+    rng = np.random.default_rng(lg)
+    x = rand_field(rng, (2, 1 << lg))
+    x[0, :5] = P - 1
+    assert np.array_equal(ctx.ntt(x), oracle.ntt(x, 0))
+    assert np.array_equal(ctx.ntt(x, inverse=True), oracle.ntt(x, 1))
+    assert np.array_equal(ctx.ntt(x, coset_shift=GENERATOR), oracle.ntt(x, 2, GENERATOR))
+    assert np.array_equal(ctx.ntt(x, inverse=True, coset_shift=GENERATOR), oracle.ntt(x, 3, GENERATOR))
+    b = zk.PolynomialBatch.from_values(ctx, x, rate_bits=1, cap_height=4)
+    co, le, di = b.export()
+    oco, ole, odi, ocap = oracle.commit(x, 1, 4)
+    assert np.array_equal(co, oco) and np.array_equal(le, ole) and np.array_equal(b.cap, ocap) and np.array_equal(di, odi)
+    b.free()
+
+
 def test_ntt_roundtrip_config1(ctx):
     # BASELINE config #1 shape on the device: 2^16 points, 128 columns
     rng = np.random.default_rng(1)
