@@ -109,3 +109,88 @@ def test_trace_file_segments_are_accepted(tmp_path, oracle):
         return orc_prove_segment(oracle, TEST_CONFIG, list(tr_), pv, labels=tuple(labels))[0]
     got = SegmentProver(streams=1, make_worker=lambda d: None, prove=prove).prove_all([trace_file.load(path)])
     assert seen == [(1, 2, 3, 4)] and len(got) == 1
+
+
+# ---- admission by device memory: segments at the top of the reference's ranges do not fit four at a time in 180 GB ---------------------
+class _Shape:
+    def __init__(self, c, lg):
+        self.shape = (c, 1 << lg)
+
+
+_WIDTHS = [116, 71, 85, 2431, 438, 523, 30, 12, 12]
+
+
+def _segment_of(lgs):
+    return [_Shape(_WIDTHS[t], lg) for t, lg in enumerate(lgs)]
+
+
+def test_estimate_of_device_memory_per_segment():
+    from zk_evm_b200.scheduler import estimate_segment_bytes
+    bench = estimate_segment_bytes(_segment_of([17, 14, 19, 17, 13, 16, 21, 19, 19]))         # BASELINE config #4 heights
+    # 3.94 GB of traces -> values + coefficients + LDE = 15.8 GB, + the widest table's auxiliary / quotient / FRI buffers, + headroom
+    assert 18e9 < bench < 24e9
+    top = estimate_segment_bytes(_segment_of([20, 20, 20, 19, 16, 20, 23, 22, 22]))           # top of the default ranges (.env:2-10)
+    assert 95e9 < top < 120e9                                                                  # one at a time on a 180 GB device
+    assert estimate_segment_bytes([None] * 9) == 0
+    some = _segment_of([17, 14, 19, 17, 13, 16, 21, 19, 19])
+    some[3] = None                                                                             # a segment without Keccak
+    assert estimate_segment_bytes(some) < bench / 2
+
+
+def _counting_prover(streams, budget, hold=0.05):
+    state = {"now": 0, "max": 0, "order": []}
+    lock = threading.Lock()
+
+    def prove(st, tr, pv, labels, abort_flag):
+        with lock:
+            state["now"] += 1
+            state["max"] = max(state["max"], state["now"])
+        time.sleep(hold)
+        with lock:
+            state["now"] -= 1
+        return int(pv)
+    return SegmentProver(streams=streams, make_worker=lambda d: None, prove=prove, memory_budget=budget), state
+
+
+def test_memory_budget_bounds_the_segments_in_flight():
+    from zk_evm_b200.scheduler import estimate_segment_bytes
+    seg = _segment_of([17, 14, 19, 17, 13, 16, 21, 19, 19])
+    need = estimate_segment_bytes(seg)
+    segs = [(seg, i) for i in range(12)]
+    # room for all four streams
+    prover, st = _counting_prover(4, 5 * need)
+    assert prover.prove_all(iter(segs)) == list(range(12)) and st["max"] == 4
+    # room for two at a time only
+    prover, st = _counting_prover(4, int(2.5 * need))
+    assert prover.prove_all(iter(segs)) == list(range(12)) and st["max"] == 2
+    # a segment larger than the whole budget still runs, alone
+    prover, st = _counting_prover(4, need // 2)
+    assert prover.prove_all(iter(segs)) == list(range(12)) and st["max"] == 1
+    # no budget: the stream count alone bounds it
+    prover, st = _counting_prover(3, None)
+    assert prover.prove_all(iter(segs)) == list(range(12)) and st["max"] == 3
+
+
+def test_memory_budget_mixed_sizes_and_abort():
+    small = _segment_of([16, 8, 12, 7, 8, 5, 17, 16, 7])
+    big = _segment_of([20, 20, 20, 19, 16, 20, 23, 22, 22])
+    from zk_evm_b200.scheduler import estimate_segment_bytes
+    budget = estimate_segment_bytes(big) + 3 * estimate_segment_bytes(small)
+    segs = [(big if i % 3 == 0 else small, i) for i in range(9)]
+    prover, st = _counting_prover(4, budget, hold=0.03)
+    assert prover.prove_all(iter(segs)) == list(range(9)) and 2 <= st["max"] <= 4
+    # the abort signal wakes the workers that wait for memory
+    prover, st = _counting_prover(4, estimate_segment_bytes(big), hold=0.2)
+    th_err = []
+
+    def run():
+        try:
+            prover.prove_all(iter([(big, i) for i in range(8)]))
+        except SegmentAborted as e:
+            th_err.append(e)
+    th = threading.Thread(target=run)
+    th.start()
+    time.sleep(0.1)
+    prover.abort()
+    th.join(5)
+    assert not th.is_alive() and th_err and st["max"] == 1

@@ -5,4 +5,4 @@ from .prover import (Context, PolynomialBatch, CtlData, StarkProof, table_info, 
 from .segment import (Challenger, AllProof, prove_with_traces, upload_traces, SegmentUpload, prove_with_traces_sharded, ZkGpuBackend, TorchComm, LocalComm,  # noqa: F401
                       default_owner, segment_challenges, ShardPlan, shard_plan, SplitCommit, NUM_TABLES, TABLE_NAMES, OPTIONAL_TABLES)
 from .public_values import PublicValues, flatten_public_values, memory_extra_looking_values, memory_extra_looking_sum  # noqa: F401,E402
-from .scheduler import SegmentProver, SegmentAborted  # noqa: F401,E402
+from .scheduler import SegmentProver, SegmentAborted, estimate_segment_bytes  # noqa: F401,E402

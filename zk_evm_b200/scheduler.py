@@ -24,6 +24,50 @@ class SegmentAborted(RuntimeError):
     pass
 
 
+# trace width c and auxiliary width a (two challenges) of the nine tables, SURVEY.md 8(a) / zkgpu_table_info
+_TABLE_WIDTHS = ((116, 100), (71, 70), (85, 24), (2431, 4), (438, 290), (523, 2), (30, 16), (12, 4), (12, 2))
+
+
+def estimate_segment_bytes(traces):
+    """Device memory one segment proof holds at its peak: every table's trace commitment is made before the first
+    table is finished — values + coefficients + the blow-up-2 LDE = 32 n c bytes and ~128 n bytes of digests per table — plus the
+    auxiliary and quotient commitments, openings and FRI buffers of the table being finished (the widest one bounds it), 15 % headroom.
+    Measured pool peaks on a B200 (tools/memory_peak.py, profiles/r2y_memory_peak.jsonl): 1.32 GB for the b3_b6 heights (estimate 1.65),
+    16.8 GB for the b19807080 heights (estimate 21.8) — the estimate is 25-30 % above the peak, on the safe side.
+    `traces`: nine (ncols, n) arrays / objects with a `shape`, or None for a table left out."""
+    total, transient = 0, 0
+    for t, tr in enumerate(traces):
+        if tr is None:
+            continue
+        shape = getattr(tr, "shape", None)
+        c, n = (int(shape[0]), int(shape[1])) if shape is not None else (_TABLE_WIDTHS[t][0], int(tr))
+        total += 32 * n * c + 128 * n
+        transient = max(transient, 32 * n * (_TABLE_WIDTHS[t][1] + 8) + 512 * n)
+    return int(1.15 * (total + transient))
+
+
+class _MemoryBudget:
+    """admission by bytes: a segment starts when its estimate fits next to the ones in flight — or when nothing is in flight (a segment
+    larger than the whole budget is not refused here; the library reports ZKGPU_ERR_NOMEM if it really does not fit)"""
+
+    def __init__(self, limit):
+        self.limit, self.used, self.running = limit, 0, 0
+        self.cv = threading.Condition()
+
+    def acquire(self, nbytes, abort):
+        with self.cv:
+            while self.running and self.used + nbytes > self.limit and not abort.value:
+                self.cv.wait(timeout=0.05)
+            self.used += nbytes
+            self.running += 1
+
+    def release(self, nbytes):
+        with self.cv:
+            self.used -= nbytes
+            self.running -= 1
+            self.cv.notify_all()
+
+
 def _unpack(segment, default_labels):
     if hasattr(segment, "traces"):          # trace_file.SegmentTraces
         return segment.traces, segment.public_values, getattr(segment, "labels", None) or default_labels
@@ -34,13 +78,18 @@ def _unpack(segment, default_labels):
 
 
 class SegmentProver:
-    def __init__(self, device=0, streams=4, config=None, labels=None, make_worker=None, prove=None):
+    def __init__(self, device=0, streams=4, config=None, labels=None, make_worker=None, prove=None, memory_budget=150 << 30):
         """make_worker(device) -> per-thread state (default: a zk_evm_b200.Context); prove(state, traces, public_values, labels,
         abort_flag) -> proof (default: prove_with_traces through the C ABI, CUDA only).  The two hooks exist so that the scheduling
-        logic can be exercised without a GPU (tests use the oracle as the stand-in); the product path has no CPU fallback."""
+        logic can be exercised without a GPU (tests use the oracle as the stand-in); the product path has no CPU fallback.
+        memory_budget: bytes of device memory the segments in flight may hold together (default 150 GB of a B200's 180 GB; None: no
+        limit).  Segments at the bench heights are estimated at 22 GB each (measured peak 16.8), so four run side by side; at the top of
+        the reference's default ranges (Keccak 2^19 x 2431, Logic 2^20 x 523, Memory 2^23) one segment is estimated at 100 GB and the scheduler runs them one at a time
+        instead of failing with ZKGPU_ERR_NOMEM."""
         if streams < 1:
             raise ValueError("at least one segment in flight")
         self.device, self.streams, self.config, self.labels = device, streams, config, labels
+        self._budget = None if memory_budget is None else _MemoryBudget(int(memory_budget))
         self._make_worker = make_worker or self._default_worker
         self._prove = prove or self._default_prove
         self._abort = C.c_int(0)
@@ -78,7 +127,16 @@ class SegmentProver:
                     if self._abort.value:
                         continue                      # drain
                     traces, pv, labels = _unpack(seg, self.labels)
-                    proof = self._prove(state, traces, pv, labels, self._abort)
+                    need = estimate_segment_bytes(traces) if self._budget is not None else 0
+                    if self._budget is not None:
+                        self._budget.acquire(need, self._abort)
+                    try:
+                        if self._abort.value:
+                            continue
+                        proof = self._prove(state, traces, pv, labels, self._abort)
+                    finally:
+                        if self._budget is not None:
+                            self._budget.release(need)
                     with lock:
                         results[idx] = proof
             except BaseException as e:               # noqa: BLE001  (re-raised by prove_all)
