@@ -78,3 +78,30 @@ def test_zz_bench_sized_wide_tables_match_oracle_word_for_word(ctx, oracle, tabl
     want, st_want = orc_prove_table(oracle, table, cfg, tr, BG2, STATE0)
     assert got.shape == want.shape and np.array_equal(got, want)
     assert np.array_equal(st, st_want)
+
+
+def test_zz_keccak_at_the_top_of_its_default_range_proves_and_verifies(oracle):
+    """The widest table at the tallest height the reference's default ranges allow (`.env` KECCAK_CIRCUIT_SIZE 4..20: 2^19 rows x 2431
+    columns = 10 GB of trace, a 20 GB LDE, 2.5e9 elements — past 2^31, where a 32-bit index anywhere in the path would wrap): a VALID trace
+    of 21845 permutations finished on the device, committed, proved; the restated verifier accepts the proof.  Own context, closed
+    afterwards, so that the 50 GB of pool do not stay with the suite's shared one."""
+    cfg = STANDARD_FAST
+    rng = np.random.default_rng(19)
+    nperm = (1 << 19) // 24
+    inputs = rng.integers(0, 1 << 63, size=(nperm, 25), dtype=np.uint64)
+    ts = np.arange(1, nperm + 1, dtype=np.uint64)
+    ctx = zk.Context(0)
+    try:
+        dt = zk.keccak_generate_trace(ctx, inputs, ts)
+        assert (dt.ncols, dt.n) == (2431, 1 << 19)
+        batch = zk.PolynomialBatch.from_device_values(ctx, dt.device_ptr, dt.ncols, dt.n, cfg[2], cfg[3], keep_values=True)
+        dt.free()
+        ctl = zk.get_ctl_data(ctx, traces.T_KECCAK, batch, BG2, cfg[1])
+        sp, st = zk.prove_single_table(ctx, traces.T_KECCAK, zk.StarkConfig(*cfg), batch, ctl, STATE0, zk.KernelLabels(*DEFAULT_LABELS))
+        proof = np.array(sp.words, dtype=np.uint64)
+        assert ctx.stats()["bytes_peak"] > 40 << 30
+    finally:
+        ctx.close()
+    ok, err, st2 = orc_verify_table(oracle, traces.T_KECCAK, cfg, proof, BG2, STATE0)
+    assert ok, err
+    assert np.array_equal(st, st2)
