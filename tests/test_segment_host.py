@@ -199,6 +199,12 @@ def test_shard_plan_properties():
     # an optional table that is not in use is nobody's
     plan = zk.shard_plan(4, [16, None, 16, None, None, None, 18, 16, None])
     assert plan.needs(0)[1] is False and not plan.split[1]
+    # a split commitment hands every rank whole cap subtrees: other world sizes shard by owner only
+    for w in (3, 5, 6, 7, 32):
+        plan = zk.shard_plan(w, bench.SEGMENT_LOG_NS)
+        assert not any(plan.split) and len(set(plan.owner)) == min(w, 9)
+    assert not any(zk.shard_plan(4, bench.SEGMENT_LOG_NS, cap_height=1).split)      # 4 ranks, 2 cap entries
+    assert any(zk.shard_plan(2, bench.SEGMENT_LOG_NS, cap_height=1).split)
 
 
 def test_sharded_prove_two_ranks_gloo(oracle):
@@ -223,6 +229,29 @@ def test_sharded_prove_two_ranks_gloo(oracle):
                 assert np.array_equal(proofs[t], want[t]), "rank %d table %d differs from the single-process proof" % (rank, t)
     ok, err = orc_verify_segment(oracle, TEST_CONFIG, res[0][1], PUBLIC_VALUES)
     assert ok, err
+
+
+def test_sharded_prove_three_ranks_gloo(oracle):
+    """a world size that is not a power of two (three GPUs of a node): shard_plan keeps whole tables with their owners, the relay and the
+    cap all-gather work as for two ranks, proofs == the single-process proofs"""
+    world, port = 3, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_split, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=900) for _ in range(world)]
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want, bg, _ = orc_prove_segment(oracle, TEST_CONFIG, traces.valid_segment(seed=3), PUBLIC_VALUES)
+    assert res[0][3]["split_over_all_gpus"] == [] and len(set(res[0][3]["owner"])) == 3
+    for rank, proofs, ctl_ch, _ in res:
+        assert np.array_equal(ctl_ch, bg)
+        for t in range(9):
+            assert (proofs[t] is None) == (want[t] is None)
+            if want[t] is not None:
+                assert np.array_equal(proofs[t], want[t]), "rank %d table %d differs from the single-process proof" % (rank, t)
 
 
 def test_sharded_prove_local_comm_equals_segment(oracle):

@@ -379,12 +379,15 @@ class ShardPlan:
         return {"owner": list(self.owner), "split_over_all_gpus": [TABLE_NAMES[t] for t in range(NUM_TABLES) if self.split[t]]}
 
 
-def shard_plan(world, log_ns, split_min_bytes=32 << 20):
+def shard_plan(world, log_ns, split_min_bytes=32 << 20, cap_height=4):
     """Split the trace commitment of every table whose trace has at least split_min_bytes (the all-gather of a small table costs more
-    than hashing it alone); owners by longest-processing-time packing of the per-table weight of the phases that stay with the owner."""
+    than hashing it alone); owners by longest-processing-time packing of the per-table weight of the phases that stay with the owner.
+    A split commitment gives every rank one block of whole cap subtrees (zkgpu_merkle_block): the number of ranks must be a power of
+    two and at most 2^cap_height.  Any other world size (3, 6, ... GPUs) still shards the tables by owner, without splitting."""
     in_use = [lg is not None for lg in log_ns]
     rows = [(1 << lg) if lg is not None else 0 for lg in log_ns]
-    split = [world > 1 and in_use[t] and 8 * NUM_COLUMNS[t] * rows[t] >= split_min_bytes for t in range(NUM_TABLES)]
+    can_split = world > 1 and (world & (world - 1)) == 0 and world <= (1 << cap_height)
+    split = [can_split and in_use[t] and 8 * NUM_COLUMNS[t] * rows[t] >= split_min_bytes for t in range(NUM_TABLES)]
     w = []
     for t in range(NUM_TABLES):
         own = rows[t] * (NUM_COLUMNS[t] + _NUM_AUX2[t] + 4) * 2.0                       # phases 2-3: streaming passes over trace + aux + quotient
