@@ -126,6 +126,40 @@ def test_sharded_path_on_one_gpu_and_device_resident_traces(ctx, oracle):
     _same(ap3, want, bg, caps)
 
 
+def test_seams_s1_s2_s3_compose_to_prove_with_traces(ctx, oracle):
+    """the reference's own decomposition (prover.rs:72-194): PolynomialBatch::from_values per table (S1) -> the transcript replay ->
+    get_ctl_data per table (S2) -> prove_with_commitments = prove_single_table per table with one challenger (S3, :211-293) gives the
+    proofs, challenges and memory caps of the one-call path, word for word"""
+    tr, labels = traces.cpu_segment("PP|PP^PPaXXJ")
+    cfg = zk.StarkConfig(*STANDARD_FAST)
+    lab = zk.KernelLabels(*labels)
+    ap = zk.prove_with_traces(ctx, tr, PUBLIC_VALUES, cfg, lab)
+    in_use = [t is not None for t in tr]
+    commits = [None if t is None else zk.PolynomialBatch.from_values(ctx, t, rate_bits=cfg.rate_bits, cap_height=cfg.cap_height, keep_values=True)
+               for t in tr]
+    capw = 4 << cfg.cap_height
+    caps = np.zeros((9, capw), dtype=np.uint64)
+    for t, b in enumerate(commits):
+        if b is not None:
+            caps[t] = np.array(b.cap, dtype=np.uint64).reshape(-1)
+    bg, st = zk.segment_challenges(caps, in_use, cfg.cap_height, PUBLIC_VALUES, cfg.num_challenges)
+    assert np.array_equal(bg, ap.ctl_challenges) and np.array_equal(caps.reshape(ap.trace_caps.shape), ap.trace_caps)
+    ctls = [None if b is None else zk.get_ctl_data(ctx, t, b, bg, cfg.num_challenges) for t, b in enumerate(commits)]
+    proofs, st_end, mem_before, mem_after = zk.prove_with_commitments(ctx, cfg, commits, in_use, ctls, st, lab)
+    for t in range(9):
+        assert (proofs[t] is None) == (ap.stark_proofs[t] is None)
+        if proofs[t] is not None:
+            assert np.array_equal(np.array(proofs[t].words, dtype=np.uint64), ap.stark_proofs[t]), zk.TABLE_NAMES[t]
+    assert np.array_equal(mem_before, np.asarray(ap.mem_before_cap).reshape(-1)) and np.array_equal(mem_after, np.asarray(ap.mem_after_cap).reshape(-1))
+    ok, err = orc_verify_segment(oracle, STANDARD_FAST, [None if p is None else np.array(p.words, dtype=np.uint64) for p in proofs], PUBLIC_VALUES, labels=labels)
+    assert ok, err
+    with pytest.raises(ValueError):
+        zk.prove_with_commitments(ctx, cfg, commits, in_use, [None] * 9, st, lab)
+    for b in commits:
+        if b is not None:
+            b.free()
+
+
 def test_missing_mandatory_table_is_an_error(ctx):
     tr = traces.valid_segment(seed=1)
     tr[traces.T_CPU] = None

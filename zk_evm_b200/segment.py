@@ -193,6 +193,29 @@ def prove_with_traces(ctx, traces, public_values, config, labels=None, forced_po
 
 
 # ---- table-sharded proving ------------------------------------------------------------------------------------------------
+def prove_with_commitments(ctx, config, trace_commitments, table_in_use, ctl_data_per_table, challenger_state, labels=None,
+                           forced_pow_witnesses=None, abort_flag=None):
+    """prover.rs:211-293: the tables in Table order, ONE challenger handed from table to table (:251-259), `None` for a table that is not in
+    use.  trace_commitments[t]: the PolynomialBatch of table t's trace (made with keep_values — the seam S1 of SURVEY 8b), or None;
+    ctl_data_per_table[t]: its CtlData (get_ctl_data, seam S2); challenger_state: the compacted transcript state after the trace caps, the
+    public values and the lookup challenges (segment_challenges).  -> (proofs[9], challenger state after the last table, mem_before cap,
+    mem_after cap — zeros when MemAfter is not in use, as ProofWithMemCaps)."""
+    st = np.ascontiguousarray(challenger_state, dtype=np.uint64).copy()
+    proofs = [None] * NUM_TABLES
+    for t in range(NUM_TABLES):
+        if not table_in_use[t]:
+            continue
+        if trace_commitments[t] is None or ctl_data_per_table[t] is None:
+            raise ValueError("table %s is in use: it needs its trace commitment and its CtlData" % TABLE_NAMES[t])
+        fp = None if forced_pow_witnesses is None else int(forced_pow_witnesses[t])
+        proofs[t], st = _p.prove_single_table(ctx, t, config, trace_commitments[t], ctl_data_per_table[t], st, labels, fp, abort_flag)
+    capw = 4 << config.cap_height
+    mem_before = np.array(trace_commitments[7].cap, dtype=np.uint64).reshape(-1)[:capw] if trace_commitments[7] is not None else np.zeros(capw, np.uint64)
+    mem_after = np.array(trace_commitments[8].cap, dtype=np.uint64).reshape(-1)[:capw] if table_in_use[8] and trace_commitments[8] is not None \
+        else np.zeros(capw, np.uint64)
+    return proofs, st, mem_before, mem_after
+
+
 class ZkGpuBackend:
     """The compute steps of one rank on its GPU (through the C ABI)."""
 
