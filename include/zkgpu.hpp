@@ -9,12 +9,15 @@
 // every computation is a call into libzkgpu.so (CUDA), and there is no CPU fallback — without a usable device the calls throw
 // Error{ZKGPU_ERR_CUDA}.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <atomic>
+#include <chrono>
 #include <exception>
 #include <functional>
 #include <map>
 #include <mutex>
+#include <condition_variable>
 #include <thread>
 #include <memory>
 #include <optional>
@@ -546,7 +549,13 @@ class SegmentStream {
 public:
     using MakeWorker = std::function<std::unique_ptr<Worker>()>;
     using Prove = std::function<Proof(Worker&, const Segment&, AbortSignal)>;
+    using Estimate = std::function<size_t(const Segment&)>;
     SegmentStream(unsigned streams, MakeWorker make_worker, Prove prove) : streams_(streams ? streams : 1), make_worker_(std::move(make_worker)), prove_(std::move(prove)) {}
+    SegmentStream(unsigned streams, MakeWorker make_worker, Prove prove, size_t budget_bytes, Estimate estimate)
+        : streams_(streams ? streams : 1), make_worker_(std::move(make_worker)), prove_(std::move(prove)), estimate_(std::move(estimate)), budget_(budget_bytes) {}
+    // Admission by device memory: a segment starts when estimate(segment) bytes fit next to the ones in flight, or when nothing is in
+    // flight (a segment larger than the whole budget still runs, alone; the library reports ZKGPU_ERR_NOMEM if it really does not fit).
+    SegmentStream& with_memory_budget(size_t budget_bytes, Estimate estimate) { budget_ = budget_bytes; estimate_ = std::move(estimate); return *this; }
     void abort() { abort_.store(1); }
     // proofs in segment order
     std::vector<Proof> prove_all(const std::function<std::optional<Segment>()>& next) {
@@ -569,6 +578,17 @@ public:
                         if (!seg) { done = true; return; }
                         idx = count++;
                     }
+                    const size_t need = estimate_ ? estimate_(*seg) : 0;
+                    if (estimate_) {
+                        std::unique_lock<std::mutex> g(mu);
+                        while (running_ && used_ + need > budget_ && !abort_.load()) cv_.wait_for(g, std::chrono::milliseconds(50));
+                        used_ += need; running_++;
+                    }
+                    struct Release {
+                        SegmentStream* s; std::mutex& mu; size_t need; bool on;
+                        ~Release() { if (on) { std::lock_guard<std::mutex> g(mu); s->used_ -= need; s->running_--; s->cv_.notify_all(); } }
+                    } release{this, mu, need, (bool)estimate_};
+                    if (abort_.load()) return;
                     Proof p = prove_(*w, *seg, &abort_);
                     std::lock_guard<std::mutex> g(mu);
                     results.emplace(idx, std::move(p));
@@ -593,6 +613,9 @@ private:
     MakeWorker make_worker_;
     Prove prove_;
     std::atomic<int> abort_{0};
+    Estimate estimate_;
+    size_t budget_ = 0, used_ = 0, running_ = 0;
+    std::condition_variable cv_;
 };
 
 // the product instance: segments as trace blocks + flattened public values, proved by prove_with_traces on `device`
@@ -601,10 +624,27 @@ struct SegmentInput {
     std::vector<F> public_values;
     int mem_kind = ZKGPU_MEM_HOST;
 };
-inline SegmentStream<SegmentInput, AllProof, Context> segment_prover(int device, unsigned streams, StarkConfig config, KernelLabels labels) {
-    return SegmentStream<SegmentInput, AllProof, Context>(
+// Device memory one segment proof holds at its peak: every table's trace commitment (values + coefficients + blow-up-2 LDE = 32 n c
+// bytes, ~128 n of digests) is alive before the first table is finished, plus the auxiliary / quotient / FRI buffers of the widest
+// table, 15 % headroom.  Measured on a B200: 16.8 GB at the b19807080 heights against an estimate of 21.8 (profiles/r2y_memory_peak.jsonl).
+inline size_t estimate_segment_bytes(const std::array<TableTrace, NUM_TABLES>& traces) {
+    static const unsigned width[NUM_TABLES][2] = {{116, 100}, {71, 70}, {85, 24}, {2431, 4}, {438, 290}, {523, 2}, {30, 16}, {12, 4}, {12, 2}};
+    double total = 0, transient = 0;
+    for (size_t t = 0; t < NUM_TABLES; t++) {
+        if (!traces[t].cols || !traces[t].n) continue;
+        const double n = (double)traces[t].n;
+        total += 32.0 * n * width[t][0] + 128.0 * n;
+        transient = std::max(transient, 32.0 * n * (width[t][1] + 8) + 512.0 * n);
+    }
+    return (size_t)(1.15 * (total + transient));
+}
+inline SegmentStream<SegmentInput, AllProof, Context> segment_prover(int device, unsigned streams, StarkConfig config, KernelLabels labels,
+                                                                     size_t memory_budget = (size_t)150 << 30) {
+    using Stream = SegmentStream<SegmentInput, AllProof, Context>;
+    return Stream(
         streams, [device]() { return std::make_unique<Context>(device); },
-        [config, labels](Context& ctx, const SegmentInput& s, AbortSignal a) { return prove_with_traces(ctx, s.traces, s.public_values, config, labels, a, s.mem_kind); });
+        [config, labels](Context& ctx, const SegmentInput& s, AbortSignal a) { return prove_with_traces(ctx, s.traces, s.public_values, config, labels, a, s.mem_kind); },
+        memory_budget, memory_budget ? Stream::Estimate([](const SegmentInput& s) { return estimate_segment_bytes(s.traces); }) : Stream::Estimate());
 }
 
 // a trace finished in device memory (zkgpu_dev_trace): KeccakStark / LogicStark generate_trace, the Arithmetic range-check columns,

@@ -155,7 +155,22 @@ int main(int argc, char** argv) {
             try { st.prove_all(src(100000, -1)); } catch (const Error& e) { aborted = e.code == ZKGPU_ERR_ABORTED; }
             killer.join();
             printf("abort %d consumed_at_most %d\n", (int)aborted, produced);
-            return ok && failed && aborted ? 0 : 1;
+            // admission by device memory: every "segment" needs 10 units; a budget of 25 lets two run side by side, 5 one at a time
+            bool budget_ok = true;
+            for (auto [budget, want_max] : {std::pair<size_t, int>{25, 2}, {5, 1}, {1000, 3}}) {
+                max_alive = 0;
+                st.with_memory_budget(budget, [](const int&) { return (size_t)10; });
+                const std::vector<long> g2 = st.prove_all(src(12, -1));
+                budget_ok = budget_ok && g2.size() == 12 && max_alive == want_max;
+                for (size_t k = 0; k < g2.size(); k++) budget_ok = budget_ok && g2[k] == (long)(k * k);
+            }
+            std::array<TableTrace, NUM_TABLES> shapes{};
+            static const F dummy = 0;
+            const unsigned lg[NUM_TABLES] = {17, 14, 19, 17, 13, 16, 21, 19, 19};
+            for (size_t t = 0; t < NUM_TABLES; t++) shapes[t] = TableTrace{&dummy, (size_t)1 << lg[t]};
+            const size_t est = estimate_segment_bytes(shapes);
+            printf("budget %d estimate %zu\n", (int)budget_ok, est);
+            return ok && failed && aborted && budget_ok ? 0 : 1;
         }
         if (mode == "decode" && argc > 2) {
             const std::vector<uint64_t> w = read_words(argv[2]);

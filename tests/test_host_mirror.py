@@ -64,6 +64,17 @@ def test_cpp_segment_stream_scheduling_logic(harness):
     f = dict(zip(out[0::2], out[1::2]))
     assert f["order"] == "1" and f["failure"] == "1" and f["abort"] == "1"
     assert int(out[out.index("failure") + 3]) < 500 and int(out[out.index("abort") + 3]) < 100000
+    # admission by device memory (with_memory_budget): two side by side / one at a time / all three, and the C++ estimate of a segment's
+    # device bytes equals the Python scheduler's
+    from zk_evm_b200.scheduler import estimate_segment_bytes
+
+    class Shape:
+        def __init__(self, c, lg):
+            self.shape = (c, 1 << lg)
+    widths = [116, 71, 85, 2431, 438, 523, 30, 12, 12]
+    want = estimate_segment_bytes([Shape(widths[t], lg) for t, lg in enumerate([17, 14, 19, 17, 13, 16, 21, 19, 19])])
+    assert out[out.index("budget") + 1] == "1"
+    assert abs(int(out[out.index("estimate") + 1]) - want) <= 2
 
 
 def _random_public_values(seed):
