@@ -132,6 +132,31 @@ def test_merkle_level_kernel_one_node(merkle_emu):
         assert got == [int(v) for v in orc.two_to_one(kids[2 * node], kids[2 * node + 1])]
 
 
+def test_merkle_tail_kernel_block(merkle_emu):
+    """merkle_tail_kernel (round 2: the levels under one cap entry in ONE launch): block s walks cap subtree s from its 8 input digests
+    down to its root, a barrier between levels — the kernel's PTX for whole blocks of 4 threads (so that the level loop strides) against
+    two_to_one of the oracle, for the second of two subtrees (the per-block offsets)"""
+    import struct
+    orc = oracle_lib.load()
+    rng = np.random.default_rng(31)
+    count0, nsub = 8, 2
+    lvl = [oracle_lib.rand_field(rng, (nsub * count0, 4))]                      # level 0: 8 digests per subtree, subtree after subtree
+    while len(lvl[-1]) > nsub:
+        prev = lvl[-1]
+        lvl.append(np.array([orc.two_to_one(prev[2 * i], prev[2 * i + 1]) for i in range(len(prev) // 2)], dtype=np.uint64))
+    off, o = [], 0
+    for l in lvl:                                                                # merkle_layout: level after level, 4 words per digest
+        off.append(o)
+        o += 4 * len(l)
+    mem = {IN + 8 * i: int(v) for i, v in enumerate(lvl[0].ravel())}
+    args = struct.pack("<Q12QII", IN, *(off + [0] * (12 - len(off))), count0, len(lvl) - 1)
+    for block in range(nsub):
+        merkle_emu.run_block("merkle_tail_kernel", [args], mem, ntid=4, ctaid=(block, 0))
+    for k in range(1, len(lvl)):
+        got = [mem[IN + 8 * (off[k] + i)] for i in range(4 * len(lvl[k]))]
+        assert got == [int(v) for v in lvl[k].ravel()], "level %d" % k
+
+
 # ---- the production NTT pass kernel: a whole 32-thread block with its barriers and shared-memory tile -----------------------------
 NTT_PTX = os.path.join(HERE, "native", "ntt.ptx")
 
@@ -262,6 +287,31 @@ def test_quotient_domain_table(quotient_emu):
         assert mem[OUT + 8 * j] == (x - last) % P
         assert mem[OUT + 8 * (N + j)] == z * ninv % P * _inv((x - 1) % P) % P
         assert mem[OUT + 8 * (2 * N + j)] == z * last % P * ninv % P * _inv((x - last) % P) % P
+
+
+@pytest.mark.parametrize("T,nc", [(1, 1), (4, 2), (7, 2), (9, 1)])
+def test_quotient_combine_kernel_point(quotient_emu, T, nc):
+    """quotient_combine_kernel (round 2: the alpha-dependent half of the quotient when the constraint values were recorded ahead of the
+    relay): storage position j -> out[k N + bitrev(j)] = zh_inv[i & 1] * sum_t alpha_k^(T - 1 - t) cons[t N + j], the Horner combination
+    the fused evaluator's ConstraintConsumer makes; the four-at-a-time loop and its remainder"""
+    rng = np.random.default_rng(70 + T)
+    log_N, N = 3, 8
+    cons = oracle_lib.rand_field(rng, (T, N))
+    a0, a1, zh0, zh1 = (int(v) for v in oracle_lib.rand_field(rng, (4,)))
+    CONS = 0x30000000
+    for j in range(N):
+        mem = {CONS + 8 * (t * N + jj): int(cons[t, jj]) for t in range(T) for jj in range(N)}
+        quotient_emu.run("quotient_combine_kernel", [CONS, T, N, log_N, nc, a0, a1, zh0, zh1, OUT], mem, tid=j, ctaid=0, ntid=256)
+        i = int("{:03b}".format(j)[::-1], 2)
+        for k, a in enumerate((a0, a1)[:nc]):
+            acc = 0
+            for t in range(T):
+                acc = (acc * a + int(cons[t, j])) % P
+            assert mem[OUT + 8 * (k * N + i)] == acc * (zh1 if i & 1 else zh0) % P, (j, k)
+        assert sum(1 for adr in mem if OUT <= adr < CONS) == nc           # nothing else is written
+    mem = {}
+    quotient_emu.run("quotient_combine_kernel", [CONS, T, N, log_N, nc, a0, a1, zh0, zh1, OUT], mem, tid=N, ctaid=0, ntid=256)
+    assert not mem                                                         # a thread past the domain does nothing
 
 
 def _ext_mul(a, b):
@@ -403,6 +453,7 @@ def test_fused_quotient_kernel_point(flat_host, table):
     kernel = "quotient_kernelILj%dEE" % table
     nthreads = 256 if table == 6 else 128
     p = lambda a: a.ctypes.data_as(u64p)
+    fused = {}
     for j in (1, 6):
         emu.run(kernel, [args], mem, tid=j, ctaid=0, ntid=nthreads)
         i = int("{:03b}".format(j)[::-1], 2)
@@ -417,6 +468,25 @@ def test_fused_quotient_kernel_point(flat_host, table):
         assert r == 1
         for k in range(2):
             assert mem[QOUT + 8 * (k * N + i)] == int(a[k]) * int(zh[i & 1]) % P, (table, j, k)
+        fused[j] = [int(a[0]), int(a[1])]
+    # constraints_record_kernel<TABLE> (round 2): the same evaluators through RecordConsumer write every constraint value of the point to
+    # its own column — alpha-independent — and thread 0 reports how many there are; Horner in alpha over the recorded column of a point
+    # must give what the fused kernel accumulated for it (before 1 / Z_H)
+    CONS, CNT = 0x340000000, 0x350000000
+    rargs = struct.pack("<QQQQQII", TR, AUX, CONS, CNT, N, logN, 0) + struct.pack("<4Q", *(int(v) for v in list(be) + list(ga))) + \
+        struct.pack("<Q", DOM) + struct.pack("<10Q", *(FLAT + int(o) for o in offs)) + struct.pack("<7I", *scal) + b"\0" * 4 + \
+        struct.pack("<4Q", *(int(v) for v in labels))
+    assert len(rargs) == 232
+    rkernel = "constraints_record_kernelILj%dEE" % table
+    emu.run(rkernel, [rargs], mem, tid=0, ctaid=0, ntid=nthreads)
+    T = mem[CNT] & 0xFFFFFFFF
+    assert T == sum(1 for adr in mem if CONS <= adr < CNT) and T >= 1          # thread 0 wrote exactly T values, 8 N bytes apart
+    emu.run(rkernel, [rargs], mem, tid=1, ctaid=0, ntid=nthreads)
+    for k in range(2):
+        acc = 0
+        for t in range(T):
+            acc = (acc * int(al[k]) + mem[CONS + 8 * (t * N + 1)]) % P
+        assert acc == fused[1][k], (table, k)
 
 
 # ---- device-side trace finishing: the Keccak row kernel ----------------------------------------------------------------------------------
