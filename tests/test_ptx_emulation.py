@@ -203,6 +203,32 @@ def test_ntt_pass_kernel_block(ntt_emu, lg, inverse):
     assert [got[rev[k]] for k in range(n)] == [int(v) for v in want]
 
 
+@pytest.mark.parametrize("inverse", [False, True])
+def test_ntt_pass_tma_kernel_block(ntt_emu, inverse):
+    """the production kernel for full tiles (round 2): 256 threads, the 4096-element tile staged by cp.async.bulk copies of 128 bytes per
+    thread into the unpadded staging area, one mbarrier, then the three radix-16 rounds of a 12-bit final pass through the padded tile.
+    The interpreter completes a bulk copy at once and treats the mbarrier wait as the block-wide phase boundary it is; everything else is
+    the kernel's own PTX.  A whole 2^12 transform against the oracle."""
+    orc = oracle_lib.load()
+    rng = np.random.default_rng(52 + int(inverse))
+    lg, n = 12, 1 << 12
+    x = oracle_lib.rand_field(rng, (n,))
+    w = int(orc.lib.orc_root_of_unity(12))
+    if inverse:
+        w = pow(w, P - 2, P)
+    ROOTS, SRC, DST = 0x30000000, IN, OUT
+    mem = {ROOTS + 8 * k: pow(w, k, P) for k in range(4096)}
+    mem.update({SRC + 8 * i: int(v) for i, v in enumerate(x)})
+    params = _pass_params(SRC, DST, n, lg, lg, lg, 0, 0, ROOTS)
+    ntt_emu.run_block("ntt_pass_tma_kernelILb%dE" % int(inverse), [params], mem, ntid=256, ctaid=(0, 0))
+    got = [mem[DST + 8 * i] for i in range(n)]
+    rev = [int("{:012b}".format(i)[::-1], 2) for i in range(n)]
+    want = orc.ntt(x, 1 if inverse else 0)[0]
+    if inverse:
+        want = [int(v) * n % P for v in want]
+    assert [got[rev[k]] for k in range(n)] == [int(v) for v in want]
+
+
 def test_ntt_two_pass_coset_transform_blocks(ntt_emu):
     """L = 13, the launcher's plan [8, 5]: a strided pass (tiles of 2^8 digit values x 16 contiguous elements, coset prescale on the
     first load, inter-pass twiddle on the store straight from the last round) and the final contiguous pass (128 sub-transforms of 32

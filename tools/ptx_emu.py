@@ -3,7 +3,7 @@
 
 Runs ONE thread (run) or one whole thread block with its barriers and shared memory (run_block) of a kernel from a `nvcc -ptx` file on
 the CPU: add/sub with carry flags, mul/mad.wide, shifts, funnel shifts, brev, logic, setp/selp, predicated branches, ld/st.global,
-ld/st.shared, bar.sync, ld.const, ld.param (scalars or a by-value struct given as bytes).  Enough to execute the Poseidon permutation, the field arithmetic and
+ld/st.shared, bar.sync, mbarrier + cp.async.bulk (TMA staging, completed at once), ld.const, ld.param (scalars or a by-value struct given as bytes).  Enough to execute the Poseidon permutation, the field arithmetic and
 the NTT butterflies exactly as nvcc emitted them (inline PTX included), so that device code can be compared with the oracle before any
 GPU time is spent.  What it cannot see is ptxas (PTX -> SASS); the GPU parity tests remain the judge of that.
 
@@ -45,7 +45,7 @@ class PtxEmu:
         for raw in body.replace("\n", " ").split(";"):
             line = raw.strip()
             while True:
-                m = re.match(r"(\$\w+):\s*(.*)", line)
+                m = re.match(r"(\$?\w+):(?!:)\s*(.*)", line)      # compiler labels ($L__BB0_1:) and the plain ones of inline asm
                 if not m:
                     break
                 labels[m.group(1)] = len(ins)
@@ -60,7 +60,7 @@ class PtxEmu:
             if not line or line.startswith("."):          # "{ .param .b64 param0" opening a call sequence
                 continue
             pred = None
-            m = re.match(r"@(!?)(%p\d+)\s+(.*)", line)
+            m = re.match(r"@(!?)(%?\w+)\s+(.*)", line)             # @%p3, @!%p3, and @p of an inline-asm predicate
             if m:
                 pred, line = (m.group(2), m.group(1) == "!"), m.group(3)
             parts = line.split(None, 1)
@@ -199,6 +199,24 @@ class PtxEmu:
                     break
                 if base == "bar":
                     yield
+                    continue
+                if base == "mbarrier":
+                    # TMA staging (ntt_pass_tma_kernel): the bulk copies below complete at once, so init / arrive.expect_tx carry no
+                    # state here; try_wait is where every thread waits for ALL threads' copies — a phase boundary of the lock-step
+                    # model, exactly like bar.sync — and then sees the phase complete
+                    if o[1] == "try_wait":
+                        yield
+                        R[a[0]] = 1
+                    continue
+                if base == "fence":
+                    continue
+                if base == "cp" and o[1:3] == ["async", "bulk"]:      # cp.async.bulk.shared::cluster.global...bytes [smem], [gmem], size, [mbar]
+                    db, doff = addr(a[0])
+                    sb, soff = addr(a[1])
+                    n = val(a[2])
+                    assert n % 8 == 0 and (val(db) + doff) % 16 == 0 and (val(sb) + soff) % 16 == 0, "bulk copies are 16-byte aligned"
+                    for i in range(0, n, 8):
+                        wr(smem, (val(db) + doff + i) & M32, 8, rd(mem, (val(sb) + soff + i) & M64, 8))
                     continue
                 if base == "bra":
                     pc = labels[a[0]]
