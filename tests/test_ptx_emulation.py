@@ -375,6 +375,42 @@ def test_fri_fold_and_leaves_kernels(fri_emu):
             assert mem[LEAVES + 8 * (kcol * rows + r)] == int(src[(r << ab) + (kcol >> 1)])
 
 
+def test_pow_and_gather_kernels(fri_emu):
+    """pow_kernel: candidate = base + thread; the transcript state with the candidate at the next input position goes through the
+    permutation, and the candidate is a witness when the challenge popped next — state[7] — has `bits` leading zero bits
+    (fri_proof_of_work; atomicMin keeps the smallest).  gather_addr_kernel: out[i] = *addrs[i] (the query answers of a table in one launch)."""
+    import struct
+    orc = oracle_lib.load()
+    rng = np.random.default_rng(91)
+    st = oracle_lib.rand_field(rng, (12,))
+    pos, bits, base = 3, 2, 1000
+    BEST = 0x30000000
+    mem = {BEST: 2 ** 64 - 1}
+    want = []
+    for k in range(12):
+        s = st.copy()
+        s[pos] = base + k
+        out = orc.poseidon(s.reshape(1, 12))[0]
+        if int(out[7]) >> (64 - bits) == 0:
+            want.append(base + k)
+    assert 1 <= len(want) < 12                                             # the case has witnesses and non-witnesses
+    for k in reversed(range(12)):                                          # any order: atomicMin
+        fri_emu.run("pow_kernel", [struct.pack("<12Q", *(int(v) for v in st)), pos, bits, base, BEST], mem, tid=k, ctaid=0, ntid=128)
+    assert mem[BEST] == want[0]
+    mem = {BEST: 2 ** 64 - 1}
+    fri_emu.run("pow_kernel", [struct.pack("<12Q", *(int(v) for v in st)), pos, bits, P - 3, BEST], mem, tid=3, ctaid=0, ntid=128)
+    assert mem[BEST] == 2 ** 64 - 1                                         # candidates >= p are not field elements
+    # gather
+    ADDRS, DATA = 0x40000000, 0x50000000
+    vals = [int(v) for v in oracle_lib.rand_field(rng, (9,))]
+    order = [7, 0, 3, 3, 8]
+    mem = {DATA + 8 * i: v for i, v in enumerate(vals)}
+    mem.update({ADDRS + 8 * i: DATA + 8 * j for i, j in enumerate(order)})
+    for i in range(6):
+        fri_emu.run("gather_addr_kernel", [ADDRS, len(order), OUT], mem, tid=i, ctaid=0, ntid=128)
+    assert [mem[OUT + 8 * i] for i in range(len(order))] == [vals[j] for j in order] and OUT + 8 * len(order) not in mem
+
+
 def test_modular_scan_kernels(aux_emu):
     """the three scan kernels of the running-sum (Z) columns: per-tile inclusive scan (256 threads x 8 items, Hillis-Steele on the thread
     sums), exclusive scan of the tile totals, offset add — prefix sums for the logUp columns, suffix sums (reverse) for the CTL columns"""
