@@ -223,6 +223,47 @@ static inline void fft_inplace(uint64_t* a, unsigned log_n) {
         for (unsigned s = 1; s <= inner; s++) fft_stage(a, b, b + ((size_t)1 << inner), s, n, tw);
     for (unsigned s = inner + 1; s <= log_n; s++) fft_stage(a, 0, n, s, n, tw);
 }
+// The same transform with its output LEFT IN BIT-REVERSED ORDER: a[bitrev(k)] = sum_j in[j] w^(jk) (decimation in frequency: the wide
+// stages first, then block by block; no permutation pass).  PolynomialBatch wants exactly this order — leaves[j] = lde[bitrev(j)] — so
+// the commitment never pays for a bit reversal.  `par`: split every stage over the OpenMP threads (tall, narrow batches).
+static inline void dif_stage(uint64_t* a, size_t lo, size_t hi, unsigned s, size_t n, const uint64_t* tw) {
+    const size_t m = (size_t)1 << s, half = m >> 1, step = n >> s;
+    if (half == 1) {
+        for (size_t k = lo; k < hi; k += 2) { uint64_t u = a[k], t = a[k + 1]; a[k] = gl_add(u, t); a[k + 1] = gl_sub(u, t); }
+        return;
+    }
+    for (size_t k = lo; k < hi; k += m)
+        for (size_t j = 0; j < half; j++) {
+            uint64_t u = a[k + j], v = a[k + j + half];
+            a[k + j] = gl_add(u, v);
+            a[k + j + half] = gl_mul(gl_sub(u, v), tw[j * step]);
+        }
+}
+static inline void fft_dif_bitrev_out(uint64_t* a, unsigned log_n, bool par = false) {
+    const size_t n = (size_t)1 << log_n;
+    if (!log_n) return;
+    const uint64_t* tw = fft_roots().get(log_n);
+    const unsigned BLK = 12;
+    const unsigned inner = log_n < BLK ? log_n : BLK;
+    const size_t blk = (size_t)1 << inner;
+    for (unsigned s = log_n; s > inner; s--) {
+        // a wide stage: 2^(log_n - s) independent groups of span 2^s; cut into pieces of 2^inner butterflies each
+        const size_t m = (size_t)1 << s, half = m >> 1, step = n >> s, pieces = n / 2 / blk * 2;
+        #pragma omp parallel for schedule(static) if (par)
+        for (size_t pc = 0; pc < pieces; pc++) {
+            const size_t per = half / (blk / 2) ? half / (blk / 2) : 1;          // pieces per group
+            const size_t g = pc / per, j0 = (pc % per) * (blk / 2), k = g * m;
+            for (size_t j = j0; j < j0 + blk / 2 && j < half; j++) {
+                uint64_t u = a[k + j], v = a[k + j + half];
+                a[k + j] = gl_add(u, v);
+                a[k + j + half] = gl_mul(gl_sub(u, v), tw[j * step]);
+            }
+        }
+    }
+    #pragma omp parallel for schedule(static) if (par)
+    for (size_t b = 0; b < n; b += blk)
+        for (unsigned s = inner; s >= 1; s--) dif_stage(a, b, b + blk, s, n, tw);
+}
 // ifft(v)[j] = n^-1 sum_i v_i w^(-ij)
 static inline void ifft_inplace(uint64_t* a, unsigned log_n) {
     size_t n = (size_t)1 << log_n;
@@ -256,16 +297,25 @@ static inline bool have_avx512();
 static inline void hash_no_pad_x8(const uint64_t* const rows[8], size_t len, Hash out[8]);
 static inline void two_to_one_x8(const Hash* children, Hash* out);
 
+// storage whose elements are NOT zeroed on allocation: the leaves of a large commitment are 10 GB that every element of is written once
+template <class T> struct DefaultInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAlloc<U>; };
+    template <class U, class... A> void construct(U* p, A&&... args) {
+        if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(args)...);
+    }
+};
+using LeafVec = std::vector<uint64_t, DefaultInitAlloc<uint64_t>>;
+
 struct MerkleTree {
     size_t num_leaves = 0, leaf_len = 0;
     unsigned cap_height = 0;
-    std::vector<uint64_t> leaves;                 // row-major num_leaves x leaf_len
+    LeafVec leaves;                               // row-major num_leaves x leaf_len
     std::vector<std::vector<Hash>> levels;        // levels[0] = leaf digests ... last = cap
     const Hash* cap() const { return levels.back().data(); }
     size_t cap_len() const { return levels.back().size(); }
     const uint64_t* leaf(size_t i) const { return &leaves[i * leaf_len]; }
 
-    void build(std::vector<uint64_t>&& rows, size_t n_leaves, size_t len, unsigned cap_h) {
+    void build(LeafVec&& rows, size_t n_leaves, size_t len, unsigned cap_h) {
         leaves = std::move(rows); num_leaves = n_leaves; leaf_len = len; cap_height = cap_h;
         if (((size_t)1 << cap_h) > n_leaves) throw std::runtime_error("cap height too large for tree");
         levels.clear();

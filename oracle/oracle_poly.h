@@ -4,6 +4,7 @@
 // Parity unpinned (no golden vectors in the reference); validated by the restated verifier.
 #pragma once
 #include <algorithm>
+#include <omp.h>
 #include "oracle_core.h"
 
 namespace orc {
@@ -26,26 +27,41 @@ struct PolyBatch {
         if (((size_t)1 << log_n) != n) throw std::runtime_error("n must be a power of two");
         size_t N = lde_size(); unsigned log_N = log_n + rate_bits;
         StageClock* sc_l = new StageClock(" lde + transpose");
-        std::vector<uint64_t> rows(N * ncols);
-        // columns in blocks of 8: the transposed, bit-reversed rows are then written one 64-byte line at a time
+        LeafVec rows(N * ncols);
+        // the coset transform of a column is left in bit-reversed order (fft_dif_bitrev_out): row j of the leaves IS position j of it
+        std::vector<uint64_t> shift_pow(N);
+        { uint64_t w = 1; for (size_t i = 0; i < n; i++) { shift_pow[i] = w; w = gl_mul(w, GL_GENERATOR); } }
+        auto lde_column = [&](size_t c, uint64_t* t, bool par) {
+            const uint64_t* src = &coeffs[c * n];
+            for (size_t i = 0; i < n; i++) t[i] = gl_mul(src[i], shift_pow[i]);
+            memset(t + n, 0, (N - n) * 8);
+            fft_dif_bitrev_out(t, log_N, par);
+        };
         const size_t CB = 8, nblocks = (ncols + CB - 1) / CB;
-        #pragma omp parallel
-        {
-            std::vector<uint64_t> tmp(CB * N);
-            #pragma omp for schedule(dynamic, 1)
-            for (size_t blk = 0; blk < nblocks; blk++) {
-                const size_t c0 = blk * CB, nb = std::min(CB, ncols - c0);
-                for (size_t b = 0; b < nb; b++) {
-                    uint64_t* t = tmp.data() + b * N;
-                    memcpy(t, &coeffs[(c0 + b) * n], n * 8);
-                    memset(t + n, 0, (N - n) * 8);
-                    coset_fft_inplace(t, log_N, GL_GENERATOR);
+        if (nblocks >= (size_t)omp_get_max_threads()) {
+            // wide batches: columns in blocks of 8 per thread; the rows are then written one 64-byte line at a time
+            #pragma omp parallel
+            {
+                std::vector<uint64_t> tmp(CB * N);
+                #pragma omp for schedule(dynamic, 1)
+                for (size_t blk = 0; blk < nblocks; blk++) {
+                    const size_t c0 = blk * CB, nb = std::min(CB, ncols - c0);
+                    for (size_t b = 0; b < nb; b++) lde_column(c0 + b, tmp.data() + b * N, false);
+                    for (size_t j = 0; j < N; j++) {
+                        uint64_t* dst = &rows[j * ncols + c0];
+                        for (size_t b = 0; b < nb; b++) dst[b] = tmp[b * N + j];
+                    }
                 }
-                for (size_t j = 0; j < N; j++) {
-                    const size_t src = bitrev(j, log_N);
-                    uint64_t* dst = &rows[j * ncols + c0];
-                    for (size_t b = 0; b < nb; b++) dst[b] = tmp[b * N + src];
-                }
+            }
+        } else {
+            // tall, narrow batches (Memory, the quotient and auxiliary polynomials): every transform uses all threads, the transposition
+            // is split over the rows
+            std::vector<uint64_t> tmp(ncols * N);
+            for (size_t c = 0; c < ncols; c++) lde_column(c, tmp.data() + c * N, true);
+            #pragma omp parallel for schedule(static)
+            for (size_t j = 0; j < N; j++) {
+                uint64_t* dst = &rows[j * ncols];
+                for (size_t c = 0; c < ncols; c++) dst[c] = tmp[c * N + j];
             }
         }
         delete sc_l;

@@ -568,7 +568,7 @@ static inline StarkProofData prove_table(uint32_t table, const Config& cfg, cons
         for (size_t i = 0; i < M; i++) br[i] = values[bitrev(i, logM)];
         if (first_layer && dbg) dbg->fri_final_values = br;
         first_layer = false;
-        std::vector<uint64_t> rows(2 * M);
+        LeafVec rows(2 * M);
         for (size_t i = 0; i < M; i++) { rows[2 * i] = br[i].a; rows[2 * i + 1] = br[i].b; }
         MerkleTree t;
         t.build(std::move(rows), M / arity, 2 * arity, cfg.cap_height);
