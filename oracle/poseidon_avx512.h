@@ -50,33 +50,68 @@ ORC_AVX512 v8 v8_sbox7(v8 x) {
     v8 x2 = v8_mul(x, x), x4 = v8_mul(x2, x2), x3 = v8_mul(x, x2);
     return v8_mul(x3, x4);
 }
-// MDS layer on the 32-bit halves of the state: every matrix entry is < 2^6, so the 13 products of an output sum to < 2^42 per half
+// MDS layer without multiplications, the way plonky2's own CPU code does it (plonky2 1.0.0 hash/poseidon_goldilocks.rs
+// `mds_multiply_freq`): the circulant part of the matrix is a cyclic convolution of length 12; splitting the index as j = b + 3a and
+// taking a 4-point DFT over a (roots 1, i, -1, -i: additions only) leaves three 3x3 twisted convolutions whose kernels are powers of
+// two for this matrix — DFT(circ)/4 = [16, 32, 16], [-1, -8, 2] and (2 + i, -4 - i, 16 - i) for the complex pair — so the layer is ~90
+// additions and shifts per half.  Done on the 32-bit halves of the state in wrap-around 64-bit lanes (every true output is < 2^42,
+// intermediates may be "negative"), then one 96-bit reduction per output.  Checked against orc::mds_layer through poseidon_x8 == poseidon.
+#define V8ADD(a, b) _mm512_add_epi64(a, b)
+#define V8SUB(a, b) _mm512_sub_epi64(a, b)
+#define V8SHL(a, k) _mm512_slli_epi64(a, k)
+ORC_AVX512 void v8_mds_freq_half(const v8 s[12], v8 o[12]) {
+    v8 F1[3], Fm[3], Fc[3], Fd[3];
+    for (int b = 0; b < 3; b++) {
+        v8 x0 = s[b], x1 = s[b + 3], x2 = s[b + 6], x3 = s[b + 9];
+        v8 A = V8ADD(x0, x2), B = V8ADD(x1, x3);
+        Fc[b] = V8SUB(x0, x2); Fd[b] = V8SUB(x1, x3);
+        F1[b] = V8ADD(A, B); Fm[b] = V8SUB(A, B);
+    }
+    // real block, kernel [16, 32, 16]:  G1_b = 16 (F1_0 + F1_1 + F1_2 + F1_(b+2))
+    v8 T = V8ADD(V8ADD(F1[0], F1[1]), F1[2]);
+    v8 G1[3] = {V8SHL(V8ADD(T, F1[2]), 4), V8SHL(V8ADD(T, F1[0]), 4), V8SHL(V8ADD(T, F1[1]), 4)};
+    // alternating block, kernel [-1, -8, 2] under the twisted (sign-changing) convolution
+    v8 Gm[3] = {V8SUB(V8SUB(V8SHL(Fm[2], 3), V8SHL(Fm[1], 1)), Fm[0]),
+                V8SUB(V8SUB(V8SUB(_mm512_setzero_si512(), V8SHL(Fm[0], 3)), V8SHL(Fm[2], 1)), Fm[1]),
+                V8SUB(V8SUB(V8SHL(Fm[0], 1), V8SHL(Fm[1], 3)), Fm[2])};
+    // complex block, kernel k0 = 2 + i, k1 = -4 - i, k2 = 16 - i:  (c + d i) k0 = (2c - d) + (2d + c) i,  k1: (-4c + d) + (-4d - c) i,
+    // k2: (16c + d) + (16d - c) i;   Gi_0 = k0 F0 + i (k1 F2 + k2 F1),  Gi_1 = k0 F1 + k1 F0 + i k2 F2,  Gi_2 = k0 F2 + k1 F1 + k2 F0
+    v8 u[3], v[3];
+    {
+        v8 re = V8ADD(V8ADD(V8SUB(V8SHL(Fc[1], 4), V8SHL(Fc[2], 2)), Fd[2]), Fd[1]);
+        v8 im = V8SUB(V8SUB(V8SUB(V8SHL(Fd[1], 4), V8SHL(Fd[2], 2)), Fc[2]), Fc[1]);
+        u[0] = V8SUB(V8SUB(V8SHL(Fc[0], 1), Fd[0]), im);
+        v[0] = V8ADD(V8ADD(V8SHL(Fd[0], 1), Fc[0]), re);
+    }
+    u[1] = V8ADD(V8SUB(V8ADD(V8SUB(V8SUB(V8SHL(Fc[1], 1), Fd[1]), V8SHL(Fc[0], 2)), Fd[0]), V8SHL(Fd[2], 4)), Fc[2]);
+    v[1] = V8ADD(V8ADD(V8SUB(V8SUB(V8ADD(V8SHL(Fd[1], 1), Fc[1]), V8SHL(Fd[0], 2)), Fc[0]), V8SHL(Fc[2], 4)), Fd[2]);
+    u[2] = V8ADD(V8ADD(V8ADD(V8SUB(V8SUB(V8SHL(Fc[2], 1), Fd[2]), V8SHL(Fc[1], 2)), Fd[1]), V8SHL(Fc[0], 4)), Fd[0]);
+    v[2] = V8SUB(V8ADD(V8SUB(V8SUB(V8ADD(V8SHL(Fd[2], 1), Fc[2]), V8SHL(Fd[1], 2)), Fc[1]), V8SHL(Fd[0], 4)), Fc[0]);
+    for (int b = 0; b < 3; b++) {
+        v8 Pp = V8ADD(G1[b], Gm[b]), Q = V8SUB(G1[b], Gm[b]);
+        o[b] = V8ADD(Pp, u[b]); o[b + 3] = V8ADD(Q, v[b]); o[b + 6] = V8SUB(Pp, u[b]); o[b + 9] = V8SUB(Q, v[b]);
+    }
+    o[0] = V8ADD(o[0], V8SHL(s[0], 3));          // + diag(8, 0, ..., 0)
+}
 ORC_AVX512 void v8_mds(v8 s[12]) {
     const v8 eps = v8_set1(EPS);
-    v8 lo[12], hi[12], out[12];
+    v8 lo[12], hi[12], ol[12], oh[12];
     for (int i = 0; i < 12; i++) { lo[i] = _mm512_and_si512(s[i], eps); hi[i] = _mm512_srli_epi64(s[i], 32); }
+    v8_mds_freq_half(lo, ol);
+    v8_mds_freq_half(hi, oh);
     for (int r = 0; r < 12; r++) {
-        v8 al = _mm512_setzero_si512(), ah = _mm512_setzero_si512();
-        for (int i = 0; i < 12; i++) {
-            const v8 c = v8_set1(MDS_CIRC[i]);
-            al = _mm512_add_epi64(al, _mm512_mul_epu32(lo[(i + r) % 12], c));
-            ah = _mm512_add_epi64(ah, _mm512_mul_epu32(hi[(i + r) % 12], c));
-        }
-        if (r == 0) {
-            const v8 d = v8_set1(ZK_POSEIDON_MDS_DIAG0);
-            al = _mm512_add_epi64(al, _mm512_mul_epu32(lo[0], d));
-            ah = _mm512_add_epi64(ah, _mm512_mul_epu32(hi[0], d));
-        }
-        // al + 2^32 ah as a 96-bit number: low word and the carries above it
-        v8 sh = _mm512_slli_epi64(ah, 32);
-        v8 low = _mm512_add_epi64(al, sh);
+        // ol + 2^32 oh as a 96-bit number: low word and the carries above it
+        v8 sh = _mm512_slli_epi64(oh[r], 32);
+        v8 low = _mm512_add_epi64(ol[r], sh);
         __mmask8 c = _mm512_cmplt_epu64_mask(low, sh);
-        v8 top = _mm512_srli_epi64(ah, 32);
+        v8 top = _mm512_srli_epi64(oh[r], 32);
         top = _mm512_mask_add_epi64(top, c, top, v8_set1(1));
-        out[r] = v8_reduce128(low, top);
+        s[r] = v8_reduce128(low, top);
     }
-    for (int r = 0; r < 12; r++) s[r] = out[r];
 }
+#undef V8ADD
+#undef V8SUB
+#undef V8SHL
 // st[lane of the state][permutation]: eight independent permutations
 __attribute__((target("avx512f,avx512dq"))) static inline void poseidon_x8(uint64_t st[12][8]) {
     v8 s[12];
